@@ -1,0 +1,137 @@
+/*
+ * superintervals_b200.h -- ADDITIVE entry points of libsuperintervals_b200.so.
+ *
+ * The reference C ABI (c_superintervals.h) is one-query-per-call and has no
+ * error channel. This header adds, without touching any reference signature:
+ *   1. a sticky error side channel for CUDA failures;
+ *   2. batch queries over HOST buffers, shaped after the only batch API the
+ *      reference defines -- the Python methods count_batch / search_idxs_batch /
+ *      search_values_batch (reference src/superintervals/intervalmap.pyx:363-494),
+ *      with their ragged list-of-lists flattened to CSR (offsets[n+1] + flat data);
+ *   3. a device-resident core (opaque siIndex) taking raw DEVICE pointers and a
+ *      stream, for callers that already hold queries in HBM and for multi-GPU
+ *      sharding. No torch / CUDA types appear in any signature: streams travel as
+ *      void* (a cudaStream_t), device arrays as plain pointers.
+ *
+ * All functions returning int return 0 on success or a cudaError_t value (also
+ * latched into the side channel).
+ */
+#ifndef SUPERINTERVALS_B200_H_INCLUDED
+#define SUPERINTERVALS_B200_H_INCLUDED 1
+
+#include "c_superintervals.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SUPERINTERVALS_B200_VERSION "0.1.0"
+
+/* ---- 1. error side channel (SURVEY 8b "Error convention") ------------------------ */
+int         si_b200_last_error(void);          /* 0 = no error since the last clear */
+const char* si_b200_last_error_string(void);   /* static buffer, "" when no error */
+void        si_b200_clear_error(void);
+const char* si_b200_version(void);
+int         si_b200_device_count(void);        /* visible CUDA devices, <0 on error */
+
+/* ---- 2. batch queries over host buffers ------------------------------------------- */
+/* Bulk add: n x addInterval (ref c_superintervals.h:402-419) in one call, same
+ * startSorted/endSorted bookkeeping. values == NULL stores the insertion index
+ * (what reference test/bench.cpp:210 passes). Shaped after from_arrays (pyx:63-131). */
+void addIntervals(cSuperIntervals* si, const int32_t* starts, const int32_t* ends,
+                  const int32_t* values, size_t n);
+
+/* When false, indexSuperIntervals() leaves si->starts/ends/data/branch untouched
+ * (insertion order, branch NULL) and skips the device->host mirror copy; only
+ * the *Batch calls remain meaningful for element access. Default: true. */
+void siSetHostMirror(cSuperIntervals* si, bool enabled);
+
+/* count_batch (pyx:363-400): counts_out[i] = countOverlaps(si, starts[i], ends[i]). */
+void countOverlapsBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n,
+                        size_t* counts_out);
+/* out[i] = anyOverlaps(si, starts[i], ends[i]) -- same last-candidate-only test. */
+void anyOverlapsBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n,
+                      bool* out);
+/* search_values_batch (pyx:448-494) as CSR. offsets_out has n+1 entries and is
+ * relative to the values APPENDED by this call: query i's results are
+ * found->data[size_before + offsets_out[i] .. size_before + offsets_out[i+1]),
+ * each list in the reference's descending order. found grows by realloc. */
+void searchValuesBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n,
+                       size_t* offsets_out, cIndexResult* found);
+/* search_idxs_batch (pyx:402-446) as CSR; all-descending order as the reference C
+ * ABI's searchIdxs (c_superintervals.h:610-643). */
+void searchIdxsBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n,
+                     size_t* offsets_out, cIndexResult* found);
+void searchKeysBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n,
+                     size_t* offsets_out, cKeyResult* found);
+void searchItemsBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n,
+                      size_t* offsets_out, cItemResult* found);
+/* coverage (c_superintervals.h:758-792) per query. */
+void coverageBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n,
+                   size_t* count_out, int32_t* coverage_out);
+
+/* ---- 3. device-resident core ------------------------------------------------------- */
+typedef struct siIndex siIndex;
+
+typedef struct {
+    const int32_t*  starts;   /* device, position order (start asc, end desc) */
+    const int32_t*  ends;     /* device, padded to a multiple of 128 entries */
+    const int32_t*  values;   /* device */
+    const uint32_t* branch;   /* device, 0xFFFFFFFF = none */
+    size_t          n;
+    int             device;
+} siDeviceView;
+
+/* how the query arrays are ordered; results are always returned in the caller's order */
+enum {
+    SI_ORDER_AUTO = 0,       /* check on device (one small host sync), sort if needed */
+    SI_ORDER_SORTED = 1,     /* caller guarantees ends are non-decreasing */
+    SI_ORDER_UNSORTED = 2,   /* radix-sort the batch by end on device, scatter results back */
+    SI_ORDER_ASIS = 3        /* process in the given order whatever it is */
+};
+enum { SI_FILL_VALUES = 0, SI_FILL_IDXS = 1, SI_FILL_KEYS = 2, SI_FILL_ITEMS = 3 };
+
+siIndex* siIndexCreate(void);            /* on the calling thread's current CUDA device */
+void     siIndexDestroy(siIndex* ix);
+siIndex* siIndexOf(cSuperIntervals* si); /* the device index behind a handle (NULL before indexing) */
+size_t   siIndexSize(const siIndex* ix);
+int      siIndexDeviceView(const siIndex* ix, siDeviceView* out);
+
+/* build(): radix sort by (start asc, end desc, insertion order) + parallel branch pass.
+ * values may be NULL (payload = insertion index). Inputs are not modified. */
+int siIndexBuildHost(siIndex* ix, const int32_t* starts, const int32_t* ends, const int32_t* values, size_t n);
+int siIndexBuildDevice(siIndex* ix, const int32_t* d_starts, const int32_t* d_ends,
+                       const int32_t* d_values, size_t n, void* stream);
+/* copy the built index to host; any pointer may be NULL. branch is widened to
+ * size_t with SI_NONE; perm[i] = insertion index of the interval at position i. */
+int siIndexExport(const siIndex* ix, int32_t* starts, int32_t* ends, int32_t* values,
+                  size_t* branch, uint32_t* perm);
+
+/* d_counts[i] = number of stored intervals overlapping [d_qs[i], d_qe[i]]. */
+int siCountDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n,
+                  uint32_t* d_counts, int order, void* stream);
+int siCountDevice64(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n,
+                    uint64_t* d_counts, int order, void* stream);
+int siAnyDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n,
+                uint8_t* d_out, void* stream);
+/* d_offsets[0..n]: exclusive scan of d_counts, d_offsets[n] = total hits. 16-byte aligned pointers. */
+int siScanDevice(siIndex* ix, const uint32_t* d_counts, size_t n, uint64_t* d_offsets, void* stream);
+/* CSR fill: for query i writes its hits to d_out[d_offsets[i] .. d_offsets[i+1]) in
+ * descending position order. what = SI_FILL_*: int32 values, uint32 positions,
+ * KeyPair, or Interval records. With SI_ORDER_UNSORTED the sort done by the
+ * preceding siCountDevice call on the same (d_qe, n) is reused. */
+int siFillDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n,
+                 const uint64_t* d_offsets, int what, void* d_out, int order, void* stream);
+/* count + clipped-length sum per query (c_superintervals.h:758-792). */
+int siCoverageDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n,
+                     uint32_t* d_counts, int32_t* d_cov, void* stream);
+
+/* bytes of device memory currently held by the index + its workspaces */
+size_t siIndexDeviceBytes(const siIndex* ix);
+/* kernels launched by this library since process start (bench.py's gpu_launches) */
+unsigned long long si_b200_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUPERINTERVALS_B200_H_INCLUDED */

@@ -1,0 +1,214 @@
+// build_kernels.cuh -- device-side build() for the superset index (sm_100a).
+//
+//   reference build()  = sort_intervals() (superintervals.hpp:1396-1439)
+//                      + sequential monotonic-stack branch loop (hpp:117-129)
+//   here               = key packing -> radix_sort.cuh -> gather
+//                      + a parallel "all nearest previous end >= mine" (ANSV) pass:
+//                        in-warp resolution by shuffles, a prefix-max early-out for
+//                        roots, and a 32-ary max-tree descent for the far tail.
+#pragma once
+
+#include "common.cuh"
+#include <limits.h>
+
+namespace sib {
+
+constexpr int BK_THREADS = 256;
+
+// ---- sortedness, as add() tracks it (hpp:96-101) ------------------------------------
+// flags bit0 = start_sorted, bit1 = end_sorted; caller initialises *flags = 3.
+__global__ void __launch_bounds__(BK_THREADS)
+bk_check_sorted_kernel(const int32_t* __restrict__ s, const int32_t* __restrict__ e, uint32_t n,
+                       uint32_t* __restrict__ flags) {
+    uint32_t bad = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x + 1; i < n; i += stride) {
+        int32_t s0 = s[i - 1], s1 = s[i];
+        if (s1 < s0) bad |= 1u;
+        else if (s1 == s0 && e[i] > e[i - 1]) bad |= 2u;
+    }
+    bad = __reduce_or_sync(FULL_MASK, bad);
+    if (lane_id() == 0 && bad) atomicAnd(flags, ~bad);
+}
+
+// ---- key packing: (start asc, end DESC, insertion idx) ------------------------------
+__global__ void __launch_bounds__(BK_THREADS)
+bk_make_keys_kernel(const int32_t* __restrict__ s, const int32_t* __restrict__ e, uint32_t n,
+                    uint64_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+    const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i < n; i += stride) {
+        uint32_t hs = flip_i32(s[i]);
+        uint32_t he = ~flip_i32(e[i]);   // complement -> descending end under an ascending sort
+        keys[i] = ((uint64_t)hs << 32) | he;
+        idx[i] = (uint32_t)i;
+    }
+}
+
+// ---- gather: sorted keys carry start and end; only the payload needs the permutation -
+__global__ void __launch_bounds__(BK_THREADS)
+bk_gather_kernel(const uint64_t* __restrict__ kA, const uint64_t* __restrict__ kB,
+                 const uint32_t* __restrict__ vA, const uint32_t* __restrict__ vB,
+                 const uint32_t* __restrict__ final_sel, const int32_t* __restrict__ values_in,
+                 uint32_t n, int32_t* __restrict__ starts, int32_t* __restrict__ ends,
+                 int32_t* __restrict__ values, uint32_t* __restrict__ perm) {
+    const bool useB = *final_sel != 0;
+    const uint64_t* __restrict__ keys = useB ? kB : kA;
+    const uint32_t* __restrict__ idx = useB ? vB : vA;
+    const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i < n; i += stride) {
+        uint64_t k = keys[i];
+        uint32_t j = idx[i];
+        starts[i] = unflip_i32((uint32_t)(k >> 32));
+        ends[i] = unflip_i32(~(uint32_t)k);
+        values[i] = values_in ? values_in[j] : (int32_t)j;
+        perm[i] = j;
+    }
+}
+
+// already (start asc, end desc): the reference performs no sort (hpp:1416,1421)
+__global__ void __launch_bounds__(BK_THREADS)
+bk_identity_kernel(const int32_t* __restrict__ s, const int32_t* __restrict__ e,
+                   const int32_t* __restrict__ values_in, uint32_t n, int32_t* __restrict__ starts,
+                   int32_t* __restrict__ ends, int32_t* __restrict__ values, uint32_t* __restrict__ perm) {
+    const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i < n; i += stride) {
+        starts[i] = s[i];
+        ends[i] = e[i];
+        values[i] = values_in ? values_in[i] : (int32_t)i;
+        perm[i] = (uint32_t)i;
+    }
+}
+
+// pad tail [n, n_padded) so 128-bit loads past the end read harmless data
+__global__ void bk_pad_kernel(int32_t* __restrict__ starts, int32_t* __restrict__ ends,
+                              uint32_t* __restrict__ branch, uint32_t n, uint32_t n_padded) {
+    uint32_t i = n + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_padded) {
+        starts[i] = INT_MAX;
+        ends[i] = INT_MIN;
+        branch[i] = NONE32;
+    }
+}
+
+// ---- 32-ary max tree over ends -------------------------------------------------------
+// level 0 = ends; level L entry k = max of level L-1 entries [32k, 32k+32).
+// One launch produces two levels: a CTA of 1024 threads folds 1024 inputs into
+// 32 level-(L+1) entries and 1 level-(L+2) entry.
+__global__ void __launch_bounds__(1024)
+bk_max2_kernel(const int32_t* __restrict__ in, uint32_t n_in, int32_t* __restrict__ out1,
+               int32_t* __restrict__ out2) {
+    __shared__ int32_t s_m[32];
+    const uint64_t i = (uint64_t)blockIdx.x * 1024u + threadIdx.x;
+    int32_t v = i < n_in ? in[i] : INT_MIN;
+    v = __reduce_max_sync(FULL_MASK, v);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if (lane == 0) {
+        s_m[warp] = v;
+        uint64_t o = (uint64_t)blockIdx.x * 32u + warp;
+        if (o * 32u < n_in) out1[o] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int32_t m = __reduce_max_sync(FULL_MASK, s_m[lane]);
+        if (lane == 0) out2[blockIdx.x] = m;
+    }
+}
+
+// Exclusive prefix max per entry of one level, top-down:
+//   P_L[k] = max(P_{L+1}[k/32], max of M_L over the left siblings of k)
+// parentP == nullptr at the top level (a single group).
+__global__ void __launch_bounds__(BK_THREADS)
+bk_prefix_level_kernel(const int32_t* __restrict__ M, uint32_t n_level,
+                       const int32_t* __restrict__ parentP, int32_t* __restrict__ P) {
+    const uint64_t k = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x;
+    const uint32_t lane = lane_id();
+    int32_t m = k < n_level ? M[k] : INT_MIN;
+    int32_t incl = m;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int32_t t = __shfl_up_sync(FULL_MASK, incl, off);
+        if (lane >= (uint32_t)off) incl = max(incl, t);
+    }
+    int32_t excl = __shfl_up_sync(FULL_MASK, incl, 1);
+    if (lane == 0) excl = INT_MIN;
+    if (k < n_level) {
+        int32_t up = parentP ? parentP[k >> 5] : INT_MIN;
+        P[k] = max(up, excl);
+    }
+}
+
+constexpr int BK_MAX_LEVELS = 7;   // 32^7 > 2^32
+struct MaxTree {
+    const int32_t* M[BK_MAX_LEVELS + 1];   // M[0] = ends
+    uint32_t n[BK_MAX_LEVELS + 1];
+    const int32_t* P1;                     // exclusive prefix max per 32-block of ends
+    int top;                               // highest level with n[top] >= 1
+};
+
+// ---- branch[i] = nearest j < i with ends[j] >= ends[i], else NONE (hpp:117-129) -------
+// One warp per 32 consecutive intervals.
+__global__ void __launch_bounds__(BK_THREADS)
+bk_branch_kernel(MaxTree t, uint32_t n, uint32_t* __restrict__ branch) {
+    const uint32_t lane = lane_id();
+    const uint64_t warps_total = (uint64_t)gridDim.x * (BK_THREADS / 32);
+    const uint32_t nblocks = t.n[1];
+    for (uint64_t b = (uint64_t)blockIdx.x * (BK_THREADS / 32) + (threadIdx.x >> 5); b < nblocks; b += warps_total) {
+        const uint64_t i = b * 32u + lane;
+        const bool live = i < n;
+        const int32_t e = live ? t.M[0][i] : INT_MIN;
+
+        // exclusive prefix max inside the block: lanes above it have no in-block answer
+        int32_t incl = e;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int32_t v = __shfl_up_sync(FULL_MASK, incl, off);
+            if (lane >= (uint32_t)off) incl = max(incl, v);
+        }
+        int32_t pm = __shfl_up_sync(FULL_MASK, incl, 1);
+        const bool in_block = live && lane > 0 && pm >= e;
+
+        uint32_t res = NONE32;
+        bool found = !in_block;
+        // nearest previous lane with end >= mine; distances are short on real data
+        for (int k = 1; k < 32; ++k) {
+            if (__all_sync(FULL_MASK, found)) break;
+            int32_t v = __shfl_up_sync(FULL_MASK, e, k);
+            if (!found && lane >= (uint32_t)k && v >= e) {
+                found = true;
+                res = (uint32_t)(i - k);
+            }
+        }
+
+        if (live && !in_block && b > 0 && e <= t.P1[b]) {
+            // some earlier interval reaches at least as far: climb the max tree
+            int level = 1;
+            uint64_t k = b;
+            int64_t hit = -1;
+            while (true) {
+                const uint64_t g0 = k & ~(uint64_t)31;
+                for (int64_t kk = (int64_t)k - 1; kk >= (int64_t)g0; --kk) {
+                    if (ld_nc(t.M[level] + kk) >= e) { hit = kk; break; }
+                }
+                if (hit >= 0 || g0 == 0 || level == t.top) break;
+                k >>= 5;
+                ++level;
+            }
+            if (hit >= 0) {
+                while (level > 0) {
+                    const uint64_t lo = (uint64_t)hit * 32u;
+                    uint64_t c = lo + 31u;
+                    const uint64_t last = (uint64_t)t.n[level - 1] - 1;
+                    if (c > last) c = last;
+                    // the subtree max is >= e, so a child >= e exists: take the last one
+                    while (c > lo && ld_nc(t.M[level - 1] + c) < e) --c;
+                    hit = (int64_t)c;
+                    --level;
+                }
+                res = (uint32_t)hit;
+            }
+        }
+        if (live) branch[i] = res;
+    }
+}
+
+}  // namespace sib

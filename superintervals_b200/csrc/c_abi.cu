@@ -1,0 +1,367 @@
+// c_abi.cu -- the reference's C ABI (include/c_superintervals.h) and the host-buffer
+// batch entry points (include/superintervals_b200.h section 2), implemented on top
+// of the device-resident core in index.cu. Host code only: no kernels here.
+//
+// Ownership follows the reference (c_superintervals.h:363-400): the handle and its
+// arrays are malloc'd by the library; result buffers are caller structs whose
+// `data` the library reallocs. The handle is over-allocated: callers see the
+// public cSuperIntervals prefix, the library keeps the device index behind it.
+#include "../../include/superintervals_b200.h"
+
+#include "common.cuh"
+#include "index.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+extern "C" int si_b200_upper_bound_(siIndex* ix, int32_t value, size_t* out);
+extern "C" int si_b200_resolve_order_(siIndex* ix, const int32_t* d_qe, size_t n, void* stream);
+
+namespace {
+
+constexpr uint64_t HANDLE_MAGIC = 0x53495F4232303021ull;   // "SI_B200!"
+
+struct Handle {
+    cSuperIntervals pub;   // must stay first: &handle->pub is what callers hold
+    uint64_t magic;
+    siIndex* ix;
+    bool mirror;
+    bool indexed;
+};
+
+inline Handle* H(cSuperIntervals* si) { return reinterpret_cast<Handle*>(si); }
+
+bool ready(Handle* h, const char* who) {
+    if (h && h->magic == HANDLE_MAGIC && h->indexed && h->ix) return true;
+    char msg[160];
+    snprintf(msg, sizeof(msg), "%s: handle not indexed (call indexSuperIntervals first)", who);
+    sib::set_error_msg(cudaErrorNotReady, msg);
+    return false;
+}
+
+template <typename R>
+bool grow(R* r, size_t need_total, size_t elem) {
+    if (need_total <= r->capacity) return true;
+    size_t cap = r->capacity ? r->capacity : 16;   // reference growth: x2 from 16 (c.h:585-588)
+    while (cap < need_total) cap *= 2;
+    void* p = realloc(r->data, cap * elem);
+    if (!p) { sib::set_error_msg(cudaErrorMemoryAllocation, "realloc of result buffer failed"); return false; }
+    r->data = reinterpret_cast<decltype(r->data)>(p);
+    r->capacity = cap;
+    return true;
+}
+
+// upload a query batch into the index's staging buffers
+int stage_queries(siIndex* ix, const int32_t* qs, const int32_t* qe, size_t n) {
+    if (ix->h_qs.ensure(n * 4) || ix->h_qe.ensure(n * 4)) return sib::last_error_code();
+    SIB_CHECK(cudaMemcpyAsync(ix->h_qs.p, qs, n * 4, cudaMemcpyHostToDevice, ix->own_stream));
+    SIB_CHECK(cudaMemcpyAsync(ix->h_qe.p, qe, n * 4, cudaMemcpyHostToDevice, ix->own_stream));
+    return 0;
+}
+
+// count -> scan -> (host learns total) -> grow -> fill -> copy back, appended to `found`
+template <typename R>
+int search_batch(Handle* h, const int32_t* qs, const int32_t* qe, size_t n, size_t* offsets_out, R* found,
+                 int what, size_t elem) {
+    siIndex* ix = h->ix;
+    if (n == 0) { if (offsets_out) offsets_out[0] = 0; return 0; }
+    int rc = stage_queries(ix, qs, qe, n);
+    if (rc) return rc;
+    if (ix->h_counts.ensure(n * 4 + 64) || ix->h_offsets.ensure((n + 1) * 8 + 64)) return sib::last_error_code();
+    const int32_t* dqs = ix->h_qs.as<int32_t>();
+    const int32_t* dqe = ix->h_qe.as<int32_t>();
+    // resolve the query order once so that count and fill agree and share one sort
+    const int order = si_b200_resolve_order_(ix, dqe, n, ix->own_stream);
+    if (order < 0) return sib::last_error_code();
+    rc = siCountDevice(ix, dqs, dqe, n, ix->h_counts.as<uint32_t>(), order, ix->own_stream);
+    if (rc) return rc;
+    rc = siScanDevice(ix, ix->h_counts.as<uint32_t>(), n, ix->h_offsets.as<uint64_t>(), ix->own_stream);
+    if (rc) return rc;
+    static_assert(sizeof(size_t) == sizeof(uint64_t), "LP64 only");
+    uint64_t total = 0;
+    if (offsets_out) {
+        SIB_CHECK(cudaMemcpyAsync(offsets_out, ix->h_offsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ix->own_stream));
+    }
+    SIB_CHECK(cudaMemcpyAsync(&total, ix->h_offsets.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, ix->own_stream));
+    SIB_CHECK(cudaStreamSynchronize(ix->own_stream));
+    if (total == 0) return 0;
+    if (!grow(found, found->size + total, elem)) return cudaErrorMemoryAllocation;
+    if (ix->h_out.ensure(total * elem)) return sib::last_error_code();
+    rc = siFillDevice(ix, dqs, dqe, n, ix->h_offsets.as<uint64_t>(), what, ix->h_out.p, order, ix->own_stream);
+    if (rc) return rc;
+    SIB_CHECK(cudaMemcpyAsync(reinterpret_cast<char*>(found->data) + found->size * elem, ix->h_out.p, total * elem,
+                              cudaMemcpyDeviceToHost, ix->own_stream));
+    SIB_CHECK(cudaStreamSynchronize(ix->own_stream));
+    found->size += total;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- lifecycle (ref c_superintervals.h:363-423) ---------------------------------------
+cSuperIntervals* createSuperIntervals(void) {
+    Handle* h = (Handle*)calloc(1, sizeof(Handle));
+    if (!h) return nullptr;
+    h->pub.startSorted = true;
+    h->pub.endSorted = true;
+    h->magic = HANDLE_MAGIC;
+    h->mirror = true;
+    return &h->pub;
+}
+
+void destroySuperIntervals(cSuperIntervals* si) {
+    if (!si) return;   // ref:378
+    Handle* h = H(si);
+    free(si->starts);
+    free(si->ends);
+    free(si->data);
+    free(si->branch);
+    if (h->magic == HANDLE_MAGIC && h->ix) siIndexDestroy(h->ix);
+    h->magic = 0;
+    free(h);
+}
+
+void clearSuperIntervals(cSuperIntervals* si) {   // keeps capacity, ref:386-391
+    si->size = 0;
+    si->idx = 0;
+    si->startSorted = true;
+    si->endSorted = true;
+    H(si)->indexed = false;
+}
+
+void reserveSuperIntervals(cSuperIntervals* si, size_t n) {
+    if (n <= si->capacity) return;
+    si->capacity = n;
+    si->starts = (int32_t*)realloc(si->starts, n * sizeof(int32_t));
+    si->ends = (int32_t*)realloc(si->ends, n * sizeof(int32_t));
+    si->data = (int32_t*)realloc(si->data, n * sizeof(int32_t));
+}
+
+void addInterval(cSuperIntervals* si, int32_t start, int32_t end, int32_t value) {
+    if (si->size >= si->capacity) reserveSuperIntervals(si, si->capacity ? si->capacity * 2 : 1);
+    // sortedness bookkeeping exactly as ref:408-413
+    if (si->startSorted && si->size > 0) {
+        const int32_t ps = si->starts[si->size - 1];
+        if (start < ps) si->startSorted = false;
+        else if (start == ps && end > si->ends[si->size - 1]) si->endSorted = false;
+    }
+    si->starts[si->size] = start;
+    si->ends[si->size] = end;
+    si->data[si->size] = value;
+    si->size++;
+}
+
+void addIntervals(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, const int32_t* values, size_t n) {
+    if (n == 0) return;
+    if (si->size + n > si->capacity) {
+        size_t cap = si->capacity ? si->capacity : 1;
+        while (cap < si->size + n) cap *= 2;
+        reserveSuperIntervals(si, cap);
+    }
+    size_t at = si->size;
+    for (size_t i = 0; i < n; ++i, ++at) {
+        if (si->startSorted && at > 0) {
+            const int32_t ps = si->starts[at - 1];
+            if (starts[i] < ps) si->startSorted = false;
+            else if (starts[i] == ps && ends[i] > si->ends[at - 1]) si->endSorted = false;
+        }
+        si->starts[at] = starts[i];
+        si->ends[at] = ends[i];
+        si->data[at] = values ? values[i] : (int32_t)at;
+    }
+    si->size = at;
+}
+
+size_t sizeSuperIntervals(const cSuperIntervals* si) { return si->size; }
+
+void siSetHostMirror(cSuperIntervals* si, bool enabled) { H(si)->mirror = enabled; }
+siIndex* siIndexOf(cSuperIntervals* si) {
+    Handle* h = H(si);
+    return (h && h->magic == HANDLE_MAGIC && h->indexed) ? h->ix : nullptr;
+}
+
+// ---- indexing (ref:462-521) ---------------------------------------------------------------
+static int build_from_handle(Handle* h) {
+    cSuperIntervals* si = &h->pub;
+    if (!h->ix) {
+        h->ix = siIndexCreate();
+        if (!h->ix) return sib::last_error_code();
+    }
+    return siIndexBuildHost(h->ix, si->starts, si->ends, si->data, si->size);
+}
+
+void sortIntervals(cSuperIntervals* si) {
+    Handle* h = H(si);
+    if (si->size == 0) return;
+    if (si->startSorted && si->endSorted) return;   // ref:463-484: nothing to do
+    if (build_from_handle(h)) return;
+    if (siIndexExport(h->ix, si->starts, si->ends, si->data, nullptr, nullptr)) return;
+    si->startSorted = true;
+    si->endSorted = true;
+}
+
+void indexSuperIntervals(cSuperIntervals* si) {
+    Handle* h = H(si);
+    if (si->size == 0) return;   // ref:488-490
+    h->indexed = false;
+    if (build_from_handle(h)) return;
+    if (h->mirror) {
+        size_t* b = (size_t*)realloc(si->branch, si->size * sizeof(size_t));
+        if (!b) { sib::set_error_msg(cudaErrorMemoryAllocation, "realloc(branch) failed"); return; }
+        si->branch = b;
+        if (siIndexExport(h->ix, si->starts, si->ends, si->data, si->branch, nullptr)) return;
+        si->startSorted = true;
+        si->endSorted = true;
+    }
+    si->idx = 0;
+    h->indexed = true;
+}
+
+// ---- element access (ref:523-535): host mirrors ------------------------------------------
+bool intervalAt(const cSuperIntervals* si, size_t index, Interval* out) {
+    if (index >= si->size) return false;
+    out->start = si->starts[index];
+    out->end = si->ends[index];
+    out->data = si->data[index];
+    return true;
+}
+int32_t startAt(const cSuperIntervals* si, size_t index) { return si->starts[index]; }
+int32_t endAt(const cSuperIntervals* si, size_t index) { return si->ends[index]; }
+int32_t dataAt(const cSuperIntervals* si, size_t index) { return si->data[index]; }
+
+// ---- batch queries over host buffers ---------------------------------------------------------
+void countOverlapsBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n,
+                        size_t* counts_out) {
+    Handle* h = H(si);
+    if (n == 0) return;
+    if (si->size == 0) { memset(counts_out, 0, n * sizeof(size_t)); return; }   // ref:730-732
+    if (!ready(h, "countOverlapsBatch")) { memset(counts_out, 0, n * sizeof(size_t)); return; }
+    siIndex* ix = h->ix;
+    if (stage_queries(ix, starts, ends, n) || ix->h_counts.ensure(n * 8)) return;
+    if (siCountDevice64(ix, ix->h_qs.as<int32_t>(), ix->h_qe.as<int32_t>(), n, ix->h_counts.as<uint64_t>(),
+                        SI_ORDER_AUTO, ix->own_stream))
+        return;
+    if (cudaMemcpyAsync(counts_out, ix->h_counts.p, n * 8, cudaMemcpyDeviceToHost, ix->own_stream) != cudaSuccess ||
+        cudaStreamSynchronize(ix->own_stream) != cudaSuccess)
+        sib::set_error(cudaGetLastError(), "countOverlapsBatch copy-back", __FILE__, __LINE__);
+}
+
+void anyOverlapsBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n, bool* out) {
+    Handle* h = H(si);
+    if (n == 0) return;
+    if (si->size == 0) { memset(out, 0, n); return; }
+    if (!ready(h, "anyOverlapsBatch")) { memset(out, 0, n); return; }
+    siIndex* ix = h->ix;
+    if (stage_queries(ix, starts, ends, n) || ix->h_counts.ensure(n)) return;
+    if (siAnyDevice(ix, ix->h_qs.as<int32_t>(), ix->h_qe.as<int32_t>(), n, ix->h_counts.as<uint8_t>(), ix->own_stream))
+        return;
+    static_assert(sizeof(bool) == 1, "bool must be one byte");
+    if (cudaMemcpyAsync(out, ix->h_counts.p, n, cudaMemcpyDeviceToHost, ix->own_stream) != cudaSuccess ||
+        cudaStreamSynchronize(ix->own_stream) != cudaSuccess)
+        sib::set_error(cudaGetLastError(), "anyOverlapsBatch copy-back", __FILE__, __LINE__);
+}
+
+#define SIB_SEARCH_BATCH(NAME, RTYPE, WHAT, ELEM)                                                         \
+    void NAME(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n, size_t* offsets_out, \
+              RTYPE* found) {                                                                             \
+        Handle* h = H(si);                                                                                \
+        if (si->size == 0 || !ready(h, #NAME)) {                                                          \
+            if (offsets_out) memset(offsets_out, 0, (n + 1) * sizeof(size_t));                            \
+            return;                                                                                       \
+        }                                                                                                 \
+        search_batch(h, starts, ends, n, offsets_out, found, WHAT, ELEM);                                 \
+    }
+SIB_SEARCH_BATCH(searchValuesBatch, cIndexResult, SI_FILL_VALUES, sizeof(int32_t))
+SIB_SEARCH_BATCH(searchIdxsBatch, cIndexResult, SI_FILL_IDXS, sizeof(int32_t))
+SIB_SEARCH_BATCH(searchKeysBatch, cKeyResult, SI_FILL_KEYS, sizeof(KeyPair))
+SIB_SEARCH_BATCH(searchItemsBatch, cItemResult, SI_FILL_ITEMS, sizeof(Interval))
+#undef SIB_SEARCH_BATCH
+
+void coverageBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n, size_t* count_out,
+                   int32_t* coverage_out) {
+    Handle* h = H(si);
+    if (n == 0) return;
+    if (si->size == 0 || !ready(h, "coverageBatch")) {
+        memset(count_out, 0, n * sizeof(size_t));
+        memset(coverage_out, 0, n * sizeof(int32_t));
+        return;
+    }
+    siIndex* ix = h->ix;
+    if (stage_queries(ix, starts, ends, n) || ix->h_counts.ensure(n * 4) || ix->h_cov.ensure(n * 4)) return;
+    if (siCoverageDevice(ix, ix->h_qs.as<int32_t>(), ix->h_qe.as<int32_t>(), n, ix->h_counts.as<uint32_t>(),
+                         ix->h_cov.as<int32_t>(), ix->own_stream))
+        return;
+    uint32_t* tmp = (uint32_t*)malloc(n * 4);
+    if (cudaMemcpyAsync(tmp, ix->h_counts.p, n * 4, cudaMemcpyDeviceToHost, ix->own_stream) != cudaSuccess ||
+        cudaMemcpyAsync(coverage_out, ix->h_cov.p, n * 4, cudaMemcpyDeviceToHost, ix->own_stream) != cudaSuccess ||
+        cudaStreamSynchronize(ix->own_stream) != cudaSuccess)
+        sib::set_error(cudaGetLastError(), "coverageBatch copy-back", __FILE__, __LINE__);
+    for (size_t i = 0; i < n; ++i) count_out[i] = tmp[i];
+    free(tmp);
+}
+
+// ---- single queries (ref:537-821): the batch path with n = 1, no CPU fallback ---------------
+size_t upperBound(cSuperIntervals* si, int32_t value) {
+    Handle* h = H(si);
+    size_t r = SI_NONE;
+    if (si->size != 0 && ready(h, "upperBound")) si_b200_upper_bound_(h->ix, value, &r);
+    si->idx = r;   // ref:539,562,566
+    return r;
+}
+
+bool anyOverlaps(cSuperIntervals* si, int32_t start, int32_t end) {
+    bool r = false;
+    anyOverlapsBatch(si, &start, &end, 1, &r);
+    return r;
+}
+
+size_t countOverlaps(cSuperIntervals* si, int32_t start, int32_t end) {
+    size_t c = 0;
+    countOverlapsBatch(si, &start, &end, 1, &c);
+    return c;
+}
+
+void searchValues(cSuperIntervals* si, int32_t start, int32_t end, cIndexResult* found) {
+    searchValuesBatch(si, &start, &end, 1, nullptr, found);
+}
+void searchIdxs(cSuperIntervals* si, int32_t start, int32_t end, cIndexResult* found) {
+    searchIdxsBatch(si, &start, &end, 1, nullptr, found);
+}
+void searchKeys(cSuperIntervals* si, int32_t start, int32_t end, cKeyResult* found) {
+    searchKeysBatch(si, &start, &end, 1, nullptr, found);
+}
+void searchItems(cSuperIntervals* si, int32_t start, int32_t end, cItemResult* found) {
+    searchItemsBatch(si, &start, &end, 1, nullptr, found);
+}
+void searchPoint(cSuperIntervals* si, int32_t point, cIndexResult* found) {   // ref:725-727
+    searchValuesBatch(si, &point, &point, 1, nullptr, found);
+}
+void coverage(cSuperIntervals* si, int32_t start, int32_t end, size_t* count_out, int32_t* coverage_out) {
+    *count_out = 0;
+    *coverage_out = 0;
+    coverageBatch(si, &start, &end, 1, count_out, coverage_out);
+}
+void findOverlaps(cSuperIntervals* si, int32_t start, int32_t end, int32_t* found, size_t* found_size) {
+    // legacy raw-buffer form (ref:794-821): the caller sized `found`
+    cIndexResult tmp = {nullptr, 0, 0};
+    searchValuesBatch(si, &start, &end, 1, nullptr, &tmp);
+    if (tmp.size) memcpy(found, tmp.data, tmp.size * sizeof(int32_t));
+    *found_size = tmp.size;
+    free(tmp.data);
+}
+
+// ---- result buffers (ref:1066-1089) -----------------------------------------------------------
+cIndexResult createIndexResult(void) { cIndexResult r = {nullptr, 0, 0}; return r; }
+void clearIndexResult(cIndexResult* r) { r->size = 0; }
+void destroyIndexResult(cIndexResult* r) { free(r->data); r->data = nullptr; r->size = r->capacity = 0; }
+cKeyResult createKeyResult(void) { cKeyResult r = {nullptr, 0, 0}; return r; }
+void clearKeyResult(cKeyResult* r) { r->size = 0; }
+void destroyKeyResult(cKeyResult* r) { free(r->data); r->data = nullptr; r->size = r->capacity = 0; }
+cItemResult createItemResult(void) { cItemResult r = {nullptr, 0, 0}; return r; }
+void clearItemResult(cItemResult* r) { r->size = 0; }
+void destroyItemResult(cItemResult* r) { free(r->data); r->data = nullptr; r->size = r->capacity = 0; }
+
+}  // extern "C"

@@ -1,0 +1,555 @@
+// index.cu -- device-resident core of libsuperintervals_b200: the siIndex object,
+// build() on device, batch query launchers. Exported with C linkage; declared in
+// include/superintervals_b200.h.
+#include "../../include/superintervals_b200.h"
+
+#include "build_kernels.cuh"
+#include "index.cuh"
+#include "query_kernels.cuh"
+#include "radix_sort.cuh"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+// ------------------------------------------------------------------------------------
+// error side channel + launch counter
+// ------------------------------------------------------------------------------------
+namespace sib {
+namespace {
+std::mutex g_err_mu;
+int g_err_code = 0;
+char g_err_msg[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+}  // namespace
+
+void set_error(cudaError_t e, const char* what, const char* file, int line) {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    if (g_err_code == 0) {   // keep the first failure
+        g_err_code = (int)e;
+        snprintf(g_err_msg, sizeof(g_err_msg), "CUDA error %d (%s) at %s:%d: %s", (int)e,
+                 cudaGetErrorString(e), file, line, what);
+    }
+    (void)cudaGetLastError();   // un-stick the runtime's last-error slot
+}
+void set_error_msg(int code, const char* msg) {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    if (g_err_code == 0) {
+        g_err_code = code;
+        snprintf(g_err_msg, sizeof(g_err_msg), "%s", msg);
+    }
+}
+int last_error_code() { return g_err_code; }
+void note_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+unsigned long long launches() { return g_launches.load(std::memory_order_relaxed); }
+
+int DevBuf::ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) { SIB_CHECK(cudaFree(p)); p = nullptr; cap = 0; }
+    size_t want = (bytes + 255) & ~(size_t)255;
+    SIB_CHECK(cudaMalloc(&p, want));
+    cap = want;
+    return 0;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+}  // namespace sib
+
+using namespace sib;
+
+#define SIB_LAUNCH(kernel, grid, block, smem, stream, ...)                      \
+    do {                                                                        \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);             \
+        SIB_CHECK_LAUNCH();                                                     \
+        note_launch();                                                          \
+    } while (0)
+
+size_t siIndex::device_bytes() const {
+    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &b_in_s, &b_in_e, &b_in_v,
+                           &b_kA, &b_kB, &b_vA, &b_vB, &b_ws, &small, &q_kA, &q_kB, &q_vA, &q_vB,
+                           &q_ws, &scan_status, &h_qs, &h_qe, &h_counts, &h_offsets, &h_out, &h_cov};
+    size_t s = 0;
+    for (auto* b : all) s += b->cap;
+    return s;
+}
+
+namespace {
+
+constexpr size_t MAX_N = 0xFFFFFFFFull - 16384;   // uint32 positions, NONE32 reserved, tile slack
+
+// Device-API streams are taken as given: NULL is the legacy default stream (CUDA
+// convention), which is also what torch hands over when no stream context is active.
+inline cudaStream_t pick_stream(siIndex*, void* stream) { return (cudaStream_t)stream; }
+
+inline int grid_for(uint64_t n, int threads, int cap) {
+    uint64_t g = (n + threads - 1) / threads;
+    if (g < 1) g = 1;
+    if (g > (uint64_t)cap) g = cap;
+    return (int)g;
+}
+
+IndexView view_of(const siIndex* ix) {
+    IndexView v;
+    v.starts = ix->starts.as<int32_t>();
+    v.ends = ix->ends.as<int32_t>();
+    v.values = ix->values.as<int32_t>();
+    v.branch = ix->branch.as<uint32_t>();
+    v.n = ix->n;
+    return v;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+// small device scalars live in ix->small: word 0 = build sortedness flags,
+// word 1 = query sortedness flag, word 2 = scan ticket, word 3 = upper_bound result
+int ensure_small(siIndex* ix) { return ix->small.ensure(256); }
+
+int build_branch(siIndex* ix, cudaStream_t s) {
+    // level sizes
+    uint32_t nl[BK_MAX_LEVELS + 2];
+    nl[0] = ix->n;
+    int produced = 0;
+    for (int L = 1; L <= BK_MAX_LEVELS + 1; ++L) nl[L] = (nl[L - 1] + 31) / 32;
+    // always build at least levels 1 and 2; stop once a level fits one group of 32
+    int top = 1;
+    while (nl[top] > 32) ++top;
+    produced = top + (top & 1);   // max2 emits levels in pairs: 1-2, 3-4, ...
+    if (produced > BK_MAX_LEVELS) produced = BK_MAX_LEVELS + 1;
+
+    size_t total = 0;
+    for (int L = 1; L <= produced; ++L) total += ((size_t)nl[L] + 31) & ~(size_t)31;
+    size_t ptotal = 0;
+    for (int L = 1; L <= top; ++L) ptotal += ((size_t)nl[L] + 31) & ~(size_t)31;
+    if (ix->tree.ensure((total + ptotal) * sizeof(int32_t))) return last_error_code();
+
+    MaxTree t;
+    memset(&t, 0, sizeof(t));
+    int32_t* base = ix->tree.as<int32_t>();
+    int32_t* M[BK_MAX_LEVELS + 2];
+    int32_t* P[BK_MAX_LEVELS + 2];
+    M[0] = ix->ends.as<int32_t>();
+    size_t off = 0;
+    for (int L = 1; L <= produced; ++L) { M[L] = base + off; off += ((size_t)nl[L] + 31) & ~(size_t)31; }
+    for (int L = 1; L <= top; ++L) { P[L] = base + off; off += ((size_t)nl[L] + 31) & ~(size_t)31; }
+
+    for (int L = 0; L < produced; L += 2) {
+        int grid = (int)(((uint64_t)nl[L] + 1023) / 1024);
+        SIB_LAUNCH(bk_max2_kernel, grid, 1024, 0, s, M[L], nl[L], M[L + 1], M[L + 2]);
+    }
+    for (int L = top; L >= 1; --L) {
+        int grid = (int)(((uint64_t)nl[L] + BK_THREADS - 1) / BK_THREADS);
+        SIB_LAUNCH(bk_prefix_level_kernel, grid, BK_THREADS, 0, s, M[L], nl[L],
+                   L == top ? (const int32_t*)nullptr : (const int32_t*)P[L + 1], P[L]);
+    }
+    for (int L = 0; L <= top; ++L) { t.M[L] = M[L]; t.n[L] = nl[L]; }
+    t.P1 = P[1];
+    t.top = top;
+    int grid = grid_for(nl[1], BK_THREADS / 32, ix->sm_count * 16);
+    SIB_LAUNCH(bk_branch_kernel, grid, BK_THREADS, 0, s, t, ix->n, ix->branch.as<uint32_t>());
+    return 0;
+}
+
+int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const int32_t* d_v, size_t n,
+                      cudaStream_t s) {
+    ix->built = false;
+    ix->plan_valid = false;
+    if (n > MAX_N) {
+        set_error_msg(cudaErrorInvalidValue, "siIndexBuild: more than 2^32-16385 intervals");
+        return cudaErrorInvalidValue;
+    }
+    ix->n = (uint32_t)n;
+    ix->n_padded = (uint32_t)(((uint64_t)n + 127) & ~(uint64_t)127);
+    if (n == 0) { ix->built = true; return 0; }   // empty build is a no-op (hpp:113-115)
+    if (ensure_small(ix)) return last_error_code();
+    const size_t pad_b = (size_t)ix->n_padded * 4;
+    if (ix->starts.ensure(pad_b) || ix->ends.ensure(pad_b) || ix->branch.ensure(pad_b) ||
+        ix->values.ensure(n * 4) || ix->perm.ensure(n * 4))
+        return last_error_code();
+    uint32_t* d_flags = ix->small.as<uint32_t>();
+    const int cap = ix->sm_count * 16;
+
+    // sortedness, as add() would have tracked it (hpp:96-101)
+    uint32_t three = 3;
+    SIB_CHECK(cudaMemcpyAsync(d_flags, &three, 4, cudaMemcpyHostToDevice, s));
+    SIB_LAUNCH(bk_check_sorted_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, d_s, d_e, ix->n, d_flags);
+    uint32_t flags = 0;
+    SIB_CHECK(cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, s));
+    SIB_CHECK(cudaStreamSynchronize(s));
+
+    if (flags == 3u) {
+        // already (start asc, end desc): the reference does not sort (hpp:1416,1421)
+        SIB_LAUNCH(bk_identity_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, d_s, d_e, d_v, ix->n,
+                   ix->starts.as<int32_t>(), ix->ends.as<int32_t>(), ix->values.as<int32_t>(),
+                   ix->perm.as<uint32_t>());
+    } else {
+        if (ix->b_kA.ensure(n * 8) || ix->b_kB.ensure(n * 8) || ix->b_vA.ensure(n * 4) ||
+            ix->b_vB.ensure(n * 4) || ix->b_ws.ensure(rs_workspace_bytes<uint64_t>(ix->n)))
+            return last_error_code();
+        SIB_LAUNCH(bk_make_keys_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, d_s, d_e, ix->n,
+                   ix->b_kA.as<uint64_t>(), ix->b_vA.as<uint32_t>());
+        int rc = radix_sort_pairs<uint64_t>(ix->b_kA.as<uint64_t>(), ix->b_kB.as<uint64_t>(),
+                                            ix->b_vA.as<uint32_t>(), ix->b_vB.as<uint32_t>(), ix->n, 64,
+                                            ix->b_ws.p, ix->sm_count, s);
+        if (rc) return rc;
+        RsWorkspace ws = rs_carve(ix->b_ws.p);
+        SIB_LAUNCH(bk_gather_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, ix->b_kA.as<uint64_t>(),
+                   ix->b_kB.as<uint64_t>(), ix->b_vA.as<uint32_t>(), ix->b_vB.as<uint32_t>(), ws.final_sel, d_v,
+                   ix->n, ix->starts.as<int32_t>(), ix->ends.as<int32_t>(), ix->values.as<int32_t>(),
+                   ix->perm.as<uint32_t>());
+    }
+    if (ix->n_padded > ix->n) {
+        SIB_LAUNCH(bk_pad_kernel, 1, 128, 0, s, ix->starts.as<int32_t>(), ix->ends.as<int32_t>(),
+                   ix->branch.as<uint32_t>(), ix->n, ix->n_padded);
+    }
+    int rc = build_branch(ix, s);
+    if (rc) return rc;
+    ix->built = true;
+    return 0;
+}
+
+void release_build_scratch(siIndex* ix) {
+    // the sort's ping-pong buffers are 24 B/interval: give them back once the index stands
+    if ((size_t)ix->n * 24 > ((size_t)64 << 20)) {
+        ix->b_kA.release(); ix->b_kB.release(); ix->b_vA.release(); ix->b_vB.release(); ix->b_ws.release();
+        ix->b_in_s.release(); ix->b_in_e.release(); ix->b_in_v.release();
+    }
+}
+
+// Sort a query batch by end. Leaves the result described by SortedQueries.
+int sort_queries(siIndex* ix, const int32_t* d_qe, uint32_t nq, cudaStream_t s, SortedQueries* out) {
+    if (ix->q_kA.ensure((size_t)nq * 4) || ix->q_kB.ensure((size_t)nq * 4) || ix->q_vA.ensure((size_t)nq * 4) ||
+        ix->q_vB.ensure((size_t)nq * 4) || ix->q_ws.ensure(rs_workspace_bytes<uint32_t>(nq)))
+        return last_error_code();
+    RsWorkspace ws = rs_carve(ix->q_ws.p);
+    out->keysA = ix->q_kA.as<uint32_t>();
+    out->keysB = ix->q_kB.as<uint32_t>();
+    out->permA = ix->q_vA.as<uint32_t>();
+    out->permB = ix->q_vB.as<uint32_t>();
+    out->sel = ws.final_sel;
+    if (ix->plan_valid && ix->plan_qe == d_qe && ix->plan_n == nq) return 0;   // reuse (count -> fill)
+    SIB_LAUNCH(qk_make_query_keys_kernel, grid_for(nq, QK_THREADS, ix->sm_count * 16), QK_THREADS, 0, s, d_qe, nq,
+               ix->q_kA.as<uint32_t>(), ix->q_vA.as<uint32_t>());
+    int rc = radix_sort_pairs<uint32_t>(ix->q_kA.as<uint32_t>(), ix->q_kB.as<uint32_t>(), ix->q_vA.as<uint32_t>(),
+                                        ix->q_vB.as<uint32_t>(), nq, 32, ix->q_ws.p, ix->sm_count, s);
+    if (rc) return rc;
+    ix->plan_qe = d_qe;
+    ix->plan_n = nq;
+    ix->plan_valid = true;
+    return 0;
+}
+
+// Resolve SI_ORDER_AUTO with one device check. Returns <0 on error, else the order to use.
+int resolve_order(siIndex* ix, const int32_t* d_qe, uint32_t nq, int order, cudaStream_t s) {
+    if (order != SI_ORDER_AUTO) return order;
+    if (nq < 4096) return SI_ORDER_ASIS;   // too small for a sort to pay
+    if (ensure_small(ix)) return -1;
+    uint32_t* d_flag = ix->small.as<uint32_t>() + 1;
+    uint32_t one = 1, flag = 0;
+    if (cudaMemcpyAsync(d_flag, &one, 4, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
+    qk_check_sorted_kernel<<<grid_for(nq, QK_THREADS, ix->sm_count * 16), QK_THREADS, 0, s>>>(d_qe, nq, d_flag);
+    note_launch();
+    if (cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return -1;
+    return flag ? SI_ORDER_SORTED : SI_ORDER_UNSORTED;
+}
+
+template <typename CountT>
+int count_impl(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, CountT* d_counts, int order,
+               void* stream) {
+    if (!ix || !ix->built) {
+        set_error_msg(cudaErrorNotReady, "siCountDevice: index not built (call build/indexSuperIntervals first)");
+        return cudaErrorNotReady;
+    }
+    if (n == 0) return 0;
+    if (n > 0xFFFFFFFFull) {
+        set_error_msg(cudaErrorInvalidValue, "siCountDevice: more than 2^32-1 queries in one batch");
+        return cudaErrorInvalidValue;
+    }
+    DeviceGuard g(ix->device);
+    cudaStream_t s = pick_stream(ix, stream);
+    const uint32_t nq = (uint32_t)n;
+    if (ix->n == 0) {
+        SIB_CHECK(cudaMemsetAsync(d_counts, 0, n * sizeof(CountT), s));
+        return 0;
+    }
+    order = resolve_order(ix, d_qe, nq, order, s);
+    if (order < 0) { set_error(cudaGetLastError(), "resolve_order", __FILE__, __LINE__); return last_error_code(); }
+    const int grid = (int)(((uint64_t)nq + QK_THREADS - 1) / QK_THREADS);
+    SortedQueries sq;
+    memset(&sq, 0, sizeof(sq));
+    if (order == SI_ORDER_UNSORTED) {
+        int rc = sort_queries(ix, d_qe, nq, s, &sq);
+        if (rc) return rc;
+        SIB_LAUNCH((qk_count_kernel<CountT, true>), grid, QK_THREADS, 0, s, view_of(ix), d_qs, d_qe, sq, nq, d_counts);
+    } else {
+        ix->plan_valid = false;
+        SIB_LAUNCH((qk_count_kernel<CountT, false>), grid, QK_THREADS, 0, s, view_of(ix), d_qs, d_qe, sq, nq, d_counts);
+    }
+    return 0;
+}
+
+template <int MODE, bool PERM>
+int launch_fill(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, const SortedQueries& sq, uint32_t nq,
+                const uint64_t* d_offsets, void* d_out, cudaStream_t s) {
+    const int grid = (int)(((uint64_t)nq + QK_THREADS - 1) / QK_THREADS);
+    SIB_LAUNCH((qk_fill_kernel<MODE, PERM>), grid, QK_THREADS, 0, s, view_of(ix), d_qs, d_qe, sq, nq, d_offsets,
+               reinterpret_cast<typename FillOut<MODE>::T*>(d_out));
+    return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// exported C ABI (superintervals_b200.h section 1 and 3)
+// ------------------------------------------------------------------------------------
+extern "C" {
+
+int si_b200_last_error(void) { return sib::last_error_code(); }
+const char* si_b200_last_error_string(void) { return sib::g_err_msg; }
+void si_b200_clear_error(void) {
+    std::lock_guard<std::mutex> lk(sib::g_err_mu);
+    sib::g_err_code = 0;
+    sib::g_err_msg[0] = 0;
+}
+const char* si_b200_version(void) { return SUPERINTERVALS_B200_VERSION; }
+int si_b200_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { sib::set_error(e, "cudaGetDeviceCount", __FILE__, __LINE__); return -1; }
+    return n;
+}
+unsigned long long si_b200_kernel_launches(void) { return sib::launches(); }
+
+siIndex* siIndexCreate(void) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { sib::set_error(e, "cudaGetDevice (no CUDA device?)", __FILE__, __LINE__); return nullptr; }
+    siIndex* ix = new siIndex();
+    ix->device = dev;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) ix->sm_count = sms;
+    e = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { sib::set_error(e, "cudaStreamCreate", __FILE__, __LINE__); delete ix; return nullptr; }
+    return ix;
+}
+
+void siIndexDestroy(siIndex* ix) {
+    if (!ix) return;
+    DeviceGuard g(ix->device);
+    DevBuf* all[] = {&ix->starts, &ix->ends, &ix->values, &ix->branch, &ix->perm, &ix->tree, &ix->b_in_s,
+                     &ix->b_in_e, &ix->b_in_v, &ix->b_kA, &ix->b_kB, &ix->b_vA, &ix->b_vB, &ix->b_ws, &ix->small,
+                     &ix->q_kA, &ix->q_kB, &ix->q_vA, &ix->q_vB, &ix->q_ws, &ix->scan_status, &ix->h_qs,
+                     &ix->h_qe, &ix->h_counts, &ix->h_offsets, &ix->h_out, &ix->h_cov};
+    for (auto* b : all) b->release();
+    if (ix->pinned) cudaFreeHost(ix->pinned);
+    if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
+    delete ix;
+}
+
+size_t siIndexSize(const siIndex* ix) { return ix ? ix->n : 0; }
+size_t siIndexDeviceBytes(const siIndex* ix) { return ix ? ix->device_bytes() : 0; }
+
+int siIndexDeviceView(const siIndex* ix, siDeviceView* out) {
+    if (!ix || !out || !ix->built) return cudaErrorNotReady;
+    out->starts = ix->starts.as<int32_t>();
+    out->ends = ix->ends.as<int32_t>();
+    out->values = ix->values.as<int32_t>();
+    out->branch = ix->branch.as<uint32_t>();
+    out->n = ix->n;
+    out->device = ix->device;
+    return 0;
+}
+
+int siIndexBuildDevice(siIndex* ix, const int32_t* d_starts, const int32_t* d_ends, const int32_t* d_values,
+                       size_t n, void* stream) {
+    if (!ix) return cudaErrorInvalidValue;
+    DeviceGuard g(ix->device);
+    cudaStream_t s = pick_stream(ix, stream);
+    int rc = build_device_impl(ix, d_starts, d_ends, d_values, n, s);
+    if (rc) return rc;
+    SIB_CHECK(cudaStreamSynchronize(s));
+    release_build_scratch(ix);
+    return 0;
+}
+
+int siIndexBuildHost(siIndex* ix, const int32_t* starts, const int32_t* ends, const int32_t* values, size_t n) {
+    if (!ix) return cudaErrorInvalidValue;
+    DeviceGuard g(ix->device);
+    cudaStream_t s = ix->own_stream;
+    if (n == 0) return build_device_impl(ix, nullptr, nullptr, nullptr, 0, s);
+    if (ix->b_in_s.ensure(n * 4) || ix->b_in_e.ensure(n * 4) || (values && ix->b_in_v.ensure(n * 4)))
+        return last_error_code();
+    SIB_CHECK(cudaMemcpyAsync(ix->b_in_s.p, starts, n * 4, cudaMemcpyHostToDevice, s));
+    SIB_CHECK(cudaMemcpyAsync(ix->b_in_e.p, ends, n * 4, cudaMemcpyHostToDevice, s));
+    if (values) SIB_CHECK(cudaMemcpyAsync(ix->b_in_v.p, values, n * 4, cudaMemcpyHostToDevice, s));
+    int rc = build_device_impl(ix, ix->b_in_s.as<int32_t>(), ix->b_in_e.as<int32_t>(),
+                               values ? ix->b_in_v.as<int32_t>() : nullptr, n, s);
+    if (rc) return rc;
+    SIB_CHECK(cudaStreamSynchronize(s));
+    release_build_scratch(ix);
+    return 0;
+}
+
+int siIndexExport(const siIndex* ix, int32_t* starts, int32_t* ends, int32_t* values, size_t* branch,
+                  uint32_t* perm) {
+    if (!ix || !ix->built) return cudaErrorNotReady;
+    if (ix->n == 0) return 0;
+    DeviceGuard g(ix->device);
+    const size_t n = ix->n;
+    if (starts) SIB_CHECK(cudaMemcpy(starts, ix->starts.p, n * 4, cudaMemcpyDeviceToHost));
+    if (ends) SIB_CHECK(cudaMemcpy(ends, ix->ends.p, n * 4, cudaMemcpyDeviceToHost));
+    if (values) SIB_CHECK(cudaMemcpy(values, ix->values.p, n * 4, cudaMemcpyDeviceToHost));
+    if (perm) SIB_CHECK(cudaMemcpy(perm, ix->perm.p, n * 4, cudaMemcpyDeviceToHost));
+    if (branch) {
+        // widen in place, back to front: the 32-bit copy sits in the first half of the buffer
+        uint32_t* tmp = reinterpret_cast<uint32_t*>(branch);
+        SIB_CHECK(cudaMemcpy(tmp, ix->branch.p, n * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = n; i-- > 0;) {
+            uint32_t b = tmp[i];
+            branch[i] = b == NONE32 ? SI_NONE : (size_t)b;
+        }
+    }
+    return 0;
+}
+
+int siCountDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, uint32_t* d_counts, int order,
+                  void* stream) {
+    return count_impl<uint32_t>(ix, d_qs, d_qe, n, d_counts, order, stream);
+}
+int siCountDevice64(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, uint64_t* d_counts, int order,
+                    void* stream) {
+    return count_impl<uint64_t>(ix, d_qs, d_qe, n, d_counts, order, stream);
+}
+
+int siAnyDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, uint8_t* d_out, void* stream) {
+    if (!ix || !ix->built) {
+        set_error_msg(cudaErrorNotReady, "siAnyDevice: index not built");
+        return cudaErrorNotReady;
+    }
+    if (n == 0) return 0;
+    if (n > 0xFFFFFFFFull) return cudaErrorInvalidValue;
+    DeviceGuard g(ix->device);
+    cudaStream_t s = pick_stream(ix, stream);
+    const int grid = (int)((n + QK_THREADS - 1) / QK_THREADS);
+    SIB_LAUNCH(qk_any_kernel, grid, QK_THREADS, 0, s, view_of(ix), d_qs, d_qe, (uint32_t)n, d_out);
+    return 0;
+}
+
+int siScanDevice(siIndex* ix, const uint32_t* d_counts, size_t n, uint64_t* d_offsets, void* stream) {
+    if (!ix) return cudaErrorInvalidValue;
+    if (n > 0xFFFFFFFFull) return cudaErrorInvalidValue;
+    DeviceGuard g(ix->device);
+    cudaStream_t s = pick_stream(ix, stream);
+    if (n == 0) {
+        SIB_CHECK(cudaMemsetAsync(d_offsets, 0, sizeof(uint64_t), s));
+        return 0;
+    }
+    if ((((uintptr_t)d_counts) | ((uintptr_t)d_offsets)) & 15u) {
+        set_error_msg(cudaErrorMisalignedAddress, "siScanDevice: d_counts and d_offsets must be 16-byte aligned");
+        return cudaErrorMisalignedAddress;
+    }
+    const uint32_t tiles = (uint32_t)((n + SC_TILE - 1) / SC_TILE);
+    if (ix->scan_status.ensure((size_t)tiles * 8 + 64) || ensure_small(ix)) return last_error_code();
+    uint32_t* ticket = ix->small.as<uint32_t>() + 2;
+    SIB_CHECK(cudaMemsetAsync(ix->scan_status.p, 0, (size_t)tiles * 8, s));
+    SIB_CHECK(cudaMemsetAsync(ticket, 0, 4, s));
+    SIB_LAUNCH(qk_scan_kernel, tiles, SC_THREADS, 0, s, d_counts, (uint32_t)n, d_offsets,
+               ix->scan_status.as<unsigned long long>(), ticket);
+    return 0;
+}
+
+int siFillDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, const uint64_t* d_offsets,
+                 int what, void* d_out, int order, void* stream) {
+    if (!ix || !ix->built) {
+        set_error_msg(cudaErrorNotReady, "siFillDevice: index not built");
+        return cudaErrorNotReady;
+    }
+    if (n == 0 || ix->n == 0) return 0;
+    if (n > 0xFFFFFFFFull) return cudaErrorInvalidValue;
+    DeviceGuard g(ix->device);
+    cudaStream_t s = pick_stream(ix, stream);
+    const uint32_t nq = (uint32_t)n;
+    order = resolve_order(ix, d_qe, nq, order, s);
+    if (order < 0) { set_error(cudaGetLastError(), "resolve_order", __FILE__, __LINE__); return last_error_code(); }
+    SortedQueries sq;
+    memset(&sq, 0, sizeof(sq));
+    const bool perm = order == SI_ORDER_UNSORTED;
+    if (perm) {
+        int rc = sort_queries(ix, d_qe, nq, s, &sq);
+        if (rc) return rc;
+    }
+#define SIB_FILL(M)                                                                              \
+    return perm ? launch_fill<M, true>(ix, d_qs, d_qe, sq, nq, d_offsets, d_out, s)              \
+                : launch_fill<M, false>(ix, d_qs, d_qe, sq, nq, d_offsets, d_out, s)
+    switch (what) {
+        case SI_FILL_VALUES: SIB_FILL(FILL_VALUES);
+        case SI_FILL_IDXS: SIB_FILL(FILL_IDXS);
+        case SI_FILL_KEYS: SIB_FILL(FILL_KEYS);
+        case SI_FILL_ITEMS: SIB_FILL(FILL_ITEMS);
+        default: break;
+    }
+#undef SIB_FILL
+    set_error_msg(cudaErrorInvalidValue, "siFillDevice: unknown fill mode");
+    return cudaErrorInvalidValue;
+}
+
+int siCoverageDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, uint32_t* d_counts,
+                     int32_t* d_cov, void* stream) {
+    if (!ix || !ix->built) {
+        set_error_msg(cudaErrorNotReady, "siCoverageDevice: index not built");
+        return cudaErrorNotReady;
+    }
+    if (n == 0) return 0;
+    if (n > 0xFFFFFFFFull) return cudaErrorInvalidValue;
+    DeviceGuard g(ix->device);
+    cudaStream_t s = pick_stream(ix, stream);
+    const int grid = (int)((n + QK_THREADS - 1) / QK_THREADS);
+    SIB_LAUNCH(qk_coverage_kernel, grid, QK_THREADS, 0, s, view_of(ix), d_qs, d_qe, (uint32_t)n, d_counts, d_cov);
+    return 0;
+}
+
+// used by c_abi.cu: resolve SI_ORDER_AUTO once for a count -> fill pair
+int si_b200_resolve_order_(siIndex* ix, const int32_t* d_qe, size_t n, void* stream) {
+    DeviceGuard g(ix->device);
+    int o = resolve_order(ix, d_qe, (uint32_t)n, SI_ORDER_AUTO, pick_stream(ix, stream));
+    if (o < 0) set_error(cudaGetLastError(), "resolve_order", __FILE__, __LINE__);
+    return o;
+}
+
+// used by c_abi.cu for the single-query upperBound
+int si_b200_upper_bound_(siIndex* ix, int32_t value, size_t* out) {
+    if (!ix || !ix->built) {
+        set_error_msg(cudaErrorNotReady, "upperBound: index not built");
+        return cudaErrorNotReady;
+    }
+    *out = SI_NONE;
+    if (ix->n == 0) return 0;
+    DeviceGuard g(ix->device);
+    if (ensure_small(ix)) return last_error_code();
+    uint32_t* d = ix->small.as<uint32_t>() + 3;
+    SIB_LAUNCH(qk_upper_bound_kernel, 1, 32, 0, ix->own_stream, view_of(ix), value, d);
+    uint32_t r = NONE32;
+    SIB_CHECK(cudaMemcpyAsync(&r, d, 4, cudaMemcpyDeviceToHost, ix->own_stream));
+    SIB_CHECK(cudaStreamSynchronize(ix->own_stream));
+    *out = r == NONE32 ? SI_NONE : (size_t)r;
+    return 0;
+}
+
+}  // extern "C"

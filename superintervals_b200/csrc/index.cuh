@@ -1,0 +1,53 @@
+// index.cuh -- the device-resident index object behind siIndex* (host-side C++).
+#pragma once
+
+#include "common.cuh"
+
+struct siIndex;   // C-visible opaque name
+
+namespace sib {
+
+// cudaMalloc'd buffer that only ever grows (reallocation drops old contents)
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes);
+    void release();
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+void note_launch(unsigned n = 1);
+unsigned long long launches();
+
+}  // namespace sib
+
+struct siIndex {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+
+    // ---- the index, position order -------------------------------------------------
+    uint32_t n = 0, n_padded = 0;
+    bool built = false;
+    sib::DevBuf starts, ends, values, branch, perm;
+    sib::DevBuf tree;          // 32-ary max tree levels + prefix-max levels (build only)
+
+    // ---- build scratch (released after build for large n) --------------------------
+    sib::DevBuf b_in_s, b_in_e, b_in_v;        // staged host inputs
+    sib::DevBuf b_kA, b_kB, b_vA, b_vB, b_ws;  // 64-bit key sort
+
+    // ---- query scratch ---------------------------------------------------------------
+    sib::DevBuf small;                          // device scalars: [0] flags/sorted, ...
+    sib::DevBuf q_kA, q_kB, q_vA, q_vB, q_ws;   // 32-bit key sort of a query batch
+    sib::DevBuf scan_status;
+    const int32_t* plan_qe = nullptr;           // query batch the cached sort belongs to
+    size_t plan_n = 0;
+    bool plan_valid = false;
+
+    // ---- staging for the host-buffer API ---------------------------------------------
+    sib::DevBuf h_qs, h_qe, h_counts, h_offsets, h_out, h_cov;
+    void* pinned = nullptr;                     // small pinned scratch for scalars
+    size_t pinned_bytes = 0;
+
+    size_t device_bytes() const;
+};

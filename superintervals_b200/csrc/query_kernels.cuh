@@ -1,0 +1,417 @@
+// query_kernels.cuh -- batch overlap queries on the device-resident superset index.
+//
+// Every query  [qs, qe]  is answered exactly as the reference's backward walk
+// (superintervals.hpp:551-579 / 651-825, c_superintervals.h:575-608 / 729-756):
+//     i = upper_bound(qe);  while i != NONE:  hit(ends[i] >= qs) ? emit, --i : i = branch[i]
+// The walk visits blocks of consecutive intervals; inside a visited block EVERY
+// hit is emitted (the reference's AVX2/NEON loop counts whole 32-blocks the same
+// way, hpp:718-748), and the block's lowest element decides what comes next:
+// a hit steps to the element below the block, a miss jumps through branch[].
+// Elements skipped by a jump have ends < ends[miss] < qs, so the emitted set is
+// { j <= ub(qe) : ends[j] >= qs } in strictly descending j -- bit-exact.
+//
+// Mapping to the GPU (one warp = one tile of 32 position-sorted queries):
+//   phase A  lane-per-query: each lane runs the branch-free upper_bound for its
+//            query (lanes of a sorted tile probe the same cache lines), then walks
+//            with 128-bit loads of ends (4 intervals per step).
+//   phase B  the few lanes whose walk is long are finished warp-cooperatively:
+//            32 lanes x 128-bit loads = 128 ends per step, hits counted with
+//            __ballot_sync/__popc (the AVX2 movemask/popcnt loop, 4x wider).
+#pragma once
+
+#include "common.cuh"
+#include <limits.h>
+
+namespace sib {
+
+constexpr int QK_THREADS = 256;
+constexpr int QK_WARPS = QK_THREADS / 32;
+
+struct IndexView {
+    const int32_t* starts;
+    const int32_t* ends;     // padded to a multiple of 128 entries (pad = INT_MIN)
+    const int32_t* values;
+    const uint32_t* branch;  // NONE32 = no previous interval reaches this far
+    uint32_t n;
+};
+
+// A query batch radix-sorted by end: keys = flipped qe in sorted order, perm = original
+// query index. *sel (device) says which of the sort's two buffers holds the result.
+struct SortedQueries {
+    const uint32_t* keysA;
+    const uint32_t* keysB;
+    const uint32_t* permA;
+    const uint32_t* permB;
+    const uint32_t* sel;
+};
+
+// Number of starts <= v, by the reference's branch-free halving search (hpp:501-513).
+// The trip count depends only on n, so a warp stays converged.
+__device__ __forceinline__ uint32_t count_le(const int32_t* __restrict__ starts, uint32_t n, int32_t v) {
+    uint32_t pos = 0, len = n;
+    while (len > 1) {
+        const uint32_t half = len >> 1;
+        pos += (ld_nc(starts + pos + half) <= v) ? (len - half) : 0u;
+        len = half;
+    }
+    return pos + ((ld_nc(starts + pos) <= v) ? 1u : 0u);
+}
+
+// phase-A policy: keep walking lane-parallel while enough lanes are busy
+__device__ __forceinline__ bool keep_lane_phase(uint32_t active_mask, int iter) {
+    const int a = __popc(active_mask);
+    return a > 16 || (a > 3 && iter < 48);
+}
+
+// ---- count ---------------------------------------------------------------------------
+// SORTED_VIA_PERM: queries were radix-sorted by qe (see SortedQueries); qs is gathered
+// through the permutation and the count is scattered back to the caller's order.
+template <typename CountT, bool SORTED_VIA_PERM>
+__global__ void __launch_bounds__(QK_THREADS)
+qk_count_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* __restrict__ qe_in,
+                SortedQueries sq, uint32_t nq, CountT* __restrict__ counts) {
+    const uint64_t t64 = (uint64_t)blockIdx.x * QK_THREADS + threadIdx.x;
+    const bool live = t64 < nq;
+    const uint32_t t = (uint32_t)t64;
+    const uint32_t lane = lane_id();
+
+    uint32_t q = t;
+    int32_t qs = 0, qe = 0;
+    if (live) {
+        if (SORTED_VIA_PERM) {
+            const bool useB = *sq.sel != 0;
+            q = ld_stream((useB ? sq.permB : sq.permA) + t);
+            qe = unflip_i32(ld_stream((useB ? sq.keysB : sq.keysA) + t));
+        } else {
+            qe = ld_stream(qe_in + t);
+        }
+        qs = ld_stream(qs_in + q);
+    }
+
+    uint32_t i = NONE32;
+    if (live && ix.n) i = count_le(ix.starts, ix.n, qe) - 1u;   // 0 - 1 wraps to NONE32
+
+    uint32_t c = 0;
+    // ---- phase A: lane-per-query, 4 intervals per step
+    uint32_t active = __ballot_sync(FULL_MASK, i != NONE32);
+    int iter = 0;
+    while (keep_lane_phase(active, iter)) {
+        if (i != NONE32) {
+            const uint32_t base = i & ~3u;
+            const int4 e = ld_nc4(ix.ends + base);
+            const uint32_t k = i - base;   // elements base .. base+k are at or below i
+            c += (e.x >= qs) ? 1u : 0u;
+            c += (k >= 1u && e.y >= qs) ? 1u : 0u;
+            c += (k >= 2u && e.z >= qs) ? 1u : 0u;
+            c += (k >= 3u && e.w >= qs) ? 1u : 0u;
+            i = (e.x >= qs) ? base - 1u : ld_nc(ix.branch + base);   // base==0: wraps to NONE32
+        }
+        active = __ballot_sync(FULL_MASK, i != NONE32);
+        ++iter;
+    }
+    // ---- phase B: stragglers, one query at a time across the whole warp
+    while (active) {
+        const int src = __ffs(active) - 1;
+        active &= active - 1;
+        uint32_t bi = __shfl_sync(FULL_MASK, i, src);
+        const int32_t bqs = __shfl_sync(FULL_MASK, qs, src);
+        uint32_t bc = 0;
+        while (bi != NONE32) {
+            const uint32_t base = bi & ~127u;
+            const uint32_t j = base + lane * 4u;
+            int4 e = make_int4(INT_MIN, INT_MIN, INT_MIN, INT_MIN);
+            if (j <= bi) e = ld_nc4(ix.ends + j);
+            const bool hx = e.x >= bqs;                 // j <= bi whenever it was loaded
+            const bool hy = (j + 1u <= bi) && e.y >= bqs;
+            const bool hz = (j + 2u <= bi) && e.z >= bqs;
+            const bool hw = (j + 3u <= bi) && e.w >= bqs;
+            const uint32_t bx = __ballot_sync(FULL_MASK, hx);
+            bc += __popc(bx) + __popc(__ballot_sync(FULL_MASK, hy)) +
+                  __popc(__ballot_sync(FULL_MASK, hz)) + __popc(__ballot_sync(FULL_MASK, hw));
+            // lane 0's .x is the block's lowest interval
+            bi = (bx & 1u) ? base - 1u : ld_nc(ix.branch + base);
+        }
+        if ((int)lane == src) { c += bc; i = NONE32; }
+    }
+    if (live) counts[q] = (CountT)c;
+}
+
+// ---- has_overlaps: tests ONLY the last candidate (hpp:865-871, quirk Q1) ----------------
+__global__ void __launch_bounds__(QK_THREADS)
+qk_any_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* __restrict__ qe_in,
+              uint32_t nq, uint8_t* __restrict__ out) {
+    const uint64_t t = (uint64_t)blockIdx.x * QK_THREADS + threadIdx.x;
+    if (t >= nq) return;
+    uint8_t r = 0;
+    if (ix.n) {
+        const uint32_t i = count_le(ix.starts, ix.n, qe_in[t]) - 1u;
+        r = (i != NONE32 && qs_in[t] <= ld_nc(ix.ends + i)) ? 1 : 0;
+    }
+    out[t] = r;
+}
+
+// ---- upperBound for the C ABI cursor (c_superintervals.h:537-568) ------------------------
+__global__ void qk_upper_bound_kernel(IndexView ix, int32_t value, uint32_t* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out = ix.n ? count_le(ix.starts, ix.n, value) - 1u : NONE32;
+}
+
+// ---- coverage: hit count + sum of clipped lengths (hpp:979-1006, c.h:758-792) -----------
+// int32 arithmetic that wraps exactly like the reference's `S` accumulator.
+__global__ void __launch_bounds__(QK_THREADS)
+qk_coverage_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* __restrict__ qe_in,
+                   uint32_t nq, uint32_t* __restrict__ counts, int32_t* __restrict__ cov) {
+    const uint64_t t = (uint64_t)blockIdx.x * QK_THREADS + threadIdx.x;
+    if (t >= nq) return;
+    const int32_t qs = qs_in[t], qe = qe_in[t];
+    uint32_t c = 0, sum = 0;
+    uint32_t i = ix.n ? count_le(ix.starts, ix.n, qe) - 1u : NONE32;
+    while (i != NONE32) {
+        const uint32_t base = i & ~3u;
+        const int4 e = ld_nc4(ix.ends + base);
+        const int4 s = ld_nc4(ix.starts + base);
+        const uint32_t k = i - base;
+#define SIB_COV(EE, SS, OK)                                                        \
+        if ((OK) && (EE) >= qs) {                                                  \
+            ++c;                                                                   \
+            sum += (uint32_t)min((EE), qe) - (uint32_t)max((SS), qs);              \
+        }
+        SIB_COV(e.x, s.x, true)
+        SIB_COV(e.y, s.y, k >= 1u)
+        SIB_COV(e.z, s.z, k >= 2u)
+        SIB_COV(e.w, s.w, k >= 3u)
+#undef SIB_COV
+        i = (e.x >= qs) ? base - 1u : ld_nc(ix.branch + base);
+    }
+    counts[t] = c;
+    cov[t] = (int32_t)sum;
+}
+
+// ---- fill: CSR values in the reference's descending order -------------------------------
+enum FillMode : int { FILL_VALUES = 0, FILL_IDXS = 1, FILL_KEYS = 2, FILL_ITEMS = 3 };
+
+template <int MODE> struct FillOut;
+template <> struct FillOut<FILL_VALUES> { using T = int32_t; };
+template <> struct FillOut<FILL_IDXS> { using T = uint32_t; };
+template <> struct FillOut<FILL_KEYS> { using T = int2; };
+struct __align__(4) Item3 { int32_t start, end, data; };
+template <> struct FillOut<FILL_ITEMS> { using T = Item3; };
+
+template <int MODE>
+__device__ __forceinline__ void emit(const IndexView& ix, typename FillOut<MODE>::T* __restrict__ out,
+                                     uint64_t pos, uint32_t j, int32_t end_j) {
+    if (MODE == FILL_VALUES) {
+        reinterpret_cast<int32_t*>(out)[pos] = ld_nc(ix.values + j);
+    } else if (MODE == FILL_IDXS) {
+        reinterpret_cast<uint32_t*>(out)[pos] = j;
+    } else if (MODE == FILL_KEYS) {
+        reinterpret_cast<int2*>(out)[pos] = make_int2(ld_nc(ix.starts + j), end_j);
+    } else {
+        Item3 it;
+        it.start = ld_nc(ix.starts + j);
+        it.end = end_j;
+        it.data = ld_nc(ix.values + j);
+        reinterpret_cast<Item3*>(out)[pos] = it;
+    }
+}
+
+constexpr uint32_t QK_FILL_LANE_MAX = 48;   // queries with more hits go straight to the warp phase
+
+template <int MODE, bool SORTED_VIA_PERM>
+__global__ void __launch_bounds__(QK_THREADS)
+qk_fill_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* __restrict__ qe_in,
+               SortedQueries sq, uint32_t nq, const uint64_t* __restrict__ offsets,
+               typename FillOut<MODE>::T* __restrict__ out) {
+    const uint64_t t64 = (uint64_t)blockIdx.x * QK_THREADS + threadIdx.x;
+    const bool live = t64 < nq;
+    const uint32_t t = (uint32_t)t64;
+    const uint32_t lane = lane_id();
+
+    uint32_t q = t;
+    int32_t qs = 0, qe = 0;
+    uint64_t o = 0, o_end = 0;
+    if (live) {
+        if (SORTED_VIA_PERM) {
+            const bool useB = *sq.sel != 0;
+            q = ld_stream((useB ? sq.permB : sq.permA) + t);
+            qe = unflip_i32(ld_stream((useB ? sq.keysB : sq.keysA) + t));
+        } else {
+            qe = ld_stream(qe_in + t);
+        }
+        qs = ld_stream(qs_in + q);
+        o = ld_stream(offsets + q);
+        o_end = ld_stream(offsets + q + 1);
+    }
+    const bool any_hits = live && o_end > o;
+    uint32_t i = NONE32;
+    if (any_hits) i = count_le(ix.starts, ix.n, qe) - 1u;   // no hits -> nothing to walk
+
+    // ---- phase A: short result lists, lane-per-query
+    const bool small = any_hits && (o_end - o) <= QK_FILL_LANE_MAX;
+    if (small) {
+        while (i != NONE32) {
+            const uint32_t base = i & ~3u;
+            const int4 e = ld_nc4(ix.ends + base);
+            const uint32_t k = i - base;
+            if (k >= 3u && e.w >= qs) emit<MODE>(ix, out, o++, base + 3u, e.w);
+            if (k >= 2u && e.z >= qs) emit<MODE>(ix, out, o++, base + 2u, e.z);
+            if (k >= 1u && e.y >= qs) emit<MODE>(ix, out, o++, base + 1u, e.y);
+            if (e.x >= qs) emit<MODE>(ix, out, o++, base, e.x);
+            if (o == o_end) break;   // every hit written: the rest of the walk only skips
+            i = (e.x >= qs) ? base - 1u : ld_nc(ix.branch + base);
+        }
+        i = NONE32;
+    }
+    // ---- phase B: long result lists, whole warp per query, coalesced stores
+    uint32_t pending = __ballot_sync(FULL_MASK, any_hits && !small);
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        uint32_t bi = __shfl_sync(FULL_MASK, i, src);
+        const int32_t bqs = __shfl_sync(FULL_MASK, qs, src);
+        uint64_t bo = __shfl_sync(FULL_MASK, o, src);
+        const uint64_t bo_end = __shfl_sync(FULL_MASK, o_end, src);
+        while (bi != NONE32 && bo < bo_end) {
+            // lane l looks at interval bi - l: 32 consecutive intervals, descending
+            const bool inb = lane <= bi;
+            const uint32_t j = bi - lane;
+            const int32_t e = inb ? ld_nc(ix.ends + j) : INT_MIN;
+            const bool hit = inb && e >= bqs;
+            const uint32_t hm = __ballot_sync(FULL_MASK, hit);
+            if (hit) emit<MODE>(ix, out, bo + __popc(hm & lanemask_lt()), j, e);
+            bo += __popc(hm);
+            if (bi < 32u) break;                     // the block reached interval 0
+            const uint32_t low = bi - 31u;           // lowest interval of the block (lane 31)
+            bi = (hm >> 31) ? low - 1u : ld_nc(ix.branch + low);
+        }
+    }
+}
+
+// ---- exclusive scan of counts -> 64-bit CSR offsets (single pass, decoupled look-back) --
+constexpr int SC_THREADS = 256;
+constexpr int SC_ITEMS = 16;
+constexpr uint32_t SC_TILE = SC_THREADS * SC_ITEMS;
+constexpr unsigned long long SC_FLAG_AGG = 1ull << 62;
+constexpr unsigned long long SC_FLAG_INC = 2ull << 62;
+constexpr unsigned long long SC_VAL_MASK = (1ull << 62) - 1;
+
+// offsets has nq+1 entries; offsets[0] = 0, offsets[nq] = total hits.
+__global__ void __launch_bounds__(SC_THREADS)
+qk_scan_kernel(const uint32_t* __restrict__ counts, uint32_t nq, uint64_t* __restrict__ offsets,
+               unsigned long long* __restrict__ status, uint32_t* __restrict__ ticket) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_warp[SC_THREADS / 32];
+    __shared__ uint64_t s_prefix;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t base = (uint64_t)tile * SC_TILE + (uint64_t)tid * SC_ITEMS;
+
+    uint32_t v[SC_ITEMS];
+    if (base + SC_ITEMS <= nq) {
+        const uint4* p = reinterpret_cast<const uint4*>(counts + base);
+#pragma unroll
+        for (int k = 0; k < SC_ITEMS / 4; ++k) {
+            uint4 x = p[k];
+            v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SC_ITEMS; ++k) v[k] = (base + k < nq) ? counts[base + k] : 0u;
+    }
+    uint64_t tsum = 0;
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; ++k) tsum += v[k];
+
+    uint64_t incl = tsum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint64_t x = __shfl_up_sync(FULL_MASK, incl, off);
+        if (lane >= (uint32_t)off) incl += x;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint64_t wpre = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < SC_THREADS / 32; ++w) {
+        uint64_t x = s_warp[w];
+        if (w < (int)warp) wpre += x;
+        tile_total += x;
+    }
+
+    if (warp == 0) {
+        // publish, then look back 32 tiles at a time
+        if (lane == 0)
+            *(volatile unsigned long long*)(status + tile) = (tile == 0 ? SC_FLAG_INC : SC_FLAG_AGG) | tile_total;
+        uint64_t excl = 0;
+        if (tile > 0) {
+            int64_t look = (int64_t)tile - 1;
+            while (true) {
+                const int64_t mine = look - lane;
+                unsigned long long w = SC_FLAG_INC;   // tiles before 0 count as an inclusive 0
+                if (mine >= 0) {
+                    do { w = *(volatile unsigned long long*)(status + mine); } while ((w & ~SC_VAL_MASK) == 0);
+                }
+                const uint32_t inc_mask = __ballot_sync(FULL_MASK, (w & ~SC_VAL_MASK) == SC_FLAG_INC);
+                // nearest tile holding a full prefix; none in this window -> take all 32 aggregates
+                const int first_inc = inc_mask ? __ffs(inc_mask) - 1 : 31;
+                uint64_t contrib = ((int)lane <= first_inc) ? (w & SC_VAL_MASK) : 0ull;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) contrib += __shfl_xor_sync(FULL_MASK, contrib, off);
+                excl += contrib;
+                if (inc_mask) break;
+                look -= 32;
+            }
+            if (lane == 0)
+                *(volatile unsigned long long*)(status + tile) = SC_FLAG_INC | (excl + tile_total);
+        }
+        if (lane == 0) s_prefix = excl;
+    }
+    __syncthreads();
+    uint64_t run = s_prefix + wpre + incl - tsum;   // exclusive prefix of this thread's first item
+    if (base + SC_ITEMS <= nq) {
+        uint64_t outv[SC_ITEMS];
+#pragma unroll
+        for (int k = 0; k < SC_ITEMS; ++k) { outv[k] = run; run += v[k]; }
+        ulonglong2* po = reinterpret_cast<ulonglong2*>(offsets + base);
+#pragma unroll
+        for (int k = 0; k < SC_ITEMS / 2; ++k) po[k] = make_ulonglong2(outv[2 * k], outv[2 * k + 1]);
+        if (base + SC_ITEMS == nq) offsets[nq] = run;
+    } else {
+#pragma unroll
+        for (int k = 0; k < SC_ITEMS; ++k) {
+            if (base + k < nq) { offsets[base + k] = run; run += v[k]; }
+            if (base + k == nq) offsets[nq] = run;   // first slot past the end carries the total
+        }
+    }
+}
+
+// ---- query ordering helpers --------------------------------------------------------------
+// *flag (init 1) is cleared when qe is not non-decreasing.
+__global__ void __launch_bounds__(QK_THREADS)
+qk_check_sorted_kernel(const int32_t* __restrict__ qe, uint32_t nq, uint32_t* __restrict__ flag) {
+    uint32_t bad = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * QK_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * QK_THREADS + threadIdx.x + 1; i < nq; i += stride)
+        bad |= (qe[i] < qe[i - 1]) ? 1u : 0u;
+    bad = __reduce_or_sync(FULL_MASK, bad);
+    if (lane_id() == 0 && bad) *flag = 0;
+}
+
+__global__ void __launch_bounds__(QK_THREADS)
+qk_make_query_keys_kernel(const int32_t* __restrict__ qe, uint32_t nq, uint32_t* __restrict__ keys,
+                          uint32_t* __restrict__ idx) {
+    const uint64_t stride = (uint64_t)gridDim.x * QK_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * QK_THREADS + threadIdx.x; i < nq; i += stride) {
+        keys[i] = flip_i32(qe[i]);
+        idx[i] = (uint32_t)i;
+    }
+}
+
+__global__ void __launch_bounds__(QK_THREADS)
+qk_widen_kernel(const uint32_t* __restrict__ in, uint32_t n, uint64_t* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * QK_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * QK_THREADS + threadIdx.x; i < n; i += stride) out[i] = in[i];
+}
+
+}  // namespace sib

@@ -1,0 +1,255 @@
+"""Python ``IntervalMap`` over libsuperintervals_b200.so.
+
+Host-side mirror of the reference's Python class for the batch overlap-query
+path (reference src/superintervals/intervalmap.pyx:18-494): same method names,
+argument meaning and error behaviour (ValueError on length mismatch,
+IndexError on out-of-range ``at``). Every query executes on the GPU through the
+C ABI (include/c_superintervals.h, include/superintervals_b200.h); payload
+objects stay on the host and are addressed by the int32 insertion index the
+device index carries.
+
+Additions to the reference API (the CSR forms the GPU path produces natively):
+``count_batch_np``, ``search_values_batch_csr``, ``search_idxs_batch_csr``,
+``search_keys_batch_csr``, ``has_overlaps_batch``, ``coverage_batch``.
+The ``*_batch`` methods of the reference return Python lists / list-of-lists
+(pyx:395-400, 436-446, 482-494); they are kept and built from the CSR forms.
+
+Not provided: the set-algebra methods (pyx:510-819) -- outside the accelerated
+path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["IntervalMap"]
+
+
+def _as_i32(a, name):
+    arr = np.ascontiguousarray(a, dtype=np.int32)
+    if arr.ndim != 1:
+        raise ValueError(f"{name} must be one-dimensional")
+    return arr
+
+
+class IntervalMap:
+    """SuperIntervals interval map: end-inclusive intervals with associated Python objects."""
+
+    def __init__(self):
+        self._L = _lib.lib()
+        self._si = self._L.createSuperIntervals()
+        if not self._si:
+            raise MemoryError("createSuperIntervals failed")
+        self._values = []          # payload objects in insertion order
+        self._built = False
+
+    def __del__(self):
+        si, self._si = getattr(self, "_si", None), None
+        if si:
+            self._L.destroySuperIntervals(si)
+
+    # ---- container protocol (pyx:38-42) --------------------------------------------------
+    def __len__(self):
+        return self.size()
+
+    def __getitem__(self, index):
+        return self.at(index)
+
+    # ---- building (pyx:44-137) -------------------------------------------------------------
+    def add(self, start, end, value=None):
+        """Add an interval [start, end] (inclusive) with an associated Python object."""
+        self._L.addInterval(self._si, int(start), int(end), len(self._values))
+        self._values.append(value)
+        self._built = False
+
+    @classmethod
+    def from_arrays(cls, starts, ends, values=None):
+        """Create a ready-to-query IntervalMap from arrays (pyx:63-131)."""
+        self = cls()
+        s = _as_i32(starts, "starts")
+        e = _as_i32(ends, "ends")
+        if s.shape[0] != e.shape[0]:
+            raise ValueError("starts and ends must have the same length")
+        n = s.shape[0]
+        if values is not None and len(values) != n:
+            raise ValueError("values length must match starts/ends length")
+        self._L.addIntervals(self._si, s.ctypes.data, e.ctypes.data, None, n)
+        self._values = list(values) if values is not None else [None] * n
+        self.build()
+        return self
+
+    def build(self):
+        """Build the superintervals index (device sort + branch pass). Required before queries."""
+        self._L.indexSuperIntervals(self._si)
+        _lib.check("build")
+        self._built = True
+
+    def clear(self):
+        self._L.clearSuperIntervals(self._si)
+        self._values = []
+        self._built = False
+
+    def reserve(self, n):
+        self._L.reserveSuperIntervals(self._si, int(n))
+
+    def size(self):
+        return int(self._L.sizeSuperIntervals(self._si))
+
+    # ---- element access (pyx:139-211) -------------------------------------------------------
+    def _check_index(self, index):
+        if self.size() == 0 or index < 0 or index >= self.size():
+            raise IndexError("Index out of range")
+
+    def at(self, index):
+        self._check_index(index)
+        c = self._si.contents
+        return c.starts[index], c.ends[index], self._values[c.data[index]]
+
+    def starts_at(self, index):
+        self._check_index(index)
+        return self._si.contents.starts[index]
+
+    def ends_at(self, index):
+        self._check_index(index)
+        return self._si.contents.ends[index]
+
+    def data_at(self, index):
+        self._check_index(index)
+        return self._values[self._si.contents.data[index]]
+
+    # index arrays in position order (host mirrors of the device index)
+    def _mirror(self, field, dtype):
+        n = self.size()
+        if n == 0:
+            return np.zeros(0, dtype)
+        return np.ctypeslib.as_array(getattr(self._si.contents, field), shape=(n,)).astype(dtype)
+
+    @property
+    def starts(self): return self._mirror("starts", np.int32)
+    @property
+    def ends(self): return self._mirror("ends", np.int32)
+    @property
+    def data_index(self): return self._mirror("data", np.int32)
+    @property
+    def branch(self):
+        if not self._si.contents.branch:
+            return np.zeros(0, np.uint64)
+        return self._mirror("branch", np.uint64)
+
+    # ---- single queries (pyx:241-361) ---------------------------------------------------------
+    def has_overlaps(self, start, end):
+        r = bool(self._L.anyOverlaps(self._si, int(start), int(end)))
+        _lib.check("has_overlaps")
+        return r
+
+    def count(self, start, end):
+        r = int(self._L.countOverlaps(self._si, int(start), int(end)))
+        _lib.check("count")
+        return r
+
+    def _one(self, start, end):
+        return (np.array([start], np.int32), np.array([end], np.int32))
+
+    def search_values(self, start, end):
+        _, vals = self.search_values_batch_csr(*self._one(start, end))
+        return [self._values[i] for i in vals]
+
+    def search_idxs(self, start, end):
+        """Positions of overlapping intervals, descending (the order of the reference's C ABI,
+        Rust crate and lazy ranges; its C++ vector overload differs)."""
+        _, idx = self.search_idxs_batch_csr(*self._one(start, end))
+        return [int(i) for i in idx]
+
+    def search_keys(self, start, end):
+        _, keys = self.search_keys_batch_csr(*self._one(start, end))
+        return [(int(a), int(b)) for a, b in keys]
+
+    def search_items(self, start, end):
+        s, e = self._one(start, end)
+        found = self._L.createItemResult()
+        self._L.searchItemsBatch(self._si, s.ctypes.data, e.ctypes.data, 1, None, C.byref(found))
+        _lib.check("search_items")
+        out = [(found.data[i].start, found.data[i].end, self._values[found.data[i].data]) for i in range(found.size)]
+        self._L.destroyItemResult(C.byref(found))
+        return out
+
+    def coverage(self, start, end):
+        cnt, cov = C.c_size_t(0), C.c_int32(0)
+        self._L.coverage(self._si, int(start), int(end), C.byref(cnt), C.byref(cov))
+        _lib.check("coverage")
+        return int(cnt.value), int(cov.value)
+
+    # ---- batch queries: numpy / CSR forms -------------------------------------------------------
+    def _pair(self, starts, ends):
+        s = _as_i32(starts, "starts")
+        e = _as_i32(ends, "ends")
+        if s.shape[0] != e.shape[0]:
+            raise ValueError("starts and ends must have the same length")   # pyx:392-393
+        return s, e
+
+    def count_batch_np(self, starts, ends):
+        s, e = self._pair(starts, ends)
+        out = np.zeros(s.shape[0], np.uint64)
+        self._L.countOverlapsBatch(self._si, s.ctypes.data, e.ctypes.data, s.shape[0], out.ctypes.data)
+        _lib.check("count_batch")
+        return out
+
+    def has_overlaps_batch(self, starts, ends):
+        s, e = self._pair(starts, ends)
+        out = np.zeros(s.shape[0], np.bool_)
+        self._L.anyOverlapsBatch(self._si, s.ctypes.data, e.ctypes.data, s.shape[0], out.ctypes.data)
+        _lib.check("has_overlaps_batch")
+        return out
+
+    def coverage_batch(self, starts, ends):
+        s, e = self._pair(starts, ends)
+        cnt = np.zeros(s.shape[0], np.uint64)
+        cov = np.zeros(s.shape[0], np.int32)
+        self._L.coverageBatch(self._si, s.ctypes.data, e.ctypes.data, s.shape[0], cnt.ctypes.data, cov.ctypes.data)
+        _lib.check("coverage_batch")
+        return cnt, cov
+
+    def _csr(self, fn, make, destroy, starts, ends, shape_tail, dtype):
+        s, e = self._pair(starts, ends)
+        n = s.shape[0]
+        offsets = np.zeros(n + 1, np.uint64)
+        found = make()
+        fn(self._si, s.ctypes.data, e.ctypes.data, n, offsets.ctypes.data, C.byref(found))
+        _lib.check(fn.__name__)
+        total = int(found.size)
+        if total:
+            buf = np.ctypeslib.as_array(C.cast(found.data, C.POINTER(C.c_int32)), shape=(total,) + shape_tail)
+            out = buf.astype(dtype, copy=True)
+        else:
+            out = np.zeros((0,) + shape_tail, dtype)
+        destroy(C.byref(found))
+        return offsets, out
+
+    def search_values_batch_csr(self, starts, ends):
+        """(offsets[n+1], idx[total]): idx are insertion indices into the payload list."""
+        return self._csr(self._L.searchValuesBatch, self._L.createIndexResult, self._L.destroyIndexResult,
+                         starts, ends, (), np.int32)
+
+    def search_idxs_batch_csr(self, starts, ends):
+        return self._csr(self._L.searchIdxsBatch, self._L.createIndexResult, self._L.destroyIndexResult,
+                         starts, ends, (), np.int32)
+
+    def search_keys_batch_csr(self, starts, ends):
+        return self._csr(self._L.searchKeysBatch, self._L.createKeyResult, self._L.destroyKeyResult,
+                         starts, ends, (2,), np.int32)
+
+    # ---- batch queries: the reference's list forms (pyx:363-494) -----------------------------------
+    def count_batch(self, starts, ends):
+        return [int(c) for c in self.count_batch_np(starts, ends)]
+
+    def search_idxs_batch(self, starts, ends):
+        off, idx = self.search_idxs_batch_csr(starts, ends)
+        return [[int(i) for i in idx[int(off[q]):int(off[q + 1])]] for q in range(len(off) - 1)]
+
+    def search_values_batch(self, starts, ends):
+        off, idx = self.search_values_batch_csr(starts, ends)
+        vals = self._values
+        return [[vals[i] for i in idx[int(off[q]):int(off[q + 1])]] for q in range(len(off) - 1)]
