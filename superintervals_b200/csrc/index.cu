@@ -100,6 +100,7 @@ IndexView view_of(const siIndex* ix) {
     v.ends = ix->ends.as<int32_t>();
     v.values = ix->values.as<int32_t>();
     v.branch = ix->branch.as<uint32_t>();
+    v.pmax32 = ix->pmax32;
     v.n = ix->n;
     return v;
 }
@@ -161,6 +162,7 @@ int build_branch(siIndex* ix, cudaStream_t s) {
     for (int L = 0; L <= top; ++L) { t.M[L] = M[L]; t.n[L] = nl[L]; }
     t.P1 = P[1];
     t.top = top;
+    ix->pmax32 = P[1];   // kept for the query kernels' sweep termination
     int grid = grid_for(nl[1], BK_THREADS / 32, ix->sm_count * 16);
     SIB_LAUNCH(bk_branch_kernel, grid, BK_THREADS, 0, s, t, ix->n, ix->branch.as<uint32_t>());
     return 0;
@@ -233,7 +235,7 @@ void release_build_scratch(siIndex* ix) {
 }
 
 // Sort a query batch by end. Leaves the result described by SortedQueries.
-int sort_queries(siIndex* ix, const int32_t* d_qe, uint32_t nq, cudaStream_t s, SortedQueries* out) {
+int sort_queries(siIndex* ix, const int32_t* d_qe, uint32_t nq, cudaStream_t s, SortedQueries* out, bool may_reuse) {
     if (ix->q_kA.ensure((size_t)nq * 4) || ix->q_kB.ensure((size_t)nq * 4) || ix->q_vA.ensure((size_t)nq * 4) ||
         ix->q_vB.ensure((size_t)nq * 4) || ix->q_ws.ensure(rs_workspace_bytes<uint32_t>(nq)))
         return last_error_code();
@@ -243,7 +245,8 @@ int sort_queries(siIndex* ix, const int32_t* d_qe, uint32_t nq, cudaStream_t s, 
     out->permA = ix->q_vA.as<uint32_t>();
     out->permB = ix->q_vB.as<uint32_t>();
     out->sel = ws.final_sel;
-    if (ix->plan_valid && ix->plan_qe == d_qe && ix->plan_n == nq) return 0;   // reuse (count -> fill)
+    // fill may reuse the sort its preceding count made for the same batch (documented contract)
+    if (may_reuse && ix->plan_valid && ix->plan_qe == d_qe && ix->plan_n == nq) return 0;
     SIB_LAUNCH(qk_make_query_keys_kernel, grid_for(nq, QK_THREADS, ix->sm_count * 16), QK_THREADS, 0, s, d_qe, nq,
                ix->q_kA.as<uint32_t>(), ix->q_vA.as<uint32_t>());
     int rc = radix_sort_pairs<uint32_t>(ix->q_kA.as<uint32_t>(), ix->q_kB.as<uint32_t>(), ix->q_vA.as<uint32_t>(),
@@ -295,7 +298,7 @@ int count_impl(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, 
     SortedQueries sq;
     memset(&sq, 0, sizeof(sq));
     if (order == SI_ORDER_UNSORTED) {
-        int rc = sort_queries(ix, d_qe, nq, s, &sq);
+        int rc = sort_queries(ix, d_qe, nq, s, &sq, false);
         if (rc) return rc;
         SIB_LAUNCH((qk_count_kernel<CountT, true>), grid, QK_THREADS, 0, s, view_of(ix), d_qs, d_qe, sq, nq, d_counts);
     } else {
@@ -492,7 +495,7 @@ int siFillDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n
     memset(&sq, 0, sizeof(sq));
     const bool perm = order == SI_ORDER_UNSORTED;
     if (perm) {
-        int rc = sort_queries(ix, d_qe, nq, s, &sq);
+        int rc = sort_queries(ix, d_qe, nq, s, &sq, true);
         if (rc) return rc;
     }
 #define SIB_FILL(M)                                                                              \

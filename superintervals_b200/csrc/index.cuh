@@ -30,7 +30,8 @@ struct siIndex {
     uint32_t n = 0, n_padded = 0;
     bool built = false;
     sib::DevBuf starts, ends, values, branch, perm;
-    sib::DevBuf tree;          // 32-ary max tree levels + prefix-max levels (build only)
+    sib::DevBuf tree;          // 32-ary max tree levels + prefix-max levels
+    const int32_t* pmax32 = nullptr;   // inside `tree`: exclusive prefix max of ends per 32-block
 
     // ---- build scratch (released after build for large n) --------------------------
     sib::DevBuf b_in_s, b_in_e, b_in_v;        // staged host inputs

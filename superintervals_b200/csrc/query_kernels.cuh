@@ -32,6 +32,7 @@ struct IndexView {
     const int32_t* ends;     // padded to a multiple of 128 entries (pad = INT_MIN)
     const int32_t* values;
     const uint32_t* branch;  // NONE32 = no previous interval reaches this far
+    const int32_t* pmax32;   // pmax32[b] = max(ends[0 .. 32b-1]) (INT_MIN for b = 0), from build()
     uint32_t n;
 };
 
@@ -63,7 +64,76 @@ __device__ __forceinline__ bool keep_lane_phase(uint32_t active_mask, int iter) 
     return a > 16 || (a > 3 && iter < 48);
 }
 
+// branch[] entries as ordered keys: NONE32 ("nothing further back can reach") must win
+// a minimum, so shift by one: NONE32 -> 0, j -> j+1. min(key) - 1 is the jump target.
+__device__ __forceinline__ uint32_t jump_key(uint32_t br) { return br + 1u; }
+
+// One lane-parallel walk step over the aligned 4-block holding i (i != NONE32):
+// counts every hit in [base, i]; returns the next index to visit. When the block's
+// lowest interval misses, every miss m in the block rules out (branch[m], m), so the
+// walk may jump to the smallest of those branch targets.
+__device__ __forceinline__ uint32_t walk_step4(const IndexView& ix, uint32_t i, int32_t qs, uint32_t& c) {
+    const uint32_t base = i & ~3u;
+    const int4 e = ld_nc4(ix.ends + base);
+    const uint32_t k = i - base;   // intervals base .. base+k are at or below i
+    const bool hx = e.x >= qs, hy = e.y >= qs, hz = e.z >= qs, hw = e.w >= qs;
+    c += (hx ? 1u : 0u) + ((k >= 1u && hy) ? 1u : 0u) + ((k >= 2u && hz) ? 1u : 0u) + ((k >= 3u && hw) ? 1u : 0u);
+    if (hx) return base - 1u;      // base == 0 wraps to NONE32: walked off the front
+    const uint4 br = __ldg(reinterpret_cast<const uint4*>(ix.branch + base));
+    uint32_t key = jump_key(br.x);
+    if (k >= 1u && !hy) key = min(key, jump_key(br.y));
+    if (k >= 2u && !hz) key = min(key, jump_key(br.z));
+    if (k >= 3u && !hw) key = min(key, jump_key(br.w));
+    return key - 1u;
+}
+
+// Warp-cooperative walk of ONE query (warp-uniform bi, bqs): 32 lanes x 128-bit loads =
+// 128 ends per step, hits counted with ballot/popc. Returns the hit count.
+__device__ __forceinline__ uint32_t walk_warp128(const IndexView& ix, uint32_t bi, int32_t bqs, uint32_t lane) {
+    uint32_t bc = 0;
+    while (bi != NONE32) {
+        const uint32_t base = bi & ~127u;
+        const uint32_t j = base + lane * 4u;
+        const bool vx = j <= bi, vy = j + 1u <= bi, vz = j + 2u <= bi, vw = j + 3u <= bi;
+        int4 e = make_int4(0, 0, 0, 0);
+        if (vx) e = ld_nc4(ix.ends + j);
+        const bool hx = vx && e.x >= bqs, hy = vy && e.y >= bqs, hz = vz && e.z >= bqs, hw = vw && e.w >= bqs;
+        const uint32_t bx = __ballot_sync(FULL_MASK, hx);
+        bc += __popc(bx) + __popc(__ballot_sync(FULL_MASK, hy)) + __popc(__ballot_sync(FULL_MASK, hz)) +
+              __popc(__ballot_sync(FULL_MASK, hw));
+        if (bx & 1u) {             // lane 0's .x is the block's lowest interval: step below the block
+            bi = base - 1u;
+        } else {                   // smallest branch target over every miss in the block
+            uint32_t key = 0xFFFFFFFFu;
+            if (vx && !(hx && hy && hz && hw)) {
+                const uint4 br = __ldg(reinterpret_cast<const uint4*>(ix.branch + j));
+                if (!hx) key = jump_key(br.x);
+                if (vy && !hy) key = min(key, jump_key(br.y));
+                if (vz && !hz) key = min(key, jump_key(br.z));
+                if (vw && !hw) key = min(key, jump_key(br.w));
+            }
+            bi = __reduce_min_sync(FULL_MASK, key) - 1u;
+        }
+    }
+    return bc;
+}
+
+constexpr uint32_t QK_DENSE_SPAN = 256;      // max spread of upper bounds inside a tile for the sweep
+constexpr uint32_t QK_DENSE_MIN_HITS = 8;    // a 32-interval chunk must yield this many hits tile-wide
+constexpr int QK_DENSE_MAX_CHUNKS = 256;     // then the sparse tail goes to the branch walk
+
 // ---- count ---------------------------------------------------------------------------
+// One warp = one tile of 32 queries (sorted by end when the caller or the radix sort
+// made them so). Three stages:
+//   search  per-lane branch-free upper_bound; a sorted tile probes the same lines.
+//   sweep   the tile's queries overlap the same window of the index, so the warp
+//           streams that window ONCE, top-down, in 32-interval chunks (uniform 128-bit
+//           loads, every lane tests each end against its own query). This is the
+//           reference's linear SIMD block count (hpp:718-748) shared by 32 queries.
+//           It stops when the prefix maximum of ends says nothing further back can
+//           reach any query of the tile, or when chunks stop producing hits.
+//   walk    whatever remains (sparse, far-reaching containers) is finished by the
+//           branch-array walk: lane-parallel first, warp-cooperative for stragglers.
 // SORTED_VIA_PERM: queries were radix-sorted by qe (see SortedQueries); qs is gathered
 // through the permutation and the count is scattered back to the caller's order.
 template <typename CountT, bool SORTED_VIA_PERM>
@@ -76,7 +146,7 @@ qk_count_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* 
     const uint32_t lane = lane_id();
 
     uint32_t q = t;
-    int32_t qs = 0, qe = 0;
+    int32_t qs = INT_MAX, qe = 0;
     if (live) {
         if (SORTED_VIA_PERM) {
             const bool useB = *sq.sel != 0;
@@ -88,52 +158,79 @@ qk_count_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* 
         qs = ld_stream(qs_in + q);
     }
 
-    uint32_t i = NONE32;
-    if (live && ix.n) i = count_le(ix.starts, ix.n, qe) - 1u;   // 0 - 1 wraps to NONE32
-
+    // lim = number of intervals with start <= qe: candidates are [0, lim)
+    uint32_t lim = 0;
+    if (live && ix.n) lim = count_le(ix.starts, ix.n, qe);
     uint32_t c = 0;
-    // ---- phase A: lane-per-query, 4 intervals per step
+    uint32_t i = lim - 1u;                       // 0 - 1 wraps to NONE32
+
+    // ---- sweep
+    const uint32_t lim_max = __reduce_max_sync(FULL_MASK, lim);
+    if (lim_max == 0) {
+        if (live) counts[q] = (CountT)0;
+        return;
+    }
+    const uint32_t lim_min = __reduce_min_sync(FULL_MASK, lim ? lim : lim_max);   // idle lanes do not widen the span
+    if (lim_max - lim_min <= QK_DENSE_SPAN) {
+        const int32_t qs_min = __reduce_min_sync(FULL_MASK, lim ? qs : INT_MAX);
+        uint32_t pos = lim_max - 1u;             // inclusive top of the window, warp-uniform
+        int chunks = 0;
+        bool finished = false;
+        while (true) {
+            const uint32_t cb = pos & ~31u;
+            uint32_t hc = 0;
+            if (pos == cb + 31u && cb + 32u <= lim_min) {
+                // whole chunk lies below every lane's upper bound: no index masks
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int4 e = ld_nc4(ix.ends + cb + 4 * k);
+                    hc += (e.x >= qs ? 1u : 0u) + (e.y >= qs ? 1u : 0u) + (e.z >= qs ? 1u : 0u) + (e.w >= qs ? 1u : 0u);
+                }
+            } else {
+                const uint32_t top = min(lim, pos + 1u);   // this lane counts indices < top
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t j = cb + 4 * k;
+                    const int4 e = ld_nc4(ix.ends + j);    // padded to 128: in bounds
+                    hc += ((j < top && e.x >= qs) ? 1u : 0u) + ((j + 1u < top && e.y >= qs) ? 1u : 0u) +
+                          ((j + 2u < top && e.z >= qs) ? 1u : 0u) + ((j + 3u < top && e.w >= qs) ? 1u : 0u);
+                }
+            }
+            c += hc;
+            if (cb == 0) { finished = true; break; }
+            pos = cb - 1u;
+            if (ld_nc(ix.pmax32 + (cb >> 5)) < qs_min) { finished = true; break; }   // nothing below reaches the tile
+            ++chunks;
+            const uint32_t tot = __reduce_add_sync(FULL_MASK, hc);
+            if ((chunks >= 2 && tot < QK_DENSE_MIN_HITS) || chunks >= QK_DENSE_MAX_CHUNKS) break;
+        }
+        if (finished) {
+            if (live) counts[q] = (CountT)(lim ? c : 0u);   // lanes without candidates swept unmasked chunks
+            return;
+        }
+        // hand the rest to the walk: everything above pos is already counted
+        i = lim ? min(i, pos) : NONE32;
+        if (i != NONE32 && ld_nc(ix.pmax32 + ((pos + 1u) >> 5)) < qs) i = NONE32;
+    }
+
+    // ---- walk, lane-parallel: 4 intervals per step
     uint32_t active = __ballot_sync(FULL_MASK, i != NONE32);
     int iter = 0;
     while (keep_lane_phase(active, iter)) {
-        if (i != NONE32) {
-            const uint32_t base = i & ~3u;
-            const int4 e = ld_nc4(ix.ends + base);
-            const uint32_t k = i - base;   // elements base .. base+k are at or below i
-            c += (e.x >= qs) ? 1u : 0u;
-            c += (k >= 1u && e.y >= qs) ? 1u : 0u;
-            c += (k >= 2u && e.z >= qs) ? 1u : 0u;
-            c += (k >= 3u && e.w >= qs) ? 1u : 0u;
-            i = (e.x >= qs) ? base - 1u : ld_nc(ix.branch + base);   // base==0: wraps to NONE32
-        }
+        if (i != NONE32) i = walk_step4(ix, i, qs, c);
         active = __ballot_sync(FULL_MASK, i != NONE32);
         ++iter;
     }
-    // ---- phase B: stragglers, one query at a time across the whole warp
+    // ---- walk, warp-cooperative: stragglers one query at a time
     while (active) {
         const int src = __ffs(active) - 1;
         active &= active - 1;
-        uint32_t bi = __shfl_sync(FULL_MASK, i, src);
+        const uint32_t bi = __shfl_sync(FULL_MASK, i, src);
         const int32_t bqs = __shfl_sync(FULL_MASK, qs, src);
-        uint32_t bc = 0;
-        while (bi != NONE32) {
-            const uint32_t base = bi & ~127u;
-            const uint32_t j = base + lane * 4u;
-            int4 e = make_int4(INT_MIN, INT_MIN, INT_MIN, INT_MIN);
-            if (j <= bi) e = ld_nc4(ix.ends + j);
-            const bool hx = e.x >= bqs;                 // j <= bi whenever it was loaded
-            const bool hy = (j + 1u <= bi) && e.y >= bqs;
-            const bool hz = (j + 2u <= bi) && e.z >= bqs;
-            const bool hw = (j + 3u <= bi) && e.w >= bqs;
-            const uint32_t bx = __ballot_sync(FULL_MASK, hx);
-            bc += __popc(bx) + __popc(__ballot_sync(FULL_MASK, hy)) +
-                  __popc(__ballot_sync(FULL_MASK, hz)) + __popc(__ballot_sync(FULL_MASK, hw));
-            // lane 0's .x is the block's lowest interval
-            bi = (bx & 1u) ? base - 1u : ld_nc(ix.branch + base);
-        }
-        if ((int)lane == src) { c += bc; i = NONE32; }
+        const uint32_t bc = walk_warp128(ix, bi, bqs, lane);
+        if ((int)lane == src) c += bc;
     }
-    if (live) counts[q] = (CountT)c;
+    if (live) counts[q] = (CountT)(lim ? c : 0u);
 }
 
 // ---- has_overlaps: tests ONLY the last candidate (hpp:865-871, quirk Q1) ----------------
