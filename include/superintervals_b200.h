@@ -85,8 +85,8 @@ typedef struct {
 /* how the query arrays are ordered; results are always returned in the caller's order */
 enum {
     SI_ORDER_AUTO = 0,       /* check on device (one small host sync), sort if needed */
-    SI_ORDER_SORTED = 1,     /* caller guarantees ends are non-decreasing */
-    SI_ORDER_UNSORTED = 2,   /* radix-sort the batch by end on device, scatter results back */
+    SI_ORDER_SORTED = 1,     /* caller guarantees query STARTS are non-decreasing (position-sorted, as `bedtools sort`) */
+    SI_ORDER_UNSORTED = 2,   /* radix-sort the batch by start on device, scatter results back */
     SI_ORDER_ASIS = 3        /* process in the given order whatever it is */
 };
 enum { SI_FILL_VALUES = 0, SI_FILL_IDXS = 1, SI_FILL_KEYS = 2, SI_FILL_ITEMS = 3 };
@@ -119,7 +119,7 @@ int siScanDevice(siIndex* ix, const uint32_t* d_counts, size_t n, uint64_t* d_of
 /* CSR fill: for query i writes its hits to d_out[d_offsets[i] .. d_offsets[i+1]) in
  * descending position order. what = SI_FILL_*: int32 values, uint32 positions,
  * KeyPair, or Interval records. With SI_ORDER_UNSORTED the sort done by the
- * preceding siCountDevice call on the same (d_qe, n) is reused. */
+ * preceding siCountDevice call on the same (d_qs, n) is reused (do not modify the batch in between). */
 int siFillDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n,
                  const uint64_t* d_offsets, int what, void* d_out, int order, void* stream);
 /* count + clipped-length sum per query (c_superintervals.h:758-792). */

@@ -16,16 +16,20 @@ namespace sib {
 constexpr int BK_THREADS = 256;
 
 // ---- sortedness, as add() tracks it (hpp:96-101) ------------------------------------
-// flags bit0 = start_sorted, bit1 = end_sorted; caller initialises *flags = 3.
+// flags bit0 = start_sorted, bit1 = end_sorted, bit2 = every interval has start <= end;
+// caller initialises *flags = 7.
 __global__ void __launch_bounds__(BK_THREADS)
 bk_check_sorted_kernel(const int32_t* __restrict__ s, const int32_t* __restrict__ e, uint32_t n,
                        uint32_t* __restrict__ flags) {
     uint32_t bad = 0;
     const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
-    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x + 1; i < n; i += stride) {
-        int32_t s0 = s[i - 1], s1 = s[i];
+    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i < n; i += stride) {
+        const int32_t s1 = s[i], e1 = e[i];
+        if (s1 > e1) bad |= 4u;
+        if (i == 0) continue;
+        const int32_t s0 = s[i - 1];
         if (s1 < s0) bad |= 1u;
-        else if (s1 == s0 && e[i] > e[i - 1]) bad |= 2u;
+        else if (s1 == s0 && e1 > e[i - 1]) bad |= 2u;
     }
     bad = __reduce_or_sync(FULL_MASK, bad);
     if (lane_id() == 0 && bad) atomicAnd(flags, ~bad);

@@ -16,7 +16,7 @@
 #include <cstring>
 
 extern "C" int si_b200_upper_bound_(siIndex* ix, int32_t value, size_t* out);
-extern "C" int si_b200_resolve_order_(siIndex* ix, const int32_t* d_qe, size_t n, void* stream);
+extern "C" int si_b200_resolve_order_(siIndex* ix, const int32_t* d_qs, size_t n, void* stream);
 
 namespace {
 
@@ -72,7 +72,7 @@ int search_batch(Handle* h, const int32_t* qs, const int32_t* qe, size_t n, size
     const int32_t* dqs = ix->h_qs.as<int32_t>();
     const int32_t* dqe = ix->h_qe.as<int32_t>();
     // resolve the query order once so that count and fill agree and share one sort
-    const int order = si_b200_resolve_order_(ix, dqe, n, ix->own_stream);
+    const int order = si_b200_resolve_order_(ix, dqs, n, ix->own_stream);
     if (order < 0) return sib::last_error_code();
     rc = siCountDevice(ix, dqs, dqe, n, ix->h_counts.as<uint32_t>(), order, ix->own_stream);
     if (rc) return rc;

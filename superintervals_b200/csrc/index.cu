@@ -102,6 +102,7 @@ IndexView view_of(const siIndex* ix) {
     v.branch = ix->branch.as<uint32_t>();
     v.pmax32 = ix->pmax32;
     v.n = ix->n;
+    v.wellformed = ix->wellformed ? 1u : 0u;
     return v;
 }
 
@@ -188,14 +189,15 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
     const int cap = ix->sm_count * 16;
 
     // sortedness, as add() would have tracked it (hpp:96-101)
-    uint32_t three = 3;
+    uint32_t three = 7;
     SIB_CHECK(cudaMemcpyAsync(d_flags, &three, 4, cudaMemcpyHostToDevice, s));
     SIB_LAUNCH(bk_check_sorted_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, d_s, d_e, ix->n, d_flags);
     uint32_t flags = 0;
     SIB_CHECK(cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, s));
     SIB_CHECK(cudaStreamSynchronize(s));
 
-    if (flags == 3u) {
+    ix->wellformed = (flags & 4u) != 0;
+    if ((flags & 3u) == 3u) {
         // already (start asc, end desc): the reference does not sort (hpp:1416,1421)
         SIB_LAUNCH(bk_identity_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, d_s, d_e, d_v, ix->n,
                    ix->starts.as<int32_t>(), ix->ends.as<int32_t>(), ix->values.as<int32_t>(),
@@ -234,8 +236,8 @@ void release_build_scratch(siIndex* ix) {
     }
 }
 
-// Sort a query batch by end. Leaves the result described by SortedQueries.
-int sort_queries(siIndex* ix, const int32_t* d_qe, uint32_t nq, cudaStream_t s, SortedQueries* out, bool may_reuse) {
+// Sort a query batch by start (position order). Leaves the result described by SortedQueries.
+int sort_queries(siIndex* ix, const int32_t* d_qs, uint32_t nq, cudaStream_t s, SortedQueries* out, bool may_reuse) {
     if (ix->q_kA.ensure((size_t)nq * 4) || ix->q_kB.ensure((size_t)nq * 4) || ix->q_vA.ensure((size_t)nq * 4) ||
         ix->q_vB.ensure((size_t)nq * 4) || ix->q_ws.ensure(rs_workspace_bytes<uint32_t>(nq)))
         return last_error_code();
@@ -246,27 +248,27 @@ int sort_queries(siIndex* ix, const int32_t* d_qe, uint32_t nq, cudaStream_t s, 
     out->permB = ix->q_vB.as<uint32_t>();
     out->sel = ws.final_sel;
     // fill may reuse the sort its preceding count made for the same batch (documented contract)
-    if (may_reuse && ix->plan_valid && ix->plan_qe == d_qe && ix->plan_n == nq) return 0;
-    SIB_LAUNCH(qk_make_query_keys_kernel, grid_for(nq, QK_THREADS, ix->sm_count * 16), QK_THREADS, 0, s, d_qe, nq,
+    if (may_reuse && ix->plan_valid && ix->plan_qs == d_qs && ix->plan_n == nq) return 0;
+    SIB_LAUNCH(qk_make_query_keys_kernel, grid_for(nq, QK_THREADS, ix->sm_count * 16), QK_THREADS, 0, s, d_qs, nq,
                ix->q_kA.as<uint32_t>(), ix->q_vA.as<uint32_t>());
     int rc = radix_sort_pairs<uint32_t>(ix->q_kA.as<uint32_t>(), ix->q_kB.as<uint32_t>(), ix->q_vA.as<uint32_t>(),
                                         ix->q_vB.as<uint32_t>(), nq, 32, ix->q_ws.p, ix->sm_count, s);
     if (rc) return rc;
-    ix->plan_qe = d_qe;
+    ix->plan_qs = d_qs;
     ix->plan_n = nq;
     ix->plan_valid = true;
     return 0;
 }
 
 // Resolve SI_ORDER_AUTO with one device check. Returns <0 on error, else the order to use.
-int resolve_order(siIndex* ix, const int32_t* d_qe, uint32_t nq, int order, cudaStream_t s) {
+int resolve_order(siIndex* ix, const int32_t* d_qs, uint32_t nq, int order, cudaStream_t s) {
     if (order != SI_ORDER_AUTO) return order;
     if (nq < 4096) return SI_ORDER_ASIS;   // too small for a sort to pay
     if (ensure_small(ix)) return -1;
     uint32_t* d_flag = ix->small.as<uint32_t>() + 1;
     uint32_t one = 1, flag = 0;
     if (cudaMemcpyAsync(d_flag, &one, 4, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
-    qk_check_sorted_kernel<<<grid_for(nq, QK_THREADS, ix->sm_count * 16), QK_THREADS, 0, s>>>(d_qe, nq, d_flag);
+    qk_check_sorted_kernel<<<grid_for(nq, QK_THREADS, ix->sm_count * 16), QK_THREADS, 0, s>>>(d_qs, nq, d_flag);
     note_launch();
     if (cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(s) != cudaSuccess) return -1;
@@ -292,13 +294,13 @@ int count_impl(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, 
         SIB_CHECK(cudaMemsetAsync(d_counts, 0, n * sizeof(CountT), s));
         return 0;
     }
-    order = resolve_order(ix, d_qe, nq, order, s);
+    order = resolve_order(ix, d_qs, nq, order, s);
     if (order < 0) { set_error(cudaGetLastError(), "resolve_order", __FILE__, __LINE__); return last_error_code(); }
     const int grid = (int)(((uint64_t)nq + QK_THREADS - 1) / QK_THREADS);
     SortedQueries sq;
     memset(&sq, 0, sizeof(sq));
     if (order == SI_ORDER_UNSORTED) {
-        int rc = sort_queries(ix, d_qe, nq, s, &sq, false);
+        int rc = sort_queries(ix, d_qs, nq, s, &sq, false);
         if (rc) return rc;
         SIB_LAUNCH((qk_count_kernel<CountT, true>), grid, QK_THREADS, 0, s, view_of(ix), d_qs, d_qe, sq, nq, d_counts);
     } else {
@@ -489,13 +491,13 @@ int siFillDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n
     DeviceGuard g(ix->device);
     cudaStream_t s = pick_stream(ix, stream);
     const uint32_t nq = (uint32_t)n;
-    order = resolve_order(ix, d_qe, nq, order, s);
+    order = resolve_order(ix, d_qs, nq, order, s);
     if (order < 0) { set_error(cudaGetLastError(), "resolve_order", __FILE__, __LINE__); return last_error_code(); }
     SortedQueries sq;
     memset(&sq, 0, sizeof(sq));
     const bool perm = order == SI_ORDER_UNSORTED;
     if (perm) {
-        int rc = sort_queries(ix, d_qe, nq, s, &sq, true);
+        int rc = sort_queries(ix, d_qs, nq, s, &sq, true);
         if (rc) return rc;
     }
 #define SIB_FILL(M)                                                                              \
@@ -529,9 +531,9 @@ int siCoverageDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size
 }
 
 // used by c_abi.cu: resolve SI_ORDER_AUTO once for a count -> fill pair
-int si_b200_resolve_order_(siIndex* ix, const int32_t* d_qe, size_t n, void* stream) {
+int si_b200_resolve_order_(siIndex* ix, const int32_t* d_qs, size_t n, void* stream) {
     DeviceGuard g(ix->device);
-    int o = resolve_order(ix, d_qe, (uint32_t)n, SI_ORDER_AUTO, pick_stream(ix, stream));
+    int o = resolve_order(ix, d_qs, (uint32_t)n, SI_ORDER_AUTO, pick_stream(ix, stream));
     if (o < 0) set_error(cudaGetLastError(), "resolve_order", __FILE__, __LINE__);
     return o;
 }

@@ -29,6 +29,7 @@ struct siIndex {
     // ---- the index, position order -------------------------------------------------
     uint32_t n = 0, n_padded = 0;
     bool built = false;
+    bool wellformed = false;   // every interval has start <= end (enables the count shortcut)
     sib::DevBuf starts, ends, values, branch, perm;
     sib::DevBuf tree;          // 32-ary max tree levels + prefix-max levels
     const int32_t* pmax32 = nullptr;   // inside `tree`: exclusive prefix max of ends per 32-block
@@ -41,7 +42,7 @@ struct siIndex {
     sib::DevBuf small;                          // device scalars: [0] flags/sorted, ...
     sib::DevBuf q_kA, q_kB, q_vA, q_vB, q_ws;   // 32-bit key sort of a query batch
     sib::DevBuf scan_status;
-    const int32_t* plan_qe = nullptr;           // query batch the cached sort belongs to
+    const int32_t* plan_qs = nullptr;           // query batch the cached sort belongs to
     size_t plan_n = 0;
     bool plan_valid = false;
 

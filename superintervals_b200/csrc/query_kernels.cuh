@@ -34,10 +34,12 @@ struct IndexView {
     const uint32_t* branch;  // NONE32 = no previous interval reaches this far
     const int32_t* pmax32;   // pmax32[b] = max(ends[0 .. 32b-1]) (INT_MIN for b = 0), from build()
     uint32_t n;
+    uint32_t wellformed;     // 1 when every stored interval has start <= end (checked by build())
 };
 
-// A query batch radix-sorted by end: keys = flipped qe in sorted order, perm = original
-// query index. *sel (device) says which of the sort's two buffers holds the result.
+// A query batch radix-sorted by START (position order, what `bedtools sort` gives):
+// keys = flipped qs in sorted order, perm = original query index. *sel (device) says
+// which of the sort's two buffers holds the result.
 struct SortedQueries {
     const uint32_t* keysA;
     const uint32_t* keysB;
@@ -56,6 +58,17 @@ __device__ __forceinline__ uint32_t count_le(const int32_t* __restrict__ starts,
         len = half;
     }
     return pos + ((ld_nc(starts + pos) <= v) ? 1u : 0u);
+}
+
+// Number of starts < v (same search, strict comparison).
+__device__ __forceinline__ uint32_t count_lt(const int32_t* __restrict__ starts, uint32_t n, int32_t v) {
+    uint32_t pos = 0, len = n;
+    while (len > 1) {
+        const uint32_t half = len >> 1;
+        pos += (ld_nc(starts + pos + half) < v) ? (len - half) : 0u;
+        len = half;
+    }
+    return pos + ((ld_nc(starts + pos) < v) ? 1u : 0u);
 }
 
 // phase-A policy: keep walking lane-parallel while enough lanes are busy
@@ -123,9 +136,10 @@ constexpr uint32_t QK_DENSE_MIN_HITS = 8;    // a 32-interval chunk must yield t
 constexpr int QK_DENSE_MAX_CHUNKS = 256;     // then the sparse tail goes to the branch walk
 
 // ---- count ---------------------------------------------------------------------------
-// One warp = one tile of 32 queries (sorted by end when the caller or the radix sort
-// made them so). Three stages:
-//   search  per-lane branch-free upper_bound; a sorted tile probes the same lines.
+// One warp = one tile of 32 queries (position-sorted, i.e. by start, when the caller or
+// the radix sort made them so). Three stages:
+//   search  per-lane branch-free upper_bound(qe) (+ lower bound of qs on a well-formed
+//           index); a sorted tile probes the same lines.
 //   sweep   the tile's queries overlap the same window of the index, so the warp
 //           streams that window ONCE, top-down, in 32-interval chunks (uniform 128-bit
 //           loads, every lane tests each end against its own query). This is the
@@ -151,49 +165,59 @@ qk_count_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* 
         if (SORTED_VIA_PERM) {
             const bool useB = *sq.sel != 0;
             q = ld_stream((useB ? sq.permB : sq.permA) + t);
-            qe = unflip_i32(ld_stream((useB ? sq.keysB : sq.keysA) + t));
+            qs = unflip_i32(ld_stream((useB ? sq.keysB : sq.keysA) + t));
         } else {
-            qe = ld_stream(qe_in + t);
+            qs = ld_stream(qs_in + t);
         }
-        qs = ld_stream(qs_in + q);
+        qe = ld_stream(qe_in + q);
     }
 
-    // lim = number of intervals with start <= qe: candidates are [0, lim)
-    uint32_t lim = 0;
-    if (live && ix.n) lim = count_le(ix.starts, ix.n, qe);
-    uint32_t c = 0;
-    uint32_t i = lim - 1u;                       // 0 - 1 wraps to NONE32
+    // Candidates are the intervals [0, lim) with start <= qe. When every stored interval is
+    // well formed (start <= end), those with start >= qs overlap for certain (end >= start
+    // >= qs) -- the run the reference's count_large locates by search (hpp:834-847) --
+    // so only [0, top) with start < qs needs its ends tested.
+    uint32_t top = 0, c0 = 0;
+    if (live && ix.n) {
+        const uint32_t lim = count_le(ix.starts, ix.n, qe);
+        top = lim;
+        if (ix.wellformed) {
+            top = min(lim, count_lt(ix.starts, ix.n, qs));
+            c0 = lim - top;
+        }
+    }
+    uint32_t c = 0;                              // hits found below top
+    uint32_t i = top - 1u;                       // 0 - 1 wraps to NONE32
 
     // ---- sweep
-    const uint32_t lim_max = __reduce_max_sync(FULL_MASK, lim);
-    if (lim_max == 0) {
-        if (live) counts[q] = (CountT)0;
+    const uint32_t top_max = __reduce_max_sync(FULL_MASK, top);
+    if (top_max == 0) {
+        if (live) counts[q] = (CountT)c0;
         return;
     }
-    const uint32_t lim_min = __reduce_min_sync(FULL_MASK, lim ? lim : lim_max);   // idle lanes do not widen the span
-    if (lim_max - lim_min <= QK_DENSE_SPAN) {
-        const int32_t qs_min = __reduce_min_sync(FULL_MASK, lim ? qs : INT_MAX);
-        uint32_t pos = lim_max - 1u;             // inclusive top of the window, warp-uniform
+    const uint32_t top_min = __reduce_min_sync(FULL_MASK, top ? top : top_max);   // idle lanes do not widen the span
+    if (top_max - top_min <= QK_DENSE_SPAN) {
+        const int32_t qs_min = __reduce_min_sync(FULL_MASK, top ? qs : INT_MAX);
+        uint32_t pos = top_max - 1u;             // inclusive top of the window, warp-uniform
         int chunks = 0;
         bool finished = false;
         while (true) {
             const uint32_t cb = pos & ~31u;
             uint32_t hc = 0;
-            if (pos == cb + 31u && cb + 32u <= lim_min) {
-                // whole chunk lies below every lane's upper bound: no index masks
+            if (pos == cb + 31u && cb + 32u <= top_min) {
+                // whole chunk lies below every lane's limit: no index masks
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int4 e = ld_nc4(ix.ends + cb + 4 * k);
                     hc += (e.x >= qs ? 1u : 0u) + (e.y >= qs ? 1u : 0u) + (e.z >= qs ? 1u : 0u) + (e.w >= qs ? 1u : 0u);
                 }
             } else {
-                const uint32_t top = min(lim, pos + 1u);   // this lane counts indices < top
+                const uint32_t lt = min(top, pos + 1u);    // this lane counts indices < lt
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const uint32_t j = cb + 4 * k;
                     const int4 e = ld_nc4(ix.ends + j);    // padded to 128: in bounds
-                    hc += ((j < top && e.x >= qs) ? 1u : 0u) + ((j + 1u < top && e.y >= qs) ? 1u : 0u) +
-                          ((j + 2u < top && e.z >= qs) ? 1u : 0u) + ((j + 3u < top && e.w >= qs) ? 1u : 0u);
+                    hc += ((j < lt && e.x >= qs) ? 1u : 0u) + ((j + 1u < lt && e.y >= qs) ? 1u : 0u) +
+                          ((j + 2u < lt && e.z >= qs) ? 1u : 0u) + ((j + 3u < lt && e.w >= qs) ? 1u : 0u);
                 }
             }
             c += hc;
@@ -201,17 +225,19 @@ qk_count_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* 
             pos = cb - 1u;
             if (ld_nc(ix.pmax32 + (cb >> 5)) < qs_min) { finished = true; break; }   // nothing below reaches the tile
             ++chunks;
-            const uint32_t tot = __reduce_add_sync(FULL_MASK, hc);
+            const uint32_t tot = __reduce_add_sync(FULL_MASK, top ? hc : 0u);
             if ((chunks >= 2 && tot < QK_DENSE_MIN_HITS) || chunks >= QK_DENSE_MAX_CHUNKS) break;
         }
         if (finished) {
-            if (live) counts[q] = (CountT)(lim ? c : 0u);   // lanes without candidates swept unmasked chunks
+            // lanes with top == 0 swept unmasked chunks: their c is meaningless
+            if (live) counts[q] = (CountT)(c0 + (top ? c : 0u));
             return;
         }
         // hand the rest to the walk: everything above pos is already counted
-        i = lim ? min(i, pos) : NONE32;
+        i = top ? min(i, pos) : NONE32;
         if (i != NONE32 && ld_nc(ix.pmax32 + ((pos + 1u) >> 5)) < qs) i = NONE32;
     }
+    if (top == 0) c = 0;
 
     // ---- walk, lane-parallel: 4 intervals per step
     uint32_t active = __ballot_sync(FULL_MASK, i != NONE32);
@@ -230,7 +256,7 @@ qk_count_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* 
         const uint32_t bc = walk_warp128(ix, bi, bqs, lane);
         if ((int)lane == src) c += bc;
     }
-    if (live) counts[q] = (CountT)(lim ? c : 0u);
+    if (live) counts[q] = (CountT)(c0 + c);
 }
 
 // ---- has_overlaps: tests ONLY the last candidate (hpp:865-871, quirk Q1) ----------------
@@ -330,11 +356,11 @@ qk_fill_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* _
         if (SORTED_VIA_PERM) {
             const bool useB = *sq.sel != 0;
             q = ld_stream((useB ? sq.permB : sq.permA) + t);
-            qe = unflip_i32(ld_stream((useB ? sq.keysB : sq.keysA) + t));
+            qs = unflip_i32(ld_stream((useB ? sq.keysB : sq.keysA) + t));
         } else {
-            qe = ld_stream(qe_in + t);
+            qs = ld_stream(qs_in + t);
         }
-        qs = ld_stream(qs_in + q);
+        qe = ld_stream(qe_in + q);
         o = ld_stream(offsets + q);
         o_end = ld_stream(offsets + q + 1);
     }
@@ -484,7 +510,7 @@ qk_scan_kernel(const uint32_t* __restrict__ counts, uint32_t nq, uint64_t* __res
 }
 
 // ---- query ordering helpers --------------------------------------------------------------
-// *flag (init 1) is cleared when qe is not non-decreasing.
+// *flag (init 1) is cleared when the query starts are not non-decreasing.
 __global__ void __launch_bounds__(QK_THREADS)
 qk_check_sorted_kernel(const int32_t* __restrict__ qe, uint32_t nq, uint32_t* __restrict__ flag) {
     uint32_t bad = 0;

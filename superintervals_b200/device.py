@@ -131,7 +131,7 @@ class DeviceIndex:
         _chk_i32(qs, "qs"); _chk_i32(qe, "qe")
         n = qs.numel()
         if order == ORDER_AUTO and n:
-            order = ORDER_SORTED if bool((qe[1:] >= qe[:-1]).all()) else ORDER_UNSORTED
+            order = ORDER_SORTED if bool((qs[1:] >= qs[:-1]).all()) else ORDER_UNSORTED
         counts = self.count(qs, qe, out=counts, order=order)
         offsets = self.scan(counts, out=offsets)
         width = {FILL_VALUES: 1, FILL_IDXS: 1, FILL_KEYS: 2, FILL_ITEMS: 3}[what]

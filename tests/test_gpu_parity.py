@@ -73,7 +73,7 @@ def test_build_matches_oracle(kind, n, nq, seed, presorted):
 def test_count_and_search_match_oracle(kind, n, nq, seed, sort_queries):
     s, e, qs, qe = _mk(kind, n, nq, seed)
     if sort_queries:
-        order = np.argsort(qe, kind="stable")
+        order = np.argsort(qs, kind="stable")
         qs, qe = qs[order], qe[order]
     o = Oracle(s, e)
     m = _imap(s, e)

@@ -66,7 +66,7 @@ for label, gen in {"C1 1M x 1M": lambda: W.config1(1_000_000, 0),
     ix = DeviceIndex()
     tb = timeit(lambda: ix.build(ds, de), reps=3)
     dqs, dqe = torch.from_numpy(qs).cuda(), torch.from_numpy(qe).cuda()
-    order = torch.argsort(dqe, stable=True)
+    order = torch.argsort(dqs, stable=True)
     sqs, sqe = dqs[order].contiguous(), dqe[order].contiguous()
     out = torch.empty_like(dqs)
     t_sorted = timeit(lambda: ix.count(sqs, sqe, out=out, order=ORDER_SORTED))

@@ -16,7 +16,7 @@ gen = {"c1": lambda: W.config1(1_000_000, 0),
 s, e, qs, qe = gen()
 ix = DeviceIndex().build(torch.from_numpy(s).cuda(), torch.from_numpy(e).cuda())
 dqs, dqe = torch.from_numpy(qs).cuda(), torch.from_numpy(qe).cuda()
-order = torch.argsort(dqe, stable=True)
+order = torch.argsort(dqs, stable=True)
 sqs, sqe = dqs[order].contiguous(), dqe[order].contiguous()
 out = torch.empty_like(sqs)
 for _ in range(reps):
