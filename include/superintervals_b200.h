@@ -112,6 +112,11 @@ int siCountDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t 
                   uint32_t* d_counts, int order, void* stream);
 int siCountDevice64(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n,
                     uint64_t* d_counts, int order, void* stream);
+/* Optional explicit first half of an SI_ORDER_UNSORTED count: radix-sort the batch by
+ * start now; the NEXT siCountDevice(.., SI_ORDER_UNSORTED, ..) on the same (d_qs, n)
+ * consumes that sort instead of redoing it (one-shot). Lets callers overlap or time
+ * the two phases separately. */
+int siSortQueriesDevice(siIndex* ix, const int32_t* d_qs, size_t n, void* stream);
 int siAnyDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n,
                 uint8_t* d_out, void* stream);
 /* d_offsets[0..n]: exclusive scan of d_counts, d_offsets[n] = total hits. 16-byte aligned pointers. */

@@ -77,7 +77,7 @@ B200_SYMBOLS = [
     "countOverlapsBatch", "anyOverlapsBatch", "searchValuesBatch", "searchIdxsBatch", "searchKeysBatch",
     "searchItemsBatch", "coverageBatch", "siIndexCreate", "siIndexDestroy", "siIndexOf", "siIndexSize",
     "siIndexDeviceView", "siIndexBuildHost", "siIndexBuildDevice", "siIndexExport", "siCountDevice",
-    "siCountDevice64", "siAnyDevice", "siScanDevice", "siFillDevice", "siCoverageDevice",
+    "siCountDevice64", "siSortQueriesDevice", "siAnyDevice", "siScanDevice", "siFillDevice", "siCoverageDevice",
     "siIndexDeviceBytes",
 ]
 
@@ -158,6 +158,7 @@ def bind_b200(L):
     L.siIndexExport.argtypes = [vp, vp, vp, vp, vp, vp]
     L.siCountDevice.argtypes = [vp, vp, vp, sz, vp, C.c_int, vp]
     L.siCountDevice64.argtypes = [vp, vp, vp, sz, vp, C.c_int, vp]
+    L.siSortQueriesDevice.argtypes = [vp, vp, sz, vp]
     L.siAnyDevice.argtypes = [vp, vp, vp, sz, vp, vp]
     L.siScanDevice.argtypes = [vp, vp, sz, vp, vp]
     L.siFillDevice.argtypes = [vp, vp, vp, sz, vp, C.c_int, vp, C.c_int, vp]

@@ -300,7 +300,9 @@ int count_impl(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, 
     SortedQueries sq;
     memset(&sq, 0, sizeof(sq));
     if (order == SI_ORDER_UNSORTED) {
-        int rc = sort_queries(ix, d_qs, nq, s, &sq, false);
+        // an explicit siSortQueriesDevice() on this batch arms a one-shot reuse; otherwise sort now
+        int rc = sort_queries(ix, d_qs, nq, s, &sq, ix->plan_armed);
+        ix->plan_armed = false;
         if (rc) return rc;
         SIB_LAUNCH((qk_count_kernel<CountT, true>), grid, QK_THREADS, 0, s, view_of(ix), d_qs, d_qe, sq, nq, d_counts);
     } else {
@@ -441,6 +443,17 @@ int siCountDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t 
 int siCountDevice64(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, uint64_t* d_counts, int order,
                     void* stream) {
     return count_impl<uint64_t>(ix, d_qs, d_qe, n, d_counts, order, stream);
+}
+
+int siSortQueriesDevice(siIndex* ix, const int32_t* d_qs, size_t n, void* stream) {
+    if (!ix) return cudaErrorInvalidValue;
+    if (n == 0) return 0;
+    if (n > 0xFFFFFFFFull) return cudaErrorInvalidValue;
+    DeviceGuard g(ix->device);
+    SortedQueries sq;
+    int rc = sort_queries(ix, d_qs, (uint32_t)n, pick_stream(ix, stream), &sq, false);
+    ix->plan_armed = rc == 0;
+    return rc;
 }
 
 int siAnyDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, uint8_t* d_out, void* stream) {

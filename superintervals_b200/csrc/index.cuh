@@ -45,6 +45,7 @@ struct siIndex {
     const int32_t* plan_qs = nullptr;           // query batch the cached sort belongs to
     size_t plan_n = 0;
     bool plan_valid = false;
+    bool plan_armed = false;                    // set by siSortQueriesDevice: next count may reuse
 
     // ---- staging for the host-buffer API ---------------------------------------------
     sib::DevBuf h_qs, h_qe, h_counts, h_offsets, h_out, h_cov;

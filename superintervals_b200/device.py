@@ -107,6 +107,12 @@ class DeviceIndex:
         _lib.check("siCountDevice")
         return out
 
+    def sort_queries(self, qs):
+        """Explicit first half of an ORDER_UNSORTED count (see siSortQueriesDevice)."""
+        _chk_i32(qs, "qs")
+        self._L.siSortQueriesDevice(self._ix, qs.data_ptr(), qs.numel(), _stream())
+        _lib.check("siSortQueriesDevice")
+
     def has_overlaps(self, qs, qe):
         _chk_i32(qs, "qs"); _chk_i32(qe, "qe")
         out = torch.empty(qs.numel(), dtype=torch.uint8, device=qs.device)

@@ -60,14 +60,28 @@ def _log_uniform(rng, lo, hi, size):
     return np.exp(rng.uniform(np.log(lo), np.log(hi), size)).astype(np.int64)
 
 
-def config2(n=10_000_000, nq=100_000_000, seed=2, axis=CHR1_LEN):
-    """Read-length intervals x range queries on one 250 Mb axis (count only)."""
-    rng = np.random.default_rng(seed)
+def config2_intervals(n=10_000_000, seed=2, axis=CHR1_LEN):
+    """Read-length intervals: length log-uniform[150, 10 kb], start uniform on the axis."""
+    rng = np.random.default_rng([seed, 0])
     ln = np.clip(_log_uniform(rng, 150, 10_000, n), 150, 10_000)
     s = (rng.random(n) * (axis - ln)).astype(np.int64)
+    return _i32(s), _i32(s + ln - 1)
+
+
+def config2_queries(nq=100_000_000, seed=2, axis=CHR1_LEN, shard=0):
+    """Range queries: length log-uniform[1, 10 kb]. `shard` selects an independent stream
+    (one per rank under weak scaling)."""
+    rng = np.random.default_rng([seed, 1, shard])
     lq = np.clip(_log_uniform(rng, 1, 10_000, nq), 1, 10_000)
     q = (rng.random(nq) * (axis - lq)).astype(np.int64)
-    return _i32(s), _i32(s + ln - 1), _i32(q), _i32(q + lq - 1)
+    return _i32(q), _i32(q + lq - 1)
+
+
+def config2(n=10_000_000, nq=100_000_000, seed=2, axis=CHR1_LEN):
+    """Read-length intervals x range queries on one 250 Mb axis (count only)."""
+    s, e = config2_intervals(n, seed, axis)
+    qs, qe = config2_queries(nq, seed, axis)
+    return s, e, qs, qe
 
 
 def _pareto_len(rng, size, xmin=50, alpha=1.1, cap=1_000_000):

@@ -1,0 +1,172 @@
+"""GPU: the C ABI as a drop-in -- golden fixtures from the real reference, the reference's
+unit-test vectors through the single-query entry points, and the same ctypes driver run
+against the reference's own C library (oracle/_ref/libsi_cref.so) and ours."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from helpers import canonical_values, golden_files, load_vectors
+from superintervals_b200 import IntervalMap, _lib
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("path", golden_files("presorted"), ids=lambda p: p.split("/")[-1])
+def test_golden_presorted_bit_exact(path):
+    g = np.load(path)
+    m = IntervalMap.from_arrays(g["in_starts"], g["in_ends"])
+    assert np.array_equal(m.starts, g["starts"]) and np.array_equal(m.ends, g["ends"])
+    assert np.array_equal(m.data_index, g["data"]) and np.array_equal(m.branch, g["branch"])
+    qs, qe = g["qs"], g["qe"]
+    assert np.array_equal(m.count_batch_np(qs, qe), g["count"])
+    assert np.array_equal(m.has_overlaps_batch(qs, qe), g["has_overlaps"])
+    off, vals = m.search_values_batch_csr(qs, qe)
+    assert np.array_equal(off, g["offsets"]) and np.array_equal(vals, g["values"])
+    assert np.array_equal(vals, g["values_large"])           # search_values_large: same output (hpp:588)
+    off, keys = m.search_keys_batch_csr(qs, qe)
+    assert np.array_equal(off, g["offsets"]) and np.array_equal(keys, g["keys"])
+    off, idx = m.search_idxs_batch_csr(qs, qe)
+    for q in range(len(qs)):                                  # same set as the C++ overload (Q2 reorders it)
+        a, b = int(off[q]), int(off[q + 1])
+        assert np.array_equal(np.sort(idx[a:b]), np.sort(g["idxs_cpp"][a:b].astype(np.int64)))
+    cnt, cov = m.coverage_batch(qs, qe)
+    assert np.array_equal(cnt, g["cov_count"]) and np.array_equal(cov, g["cov_sum"])
+
+
+@pytest.mark.parametrize("path", golden_files("shuffled"), ids=lambda p: p.split("/")[-1])
+def test_golden_shuffled(path):
+    g = np.load(path)
+    m = IntervalMap.from_arrays(g["in_starts"], g["in_ends"])
+    assert np.array_equal(m.starts, g["starts"]) and np.array_equal(m.ends, g["ends"])
+    assert np.array_equal(m.branch, g["branch"])
+    assert np.array_equal(m.count_batch_np(g["qs"], g["qe"]), g["count"])
+    off, vals = m.search_values_batch_csr(g["qs"], g["qe"])
+    _, keys = m.search_keys_batch_csr(g["qs"], g["qe"])
+    assert np.array_equal(off, g["offsets"]) and np.array_equal(keys, g["keys"])
+    assert np.array_equal(canonical_values(off, vals, keys), canonical_values(g["offsets"], g["values"], g["keys"]))
+
+
+def _drive(L, case):
+    """Run one tests.cpp-style case through a library exporting the reference C ABI. Returns a
+    transcript that must be identical for the reference's library and ours."""
+    si = L.createSuperIntervals()
+    out = []
+    for s, e, d in case["intervals"]:
+        L.addInterval(si, s, e, d)
+    L.indexSuperIntervals(si)
+    c = si.contents
+    out.append(("size", int(L.sizeSuperIntervals(si))))
+    out.append(("sorted", [(c.starts[i], c.ends[i], c.data[i]) for i in range(c.size)]))
+    if c.size:
+        out.append(("branch", [int(c.branch[i]) for i in range(c.size)]))
+    qlist = [tuple(q["q"]) for q in case.get("queries", [])]
+    if "batch" in case:
+        qlist += list(zip(case["batch"]["starts"], case["batch"]["ends"]))
+    for s, e in qlist:
+        out.append(("any", bool(L.anyOverlaps(si, s, e))))
+        out.append(("count", int(L.countOverlaps(si, s, e))))
+        out.append(("ub", int(L.upperBound(si, e)), int(c.idx)))
+        r = L.createIndexResult()
+        L.searchValues(si, s, e, C.byref(r))
+        out.append(("values", [r.data[i] for i in range(r.size)]))
+        L.searchValues(si, s, e, C.byref(r))                  # appends (ref c.h:209)
+        out.append(("values_appended", int(r.size)))
+        L.clearIndexResult(C.byref(r))
+        L.searchIdxs(si, s, e, C.byref(r))
+        out.append(("idxs", [r.data[i] for i in range(r.size)]))
+        L.clearIndexResult(C.byref(r))
+        L.searchPoint(si, s, C.byref(r))
+        out.append(("point", [r.data[i] for i in range(r.size)]))
+        L.destroyIndexResult(C.byref(r))
+        k = L.createKeyResult()
+        L.searchKeys(si, s, e, C.byref(k))
+        out.append(("keys", [(k.data[i].start, k.data[i].end) for i in range(k.size)]))
+        L.destroyKeyResult(C.byref(k))
+        it = L.createItemResult()
+        L.searchItems(si, s, e, C.byref(it))
+        out.append(("items", [(it.data[i].start, it.data[i].end, it.data[i].data) for i in range(it.size)]))
+        L.destroyItemResult(C.byref(it))
+        cnt, cov = C.c_size_t(0), C.c_int32(0)
+        L.coverage(si, s, e, C.byref(cnt), C.byref(cov))
+        out.append(("coverage", int(cnt.value), int(cov.value)))
+        buf = (C.c_int32 * 64)()
+        nfound = C.c_size_t(0)
+        L.findOverlaps(si, s, e, buf, C.byref(nfound))
+        out.append(("find", [buf[i] for i in range(nfound.value)]))
+    L.destroySuperIntervals(si)
+    return out
+
+
+@pytest.mark.parametrize("case", load_vectors(), ids=lambda c: c["name"].split(" (")[0])
+def test_reference_unit_vectors_through_c_abi(case):
+    L = _lib.lib()
+    L.si_b200_clear_error()
+    t = dict((x[0] + str(i), x[1:]) for i, x in enumerate(_drive(L, case)))
+    _lib.check(case["name"])
+    got = _drive(L, case)
+    it = iter(got[3:] if case["intervals"] else got[2:])
+    for q in case.get("queries", []):
+        rec = {}
+        for _ in range(11):
+            x = next(it)
+            rec[x[0]] = x[1:] if len(x) > 2 else x[1]
+        op = q["op"]
+        if op == "count": assert rec["count"] == q["expect"]
+        if op == "has_overlaps": assert rec["any"] == q["expect"]
+        if op == "search_values":
+            if "expect" in q: assert rec["values"] == q["expect"]
+            if "expect_size" in q: assert len(rec["values"]) == q["expect_size"] and rec["values_appended"] == 2 * q["expect_size"]
+            if "expect_last" in q: assert rec["values"][-1] == q["expect_last"]
+            assert rec["find"] == rec["values"]
+        if op == "search_idxs": assert rec["idxs"] == q["expect"]
+        if op == "search_keys": assert [list(k) for k in rec["keys"]] == q["expect"]
+        if op == "search_items": assert [list(k) for k in rec["items"]] == q["expect"]
+        if op == "coverage":
+            if "expect_count" in q: assert rec["coverage"][0] == q["expect_count"]
+            assert rec["coverage"][1] == q["expect_sum"]
+    if "expect_branch" in case:
+        want = [(1 << 64) - 1 if v < 0 else v for v in case["expect_branch"]]
+        assert got[2][1] == want
+    del t
+
+
+CREF = os.path.join(ROOT, "oracle", "_ref", "libsi_cref.so")
+
+
+@pytest.mark.skipif(not os.path.exists(CREF), reason="reference C library not built")
+@pytest.mark.parametrize("case", [c for c in load_vectors() if c["intervals"]], ids=lambda c: c["name"].split(" (")[0])
+def test_same_driver_reference_c_library_vs_ours(case):
+    """The identical ctypes transcript from the reference's compiled c_superintervals.h and from
+    libsuperintervals_b200.so (tie order: these cases are inserted pre-sorted or tie-free except
+    'duplicates', whose equal keys keep insertion order under glibc qsort's merge sort too)."""
+    ref = _lib.bind(C.CDLL(CREF))
+    ours = _lib.lib()
+    assert _drive(ref, case) == _drive(ours, case)
+
+
+def test_python_doc_example():
+    """src/superintervals/README.md:16-26 -- values ride as payload objects on the host."""
+    m = IntervalMap.from_arrays([10, 15, 30], [20, 25, 40], ["A", "B", "C"])
+    assert m.count_batch(np.array([5, 18, 35], np.int32), np.array([12, 22, 45], np.int32)) == [1, 2, 1]
+    assert m.search_values_batch(np.array([5, 18, 35], np.int32), np.array([12, 22, 45], np.int32)) == [["A"], ["B", "A"], ["C"]]
+    assert m.search_idxs_batch(np.array([5, 18, 35], np.int32), np.array([12, 22, 45], np.int32)) == [[0], [1, 0], [2]]
+    assert m.search_values(8, 20) == ["B", "A"] and m.count(8, 20) == 2 and m.has_overlaps(8, 20)
+    assert m.search_keys(8, 20) == [(15, 25), (10, 20)] and m.search_items(31, 31) == [(30, 40, "C")]
+    assert m.coverage(12, 18) == (2, 9) and m.at(1) == (15, 25, "B")
+
+
+def test_rebuild_after_adding_and_clear():
+    m = IntervalMap()
+    for i in range(50):
+        m.add(100 - i, 200 - i, i)                         # reverse order: forces the device sort
+    m.build()
+    assert m.count(0, 1000) == 50 and m.starts.tolist() == sorted(m.starts.tolist())
+    m.add(500, 600, "late")
+    m.build()
+    assert m.count(550, 560) == 1 and m.search_values(550, 560) == ["late"] and m.count(0, 1000) == 51
+    m.clear()
+    m.build()
+    assert m.count(0, 1000) == 0 and not m.has_overlaps(0, 1000)

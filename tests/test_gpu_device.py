@@ -1,0 +1,143 @@
+"""GPU: the device-resident core (raw pointers + stream) -- order modes, the explicit
+sort/count split, CSR scan, and full-size runs checked through size-independent properties."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.pyoracle import Oracle
+from superintervals_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _u32(t):
+    return t.cpu().numpy().astype(np.uint32).astype(np.uint64)
+
+
+@pytest.fixture(scope="module")
+def c3():
+    from superintervals_b200.device import DeviceIndex
+    s, e, qs, qe = W.config3(300_000, 200_000, 42, axis=20_000_000)
+    return s, e, qs, qe, DeviceIndex().build(_dev(s), _dev(e)), Oracle(s, e)
+
+
+def test_every_order_mode_gives_the_callers_order(c3):
+    from superintervals_b200.device import ORDER_ASIS, ORDER_AUTO, ORDER_SORTED, ORDER_UNSORTED
+    s, e, qs, qe, ix, orc = c3
+    want = orc.count_batch(qs, qe)
+    dqs, dqe = _dev(qs), _dev(qe)
+    for order in (ORDER_AUTO, ORDER_UNSORTED, ORDER_ASIS):
+        assert np.array_equal(_u32(ix.count(dqs, dqe, order=order)), want), order
+    ix.sort_queries(dqs)                                     # explicit two-phase form
+    assert np.array_equal(_u32(ix.count(dqs, dqe, order=ORDER_UNSORTED)), want)
+    o = np.argsort(qs, kind="stable")
+    assert np.array_equal(_u32(ix.count(_dev(qs[o]), _dev(qe[o]), order=ORDER_SORTED)), want[o])
+
+
+def test_unsorted_count_resorts_when_the_batch_changes_in_place(c3):
+    from superintervals_b200.device import ORDER_UNSORTED
+    s, e, qs, qe, ix, orc = c3
+    dqs, dqe = _dev(qs[:50_000]), _dev(qe[:50_000])
+    assert np.array_equal(_u32(ix.count(dqs, dqe, order=ORDER_UNSORTED)), orc.count_batch(qs[:50_000], qe[:50_000]))
+    dqs.copy_(_dev(qs[50_000:100_000])); dqe.copy_(_dev(qe[50_000:100_000]))   # same pointers, new contents
+    assert np.array_equal(_u32(ix.count(dqs, dqe, order=ORDER_UNSORTED)),
+                          orc.count_batch(qs[50_000:100_000], qe[50_000:100_000]))
+
+
+def test_search_csr_on_device(c3):
+    from superintervals_b200._lib import FILL_ITEMS
+    s, e, qs, qe, ix, orc = c3
+    off_o, res = orc.search_batch(qs, qe, want=("values", "idxs", "keys"))
+    dqs, dqe = _dev(qs), _dev(qe)
+    off, vals = ix.search_values(dqs, dqe)
+    assert np.array_equal(off.cpu().numpy().astype(np.uint64), off_o)
+    assert np.array_equal(vals.cpu().numpy(), res["values"])
+    _, idx = ix.search_idxs(dqs, dqe)
+    assert np.array_equal(idx.cpu().numpy().astype(np.uint32), res["idxs"])
+    _, keys = ix.search_keys(dqs, dqe)
+    assert np.array_equal(keys.cpu().numpy(), res["keys"])
+    _, items = ix.search(dqs, dqe, FILL_ITEMS)
+    assert np.array_equal(items.cpu().numpy()[:, :2], res["keys"]) and np.array_equal(items.cpu().numpy()[:, 2], res["values"])
+    cnt, cov = ix.coverage(dqs, dqe)
+    assert np.array_equal(_u32(cnt), orc.count_batch(qs, qe))
+    assert np.array_equal(ix.has_overlaps(dqs, dqe).cpu().numpy(), orc.has_overlaps_batch(qs, qe))
+
+
+def test_scan_matches_cumsum_at_awkward_sizes():
+    from superintervals_b200.device import DeviceIndex
+    ix = DeviceIndex()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for n in (1, 15, 16, 17, 4095, 4096, 4097, 1_000_003):
+        c = torch.randint(0, 1 << 20, (n,), device="cuda", dtype=torch.int32, generator=g)
+        off = ix.scan(c)
+        want = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+        want[1:] = torch.cumsum(c.to(torch.int64), 0)
+        assert torch.equal(off, want), n
+
+
+def test_malformed_intervals_disable_the_shortcut_but_stay_exact():
+    """start > end is accepted by the reference (Q6); the walk definition still holds verbatim."""
+    from superintervals_b200.device import DeviceIndex
+    rng = np.random.default_rng(5)
+    n, nq = 40_000, 60_000
+    s = rng.integers(0, 1_000_000, n).astype(np.int32)
+    e = (s + rng.integers(-300, 3000, n)).astype(np.int32)
+    qs = rng.integers(0, 1_000_000, nq).astype(np.int32)
+    qe = (qs + rng.integers(-50, 4000, nq)).astype(np.int32)
+    orc = Oracle(s, e)
+    ix = DeviceIndex().build(_dev(s), _dev(e))
+    assert np.array_equal(_u32(ix.count(_dev(qs), _dev(qe))), orc.count_batch(qs, qe))
+    off_o, res = orc.search_batch(qs, qe)
+    off, vals = ix.search_values(_dev(qs), _dev(qe))
+    assert np.array_equal(off.cpu().numpy().astype(np.uint64), off_o) and np.array_equal(vals.cpu().numpy(), res["values"])
+
+
+def test_build_export_roundtrip_and_idempotence():
+    from superintervals_b200.device import DeviceIndex
+    s, e, _, _ = W.config2(200_000, 10, 3, axis=5_000_000)
+    ix = DeviceIndex().build(_dev(s), _dev(e))
+    s1, e1, v1, b1, p1 = ix.export()
+    assert np.array_equal(s1, s[p1]) and np.array_equal(e1, e[p1]) and np.array_equal(v1.astype(np.uint32), p1)
+    k = s1.astype(np.int64) * (1 << 32) - e1.astype(np.int64)
+    assert (np.diff(k) >= 0).all()                               # (start asc, end desc)
+    ix2 = DeviceIndex().build(_dev(s1), _dev(e1))                # rebuilding a built index changes nothing
+    s2, e2, _, b2, p2 = ix2.export()
+    assert np.array_equal(s2, s1) and np.array_equal(e2, e1) and np.array_equal(b2, b1)
+    assert np.array_equal(p2, np.arange(len(s), dtype=np.uint32))
+    assert np.array_equal(b1, Oracle(s, e).branch)
+
+
+@pytest.mark.parametrize("nq", [20_000_000])
+def test_full_size_c2_properties(nq):
+    """BASELINE configs[1] at full index size: 10M intervals. Checked without the oracle's
+    per-query walk: closed-form rank count on GPU, invariance under query order, oracle on a sample."""
+    from superintervals_b200.device import DeviceIndex, ORDER_SORTED, ORDER_UNSORTED
+    s, e = W.config2_intervals(10_000_000, 2)
+    qs, qe = W.config2_queries(nq, 2)
+    ds, de, dqs, dqe = _dev(s), _dev(e), _dev(qs), _dev(qe)
+    ix = DeviceIndex().build(ds, de)
+    c = ix.count(dqs, dqe, order=ORDER_UNSORTED)
+    # closed form (well-formed data): #{starts <= qe} - #{ends < qs}
+    ss, se = torch.sort(ds)[0], torch.sort(de)[0]
+    want = torch.searchsorted(ss, dqe, right=True) - torch.searchsorted(se, dqs, right=False)
+    assert torch.equal(c.to(torch.int64), want.to(torch.int64))
+    # sorted order gives the same multiset, position by position after permuting
+    o = torch.argsort(dqs, stable=True)
+    c2 = ix.count(dqs[o].contiguous(), dqe[o].contiguous(), order=ORDER_SORTED)
+    assert torch.equal(c2, c[o])
+    # oracle on a sample + index structure on the whole build
+    orc = Oracle(s, e)
+    m = 100_000
+    assert np.array_equal(_u32(c[:m]), orc.count_batch(qs[:m], qe[:m]))
+    s1, e1, _, b1, _ = ix.export()
+    assert np.array_equal(s1, orc.starts) and np.array_equal(e1, orc.ends) and np.array_equal(b1, orc.branch)
+    # search_values on a slice: offsets are the scan of counts, values resolve to overlapping intervals
+    off, vals = ix.search_values(dqs[:200_000].contiguous(), dqe[:200_000].contiguous())
+    assert torch.equal(off[1:] - off[:-1], c[:200_000].to(torch.int64))
+    seg = torch.repeat_interleave(torch.arange(200_000, device="cuda"), c[:200_000].to(torch.int64))
+    v = vals.to(torch.int64)
+    assert bool(((ds[v] <= dqe[seg]) & (de[v] >= dqs[seg])).all())

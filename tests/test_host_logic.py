@@ -1,0 +1,105 @@
+"""CPU: host-side logic -- workload generators, Python API error behaviour, sharding maths,
+and the N>1 bookkeeping over a world_size-2 gloo group."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from superintervals_b200 import IntervalMap, workloads as W
+from superintervals_b200.sharding import assign_contigs, csr_shard_bases, gather_counts, lpt_assign, shard_range
+
+
+def test_workloads_are_seeded_and_well_formed():
+    a, b = W.config1(5000, 0), W.config1(5000, 0)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    s, e, qs, qe = a
+    assert s.dtype == np.int32 and (s <= e).all() and (qs <= qe).all()
+    assert 1900 < (e - s + 1).mean() < 2100                     # ~2 kb log-normal (generate_test_intervals.py)
+    s, e, qs, qe = W.config2(20_000, 30_000, 2)
+    assert ((e - s + 1) >= 150).all() and ((e - s + 1) <= 10_000).all() and ((qe - qs + 1) <= 10_000).all()
+    assert not np.array_equal(W.config2_queries(1000, 2, shard=0)[0], W.config2_queries(1000, 2, shard=1)[0])
+    s, e, _, _ = W.config3(50_000, 10, 42)
+    assert (e - s + 1).max() <= 1_000_000 and (e - s + 1).min() >= 50
+    parts = W.config4_partition(1_000_000, 10_000_000)
+    assert len(parts) == 24 and sum(p[0] for p in parts) == 1_000_000 and sum(p[1] for p in parts) == 10_000_000
+
+
+def test_shard_range_covers_everything_once():
+    for n in (0, 1, 7, 100, 101):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_lpt_balances_contigs():
+    parts = W.config4_partition()
+    owner = assign_contigs([p[0] for p in parts], [p[1] for p in parts], 8)
+    load = np.zeros(8)
+    for (n, q, _, _), o in zip(parts, owner):
+        load[o] += n + q
+    assert load.max() / load.mean() < 1.08
+    assert list(lpt_assign([5, 4, 3, 3, 3], 2)) in ([0, 1, 1, 0, 1], [0, 1, 1, 0, 0])
+
+
+def test_python_api_error_behaviour():
+    """ValueError / IndexError exactly where the reference raises them (pyx:112-113,126,152-153,392-393)."""
+    m = IntervalMap()
+    with pytest.raises(IndexError):
+        m.at(0)
+    m.add(1, 5, "x")
+    assert len(m) == 1 and m.at(0) == (1, 5, "x") and m[0] == (1, 5, "x")
+    with pytest.raises(IndexError):
+        m.at(1)
+    with pytest.raises(IndexError):
+        m.starts_at(-1)
+    with pytest.raises(ValueError):
+        m.count_batch(np.array([1, 2], np.int32), np.array([1], np.int32))
+    with pytest.raises(ValueError):
+        IntervalMap.from_arrays([1, 2], [3])
+    with pytest.raises(ValueError):
+        IntervalMap.from_arrays([1, 2], [3, 4], values=["only one"])
+    m.clear()
+    assert len(m) == 0
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_total, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the full batch's counts, as a single GPU would produce them (deterministic stand-in)
+    full = (torch.arange(n_total, dtype=torch.int64) * 7919) % 13
+    lo, hi = shard_range(n_total, rank, world)
+    local = full[lo:hi].to(torch.int32)                    # what this rank's count kernel returns
+    bases, totals = csr_shard_bases(int(local.sum()))
+    gathered = gather_counts(local, n_total)
+    ok = torch.equal(gathered.to(torch.int64), full)
+    ok &= totals == [int(full[a:b].sum()) for a, b in (shard_range(n_total, r, world) for r in range(world))]
+    ok &= bases == [int(full[: shard_range(n_total, r, world)[0]].sum()) for r in range(world)]
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [10, 1001])
+def test_world_size_2_csr_bookkeeping_gloo(n_total):
+    world = 2
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        out = mgr.dict()
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, n_total, out)) for r in range(world)]
+        for p in procs: p.start()
+        for p in procs: p.join(120)
+        assert all(p.exitcode == 0 for p in procs)
+        assert dict(out) == {0: True, 1: True}
