@@ -1,0 +1,244 @@
+// superintervals.hpp -- C++ si::IntervalMap<S,T> backed by libsuperintervals_b200.so.
+//
+// Host-side mirror of the reference class template for the batch overlap-query path
+// (reference src/superintervals.hpp:45-150 storage/add/build/at, :501-1035 queries):
+// same namespace, class name, public members (starts, ends, branch, data,
+// start_sorted, end_sorted), method names, argument meaning, append-to-output
+// behaviour and result order. All index construction and every query execute on the
+// GPU through the C ABI (c_superintervals.h / superintervals_b200.h); payloads of
+// any type T stay on the host and are addressed by position.
+//
+//   #include "superintervals.hpp"        // this file instead of the reference's
+//   g++ -std=c++17 app.cpp -Iinclude -Lsuperintervals_b200 -lsuperintervals_b200
+//
+// Differences from the reference, all outside the accelerated path:
+//   * S must be a 32-bit integer type (the reference's AVX2 path has the same
+//     restriction, hpp:688; its C ABI is int32 only).
+//   * IntervalMapEytz, the set algebra (hpp:1037-1390) and the lazy iterator classes
+//     are not provided; search_idxs(s,e)/search_items(s,e) return eager ranges.
+//   * New: count_batch / search_values_batch / search_idxs_batch / search_keys_batch
+//     (CSR), the throughput path.
+#pragma once
+
+#include <algorithm>
+#include <cstddef>
+#include <cstdint>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "superintervals_b200.h"
+
+namespace si {
+
+template <typename S, typename T>
+struct Interval {
+    S start, end;
+    T data;
+    Interval() = default;
+    Interval(S s, S e, T d) : start(s), end(e), data(d) {}
+};
+
+template <typename S, typename T>
+class IntervalMap {
+    static_assert(std::is_integral<S>::value && sizeof(S) == 4,
+                  "superintervals_b200: coordinates must be a 32-bit integer type");
+
+   public:
+    std::vector<S> starts;
+    std::vector<S> ends;
+    std::vector<size_t> branch;
+    std::vector<T> data;
+    bool start_sorted, end_sorted;
+
+    IntervalMap() : start_sorted(true), end_sorted(true), h_(nullptr) {}
+    virtual ~IntervalMap() { destroySuperIntervals(h_); }
+    IntervalMap(const IntervalMap&) = delete;
+    IntervalMap& operator=(const IntervalMap&) = delete;
+    IntervalMap(IntervalMap&& o) noexcept { *this = std::move(o); }
+    IntervalMap& operator=(IntervalMap&& o) noexcept {
+        if (this != &o) {
+            destroySuperIntervals(h_);
+            starts = std::move(o.starts); ends = std::move(o.ends);
+            branch = std::move(o.branch); data = std::move(o.data);
+            start_sorted = o.start_sorted; end_sorted = o.end_sorted;
+            h_ = o.h_; o.h_ = nullptr;
+        }
+        return *this;
+    }
+
+    void clear() noexcept { data.clear(); starts.clear(); ends.clear(); branch.clear(); }   // hpp:69-71
+    void reserve(size_t n) { data.reserve(n); starts.reserve(n); ends.reserve(n); }
+    size_t size() { return starts.size(); }
+
+    void add(S start, S end, const T& value) {   // hpp:95-105
+        if (start_sorted && !starts.empty()) {
+            start_sorted = !(start < starts.back());
+            if (start_sorted && start == starts.back() && end > ends.back()) end_sorted = false;
+        }
+        starts.push_back(start);
+        ends.push_back(end);
+        data.emplace_back(value);
+    }
+
+    // hpp:112-130: sort by (start asc, end desc) + branch array -- on the device.
+    virtual void build() {
+        if (starts.empty()) return;
+        if (!h_) h_ = createSuperIntervals();
+        clearSuperIntervals(h_);
+        addIntervals(h_, reinterpret_cast<const int32_t*>(starts.data()),
+                     reinterpret_cast<const int32_t*>(ends.data()), nullptr, starts.size());
+        indexSuperIntervals(h_);
+        if (si_b200_last_error()) return;   // inspect si_b200_last_error_string()
+        const size_t n = starts.size();
+        std::vector<T> sorted;
+        sorted.reserve(n);
+        for (size_t i = 0; i < n; ++i) sorted.emplace_back(std::move(data[(size_t)h_->data[i]]));
+        data.swap(sorted);
+        std::copy(h_->starts, h_->starts + n, starts.begin());
+        std::copy(h_->ends, h_->ends + n, ends.begin());
+        branch.assign(h_->branch, h_->branch + n);
+        start_sorted = end_sorted = true;
+    }
+
+    Interval<S, T> at(size_t index) const { return Interval<S, T>{starts[index], ends[index], data[index]}; }
+    void at(size_t index, Interval<S, T>& itv) {
+        itv.start = starts[index]; itv.end = ends[index]; itv.data = data[index];
+    }
+
+    // hpp:501-513: largest index with starts[index] <= value, SIZE_MAX if none.
+    virtual size_t upper_bound(const S value) const noexcept {
+        if (!ready()) return SIZE_MAX;
+        return upperBound(h_, (int32_t)value);
+    }
+
+    // ---- single queries: appended to `found`, descending position order -------------------
+    void search_values(const S start, const S end, std::vector<T>& found) const {   // hpp:551-579
+        if (!ready()) return;
+        scratch_.size = 0;
+        searchIdxs(h_, (int32_t)start, (int32_t)end, &scratch_);
+        for (size_t k = 0; k < scratch_.size; ++k) found.push_back(data[(size_t)(uint32_t)scratch_.data[k]]);
+    }
+    void search_values_large(const S start, const S end, std::vector<T>& found) const {   // hpp:588: same output
+        search_values(start, end, found);
+    }
+    void search_point(const S point, std::vector<T>& found) const { search_values(point, point, found); }   // hpp:1013
+
+    size_t count(const S start, const S end) const noexcept {   // hpp:651-825
+        return ready() ? countOverlaps(h_, (int32_t)start, (int32_t)end) : 0;
+    }
+    size_t count_linear(const S start, const S end) const noexcept { return count(start, end); }   // hpp:623
+    size_t count_large(const S start, const S end) const noexcept { return count(start, end); }    // hpp:834
+
+    bool has_overlaps(const S start, const S end) const noexcept {   // hpp:865-871 (last candidate only)
+        return ready() && anyOverlaps(h_, (int32_t)start, (int32_t)end);
+    }
+
+    // hpp:879-905. The reference inserts its first contiguous run ASCENDING and the rest
+    // descending; reproduced here from the descending device result.
+    void search_idxs(const S start, const S end, std::vector<size_t>& found) const {
+        if (!ready()) return;
+        scratch_.size = 0;
+        searchIdxs(h_, (int32_t)start, (int32_t)end, &scratch_);
+        const size_t first = found.size();
+        for (size_t k = 0; k < scratch_.size; ++k) found.push_back((size_t)(uint32_t)scratch_.data[k]);
+        if (scratch_.size == 0) return;
+        const size_t ub = (size_t)(std::upper_bound(starts.begin(), starts.end(), end) - starts.begin()) - 1;
+        if (found[first] != ub) return;
+        size_t run = 1;
+        while (first + run < found.size() && found[first + run] + 1 == found[first + run - 1]) ++run;
+        std::reverse(found.begin() + first, found.begin() + first + run);
+    }
+
+    void search_keys(const S start, const S end, std::vector<std::pair<S, S>>& found) const {   // hpp:913-938
+        if (!ready()) return;
+        cKeyResult r = createKeyResult();
+        searchKeys(h_, (int32_t)start, (int32_t)end, &r);
+        for (size_t k = 0; k < r.size; ++k) found.emplace_back((S)r.data[k].start, (S)r.data[k].end);
+        destroyKeyResult(&r);
+    }
+
+    void search_items(const S start, const S end, std::vector<Interval<S, T>>& found) const {   // hpp:946-971
+        if (!ready()) return;
+        scratch_.size = 0;
+        searchIdxs(h_, (int32_t)start, (int32_t)end, &scratch_);
+        for (size_t k = 0; k < scratch_.size; ++k) {
+            const size_t j = (size_t)(uint32_t)scratch_.data[k];
+            found.emplace_back(starts[j], ends[j], data[j]);
+        }
+    }
+
+    void coverage(const S start, const S end, std::pair<size_t, S>& cov_result) const {   // hpp:979-1006 (accumulates)
+        if (!ready()) return;
+        size_t c = 0;
+        int32_t v = 0;
+        ::coverage(h_, (int32_t)start, (int32_t)end, &c, &v);
+        cov_result.first += c;
+        cov_result.second += (S)v;
+    }
+
+    // eager stand-ins for the reference's lazy ranges (hpp:153-494): usable in range-for
+    std::vector<size_t> search_idxs(const S start, const S end) const {
+        std::vector<size_t> v;
+        if (!ready()) return v;
+        scratch_.size = 0;
+        searchIdxs(h_, (int32_t)start, (int32_t)end, &scratch_);
+        for (size_t k = 0; k < scratch_.size; ++k) v.push_back((size_t)(uint32_t)scratch_.data[k]);
+        return v;   // all-descending, like the reference's IndexRange
+    }
+    std::vector<Interval<S, T>> search_items(const S start, const S end) const {
+        std::vector<Interval<S, T>> v;
+        search_items(start, end, v);
+        return v;
+    }
+
+    // ---- batch queries (the throughput path; shaped after intervalmap.pyx:363-494) --------
+    void count_batch(const S* qs, const S* qe, size_t n, std::vector<size_t>& counts) const {
+        counts.assign(n, 0);
+        if (!ready() || n == 0) return;
+        countOverlapsBatch(h_, reinterpret_cast<const int32_t*>(qs), reinterpret_cast<const int32_t*>(qe), n, counts.data());
+    }
+    // CSR: query i's hits are positions[offsets[i] .. offsets[i+1]) (descending)
+    void search_idxs_batch(const S* qs, const S* qe, size_t n, std::vector<size_t>& offsets,
+                           std::vector<uint32_t>& positions) const {
+        offsets.assign(n + 1, 0);
+        positions.clear();
+        if (!ready() || n == 0) return;
+        cIndexResult r = createIndexResult();
+        searchIdxsBatch(h_, reinterpret_cast<const int32_t*>(qs), reinterpret_cast<const int32_t*>(qe), n, offsets.data(), &r);
+        positions.assign(reinterpret_cast<uint32_t*>(r.data), reinterpret_cast<uint32_t*>(r.data) + r.size);
+        destroyIndexResult(&r);
+    }
+    void search_values_batch(const S* qs, const S* qe, size_t n, std::vector<size_t>& offsets,
+                             std::vector<T>& values) const {
+        std::vector<uint32_t> pos;
+        search_idxs_batch(qs, qe, n, offsets, pos);
+        values.clear();
+        values.reserve(pos.size());
+        for (uint32_t j : pos) values.push_back(data[j]);
+    }
+    void search_keys_batch(const S* qs, const S* qe, size_t n, std::vector<size_t>& offsets,
+                           std::vector<std::pair<S, S>>& keys) const {
+        offsets.assign(n + 1, 0);
+        keys.clear();
+        if (!ready() || n == 0) return;
+        cKeyResult r = createKeyResult();
+        searchKeysBatch(h_, reinterpret_cast<const int32_t*>(qs), reinterpret_cast<const int32_t*>(qe), n, offsets.data(), &r);
+        keys.reserve(r.size);
+        for (size_t k = 0; k < r.size; ++k) keys.emplace_back((S)r.data[k].start, (S)r.data[k].end);
+        destroyKeyResult(&r);
+    }
+
+    cSuperIntervals* handle() const { return h_; }   // for the device-resident API: siIndexOf(handle())
+
+   private:
+    bool ready() const { return h_ != nullptr && !starts.empty() && siIndexOf(h_) != nullptr; }
+    cSuperIntervals* h_;
+    mutable cIndexResult scratch_ = {nullptr, 0, 0};
+
+   public:
+    // scratch_ is malloc'd by the library; released with the object
+    struct ScratchGuard { cIndexResult* r; ~ScratchGuard() { destroyIndexResult(r); } } guard_{&scratch_};
+};
+
+}  // namespace si

@@ -1,0 +1,173 @@
+// hotpath.cpp -- the reference's hot-path unit tests (reference test/tests.cpp:63-238), restated
+// against include/superintervals.hpp (GPU-backed si::IntervalMap), plus the batch API.
+// Built and run by tests/test_gpu_cpp.py on the GPU box; compiled (not run) on CPU.
+#include "superintervals.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+#include <numeric>
+#include <utility>
+#include <vector>
+
+using Map = si::IntervalMap<int, int>;
+
+#define CHECK(cond)                                                                   \
+    do {                                                                              \
+        if (!(cond)) {                                                                \
+            std::fprintf(stderr, "FAILED %s:%d: %s  [%s]\n", __FILE__, __LINE__, #cond, \
+                         si_b200_last_error_string());                                \
+            std::exit(1);                                                             \
+        }                                                                             \
+    } while (0)
+
+static void test_basics() {   // tests.cpp:63-107
+    Map itv;
+    CHECK(!itv.has_overlaps(0, 1));
+    itv.add(10, 20, 0);
+    itv.add(11, 12, -1);
+    itv.add(13, 14, -1);
+    itv.add(15, 16, -1);
+    itv.add(25, 29, 4);
+    itv.build();
+    CHECK(itv.has_overlaps(17, 30));
+    CHECK(!itv.has_overlaps(1, 3));
+    std::vector<int> values;
+    itv.search_values(17, 30, values);
+    CHECK(values.size() == 2 && values[0] == 4 && values[1] == 0);
+    CHECK(itv.count(17, 30) == 2);
+    std::vector<size_t> idxs;
+    itv.search_idxs(17, 30, idxs);
+    CHECK(idxs.size() == 2 && idxs[0] == 4 && idxs[1] == 0);
+    std::vector<std::pair<int, int>> keys;
+    itv.search_keys(17, 30, keys);
+    CHECK(keys[0].first == 25 && keys[1].second == 20);
+    std::pair<size_t, int> cov{0, 0};
+    itv.coverage(10, 29, cov);
+    CHECK(cov.second == 17);
+    CHECK(itv.branch.size() == 5 && itv.branch[0] == SIZE_MAX && itv.branch[1] == 0 && itv.branch[4] == SIZE_MAX);
+    CHECK(itv.upper_bound(12) == 1 && itv.upper_bound(9) == SIZE_MAX);
+}
+
+static void test_iteration() {   // tests.cpp:113-133
+    Map itv;
+    itv.add(1, 10, 0);
+    itv.build();
+    size_t count = 0;
+    int last_data = -1;
+    for (const size_t i : itv.search_idxs(5, 11)) { last_data = itv.data[i]; ++count; }
+    CHECK(count == 1 && last_data == 0);
+    for (const auto& interval : itv.search_items(5, 11)) CHECK(interval.start == 1 && interval.end == 10 && interval.data == 0);
+}
+
+static void test_overlap_queries() {   // tests.cpp:140-188
+    std::vector<int> a;
+    {
+        Map itv;
+        itv.add(0, 250000, 0);
+        for (int s : {55, 115, 130, 281, 639, 842, 999, 1094, 1157, 1161, 1265, 1532, 1590, 1665, 1945, 2384, 2515})
+            itv.add(s, s + 1000, -1);
+        itv.build();
+        itv.search_values(1377, 2377, a);
+        CHECK(a.back() == 0 && a.size() == 12);
+        a.clear();
+    }
+    {
+        Map itv;
+        itv.add(3, 40, 0); itv.add(4, 5, 4); itv.add(6, 7, 4); itv.add(10, 31, 5); itv.add(31, 32, 5);
+        itv.build();
+        itv.search_values(31, 32, a); CHECK(a.size() == 3); a.clear();
+        itv.search_values(10, 11, a); CHECK(a.size() == 2); a.clear();
+        itv.search_values(4, 7, a);   CHECK(a.size() == 3); a.clear();
+    }
+    {
+        Map itv;
+        itv.add(3, 40, 0); itv.add(3, 40, 4); itv.add(3, 40, 4); itv.add(3, 4, 4);
+        itv.add(35, 50, 4); itv.add(40, 400, 5); itv.add(40, 400, 4);
+        itv.build();
+        itv.search_values(38, 41, a); CHECK(a.size() == 6); a.clear();
+        itv.search_values(41, 42, a); CHECK(a.size() == 3); a.clear();
+    }
+}
+
+static void test_coverage() {   // tests.cpp:194-213
+    Map itv;
+    itv.add(1, 100, 0); itv.add(30, 200, 7); itv.add(40, 50, 6); itv.add(60, 70, 7);
+    itv.build();
+    std::vector<int> a;
+    itv.search_values(55, 65, a);
+    CHECK(a.size() == 3);
+    std::pair<size_t, int> cov{0, 0};
+    itv.coverage(55, 65, cov);
+    CHECK(cov.first == 3 && cov.second == 25);
+}
+
+static void test_edge_cases() {   // tests.cpp:219-238
+    {
+        Map itv;
+        itv.build();
+        CHECK(itv.count(1, 5) == 0);
+        CHECK(!itv.has_overlaps(1, 5));
+    }
+    {
+        Map itv;
+        itv.add(1, 10, 1);
+        itv.build();
+        CHECK(itv.count(1, 5) == 1);
+        CHECK(itv.count(11, 20) == 0);
+    }
+}
+
+static void test_quirks() {
+    Map itv;   // Q1: has_overlaps looks at the last candidate only (hpp:869-870)
+    itv.add(1, 100, 0); itv.add(5, 6, 1);
+    itv.build();
+    CHECK(!itv.has_overlaps(50, 60) && itv.count(50, 60) == 1);
+    Map q2;    // Q2: vector search_idxs has its first run ascending (hpp:892-895)
+    q2.add(1, 100, 0); q2.add(2, 3, 1); q2.add(10, 50, 2); q2.add(11, 50, 3); q2.add(12, 50, 4);
+    q2.build();
+    std::vector<size_t> idx;
+    q2.search_idxs(20, 30, idx);
+    CHECK((idx == std::vector<size_t>{2, 3, 4, 0}));
+    std::vector<int> v;
+    q2.search_values(20, 30, v);
+    CHECK((v == std::vector<int>{4, 3, 2, 0}));
+}
+
+static void test_batch_and_payload_types() {
+    // non-int payloads ride on the host; batch CSR equals the per-query calls
+    si::IntervalMap<int, std::pair<int, double>> m;
+    const int n = 5000;
+    unsigned x = 12345;
+    auto rnd = [&x]() { x = x * 1664525u + 1013904223u; return (int)(x >> 8); };
+    for (int i = 0; i < n; ++i) { int s = rnd() % 100000; m.add(s, s + rnd() % 700, {i, i * 0.5}); }
+    m.build();
+    std::vector<int> qs, qe;
+    for (int i = 0; i < 3000; ++i) { int s = rnd() % 100000; qs.push_back(s); qe.push_back(s + rnd() % 900); }
+    std::vector<size_t> counts, off;
+    std::vector<std::pair<int, double>> vals;
+    m.count_batch(qs.data(), qe.data(), qs.size(), counts);
+    m.search_values_batch(qs.data(), qe.data(), qs.size(), off, vals);
+    CHECK(off.back() == std::accumulate(counts.begin(), counts.end(), size_t(0)) && vals.size() == off.back());
+    for (size_t q = 0; q < qs.size(); q += 97) {
+        std::vector<std::pair<int, double>> one;
+        m.search_values(qs[q], qe[q], one);
+        CHECK(one.size() == counts[q] && m.count(qs[q], qe[q]) == counts[q]);
+        for (size_t k = 0; k < one.size(); ++k) CHECK(one[k] == vals[off[q] + k]);
+        size_t brute = 0;
+        for (size_t j = 0; j < m.starts.size(); ++j) brute += (m.starts[j] <= qe[q] && m.ends[j] >= qs[q]);
+        CHECK(brute == counts[q]);
+    }
+}
+
+int main() {
+    test_basics();
+    test_iteration();
+    test_overlap_queries();
+    test_coverage();
+    test_edge_cases();
+    test_quirks();
+    test_batch_and_payload_types();
+    CHECK(si_b200_last_error() == 0);
+    std::printf("All query tests passed\n");
+    return 0;
+}
