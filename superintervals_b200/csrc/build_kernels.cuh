@@ -94,6 +94,29 @@ __global__ void bk_pad_kernel(int32_t* __restrict__ starts, int32_t* __restrict_
     }
 }
 
+// ---- esort: ends with every aligned 32-block sorted ascending (bitonic network in a warp) ----
+// Lets the count sweep rank a query start inside a block with 6 probes (query_kernels.cuh).
+__global__ void __launch_bounds__(BK_THREADS)
+bk_sort_blocks_kernel(const int32_t* __restrict__ ends, uint32_t n_padded, int32_t* __restrict__ esort) {
+    const uint32_t lane = lane_id();
+    const uint64_t warps_total = (uint64_t)gridDim.x * (BK_THREADS / 32);
+    const uint64_t nblocks = n_padded >> 5;
+    for (uint64_t b = (uint64_t)blockIdx.x * (BK_THREADS / 32) + (threadIdx.x >> 5); b < nblocks; b += warps_total) {
+        int32_t v = ends[b * 32u + lane];
+#pragma unroll
+        for (uint32_t k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                const int32_t o = __shfl_xor_sync(FULL_MASK, v, j);
+                const bool asc = (lane & k) == 0;
+                const bool low = (lane & j) == 0;
+                v = (low == asc) ? min(v, o) : max(v, o);
+            }
+        }
+        esort[b * 32u + lane] = v;
+    }
+}
+
 // ---- 32-ary max tree over ends -------------------------------------------------------
 // level 0 = ends; level L entry k = max of level L-1 entries [32k, 32k+32).
 // One launch produces two levels: a CTA of 1024 threads folds 1024 inputs into

@@ -233,6 +233,55 @@ int32_t endAt(const cSuperIntervals* si, size_t index) { return si->ends[index];
 int32_t dataAt(const cSuperIntervals* si, size_t index) { return si->data[index]; }
 
 // ---- batch queries over host buffers ---------------------------------------------------------
+// Large batches are pipelined in chunks over three streams so the PCIe copies of chunk
+// k+1 (H2D) and k-1 (D2H) overlap the kernels of chunk k; two buffer slots.
+static int count_batch_pipelined(siIndex* ix, const int32_t* qs, const int32_t* qe, size_t n, size_t* counts_out) {
+    constexpr size_t CHUNK = (size_t)8 << 20;   // queries per chunk: 64 MB in, 64 MB out
+    if (!ix->pipe_ready) {
+        SIB_CHECK(cudaStreamCreateWithFlags(&ix->s_in, cudaStreamNonBlocking));
+        SIB_CHECK(cudaStreamCreateWithFlags(&ix->s_out, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            SIB_CHECK(cudaEventCreateWithFlags(&ix->e_in[k], cudaEventDisableTiming));
+            SIB_CHECK(cudaEventCreateWithFlags(&ix->e_k[k], cudaEventDisableTiming));
+            SIB_CHECK(cudaEventCreateWithFlags(&ix->e_out[k], cudaEventDisableTiming));
+        }
+        ix->pipe_ready = true;
+    }
+    if (ix->h_qs.ensure(2 * CHUNK * 4) || ix->h_qe.ensure(2 * CHUNK * 4) || ix->h_counts.ensure(2 * CHUNK * 8))
+        return sib::last_error_code();
+    cudaStream_t s_in = ix->s_in, s_k = ix->own_stream, s_out = ix->s_out;
+    int order = SI_ORDER_AUTO;
+    size_t k = 0;
+    for (size_t at = 0; at < n; at += CHUNK, ++k) {
+        const size_t m = n - at < CHUNK ? n - at : CHUNK;
+        const int slot = (int)(k & 1);
+        int32_t* dqs = ix->h_qs.as<int32_t>() + slot * CHUNK;
+        int32_t* dqe = ix->h_qe.as<int32_t>() + slot * CHUNK;
+        uint64_t* dc = ix->h_counts.as<uint64_t>() + slot * CHUNK;
+        if (k >= 2) SIB_CHECK(cudaStreamWaitEvent(s_in, ix->e_k[slot], 0));    // slot's inputs consumed (chunk k-2)
+        SIB_CHECK(cudaMemcpyAsync(dqs, qs + at, m * 4, cudaMemcpyHostToDevice, s_in));
+        SIB_CHECK(cudaMemcpyAsync(dqe, qe + at, m * 4, cudaMemcpyHostToDevice, s_in));
+        SIB_CHECK(cudaEventRecord(ix->e_in[slot], s_in));
+        SIB_CHECK(cudaStreamWaitEvent(s_k, ix->e_in[slot], 0));
+        if (k >= 2) SIB_CHECK(cudaStreamWaitEvent(s_k, ix->e_out[slot], 0));   // slot's counts drained (chunk k-2)
+        if (k == 0) {
+            // one device check on the first chunk decides sort-or-not for the whole batch; any
+            // order is answered correctly, the choice only affects locality
+            order = si_b200_resolve_order_(ix, dqs, m, s_k);
+            if (order < 0) return sib::last_error_code();
+        }
+        int rc = siCountDevice64(ix, dqs, dqe, m, dc, order, s_k);
+        if (rc) return rc;
+        SIB_CHECK(cudaEventRecord(ix->e_k[slot], s_k));
+        SIB_CHECK(cudaStreamWaitEvent(s_out, ix->e_k[slot], 0));
+        SIB_CHECK(cudaMemcpyAsync(counts_out + at, dc, m * 8, cudaMemcpyDeviceToHost, s_out));
+        SIB_CHECK(cudaEventRecord(ix->e_out[slot], s_out));
+    }
+    SIB_CHECK(cudaStreamSynchronize(s_out));
+    SIB_CHECK(cudaStreamSynchronize(s_k));
+    return 0;
+}
+
 void countOverlapsBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n,
                         size_t* counts_out) {
     Handle* h = H(si);
@@ -240,6 +289,11 @@ void countOverlapsBatch(cSuperIntervals* si, const int32_t* starts, const int32_
     if (si->size == 0) { memset(counts_out, 0, n * sizeof(size_t)); return; }   // ref:730-732
     if (!ready(h, "countOverlapsBatch")) { memset(counts_out, 0, n * sizeof(size_t)); return; }
     siIndex* ix = h->ix;
+    static_assert(sizeof(size_t) == 8, "LP64 only");
+    if (n > ((size_t)12 << 20)) {
+        count_batch_pipelined(ix, starts, ends, n, counts_out);
+        return;
+    }
     if (stage_queries(ix, starts, ends, n) || ix->h_counts.ensure(n * 8)) return;
     if (siCountDevice64(ix, ix->h_qs.as<int32_t>(), ix->h_qe.as<int32_t>(), n, ix->h_counts.as<uint64_t>(),
                         SI_ORDER_AUTO, ix->own_stream))

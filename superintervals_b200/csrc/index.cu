@@ -71,7 +71,7 @@ using namespace sib;
     } while (0)
 
 size_t siIndex::device_bytes() const {
-    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &b_in_s, &b_in_e, &b_in_v,
+    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &esort, &b_in_s, &b_in_e, &b_in_v,
                            &b_kA, &b_kB, &b_vA, &b_vB, &b_ws, &small, &q_kA, &q_kB, &q_vA, &q_vB,
                            &q_ws, &scan_status, &h_qs, &h_qe, &h_counts, &h_offsets, &h_out, &h_cov};
     size_t s = 0;
@@ -101,6 +101,7 @@ IndexView view_of(const siIndex* ix) {
     v.values = ix->values.as<int32_t>();
     v.branch = ix->branch.as<uint32_t>();
     v.pmax32 = ix->pmax32;
+    v.esort = ix->esort.as<int32_t>();
     v.n = ix->n;
     v.wellformed = ix->wellformed ? 1u : 0u;
     return v;
@@ -222,6 +223,9 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
         SIB_LAUNCH(bk_pad_kernel, 1, 128, 0, s, ix->starts.as<int32_t>(), ix->ends.as<int32_t>(),
                    ix->branch.as<uint32_t>(), ix->n, ix->n_padded);
     }
+    if (ix->esort.ensure(pad_b)) return last_error_code();
+    SIB_LAUNCH(bk_sort_blocks_kernel, grid_for(ix->n_padded / 32, BK_THREADS / 32, cap), BK_THREADS, 0, s,
+               ix->ends.as<int32_t>(), ix->n_padded, ix->esort.as<int32_t>());
     int rc = build_branch(ix, s);
     if (rc) return rc;
     ix->built = true;
@@ -360,11 +364,16 @@ siIndex* siIndexCreate(void) {
 void siIndexDestroy(siIndex* ix) {
     if (!ix) return;
     DeviceGuard g(ix->device);
-    DevBuf* all[] = {&ix->starts, &ix->ends, &ix->values, &ix->branch, &ix->perm, &ix->tree, &ix->b_in_s,
+    DevBuf* all[] = {&ix->starts, &ix->ends, &ix->values, &ix->branch, &ix->perm, &ix->tree, &ix->esort, &ix->b_in_s,
                      &ix->b_in_e, &ix->b_in_v, &ix->b_kA, &ix->b_kB, &ix->b_vA, &ix->b_vB, &ix->b_ws, &ix->small,
                      &ix->q_kA, &ix->q_kB, &ix->q_vA, &ix->q_vB, &ix->q_ws, &ix->scan_status, &ix->h_qs,
                      &ix->h_qe, &ix->h_counts, &ix->h_offsets, &ix->h_out, &ix->h_cov};
     for (auto* b : all) b->release();
+    if (ix->pipe_ready) {
+        cudaStreamDestroy(ix->s_in);
+        cudaStreamDestroy(ix->s_out);
+        for (int k = 0; k < 2; ++k) { cudaEventDestroy(ix->e_in[k]); cudaEventDestroy(ix->e_k[k]); cudaEventDestroy(ix->e_out[k]); }
+    }
     if (ix->pinned) cudaFreeHost(ix->pinned);
     if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
     delete ix;

@@ -31,6 +31,7 @@ struct siIndex {
     bool built = false;
     bool wellformed = false;   // every interval has start <= end (enables the count shortcut)
     sib::DevBuf starts, ends, values, branch, perm;
+    sib::DevBuf esort;         // ends, each aligned 32-block sorted ascending (count sweep)
     sib::DevBuf tree;          // 32-ary max tree levels + prefix-max levels
     const int32_t* pmax32 = nullptr;   // inside `tree`: exclusive prefix max of ends per 32-block
 
@@ -49,6 +50,9 @@ struct siIndex {
 
     // ---- staging for the host-buffer API ---------------------------------------------
     sib::DevBuf h_qs, h_qe, h_counts, h_offsets, h_out, h_cov;
+    bool pipe_ready = false;                    // chunked host-batch pipeline (c_abi.cu)
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t e_in[2] = {nullptr, nullptr}, e_k[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};
     void* pinned = nullptr;                     // small pinned scratch for scalars
     size_t pinned_bytes = 0;
 

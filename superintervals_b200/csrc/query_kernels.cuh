@@ -33,6 +33,7 @@ struct IndexView {
     const int32_t* values;
     const uint32_t* branch;  // NONE32 = no previous interval reaches this far
     const int32_t* pmax32;   // pmax32[b] = max(ends[0 .. 32b-1]) (INT_MIN for b = 0), from build()
+    const int32_t* esort;    // ends with every aligned 32-block sorted ascending (n_pad entries), from build()
     uint32_t n;
     uint32_t wellformed;     // 1 when every stored interval has start <= end (checked by build())
 };
@@ -131,6 +132,19 @@ __device__ __forceinline__ uint32_t walk_warp128(const IndexView& ix, uint32_t b
     return bc;
 }
 
+// Hits (ends >= qs) among the 32 intervals of one aligned block, from the block's
+// ascending-sorted copy of ends: a 6-probe branch-free rank. The lanes of a tile read
+// different words of the same 128-byte line, so each probe is one L1 wavefront.
+__device__ __forceinline__ uint32_t block_hits_sorted(const int32_t* __restrict__ es, int32_t qs) {
+    uint32_t c = (ld_nc(es + 15) < qs) ? 16u : 0u;
+    c += (ld_nc(es + c + 7) < qs) ? 8u : 0u;
+    c += (ld_nc(es + c + 3) < qs) ? 4u : 0u;
+    c += (ld_nc(es + c + 1) < qs) ? 2u : 0u;
+    c += (ld_nc(es + c) < qs) ? 1u : 0u;
+    c += (ld_nc(es + c) < qs) ? 1u : 0u;   // c <= 31 here; moves only when all 32 are below qs
+    return 32u - c;
+}
+
 constexpr uint32_t QK_DENSE_SPAN = 256;      // max spread of upper bounds inside a tile for the sweep
 constexpr uint32_t QK_DENSE_MIN_HITS = 8;    // a 32-interval chunk must yield this many hits tile-wide
 constexpr int QK_DENSE_MAX_CHUNKS = 256;     // then the sparse tail goes to the branch walk
@@ -140,12 +154,14 @@ constexpr int QK_DENSE_MAX_CHUNKS = 256;     // then the sparse tail goes to the
 // the radix sort made them so). Three stages:
 //   search  per-lane branch-free upper_bound(qe) (+ lower bound of qs on a well-formed
 //           index); a sorted tile probes the same lines.
-//   sweep   the tile's queries overlap the same window of the index, so the warp
-//           streams that window ONCE, top-down, in 32-interval chunks (uniform 128-bit
-//           loads, every lane tests each end against its own query). This is the
-//           reference's linear SIMD block count (hpp:718-748) shared by 32 queries.
-//           It stops when the prefix maximum of ends says nothing further back can
-//           reach any query of the tile, or when chunks stop producing hits.
+//   sweep   the tile's queries overlap the same window of the index, so the warp walks
+//           that window ONCE, top-down, in aligned 32-interval blocks -- the reference's
+//           linear SIMD block count (hpp:718-748) shared by 32 queries. build() keeps a
+//           copy of ends sorted inside each block, so a whole block costs each lane a
+//           6-probe rank of its qs instead of 32 compares; the partial block at the top
+//           is corrected with 128-bit loads of the plain ends. It stops when the prefix
+//           maximum of ends says nothing further back can reach any query of the tile,
+//           or when blocks stop producing hits.
 //   walk    whatever remains (sparse, far-reaching containers) is finished by the
 //           branch-array walk: lane-parallel first, warp-cooperative for stragglers.
 // SORTED_VIA_PERM: queries were radix-sorted by qe (see SortedQueries); qs is gathered
@@ -201,32 +217,40 @@ qk_count_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* 
         int chunks = 0;
         bool finished = false;
         while (true) {
-            const uint32_t cb = pos & ~31u;
-            uint32_t hc = 0;
+            uint32_t cb = pos & ~31u;
+            uint32_t hc, nblk = 1;
             if (pos == cb + 31u && cb + 32u <= top_min) {
-                // whole chunk lies below every lane's limit: no index masks
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int4 e = ld_nc4(ix.ends + cb + 4 * k);
-                    hc += (e.x >= qs ? 1u : 0u) + (e.y >= qs ? 1u : 0u) + (e.z >= qs ? 1u : 0u) + (e.w >= qs ? 1u : 0u);
+                // whole blocks below every lane's limit: rank qs in each block's sorted copy.
+                // Four independent searches per round keep loads in flight; blocks below the
+                // termination point contribute exact zeros, so overshooting is harmless.
+                if (cb >= 96u) {
+                    hc = block_hits_sorted(ix.esort + cb, qs) + block_hits_sorted(ix.esort + cb - 32u, qs) +
+                         block_hits_sorted(ix.esort + cb - 64u, qs) + block_hits_sorted(ix.esort + cb - 96u, qs);
+                    cb -= 96u;
+                    nblk = 4;
+                } else {
+                    hc = block_hits_sorted(ix.esort + cb, qs);
                 }
             } else {
-                const uint32_t lt = min(top, pos + 1u);    // this lane counts indices < lt
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t j = cb + 4 * k;
+                // top of the window: the whole block from its sorted copy, minus the block's
+                // intervals at or above this lane's limit (a lane whose limit is below the
+                // block subtracts all of it and gets 0)
+                const uint32_t lt = min(top, pos + 1u);
+                const uint32_t lt_min = max(cb, __reduce_min_sync(FULL_MASK, lt));
+                hc = block_hits_sorted(ix.esort + cb, qs);
+                for (uint32_t j = lt_min & ~3u; j < cb + 32u; j += 4u) {
                     const int4 e = ld_nc4(ix.ends + j);    // padded to 128: in bounds
-                    hc += ((j < lt && e.x >= qs) ? 1u : 0u) + ((j + 1u < lt && e.y >= qs) ? 1u : 0u) +
-                          ((j + 2u < lt && e.z >= qs) ? 1u : 0u) + ((j + 3u < lt && e.w >= qs) ? 1u : 0u);
+                    hc -= ((j >= lt && e.x >= qs) ? 1u : 0u) + ((j + 1u >= lt && e.y >= qs) ? 1u : 0u) +
+                          ((j + 2u >= lt && e.z >= qs) ? 1u : 0u) + ((j + 3u >= lt && e.w >= qs) ? 1u : 0u);
                 }
             }
             c += hc;
             if (cb == 0) { finished = true; break; }
             pos = cb - 1u;
             if (ld_nc(ix.pmax32 + (cb >> 5)) < qs_min) { finished = true; break; }   // nothing below reaches the tile
-            ++chunks;
+            chunks += (int)nblk;
             const uint32_t tot = __reduce_add_sync(FULL_MASK, top ? hc : 0u);
-            if ((chunks >= 2 && tot < QK_DENSE_MIN_HITS) || chunks >= QK_DENSE_MAX_CHUNKS) break;
+            if ((chunks >= 2 && tot < QK_DENSE_MIN_HITS * nblk) || chunks >= QK_DENSE_MAX_CHUNKS) break;
         }
         if (finished) {
             // lanes with top == 0 swept unmasked chunks: their c is meaningless
