@@ -50,6 +50,10 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=16_000_000, help="queries timed on the host CPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-search-values", action="store_true", help="skip the secondary search_values (C3) measurement")
+    ap.add_argument("--algo", default="auto", choices=["auto", "walk", "rank"], help="count kernel (SI_OPT_COUNT_ALGO)")
+    ap.add_argument("--sv-intervals", type=int, default=4_000_000)
+    ap.add_argument("--sv-queries", type=int, default=4_000_000)
     return ap.parse_args()
 
 
@@ -76,47 +80,64 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed regions (B200_PROFILING.md): an NVML
+    polling thread (about every 2 ms; nvidia-smi -lms cannot start fast enough for a 40 ms region),
+    nvidia-smi as a fallback. Samples carry host timestamps; stop(t0, t1) keeps those inside."""
+    HW_SLOWDOWN, SW_THERMAL, HW_THERMAL, SW_POWER_CAP = 0x8, 0x20, 0x40, 0x4
 
     def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.rows, self.run, self.t, self.h, self.nv = gpu_index, [], False, None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        for r in self.rows:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
             try:
-                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+                h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
             except Exception:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nv, self.h, self.run = nv, h, True
+            self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+        except Exception as ex:   # noqa: BLE001
+            self.err = repr(ex)
+            self.run = False
+
+    def _poll(self):
+        nv, h = self.nv, self.h
+        while self.run:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.rows.append((time.perf_counter(), sm, rs, pw))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self, windows):
+        """windows: [(t0, t1), ...] host-clock intervals of the timed regions."""
+        if not self.run:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")]}
+        self.run = False
+        self.t.join(timeout=1)
+        rows = [r for r in self.rows if any(t0 <= r[0] <= t1 for t0, t1 in windows)] or self.rows
+        sm = [r[1] for r in rows]
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        reasons = [n for n, m in (("hw_slowdown", self.HW_SLOWDOWN), ("hw_thermal_slowdown", self.HW_THERMAL),
+                                  ("sw_thermal_slowdown", self.SW_THERMAL), ("sw_power_cap", self.SW_POWER_CAP)) if bits & m]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": self.max_sm, "power_w_max": max(r[3] for r in rows) if rows else None,
+                "samples": len(rows), "reasons": reasons, "source": "NVML polled every ~2 ms inside the timed regions"}
 
 
 # ---------------------------------------------------------------------------------------
@@ -184,6 +205,84 @@ def run_reference_arm(a):
 # ---------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------
+def kernel_table(recs, steps, nq, passes, a_walk):
+    """Group the library's per-launch CUDA-event records: per kernel class the launches per step,
+    the mean launch duration and the algorithmic bytes one launch moves."""
+    alg = {"pt_histogram": 4.0 * nq,                                             # one read of the starts
+           "pt_onesweep": (20.0 + 24.0 * max(0, passes - 1)) / max(1, passes) * nq,  # 8+12 first pass, 12+12 after
+           "count_rank": 16.0 * nq,                                              # 12 B record in, 4 B count out
+           "count_walk": a_walk * nq}                                            # SURVEY 8d A_count: the reference walk
+    out = {}
+    for name, ms in recs:
+        d = out.setdefault(name, {"launches": 0, "ms_total": 0.0})
+        d["launches"] += 1
+        d["ms_total"] += ms
+    for name, d in out.items():
+        d["ms_per_launch"] = d["ms_total"] / d["launches"]
+        d["ms_per_step"] = d["ms_total"] / steps
+        d["launches_per_step"] = d["launches"] / steps
+        if name in alg:
+            d["algorithmic_bytes_per_launch"] = alg[name]
+            d["achieved_gbs"] = alg[name] / (d["ms_per_launch"] * 1e-3) / 1e9
+        del d["ms_total"]
+    return out
+
+
+def bench_search_values(a, torch, L, _lib, rank):
+    """Secondary line: search_values (CSR) on BASELINE configs[2] -- heavy-tailed nested intervals."""
+    from superintervals_b200 import IntervalMap, workloads as W
+    from superintervals_b200.device import DeviceIndex, OPT_TIMING, ORDER_UNSORTED
+    n, nq = a.sv_intervals, a.sv_queries
+    s, e, qs, qe = W.config3(n, nq, 42)
+    ix = DeviceIndex().build(torch.from_numpy(s).cuda(), torch.from_numpy(e).cuda())
+    dqs, dqe = torch.from_numpy(qs).cuda(), torch.from_numpy(qe).cuda()
+    off, vals = ix.search_values(dqs, dqe, order=ORDER_UNSORTED)
+    total = int(off[nq].item())
+    counts = torch.empty(nq, dtype=torch.int32, device="cuda")
+    for _ in range(3):
+        ix.search_values(dqs, dqe, order=ORDER_UNSORTED, counts=counts, offsets=off, out=vals)
+    torch.cuda.synchronize()
+    ix.set_option(OPT_TIMING, 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        ix.search_values(dqs, dqe, order=ORDER_UNSORTED, counts=counts, offsets=off, out=vals)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    recs = ix.read_timings()
+    ix.set_option(OPT_TIMING, 0)
+    per = {}
+    for name, t in recs:
+        per[name] = per.get(name, 0.0) + t / a.steps
+    # e2e through the C ABI with host buffers (searchValuesBatch: H2D queries, D2H offsets + values)
+    m = IntervalMap.from_arrays(s, e)
+    m.search_values_batch_csr(qs, qe)
+    t0 = time.perf_counter()
+    for _ in range(a.e2e_steps):
+        o2, v2 = m.search_values_batch_csr(qs, qe)
+    e2e_s = (time.perf_counter() - t0) / a.e2e_steps
+    ok = bool(np.array_equal(o2.astype(np.int64), off.cpu().numpy()) and np.array_equal(v2, vals.cpu().numpy()))
+    out = {"workload": f"C3: {n/1e6:g}M heavy-tailed nested intervals (Pareto 1.1, <=1Mb) x {nq/1e6:g}M queries, "
+                       f"search_values CSR, shuffled queries", "value": nq / (ms * 1e-3), "unit": UNIT,
+           "ms_per_step": ms, "hits": total, "hits_per_query": total / nq, "kernel_ms_per_step": per,
+           "result_gbs": (total * 4 + nq * 8) / (ms * 1e-3) / 1e9,
+           "e2e": {"value": nq / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": 8 * nq,
+                   "d2h_bytes_per_step": 8 * (nq + 1) + 4 * total, "equals_device": ok,
+                   "call": "searchValuesBatch(si, qs, qe, n, offsets, cIndexResult*) with host buffers"}}
+    if rank == 0 and not a.no_cpu_baseline:
+        from oracle.pyoracle import Reference
+        if Reference.available():
+            ref = Reference(s, e)
+            th = host_threads()
+            t, found = ref.time_search_values(qs, qe, th)
+            t, found = ref.time_search_values(qs, qe, th)
+            out["cpu_baseline"] = {"value": nq / t, "unit": UNIT, "cores": th, "kind": "reference",
+                                   "sample": f"all {nq} queries, si::IntervalMap<int,int>::search_values into per-thread vectors",
+                                   "found": int(found), "found_equals_gpu": int(found) == total}
+    return out
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -192,7 +291,7 @@ def main():
     import torch
     import torch.distributed as dist
     from superintervals_b200 import _lib, workloads as W
-    from superintervals_b200.device import DeviceIndex, ORDER_SORTED, ORDER_UNSORTED
+    from superintervals_b200.device import DeviceIndex, OPT_TIMING, ORDER_SORTED, ORDER_UNSORTED
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -214,9 +313,13 @@ def main():
     order = ORDER_SORTED if a.order == "sorted" else ORDER_UNSORTED
 
     ix = DeviceIndex()
+    if a.algo != "auto":
+        from superintervals_b200.device import COUNT_RANK, COUNT_WALK, OPT_COUNT_ALGO
+        ix.set_option(OPT_COUNT_ALGO, COUNT_WALK if a.algo == "walk" else COUNT_RANK)
     d_s, d_e = torch.from_numpy(starts).cuda(), torch.from_numpy(ends).cuda()
     torch.cuda.synchronize()
     t0 = time.perf_counter(); ix.build(d_s, d_e); torch.cuda.synchronize(); build_ms = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter(); ix.build(d_s, d_e); torch.cuda.synchronize(); build_ms = min(build_ms, (time.perf_counter() - t0) * 1e3)
     d_qs, d_qe = torch.from_numpy(qs).cuda(), torch.from_numpy(qe).cuda()
     counts = torch.empty(nq, dtype=torch.int32, device="cuda")
 
@@ -226,14 +329,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(evs=None):
-        if order == ORDER_UNSORTED:
-            ix.sort_queries(d_qs)                    # radix sort of the batch by start (arms the next count)
-        if evs is not None:
-            evs[0].record()
+    def step():
+        # shuffled batch: partition by position on the device (records of start, end, index), then count
         ix.count(d_qs, d_qe, out=counts, order=order)
-        if evs is not None:
-            evs[1].record()
 
     for _ in range(max(a.warmup, 3)):
         step()
@@ -243,25 +341,27 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
+        time.sleep(0.05)
+    ix.set_option(OPT_TIMING, 1)            # CUDA event pair around every hot kernel launch, on its own stream
     launches0 = L.si_b200_kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     barrier()
+    w0 = time.perf_counter()
     ev0.record()
     for k in range(a.steps):
-        step(kev[k])
+        step()
     ev1.record()
     barrier()
+    w1 = time.perf_counter()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = int(L.si_b200_kernel_launches() - launches0)
-    count_kernel_ms = float(np.mean([x.elapsed_time(y) for x, y in kev]))
-    clocks = sampler.stop() if rank == 0 else None
+    recs = ix.read_timings()
+    ix.set_option(OPT_TIMING, 0)
 
-    t = torch.tensor([elapsed_ms, count_kernel_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, count_kernel_ms_max = float(t[0]), float(t[1])
+    elapsed_ms = float(t[0])
     ms_per_step = elapsed_ms / a.steps
     value = world * nq / (ms_per_step * 1e-3)
 
@@ -288,24 +388,30 @@ def main():
     e2e_step()
     _lib.check("countOverlapsBatch")
     barrier()
-    t0 = time.perf_counter()
+    w2 = time.perf_counter()
     for _ in range(a.e2e_steps):
         e2e_step()
     torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / a.e2e_steps
+    w3 = time.perf_counter()
+    e2e_s = (w3 - w2) / a.e2e_steps
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te[0])
+    clocks = sampler.stop([(w0, w1), (w2, w3)]) if rank == 0 else None
     e2e_ok = bool((h_out.numpy().astype(np.int64) == counts.cpu().numpy().astype(np.uint32).astype(np.int64)).all())
     L.destroySuperIntervals(si)
+
+    sv = None
+    if world == 1 and not a.no_search_values:
+        sv = bench_search_values(a, torch, L, _lib, rank)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (qk_count_kernel): algorithmic bytes / its own duration
+    # ---- roofline of the dominant kernel: algorithmic bytes per launch / its own CUDA-event duration
     from oracle.pyoracle import Oracle   # checker only: walk statistics + parity of a sample
     Lg = max(1, math.ceil(math.log2(max(2, a.intervals))))
     stat_n = min(nq, 200_000)
@@ -313,23 +419,31 @@ def main():
     h_s, j_s = orc.walk_stats(qs[:stat_n], qe[:stat_n])
     h_per_q = shard_hits[0] / nq                         # exact, from the GPU counts
     j_per_q = j_s / stat_n                               # reference-walk failed tests, sample estimate
-    a_count = 8 + 4 + 4 * Lg + 4 * (h_per_q + j_per_q) + 4 * j_per_q      # SURVEY 8d A_count(q)
+    a_walk = 8 + 4 + 4 * Lg + 4 * (h_per_q + j_per_q) + 4 * j_per_q      # SURVEY 8d A_count(q)
+    passes = int(round(sum(1 for n_, _ in recs if n_ == "pt_onesweep") / a.steps))
+    kernels = kernel_table(recs, a.steps, nq, passes, a_walk)
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     peak, peak_src = measured_peak()
-    achieved = nq * a_count / (count_kernel_ms_max * 1e-3) / 1e9
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "count_kernel_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get(dom, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "qk_count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
-                "kernel_ms": count_kernel_ms_max, "algorithmic_bytes_per_query": a_count,
-                "hits_per_query": h_per_q, "jumps_per_query_sampled": j_per_q, "log2_n": Lg,
-                "compulsory_hbm_bytes_per_launch": 12 * nq + 12 * a.intervals,
-                "note": "algorithmic bytes are the reference walk's element-granular traffic (no cache credit); "
-                        "the kernel serves them from L1/L2, so frac can exceed 1 -- see traffic for DRAM bytes"}
+    dk = kernels[dom]
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": dk.get("achieved_gbs"), "peak": peak, "unit": "GB/s",
+                "frac": (dk.get("achieved_gbs") or 0.0) / peak, "peak_source": peak_src, "traffic": traffic,
+                "kernel_ms": dk["ms_per_launch"], "launches_per_step": dk["launches_per_step"],
+                "share_of_step": dk["ms_per_step"] / ms_per_step,
+                "algorithmic_bytes_per_launch": dk.get("algorithmic_bytes_per_launch"),
+                "whole_step": {"compulsory_hbm_bytes": 12 * nq + 16 * a.intervals,
+                               "compulsory_gbs": (12 * nq + 16 * a.intervals) / (ms_per_step * 1e-3) / 1e9,
+                               "reference_walk_bytes_per_query": a_walk, "hits_per_query": h_per_q,
+                               "jumps_per_query_sampled": j_per_q, "log2_n": Lg,
+                               "reference_walk_gbs": a_walk * nq / (ms_per_step * 1e-3) / 1e9},
+                "note": "per-launch CUDA events recorded by the library on the launching stream (SI_OPT_TIMING); "
+                        "algorithmic bytes per kernel are defined in DESIGN.md section 4"}
 
     parity = {"sample": int(stat_n), "mismatches": int((orc.count_batch(qs[:stat_n], qe[:stat_n]).astype(np.int64)
                                                         != counts[:stat_n].cpu().numpy().astype(np.uint32).astype(np.int64)).sum()),
@@ -352,17 +466,19 @@ def main():
             "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": workload_name(a), "intervals": a.intervals, "queries_per_gpu": nq,
-                       "step": "device radix sort of the batch by start + count kernel" if a.order == "shuffled"
-                               else "count kernel on position-sorted queries",
+                       "step": (f"device partition of the batch by position ({passes} onesweep passes over 12-byte records) + count kernel"
+                                if a.order == "shuffled" else "count kernel on position-sorted queries"),
+                       "count_algo": a.algo,
                        "l2": "inputs larger than L2: 800 MB of queries + 400 MB of counts per step vs 126 MB",
                        "index": "replicated per GPU", "collective": "all_gather of per-rank hit totals (CSR bases)"},
             "e2e": {"value": world * nq / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * nq,
                     "d2h_bytes_per_step": 8 * nq, "ms_per_step": e2e_s * 1e3,
+                    "pcie_gbs_each_way": 8 * nq / e2e_s / 1e9,
                     "call": "countOverlapsBatch(si, qs, qe, n, size_t* counts) with pinned host buffers"},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "parity": parity, "build_ms": build_ms, "count_kernel_ms": count_kernel_ms_max,
-            "shard_hits": shard_hits, "shard_csr_base": shard_base,
-            "device_bytes": ix.device_bytes}
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
+            "cpu_baseline": cpu_baseline, "parity": parity, "build_ms": build_ms,
+            "shard_hits": shard_hits, "shard_csr_base": shard_base, "device_bytes": ix.device_bytes,
+            "search_values": sv}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

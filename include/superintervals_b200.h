@@ -86,7 +86,7 @@ typedef struct {
 enum {
     SI_ORDER_AUTO = 0,       /* check on device (one small host sync), sort if needed */
     SI_ORDER_SORTED = 1,     /* caller guarantees query STARTS are non-decreasing (position-sorted, as `bedtools sort`) */
-    SI_ORDER_UNSORTED = 2,   /* radix-sort the batch by start on device, scatter results back */
+    SI_ORDER_UNSORTED = 2,   /* partition the batch by position on device first; results still go to the caller's slots */
     SI_ORDER_ASIS = 3        /* process in the given order whatever it is */
 };
 enum { SI_FILL_VALUES = 0, SI_FILL_IDXS = 1, SI_FILL_KEYS = 2, SI_FILL_ITEMS = 3 };
@@ -112,19 +112,37 @@ int siCountDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t 
                   uint32_t* d_counts, int order, void* stream);
 int siCountDevice64(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n,
                     uint64_t* d_counts, int order, void* stream);
-/* Optional explicit first half of an SI_ORDER_UNSORTED count: radix-sort the batch by
- * start now; the NEXT siCountDevice(.., SI_ORDER_UNSORTED, ..) on the same (d_qs, n)
- * consumes that sort instead of redoing it (one-shot). Lets callers overlap or time
- * the two phases separately. */
-int siSortQueriesDevice(siIndex* ix, const int32_t* d_qs, size_t n, void* stream);
+/* Optional explicit first half of an SI_ORDER_UNSORTED count: partition the batch by
+ * position now (records of start, end, index grouped by result window and position
+ * bucket); the NEXT siCountDevice(.., SI_ORDER_UNSORTED, ..) on the same (d_qs, d_qe, n)
+ * consumes that partition instead of redoing it (one-shot). Lets callers overlap or time
+ * the two phases separately. No-op for batches above 2^27 queries (those are sliced). */
+int siSortQueriesDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, void* stream);
+
+/* Tunables of one index. SI_OPT_COUNT_ALGO: which count kernel answers batches --
+ * SI_COUNT_WALK is the tile sweep + branch-array walk (the reference's algorithm,
+ * hpp:651-825, on any index); SI_COUNT_RANK is the closed form
+ * #{starts <= qe} - #{ends < qs} (valid on an index whose intervals all have
+ * start <= end; queries with qs > qe inside such a batch still take the walk);
+ * SI_COUNT_AUTO picks RANK whenever the index allows it. Results are identical. */
+enum { SI_OPT_COUNT_ALGO = 0, SI_OPT_BUCKET_INTERVALS = 1, SI_OPT_WINDOW_SHIFT = 2, SI_OPT_TIMING = 3 };
+enum { SI_COUNT_AUTO = 0, SI_COUNT_WALK = 1, SI_COUNT_RANK = 2 };
+int siIndexSetOption(siIndex* ix, int option, long long value);
+/* With SI_OPT_TIMING = 1 every hot kernel launch is bracketed by a CUDA event pair on its
+ * own stream. Returns the number of (tag, milliseconds) records written (oldest first) and
+ * clears them; waits for the recorded work. Tags: 1 partition histogram + scan, 2 partition
+ * pass, 3 count (walk), 4 count (rank), 5 CSR scan, 6 CSR fill. bench.py's roofline uses it. */
+enum { SI_TAG_PT_HIST = 1, SI_TAG_PT_PASS = 2, SI_TAG_COUNT_WALK = 3, SI_TAG_COUNT_RANK = 4, SI_TAG_SCAN = 5, SI_TAG_FILL = 6 };
+int siIndexReadTimings(siIndex* ix, int* tags, float* ms, int max_out);
+
 int siAnyDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n,
                 uint8_t* d_out, void* stream);
 /* d_offsets[0..n]: exclusive scan of d_counts, d_offsets[n] = total hits. 16-byte aligned pointers. */
 int siScanDevice(siIndex* ix, const uint32_t* d_counts, size_t n, uint64_t* d_offsets, void* stream);
 /* CSR fill: for query i writes its hits to d_out[d_offsets[i] .. d_offsets[i+1]) in
  * descending position order. what = SI_FILL_*: int32 values, uint32 positions,
- * KeyPair, or Interval records. With SI_ORDER_UNSORTED the sort done by the
- * preceding siCountDevice call on the same (d_qs, n) is reused (do not modify the batch in between). */
+ * KeyPair, or Interval records. With SI_ORDER_UNSORTED the partition made by the
+ * preceding siCountDevice call on the same (d_qs, d_qe, n) is reused (do not modify the batch in between). */
 int siFillDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n,
                  const uint64_t* d_offsets, int what, void* d_out, int order, void* stream);
 /* count + clipped-length sum per query (c_superintervals.h:758-792). */

@@ -16,6 +16,9 @@ SI_NONE = (1 << 64) - 1
 
 ORDER_AUTO, ORDER_SORTED, ORDER_UNSORTED, ORDER_ASIS = 0, 1, 2, 3
 FILL_VALUES, FILL_IDXS, FILL_KEYS, FILL_ITEMS = 0, 1, 2, 3
+OPT_COUNT_ALGO, OPT_BUCKET_INTERVALS, OPT_WINDOW_SHIFT, OPT_TIMING = 0, 1, 2, 3
+TAG_NAMES = {1: "pt_histogram", 2: "pt_onesweep", 3: "count_walk", 4: "count_rank", 5: "scan", 6: "fill"}
+COUNT_AUTO, COUNT_WALK, COUNT_RANK = 0, 1, 2
 
 
 class cSuperIntervals(C.Structure):
@@ -77,7 +80,7 @@ B200_SYMBOLS = [
     "countOverlapsBatch", "anyOverlapsBatch", "searchValuesBatch", "searchIdxsBatch", "searchKeysBatch",
     "searchItemsBatch", "coverageBatch", "siIndexCreate", "siIndexDestroy", "siIndexOf", "siIndexSize",
     "siIndexDeviceView", "siIndexBuildHost", "siIndexBuildDevice", "siIndexExport", "siCountDevice",
-    "siCountDevice64", "siSortQueriesDevice", "siAnyDevice", "siScanDevice", "siFillDevice", "siCoverageDevice",
+    "siCountDevice64", "siSortQueriesDevice", "siIndexSetOption", "siIndexReadTimings", "siAnyDevice", "siScanDevice", "siFillDevice", "siCoverageDevice",
     "siIndexDeviceBytes",
 ]
 
@@ -158,7 +161,11 @@ def bind_b200(L):
     L.siIndexExport.argtypes = [vp, vp, vp, vp, vp, vp]
     L.siCountDevice.argtypes = [vp, vp, vp, sz, vp, C.c_int, vp]
     L.siCountDevice64.argtypes = [vp, vp, vp, sz, vp, C.c_int, vp]
-    L.siSortQueriesDevice.argtypes = [vp, vp, sz, vp]
+    L.siSortQueriesDevice.argtypes = [vp, vp, vp, sz, vp]
+    L.siIndexSetOption.argtypes = [vp, C.c_int, C.c_longlong]
+    L.siIndexSetOption.restype = C.c_int
+    L.siIndexReadTimings.argtypes = [vp, vp, vp, C.c_int]
+    L.siIndexReadTimings.restype = C.c_int
     L.siAnyDevice.argtypes = [vp, vp, vp, sz, vp, vp]
     L.siScanDevice.argtypes = [vp, vp, sz, vp, vp]
     L.siFillDevice.argtypes = [vp, vp, vp, sz, vp, C.c_int, vp, C.c_int, vp]

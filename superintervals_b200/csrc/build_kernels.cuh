@@ -117,6 +117,23 @@ bk_sort_blocks_kernel(const int32_t* __restrict__ ends, uint32_t n_padded, int32
     }
 }
 
+// ---- eall: every end, ascending (count by rank, query_kernels.cuh) ----------------------
+__global__ void __launch_bounds__(BK_THREADS)
+bk_end_keys_kernel(const int32_t* __restrict__ ends, uint32_t n, uint32_t* __restrict__ keys) {
+    const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i < n; i += stride) keys[i] = flip_i32(ends[i]);
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+bk_sorted_ends_kernel(const uint32_t* __restrict__ kA, const uint32_t* __restrict__ kB,
+                      const uint32_t* __restrict__ final_sel, uint32_t n, uint32_t n_padded,
+                      int32_t* __restrict__ eall) {
+    const uint32_t* __restrict__ keys = *final_sel ? kB : kA;
+    const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i < n_padded; i += stride)
+        eall[i] = i < n ? unflip_i32(keys[i]) : INT_MAX;
+}
+
 // ---- 32-ary max tree over ends -------------------------------------------------------
 // level 0 = ends; level L entry k = max of level L-1 entries [32k, 32k+32).
 // One launch produces two levels: a CTA of 1024 threads folds 1024 inputs into

@@ -5,6 +5,7 @@
 
 #include "build_kernels.cuh"
 #include "index.cuh"
+#include "partition.cuh"
 #include "query_kernels.cuh"
 #include "radix_sort.cuh"
 
@@ -54,6 +55,46 @@ int DevBuf::ensure(size_t bytes) {
     cap = want;
     return 0;
 }
+void LaunchTimer::begin(int tag, cudaStream_t s) {
+    if (!on) return;
+    if (used == cap) {
+        const size_t ncap = cap ? cap * 2 : 256;
+        cudaEvent_t* nev = (cudaEvent_t*)realloc(ev, sizeof(cudaEvent_t) * 2 * ncap);
+        int* ntags = (int*)realloc(tags, sizeof(int) * ncap);
+        if (!nev || !ntags) { if (nev) ev = nev; if (ntags) tags = ntags; return; }
+        ev = nev; tags = ntags;
+        for (size_t i = 2 * cap; i < 2 * ncap; ++i)
+            if (cudaEventCreate(&ev[i]) != cudaSuccess) { ev[i] = nullptr; }
+        cap = ncap;
+    }
+    tags[used] = tag;
+    open = cudaEventRecord(ev[2 * used], s) == cudaSuccess;
+}
+void LaunchTimer::end(cudaStream_t s) {
+    if (!on || !open) return;
+    open = false;
+    if (cudaEventRecord(ev[2 * used + 1], s) == cudaSuccess) ++used;
+}
+int LaunchTimer::read(int* out_tags, float* out_ms, int max_out) {
+    int k = 0;
+    for (size_t i = 0; i < used && k < max_out; ++i) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(ev[2 * i + 1]) != cudaSuccess) break;
+        if (cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]) != cudaSuccess) break;
+        out_tags[k] = tags[i];
+        out_ms[k] = ms;
+        ++k;
+    }
+    used = 0;
+    return k;
+}
+void LaunchTimer::release() {
+    for (size_t i = 0; i < 2 * cap; ++i)
+        if (ev[i]) cudaEventDestroy(ev[i]);
+    free(ev); free(tags);
+    ev = nullptr; tags = nullptr; cap = used = 0;
+}
+
 void DevBuf::release() {
     if (p) cudaFree(p);
     p = nullptr;
@@ -63,6 +104,15 @@ void DevBuf::release() {
 
 using namespace sib;
 
+#define SIB_LAUNCH_T(ix, tag, kernel, grid, block, smem, stream, ...)            \
+    do {                                                                        \
+        (ix)->timer.begin((tag), (stream));                                     \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);             \
+        SIB_CHECK_LAUNCH();                                                     \
+        (ix)->timer.end((stream));                                              \
+        note_launch();                                                          \
+    } while (0)
+
 #define SIB_LAUNCH(kernel, grid, block, smem, stream, ...)                      \
     do {                                                                        \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);             \
@@ -71,8 +121,8 @@ using namespace sib;
     } while (0)
 
 size_t siIndex::device_bytes() const {
-    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &esort, &b_in_s, &b_in_e, &b_in_v,
-                           &b_kA, &b_kB, &b_vA, &b_vB, &b_ws, &small, &q_kA, &q_kB, &q_vA, &q_vB,
+    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &esort, &eall, &b_in_s, &b_in_e, &b_in_v,
+                           &b_kA, &b_kB, &b_vA, &b_vB, &b_ws, &small, &q_A, &q_B,
                            &q_ws, &scan_status, &h_qs, &h_qe, &h_counts, &h_offsets, &h_out, &h_cov};
     size_t s = 0;
     for (auto* b : all) s += b->cap;
@@ -102,6 +152,7 @@ IndexView view_of(const siIndex* ix) {
     v.branch = ix->branch.as<uint32_t>();
     v.pmax32 = ix->pmax32;
     v.esort = ix->esort.as<int32_t>();
+    v.eall = ix->eall.as<int32_t>();
     v.n = ix->n;
     v.wellformed = ix->wellformed ? 1u : 0u;
     return v;
@@ -228,6 +279,28 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
                ix->ends.as<int32_t>(), ix->n_padded, ix->esort.as<int32_t>());
     int rc = build_branch(ix, s);
     if (rc) return rc;
+
+    // span of the index on the host (the partition key buckets it); callers synchronise `s`
+    SIB_CHECK(cudaMemcpyAsync(&ix->lo, ix->starts.p, 4, cudaMemcpyDeviceToHost, s));
+    if (ix->wellformed) {
+        // every end, ascending: the second array of the count-by-rank kernel
+        if (ix->eall.ensure(pad_b) || ix->b_kA.ensure(n * 4) || ix->b_kB.ensure(n * 4) || ix->b_vA.ensure(n * 4) ||
+            ix->b_vB.ensure(n * 4) || ix->b_ws.ensure(rs_workspace_bytes<uint32_t>(ix->n)))
+            return last_error_code();
+        SIB_LAUNCH(bk_end_keys_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, ix->ends.as<int32_t>(), ix->n,
+                   ix->b_kA.as<uint32_t>());
+        // payload buffers ride along unused: the sort moves (key, uint32) pairs
+        rc = radix_sort_pairs<uint32_t>(ix->b_kA.as<uint32_t>(), ix->b_kB.as<uint32_t>(), ix->b_vA.as<uint32_t>(),
+                                        ix->b_vB.as<uint32_t>(), ix->n, 32, ix->b_ws.p, ix->sm_count, s);
+        if (rc) return rc;
+        RsWorkspace ws = rs_carve(ix->b_ws.p);
+        SIB_LAUNCH(bk_sorted_ends_kernel, grid_for(ix->n_padded, BK_THREADS, cap), BK_THREADS, 0, s,
+                   ix->b_kA.as<uint32_t>(), ix->b_kB.as<uint32_t>(), ws.final_sel, ix->n, ix->n_padded,
+                   ix->eall.as<int32_t>());
+        SIB_CHECK(cudaMemcpyAsync(&ix->hi, ix->eall.as<int32_t>() + (ix->n - 1), 4, cudaMemcpyDeviceToHost, s));
+    } else {
+        SIB_CHECK(cudaMemcpyAsync(&ix->hi, ix->starts.as<int32_t>() + (ix->n - 1), 4, cudaMemcpyDeviceToHost, s));
+    }
     ix->built = true;
     return 0;
 }
@@ -240,26 +313,26 @@ void release_build_scratch(siIndex* ix) {
     }
 }
 
-// Sort a query batch by start (position order). Leaves the result described by SortedQueries.
-int sort_queries(siIndex* ix, const int32_t* d_qs, uint32_t nq, cudaStream_t s, SortedQueries* out, bool may_reuse) {
-    if (ix->q_kA.ensure((size_t)nq * 4) || ix->q_kB.ensure((size_t)nq * 4) || ix->q_vA.ensure((size_t)nq * 4) ||
-        ix->q_vB.ensure((size_t)nq * 4) || ix->q_ws.ensure(rs_workspace_bytes<uint32_t>(nq)))
+// Partition a query batch for locality (partition.cuh): records grouped by (result window,
+// position bucket). *out describes the partitioned records; the partition of the same
+// (d_qs, d_qe, nq) may be reused by the fill that follows a count (documented contract).
+int partition_queries(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, uint32_t nq, cudaStream_t s,
+                      QueryRecords* out, bool may_reuse) {
+    if (may_reuse && ix->plan_valid && ix->plan_qs == d_qs && ix->plan_qe == d_qe && ix->plan_n == nq) {
+        out->qs = ix->plan_rec_qs; out->qe = ix->plan_rec_qe; out->idx = ix->plan_rec_idx;
+        return 0;
+    }
+    ix->plan_valid = false;
+    const PtPlan plan = pt_make_plan(nq, ix->n, ix->lo, ix->hi, ix->bucket_intervals, ix->window_shift);
+    const size_t cap = ((size_t)nq + 63) & ~(size_t)63;
+    if (plan.passes > 0 && (ix->q_A.ensure(cap * 12) || (plan.passes > 1 && ix->q_B.ensure(cap * 12)) ||
+                            ix->q_ws.ensure(pt_workspace_bytes(nq))))
         return last_error_code();
-    RsWorkspace ws = rs_carve(ix->q_ws.p);
-    out->keysA = ix->q_kA.as<uint32_t>();
-    out->keysB = ix->q_kB.as<uint32_t>();
-    out->permA = ix->q_vA.as<uint32_t>();
-    out->permB = ix->q_vB.as<uint32_t>();
-    out->sel = ws.final_sel;
-    // fill may reuse the sort its preceding count made for the same batch (documented contract)
-    if (may_reuse && ix->plan_valid && ix->plan_qs == d_qs && ix->plan_n == nq) return 0;
-    SIB_LAUNCH(qk_make_query_keys_kernel, grid_for(nq, QK_THREADS, ix->sm_count * 16), QK_THREADS, 0, s, d_qs, nq,
-               ix->q_kA.as<uint32_t>(), ix->q_vA.as<uint32_t>());
-    int rc = radix_sort_pairs<uint32_t>(ix->q_kA.as<uint32_t>(), ix->q_kB.as<uint32_t>(), ix->q_vA.as<uint32_t>(),
-                                        ix->q_vB.as<uint32_t>(), nq, 32, ix->q_ws.p, ix->sm_count, s);
+    int rc = pt_partition(plan, d_qs, d_qe, nq, ix->q_A.p, ix->q_B.p, cap, ix->q_ws.p, ix->sm_count, s, out,
+                          &ix->timer);
     if (rc) return rc;
-    ix->plan_qs = d_qs;
-    ix->plan_n = nq;
+    ix->plan_qs = d_qs; ix->plan_qe = d_qe; ix->plan_n = nq;
+    ix->plan_rec_qs = out->qs; ix->plan_rec_qe = out->qe; ix->plan_rec_idx = out->idx;
     ix->plan_valid = true;
     return 0;
 }
@@ -280,6 +353,19 @@ int resolve_order(siIndex* ix, const int32_t* d_qs, uint32_t nq, int order, cuda
 }
 
 template <typename CountT>
+int launch_count(siIndex* ix, const QueryRecords& rec, uint32_t nq, CountT* d_counts, cudaStream_t s) {
+    const bool rank = ix->wellformed && ix->count_algo != SI_COUNT_WALK;
+    if (rank) {
+        const int grid = (int)(((uint64_t)nq + QR_TILE - 1) / QR_TILE);
+        SIB_LAUNCH_T(ix, TAG_COUNT_RANK, (qk_count_rank_kernel<CountT>), grid, QR_THREADS, 0, s, view_of(ix), rec, nq, d_counts);
+    } else {
+        const int grid = (int)(((uint64_t)nq + QK_THREADS - 1) / QK_THREADS);
+        SIB_LAUNCH_T(ix, TAG_COUNT_WALK, (qk_count_kernel<CountT>), grid, QK_THREADS, 0, s, view_of(ix), rec, nq, d_counts);
+    }
+    return 0;
+}
+
+template <typename CountT>
 int count_impl(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, CountT* d_counts, int order,
                void* stream) {
     if (!ix || !ix->built) {
@@ -293,34 +379,36 @@ int count_impl(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, 
     }
     DeviceGuard g(ix->device);
     cudaStream_t s = pick_stream(ix, stream);
-    const uint32_t nq = (uint32_t)n;
     if (ix->n == 0) {
         SIB_CHECK(cudaMemsetAsync(d_counts, 0, n * sizeof(CountT), s));
         return 0;
     }
-    order = resolve_order(ix, d_qs, nq, order, s);
+    order = resolve_order(ix, d_qs, (uint32_t)n, order, s);
     if (order < 0) { set_error(cudaGetLastError(), "resolve_order", __FILE__, __LINE__); return last_error_code(); }
-    const int grid = (int)(((uint64_t)nq + QK_THREADS - 1) / QK_THREADS);
-    SortedQueries sq;
-    memset(&sq, 0, sizeof(sq));
-    if (order == SI_ORDER_UNSORTED) {
-        // an explicit siSortQueriesDevice() on this batch arms a one-shot reuse; otherwise sort now
-        int rc = sort_queries(ix, d_qs, nq, s, &sq, ix->plan_armed);
-        ix->plan_armed = false;
+    const bool armed = ix->plan_armed;
+    ix->plan_armed = false;
+    // batches beyond the partition's size are processed in slices (their scratch is bounded too)
+    for (size_t at = 0; at < n; at += PT_MAX_BATCH) {
+        const uint32_t m = (uint32_t)(n - at < PT_MAX_BATCH ? n - at : PT_MAX_BATCH);
+        QueryRecords rec{d_qs + at, d_qe + at, nullptr};
+        if (order == SI_ORDER_UNSORTED) {
+            // an explicit siSortQueriesDevice() on this batch arms a one-shot reuse; otherwise partition now
+            int rc = partition_queries(ix, d_qs + at, d_qe + at, m, s, &rec, armed && n <= PT_MAX_BATCH);
+            if (rc) return rc;
+        } else {
+            ix->plan_valid = false;
+        }
+        int rc = launch_count<CountT>(ix, rec, m, d_counts + at, s);
         if (rc) return rc;
-        SIB_LAUNCH((qk_count_kernel<CountT, true>), grid, QK_THREADS, 0, s, view_of(ix), d_qs, d_qe, sq, nq, d_counts);
-    } else {
-        ix->plan_valid = false;
-        SIB_LAUNCH((qk_count_kernel<CountT, false>), grid, QK_THREADS, 0, s, view_of(ix), d_qs, d_qe, sq, nq, d_counts);
     }
     return 0;
 }
 
-template <int MODE, bool PERM>
-int launch_fill(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, const SortedQueries& sq, uint32_t nq,
-                const uint64_t* d_offsets, void* d_out, cudaStream_t s) {
+template <int MODE>
+int launch_fill(siIndex* ix, const QueryRecords& rec, uint32_t nq, const uint64_t* d_offsets, void* d_out,
+                cudaStream_t s) {
     const int grid = (int)(((uint64_t)nq + QK_THREADS - 1) / QK_THREADS);
-    SIB_LAUNCH((qk_fill_kernel<MODE, PERM>), grid, QK_THREADS, 0, s, view_of(ix), d_qs, d_qe, sq, nq, d_offsets,
+    SIB_LAUNCH_T(ix, TAG_FILL, (qk_fill_kernel<MODE>), grid, QK_THREADS, 0, s, view_of(ix), rec, nq, d_offsets,
                reinterpret_cast<typename FillOut<MODE>::T*>(d_out));
     return 0;
 }
@@ -364,9 +452,9 @@ siIndex* siIndexCreate(void) {
 void siIndexDestroy(siIndex* ix) {
     if (!ix) return;
     DeviceGuard g(ix->device);
-    DevBuf* all[] = {&ix->starts, &ix->ends, &ix->values, &ix->branch, &ix->perm, &ix->tree, &ix->esort, &ix->b_in_s,
-                     &ix->b_in_e, &ix->b_in_v, &ix->b_kA, &ix->b_kB, &ix->b_vA, &ix->b_vB, &ix->b_ws, &ix->small,
-                     &ix->q_kA, &ix->q_kB, &ix->q_vA, &ix->q_vB, &ix->q_ws, &ix->scan_status, &ix->h_qs,
+    DevBuf* all[] = {&ix->starts, &ix->ends, &ix->values, &ix->branch, &ix->perm, &ix->tree, &ix->esort, &ix->eall,
+                     &ix->b_in_s, &ix->b_in_e, &ix->b_in_v, &ix->b_kA, &ix->b_kB, &ix->b_vA, &ix->b_vB, &ix->b_ws,
+                     &ix->small, &ix->q_A, &ix->q_B, &ix->q_ws, &ix->scan_status, &ix->h_qs,
                      &ix->h_qe, &ix->h_counts, &ix->h_offsets, &ix->h_out, &ix->h_cov};
     for (auto* b : all) b->release();
     if (ix->pipe_ready) {
@@ -374,6 +462,7 @@ void siIndexDestroy(siIndex* ix) {
         cudaStreamDestroy(ix->s_out);
         for (int k = 0; k < 2; ++k) { cudaEventDestroy(ix->e_in[k]); cudaEventDestroy(ix->e_k[k]); cudaEventDestroy(ix->e_out[k]); }
     }
+    ix->timer.release();
     if (ix->pinned) cudaFreeHost(ix->pinned);
     if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
     delete ix;
@@ -454,15 +543,51 @@ int siCountDevice64(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_
     return count_impl<uint64_t>(ix, d_qs, d_qe, n, d_counts, order, stream);
 }
 
-int siSortQueriesDevice(siIndex* ix, const int32_t* d_qs, size_t n, void* stream) {
-    if (!ix) return cudaErrorInvalidValue;
-    if (n == 0) return 0;
-    if (n > 0xFFFFFFFFull) return cudaErrorInvalidValue;
+int siSortQueriesDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, void* stream) {
+    if (!ix || !ix->built) {
+        set_error_msg(cudaErrorNotReady, "siSortQueriesDevice: index not built");
+        return cudaErrorNotReady;
+    }
+    if (n == 0 || ix->n == 0) return 0;
+    if (n > PT_MAX_BATCH) return 0;   // larger batches are partitioned slice by slice inside the query calls
     DeviceGuard g(ix->device);
-    SortedQueries sq;
-    int rc = sort_queries(ix, d_qs, (uint32_t)n, pick_stream(ix, stream), &sq, false);
+    QueryRecords rec;
+    int rc = partition_queries(ix, d_qs, d_qe, (uint32_t)n, pick_stream(ix, stream), &rec, false);
     ix->plan_armed = rc == 0;
     return rc;
+}
+
+int siIndexReadTimings(siIndex* ix, int* tags, float* ms, int max_out) {
+    if (!ix || !tags || !ms || max_out < 0) return 0;
+    DeviceGuard g(ix->device);
+    return ix->timer.read(tags, ms, max_out);
+}
+
+int siIndexSetOption(siIndex* ix, int option, long long value) {
+    if (!ix) return cudaErrorInvalidValue;
+    switch (option) {
+        case SI_OPT_COUNT_ALGO:
+            if (value < SI_COUNT_AUTO || value > SI_COUNT_RANK) break;
+            ix->count_algo = (int)value;
+            return 0;
+        case SI_OPT_BUCKET_INTERVALS:
+            if (value < 1 || value > (1ll << 30)) break;
+            ix->bucket_intervals = (uint32_t)value;
+            ix->plan_valid = false;
+            return 0;
+        case SI_OPT_TIMING:
+            ix->timer.on = value != 0;
+            ix->timer.used = 0;
+            return 0;
+        case SI_OPT_WINDOW_SHIFT:
+            if (value < 10 || value > 31) break;
+            ix->window_shift = (uint32_t)value;
+            ix->plan_valid = false;
+            return 0;
+        default: break;
+    }
+    set_error_msg(cudaErrorInvalidValue, "siIndexSetOption: unknown option or value out of range");
+    return cudaErrorInvalidValue;
 }
 
 int siAnyDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, uint8_t* d_out, void* stream) {
@@ -497,7 +622,7 @@ int siScanDevice(siIndex* ix, const uint32_t* d_counts, size_t n, uint64_t* d_of
     uint32_t* ticket = ix->small.as<uint32_t>() + 2;
     SIB_CHECK(cudaMemsetAsync(ix->scan_status.p, 0, (size_t)tiles * 8, s));
     SIB_CHECK(cudaMemsetAsync(ticket, 0, 4, s));
-    SIB_LAUNCH(qk_scan_kernel, tiles, SC_THREADS, 0, s, d_counts, (uint32_t)n, d_offsets,
+    SIB_LAUNCH_T(ix, TAG_SCAN, qk_scan_kernel, tiles, SC_THREADS, 0, s, d_counts, (uint32_t)n, d_offsets,
                ix->scan_status.as<unsigned long long>(), ticket);
     return 0;
 }
@@ -515,26 +640,27 @@ int siFillDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n
     const uint32_t nq = (uint32_t)n;
     order = resolve_order(ix, d_qs, nq, order, s);
     if (order < 0) { set_error(cudaGetLastError(), "resolve_order", __FILE__, __LINE__); return last_error_code(); }
-    SortedQueries sq;
-    memset(&sq, 0, sizeof(sq));
-    const bool perm = order == SI_ORDER_UNSORTED;
-    if (perm) {
-        int rc = sort_queries(ix, d_qs, nq, s, &sq, true);
+    if (what < SI_FILL_VALUES || what > SI_FILL_ITEMS) {
+        set_error_msg(cudaErrorInvalidValue, "siFillDevice: unknown fill mode");
+        return cudaErrorInvalidValue;
+    }
+    for (size_t at = 0; at < n; at += PT_MAX_BATCH) {
+        const uint32_t m = (uint32_t)(n - at < PT_MAX_BATCH ? n - at : PT_MAX_BATCH);
+        QueryRecords rec{d_qs + at, d_qe + at, nullptr};
+        if (order == SI_ORDER_UNSORTED) {
+            int rc = partition_queries(ix, d_qs + at, d_qe + at, m, s, &rec, n <= PT_MAX_BATCH);
+            if (rc) return rc;
+        }
+        int rc = 0;
+        switch (what) {
+            case SI_FILL_VALUES: rc = launch_fill<FILL_VALUES>(ix, rec, m, d_offsets + at, d_out, s); break;
+            case SI_FILL_IDXS: rc = launch_fill<FILL_IDXS>(ix, rec, m, d_offsets + at, d_out, s); break;
+            case SI_FILL_KEYS: rc = launch_fill<FILL_KEYS>(ix, rec, m, d_offsets + at, d_out, s); break;
+            default: rc = launch_fill<FILL_ITEMS>(ix, rec, m, d_offsets + at, d_out, s); break;
+        }
         if (rc) return rc;
     }
-#define SIB_FILL(M)                                                                              \
-    return perm ? launch_fill<M, true>(ix, d_qs, d_qe, sq, nq, d_offsets, d_out, s)              \
-                : launch_fill<M, false>(ix, d_qs, d_qe, sq, nq, d_offsets, d_out, s)
-    switch (what) {
-        case SI_FILL_VALUES: SIB_FILL(FILL_VALUES);
-        case SI_FILL_IDXS: SIB_FILL(FILL_IDXS);
-        case SI_FILL_KEYS: SIB_FILL(FILL_KEYS);
-        case SI_FILL_ITEMS: SIB_FILL(FILL_ITEMS);
-        default: break;
-    }
-#undef SIB_FILL
-    set_error_msg(cudaErrorInvalidValue, "siFillDevice: unknown fill mode");
-    return cudaErrorInvalidValue;
+    return 0;
 }
 
 int siCoverageDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, uint32_t* d_counts,

@@ -19,6 +19,21 @@ struct DevBuf {
 void note_launch(unsigned n = 1);
 unsigned long long launches();
 
+// Optional per-launch device timing (siIndexSetOption SI_OPT_TIMING): a CUDA event pair on the
+// launching stream around each hot kernel, read back by siIndexReadTimings. Off by default.
+enum LaunchTag : int { TAG_PT_HIST = 1, TAG_PT_PASS = 2, TAG_COUNT_WALK = 3, TAG_COUNT_RANK = 4, TAG_SCAN = 5, TAG_FILL = 6 };
+struct LaunchTimer {
+    bool on = false;
+    cudaEvent_t* ev = nullptr;   // 2 * cap events
+    int* tags = nullptr;
+    size_t cap = 0, used = 0;
+    bool open = false;
+    void begin(int tag, cudaStream_t s);
+    void end(cudaStream_t s);
+    int read(int* out_tags, float* out_ms, int max_out);   // synchronises the recorded events, then clears
+    void release();
+};
+
 }  // namespace sib
 
 struct siIndex {
@@ -32,6 +47,8 @@ struct siIndex {
     bool wellformed = false;   // every interval has start <= end (enables the count shortcut)
     sib::DevBuf starts, ends, values, branch, perm;
     sib::DevBuf esort;         // ends, each aligned 32-block sorted ascending (count sweep)
+    sib::DevBuf eall;          // all ends sorted ascending (count by rank); well-formed indexes only
+    int32_t lo = 0, hi = 0;    // smallest start / largest end: the span the partition key buckets
     sib::DevBuf tree;          // 32-ary max tree levels + prefix-max levels
     const int32_t* pmax32 = nullptr;   // inside `tree`: exclusive prefix max of ends per 32-block
 
@@ -41,12 +58,23 @@ struct siIndex {
 
     // ---- query scratch ---------------------------------------------------------------
     sib::DevBuf small;                          // device scalars: [0] flags/sorted, ...
-    sib::DevBuf q_kA, q_kB, q_vA, q_vB, q_ws;   // 32-bit key sort of a query batch
+    sib::DevBuf q_A, q_B, q_ws;                 // partitioned query records (qs | qe | idx) x 2, workspace
     sib::DevBuf scan_status;
-    const int32_t* plan_qs = nullptr;           // query batch the cached sort belongs to
+    const int32_t* plan_qs = nullptr;           // query batch the cached partition belongs to
+    const int32_t* plan_qe = nullptr;
     size_t plan_n = 0;
+    const int32_t* plan_rec_qs = nullptr;       // where its records are (inside q_A / q_B)
+    const int32_t* plan_rec_qe = nullptr;
+    const uint32_t* plan_rec_idx = nullptr;
     bool plan_valid = false;
     bool plan_armed = false;                    // set by siSortQueriesDevice: next count may reuse
+
+    sib::LaunchTimer timer;
+
+    // ---- options (siIndexSetOption) ----------------------------------------------------
+    int count_algo = 0;                         // SI_COUNT_AUTO / SI_COUNT_WALK / SI_COUNT_RANK
+    uint32_t bucket_intervals = 1024;           // partition: index intervals per position bucket
+    uint32_t window_shift = 22;                 // partition: log2(queries per result window)
 
     // ---- staging for the host-buffer API ---------------------------------------------
     sib::DevBuf h_qs, h_qe, h_counts, h_offsets, h_out, h_cov;

@@ -20,6 +20,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "partition.cuh"
 #include <limits.h>
 
 namespace sib {
@@ -34,19 +35,9 @@ struct IndexView {
     const uint32_t* branch;  // NONE32 = no previous interval reaches this far
     const int32_t* pmax32;   // pmax32[b] = max(ends[0 .. 32b-1]) (INT_MIN for b = 0), from build()
     const int32_t* esort;    // ends with every aligned 32-block sorted ascending (n_pad entries), from build()
+    const int32_t* eall;     // all ends sorted ascending (n entries), from build(); only on a well-formed index
     uint32_t n;
     uint32_t wellformed;     // 1 when every stored interval has start <= end (checked by build())
-};
-
-// A query batch radix-sorted by START (position order, what `bedtools sort` gives):
-// keys = flipped qs in sorted order, perm = original query index. *sel (device) says
-// which of the sort's two buffers holds the result.
-struct SortedQueries {
-    const uint32_t* keysA;
-    const uint32_t* keysB;
-    const uint32_t* permA;
-    const uint32_t* permB;
-    const uint32_t* sel;
 };
 
 // Number of starts <= v, by the reference's branch-free halving search (hpp:501-513).
@@ -145,6 +136,27 @@ __device__ __forceinline__ uint32_t block_hits_sorted(const int32_t* __restrict_
     return 32u - c;
 }
 
+// Finish the walks of one warp's queries: lane-parallel (4 intervals per step) while enough
+// lanes are busy, then warp-cooperative for the stragglers, one query at a time. `i` is the
+// lane's next interval to visit (NONE32 = nothing left); hits are added to `c`. Whole-warp call.
+__device__ __forceinline__ void walk_tail(const IndexView& ix, uint32_t i, int32_t qs, uint32_t& c, uint32_t lane) {
+    uint32_t active = __ballot_sync(FULL_MASK, i != NONE32);
+    int iter = 0;
+    while (keep_lane_phase(active, iter)) {
+        if (i != NONE32) i = walk_step4(ix, i, qs, c);
+        active = __ballot_sync(FULL_MASK, i != NONE32);
+        ++iter;
+    }
+    while (active) {
+        const int src = __ffs(active) - 1;
+        active &= active - 1;
+        const uint32_t bi = __shfl_sync(FULL_MASK, i, src);
+        const int32_t bqs = __shfl_sync(FULL_MASK, qs, src);
+        const uint32_t bc = walk_warp128(ix, bi, bqs, lane);
+        if ((int)lane == src) c += bc;
+    }
+}
+
 constexpr uint32_t QK_DENSE_SPAN = 256;      // max spread of upper bounds inside a tile for the sweep
 constexpr uint32_t QK_DENSE_MIN_HITS = 8;    // a 32-interval chunk must yield this many hits tile-wide
 constexpr int QK_DENSE_MAX_CHUNKS = 256;     // then the sparse tail goes to the branch walk
@@ -164,12 +176,11 @@ constexpr int QK_DENSE_MAX_CHUNKS = 256;     // then the sparse tail goes to the
 //           or when blocks stop producing hits.
 //   walk    whatever remains (sparse, far-reaching containers) is finished by the
 //           branch-array walk: lane-parallel first, warp-cooperative for stragglers.
-// SORTED_VIA_PERM: queries were radix-sorted by qe (see SortedQueries); qs is gathered
-// through the permutation and the count is scattered back to the caller's order.
-template <typename CountT, bool SORTED_VIA_PERM>
+// Queries arrive as records (partition.cuh): either the caller's arrays as they are
+// (rec.idx == nullptr) or the partitioned copy, whose idx says where each count goes.
+template <typename CountT>
 __global__ void __launch_bounds__(QK_THREADS)
-qk_count_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* __restrict__ qe_in,
-                SortedQueries sq, uint32_t nq, CountT* __restrict__ counts) {
+qk_count_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __restrict__ counts) {
     const uint64_t t64 = (uint64_t)blockIdx.x * QK_THREADS + threadIdx.x;
     const bool live = t64 < nq;
     const uint32_t t = (uint32_t)t64;
@@ -178,14 +189,9 @@ qk_count_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* 
     uint32_t q = t;
     int32_t qs = INT_MAX, qe = 0;
     if (live) {
-        if (SORTED_VIA_PERM) {
-            const bool useB = *sq.sel != 0;
-            q = ld_stream((useB ? sq.permB : sq.permA) + t);
-            qs = unflip_i32(ld_stream((useB ? sq.keysB : sq.keysA) + t));
-        } else {
-            qs = ld_stream(qs_in + t);
-        }
-        qe = ld_stream(qe_in + q);
+        qs = ld_stream(rec.qs + t);
+        qe = ld_stream(rec.qe + t);
+        if (rec.idx) q = ld_stream(rec.idx + t);
     }
 
     // Candidates are the intervals [0, lim) with start <= qe. When every stored interval is
@@ -263,24 +269,151 @@ qk_count_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* 
     }
     if (top == 0) c = 0;
 
-    // ---- walk, lane-parallel: 4 intervals per step
-    uint32_t active = __ballot_sync(FULL_MASK, i != NONE32);
-    int iter = 0;
-    while (keep_lane_phase(active, iter)) {
-        if (i != NONE32) i = walk_step4(ix, i, qs, c);
-        active = __ballot_sync(FULL_MASK, i != NONE32);
-        ++iter;
-    }
-    // ---- walk, warp-cooperative: stragglers one query at a time
-    while (active) {
-        const int src = __ffs(active) - 1;
-        active &= active - 1;
-        const uint32_t bi = __shfl_sync(FULL_MASK, i, src);
-        const int32_t bqs = __shfl_sync(FULL_MASK, qs, src);
-        const uint32_t bc = walk_warp128(ix, bi, bqs, lane);
-        if ((int)lane == src) c += bc;
-    }
+    walk_tail(ix, i, qs, c, lane);
     if (live) counts[q] = (CountT)(c0 + c);
+}
+
+// ---- count by rank -----------------------------------------------------------------------
+// On an index whose intervals are all well formed (start <= end, checked by build()) and for
+// a query with qs <= qe, the walk's answer  #{ j : starts[j] <= qe, ends[j] >= qs }  has a
+// closed form: an interval that ends before qs also starts before qs <= qe, so it is among
+// the candidates, hence
+//       count = #{ starts <= qe }  -  #{ ends < qs }
+// -- the reference's upper_bound (hpp:501-513) on starts, and the same search on build()'s
+// ascending copy of the ends (IndexView::eall). One CTA takes 512 queries that the partition
+// (or the caller) made neighbours in position: it brackets the two rank ranges of the whole
+// tile with four warp-cooperative 32-ary searches, stages those two short windows of the
+// index in shared memory, and every thread finishes its two queries with branch-free
+// halving searches over shared memory. Queries with qs > qe (quirk Q6: the closed form does
+// not hold) are answered by the branch-array walk in the same kernel. Bit-exact with
+// qk_count_kernel on every input it accepts (tests/test_gpu_parity.py runs both).
+constexpr int QR_THREADS = 256;
+constexpr int QR_PER_THREAD = 2;
+constexpr uint32_t QR_TILE = QR_THREADS * QR_PER_THREAD;
+constexpr uint32_t QR_WINDOW_MAX = 6144;   // staged entries (starts + sorted ends) per CTA: 24 KB
+
+// #{ a[0..n) below v } for a sorted global array, one warp: 32 probes per round, 5 rounds for 10 M
+template <bool STRICT>
+__device__ __forceinline__ uint32_t warp_rank(const int32_t* __restrict__ a, uint32_t n, int32_t v, uint32_t lane) {
+    uint32_t lo = 0, len = n;   // the answer lies in [lo, lo + len]
+    while (len > 0) {
+        const uint32_t step = (len + 31u) >> 5;
+        const uint32_t off = lane * step;
+        bool below = false;
+        if (off < len) {
+            const int32_t x = ld_nc(a + lo + off);
+            below = STRICT ? (x < v) : (x <= v);
+        }
+        const uint32_t cnt = __popc(__ballot_sync(FULL_MASK, below));
+        if (cnt == 0) break;                              // a[lo] is not below v
+        const uint32_t base = (cnt - 1u) * step + 1u;     // a[lo + (cnt-1)*step] is below v ...
+        const uint32_t hi = min(cnt * step, len);         // ... and a[lo + cnt*step], if probed, is not
+        lo += base;
+        len = hi - base;
+    }
+    return lo;
+}
+
+template <typename CountT>
+__global__ void __launch_bounds__(QR_THREADS, 6)
+qk_count_rank_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __restrict__ counts) {
+    __shared__ int32_t s_win[QR_WINDOW_MAX];
+    __shared__ int32_t s_red[4][QR_THREADS / 32];
+    __shared__ uint32_t s_bound[4];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint64_t base = (uint64_t)blockIdx.x * QR_TILE;
+
+    int32_t qs[QR_PER_THREAD], qe[QR_PER_THREAD];
+    uint32_t q[QR_PER_THREAD];
+    bool live[QR_PER_THREAD], ok[QR_PER_THREAD];
+    int32_t mn_s = INT_MAX, mx_s = INT_MIN, mn_e = INT_MAX, mx_e = INT_MIN;
+#pragma unroll
+    for (int j = 0; j < QR_PER_THREAD; ++j) {
+        const uint64_t t = base + (uint64_t)j * QR_THREADS + tid;
+        live[j] = t < nq;
+        qs[j] = live[j] ? ld_stream(rec.qs + t) : 0;
+        qe[j] = live[j] ? ld_stream(rec.qe + t) : 0;
+        q[j] = (live[j] && rec.idx) ? ld_stream(rec.idx + t) : (uint32_t)t;
+        ok[j] = live[j] && qs[j] <= qe[j];
+        if (ok[j]) {
+            mn_s = min(mn_s, qs[j]); mx_s = max(mx_s, qs[j]);
+            mn_e = min(mn_e, qe[j]); mx_e = max(mx_e, qe[j]);
+        }
+    }
+    mn_s = __reduce_min_sync(FULL_MASK, mn_s); mx_s = __reduce_max_sync(FULL_MASK, mx_s);
+    mn_e = __reduce_min_sync(FULL_MASK, mn_e); mx_e = __reduce_max_sync(FULL_MASK, mx_e);
+    if (lane == 0) { s_red[0][warp] = mn_s; s_red[1][warp] = mx_s; s_red[2][warp] = mn_e; s_red[3][warp] = mx_e; }
+    __syncthreads();
+    if (warp < 4) {
+        // warp 0: #ends < min qs, warp 1: #ends < max qs, warp 2: #starts <= min qe, warp 3: #starts <= max qe
+        const bool is_min = (warp & 1u) == 0;
+        int32_t v = lane < QR_THREADS / 32 ? s_red[warp][lane] : (is_min ? INT_MAX : INT_MIN);
+        v = is_min ? __reduce_min_sync(FULL_MASK, v) : __reduce_max_sync(FULL_MASK, v);
+        const uint32_t r = warp < 2 ? warp_rank<true>(ix.eall, ix.n, v, lane) : warp_rank<false>(ix.starts, ix.n, v, lane);
+        if (lane == 0) s_bound[warp] = r;
+    }
+    __syncthreads();
+    const uint32_t e_lo = s_bound[0], s_lo = s_bound[2];
+    const uint32_t w_e = s_bound[1] > e_lo ? s_bound[1] - e_lo : 0u;   // a tile without a valid query has empty windows
+    const uint32_t w_s = s_bound[3] > s_lo ? s_bound[3] - s_lo : 0u;
+    const bool staged = w_e + w_s <= QR_WINDOW_MAX;
+
+    uint32_t pe[QR_PER_THREAD], ps[QR_PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < QR_PER_THREAD; ++j) pe[j] = ps[j] = 0;
+    if (staged) {
+        const int32_t* __restrict__ ge = ix.eall + e_lo;
+        const int32_t* __restrict__ gs = ix.starts + s_lo;
+        for (uint32_t k = tid; k < w_e; k += QR_THREADS) s_win[k] = ld_nc(ge + k);
+        for (uint32_t k = tid; k < w_s; k += QR_THREADS) s_win[w_e + k] = ld_nc(gs + k);
+        __syncthreads();
+        const int32_t* we = s_win;
+        const int32_t* ws = s_win + w_e;
+        if (w_e) {
+            uint32_t len = w_e;
+            while (len > 1) {
+                const uint32_t half = len >> 1;
+#pragma unroll
+                for (int j = 0; j < QR_PER_THREAD; ++j) pe[j] += (we[pe[j] + half] < qs[j]) ? (len - half) : 0u;
+                len = half;
+            }
+#pragma unroll
+            for (int j = 0; j < QR_PER_THREAD; ++j) pe[j] += (we[pe[j]] < qs[j]) ? 1u : 0u;
+        }
+        if (w_s) {
+            uint32_t len = w_s;
+            while (len > 1) {
+                const uint32_t half = len >> 1;
+#pragma unroll
+                for (int j = 0; j < QR_PER_THREAD; ++j) ps[j] += (ws[ps[j] + half] <= qe[j]) ? (len - half) : 0u;
+                len = half;
+            }
+#pragma unroll
+            for (int j = 0; j < QR_PER_THREAD; ++j) ps[j] += (ws[ps[j]] <= qe[j]) ? 1u : 0u;
+        }
+    } else {
+        // the tile spans too much of the index for shared memory (a batch processed as given,
+        // or very long queries): same searches over the bracketed ranges in global memory
+#pragma unroll
+        for (int j = 0; j < QR_PER_THREAD; ++j) {
+            pe[j] = w_e ? count_lt(ix.eall + e_lo, w_e, qs[j]) : 0u;
+            ps[j] = w_s ? count_le(ix.starts + s_lo, w_s, qe[j]) : 0u;
+        }
+    }
+
+#pragma unroll
+    for (int j = 0; j < QR_PER_THREAD; ++j) {
+        uint32_t c = (s_lo + ps[j]) - (e_lo + pe[j]);
+        const bool inverted = live[j] && !ok[j];
+        if (__any_sync(FULL_MASK, inverted)) {
+            // qs > qe: the walk's own definition, #{ j <= ub(qe) : ends[j] >= qs }
+            uint32_t cw = 0;
+            const uint32_t i = inverted ? count_le(ix.starts, ix.n, qe[j]) - 1u : NONE32;
+            walk_tail(ix, i, qs[j], cw, lane);
+            if (inverted) c = cw;
+        }
+        if (live[j]) counts[q[j]] = (CountT)c;
+    }
 }
 
 // ---- has_overlaps: tests ONLY the last candidate (hpp:865-871, quirk Q1) ----------------
@@ -363,10 +496,9 @@ __device__ __forceinline__ void emit(const IndexView& ix, typename FillOut<MODE>
 
 constexpr uint32_t QK_FILL_LANE_MAX = 48;   // queries with more hits go straight to the warp phase
 
-template <int MODE, bool SORTED_VIA_PERM>
+template <int MODE>
 __global__ void __launch_bounds__(QK_THREADS)
-qk_fill_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* __restrict__ qe_in,
-               SortedQueries sq, uint32_t nq, const uint64_t* __restrict__ offsets,
+qk_fill_kernel(IndexView ix, QueryRecords rec, uint32_t nq, const uint64_t* __restrict__ offsets,
                typename FillOut<MODE>::T* __restrict__ out) {
     const uint64_t t64 = (uint64_t)blockIdx.x * QK_THREADS + threadIdx.x;
     const bool live = t64 < nq;
@@ -377,14 +509,9 @@ qk_fill_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* _
     int32_t qs = 0, qe = 0;
     uint64_t o = 0, o_end = 0;
     if (live) {
-        if (SORTED_VIA_PERM) {
-            const bool useB = *sq.sel != 0;
-            q = ld_stream((useB ? sq.permB : sq.permA) + t);
-            qs = unflip_i32(ld_stream((useB ? sq.keysB : sq.keysA) + t));
-        } else {
-            qs = ld_stream(qs_in + t);
-        }
-        qe = ld_stream(qe_in + q);
+        qs = ld_stream(rec.qs + t);
+        qe = ld_stream(rec.qe + t);
+        if (rec.idx) q = ld_stream(rec.idx + t);
         o = ld_stream(offsets + q);
         o_end = ld_stream(offsets + q + 1);
     }
@@ -543,16 +670,6 @@ qk_check_sorted_kernel(const int32_t* __restrict__ qe, uint32_t nq, uint32_t* __
         bad |= (qe[i] < qe[i - 1]) ? 1u : 0u;
     bad = __reduce_or_sync(FULL_MASK, bad);
     if (lane_id() == 0 && bad) *flag = 0;
-}
-
-__global__ void __launch_bounds__(QK_THREADS)
-qk_make_query_keys_kernel(const int32_t* __restrict__ qe, uint32_t nq, uint32_t* __restrict__ keys,
-                          uint32_t* __restrict__ idx) {
-    const uint64_t stride = (uint64_t)gridDim.x * QK_THREADS;
-    for (uint64_t i = (uint64_t)blockIdx.x * QK_THREADS + threadIdx.x; i < nq; i += stride) {
-        keys[i] = flip_i32(qe[i]);
-        idx[i] = (uint32_t)i;
-    }
 }
 
 __global__ void __launch_bounds__(QK_THREADS)

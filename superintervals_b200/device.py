@@ -13,9 +13,11 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import FILL_IDXS, FILL_ITEMS, FILL_KEYS, FILL_VALUES, ORDER_ASIS, ORDER_AUTO, ORDER_SORTED, ORDER_UNSORTED
+from ._lib import (COUNT_AUTO, COUNT_RANK, COUNT_WALK, FILL_IDXS, FILL_ITEMS, FILL_KEYS, FILL_VALUES, OPT_BUCKET_INTERVALS,
+                   OPT_COUNT_ALGO, OPT_TIMING, OPT_WINDOW_SHIFT, ORDER_ASIS, ORDER_AUTO, ORDER_SORTED, ORDER_UNSORTED)
 
-__all__ = ["DeviceIndex", "ORDER_AUTO", "ORDER_SORTED", "ORDER_UNSORTED", "ORDER_ASIS"]
+__all__ = ["DeviceIndex", "ORDER_AUTO", "ORDER_SORTED", "ORDER_UNSORTED", "ORDER_ASIS", "OPT_COUNT_ALGO",
+           "OPT_BUCKET_INTERVALS", "OPT_WINDOW_SHIFT", "OPT_TIMING", "COUNT_AUTO", "COUNT_WALK", "COUNT_RANK"]
 
 
 def _stream():
@@ -107,11 +109,26 @@ class DeviceIndex:
         _lib.check("siCountDevice")
         return out
 
-    def sort_queries(self, qs):
+    def sort_queries(self, qs, qe):
         """Explicit first half of an ORDER_UNSORTED count (see siSortQueriesDevice)."""
-        _chk_i32(qs, "qs")
-        self._L.siSortQueriesDevice(self._ix, qs.data_ptr(), qs.numel(), _stream())
+        _chk_i32(qs, "qs"); _chk_i32(qe, "qe")
+        self._L.siSortQueriesDevice(self._ix, qs.data_ptr(), qe.data_ptr(), qs.numel(), _stream())
         _lib.check("siSortQueriesDevice")
+
+    def set_option(self, option, value):
+        """siIndexSetOption: OPT_COUNT_ALGO (COUNT_AUTO/WALK/RANK), OPT_BUCKET_INTERVALS, OPT_WINDOW_SHIFT."""
+        rc = self._L.siIndexSetOption(self._ix, int(option), int(value))
+        _lib.check("siIndexSetOption")
+        if rc:
+            raise ValueError(f"siIndexSetOption({option}, {value}) failed")
+        return self
+
+    def read_timings(self, max_records=4096):
+        """[(kernel name, ms), ...] recorded since the last read (needs set_option(OPT_TIMING, 1))."""
+        tags = (C.c_int * max_records)()
+        ms = (C.c_float * max_records)()
+        k = self._L.siIndexReadTimings(self._ix, tags, ms, max_records)
+        return [(_lib.TAG_NAMES.get(tags[i], str(tags[i])), float(ms[i])) for i in range(k)]
 
     def has_overlaps(self, qs, qe):
         _chk_i32(qs, "qs"); _chk_i32(qe, "qe")

@@ -32,7 +32,7 @@ def test_every_order_mode_gives_the_callers_order(c3):
     dqs, dqe = _dev(qs), _dev(qe)
     for order in (ORDER_AUTO, ORDER_UNSORTED, ORDER_ASIS):
         assert np.array_equal(_u32(ix.count(dqs, dqe, order=order)), want), order
-    ix.sort_queries(dqs)                                     # explicit two-phase form
+    ix.sort_queries(dqs, dqe)                                  # explicit two-phase form
     assert np.array_equal(_u32(ix.count(dqs, dqe, order=ORDER_UNSORTED)), want)
     o = np.argsort(qs, kind="stable")
     assert np.array_equal(_u32(ix.count(_dev(qs[o]), _dev(qe[o]), order=ORDER_SORTED)), want[o])

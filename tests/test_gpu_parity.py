@@ -89,3 +89,39 @@ def test_count_and_search_match_oracle(kind, n, nq, seed, sort_queries):
     assert np.array_equal(off2, off_o) and np.array_equal(idx.astype(np.uint32), res["idxs"])
     off3, keys = m.search_keys_batch_csr(qs, qe)
     assert np.array_equal(off3, off_o) and np.array_equal(keys, res["keys"])
+
+
+PLANS = [(1024, 22), (1, 10), (64, 12), (1 << 20, 22), (16, 16)]   # (bucket_intervals, window_shift): 0..3 partition passes
+
+
+@pytest.mark.parametrize("kind,n,nq,seed", [("c1", 200_000, 200_000, 1), ("c2", 50_000, 300_000, 2),
+                                            ("c3", 100_000, 100_000, 42), ("dups", 5_000, 8_000, 7),
+                                            ("nested", 70_000, 30_000, 9), ("negative", 30_000, 30_000, 11),
+                                            ("c1", 1, 10, 4)])
+def test_count_kernels_and_partition_plans_agree(kind, n, nq, seed):
+    """Both count kernels (branch-array walk / closed-form rank), every partition shape (0-3 passes,
+    with and without result windows) and every order mode give the oracle's counts; the CSR fill
+    reuses each partition. Inverted queries inside a rank batch take the walk (quirk Q6)."""
+    import torch
+    from superintervals_b200.device import (COUNT_RANK, COUNT_WALK, OPT_BUCKET_INTERVALS, OPT_COUNT_ALGO,
+                                            OPT_WINDOW_SHIFT, ORDER_ASIS, ORDER_SORTED, ORDER_UNSORTED, DeviceIndex)
+    s, e, qs, qe = _mk(kind, n, nq, seed)
+    o = Oracle(s, e)
+    want = o.count_batch(qs, qe)
+    off_o, res = o.search_batch(qs, qe)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    u32 = lambda t: t.cpu().numpy().astype(np.uint32).astype(np.uint64)
+    ix = DeviceIndex().build(dev(s), dev(e))
+    dqs, dqe = dev(qs), dev(qe)
+    srt = np.argsort(qs, kind="stable")
+    sqs, sqe = dev(qs[srt]), dev(qe[srt])
+    for algo in (COUNT_WALK, COUNT_RANK):
+        ix.set_option(OPT_COUNT_ALGO, algo)
+        assert np.array_equal(u32(ix.count(dqs, dqe, order=ORDER_ASIS)), want), (algo, "asis")
+        assert np.array_equal(u32(ix.count(sqs, sqe, order=ORDER_SORTED)), want[srt]), (algo, "sorted")
+        for bucket, wshift in PLANS:
+            ix.set_option(OPT_BUCKET_INTERVALS, bucket).set_option(OPT_WINDOW_SHIFT, wshift)
+            assert np.array_equal(u32(ix.count(dqs, dqe, order=ORDER_UNSORTED)), want), (algo, bucket, wshift)
+            off, vals = ix.search_values(dqs, dqe, order=ORDER_UNSORTED)
+            assert np.array_equal(off.cpu().numpy().astype(np.uint64), off_o), (algo, bucket, wshift)
+            assert np.array_equal(vals.cpu().numpy(), res["values"]), (algo, bucket, wshift)
