@@ -15,13 +15,13 @@
 // its results inside one window of the output at a time (L2 merges the 4-byte stores).
 //
 // Each pass is a single-sweep ("onesweep") kernel: one histogram read of the starts up
-// front gives every pass its global digit offsets; a tile ranks its records with
-// __match_any_sync, publishes its per-digit counts and resolves its global offsets by a
-// chained decoupled look-back over 32-bit status words; records are staged in shared
-// memory in digit order so that global stores are coalesced runs. Tiles take tickets
+// front gives every pass its global digit offsets; a tile (8192 records) hands out slots
+// with shared-memory atomics, publishes its per-digit counts and resolves its global
+// offsets by a chained decoupled look-back over 32-bit status words; records are staged
+// in shared memory in digit order so that global stores are coalesced runs. Tiles take tickets
 // (atomic counter) so every predecessor a tile waits for is already running.
 // Traffic per pass: 12 B read + 12 B written per query (first pass reads 8 B) plus
-// 4*2^bits B of look-back state per 4096-record tile; HBM-bound.
+// 4*2^bits B of look-back state per 8192-record tile; HBM-bound.
 #pragma once
 
 #include "common.cuh"
@@ -31,7 +31,7 @@ namespace sib {
 
 constexpr int PT_THREADS = 256;
 constexpr int PT_WARPS = PT_THREADS / 32;
-constexpr int PT_ITEMS = 16;
+constexpr int PT_ITEMS = 32;
 constexpr uint32_t PT_TILE = PT_THREADS * PT_ITEMS;   // records per tile
 constexpr int PT_MAX_PASSES = 3;
 constexpr int PT_MAX_BITS = 10;
@@ -132,37 +132,43 @@ struct PtPass {
 
 template <int BITS>
 __host__ __device__ constexpr size_t pt_onesweep_smem_bytes() {
-    // record staging (aliases the per-warp histograms, which are dead by then) + dstart + gofs
-    return sizeof(uint32_t) * (3 * (size_t)PT_TILE + 2 * ((size_t)1 << BITS));
+    // record staging (3 arrays) + tile histogram + dstart + gofs
+    return sizeof(uint32_t) * (3 * (size_t)PT_TILE + 3 * ((size_t)1 << BITS));
 }
 
+// The ranking inside a tile is NOT stable (shared-memory atomics hand out the slots of a
+// digit): a pass may permute the records one tile contributes to one digit among
+// themselves. That is all the consumers need -- after an LSD pass a tile holds one or two
+// adjacent values of the previous digit, so the final order is the key order up to swaps
+// between neighbouring buckets inside runs of a few records; results never depend on it.
 template <int BITS>
-__global__ void __launch_bounds__(PT_THREADS, 3)
+__global__ void __launch_bounds__(PT_THREADS, 2)
 pt_onesweep_kernel(PtPass a) {
     constexpr uint32_t NB = 1u << BITS;
     constexpr int DPT = NB / PT_THREADS;   // digits owned per thread (blocked): 1, 2 or 4
-    static_assert(NB >= PT_THREADS && PT_WARPS * NB <= 3 * PT_TILE, "histograms must fit under the staging area");
+    static_assert(NB >= PT_THREADS, "one digit per thread at least");
 
     extern __shared__ __align__(16) unsigned char pt_smem[];
-    uint32_t* s_whist = reinterpret_cast<uint32_t*>(pt_smem);   // [WARPS][NB]
-    int32_t* s_qs = reinterpret_cast<int32_t*>(pt_smem);        // [TILE]   (aliases s_whist)
-    int32_t* s_qe = s_qs + PT_TILE;                             // [TILE]
+    int32_t* s_qs = reinterpret_cast<int32_t*>(pt_smem);             // [TILE] staging, digit order
+    int32_t* s_qe = s_qs + PT_TILE;                                  // [TILE]
     uint32_t* s_idx = reinterpret_cast<uint32_t*>(s_qe + PT_TILE);   // [TILE]
-    uint32_t* s_dstart = s_idx + PT_TILE;                       // [NB]
-    uint32_t* s_gofs = s_dstart + NB;                           // [NB]
+    uint32_t* s_hist = s_idx + PT_TILE;                              // [NB] records per digit in this tile
+    uint32_t* s_dstart = s_hist + NB;                                // [NB] exclusive scan of s_hist
+    uint32_t* s_gofs = s_dstart + NB;                                // [NB] global offset of the digit's run - dstart
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_wsum[PT_WARPS];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
-    for (uint32_t i = tid; i < PT_WARPS * NB; i += PT_THREADS) s_whist[i] = 0;
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) s_hist[tid * DPT + j] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint64_t tile_base = (uint64_t)tile * PT_TILE;
     const uint64_t wbase = tile_base + (uint64_t)warp * 32u * PT_ITEMS;
     const bool first = a.in_idx == nullptr;
 
-    // warp-striped load: item k of lane l is record wbase + 32k + l (coalesced; rank order = (warp, k, lane))
+    // warp-striped load: item k of lane l is record wbase + 32k + l (coalesced)
     int32_t qs[PT_ITEMS];
     uint32_t qi[PT_ITEMS];
 #pragma unroll
@@ -171,50 +177,30 @@ pt_onesweep_kernel(PtPass a) {
         qs[k] = e < a.n ? ld_stream(a.in_qs + e) : 0;
         qi[k] = e < a.n ? (first ? (uint32_t)e : ld_stream(a.in_idx + e)) : 0u;
     }
-
-    // stable rank of every record inside its warp's digit bucket; dr = digit << 16 | rank
+    // slot of every record inside its digit: dr = digit << 16 | rank (rank < TILE <= 2^16)
     uint32_t dr[PT_ITEMS];
-    uint32_t* wh = s_whist + warp * NB;
-    const uint32_t lt = lanemask_lt();
 #pragma unroll
     for (int k = 0; k < PT_ITEMS; ++k) {
         const uint64_t e = wbase + (uint64_t)k * 32u + lane;
-        // padding takes the last digit: it is last in rank order, so it ends up at the tile's very end
-        const uint32_t d = e < a.n ? ((pt_key(a.key, qs[k], qi[k]) >> a.shift) & a.dmask) : a.dmask;
-        const uint32_t peers = __match_any_sync(FULL_MASK, d);
-        const uint32_t leader = __ffs(peers) - 1;
-        uint32_t pre = 0;
-        if (lane == leader) {
-            pre = wh[d];
-            wh[d] = pre + __popc(peers);
+        dr[k] = 0xFFFFFFFFu;
+        if (e < a.n) {
+            const uint32_t d = (pt_key(a.key, qs[k], qi[k]) >> a.shift) & a.dmask;
+            dr[k] = (d << 16) | atomicAdd(&s_hist[d], 1u);
         }
-        pre = __shfl_sync(FULL_MASK, pre, leader);
-        dr[k] = (d << 16) | (pre + __popc(peers & lt));
-        __syncwarp();
     }
     __syncthreads();
 
-    // digits [tid*DPT, tid*DPT+DPT): exclusive prefix over warps, tile totals, publish the aggregate
+    // digits [tid*DPT, tid*DPT+DPT): publish the tile's counts, then scan them over the block
     uint32_t total[DPT];
     uint32_t tsum = 0;
 #pragma unroll
     for (int j = 0; j < DPT; ++j) {
-        const uint32_t d = tid * DPT + j;
-        uint32_t run = 0;
-#pragma unroll
-        for (int w = 0; w < PT_WARPS; ++w) {
-            const uint32_t t = s_whist[w * NB + d];
-            s_whist[w * NB + d] = run;
-            run += t;
-        }
-        total[j] = run;
-        tsum += run;
+        total[j] = s_hist[tid * DPT + j];
+        tsum += total[j];
     }
     volatile uint32_t* my_status = a.status + (uint64_t)tile * NB + tid * DPT;
 #pragma unroll
     for (int j = 0; j < DPT; ++j) my_status[j] = (tile == 0 ? PT_FLAG_INC : PT_FLAG_AGG) | total[j];
-
-    // block-wide exclusive scan of the totals over digits -> s_dstart
     {
         uint32_t incl = tsum;
 #pragma unroll
@@ -244,18 +230,22 @@ pt_onesweep_kernel(PtPass a) {
 #pragma unroll
         for (int j = 0; j < DPT; ++j) look[j] = tile - 1;
         while (pending) {
+            bool waited = false;
 #pragma unroll
             for (int j = 0; j < DPT; ++j) {
                 if (pending & (1u << j)) {
                     const uint32_t v = *(volatile const uint32_t*)(a.status + (uint64_t)look[j] * NB + tid * DPT + j);
                     const uint32_t f = v & ~PT_VAL_MASK;
-                    if (f) {   // else: predecessor not published yet (it holds an earlier ticket: it is running)
+                    if (f) {
                         excl[j] += v & PT_VAL_MASK;
                         if (f == PT_FLAG_INC) pending &= ~(1u << j);
                         else --look[j];
+                    } else {
+                        waited = true;   // predecessor not published yet (it holds an earlier ticket: it is running)
                     }
                 }
             }
+            if (waited) __nanosleep(64);
         }
 #pragma unroll
         for (int j = 0; j < DPT; ++j) my_status[j] = PT_FLAG_INC | (excl[j] + total[j]);
@@ -267,28 +257,25 @@ pt_onesweep_kernel(PtPass a) {
     }
     __syncthreads();
 
-    // slot of every record in the tile's digit-ordered staging area
+    // stage the records in digit order
 #pragma unroll
     for (int k = 0; k < PT_ITEMS; ++k) {
-        const uint32_t d = dr[k] >> 16;
-        dr[k] = s_dstart[d] + wh[d] + (dr[k] & 0xFFFFu);
-    }
-    __syncthreads();   // the histograms are dead from here: the staging area takes their place
-#pragma unroll
-    for (int k = 0; k < PT_ITEMS; ++k) {
-        s_qs[dr[k]] = qs[k];
-        s_idx[dr[k]] = qi[k];
+        if (dr[k] != 0xFFFFFFFFu) {
+            dr[k] = s_dstart[dr[k] >> 16] + (dr[k] & 0xFFFFu);
+            s_qs[dr[k]] = qs[k];
+            s_idx[dr[k]] = qi[k];
+        }
     }
 #pragma unroll
     for (int k = 0; k < PT_ITEMS; ++k) {
         const uint64_t e = wbase + (uint64_t)k * 32u + lane;
-        s_qe[dr[k]] = e < a.n ? ld_stream(a.in_qe + e) : 0;
+        if (e < a.n) s_qe[dr[k]] = ld_stream(a.in_qe + e);
     }
     __syncthreads();
 
     // coalesced write-out: consecutive threads write consecutive addresses inside a digit run
     const uint32_t valid = (uint32_t)(((uint64_t)a.n - tile_base) < PT_TILE ? ((uint64_t)a.n - tile_base) : PT_TILE);
-#pragma unroll
+#pragma unroll 8
     for (int k = 0; k < PT_ITEMS; ++k) {
         const uint32_t li = k * PT_THREADS + tid;
         if (li < valid) {

@@ -1,10 +1,11 @@
 """Tiny driver for ncu captures: builds one index, runs the hot kernels a few times.
-usage: prof_driver.py [c1|c2|c2s|c3] [count|search] [reps]"""
+usage: prof_driver.py [c1|c2|c2s|c3] [count|count_unsorted|count_walk|search] [reps]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from superintervals_b200 import workloads as W
-from superintervals_b200.device import DeviceIndex, ORDER_SORTED, ORDER_UNSORTED
+from superintervals_b200.device import (DeviceIndex, ORDER_SORTED, ORDER_UNSORTED, OPT_COUNT_ALGO, COUNT_WALK,
+                                        OPT_BUCKET_INTERVALS, OPT_WINDOW_SHIFT)
 
 which = sys.argv[1] if len(sys.argv) > 1 else "c2s"
 mode = sys.argv[2] if len(sys.argv) > 2 else "count"
@@ -15,16 +16,25 @@ gen = {"c1": lambda: W.config1(1_000_000, 0),
        "c3": lambda: W.config3()}[which]
 s, e, qs, qe = gen()
 ix = DeviceIndex().build(torch.from_numpy(s).cuda(), torch.from_numpy(e).cuda())
+if os.environ.get("SIB_BUCKET"):
+    ix.set_option(OPT_BUCKET_INTERVALS, int(os.environ["SIB_BUCKET"]))
+if os.environ.get("SIB_WSHIFT"):
+    ix.set_option(OPT_WINDOW_SHIFT, int(os.environ["SIB_WSHIFT"]))
 dqs, dqe = torch.from_numpy(qs).cuda(), torch.from_numpy(qe).cuda()
-order = torch.argsort(dqs, stable=True)
-sqs, sqe = dqs[order].contiguous(), dqe[order].contiguous()
-out = torch.empty_like(sqs)
+out = torch.empty_like(dqs)
+if mode in ("count", "count_walk_sorted", "search_sorted"):
+    order = torch.argsort(dqs, stable=True)
+    sqs, sqe = dqs[order].contiguous(), dqe[order].contiguous()
+if mode.startswith("count_walk"):
+    ix.set_option(OPT_COUNT_ALGO, COUNT_WALK)
 for _ in range(reps):
-    if mode == "count":
+    if mode in ("count", "count_walk_sorted"):
         ix.count(sqs, sqe, out=out, order=ORDER_SORTED)
-    elif mode == "count_unsorted":
+    elif mode in ("count_unsorted", "count_walk"):
         ix.count(dqs, dqe, out=out, order=ORDER_UNSORTED)
-    else:
+    elif mode == "search_sorted":
         ix.search_values(sqs, sqe, order=ORDER_SORTED)
+    else:
+        ix.search_values(dqs, dqe, order=ORDER_UNSORTED)
 torch.cuda.synchronize()
 print("hits", int(out.long().sum().item()))
