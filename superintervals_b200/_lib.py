@@ -181,7 +181,8 @@ def lib():
             raise ImportError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "or `make -C superintervals_b200/csrc`. superintervals_b200 has no CPU fallback.")
-        _lib = bind_b200(bind(C.CDLL(LIB_PATH)))
+        # SIB_LIBRARY: an alternative build of the same sources (kernel tuning experiments, tools/variants.sh)
+        _lib = bind_b200(bind(C.CDLL(os.environ.get("SIB_LIBRARY") or LIB_PATH)))
     return _lib
 
 

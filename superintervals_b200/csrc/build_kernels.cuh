@@ -134,6 +134,31 @@ bk_sorted_ends_kernel(const uint32_t* __restrict__ kA, const uint32_t* __restric
         eall[i] = i < n ? unflip_i32(keys[i]) : INT_MAX;
 }
 
+// ---- rank grid: #{starts < v}, #{ends < v} at the points v = lo + c * 2^shift, c = 0..cells ----
+__global__ void __launch_bounds__(BK_THREADS)
+bk_rank_grid_kernel(const int32_t* __restrict__ starts, const int32_t* __restrict__ eall, uint32_t n, int32_t lo,
+                    uint32_t shift, uint32_t cells, uint32_t* __restrict__ tab_s, uint32_t* __restrict__ tab_e) {
+    const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
+    for (uint64_t c = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; c <= cells; c += stride) {
+        const int64_t v = (int64_t)lo + (int64_t)(c << shift);
+        uint32_t rs = n, re = n;
+        if (v <= (int64_t)INT_MAX) {
+            // branch-free halving search for #{a < v} (same shape as hpp:501-513)
+            uint32_t ps = 0, pe = 0, len = n;
+            while (len > 1) {
+                const uint32_t half = len >> 1;
+                ps += (starts[ps + half] < (int32_t)v) ? (len - half) : 0u;
+                pe += (eall[pe + half] < (int32_t)v) ? (len - half) : 0u;
+                len = half;
+            }
+            rs = ps + ((starts[ps] < (int32_t)v) ? 1u : 0u);
+            re = pe + ((eall[pe] < (int32_t)v) ? 1u : 0u);
+        }
+        tab_s[c] = rs;
+        tab_e[c] = re;
+    }
+}
+
 // ---- 32-ary max tree over ends -------------------------------------------------------
 // level 0 = ends; level L entry k = max of level L-1 entries [32k, 32k+32).
 // One launch produces two levels: a CTA of 1024 threads folds 1024 inputs into

@@ -121,7 +121,7 @@ using namespace sib;
     } while (0)
 
 size_t siIndex::device_bytes() const {
-    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &esort, &eall, &b_in_s, &b_in_e, &b_in_v,
+    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &esort, &eall, &grid_tab, &b_in_s, &b_in_e, &b_in_v,
                            &b_kA, &b_kB, &b_vA, &b_vB, &b_ws, &small, &q_A, &q_B,
                            &q_ws, &scan_status, &h_qs, &h_qe, &h_counts, &h_offsets, &h_out, &h_cov};
     size_t s = 0;
@@ -153,6 +153,11 @@ IndexView view_of(const siIndex* ix) {
     v.pmax32 = ix->pmax32;
     v.esort = ix->esort.as<int32_t>();
     v.eall = ix->eall.as<int32_t>();
+    v.grid.tab_s = ix->grid_tab.as<uint32_t>();
+    v.grid.tab_e = ix->grid_tab.as<uint32_t>() + (((size_t)ix->grid_cells + 1 + 31) & ~(size_t)31);
+    v.grid.lo = ix->lo;
+    v.grid.shift = ix->grid_shift;
+    v.grid.cells = ix->grid_cells;
     v.n = ix->n;
     v.wellformed = ix->wellformed ? 1u : 0u;
     return v;
@@ -298,6 +303,22 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
                    ix->b_kA.as<uint32_t>(), ix->b_kB.as<uint32_t>(), ws.final_sel, ix->n, ix->n_padded,
                    ix->eall.as<int32_t>());
         SIB_CHECK(cudaMemcpyAsync(&ix->hi, ix->eall.as<int32_t>() + (ix->n - 1), 4, cudaMemcpyDeviceToHost, s));
+        // rank grid over [lo, hi]: the span has to be known on the host to size the tables
+        SIB_CHECK(cudaStreamSynchronize(s));
+        {
+            const uint64_t range = (uint64_t)((int64_t)ix->hi - (int64_t)ix->lo) + 1;   // >= 1 on a well-formed index
+            int gbits = 0;
+            while (gbits < 24 && ((uint64_t)ix->grid_intervals << gbits) < n) ++gbits;
+            uint32_t shift = 0;
+            while (((range - 1) >> shift) >= ((uint64_t)1 << gbits)) ++shift;
+            ix->grid_shift = shift;
+            ix->grid_cells = (uint32_t)((range - 1) >> shift) + 1u;
+            const size_t per = ((size_t)ix->grid_cells + 1 + 31) & ~(size_t)31;
+            if (ix->grid_tab.ensure(2 * per * sizeof(uint32_t))) return last_error_code();
+            SIB_LAUNCH(bk_rank_grid_kernel, grid_for((uint64_t)ix->grid_cells + 1, BK_THREADS, cap), BK_THREADS, 0, s,
+                       ix->starts.as<int32_t>(), ix->eall.as<int32_t>(), ix->n, ix->lo, shift, ix->grid_cells,
+                       ix->grid_tab.as<uint32_t>(), ix->grid_tab.as<uint32_t>() + per);
+        }
     } else {
         SIB_CHECK(cudaMemcpyAsync(&ix->hi, ix->starts.as<int32_t>() + (ix->n - 1), 4, cudaMemcpyDeviceToHost, s));
     }
@@ -452,7 +473,7 @@ siIndex* siIndexCreate(void) {
 void siIndexDestroy(siIndex* ix) {
     if (!ix) return;
     DeviceGuard g(ix->device);
-    DevBuf* all[] = {&ix->starts, &ix->ends, &ix->values, &ix->branch, &ix->perm, &ix->tree, &ix->esort, &ix->eall,
+    DevBuf* all[] = {&ix->starts, &ix->ends, &ix->values, &ix->branch, &ix->perm, &ix->tree, &ix->esort, &ix->eall, &ix->grid_tab,
                      &ix->b_in_s, &ix->b_in_e, &ix->b_in_v, &ix->b_kA, &ix->b_kB, &ix->b_vA, &ix->b_vB, &ix->b_ws,
                      &ix->small, &ix->q_A, &ix->q_B, &ix->q_ws, &ix->scan_status, &ix->h_qs,
                      &ix->h_qe, &ix->h_counts, &ix->h_offsets, &ix->h_out, &ix->h_cov};

@@ -15,13 +15,13 @@
 // its results inside one window of the output at a time (L2 merges the 4-byte stores).
 //
 // Each pass is a single-sweep ("onesweep") kernel: one histogram read of the starts up
-// front gives every pass its global digit offsets; a tile (8192 records) hands out slots
+// front gives every pass its global digit offsets; a tile (16384 records, one CTA of 1024 threads) hands out slots
 // with shared-memory atomics, publishes its per-digit counts and resolves its global
 // offsets by a chained decoupled look-back over 32-bit status words; records are staged
 // in shared memory in digit order so that global stores are coalesced runs. Tiles take tickets
 // (atomic counter) so every predecessor a tile waits for is already running.
 // Traffic per pass: 12 B read + 12 B written per query (first pass reads 8 B) plus
-// 4*2^bits B of look-back state per 8192-record tile; HBM-bound.
+// 4*2^bits B of look-back state per 16384-record tile; HBM-bound.
 #pragma once
 
 #include "common.cuh"
@@ -29,9 +29,21 @@
 
 namespace sib {
 
-constexpr int PT_THREADS = 256;
+#ifndef SIB_PT_THREADS
+#define SIB_PT_THREADS 1024
+#endif
+constexpr int PT_THREADS = SIB_PT_THREADS;
 constexpr int PT_WARPS = PT_THREADS / 32;
-constexpr int PT_ITEMS = 32;
+#ifndef SIB_PT_ITEMS
+#define SIB_PT_ITEMS 16
+#endif
+#ifndef SIB_PT_LOOK
+#define SIB_PT_LOOK 8
+#endif
+#ifndef SIB_PT_MINBLOCKS
+#define SIB_PT_MINBLOCKS 1
+#endif
+constexpr int PT_ITEMS = SIB_PT_ITEMS;
 constexpr uint32_t PT_TILE = PT_THREADS * PT_ITEMS;   // records per tile
 constexpr int PT_MAX_PASSES = 3;
 constexpr int PT_MAX_BITS = 10;
@@ -130,6 +142,21 @@ struct PtPass {
     PtKey key;
 };
 
+constexpr int PT_LOOK = SIB_PT_LOOK;   // predecessors inspected per look-back round
+
+// volatile (L2) load of the N consecutive status words one thread owns
+template <int N>
+__device__ __forceinline__ void pt_ld_status(const uint32_t* p, uint32_t (&w)[N]) {
+    if constexpr (N == 4) {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(p));
+    } else if constexpr (N == 2) {
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "l"(p));
+    } else {
+        asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(w[0]) : "l"(p));
+    }
+}
+
 template <int BITS>
 __host__ __device__ constexpr size_t pt_onesweep_smem_bytes() {
     // record staging (3 arrays) + tile histogram + dstart + gofs
@@ -142,11 +169,10 @@ __host__ __device__ constexpr size_t pt_onesweep_smem_bytes() {
 // adjacent values of the previous digit, so the final order is the key order up to swaps
 // between neighbouring buckets inside runs of a few records; results never depend on it.
 template <int BITS>
-__global__ void __launch_bounds__(PT_THREADS, 2)
+__global__ void __launch_bounds__(PT_THREADS, SIB_PT_MINBLOCKS)
 pt_onesweep_kernel(PtPass a) {
     constexpr uint32_t NB = 1u << BITS;
-    constexpr int DPT = NB / PT_THREADS;   // digits owned per thread (blocked): 1, 2 or 4
-    static_assert(NB >= PT_THREADS, "one digit per thread at least");
+    constexpr int DPT = NB >= PT_THREADS ? NB / PT_THREADS : 1;   // digits owned per thread (blocked)
 
     extern __shared__ __align__(16) unsigned char pt_smem[];
     int32_t* s_qs = reinterpret_cast<int32_t*>(pt_smem);             // [TILE] staging, digit order
@@ -159,9 +185,12 @@ pt_onesweep_kernel(PtPass a) {
     __shared__ uint32_t s_wsum[PT_WARPS];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const bool owner = tid * DPT < NB;   // threads beyond the digit count own none
     if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+    if (owner) {
 #pragma unroll
-    for (int j = 0; j < DPT; ++j) s_hist[tid * DPT + j] = 0;
+        for (int j = 0; j < DPT; ++j) s_hist[tid * DPT + j] = 0;
+    }
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint64_t tile_base = (uint64_t)tile * PT_TILE;
@@ -195,12 +224,14 @@ pt_onesweep_kernel(PtPass a) {
     uint32_t tsum = 0;
 #pragma unroll
     for (int j = 0; j < DPT; ++j) {
-        total[j] = s_hist[tid * DPT + j];
+        total[j] = owner ? s_hist[tid * DPT + j] : 0u;
         tsum += total[j];
     }
     volatile uint32_t* my_status = a.status + (uint64_t)tile * NB + tid * DPT;
+    if (owner) {
 #pragma unroll
-    for (int j = 0; j < DPT; ++j) my_status[j] = (tile == 0 ? PT_FLAG_INC : PT_FLAG_AGG) | total[j];
+        for (int j = 0; j < DPT; ++j) my_status[j] = (tile == 0 ? PT_FLAG_INC : PT_FLAG_AGG) | total[j];
+    }
     {
         uint32_t incl = tsum;
 #pragma unroll
@@ -213,51 +244,17 @@ pt_onesweep_kernel(PtPass a) {
         uint32_t run = incl - tsum;
 #pragma unroll
         for (int w = 0; w < PT_WARPS; ++w) run += (w < (int)warp) ? s_wsum[w] : 0u;
-#pragma unroll
-        for (int j = 0; j < DPT; ++j) {
-            s_dstart[tid * DPT + j] = run;
-            run += total[j];
-        }
-    }
-
-    // chained look-back: records with my digits in all earlier tiles (DPT chains interleaved)
-    uint32_t excl[DPT];
-#pragma unroll
-    for (int j = 0; j < DPT; ++j) excl[j] = 0;
-    if (tile > 0) {
-        uint32_t look[DPT];
-        uint32_t pending = (1u << DPT) - 1u;
-#pragma unroll
-        for (int j = 0; j < DPT; ++j) look[j] = tile - 1;
-        while (pending) {
-            bool waited = false;
+        if (owner) {
 #pragma unroll
             for (int j = 0; j < DPT; ++j) {
-                if (pending & (1u << j)) {
-                    const uint32_t v = *(volatile const uint32_t*)(a.status + (uint64_t)look[j] * NB + tid * DPT + j);
-                    const uint32_t f = v & ~PT_VAL_MASK;
-                    if (f) {
-                        excl[j] += v & PT_VAL_MASK;
-                        if (f == PT_FLAG_INC) pending &= ~(1u << j);
-                        else --look[j];
-                    } else {
-                        waited = true;   // predecessor not published yet (it holds an earlier ticket: it is running)
-                    }
-                }
+                s_dstart[tid * DPT + j] = run;
+                run += total[j];
             }
-            if (waited) __nanosleep(64);
         }
-#pragma unroll
-        for (int j = 0; j < DPT; ++j) my_status[j] = PT_FLAG_INC | (excl[j] + total[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < DPT; ++j) {
-        const uint32_t d = tid * DPT + j;
-        s_gofs[d] = a.gbase[d] + excl[j] - s_dstart[d];
     }
     __syncthreads();
 
-    // stage the records in digit order
+    // stage the records in digit order; the ends are requested now and land after the look-back
 #pragma unroll
     for (int k = 0; k < PT_ITEMS; ++k) {
         if (dr[k] != 0xFFFFFFFFu) {
@@ -266,11 +263,74 @@ pt_onesweep_kernel(PtPass a) {
             s_idx[dr[k]] = qi[k];
         }
     }
+    int32_t qe[PT_ITEMS];
 #pragma unroll
     for (int k = 0; k < PT_ITEMS; ++k) {
         const uint64_t e = wbase + (uint64_t)k * 32u + lane;
-        if (e < a.n) s_qe[dr[k]] = ld_stream(a.in_qe + e);
+        qe[k] = e < a.n ? ld_stream(a.in_qe + e) : 0;
     }
+
+    // decoupled look-back, PT_LOOK predecessors per round: records with my digits in all earlier
+    // tiles. The status words of the window are fetched together (independent vector loads, one
+    // L2 round trip) and then consumed nearest-first per digit, stopping at the first tile that
+    // already holds an inclusive prefix. An unpublished predecessor (it holds an earlier ticket,
+    // so it is running) is re-polled after a short sleep.
+    uint32_t excl[DPT];
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) excl[j] = 0;
+    if (tile > 0 && owner) {
+        uint32_t look[DPT];
+        uint32_t pending = (1u << DPT) - 1u;
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) look[j] = tile - 1;
+        while (pending) {
+            uint32_t base = 0;
+#pragma unroll
+            for (int j = 0; j < DPT; ++j)
+                if (pending & (1u << j)) base = max(base, look[j]);
+            uint32_t w[PT_LOOK][DPT];
+#pragma unroll
+            for (int p = 0; p < PT_LOOK; ++p) {
+                if (base >= (uint32_t)p) {
+                    pt_ld_status<DPT>(a.status + (uint64_t)(base - p) * NB + tid * DPT, w[p]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < DPT; ++j) w[p][j] = 0;
+                }
+            }
+            bool waited = false;
+#pragma unroll
+            for (int p = 0; p < PT_LOOK; ++p) {
+#pragma unroll
+                for (int j = 0; j < DPT; ++j) {
+                    if ((pending & (1u << j)) && look[j] == base - (uint32_t)p && base >= (uint32_t)p) {
+                        const uint32_t v = w[p][j];
+                        const uint32_t f = v & ~PT_VAL_MASK;
+                        if (f) {
+                            excl[j] += v & PT_VAL_MASK;
+                            if (f == PT_FLAG_INC) pending &= ~(1u << j);
+                            else --look[j];
+                        } else {
+                            waited = true;
+                        }
+                    }
+                }
+            }
+            if (waited) __nanosleep(64);
+        }
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) my_status[j] = PT_FLAG_INC | (excl[j] + total[j]);
+    }
+    if (owner) {
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) {
+            const uint32_t d = tid * DPT + j;
+            s_gofs[d] = a.gbase[d] + excl[j] - s_dstart[d];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < PT_ITEMS; ++k)
+        if (dr[k] != 0xFFFFFFFFu) s_qe[dr[k]] = qe[k];
     __syncthreads();
 
     // coalesced write-out: consecutive threads write consecutive addresses inside a digit run

@@ -28,6 +28,17 @@ namespace sib {
 constexpr int QK_THREADS = 256;
 constexpr int QK_WARPS = QK_THREADS / 32;
 
+// Ranks tabulated on a regular grid over the index span (build(), well-formed indexes only):
+// tab_s[c] = #{ starts < lo + c * 2^shift },  tab_e[c] = #{ ends < lo + c * 2^shift },  c = 0..cells
+// (cells + 1 entries; the last grid point lies beyond every start and end, so tab[cells] = n).
+struct RankGrid {
+    const uint32_t* tab_s;
+    const uint32_t* tab_e;
+    int32_t lo;
+    uint32_t shift;
+    uint32_t cells;
+};
+
 struct IndexView {
     const int32_t* starts;
     const int32_t* ends;     // padded to a multiple of 128 entries (pad = INT_MIN)
@@ -36,6 +47,7 @@ struct IndexView {
     const int32_t* pmax32;   // pmax32[b] = max(ends[0 .. 32b-1]) (INT_MIN for b = 0), from build()
     const int32_t* esort;    // ends with every aligned 32-block sorted ascending (n_pad entries), from build()
     const int32_t* eall;     // all ends sorted ascending (n entries), from build(); only on a well-formed index
+    RankGrid grid;           // rank tables for qk_count_rank_kernel; only on a well-formed index
     uint32_t n;
     uint32_t wellformed;     // 1 when every stored interval has start <= end (checked by build())
 };
@@ -280,53 +292,33 @@ qk_count_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __restrict_
 // the candidates, hence
 //       count = #{ starts <= qe }  -  #{ ends < qs }
 // -- the reference's upper_bound (hpp:501-513) on starts, and the same search on build()'s
-// ascending copy of the ends (IndexView::eall). One CTA takes 512 queries that the partition
-// (or the caller) made neighbours in position: it brackets the two rank ranges of the whole
-// tile with four warp-cooperative 32-ary searches, stages those two short windows of the
-// index in shared memory, and every thread finishes its two queries with branch-free
-// halving searches over shared memory. Queries with qs > qe (quirk Q6: the closed form does
-// not hold) are answered by the branch-array walk in the same kernel. Bit-exact with
-// qk_count_kernel on every input it accepts (tests/test_gpu_parity.py runs both).
+// ascending copy of the ends (IndexView::eall). build() also tabulates both ranks on a regular
+// grid over the index span (RankGrid, about 16 intervals per cell), so a query reads the two
+// table entries that bracket each rank and finishes with a handful of branch-free halving
+// steps inside the cell. Neighbouring queries (the partition, or a position-sorted caller,
+// made them neighbours) hit the same table and index lines in L1. Queries with qs > qe
+// (quirk Q6: the closed form does not hold) are answered by the branch-array walk in the
+// same kernel. Bit-exact with qk_count_kernel on every input it accepts
+// (tests/test_gpu_parity.py runs both).
 constexpr int QR_THREADS = 256;
 constexpr int QR_PER_THREAD = 2;
 constexpr uint32_t QR_TILE = QR_THREADS * QR_PER_THREAD;
-constexpr uint32_t QR_WINDOW_MAX = 6144;   // staged entries (starts + sorted ends) per CTA: 24 KB
 
-// #{ a[0..n) below v } for a sorted global array, one warp: 32 probes per round, 5 rounds for 10 M
-template <bool STRICT>
-__device__ __forceinline__ uint32_t warp_rank(const int32_t* __restrict__ a, uint32_t n, int32_t v, uint32_t lane) {
-    uint32_t lo = 0, len = n;   // the answer lies in [lo, lo + len]
-    while (len > 0) {
-        const uint32_t step = (len + 31u) >> 5;
-        const uint32_t off = lane * step;
-        bool below = false;
-        if (off < len) {
-            const int32_t x = ld_nc(a + lo + off);
-            below = STRICT ? (x < v) : (x <= v);
-        }
-        const uint32_t cnt = __popc(__ballot_sync(FULL_MASK, below));
-        if (cnt == 0) break;                              // a[lo] is not below v
-        const uint32_t base = (cnt - 1u) * step + 1u;     // a[lo + (cnt-1)*step] is below v ...
-        const uint32_t hi = min(cnt * step, len);         // ... and a[lo + cnt*step], if probed, is not
-        lo += base;
-        len = hi - base;
-    }
-    return lo;
+__device__ __forceinline__ uint32_t grid_cell(const RankGrid& g, int32_t v) {
+    const uint32_t d = v > g.lo ? (uint32_t)v - (uint32_t)g.lo : 0u;
+    return min(d >> g.shift, g.cells - 1u);
 }
 
 template <typename CountT>
-__global__ void __launch_bounds__(QR_THREADS, 6)
+__global__ void __launch_bounds__(QR_THREADS)
 qk_count_rank_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __restrict__ counts) {
-    __shared__ int32_t s_win[QR_WINDOW_MAX];
-    __shared__ int32_t s_red[4][QR_THREADS / 32];
-    __shared__ uint32_t s_bound[4];
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const uint64_t base = (uint64_t)blockIdx.x * QR_TILE;
+    const RankGrid g = ix.grid;
 
     int32_t qs[QR_PER_THREAD], qe[QR_PER_THREAD];
     uint32_t q[QR_PER_THREAD];
-    bool live[QR_PER_THREAD], ok[QR_PER_THREAD];
-    int32_t mn_s = INT_MAX, mx_s = INT_MIN, mn_e = INT_MAX, mx_e = INT_MIN;
+    bool live[QR_PER_THREAD];
 #pragma unroll
     for (int j = 0; j < QR_PER_THREAD; ++j) {
         const uint64_t t = base + (uint64_t)j * QR_THREADS + tid;
@@ -334,81 +326,47 @@ qk_count_rank_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __rest
         qs[j] = live[j] ? ld_stream(rec.qs + t) : 0;
         qe[j] = live[j] ? ld_stream(rec.qe + t) : 0;
         q[j] = (live[j] && rec.idx) ? ld_stream(rec.idx + t) : (uint32_t)t;
-        ok[j] = live[j] && qs[j] <= qe[j];
-        if (ok[j]) {
-            mn_s = min(mn_s, qs[j]); mx_s = max(mx_s, qs[j]);
-            mn_e = min(mn_e, qe[j]); mx_e = max(mx_e, qe[j]);
-        }
     }
-    mn_s = __reduce_min_sync(FULL_MASK, mn_s); mx_s = __reduce_max_sync(FULL_MASK, mx_s);
-    mn_e = __reduce_min_sync(FULL_MASK, mn_e); mx_e = __reduce_max_sync(FULL_MASK, mx_e);
-    if (lane == 0) { s_red[0][warp] = mn_s; s_red[1][warp] = mx_s; s_red[2][warp] = mn_e; s_red[3][warp] = mx_e; }
-    __syncthreads();
-    if (warp < 4) {
-        // warp 0: #ends < min qs, warp 1: #ends < max qs, warp 2: #starts <= min qe, warp 3: #starts <= max qe
-        const bool is_min = (warp & 1u) == 0;
-        int32_t v = lane < QR_THREADS / 32 ? s_red[warp][lane] : (is_min ? INT_MAX : INT_MIN);
-        v = is_min ? __reduce_min_sync(FULL_MASK, v) : __reduce_max_sync(FULL_MASK, v);
-        const uint32_t r = warp < 2 ? warp_rank<true>(ix.eall, ix.n, v, lane) : warp_rank<false>(ix.starts, ix.n, v, lane);
-        if (lane == 0) s_bound[warp] = r;
-    }
-    __syncthreads();
-    const uint32_t e_lo = s_bound[0], s_lo = s_bound[2];
-    const uint32_t w_e = s_bound[1] > e_lo ? s_bound[1] - e_lo : 0u;   // a tile without a valid query has empty windows
-    const uint32_t w_s = s_bound[3] > s_lo ? s_bound[3] - s_lo : 0u;
-    const bool staged = w_e + w_s <= QR_WINDOW_MAX;
-
-    uint32_t pe[QR_PER_THREAD], ps[QR_PER_THREAD];
-#pragma unroll
-    for (int j = 0; j < QR_PER_THREAD; ++j) pe[j] = ps[j] = 0;
-    if (staged) {
-        const int32_t* __restrict__ ge = ix.eall + e_lo;
-        const int32_t* __restrict__ gs = ix.starts + s_lo;
-        for (uint32_t k = tid; k < w_e; k += QR_THREADS) s_win[k] = ld_nc(ge + k);
-        for (uint32_t k = tid; k < w_s; k += QR_THREADS) s_win[w_e + k] = ld_nc(gs + k);
-        __syncthreads();
-        const int32_t* we = s_win;
-        const int32_t* ws = s_win + w_e;
-        if (w_e) {
-            uint32_t len = w_e;
-            while (len > 1) {
-                const uint32_t half = len >> 1;
-#pragma unroll
-                for (int j = 0; j < QR_PER_THREAD; ++j) pe[j] += (we[pe[j] + half] < qs[j]) ? (len - half) : 0u;
-                len = half;
-            }
-#pragma unroll
-            for (int j = 0; j < QR_PER_THREAD; ++j) pe[j] += (we[pe[j]] < qs[j]) ? 1u : 0u;
-        }
-        if (w_s) {
-            uint32_t len = w_s;
-            while (len > 1) {
-                const uint32_t half = len >> 1;
-#pragma unroll
-                for (int j = 0; j < QR_PER_THREAD; ++j) ps[j] += (ws[ps[j] + half] <= qe[j]) ? (len - half) : 0u;
-                len = half;
-            }
-#pragma unroll
-            for (int j = 0; j < QR_PER_THREAD; ++j) ps[j] += (ws[ps[j]] <= qe[j]) ? 1u : 0u;
-        }
-    } else {
-        // the tile spans too much of the index for shared memory (a batch processed as given,
-        // or very long queries): same searches over the bracketed ranges in global memory
-#pragma unroll
-        for (int j = 0; j < QR_PER_THREAD; ++j) {
-            pe[j] = w_e ? count_lt(ix.eall + e_lo, w_e, qs[j]) : 0u;
-            ps[j] = w_s ? count_le(ix.starts + s_lo, w_s, qe[j]) : 0u;
-        }
-    }
-
+    // bracket both ranks from the grid tables: answer in [lo, lo + len]
+    uint32_t elo[QR_PER_THREAD], elen[QR_PER_THREAD], slo[QR_PER_THREAD], slen[QR_PER_THREAD];
 #pragma unroll
     for (int j = 0; j < QR_PER_THREAD; ++j) {
-        uint32_t c = (s_lo + ps[j]) - (e_lo + pe[j]);
-        const bool inverted = live[j] && !ok[j];
+        const uint32_t ce = grid_cell(g, qs[j]), cs = grid_cell(g, qe[j]);
+        elo[j] = ld_nc(g.tab_e + ce);
+        elen[j] = ld_nc(g.tab_e + ce + 1u) - elo[j];
+        slo[j] = ld_nc(g.tab_s + cs);
+        slen[j] = ld_nc(g.tab_s + cs + 1u) - slo[j];
+    }
+    // halving steps inside the cells, all chains in one warp-uniform loop
+    while (true) {
+        uint32_t any = 0;
+#pragma unroll
+        for (int j = 0; j < QR_PER_THREAD; ++j) any |= elen[j] | slen[j];
+        if (!__any_sync(FULL_MASK, any != 0)) break;
+#pragma unroll
+        for (int j = 0; j < QR_PER_THREAD; ++j) {
+            if (elen[j]) {
+                const uint32_t half = elen[j] >> 1;
+                const bool below = ld_nc(ix.eall + elo[j] + half) < qs[j];
+                elo[j] += below ? half + 1u : 0u;
+                elen[j] = below ? elen[j] - half - 1u : half;
+            }
+            if (slen[j]) {
+                const uint32_t half = slen[j] >> 1;
+                const bool below = ld_nc(ix.starts + slo[j] + half) <= qe[j];
+                slo[j] += below ? half + 1u : 0u;
+                slen[j] = below ? slen[j] - half - 1u : half;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < QR_PER_THREAD; ++j) {
+        uint32_t c = slo[j] - elo[j];
+        const bool inverted = live[j] && qs[j] > qe[j];
         if (__any_sync(FULL_MASK, inverted)) {
             // qs > qe: the walk's own definition, #{ j <= ub(qe) : ends[j] >= qs }
             uint32_t cw = 0;
-            const uint32_t i = inverted ? count_le(ix.starts, ix.n, qe[j]) - 1u : NONE32;
+            const uint32_t i = inverted ? slo[j] - 1u : NONE32;   // slo = #{starts <= qe}; 0 - 1 wraps to NONE32
             walk_tail(ix, i, qs[j], cw, lane);
             if (inverted) c = cw;
         }
