@@ -230,7 +230,7 @@ def kernel_table(recs, steps, nq, passes, a_walk):
 
 def bench_search_values(a, torch, L, _lib, rank):
     """Secondary line: search_values (CSR) on BASELINE configs[2] -- heavy-tailed nested intervals."""
-    from superintervals_b200 import IntervalMap, workloads as W
+    from superintervals_b200 import workloads as W
     from superintervals_b200.device import DeviceIndex, OPT_TIMING, ORDER_UNSORTED
     n, nq = a.sv_intervals, a.sv_queries
     s, e, qs, qe = W.config3(n, nq, 42)
@@ -255,21 +255,39 @@ def bench_search_values(a, torch, L, _lib, rank):
     per = {}
     for name, t in recs:
         per[name] = per.get(name, 0.0) + t / a.steps
-    # e2e through the C ABI with host buffers (searchValuesBatch: H2D queries, D2H offsets + values)
-    m = IntervalMap.from_arrays(s, e)
-    m.search_values_batch_csr(qs, qe)
+    # e2e through the C ABI with host buffers (searchValuesBatch: H2D queries, D2H offsets + values).
+    # The caller owns one cIndexResult and reuses it (clearIndexResult keeps its capacity), as a C
+    # caller of the reference would (c_superintervals.h:98-104, 1066-1075); buffers are plain pageable memory.
+    import ctypes as C_
+    si = L.createSuperIntervals()
+    L.siSetHostMirror(si, False)
+    L.addIntervals(si, s.ctypes.data, e.ctypes.data, None, s.size)
+    L.indexSuperIntervals(si)
+    _lib.check("indexSuperIntervals")
+    found = L.createIndexResult()
+    h_off = np.zeros(nq + 1, np.uint64)
+    def e2e_step():
+        L.clearIndexResult(C_.byref(found))
+        L.searchValuesBatch(si, qs.ctypes.data, qe.ctypes.data, nq, h_off.ctypes.data, C_.byref(found))
+    t0 = time.perf_counter(); e2e_step(); first_s = time.perf_counter() - t0     # includes growing the result buffer
+    _lib.check("searchValuesBatch")
     t0 = time.perf_counter()
     for _ in range(a.e2e_steps):
-        o2, v2 = m.search_values_batch_csr(qs, qe)
+        e2e_step()
     e2e_s = (time.perf_counter() - t0) / a.e2e_steps
-    ok = bool(np.array_equal(o2.astype(np.int64), off.cpu().numpy()) and np.array_equal(v2, vals.cpu().numpy()))
+    v2 = np.ctypeslib.as_array(C_.cast(found.data, C_.POINTER(C_.c_int32)), shape=(int(found.size),))
+    ok = bool(int(found.size) == total and np.array_equal(h_off.astype(np.int64), off.cpu().numpy())
+              and np.array_equal(v2, vals.cpu().numpy()))
+    L.destroyIndexResult(C_.byref(found))
+    L.destroySuperIntervals(si)
     out = {"workload": f"C3: {n/1e6:g}M heavy-tailed nested intervals (Pareto 1.1, <=1Mb) x {nq/1e6:g}M queries, "
                        f"search_values CSR, shuffled queries", "value": nq / (ms * 1e-3), "unit": UNIT,
            "ms_per_step": ms, "hits": total, "hits_per_query": total / nq, "kernel_ms_per_step": per,
            "result_gbs": (total * 4 + nq * 8) / (ms * 1e-3) / 1e9,
            "e2e": {"value": nq / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": 8 * nq,
                    "d2h_bytes_per_step": 8 * (nq + 1) + 4 * total, "equals_device": ok,
-                   "call": "searchValuesBatch(si, qs, qe, n, offsets, cIndexResult*) with host buffers"}}
+                   "first_call_ms": first_s * 1e3,
+                   "call": "searchValuesBatch(si, qs, qe, n, offsets, cIndexResult*) with pageable host buffers, result struct reused"}}
     if rank == 0 and not a.no_cpu_baseline:
         from oracle.pyoracle import Reference
         if Reference.available():
@@ -316,6 +334,9 @@ def main():
     if a.algo != "auto":
         from superintervals_b200.device import COUNT_RANK, COUNT_WALK, OPT_COUNT_ALGO
         ix.set_option(OPT_COUNT_ALGO, COUNT_WALK if a.algo == "walk" else COUNT_RANK)
+    for env, opt in (("SIB_BUCKET", 1), ("SIB_WSHIFT", 2)):      # tuning experiments (tools/variants.sh)
+        if os.environ.get(env):
+            ix.set_option(opt, int(os.environ[env]))
     d_s, d_e = torch.from_numpy(starts).cuda(), torch.from_numpy(ends).cuda()
     torch.cuda.synchronize()
     t0 = time.perf_counter(); ix.build(d_s, d_e); torch.cuda.synchronize(); build_ms = (time.perf_counter() - t0) * 1e3

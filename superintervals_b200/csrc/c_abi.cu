@@ -11,9 +11,14 @@
 #include "common.cuh"
 #include "index.cuh"
 
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 extern "C" int si_b200_upper_bound_(siIndex* ix, int32_t value, size_t* out);
 extern "C" int si_b200_resolve_order_(siIndex* ix, const int32_t* d_qs, size_t n, void* stream);
@@ -52,12 +57,157 @@ bool grow(R* r, size_t need_total, size_t elem) {
     return true;
 }
 
+// ---- host side of the copies -------------------------------------------------------------
+// Caller buffers are usually pageable (malloc / realloc'd result arrays, numpy). A plain
+// cudaMemcpy on such memory is staged by the driver through one thread, and a freshly
+// realloc'd result array additionally takes a page fault per 4 KB. Copies of more than a
+// few MB therefore go through two pinned staging buffers: the DMA of chunk k+1 overlaps a
+// multi-threaded memcpy of chunk k between the staging buffer and the caller's memory
+// (the page faults are spread over the same threads). Pinned caller buffers are copied directly.
+class HostPool {
+public:
+    static HostPool& get() { static HostPool p; return p; }
+    int size() const { return (int)workers_.size() + 1; }
+    // runs f(t, n) for t = 0..n-1, n = size(); the caller is worker 0; returns when all are done
+    void run(const std::function<void(int, int)>& f) {
+        std::lock_guard<std::mutex> serial(run_mu_);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &f;
+            pending_ = (int)workers_.size();
+            ++gen_;
+        }
+        cv_work_.notify_all();
+        f(0, size());
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_work_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+private:
+    HostPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        int n = hw >= 16 ? 8 : (hw >= 4 ? (int)hw / 2 : 1);
+        if (const char* e = getenv("SIB_HOST_THREADS")) n = atoi(e) > 0 ? atoi(e) : n;
+        for (int t = 1; t < n; ++t) workers_.emplace_back([this, t] { loop(t); });
+    }
+    void loop(int t) {
+        unsigned seen = 0;
+        while (true) {
+            const std::function<void(int, int)>* f;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_work_.wait(lk, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+                f = fn_;
+            }
+            (*f)(t, size());
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) cv_done_.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_, run_mu_;
+    std::condition_variable cv_work_, cv_done_;
+    const std::function<void(int, int)>* fn_ = nullptr;
+    unsigned gen_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
+void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    if (bytes < ((size_t)1 << 20)) { memcpy(dst, src, bytes); return; }
+    HostPool::get().run([&](int t, int n) {
+        const size_t per = ((bytes + n - 1) / n + 4095) & ~(size_t)4095;
+        const size_t a = (size_t)t * per;
+        if (a < bytes) memcpy((char*)dst + a, (const char*)src + a, bytes - a < per ? bytes - a : per);
+    });
+}
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+constexpr size_t STAGE_BYTES = (size_t)16 << 20;   // per staging slot
+constexpr size_t DIRECT_BYTES = (size_t)4 << 20;   // below this a plain cudaMemcpyAsync is as good
+
+int ensure_stage(siIndex* ix) {
+    if (ix->pinned && ix->pinned_bytes >= 2 * STAGE_BYTES) return 0;
+    if (ix->pinned) { cudaFreeHost(ix->pinned); ix->pinned = nullptr; ix->pinned_bytes = 0; }
+    SIB_CHECK(cudaHostAlloc(&ix->pinned, 2 * STAGE_BYTES, cudaHostAllocDefault));
+    ix->pinned_bytes = 2 * STAGE_BYTES;
+    if (!ix->e_stage[0]) {
+        SIB_CHECK(cudaEventCreateWithFlags(&ix->e_stage[0], cudaEventDisableTiming));
+        SIB_CHECK(cudaEventCreateWithFlags(&ix->e_stage[1], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+// device -> host, returns when the bytes are in dst
+int copy_d2h(siIndex* ix, void* dst, const void* src_dev, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return 0;
+    if (bytes <= DIRECT_BYTES || is_pinned(dst)) {
+        SIB_CHECK(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, s));
+        SIB_CHECK(cudaStreamSynchronize(s));
+        return 0;
+    }
+    if (ensure_stage(ix)) return sib::last_error_code();
+    char* stage[2] = {(char*)ix->pinned, (char*)ix->pinned + STAGE_BYTES};
+    const size_t chunks = (bytes + STAGE_BYTES - 1) / STAGE_BYTES;
+    auto len = [&](size_t k) { return k + 1 < chunks ? STAGE_BYTES : bytes - k * STAGE_BYTES; };
+    SIB_CHECK(cudaMemcpyAsync(stage[0], src_dev, len(0), cudaMemcpyDeviceToHost, s));
+    SIB_CHECK(cudaEventRecord(ix->e_stage[0], s));
+    for (size_t k = 0; k < chunks; ++k) {
+        if (k + 1 < chunks) {   // slot (k+1)&1 is free: its previous contents were copied out synchronously
+            SIB_CHECK(cudaMemcpyAsync(stage[(k + 1) & 1], (const char*)src_dev + (k + 1) * STAGE_BYTES, len(k + 1),
+                                      cudaMemcpyDeviceToHost, s));
+            SIB_CHECK(cudaEventRecord(ix->e_stage[(k + 1) & 1], s));
+        }
+        SIB_CHECK(cudaEventSynchronize(ix->e_stage[k & 1]));
+        parallel_memcpy((char*)dst + k * STAGE_BYTES, stage[k & 1], len(k));
+    }
+    return 0;
+}
+
+// host -> device, stream-ordered on s; src may be reused when the call returns
+int copy_h2d(siIndex* ix, void* dst_dev, const void* src, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return 0;
+    if (bytes <= DIRECT_BYTES || is_pinned(src)) {
+        SIB_CHECK(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, s));
+        if (bytes > DIRECT_BYTES) return 0;       // pinned: truly asynchronous, the caller synchronises before returning
+        return 0;                                  // small pageable: the runtime stages it before returning
+    }
+    if (ensure_stage(ix)) return sib::last_error_code();
+    char* stage[2] = {(char*)ix->pinned, (char*)ix->pinned + STAGE_BYTES};
+    const size_t chunks = (bytes + STAGE_BYTES - 1) / STAGE_BYTES;
+    for (size_t k = 0; k < chunks; ++k) {
+        const size_t l = k + 1 < chunks ? STAGE_BYTES : bytes - k * STAGE_BYTES;
+        if (k >= 2) SIB_CHECK(cudaEventSynchronize(ix->e_stage[k & 1]));   // the DMA that last read this slot
+        parallel_memcpy(stage[k & 1], (const char*)src + k * STAGE_BYTES, l);
+        SIB_CHECK(cudaMemcpyAsync((char*)dst_dev + k * STAGE_BYTES, stage[k & 1], l, cudaMemcpyHostToDevice, s));
+        SIB_CHECK(cudaEventRecord(ix->e_stage[k & 1], s));
+    }
+    // the staging slots may be reused by the next copy only after these DMAs have read them
+    SIB_CHECK(cudaEventSynchronize(ix->e_stage[(chunks - 1) & 1]));
+    if (chunks > 1) SIB_CHECK(cudaEventSynchronize(ix->e_stage[(chunks - 2) & 1]));
+    return 0;
+}
+
 // upload a query batch into the index's staging buffers
 int stage_queries(siIndex* ix, const int32_t* qs, const int32_t* qe, size_t n) {
     if (ix->h_qs.ensure(n * 4) || ix->h_qe.ensure(n * 4)) return sib::last_error_code();
-    SIB_CHECK(cudaMemcpyAsync(ix->h_qs.p, qs, n * 4, cudaMemcpyHostToDevice, ix->own_stream));
-    SIB_CHECK(cudaMemcpyAsync(ix->h_qe.p, qe, n * 4, cudaMemcpyHostToDevice, ix->own_stream));
-    return 0;
+    int rc = copy_h2d(ix, ix->h_qs.p, qs, n * 4, ix->own_stream);
+    if (rc) return rc;
+    return copy_h2d(ix, ix->h_qe.p, qe, n * 4, ix->own_stream);
 }
 
 // count -> scan -> (host learns total) -> grow -> fill -> copy back, appended to `found`
@@ -80,19 +230,27 @@ int search_batch(Handle* h, const int32_t* qs, const int32_t* qe, size_t n, size
     if (rc) return rc;
     static_assert(sizeof(size_t) == sizeof(uint64_t), "LP64 only");
     uint64_t total = 0;
-    if (offsets_out) {
-        SIB_CHECK(cudaMemcpyAsync(offsets_out, ix->h_offsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ix->own_stream));
-    }
     SIB_CHECK(cudaMemcpyAsync(&total, ix->h_offsets.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, ix->own_stream));
     SIB_CHECK(cudaStreamSynchronize(ix->own_stream));
+    if (total) {
+        if (!grow(found, found->size + total, elem)) return cudaErrorMemoryAllocation;
+        if (ix->h_out.ensure(total * elem)) return sib::last_error_code();
+        // the fill runs while the offsets travel
+        rc = siFillDevice(ix, dqs, dqe, n, ix->h_offsets.as<uint64_t>(), what, ix->h_out.p, order, ix->own_stream);
+        if (rc) return rc;
+    }
+    if (offsets_out) {
+        if (!ix->pipe_ready_out) {
+            SIB_CHECK(cudaStreamCreateWithFlags(&ix->s_out2, cudaStreamNonBlocking));
+            ix->pipe_ready_out = true;
+        }
+        // offsets were final before the fill was launched: copy them on a second stream meanwhile
+        rc = copy_d2h(ix, offsets_out, ix->h_offsets.p, (n + 1) * 8, ix->s_out2);
+        if (rc) return rc;
+    }
     if (total == 0) return 0;
-    if (!grow(found, found->size + total, elem)) return cudaErrorMemoryAllocation;
-    if (ix->h_out.ensure(total * elem)) return sib::last_error_code();
-    rc = siFillDevice(ix, dqs, dqe, n, ix->h_offsets.as<uint64_t>(), what, ix->h_out.p, order, ix->own_stream);
+    rc = copy_d2h(ix, reinterpret_cast<char*>(found->data) + found->size * elem, ix->h_out.p, total * elem, ix->own_stream);
     if (rc) return rc;
-    SIB_CHECK(cudaMemcpyAsync(reinterpret_cast<char*>(found->data) + found->size * elem, ix->h_out.p, total * elem,
-                              cudaMemcpyDeviceToHost, ix->own_stream));
-    SIB_CHECK(cudaStreamSynchronize(ix->own_stream));
     found->size += total;
     return 0;
 }

@@ -484,6 +484,8 @@ void siIndexDestroy(siIndex* ix) {
         for (int k = 0; k < 2; ++k) { cudaEventDestroy(ix->e_in[k]); cudaEventDestroy(ix->e_k[k]); cudaEventDestroy(ix->e_out[k]); }
     }
     ix->timer.release();
+    if (ix->e_stage[0]) { cudaEventDestroy(ix->e_stage[0]); cudaEventDestroy(ix->e_stage[1]); }
+    if (ix->pipe_ready_out) cudaStreamDestroy(ix->s_out2);
     if (ix->pinned) cudaFreeHost(ix->pinned);
     if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
     delete ix;

@@ -84,8 +84,11 @@ struct siIndex {
     bool pipe_ready = false;                    // chunked host-batch pipeline (c_abi.cu)
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t e_in[2] = {nullptr, nullptr}, e_k[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};
-    void* pinned = nullptr;                     // small pinned scratch for scalars
+    void* pinned = nullptr;                     // two pinned staging slots for pageable caller buffers (c_abi.cu)
     size_t pinned_bytes = 0;
+    cudaEvent_t e_stage[2] = {nullptr, nullptr};
+    cudaStream_t s_out2 = nullptr;              // second copy-out stream (offsets travel while the fill runs)
+    bool pipe_ready_out = false;
 
     size_t device_bytes() const;
 };
