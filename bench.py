@@ -334,7 +334,7 @@ def main():
     if a.algo != "auto":
         from superintervals_b200.device import COUNT_RANK, COUNT_WALK, OPT_COUNT_ALGO
         ix.set_option(OPT_COUNT_ALGO, COUNT_WALK if a.algo == "walk" else COUNT_RANK)
-    for env, opt in (("SIB_BUCKET", 1), ("SIB_WSHIFT", 2)):      # tuning experiments (tools/variants.sh)
+    for env, opt in (("SIB_BUCKET", 1), ("SIB_WSHIFT", 2), ("SIB_GRID", 4)):      # tuning experiments (tools/variants.sh)
         if os.environ.get(env):
             ix.set_option(opt, int(os.environ[env]))
     d_s, d_e = torch.from_numpy(starts).cuda(), torch.from_numpy(ends).cuda()

@@ -125,7 +125,8 @@ int siSortQueriesDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, s
  * #{starts <= qe} - #{ends < qs} (valid on an index whose intervals all have
  * start <= end; queries with qs > qe inside such a batch still take the walk);
  * SI_COUNT_AUTO picks RANK whenever the index allows it. Results are identical. */
-enum { SI_OPT_COUNT_ALGO = 0, SI_OPT_BUCKET_INTERVALS = 1, SI_OPT_WINDOW_SHIFT = 2, SI_OPT_TIMING = 3 };
+enum { SI_OPT_COUNT_ALGO = 0, SI_OPT_BUCKET_INTERVALS = 1, SI_OPT_WINDOW_SHIFT = 2, SI_OPT_TIMING = 3,
+       SI_OPT_GRID_INTERVALS = 4 /* intervals per cell of the rank grid; applies to the next build */ };
 enum { SI_COUNT_AUTO = 0, SI_COUNT_WALK = 1, SI_COUNT_RANK = 2 };
 int siIndexSetOption(siIndex* ix, int option, long long value);
 /* With SI_OPT_TIMING = 1 every hot kernel launch is bracketed by a CUDA event pair on its

@@ -16,7 +16,7 @@ SI_NONE = (1 << 64) - 1
 
 ORDER_AUTO, ORDER_SORTED, ORDER_UNSORTED, ORDER_ASIS = 0, 1, 2, 3
 FILL_VALUES, FILL_IDXS, FILL_KEYS, FILL_ITEMS = 0, 1, 2, 3
-OPT_COUNT_ALGO, OPT_BUCKET_INTERVALS, OPT_WINDOW_SHIFT, OPT_TIMING = 0, 1, 2, 3
+OPT_COUNT_ALGO, OPT_BUCKET_INTERVALS, OPT_WINDOW_SHIFT, OPT_TIMING, OPT_GRID_INTERVALS = 0, 1, 2, 3, 4
 TAG_NAMES = {1: "pt_histogram", 2: "pt_onesweep", 3: "count_walk", 4: "count_rank", 5: "scan", 6: "fill"}
 COUNT_AUTO, COUNT_WALK, COUNT_RANK = 0, 1, 2
 

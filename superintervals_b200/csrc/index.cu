@@ -344,7 +344,12 @@ int partition_queries(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, uin
         return 0;
     }
     ix->plan_valid = false;
-    const PtPlan plan = pt_make_plan(nq, ix->n, ix->lo, ix->hi, ix->bucket_intervals, ix->window_shift);
+    // the rank kernel only needs its queries in the same few hundred intervals (table and index
+    // lines shared in L1); the walk kernel's tile sweep wants a tile of 32 queries within a few
+    // dozen intervals of each other, i.e. (almost) start-sorted: finer buckets, one more pass
+    const bool walk = !(ix->wellformed && ix->count_algo != SI_COUNT_WALK);
+    const uint32_t bucket = walk && ix->bucket_intervals > 8 ? 8 : ix->bucket_intervals;
+    const PtPlan plan = pt_make_plan(nq, ix->n, ix->lo, ix->hi, bucket, ix->window_shift);
     const size_t cap = ((size_t)nq + 63) & ~(size_t)63;
     if (plan.passes > 0 && (ix->q_A.ensure(cap * 12) || (plan.passes > 1 && ix->q_B.ensure(cap * 12)) ||
                             ix->q_ws.ensure(pt_workspace_bytes(nq))))
@@ -597,6 +602,10 @@ int siIndexSetOption(siIndex* ix, int option, long long value) {
             if (value < 1 || value > (1ll << 30)) break;
             ix->bucket_intervals = (uint32_t)value;
             ix->plan_valid = false;
+            return 0;
+        case SI_OPT_GRID_INTERVALS:   // takes effect at the next build()
+            if (value < 1 || value > (1ll << 20)) break;
+            ix->grid_intervals = (uint32_t)value;
             return 0;
         case SI_OPT_TIMING:
             ix->timer.on = value != 0;

@@ -51,7 +51,7 @@ struct siIndex {
     int32_t lo = 0, hi = 0;    // smallest start / largest end: the span the partition key buckets
     sib::DevBuf grid_tab;      // rank grid tables (tab_s | tab_e), cells + 1 entries each
     uint32_t grid_shift = 0, grid_cells = 0;
-    uint32_t grid_intervals = 16;   // target intervals per grid cell
+    uint32_t grid_intervals = 8;    // target intervals per grid cell
     sib::DevBuf tree;          // 32-ary max tree levels + prefix-max levels
     const int32_t* pmax32 = nullptr;   // inside `tree`: exclusive prefix max of ends per 32-block
 

@@ -293,7 +293,7 @@ qk_count_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __restrict_
 //       count = #{ starts <= qe }  -  #{ ends < qs }
 // -- the reference's upper_bound (hpp:501-513) on starts, and the same search on build()'s
 // ascending copy of the ends (IndexView::eall). build() also tabulates both ranks on a regular
-// grid over the index span (RankGrid, about 16 intervals per cell), so a query reads the two
+// grid over the index span (RankGrid, about 8 intervals per cell), so a query reads the two
 // table entries that bracket each rank and finishes with a handful of branch-free halving
 // steps inside the cell. Neighbouring queries (the partition, or a position-sorted caller,
 // made them neighbours) hit the same table and index lines in L1. Queries with qs > qe
