@@ -51,7 +51,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-search-values", action="store_true", help="skip the secondary search_values (C3) measurement")
-    ap.add_argument("--algo", default="auto", choices=["auto", "walk", "rank"], help="count kernel (SI_OPT_COUNT_ALGO)")
+    ap.add_argument("--algo", default="auto", choices=["auto", "walk", "rank", "cells"], help="count kernel (SI_OPT_COUNT_ALGO)")
+    ap.add_argument("--partition", action="store_true", help="cells kernel through the locality partition (SI_OPT_CELLS_DIRECT_BYTES=1)")
     ap.add_argument("--sv-intervals", type=int, default=4_000_000)
     ap.add_argument("--sv-queries", type=int, default=4_000_000)
     return ap.parse_args()
@@ -211,6 +212,7 @@ def kernel_table(recs, steps, nq, passes, a_walk):
     alg = {"pt_histogram": 4.0 * nq,                                             # one read of the starts
            "pt_onesweep": (20.0 + 24.0 * max(0, passes - 1)) / max(1, passes) * nq,  # 8+12 first pass, 12+12 after
            "count_rank": 16.0 * nq,                                              # 12 B record in, 4 B count out
+           "count_cells": 76.0 * nq,                                             # 8 B query in, 4 B count out, 2 x 32 B rank-cell sectors
            "count_walk": a_walk * nq}                                            # SURVEY 8d A_count: the reference walk
     out = {}
     for name, ms in recs:
@@ -332,15 +334,18 @@ def main():
 
     ix = DeviceIndex()
     if a.algo != "auto":
-        from superintervals_b200.device import COUNT_RANK, COUNT_WALK, OPT_COUNT_ALGO
-        ix.set_option(OPT_COUNT_ALGO, COUNT_WALK if a.algo == "walk" else COUNT_RANK)
-    for env, opt in (("SIB_BUCKET", 1), ("SIB_WSHIFT", 2), ("SIB_GRID", 4)):      # tuning experiments (tools/variants.sh)
+        from superintervals_b200.device import COUNT_CELLS, COUNT_RANK, COUNT_WALK, OPT_COUNT_ALGO
+        ix.set_option(OPT_COUNT_ALGO, {"walk": COUNT_WALK, "rank": COUNT_RANK, "cells": COUNT_CELLS}[a.algo])
+    if a.partition:
+        ix.set_option(5, 1)
+    for env, opt in (("SIB_BUCKET", 1), ("SIB_WSHIFT", 2), ("SIB_GRID", 4), ("SIB_CELLS_FILL", 6)):      # tuning experiments (tools/variants.sh)
         if os.environ.get(env):
             ix.set_option(opt, int(os.environ[env]))
     d_s, d_e = torch.from_numpy(starts).cuda(), torch.from_numpy(ends).cuda()
     torch.cuda.synchronize()
     t0 = time.perf_counter(); ix.build(d_s, d_e); torch.cuda.synchronize(); build_ms = (time.perf_counter() - t0) * 1e3
     t0 = time.perf_counter(); ix.build(d_s, d_e); torch.cuda.synchronize(); build_ms = min(build_ms, (time.perf_counter() - t0) * 1e3)
+    cells_info = ix.cells_info()
     d_qs, d_qe = torch.from_numpy(qs).cuda(), torch.from_numpy(qe).cuda()
     counts = torch.empty(nq, dtype=torch.int32, device="cuda")
 
@@ -487,8 +492,11 @@ def main():
             "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": workload_name(a), "intervals": a.intervals, "queries_per_gpu": nq,
-                       "step": (f"device partition of the batch by position ({passes} onesweep passes over 12-byte records) + count kernel"
+                       "step": ((f"device partition of the batch by position ({passes} onesweep passes over 12-byte records) + count kernel"
+                                 if passes else "count kernel straight on the shuffled batch (rank cells resident in L2, no partition)")
                                 if a.order == "shuffled" else "count kernel on position-sorted queries"),
+                       "count_kernel": next((k for k in ("count_cells", "count_rank", "count_walk") if k in kernels), None),
+                       "rank_cells": cells_info,
                        "count_algo": a.algo,
                        "l2": "inputs larger than L2: 800 MB of queries + 400 MB of counts per step vs 126 MB",
                        "index": "replicated per GPU", "collective": "all_gather of per-rank hit totals (CSR bases)"},

@@ -124,16 +124,32 @@ int siSortQueriesDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, s
  * hpp:651-825, on any index); SI_COUNT_RANK is the closed form
  * #{starts <= qe} - #{ends < qs} (valid on an index whose intervals all have
  * start <= end; queries with qs > qe inside such a batch still take the walk);
- * SI_COUNT_AUTO picks RANK whenever the index allows it. Results are identical. */
+ * SI_COUNT_CELLS is the same closed form answered from build()'s rank cells (one
+ * 32-byte record per 2^k coordinates: one sector read per rank, no locality needed, so a
+ * shuffled batch whose cells fit in L2 is answered without partitioning it);
+ * SI_COUNT_AUTO picks CELLS, else RANK, whenever the index allows it. Results are identical. */
 enum { SI_OPT_COUNT_ALGO = 0, SI_OPT_BUCKET_INTERVALS = 1, SI_OPT_WINDOW_SHIFT = 2, SI_OPT_TIMING = 3,
-       SI_OPT_GRID_INTERVALS = 4 /* intervals per cell of the rank grid; applies to the next build */ };
-enum { SI_COUNT_AUTO = 0, SI_COUNT_WALK = 1, SI_COUNT_RANK = 2 };
+       SI_OPT_GRID_INTERVALS = 4, /* intervals per cell of the rank grid; applies to the next build */
+       SI_OPT_CELLS_DIRECT_BYTES = 5, /* rank cells up to this many bytes answer batches unpartitioned (0 = 60 % of L2) */
+       SI_OPT_CELLS_FILL = 6 /* mean values per rank cell (1..28); applies to the next build */ };
+enum { SI_COUNT_AUTO = 0, SI_COUNT_WALK = 1, SI_COUNT_RANK = 2, SI_COUNT_CELLS = 3 };
 int siIndexSetOption(siIndex* ix, int option, long long value);
+/* The rank cells build() made (which = 0: over starts, 1: over ends). format 0 = none
+ * (malformed index or >= 2^31 intervals), 1 = 28 one-byte offsets, 2 = 14 two-byte offsets per
+ * 32-byte cell of 2^shift coordinates; overfull = cells answered from the sorted array instead;
+ * direct = 1 when count answers unpartitioned batches straight from the cells. */
+typedef struct {
+    unsigned format, shift;
+    unsigned long long cells, bytes, overfull;
+    int direct;
+} siCellsInfo;
+int siIndexCellsInfo(const siIndex* ix, int which, siCellsInfo* out);
 /* With SI_OPT_TIMING = 1 every hot kernel launch is bracketed by a CUDA event pair on its
  * own stream. Returns the number of (tag, milliseconds) records written (oldest first) and
  * clears them; waits for the recorded work. Tags: 1 partition histogram + scan, 2 partition
- * pass, 3 count (walk), 4 count (rank), 5 CSR scan, 6 CSR fill. bench.py's roofline uses it. */
-enum { SI_TAG_PT_HIST = 1, SI_TAG_PT_PASS = 2, SI_TAG_COUNT_WALK = 3, SI_TAG_COUNT_RANK = 4, SI_TAG_SCAN = 5, SI_TAG_FILL = 6 };
+ * pass, 3 count (walk), 4 count (rank), 5 CSR scan, 6 CSR fill, 7 count (cells). bench.py's roofline uses it. */
+enum { SI_TAG_PT_HIST = 1, SI_TAG_PT_PASS = 2, SI_TAG_COUNT_WALK = 3, SI_TAG_COUNT_RANK = 4, SI_TAG_SCAN = 5, SI_TAG_FILL = 6,
+       SI_TAG_COUNT_CELLS = 7 };
 int siIndexReadTimings(siIndex* ix, int* tags, float* ms, int max_out);
 
 int siAnyDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n,

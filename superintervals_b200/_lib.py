@@ -17,8 +17,9 @@ SI_NONE = (1 << 64) - 1
 ORDER_AUTO, ORDER_SORTED, ORDER_UNSORTED, ORDER_ASIS = 0, 1, 2, 3
 FILL_VALUES, FILL_IDXS, FILL_KEYS, FILL_ITEMS = 0, 1, 2, 3
 OPT_COUNT_ALGO, OPT_BUCKET_INTERVALS, OPT_WINDOW_SHIFT, OPT_TIMING, OPT_GRID_INTERVALS = 0, 1, 2, 3, 4
-TAG_NAMES = {1: "pt_histogram", 2: "pt_onesweep", 3: "count_walk", 4: "count_rank", 5: "scan", 6: "fill"}
-COUNT_AUTO, COUNT_WALK, COUNT_RANK = 0, 1, 2
+OPT_CELLS_DIRECT_BYTES, OPT_CELLS_FILL = 5, 6
+TAG_NAMES = {1: "pt_histogram", 2: "pt_onesweep", 3: "count_walk", 4: "count_rank", 5: "scan", 6: "fill", 7: "count_cells"}
+COUNT_AUTO, COUNT_WALK, COUNT_RANK, COUNT_CELLS = 0, 1, 2, 3
 
 
 class cSuperIntervals(C.Structure):
@@ -54,6 +55,11 @@ class siDeviceView(C.Structure):
                 ("branch", C.c_void_p), ("n", C.c_size_t), ("device", C.c_int)]
 
 
+class siCellsInfo(C.Structure):
+    _fields_ = [("format", C.c_uint), ("shift", C.c_uint), ("cells", C.c_ulonglong), ("bytes", C.c_ulonglong),
+                ("overfull", C.c_ulonglong), ("direct", C.c_int)]
+
+
 def build_library(verbose: bool = False) -> str:
     """nvcc-compile the CUDA library for sm_100a (cross-compiles without a GPU)."""
     cmd = ["make", "-C", os.path.join(HERE, "csrc")]
@@ -80,7 +86,7 @@ B200_SYMBOLS = [
     "countOverlapsBatch", "anyOverlapsBatch", "searchValuesBatch", "searchIdxsBatch", "searchKeysBatch",
     "searchItemsBatch", "coverageBatch", "siIndexCreate", "siIndexDestroy", "siIndexOf", "siIndexSize",
     "siIndexDeviceView", "siIndexBuildHost", "siIndexBuildDevice", "siIndexExport", "siCountDevice",
-    "siCountDevice64", "siSortQueriesDevice", "siIndexSetOption", "siIndexReadTimings", "siAnyDevice", "siScanDevice", "siFillDevice", "siCoverageDevice",
+    "siCountDevice64", "siSortQueriesDevice", "siIndexSetOption", "siIndexCellsInfo", "siIndexReadTimings", "siAnyDevice", "siScanDevice", "siFillDevice", "siCoverageDevice",
     "siIndexDeviceBytes",
 ]
 
@@ -162,6 +168,8 @@ def bind_b200(L):
     L.siCountDevice.argtypes = [vp, vp, vp, sz, vp, C.c_int, vp]
     L.siCountDevice64.argtypes = [vp, vp, vp, sz, vp, C.c_int, vp]
     L.siSortQueriesDevice.argtypes = [vp, vp, vp, sz, vp]
+    L.siIndexCellsInfo.argtypes = [vp, C.c_int, C.POINTER(siCellsInfo)]
+    L.siIndexCellsInfo.restype = C.c_int
     L.siIndexSetOption.argtypes = [vp, C.c_int, C.c_longlong]
     L.siIndexSetOption.restype = C.c_int
     L.siIndexReadTimings.argtypes = [vp, vp, vp, C.c_int]

@@ -159,6 +159,57 @@ bk_rank_grid_kernel(const int32_t* __restrict__ starts, const int32_t* __restric
     }
 }
 
+// ---- rank cells: one 32-byte record per 2^shift coordinates of a sorted array A -------------
+// (layout: RankCells in query_kernels.cuh). FMT 1: 28 one-byte offsets, FMT 2: 14 two-byte
+// offsets. Records 0..cells; the last one lies beyond A[n-1] and carries word 0 = n.
+// *overfull counts the cells whose values do not fit (they are answered from A itself).
+template <int FMT>
+__global__ void __launch_bounds__(BK_THREADS)
+bk_rank_cells_kernel(const int32_t* __restrict__ A, uint32_t n, int32_t lo, uint32_t shift, uint32_t cells,
+                     uint4* __restrict__ rec, unsigned long long* __restrict__ overfull) {
+    constexpr uint32_t SLOTS = FMT == 1 ? 28u : 14u;
+    const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
+    for (uint64_t c = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; c <= cells; c += stride) {
+        const int64_t v0 = (int64_t)lo + (int64_t)(c << shift);
+        const int64_t v1 = v0 + ((int64_t)1 << shift);
+        // #{A < v0}, #{A < v1}: halving searches compared in 64 bits (v1 may exceed INT_MAX)
+        uint32_t p0 = 0, p1 = 0, len = n;
+        while (len > 1) {
+            const uint32_t half = len >> 1;
+            p0 += ((int64_t)A[p0 + half] < v0) ? (len - half) : 0u;
+            p1 += ((int64_t)A[p1 + half] < v1) ? (len - half) : 0u;
+            len = half;
+        }
+        p0 += ((int64_t)A[p0] < v0) ? 1u : 0u;
+        p1 += ((int64_t)A[p1] < v1) ? 1u : 0u;
+        const uint32_t cnt = p1 - p0;
+        uint32_t w[8];
+        w[0] = p0;
+#pragma unroll
+        for (int k = 1; k < 8; ++k) w[k] = 0xFFFFFFFFu;
+        if (cnt > SLOTS) {
+            w[0] |= 0x80000000u;
+            atomicAdd(overfull, 1ull);
+        } else {
+#pragma unroll
+            for (uint32_t k = 0; k < SLOTS; ++k) {
+                if (k < cnt) {
+                    const uint32_t off = (uint32_t)((int64_t)A[p0 + k] - v0);
+                    if (FMT == 1) {
+                        const uint32_t sh = (k & 3u) * 8u;
+                        w[1 + (k >> 2)] = (w[1 + (k >> 2)] & ~(0xFFu << sh)) | (off << sh);
+                    } else {
+                        const uint32_t sh = (k & 1u) * 16u;
+                        w[1 + (k >> 1)] = (w[1 + (k >> 1)] & ~(0xFFFFu << sh)) | (off << sh);
+                    }
+                }
+            }
+        }
+        rec[2 * c] = make_uint4(w[0], w[1], w[2], w[3]);
+        rec[2 * c + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+
 // ---- 32-ary max tree over ends -------------------------------------------------------
 // level 0 = ends; level L entry k = max of level L-1 entries [32k, 32k+32).
 // One launch produces two levels: a CTA of 1024 threads folds 1024 inputs into

@@ -52,6 +52,11 @@ __device__ __forceinline__ uint64_t ld_stream(const uint64_t* p) {
     return v;
 }
 
+__device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(uint64_t* p, uint64_t v) {
+    __stcs(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+}
+
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;

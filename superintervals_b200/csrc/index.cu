@@ -121,7 +121,7 @@ using namespace sib;
     } while (0)
 
 size_t siIndex::device_bytes() const {
-    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &esort, &eall, &grid_tab, &b_in_s, &b_in_e, &b_in_v,
+    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &esort, &eall, &grid_tab, &cells_s, &cells_e, &b_in_s, &b_in_e, &b_in_v,
                            &b_kA, &b_kB, &b_vA, &b_vB, &b_ws, &small, &q_A, &q_B,
                            &q_ws, &scan_status, &h_qs, &h_qe, &h_counts, &h_offsets, &h_out, &h_cov};
     size_t s = 0;
@@ -158,6 +158,8 @@ IndexView view_of(const siIndex* ix) {
     v.grid.lo = ix->lo;
     v.grid.shift = ix->grid_shift;
     v.grid.cells = ix->grid_cells;
+    v.cells_s = RankCells{ix->cells_s.as<uint4>(), ix->cm_s.lo, ix->cm_s.span, ix->cm_s.shift, ix->cm_s.fmt};
+    v.cells_e = RankCells{ix->cells_e.as<uint4>(), ix->cm_e.lo, ix->cm_e.span, ix->cm_e.shift, ix->cm_e.fmt};
     v.n = ix->n;
     v.wellformed = ix->wellformed ? 1u : 0u;
     return v;
@@ -226,10 +228,43 @@ int build_branch(siIndex* ix, cudaStream_t s) {
     return 0;
 }
 
+// Rank cells over a sorted device array A[0..n) whose first and last values are known on the
+// host: pick the record format and the cell width from the density, then one thread per cell.
+int build_cells(siIndex* ix, const int32_t* A, int32_t first, int32_t last, DevBuf* buf, siIndex::CellsMeta* m,
+                unsigned long long* d_overfull, cudaStream_t s) {
+    const uint32_t n = ix->n;
+    const uint64_t range = (uint64_t)((int64_t)last - (int64_t)first) + 1;
+    // largest shift <= smax with a mean of at most `fill` values per cell
+    auto pick = [&](uint32_t fill, uint32_t smax) {
+        uint32_t sh = 0;
+        while (sh < smax && ((uint64_t)n << (sh + 1)) <= (uint64_t)fill * range) ++sh;
+        return sh;
+    };
+    uint32_t shift = pick(ix->cells_fill8, 8), fmt = 1;
+    if (((uint64_t)n << shift) < 3 * range) {   // sparse: one-byte offsets would leave the cells empty
+        fmt = 2;
+        shift = pick(ix->cells_fill16, 16);
+    }
+    m->lo = first;
+    m->span = (uint32_t)(range - 1);
+    m->shift = shift;
+    m->cells = (uint32_t)(range >> shift) + 1u;   // cell of hi + 1 included
+    const size_t bytes = ((size_t)m->cells + 1) * 32;
+    if (buf->ensure(bytes)) return last_error_code();
+    const int grid = grid_for((uint64_t)m->cells + 1, BK_THREADS, ix->sm_count * 16);
+    if (fmt == 1)
+        SIB_LAUNCH((bk_rank_cells_kernel<1>), grid, BK_THREADS, 0, s, A, n, first, shift, m->cells, buf->as<uint4>(), d_overfull);
+    else
+        SIB_LAUNCH((bk_rank_cells_kernel<2>), grid, BK_THREADS, 0, s, A, n, first, shift, m->cells, buf->as<uint4>(), d_overfull);
+    m->fmt = fmt;
+    return 0;
+}
+
 int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const int32_t* d_v, size_t n,
                       cudaStream_t s) {
     ix->built = false;
     ix->plan_valid = false;
+    ix->cm_s.fmt = ix->cm_e.fmt = 0;
     if (n > MAX_N) {
         set_error_msg(cudaErrorInvalidValue, "siIndexBuild: more than 2^32-16385 intervals");
         return cudaErrorInvalidValue;
@@ -303,8 +338,24 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
                    ix->b_kA.as<uint32_t>(), ix->b_kB.as<uint32_t>(), ws.final_sel, ix->n, ix->n_padded,
                    ix->eall.as<int32_t>());
         SIB_CHECK(cudaMemcpyAsync(&ix->hi, ix->eall.as<int32_t>() + (ix->n - 1), 4, cudaMemcpyDeviceToHost, s));
+        int32_t last_start = 0, first_end = 0;
+        SIB_CHECK(cudaMemcpyAsync(&last_start, ix->starts.as<int32_t>() + (ix->n - 1), 4, cudaMemcpyDeviceToHost, s));
+        SIB_CHECK(cudaMemcpyAsync(&first_end, ix->eall.as<int32_t>(), 4, cudaMemcpyDeviceToHost, s));
         // rank grid over [lo, hi]: the span has to be known on the host to size the tables
         SIB_CHECK(cudaStreamSynchronize(s));
+        if (n < 0x80000000ull) {   // bit 31 of a cell's rank word flags an over-full cell
+            unsigned long long* d_over = reinterpret_cast<unsigned long long*>(ix->small.as<uint32_t>() + 8);
+            SIB_CHECK(cudaMemsetAsync(d_over, 0, 16, s));
+            rc = build_cells(ix, ix->starts.as<int32_t>(), ix->lo, last_start, &ix->cells_s, &ix->cm_s, d_over, s);
+            if (rc) return rc;
+            rc = build_cells(ix, ix->eall.as<int32_t>(), first_end, ix->hi, &ix->cells_e, &ix->cm_e, d_over + 1, s);
+            if (rc) return rc;
+            unsigned long long over[2] = {0, 0};
+            SIB_CHECK(cudaMemcpyAsync(over, d_over, 16, cudaMemcpyDeviceToHost, s));
+            SIB_CHECK(cudaStreamSynchronize(s));
+            ix->cm_s.overfull = over[0];
+            ix->cm_e.overfull = over[1];
+        }
         {
             const uint64_t range = (uint64_t)((int64_t)ix->hi - (int64_t)ix->lo) + 1;   // >= 1 on a well-formed index
             int gbits = 0;
@@ -334,6 +385,23 @@ void release_build_scratch(siIndex* ix) {
     }
 }
 
+// which count kernel answers this index (SI_OPT_COUNT_ALGO; results are identical)
+int count_algo_of(const siIndex* ix) {
+    const bool cells_ok = ix->wellformed && ix->cm_s.fmt && ix->cm_e.fmt;
+    switch (ix->count_algo) {
+        case SI_COUNT_WALK: return SI_COUNT_WALK;
+        case SI_COUNT_RANK: return ix->wellformed ? SI_COUNT_RANK : SI_COUNT_WALK;
+        default: return cells_ok ? SI_COUNT_CELLS : ix->wellformed ? SI_COUNT_RANK : SI_COUNT_WALK;
+    }
+}
+
+// Rank cells small enough to stay in L2 answer a batch in whatever order it arrives: no partition.
+bool cells_direct(const siIndex* ix) {
+    if (count_algo_of(ix) != SI_COUNT_CELLS) return false;
+    const size_t limit = ix->cells_direct_bytes ? ix->cells_direct_bytes : ix->l2_bytes / 10 * 6;
+    return ((size_t)ix->cm_s.cells + ix->cm_e.cells + 2) * 32 <= limit;
+}
+
 // Partition a query batch for locality (partition.cuh): records grouped by (result window,
 // position bucket). *out describes the partitioned records; the partition of the same
 // (d_qs, d_qe, nq) may be reused by the fill that follows a count (documented contract).
@@ -347,7 +415,7 @@ int partition_queries(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, uin
     // the rank kernel only needs its queries in the same few hundred intervals (table and index
     // lines shared in L1); the walk kernel's tile sweep wants a tile of 32 queries within a few
     // dozen intervals of each other, i.e. (almost) start-sorted: finer buckets, one more pass
-    const bool walk = !(ix->wellformed && ix->count_algo != SI_COUNT_WALK);
+    const bool walk = count_algo_of(ix) == SI_COUNT_WALK;
     const uint32_t bucket = walk && ix->bucket_intervals > 8 ? 8 : ix->bucket_intervals;
     const PtPlan plan = pt_make_plan(nq, ix->n, ix->lo, ix->hi, bucket, ix->window_shift);
     const size_t cap = ((size_t)nq + 63) & ~(size_t)63;
@@ -380,8 +448,11 @@ int resolve_order(siIndex* ix, const int32_t* d_qs, uint32_t nq, int order, cuda
 
 template <typename CountT>
 int launch_count(siIndex* ix, const QueryRecords& rec, uint32_t nq, CountT* d_counts, cudaStream_t s) {
-    const bool rank = ix->wellformed && ix->count_algo != SI_COUNT_WALK;
-    if (rank) {
+    const int algo = count_algo_of(ix);
+    if (algo == SI_COUNT_CELLS) {
+        const int grid = (int)(((uint64_t)nq + QC_TILE - 1) / QC_TILE);
+        SIB_LAUNCH_T(ix, TAG_COUNT_CELLS, (qk_count_cells_kernel<CountT>), grid, QC_THREADS, 0, s, view_of(ix), rec, nq, d_counts);
+    } else if (algo == SI_COUNT_RANK) {
         const int grid = (int)(((uint64_t)nq + QR_TILE - 1) / QR_TILE);
         SIB_LAUNCH_T(ix, TAG_COUNT_RANK, (qk_count_rank_kernel<CountT>), grid, QR_THREADS, 0, s, view_of(ix), rec, nq, d_counts);
     } else {
@@ -409,10 +480,11 @@ int count_impl(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, 
         SIB_CHECK(cudaMemsetAsync(d_counts, 0, n * sizeof(CountT), s));
         return 0;
     }
-    order = resolve_order(ix, d_qs, (uint32_t)n, order, s);
-    if (order < 0) { set_error(cudaGetLastError(), "resolve_order", __FILE__, __LINE__); return last_error_code(); }
     const bool armed = ix->plan_armed;
     ix->plan_armed = false;
+    if (cells_direct(ix) && !(armed && order == SI_ORDER_UNSORTED)) order = SI_ORDER_ASIS;   // order is irrelevant to the cells kernel
+    order = resolve_order(ix, d_qs, (uint32_t)n, order, s);
+    if (order < 0) { set_error(cudaGetLastError(), "resolve_order", __FILE__, __LINE__); return last_error_code(); }
     // batches beyond the partition's size are processed in slices (their scratch is bounded too)
     for (size_t at = 0; at < n; at += PT_MAX_BATCH) {
         const uint32_t m = (uint32_t)(n - at < PT_MAX_BATCH ? n - at : PT_MAX_BATCH);
@@ -470,6 +542,8 @@ siIndex* siIndexCreate(void) {
     ix->device = dev;
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) ix->sm_count = sms;
+    int l2 = 0;
+    if (cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev) == cudaSuccess && l2 > 0) ix->l2_bytes = (size_t)l2;
     e = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { sib::set_error(e, "cudaStreamCreate", __FILE__, __LINE__); delete ix; return nullptr; }
     return ix;
@@ -479,6 +553,7 @@ void siIndexDestroy(siIndex* ix) {
     if (!ix) return;
     DeviceGuard g(ix->device);
     DevBuf* all[] = {&ix->starts, &ix->ends, &ix->values, &ix->branch, &ix->perm, &ix->tree, &ix->esort, &ix->eall, &ix->grid_tab,
+                     &ix->cells_s, &ix->cells_e,
                      &ix->b_in_s, &ix->b_in_e, &ix->b_in_v, &ix->b_kA, &ix->b_kB, &ix->b_vA, &ix->b_vB, &ix->b_ws,
                      &ix->small, &ix->q_A, &ix->q_B, &ix->q_ws, &ix->scan_status, &ix->h_qs,
                      &ix->h_qe, &ix->h_counts, &ix->h_offsets, &ix->h_out, &ix->h_cov};
@@ -498,6 +573,18 @@ void siIndexDestroy(siIndex* ix) {
 
 size_t siIndexSize(const siIndex* ix) { return ix ? ix->n : 0; }
 size_t siIndexDeviceBytes(const siIndex* ix) { return ix ? ix->device_bytes() : 0; }
+
+int siIndexCellsInfo(const siIndex* ix, int which, siCellsInfo* out) {
+    if (!ix || !out || !ix->built || which < 0 || which > 1) return cudaErrorInvalidValue;
+    const siIndex::CellsMeta& m = which ? ix->cm_e : ix->cm_s;
+    out->format = m.fmt;
+    out->shift = m.shift;
+    out->cells = m.fmt ? (unsigned long long)m.cells + 1 : 0;
+    out->bytes = out->cells * 32;
+    out->overfull = m.overfull;
+    out->direct = cells_direct(ix) ? 1 : 0;
+    return 0;
+}
 
 int siIndexDeviceView(const siIndex* ix, siDeviceView* out) {
     if (!ix || !out || !ix->built) return cudaErrorNotReady;
@@ -595,7 +682,7 @@ int siIndexSetOption(siIndex* ix, int option, long long value) {
     if (!ix) return cudaErrorInvalidValue;
     switch (option) {
         case SI_OPT_COUNT_ALGO:
-            if (value < SI_COUNT_AUTO || value > SI_COUNT_RANK) break;
+            if (value < SI_COUNT_AUTO || value > SI_COUNT_CELLS) break;
             ix->count_algo = (int)value;
             return 0;
         case SI_OPT_BUCKET_INTERVALS:
@@ -610,6 +697,15 @@ int siIndexSetOption(siIndex* ix, int option, long long value) {
         case SI_OPT_TIMING:
             ix->timer.on = value != 0;
             ix->timer.used = 0;
+            return 0;
+        case SI_OPT_CELLS_DIRECT_BYTES:   // 0 restores the default (60 % of L2); 1 = never direct
+            if (value < 0) break;
+            ix->cells_direct_bytes = (size_t)value;
+            return 0;
+        case SI_OPT_CELLS_FILL:           // mean values per cell, one-byte format; applies to the next build
+            if (value < 1 || value > 28) break;
+            ix->cells_fill8 = (uint32_t)value;
+            ix->cells_fill16 = (uint32_t)(value + 1) / 2 > 14 ? 14 : (uint32_t)(value + 1) / 2;
             return 0;
         case SI_OPT_WINDOW_SHIFT:
             if (value < 10 || value > 31) break;

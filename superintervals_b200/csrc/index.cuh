@@ -21,7 +21,7 @@ unsigned long long launches();
 
 // Optional per-launch device timing (siIndexSetOption SI_OPT_TIMING): a CUDA event pair on the
 // launching stream around each hot kernel, read back by siIndexReadTimings. Off by default.
-enum LaunchTag : int { TAG_PT_HIST = 1, TAG_PT_PASS = 2, TAG_COUNT_WALK = 3, TAG_COUNT_RANK = 4, TAG_SCAN = 5, TAG_FILL = 6 };
+enum LaunchTag : int { TAG_PT_HIST = 1, TAG_PT_PASS = 2, TAG_COUNT_WALK = 3, TAG_COUNT_RANK = 4, TAG_SCAN = 5, TAG_FILL = 6, TAG_COUNT_CELLS = 7 };
 struct LaunchTimer {
     bool on = false;
     cudaEvent_t* ev = nullptr;   // 2 * cap events
@@ -52,6 +52,13 @@ struct siIndex {
     sib::DevBuf grid_tab;      // rank grid tables (tab_s | tab_e), cells + 1 entries each
     uint32_t grid_shift = 0, grid_cells = 0;
     uint32_t grid_intervals = 8;    // target intervals per grid cell
+    // rank cells (RankCells in query_kernels.cuh): one 32-byte record per 2^shift coordinates
+    struct CellsMeta { int32_t lo = 0; uint32_t span = 0, shift = 0, fmt = 0, cells = 0; unsigned long long overfull = 0; };
+    sib::DevBuf cells_s, cells_e;
+    CellsMeta cm_s, cm_e;
+    uint32_t cells_fill8 = 16, cells_fill16 = 7;   // target mean values per cell (28 / 14 slots)
+    size_t cells_direct_bytes = 0;                 // cells up to this size answer unpartitioned batches (0: 60 % of L2)
+    size_t l2_bytes = 0;
     sib::DevBuf tree;          // 32-ary max tree levels + prefix-max levels
     const int32_t* pmax32 = nullptr;   // inside `tree`: exclusive prefix max of ends per 32-block
 
@@ -75,7 +82,7 @@ struct siIndex {
     sib::LaunchTimer timer;
 
     // ---- options (siIndexSetOption) ----------------------------------------------------
-    int count_algo = 0;                         // SI_COUNT_AUTO / SI_COUNT_WALK / SI_COUNT_RANK
+    int count_algo = 0;                         // SI_COUNT_AUTO / SI_COUNT_WALK / SI_COUNT_RANK / SI_COUNT_CELLS
     uint32_t bucket_intervals = 1024;           // partition: index intervals per position bucket
     uint32_t window_shift = 22;                 // partition: log2(queries per result window)
 

@@ -39,6 +39,20 @@ struct RankGrid {
     uint32_t cells;
 };
 
+// Rank cells (build(), well-formed indexes only): the sorted array A (the starts, or all ends
+// ascending) cut into cells of 2^shift coordinates; one 32-byte record -- one L2 sector -- per
+// cell:   word 0 = #{ A < cell_lo }  (bit 31 set: the cell holds more values than fit, use A),
+//         then the cell's values as ascending offsets from cell_lo, 28 x u8 (fmt 1, shift <= 8)
+//         or 14 x u16 (fmt 2, shift <= 16), padded with all-ones (never below any offset).
+// #{ A < x } is then ONE 256-bit load + a SWAR count, wherever x falls.
+struct RankCells {
+    const uint4* rec;   // 2 x uint4 per cell, cells + 1 records (the last is a sentinel with word 0 = n)
+    int32_t lo;         // A[0]
+    uint32_t span;      // A[n-1] - A[0]
+    uint32_t shift;
+    uint32_t fmt;       // 0 = not built
+};
+
 struct IndexView {
     const int32_t* starts;
     const int32_t* ends;     // padded to a multiple of 128 entries (pad = INT_MIN)
@@ -48,6 +62,8 @@ struct IndexView {
     const int32_t* esort;    // ends with every aligned 32-block sorted ascending (n_pad entries), from build()
     const int32_t* eall;     // all ends sorted ascending (n entries), from build(); only on a well-formed index
     RankGrid grid;           // rank tables for qk_count_rank_kernel; only on a well-formed index
+    RankCells cells_s;       // rank cells over starts  } qk_count_cells_kernel; only on a well-formed
+    RankCells cells_e;       // rank cells over eall    } index of fewer than 2^31 intervals
     uint32_t n;
     uint32_t wellformed;     // 1 when every stored interval has start <= end (checked by build())
 };
@@ -371,6 +387,136 @@ qk_count_rank_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __rest
             if (inverted) c = cw;
         }
         if (live[j]) counts[q[j]] = (CountT)c;
+    }
+}
+
+// ---- count by rank cells ---------------------------------------------------------------------
+// The same closed form as qk_count_rank_kernel, count = #{starts <= qe} - #{ends < qs}, but each
+// rank costs ONE 32-byte sector wherever the query falls (RankCells above), so a batch needs no
+// locality at all: a shuffled batch is answered in the caller's order, the queries streamed in and
+// the counts streamed out coalesced, the two sectors per query served by L2 (C2: 62 MB of cells).
+// Per query: 8 B in, 4 B out, 2 x 32 B sector reads. Queries with qs > qe (quirk Q6) take the
+// branch-array walk, as in qk_count_rank_kernel. Bit-exact with qk_count_kernel.
+constexpr int QC_THREADS = 256;
+#ifndef SIB_QC_PER_THREAD
+#define SIB_QC_PER_THREAD 4
+#endif
+constexpr int QC_PER_THREAD = SIB_QC_PER_THREAD;
+constexpr uint32_t QC_TILE = QC_THREADS * QC_PER_THREAD;
+
+struct __align__(32) CellRec { uint32_t w[8]; };
+
+__device__ __forceinline__ CellRec ld_cell(const uint4* p) {
+    CellRec r;
+#ifdef SIB_QC_NOALLOC
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+                 : "l"(p));
+    return r;
+}
+
+// where x falls: cell number and offset inside the cell. x is clamped to [lo, hi + 1], so
+// everything below the array ranks 0 (cell 0, offset 0) and everything above ranks n.
+__device__ __forceinline__ void cell_of(const RankCells& rc, int64_t x, uint32_t& cell, uint32_t& off) {
+    int64_t d = x - (int64_t)rc.lo;
+    d = d < 0 ? 0 : d;
+    const int64_t dmax = (int64_t)rc.span + 1;
+    d = d > dmax ? dmax : d;
+    cell = (uint32_t)((uint64_t)d >> rc.shift);
+    off = (uint32_t)d & ((1u << rc.shift) - 1u);
+}
+
+// #{ offsets in the record < off }, SWAR over the 7 payload words
+__device__ __forceinline__ uint32_t cell_below(const CellRec& r, uint32_t off, uint32_t fmt) {
+    uint32_t acc = 0;
+    if (fmt == 1u) {
+        const uint32_t t = off * 0x01010101u;
+#pragma unroll
+        for (int k = 1; k < 8; ++k) acc += __vcmpltu4(r.w[k], t) & 0x01010101u;
+        return (acc * 0x01010101u) >> 24;
+    }
+    const uint32_t t = off * 0x00010001u;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) acc += __vcmpltu2(r.w[k], t) & 0x00010001u;
+    return (acc + (acc >> 16)) & 0xFFFFu;
+}
+
+// an over-full cell (bit 31 of word 0): #{ A < x } by halving search inside the cell's run of A
+__device__ __noinline__ uint32_t cell_overflow_rank(const RankCells& rc, const int32_t* __restrict__ A, uint32_t cell,
+                                                    uint32_t base, int64_t x) {
+    const uint32_t next = __ldg(reinterpret_cast<const uint32_t*>(rc.rec + 2 * ((size_t)cell + 1))) & 0x7FFFFFFFu;
+    uint32_t lo = base, len = next - base;
+    while (len) {
+        const uint32_t half = len >> 1;
+        const bool below = (int64_t)ld_nc(A + lo + half) < x;
+        lo += below ? half + 1u : 0u;
+        len = below ? len - half - 1u : half;
+    }
+    return lo;
+}
+
+// #{ A < x } from an already loaded record
+__device__ __forceinline__ uint32_t cell_rank(const RankCells& rc, const int32_t* __restrict__ A, const CellRec& r,
+                                              uint32_t cell, uint32_t off, int64_t x) {
+    if (r.w[0] & 0x80000000u) return cell_overflow_rank(rc, A, cell, r.w[0] & 0x7FFFFFFFu, x);
+    return r.w[0] + cell_below(r, off, rc.fmt);
+}
+
+// #{ A < x } (one dependent load); used by the fill kernel for upper_bound(qe)
+__device__ __forceinline__ uint32_t cells_rank_lt(const RankCells& rc, const int32_t* __restrict__ A, int64_t x) {
+    uint32_t cell, off;
+    cell_of(rc, x, cell, off);
+    const CellRec r = ld_cell(rc.rec + 2 * (size_t)cell);
+    return cell_rank(rc, A, r, cell, off, x);
+}
+
+template <typename CountT>
+__global__ void __launch_bounds__(QC_THREADS)
+qk_count_cells_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __restrict__ counts) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint64_t base = (uint64_t)blockIdx.x * QC_TILE;
+    const RankCells cs = ix.cells_s, ce = ix.cells_e;
+
+    int32_t qs[QC_PER_THREAD], qe[QC_PER_THREAD];
+    bool live[QC_PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < QC_PER_THREAD; ++j) {
+        const uint64_t t = base + (uint64_t)j * QC_THREADS + tid;
+        live[j] = t < nq;
+        qs[j] = live[j] ? ld_stream(rec.qs + t) : 0;
+        qe[j] = live[j] ? ld_stream(rec.qe + t) : 0;
+    }
+    // all sector loads of the thread's queries in flight together
+    uint32_t cell_s[QC_PER_THREAD], off_s[QC_PER_THREAD], cell_e[QC_PER_THREAD], off_e[QC_PER_THREAD];
+    CellRec rs[QC_PER_THREAD], re[QC_PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < QC_PER_THREAD; ++j) {
+        cell_of(cs, (int64_t)qe[j] + 1, cell_s[j], off_s[j]);   // #{starts <= qe} = #{starts < qe + 1}
+        cell_of(ce, (int64_t)qs[j], cell_e[j], off_e[j]);       // #{ends < qs}
+        rs[j] = ld_cell(cs.rec + 2 * (size_t)cell_s[j]);
+        re[j] = ld_cell(ce.rec + 2 * (size_t)cell_e[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < QC_PER_THREAD; ++j) {
+        const uint32_t ns = cell_rank(cs, ix.starts, rs[j], cell_s[j], off_s[j], (int64_t)qe[j] + 1);
+        const uint32_t ne = cell_rank(ce, ix.eall, re[j], cell_e[j], off_e[j], (int64_t)qs[j]);
+        uint32_t c = ns - ne;
+        const bool inverted = live[j] && qs[j] > qe[j];
+        if (__any_sync(FULL_MASK, inverted)) {
+            // qs > qe: the walk's own definition, #{ j <= ub(qe) : ends[j] >= qs }
+            uint32_t cw = 0;
+            const uint32_t i = inverted ? ns - 1u : NONE32;   // ns = #{starts <= qe}; 0 - 1 wraps to NONE32
+            walk_tail(ix, i, qs[j], cw, lane);
+            if (inverted) c = cw;
+        }
+        const uint64_t t = base + (uint64_t)j * QC_THREADS + tid;
+        if (live[j]) {
+            if (rec.idx) counts[ld_stream(rec.idx + t)] = (CountT)c;
+            else st_stream(counts + t, (CountT)c);
+        }
     }
 }
 

@@ -13,11 +13,12 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (COUNT_AUTO, COUNT_RANK, COUNT_WALK, FILL_IDXS, FILL_ITEMS, FILL_KEYS, FILL_VALUES, OPT_BUCKET_INTERVALS,
+from ._lib import (COUNT_AUTO, COUNT_CELLS, COUNT_RANK, COUNT_WALK, OPT_CELLS_DIRECT_BYTES, OPT_CELLS_FILL, FILL_IDXS, FILL_ITEMS, FILL_KEYS, FILL_VALUES, OPT_BUCKET_INTERVALS,
                    OPT_COUNT_ALGO, OPT_TIMING, OPT_WINDOW_SHIFT, ORDER_ASIS, ORDER_AUTO, ORDER_SORTED, ORDER_UNSORTED)
 
 __all__ = ["DeviceIndex", "ORDER_AUTO", "ORDER_SORTED", "ORDER_UNSORTED", "ORDER_ASIS", "OPT_COUNT_ALGO",
-           "OPT_BUCKET_INTERVALS", "OPT_WINDOW_SHIFT", "OPT_TIMING", "COUNT_AUTO", "COUNT_WALK", "COUNT_RANK"]
+           "OPT_BUCKET_INTERVALS", "OPT_WINDOW_SHIFT", "OPT_TIMING", "COUNT_AUTO", "COUNT_WALK", "COUNT_RANK", "COUNT_CELLS",
+           "OPT_CELLS_DIRECT_BYTES", "OPT_CELLS_FILL"]
 
 
 def _stream():
@@ -116,12 +117,23 @@ class DeviceIndex:
         _lib.check("siSortQueriesDevice")
 
     def set_option(self, option, value):
-        """siIndexSetOption: OPT_COUNT_ALGO (COUNT_AUTO/WALK/RANK), OPT_BUCKET_INTERVALS, OPT_WINDOW_SHIFT."""
+        """siIndexSetOption: OPT_COUNT_ALGO (COUNT_AUTO/WALK/RANK/CELLS), OPT_BUCKET_INTERVALS, OPT_WINDOW_SHIFT."""
         rc = self._L.siIndexSetOption(self._ix, int(option), int(value))
         _lib.check("siIndexSetOption")
         if rc:
             raise ValueError(f"siIndexSetOption({option}, {value}) failed")
         return self
+
+    def cells_info(self):
+        """Rank cells of the built index: {"starts": {...}, "ends": {...}} (siIndexCellsInfo)."""
+        out = {}
+        for which, name in ((0, "starts"), (1, "ends")):
+            ci = _lib.siCellsInfo()
+            if self._L.siIndexCellsInfo(self._ix, which, C.byref(ci)):
+                raise RuntimeError("siIndexCellsInfo: index not built")
+            out[name] = {"format": int(ci.format), "shift": int(ci.shift), "cells": int(ci.cells), "bytes": int(ci.bytes),
+                         "overfull": int(ci.overfull), "direct": bool(ci.direct)}
+        return out
 
     def read_timings(self, max_records=4096):
         """[(kernel name, ms), ...] recorded since the last read (needs set_option(OPT_TIMING, 1))."""

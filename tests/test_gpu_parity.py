@@ -99,12 +99,13 @@ PLANS = [(1024, 22), (1, 10), (64, 12), (1 << 20, 22), (16, 16)]   # (bucket_int
                                             ("nested", 70_000, 30_000, 9), ("negative", 30_000, 30_000, 11),
                                             ("c1", 1, 10, 4)])
 def test_count_kernels_and_partition_plans_agree(kind, n, nq, seed):
-    """Both count kernels (branch-array walk / closed-form rank), every partition shape (0-3 passes,
+    """All count kernels (branch-array walk / closed-form rank by grid / by rank cells), every partition shape (0-3 passes,
     with and without result windows) and every order mode give the oracle's counts; the CSR fill
     reuses each partition. Inverted queries inside a rank batch take the walk (quirk Q6)."""
     import torch
-    from superintervals_b200.device import (COUNT_RANK, COUNT_WALK, OPT_BUCKET_INTERVALS, OPT_COUNT_ALGO,
-                                            OPT_WINDOW_SHIFT, ORDER_ASIS, ORDER_SORTED, ORDER_UNSORTED, DeviceIndex)
+    from superintervals_b200.device import (COUNT_CELLS, COUNT_RANK, COUNT_WALK, OPT_BUCKET_INTERVALS,
+                                            OPT_CELLS_DIRECT_BYTES, OPT_COUNT_ALGO, OPT_WINDOW_SHIFT, ORDER_ASIS,
+                                            ORDER_SORTED, ORDER_UNSORTED, DeviceIndex)
     s, e, qs, qe = _mk(kind, n, nq, seed)
     o = Oracle(s, e)
     want = o.count_batch(qs, qe)
@@ -115,8 +116,9 @@ def test_count_kernels_and_partition_plans_agree(kind, n, nq, seed):
     dqs, dqe = dev(qs), dev(qe)
     srt = np.argsort(qs, kind="stable")
     sqs, sqe = dev(qs[srt]), dev(qe[srt])
-    for algo in (COUNT_WALK, COUNT_RANK):
-        ix.set_option(OPT_COUNT_ALGO, algo)
+    for algo, direct in ((COUNT_WALK, 0), (COUNT_RANK, 0), (COUNT_CELLS, 0), (COUNT_CELLS, 1)):
+        # cells: once answering the unpartitioned batch straight from L2, once through the partition
+        ix.set_option(OPT_COUNT_ALGO, algo).set_option(OPT_CELLS_DIRECT_BYTES, direct)
         assert np.array_equal(u32(ix.count(dqs, dqe, order=ORDER_ASIS)), want), (algo, "asis")
         assert np.array_equal(u32(ix.count(sqs, sqe, order=ORDER_SORTED)), want[srt]), (algo, "sorted")
         for bucket, wshift in PLANS:
@@ -125,3 +127,76 @@ def test_count_kernels_and_partition_plans_agree(kind, n, nq, seed):
             off, vals = ix.search_values(dqs, dqe, order=ORDER_UNSORTED)
             assert np.array_equal(off.cpu().numpy().astype(np.uint64), off_o), (algo, bucket, wshift)
             assert np.array_equal(vals.cpu().numpy(), res["values"]), (algo, bucket, wshift)
+
+
+def _brute_counts(s, e, qs, qe):
+    """#{ j : s[j] <= qe, e[j] >= qs } for well-formed intervals and qs <= qe (closed form, int64)."""
+    ss, es = np.sort(s.astype(np.int64)), np.sort(e.astype(np.int64))
+    return (np.searchsorted(ss, qe.astype(np.int64), "right") - np.searchsorted(es, qs.astype(np.int64), "left")).astype(np.uint64)
+
+
+CELL_CASES = ["full_range", "one_point", "clusters", "dense", "sparse", "single", "two_far"]
+
+
+@pytest.mark.parametrize("case", CELL_CASES)
+@pytest.mark.parametrize("fill", [0, 1, 3, 28])
+def test_rank_cells_edge_cases(case, fill):
+    """The rank cells (one 32-byte record per 2^k coordinates) at their edges: the whole int32 span,
+    every interval on one coordinate (over-full cells fall back to the sorted arrays), clustered starts,
+    both record formats at several cell widths, queries at INT_MIN / INT_MAX and inverted queries."""
+    import torch
+    from superintervals_b200.device import (COUNT_CELLS, COUNT_WALK, OPT_CELLS_FILL, OPT_COUNT_ALGO, ORDER_ASIS,
+                                            DeviceIndex)
+    rng = np.random.default_rng(100 * CELL_CASES.index(case) + fill)
+    I32 = np.iinfo(np.int32)
+    n, nq = 40_000, 60_000
+    if case == "full_range":
+        s = rng.integers(I32.min, I32.max, n, dtype=np.int64)
+        e = np.minimum(s + rng.integers(0, 1 << 28, n), I32.max)
+        s[0], e[0] = I32.min, I32.min
+        s[1], e[1] = I32.max, I32.max
+        s[2], e[2] = I32.min, I32.max
+    elif case == "one_point":
+        s = np.full(n, 12345, np.int64); e = s.copy()
+    elif case == "clusters":
+        c = rng.integers(0, 20, n) * 1_000_000
+        s = c + rng.integers(0, 40, n); e = s + rng.integers(0, 300, n)
+    elif case == "dense":
+        s = rng.integers(0, 4_000, n, dtype=np.int64); e = s + rng.integers(0, 50, n)
+    elif case == "sparse":
+        s = rng.integers(-1_000_000_000, 1_000_000_000, 3_000, dtype=np.int64); e = s + rng.integers(0, 5_000_000, 3_000)
+    elif case == "single":
+        s = np.array([7], np.int64); e = np.array([9], np.int64)
+    else:
+        s = np.array([I32.min, I32.max - 5], np.int64); e = np.array([I32.min + 3, I32.max], np.int64)
+    s, e = s.astype(np.int32), e.astype(np.int32)
+    lo, hi = int(s.min()), int(e.max())
+    near = np.clip(rng.integers(lo - 300, hi + 300, nq - 8, dtype=np.int64), I32.min, I32.max)
+    pick = rng.integers(0, s.size, nq - 8)
+    mix = rng.random(nq - 8)
+    qs = np.where(mix < 0.5, near, np.where(mix < 0.75, s[pick], e[pick]).astype(np.int64) + rng.integers(-2, 3, nq - 8))
+    qs = np.clip(qs, I32.min, I32.max)
+    qe = np.clip(qs + rng.integers(0, 1 << int(rng.integers(1, 30)), nq - 8), I32.min, I32.max)
+    qs = np.concatenate([qs, [I32.min, I32.min, I32.max, I32.max, lo, hi, hi, I32.min]])
+    qe = np.concatenate([qe, [I32.min, I32.max, I32.max, I32.max, lo, hi, I32.max, lo]])
+    inv = rng.random(qs.size) < 0.02                       # a few inverted queries (quirk Q6) take the walk
+    qs, qe = np.where(inv, qe, qs).astype(np.int32), np.where(inv, qs, qe).astype(np.int32)
+
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    u32 = lambda t: t.cpu().numpy().astype(np.uint32).astype(np.uint64)
+    ix = DeviceIndex()
+    if fill:
+        ix.set_option(OPT_CELLS_FILL, fill)
+    ix.build(dev(s), dev(e))
+    info = ix.cells_info()
+    assert info["starts"]["format"] in (1, 2) and info["ends"]["format"] in (1, 2)
+    if case == "one_point":
+        assert info["starts"]["overfull"] >= 1
+    dqs, dqe = dev(qs), dev(qe)
+    got = u32(ix.set_option(OPT_COUNT_ALGO, COUNT_CELLS).count(dqs, dqe, order=ORDER_ASIS))
+    walk = u32(ix.set_option(OPT_COUNT_ALGO, COUNT_WALK).count(dqs, dqe, order=ORDER_ASIS))
+    assert np.array_equal(got, walk)
+    ok = qs <= qe
+    assert np.array_equal(got[ok], _brute_counts(s, e, qs[ok], qe[ok]))
+    want = Oracle(s, e).count_batch(qs, qe)
+    assert np.array_equal(got, want)
