@@ -282,10 +282,18 @@ def bench_search_values(a, torch, L, _lib, rank):
               and np.array_equal(v2, vals.cpu().numpy()))
     L.destroyIndexResult(C_.byref(found))
     L.destroySuperIntervals(si)
+    fill_ms = per.get("fill_runs", per.get("fill", 0.0))
+    compulsory = 24.0 * nq + 8.0 * total            # queries + the offset pair in, value read + value written per hit
+    peak, _ = measured_peak()
+    sv_roof = {"bound": "hbm", "kernel": "fill_runs" if "fill_runs" in per else "fill", "kernel_ms": fill_ms,
+               "compulsory_bytes_per_launch": compulsory,
+               "achieved": compulsory / (fill_ms * 1e-3) / 1e9 if fill_ms else None, "peak": peak, "unit": "GB/s",
+               "frac": (compulsory / (fill_ms * 1e-3) / 1e9 / peak) if fill_ms else None,
+               "stab_lists": ix.stab_info()}
     out = {"workload": f"C3: {n/1e6:g}M heavy-tailed nested intervals (Pareto 1.1, <=1Mb) x {nq/1e6:g}M queries, "
                        f"search_values CSR, shuffled queries", "value": nq / (ms * 1e-3), "unit": UNIT,
            "ms_per_step": ms, "hits": total, "hits_per_query": total / nq, "kernel_ms_per_step": per,
-           "result_gbs": (total * 4 + nq * 8) / (ms * 1e-3) / 1e9,
+           "result_gbs": (total * 4 + nq * 8) / (ms * 1e-3) / 1e9, "roofline": sv_roof,
            "e2e": {"value": nq / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": 8 * nq,
                    "d2h_bytes_per_step": 8 * (nq + 1) + 4 * total, "equals_device": ok,
                    "first_call_ms": first_s * 1e3,

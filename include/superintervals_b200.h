@@ -131,7 +131,9 @@ int siSortQueriesDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, s
 enum { SI_OPT_COUNT_ALGO = 0, SI_OPT_BUCKET_INTERVALS = 1, SI_OPT_WINDOW_SHIFT = 2, SI_OPT_TIMING = 3,
        SI_OPT_GRID_INTERVALS = 4, /* intervals per cell of the rank grid; applies to the next build */
        SI_OPT_CELLS_DIRECT_BYTES = 5, /* rank cells up to this many bytes answer batches unpartitioned (0 = 60 % of L2) */
-       SI_OPT_CELLS_FILL = 6 /* mean values per rank cell (1..28); applies to the next build */ };
+       SI_OPT_CELLS_FILL = 6, /* mean values per rank cell (1..28); applies to the next build */
+       SI_OPT_STAB_LISTS = 7, /* 1 (default): the CSR fill of a well-formed index reads its stab lists; 0: it walks the branch array */
+       SI_OPT_STAB_BUDGET = 8 /* stab-list entries per interval at most (default 6); deeper indexes double the checkpoint spacing, then walk */ };
 enum { SI_COUNT_AUTO = 0, SI_COUNT_WALK = 1, SI_COUNT_RANK = 2, SI_COUNT_CELLS = 3 };
 int siIndexSetOption(siIndex* ix, int option, long long value);
 /* The rank cells build() made (which = 0: over starts, 1: over ends). format 0 = none
@@ -144,12 +146,21 @@ typedef struct {
     int direct;
 } siCellsInfo;
 int siIndexCellsInfo(const siIndex* ix, int which, siCellsInfo* out);
+/* The stab lists of the CSR fill (made by the first siFillDevice after a build): state 0 = not
+ * made yet, 1 = in use, 2 = over budget or too small (the fill walks); a checkpoint every
+ * 2^shift positions, `lists` lists holding `entries` (position, end) pairs of 8 bytes. */
+typedef struct {
+    int state;
+    unsigned shift;
+    unsigned long long lists, entries;
+} siStabInfo;
+int siIndexStabInfo(const siIndex* ix, siStabInfo* out);
 /* With SI_OPT_TIMING = 1 every hot kernel launch is bracketed by a CUDA event pair on its
  * own stream. Returns the number of (tag, milliseconds) records written (oldest first) and
  * clears them; waits for the recorded work. Tags: 1 partition histogram + scan, 2 partition
- * pass, 3 count (walk), 4 count (rank), 5 CSR scan, 6 CSR fill, 7 count (cells). bench.py's roofline uses it. */
+ * pass, 3 count (walk), 4 count (rank), 5 CSR scan, 6 CSR fill (walk), 7 count (cells), 8 CSR fill (runs + stab lists). bench.py's roofline uses it. */
 enum { SI_TAG_PT_HIST = 1, SI_TAG_PT_PASS = 2, SI_TAG_COUNT_WALK = 3, SI_TAG_COUNT_RANK = 4, SI_TAG_SCAN = 5, SI_TAG_FILL = 6,
-       SI_TAG_COUNT_CELLS = 7 };
+       SI_TAG_COUNT_CELLS = 7, SI_TAG_FILL_RUNS = 8 };
 int siIndexReadTimings(siIndex* ix, int* tags, float* ms, int max_out);
 
 int siAnyDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n,

@@ -18,7 +18,8 @@ ORDER_AUTO, ORDER_SORTED, ORDER_UNSORTED, ORDER_ASIS = 0, 1, 2, 3
 FILL_VALUES, FILL_IDXS, FILL_KEYS, FILL_ITEMS = 0, 1, 2, 3
 OPT_COUNT_ALGO, OPT_BUCKET_INTERVALS, OPT_WINDOW_SHIFT, OPT_TIMING, OPT_GRID_INTERVALS = 0, 1, 2, 3, 4
 OPT_CELLS_DIRECT_BYTES, OPT_CELLS_FILL = 5, 6
-TAG_NAMES = {1: "pt_histogram", 2: "pt_onesweep", 3: "count_walk", 4: "count_rank", 5: "scan", 6: "fill", 7: "count_cells"}
+OPT_STAB_LISTS, OPT_STAB_BUDGET = 7, 8
+TAG_NAMES = {1: "pt_histogram", 2: "pt_onesweep", 3: "count_walk", 4: "count_rank", 5: "scan", 6: "fill", 7: "count_cells", 8: "fill_runs"}
 COUNT_AUTO, COUNT_WALK, COUNT_RANK, COUNT_CELLS = 0, 1, 2, 3
 
 
@@ -60,6 +61,10 @@ class siCellsInfo(C.Structure):
                 ("overfull", C.c_ulonglong), ("direct", C.c_int)]
 
 
+class siStabInfo(C.Structure):
+    _fields_ = [("state", C.c_int), ("shift", C.c_uint), ("lists", C.c_ulonglong), ("entries", C.c_ulonglong)]
+
+
 def build_library(verbose: bool = False) -> str:
     """nvcc-compile the CUDA library for sm_100a (cross-compiles without a GPU)."""
     cmd = ["make", "-C", os.path.join(HERE, "csrc")]
@@ -86,7 +91,7 @@ B200_SYMBOLS = [
     "countOverlapsBatch", "anyOverlapsBatch", "searchValuesBatch", "searchIdxsBatch", "searchKeysBatch",
     "searchItemsBatch", "coverageBatch", "siIndexCreate", "siIndexDestroy", "siIndexOf", "siIndexSize",
     "siIndexDeviceView", "siIndexBuildHost", "siIndexBuildDevice", "siIndexExport", "siCountDevice",
-    "siCountDevice64", "siSortQueriesDevice", "siIndexSetOption", "siIndexCellsInfo", "siIndexReadTimings", "siAnyDevice", "siScanDevice", "siFillDevice", "siCoverageDevice",
+    "siCountDevice64", "siSortQueriesDevice", "siIndexSetOption", "siIndexCellsInfo", "siIndexStabInfo", "siIndexReadTimings", "siAnyDevice", "siScanDevice", "siFillDevice", "siCoverageDevice",
     "siIndexDeviceBytes",
 ]
 
@@ -170,6 +175,8 @@ def bind_b200(L):
     L.siSortQueriesDevice.argtypes = [vp, vp, vp, sz, vp]
     L.siIndexCellsInfo.argtypes = [vp, C.c_int, C.POINTER(siCellsInfo)]
     L.siIndexCellsInfo.restype = C.c_int
+    L.siIndexStabInfo.argtypes = [vp, C.POINTER(siStabInfo)]
+    L.siIndexStabInfo.restype = C.c_int
     L.siIndexSetOption.argtypes = [vp, C.c_int, C.c_longlong]
     L.siIndexSetOption.restype = C.c_int
     L.siIndexReadTimings.argtypes = [vp, vp, vp, C.c_int]

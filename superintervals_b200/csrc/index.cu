@@ -121,13 +121,15 @@ using namespace sib;
     } while (0)
 
 size_t siIndex::device_bytes() const {
-    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &esort, &eall, &grid_tab, &cells_s, &cells_e, &b_in_s, &b_in_e, &b_in_v,
+    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &esort, &eall, &grid_tab, &cells_s, &cells_e, &stab_off, &stab_ent, &stab_cnt, &b_in_s, &b_in_e, &b_in_v,
                            &b_kA, &b_kB, &b_vA, &b_vB, &b_ws, &small, &q_A, &q_B,
                            &q_ws, &scan_status, &h_qs, &h_qe, &h_counts, &h_offsets, &h_out, &h_cov};
     size_t s = 0;
     for (auto* b : all) s += b->cap;
     return s;
 }
+
+extern "C" int siScanDevice(siIndex* ix, const uint32_t* d_counts, size_t n, uint64_t* d_offsets, void* stream);
 
 namespace {
 
@@ -160,6 +162,8 @@ IndexView view_of(const siIndex* ix) {
     v.grid.cells = ix->grid_cells;
     v.cells_s = RankCells{ix->cells_s.as<uint4>(), ix->cm_s.lo, ix->cm_s.span, ix->cm_s.shift, ix->cm_s.fmt};
     v.cells_e = RankCells{ix->cells_e.as<uint4>(), ix->cm_e.lo, ix->cm_e.span, ix->cm_e.shift, ix->cm_e.fmt};
+    const bool stab = ix->stab_state == 1 && ix->stab_enabled;
+    v.stab = StabLists{ix->stab_off.as<uint64_t>(), stab ? ix->stab_ent.as<int2>() : nullptr, ix->stab_kshift, ix->stab_nlists};
     v.n = ix->n;
     v.wellformed = ix->wellformed ? 1u : 0u;
     return v;
@@ -265,6 +269,8 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
     ix->built = false;
     ix->plan_valid = false;
     ix->cm_s.fmt = ix->cm_e.fmt = 0;
+    ix->stab_state = 0;
+    ix->stab_entries = 0;
     if (n > MAX_N) {
         set_error_msg(cudaErrorInvalidValue, "siIndexBuild: more than 2^32-16385 intervals");
         return cudaErrorInvalidValue;
@@ -402,6 +408,10 @@ bool cells_direct(const siIndex* ix) {
     return ((size_t)ix->cm_s.cells + ix->cm_e.cells + 2) * 32 <= limit;
 }
 
+// The CSR fill follows the count kernel: with rank cells it copies each query's certain run and
+// walks only below it (qk_fill_runs_kernel); otherwise the plain walk (qk_fill_kernel).
+bool fill_by_runs(const siIndex* ix) { return count_algo_of(ix) == SI_COUNT_CELLS; }
+
 // Partition a query batch for locality (partition.cuh): records grouped by (result window,
 // position bucket). *out describes the partitioned records; the partition of the same
 // (d_qs, d_qe, nq) may be reused by the fill that follows a count (documented contract).
@@ -502,9 +512,56 @@ int count_impl(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, 
     return 0;
 }
 
+// Stab lists for qk_fill_runs_kernel, made once per build by the first fill that can use them.
+// Checkpoint spacing: 32 positions, doubled (up to 1024) until the lists fit the budget of
+// stab_budget entries per interval; an index nested deeper than that keeps the walk.
+int ensure_stab_lists(siIndex* ix, cudaStream_t s) {
+    if (ix->stab_state != 0 || !ix->stab_enabled) return 0;
+    ix->stab_state = 2;
+    if (ix->n < 64) return 0;   // nothing to skip
+    const uint32_t n = ix->n;
+    const uint32_t nl0 = (n >> 5) + 1;
+    if (ix->stab_cnt.ensure(((size_t)nl0 + 4) * 4) || ensure_small(ix)) return last_error_code();
+    unsigned long long* d_tot = reinterpret_cast<unsigned long long*>(ix->small.as<uint32_t>() + 16);
+    SIB_CHECK(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long) * QK_STAB_SPACINGS, s));
+    const IndexView v = view_of(ix);
+    SIB_LAUNCH((qk_stab_lists_kernel<false>), (nl0 + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, 5u, nl0,
+               ix->stab_cnt.as<uint32_t>(), (const uint64_t*)nullptr, (int2*)nullptr);
+    SIB_LAUNCH(qk_stab_totals_kernel, grid_for(nl0, QK_THREADS, ix->sm_count * 8), QK_THREADS, 0, s,
+               ix->stab_cnt.as<uint32_t>(), nl0, d_tot);
+    unsigned long long tot[QK_STAB_SPACINGS];
+    SIB_CHECK(cudaMemcpyAsync(tot, d_tot, sizeof(tot), cudaMemcpyDeviceToHost, s));
+    SIB_CHECK(cudaStreamSynchronize(s));
+    const unsigned long long budget = (unsigned long long)ix->stab_budget * n;
+    int k = 0;
+    while (k < QK_STAB_SPACINGS && tot[k] > budget) ++k;
+    if (k == QK_STAB_SPACINGS) return 0;   // too deep: stay with the walk
+    const uint32_t kshift = 5u + (uint32_t)k;
+    const uint32_t nl = (n >> kshift) + 1;
+    if (k > 0)   // the kept checkpoints' counts, contiguous
+        SIB_LAUNCH((qk_stab_lists_kernel<false>), (nl + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, kshift, nl,
+                   ix->stab_cnt.as<uint32_t>(), (const uint64_t*)nullptr, (int2*)nullptr);
+    if (ix->stab_off.ensure(((size_t)nl + 1) * 8) || ix->stab_ent.ensure((size_t)(tot[k] ? tot[k] : 1) * 8)) return last_error_code();
+    int rc = siScanDevice(ix, ix->stab_cnt.as<uint32_t>(), nl, ix->stab_off.as<uint64_t>(), (void*)s);
+    if (rc) return rc;
+    SIB_LAUNCH((qk_stab_lists_kernel<true>), (nl + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, kshift, nl,
+               (uint32_t*)nullptr, ix->stab_off.as<uint64_t>(), ix->stab_ent.as<int2>());
+    ix->stab_kshift = kshift;
+    ix->stab_nlists = nl;
+    ix->stab_entries = tot[k];
+    ix->stab_state = 1;
+    return 0;
+}
+
 template <int MODE>
 int launch_fill(siIndex* ix, const QueryRecords& rec, uint32_t nq, const uint64_t* d_offsets, void* d_out,
                 cudaStream_t s) {
+    if (fill_by_runs(ix)) {
+        const int grid = (int)(((uint64_t)nq + QF_THREADS - 1) / QF_THREADS);
+        SIB_LAUNCH_T(ix, TAG_FILL_RUNS, (qk_fill_runs_kernel<MODE>), grid, QF_THREADS, 0, s, view_of(ix), rec, nq, d_offsets,
+                     reinterpret_cast<typename FillOut<MODE>::T*>(d_out));
+        return 0;
+    }
     const int grid = (int)(((uint64_t)nq + QK_THREADS - 1) / QK_THREADS);
     SIB_LAUNCH_T(ix, TAG_FILL, (qk_fill_kernel<MODE>), grid, QK_THREADS, 0, s, view_of(ix), rec, nq, d_offsets,
                reinterpret_cast<typename FillOut<MODE>::T*>(d_out));
@@ -553,7 +610,7 @@ void siIndexDestroy(siIndex* ix) {
     if (!ix) return;
     DeviceGuard g(ix->device);
     DevBuf* all[] = {&ix->starts, &ix->ends, &ix->values, &ix->branch, &ix->perm, &ix->tree, &ix->esort, &ix->eall, &ix->grid_tab,
-                     &ix->cells_s, &ix->cells_e,
+                     &ix->cells_s, &ix->cells_e, &ix->stab_off, &ix->stab_ent, &ix->stab_cnt,
                      &ix->b_in_s, &ix->b_in_e, &ix->b_in_v, &ix->b_kA, &ix->b_kB, &ix->b_vA, &ix->b_vB, &ix->b_ws,
                      &ix->small, &ix->q_A, &ix->q_B, &ix->q_ws, &ix->scan_status, &ix->h_qs,
                      &ix->h_qe, &ix->h_counts, &ix->h_offsets, &ix->h_out, &ix->h_cov};
@@ -583,6 +640,15 @@ int siIndexCellsInfo(const siIndex* ix, int which, siCellsInfo* out) {
     out->bytes = out->cells * 32;
     out->overfull = m.overfull;
     out->direct = cells_direct(ix) ? 1 : 0;
+    return 0;
+}
+
+int siIndexStabInfo(const siIndex* ix, siStabInfo* out) {
+    if (!ix || !out || !ix->built) return cudaErrorInvalidValue;
+    out->state = ix->stab_state;
+    out->shift = ix->stab_state == 1 ? ix->stab_kshift : 0;
+    out->lists = ix->stab_state == 1 ? ix->stab_nlists : 0;
+    out->entries = ix->stab_state == 1 ? ix->stab_entries : 0;
     return 0;
 }
 
@@ -707,6 +773,15 @@ int siIndexSetOption(siIndex* ix, int option, long long value) {
             ix->cells_fill8 = (uint32_t)value;
             ix->cells_fill16 = (uint32_t)(value + 1) / 2 > 14 ? 14 : (uint32_t)(value + 1) / 2;
             return 0;
+        case SI_OPT_STAB_LISTS:            // 0: the fill walks the branch array below each run; 1 (default): stab lists
+            if (value < 0 || value > 1) break;
+            ix->stab_enabled = value != 0;
+            return 0;
+        case SI_OPT_STAB_BUDGET:           // list entries per interval at most; applies to lists not built yet
+            if (value < 0 || value > 4096) break;
+            ix->stab_budget = (uint32_t)value;
+            if (ix->stab_state == 2) ix->stab_state = 0;
+            return 0;
         case SI_OPT_WINDOW_SHIFT:
             if (value < 10 || value > 31) break;
             ix->window_shift = (uint32_t)value;
@@ -772,10 +847,15 @@ int siFillDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n
         set_error_msg(cudaErrorInvalidValue, "siFillDevice: unknown fill mode");
         return cudaErrorInvalidValue;
     }
+    if (fill_by_runs(ix)) {
+        int rc = ensure_stab_lists(ix, s);
+        if (rc) return rc;
+    }
     for (size_t at = 0; at < n; at += PT_MAX_BATCH) {
         const uint32_t m = (uint32_t)(n - at < PT_MAX_BATCH ? n - at : PT_MAX_BATCH);
         QueryRecords rec{d_qs + at, d_qe + at, nullptr};
-        if (order == SI_ORDER_UNSORTED) {
+        // rank cells that stay in L2 need no locality: the batch is filled in the caller's order
+        if (order == SI_ORDER_UNSORTED && !(fill_by_runs(ix) && cells_direct(ix))) {
             int rc = partition_queries(ix, d_qs + at, d_qe + at, m, s, &rec, n <= PT_MAX_BATCH);
             if (rc) return rc;
         }

@@ -21,7 +21,7 @@ unsigned long long launches();
 
 // Optional per-launch device timing (siIndexSetOption SI_OPT_TIMING): a CUDA event pair on the
 // launching stream around each hot kernel, read back by siIndexReadTimings. Off by default.
-enum LaunchTag : int { TAG_PT_HIST = 1, TAG_PT_PASS = 2, TAG_COUNT_WALK = 3, TAG_COUNT_RANK = 4, TAG_SCAN = 5, TAG_FILL = 6, TAG_COUNT_CELLS = 7 };
+enum LaunchTag : int { TAG_PT_HIST = 1, TAG_PT_PASS = 2, TAG_COUNT_WALK = 3, TAG_COUNT_RANK = 4, TAG_SCAN = 5, TAG_FILL = 6, TAG_COUNT_CELLS = 7, TAG_FILL_RUNS = 8 };
 struct LaunchTimer {
     bool on = false;
     cudaEvent_t* ev = nullptr;   // 2 * cap events
@@ -59,6 +59,13 @@ struct siIndex {
     uint32_t cells_fill8 = 16, cells_fill16 = 7;   // target mean values per cell (28 / 14 slots)
     size_t cells_direct_bytes = 0;                 // cells up to this size answer unpartitioned batches (0: 60 % of L2)
     size_t l2_bytes = 0;
+    // stab lists (StabLists in query_kernels.cuh), made by the first CSR fill that can use them
+    sib::DevBuf stab_off, stab_ent, stab_cnt;
+    uint32_t stab_kshift = 0, stab_nlists = 0;
+    int stab_state = 0;                            // 0 = not tried yet, 1 = built, 2 = over budget (the fill walks)
+    unsigned long long stab_entries = 0;
+    bool stab_enabled = true;                      // SI_OPT_STAB_LISTS
+    uint32_t stab_budget = 6;                      // SI_OPT_STAB_BUDGET: list entries per interval at most
     sib::DevBuf tree;          // 32-ary max tree levels + prefix-max levels
     const int32_t* pmax32 = nullptr;   // inside `tree`: exclusive prefix max of ends per 32-block
 

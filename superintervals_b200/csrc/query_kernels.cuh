@@ -53,6 +53,21 @@ struct RankCells {
     uint32_t fmt;       // 0 = not built
 };
 
+// Stab lists (built on the first CSR fill of a well-formed index): a checkpoint every 2^kshift
+// positions; list b holds every interval below position b << kshift that is still open just after
+// the start at position (b << kshift) - 1,
+//     L(b) = { j < b << kshift : ends[j] > starts[(b << kshift) - 1] },   L(0) empty,
+// as (position, end) pairs in descending position. Any query whose candidates end at
+// top = #{starts < qs} with top >> kshift == b has qs > starts[(b << kshift) - 1], so its hits
+// below the checkpoint are exactly the entries of L(b) with end >= qs: one sequential list read
+// instead of the branch-array walk's chain of dependent loads.
+struct StabLists {
+    const uint64_t* off;   // nlists + 1 offsets into ent
+    const int2* ent;       // (position, end); nullptr = not built (too deep, or not asked for yet)
+    uint32_t kshift;
+    uint32_t nlists;       // (n >> kshift) + 1
+};
+
 struct IndexView {
     const int32_t* starts;
     const int32_t* ends;     // padded to a multiple of 128 entries (pad = INT_MIN)
@@ -64,6 +79,7 @@ struct IndexView {
     RankGrid grid;           // rank tables for qk_count_rank_kernel; only on a well-formed index
     RankCells cells_s;       // rank cells over starts  } qk_count_cells_kernel; only on a well-formed
     RankCells cells_e;       // rank cells over eall    } index of fewer than 2^31 intervals
+    StabLists stab;          // qk_fill_runs_kernel's lists; ent == nullptr -> it walks instead
     uint32_t n;
     uint32_t wellformed;     // 1 when every stored interval has start <= end (checked by build())
 };
@@ -659,6 +675,253 @@ qk_fill_kernel(IndexView ix, QueryRecords rec, uint32_t nq, const uint64_t* __re
             bo += __popc(hm);
             if (bi < 32u) break;                     // the block reached interval 0
             const uint32_t low = bi - 31u;           // lowest interval of the block (lane 31)
+            bi = (hm >> 31) ? low - 1u : ld_nc(ix.branch + low);
+        }
+    }
+}
+
+// ---- stab lists: one branch-array walk per checkpoint, at build time ------------------------
+// FILL = false counts |L(b)|, FILL = true writes the entries at off[b]. The walk is the
+// reference's (hpp:551-579) with the threshold x = starts[(b << kshift) - 1] + 1, started at the
+// checkpoint's last position; a miss jumps to the smallest branch target over the block's misses.
+template <bool FILL>
+__global__ void __launch_bounds__(QK_THREADS)
+qk_stab_lists_kernel(IndexView ix, uint32_t kshift, uint32_t nlists, uint32_t* __restrict__ counts,
+                     const uint64_t* __restrict__ off, int2* __restrict__ ent) {
+    const uint64_t t64 = (uint64_t)blockIdx.x * QK_THREADS + threadIdx.x;
+    if (t64 >= nlists) return;
+    const uint32_t b = (uint32_t)t64;
+    uint32_t c = 0;
+    uint64_t o = FILL ? off[b] : 0;
+    if (b > 0) {
+        uint32_t i = (b << kshift) - 1u;
+        const int32_t sv = ld_nc(ix.starts + i);
+        if (sv != INT_MAX) {                 // nothing ends beyond INT_MAX
+            const int32_t x = sv + 1;
+            while (i != NONE32) {
+                const uint32_t base = i & ~3u;
+                const int4 e = ld_nc4(ix.ends + base);
+                const uint32_t k = i - base;
+                const bool hx = e.x >= x, hy = k >= 1u && e.y >= x, hz = k >= 2u && e.z >= x, hw = k >= 3u && e.w >= x;
+                if (FILL) {
+                    if (hw) ent[o++] = make_int2((int)(base + 3u), e.w);
+                    if (hz) ent[o++] = make_int2((int)(base + 2u), e.z);
+                    if (hy) ent[o++] = make_int2((int)(base + 1u), e.y);
+                    if (hx) ent[o++] = make_int2((int)base, e.x);
+                } else {
+                    c += (hx ? 1u : 0u) + (hy ? 1u : 0u) + (hz ? 1u : 0u) + (hw ? 1u : 0u);
+                }
+                if (hx) { i = base - 1u; continue; }
+                const uint4 br = __ldg(reinterpret_cast<const uint4*>(ix.branch + base));
+                uint32_t key = jump_key(br.x);
+                if (k >= 1u && !hy) key = min(key, jump_key(br.y));
+                if (k >= 2u && !hz) key = min(key, jump_key(br.z));
+                if (k >= 3u && !hw) key = min(key, jump_key(br.w));
+                i = key - 1u;
+            }
+        }
+    }
+    if (!FILL) counts[b] = c;
+}
+
+// totals[k] = sum of counts[b] over the checkpoints a spacing of 2^(kshift0 + k) keeps (b % 2^k == 0)
+constexpr int QK_STAB_SPACINGS = 6;
+__global__ void __launch_bounds__(QK_THREADS)
+qk_stab_totals_kernel(const uint32_t* __restrict__ counts, uint32_t nlists, unsigned long long* __restrict__ totals) {
+    unsigned long long acc[QK_STAB_SPACINGS];
+#pragma unroll
+    for (int k = 0; k < QK_STAB_SPACINGS; ++k) acc[k] = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * QK_THREADS;
+    for (uint64_t b = (uint64_t)blockIdx.x * QK_THREADS + threadIdx.x; b < nlists; b += stride) {
+        const uint32_t c = counts[b];
+#pragma unroll
+        for (int k = 0; k < QK_STAB_SPACINGS; ++k)
+            if ((b & ((1u << k) - 1u)) == 0) acc[k] += c;
+    }
+#pragma unroll
+    for (int k = 0; k < QK_STAB_SPACINGS; ++k) {
+        unsigned long long v = acc[k];
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL_MASK, v, d);
+        if (lane_id() == 0 && v) atomicAdd(totals + k, v);
+    }
+}
+
+// ---- fill by run + stab (well-formed index with rank cells) --------------------------------
+// On an index whose intervals all have start <= end, the walk's hit list
+//     { j <= ub(qe) : ends[j] >= qs }   in descending j
+// splits at  top = #{ starts < qs }  (clamped to ub(qe) + 1):
+//   run   j in [top, ub(qe)]: start >= qs, so end >= start >= qs -- EVERY one is a hit (the run the
+//         reference's search_values_large locates by search, hpp:588-615). No ends are tested:
+//         the list's head is a reversed copy of values[top .. ub(qe)].
+//   stab  j < top with ends[j] >= qs: the intervals that begin before the query and reach into
+//         it. With stab lists (StabLists above): the ends of the partial checkpoint block
+//         [top & ~(2^kshift - 1), top) are tested with 128-bit loads, then the checkpoint's list is
+//         read front to back and filtered by end >= qs -- independent loads, no pointer chase.
+//         Without them (an index nested too deeply for the lists' memory budget): the
+//         reference's own branch-array walk from top - 1. Either way it stops as soon as the CSR
+//         slot is full (the offsets say how many hits exist).
+// Both ranks come from the rank cells over starts (one sector each, no binary search), so the
+// batch needs no locality and is filled in the caller's order, unpartitioned.
+// The runs of a warp's 32 queries are pooled and copied by all lanes together (lane k of the
+// pool finds its query by a 5-step search over the warp's prefix sums in shared memory): the
+// copy is load-balanced whatever the distribution of run lengths. Runs longer than
+// QF_LONG_RUN are streamed by the whole warp, one query at a time. Inverted queries
+// (qs > qe, quirk Q6) get top = ub(qe) + 1: empty run, plain walk.
+constexpr int QF_THREADS = 256;
+constexpr int QF_WARPS = QF_THREADS / 32;
+constexpr uint32_t QF_LONG_RUN = 1024;
+
+// one element of a run: position j is a hit for certain, only the payload is read
+template <int MODE>
+__device__ __forceinline__ void emit_run(const IndexView& ix, typename FillOut<MODE>::T* __restrict__ out,
+                                         uint64_t pos, uint32_t j) {
+    if (MODE == FILL_VALUES) {
+        __stcs(reinterpret_cast<int32_t*>(out) + pos, ld_nc(ix.values + j));
+    } else if (MODE == FILL_IDXS) {
+        __stcs(reinterpret_cast<uint32_t*>(out) + pos, j);
+    } else {
+        emit<MODE>(ix, out, pos, j, ld_nc(ix.ends + j));
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(QF_THREADS)
+qk_fill_runs_kernel(IndexView ix, QueryRecords rec, uint32_t nq, const uint64_t* __restrict__ offsets,
+                    typename FillOut<MODE>::T* __restrict__ out) {
+    __shared__ uint32_t s_pre[QF_WARPS][32];   // inclusive prefix sums of the warp's pooled run lengths
+    __shared__ uint32_t s_top[QF_WARPS][32];   // highest position of each run (= ub(qe))
+    __shared__ uint64_t s_out[QF_WARPS][32];   // where each run's first element goes
+    const uint64_t t64 = (uint64_t)blockIdx.x * QF_THREADS + threadIdx.x;
+    const bool live = t64 < nq;
+    const uint32_t t = (uint32_t)t64;
+    const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
+
+    uint32_t q = t;
+    int32_t qs = 0, qe = 0;
+    uint64_t o = 0, o_end = 0;
+    if (live) {
+        qs = ld_stream(rec.qs + t);
+        qe = ld_stream(rec.qe + t);
+        if (rec.idx) q = ld_stream(rec.idx + t);
+        o = ld_stream(offsets + q);
+        o_end = ld_stream(offsets + q + 1);
+    }
+    const bool any_hits = live && o_end > o;
+    uint32_t lim = 0, top = 0;   // lim = #{starts <= qe}, top = min(#{starts < qs}, lim)
+    if (any_hits) {
+        uint32_t c1, f1, c2, f2;
+        cell_of(ix.cells_s, (int64_t)qe + 1, c1, f1);
+        cell_of(ix.cells_s, (int64_t)qs, c2, f2);
+        const CellRec r1 = ld_cell(ix.cells_s.rec + 2 * (size_t)c1);   // both sectors in flight
+        const CellRec r2 = ld_cell(ix.cells_s.rec + 2 * (size_t)c2);
+        lim = cell_rank(ix.cells_s, ix.starts, r1, c1, f1, (int64_t)qe + 1);
+        top = min(cell_rank(ix.cells_s, ix.starts, r2, c2, f2, (int64_t)qs), lim);
+    }
+    const uint32_t run = lim - top;
+
+    // ---- run: long ones by the whole warp, one query at a time
+    uint32_t longm = __ballot_sync(FULL_MASK, run > QF_LONG_RUN);
+    while (longm) {
+        const int src = __ffs(longm) - 1;
+        longm &= longm - 1;
+        const uint32_t blen = __shfl_sync(FULL_MASK, run, src);
+        const uint32_t bhi = __shfl_sync(FULL_MASK, lim, src) - 1u;
+        const uint64_t bo = __shfl_sync(FULL_MASK, o, src);
+#pragma unroll 4
+        for (uint32_t k = lane; k < blen; k += 32u) emit_run<MODE>(ix, out, bo + k, bhi - k);
+    }
+    // ---- run: the rest pooled over the warp
+    const uint32_t pooled = run > QF_LONG_RUN ? 0u : run;
+    uint32_t incl = pooled;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t x = __shfl_up_sync(FULL_MASK, incl, d);
+        if ((int)lane >= d) incl += x;
+    }
+    const uint32_t total = __shfl_sync(FULL_MASK, incl, 31);
+    if (total) {
+        s_pre[w][lane] = incl;
+        s_top[w][lane] = lim - 1u;
+        s_out[w][lane] = o;
+        __syncwarp();
+        for (uint32_t k = lane; k < total; k += 32u) {
+            uint32_t own = 0;                       // number of queries whose pooled runs end at or before k
+#pragma unroll
+            for (uint32_t step = 16; step; step >>= 1) own += (s_pre[w][own + step - 1u] <= k) ? step : 0u;
+            const uint32_t within = k - (own ? s_pre[w][own - 1u] : 0u);
+            emit_run<MODE>(ix, out, s_out[w][own] + within, s_top[w][own] - within);
+        }
+        __syncwarp();
+    }
+    o += run;
+
+    // ---- stab: below top, until the slot is full
+    const bool more = any_hits && o < o_end;
+    if (ix.stab.ent) {
+        if (more && top) {
+            const uint32_t cb = (top >> ix.stab.kshift) << ix.stab.kshift;   // checkpoint at or below top
+            const uint64_t* lp = ix.stab.off + (top >> ix.stab.kshift);
+            const uint64_t l0 = __ldg(lp), l1 = __ldg(lp + 1);               // requested before the block scan
+            if (top > cb) {
+                uint32_t base = (top - 1u) & ~3u;
+                uint32_t k = (top - 1u) - base;
+                while (true) {
+                    const int4 e = ld_nc4(ix.ends + base);
+                    if (k >= 3u && e.w >= qs) emit<MODE>(ix, out, o++, base + 3u, e.w);
+                    if (k >= 2u && e.z >= qs) emit<MODE>(ix, out, o++, base + 2u, e.z);
+                    if (k >= 1u && e.y >= qs) emit<MODE>(ix, out, o++, base + 1u, e.y);
+                    if (e.x >= qs) emit<MODE>(ix, out, o++, base, e.x);
+                    if (base == cb || o == o_end) break;
+                    base -= 4u;
+                    k = 3u;
+                }
+            }
+            for (uint64_t p = l0; p < l1 && o < o_end; p += 4) {
+                int2 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = (p + u < l1) ? __ldg(ix.stab.ent + p + u) : make_int2(0, INT_MIN);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (p + u < l1 && v[u].y >= qs) emit<MODE>(ix, out, o++, (uint32_t)v[u].x, v[u].y);
+            }
+        }
+        return;
+    }
+    uint32_t i = (more && top) ? top - 1u : NONE32;
+    const bool small = more && (o_end - o) <= QK_FILL_LANE_MAX;
+    if (small) {
+        while (i != NONE32) {
+            const uint32_t base = i & ~3u;
+            const int4 e = ld_nc4(ix.ends + base);
+            const uint32_t br = ld_nc(ix.branch + base);   // requested with the ends: a miss does not wait twice
+            const uint32_t k = i - base;
+            if (k >= 3u && e.w >= qs) emit<MODE>(ix, out, o++, base + 3u, e.w);
+            if (k >= 2u && e.z >= qs) emit<MODE>(ix, out, o++, base + 2u, e.z);
+            if (k >= 1u && e.y >= qs) emit<MODE>(ix, out, o++, base + 1u, e.y);
+            if (e.x >= qs) emit<MODE>(ix, out, o++, base, e.x);
+            if (o == o_end) break;
+            i = (e.x >= qs) ? base - 1u : br;
+        }
+        i = NONE32;
+    }
+    uint32_t pending = __ballot_sync(FULL_MASK, more && !small);
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        uint32_t bi = __shfl_sync(FULL_MASK, i, src);
+        const int32_t bqs = __shfl_sync(FULL_MASK, qs, src);
+        uint64_t bo = __shfl_sync(FULL_MASK, o, src);
+        const uint64_t bo_end = __shfl_sync(FULL_MASK, o_end, src);
+        while (bi != NONE32 && bo < bo_end) {
+            const bool inb = lane <= bi;
+            const uint32_t j = bi - lane;
+            const int32_t e = inb ? ld_nc(ix.ends + j) : INT_MIN;
+            const bool hit = inb && e >= bqs;
+            const uint32_t hm = __ballot_sync(FULL_MASK, hit);
+            if (hit) emit<MODE>(ix, out, bo + __popc(hm & lanemask_lt()), j, e);
+            bo += __popc(hm);
+            if (bi < 32u) break;
+            const uint32_t low = bi - 31u;
             bi = (hm >> 31) ? low - 1u : ld_nc(ix.branch + low);
         }
     }

@@ -13,12 +13,12 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (COUNT_AUTO, COUNT_CELLS, COUNT_RANK, COUNT_WALK, OPT_CELLS_DIRECT_BYTES, OPT_CELLS_FILL, FILL_IDXS, FILL_ITEMS, FILL_KEYS, FILL_VALUES, OPT_BUCKET_INTERVALS,
+from ._lib import (OPT_STAB_BUDGET, OPT_STAB_LISTS, COUNT_AUTO, COUNT_CELLS, COUNT_RANK, COUNT_WALK, OPT_CELLS_DIRECT_BYTES, OPT_CELLS_FILL, FILL_IDXS, FILL_ITEMS, FILL_KEYS, FILL_VALUES, OPT_BUCKET_INTERVALS,
                    OPT_COUNT_ALGO, OPT_TIMING, OPT_WINDOW_SHIFT, ORDER_ASIS, ORDER_AUTO, ORDER_SORTED, ORDER_UNSORTED)
 
 __all__ = ["DeviceIndex", "ORDER_AUTO", "ORDER_SORTED", "ORDER_UNSORTED", "ORDER_ASIS", "OPT_COUNT_ALGO",
            "OPT_BUCKET_INTERVALS", "OPT_WINDOW_SHIFT", "OPT_TIMING", "COUNT_AUTO", "COUNT_WALK", "COUNT_RANK", "COUNT_CELLS",
-           "OPT_CELLS_DIRECT_BYTES", "OPT_CELLS_FILL"]
+           "OPT_CELLS_DIRECT_BYTES", "OPT_CELLS_FILL", "OPT_STAB_LISTS", "OPT_STAB_BUDGET"]
 
 
 def _stream():
@@ -134,6 +134,14 @@ class DeviceIndex:
             out[name] = {"format": int(ci.format), "shift": int(ci.shift), "cells": int(ci.cells), "bytes": int(ci.bytes),
                          "overfull": int(ci.overfull), "direct": bool(ci.direct)}
         return out
+
+    def stab_info(self):
+        """Stab lists of the CSR fill (siIndexStabInfo): state 0 not made yet / 1 in use / 2 the fill walks."""
+        si = _lib.siStabInfo()
+        if self._L.siIndexStabInfo(self._ix, C.byref(si)):
+            raise RuntimeError("siIndexStabInfo: index not built")
+        return {"state": int(si.state), "shift": int(si.shift), "lists": int(si.lists), "entries": int(si.entries),
+                "bytes": int(si.entries) * 8 + (int(si.lists) + 1) * 8 if si.state == 1 else 0}
 
     def read_timings(self, max_records=4096):
         """[(kernel name, ms), ...] recorded since the last read (needs set_option(OPT_TIMING, 1))."""

@@ -198,5 +198,68 @@ def test_rank_cells_edge_cases(case, fill):
     assert np.array_equal(got, walk)
     ok = qs <= qe
     assert np.array_equal(got[ok], _brute_counts(s, e, qs[ok], qe[ok]))
-    want = Oracle(s, e).count_batch(qs, qe)
+    orc = Oracle(s, e)
+    want = orc.count_batch(qs, qe)
     assert np.array_equal(got, want)
+    # CSR fill by run + stab (qk_fill_runs_kernel) on the same edges, every payload, against the oracle and
+    # against the plain walk fill; a prefix of the batch whose lists stay small enough to compare
+    from superintervals_b200.device import FILL_IDXS, FILL_ITEMS, FILL_KEYS, FILL_VALUES
+    m = max(1, int(np.searchsorted(np.cumsum(want), 3_000_000)))
+    off_o, res = orc.search_batch(qs[:m], qe[:m], want=("values", "idxs", "keys"))
+    pqs, pqe = dev(qs[:m]), dev(qe[:m])
+    from superintervals_b200.device import OPT_STAB_BUDGET, OPT_STAB_LISTS
+    for what, key in ((FILL_VALUES, "values"), (FILL_IDXS, "idxs"), (FILL_KEYS, "keys"), (FILL_ITEMS, None)):
+        off_w, lst_w = ix.set_option(OPT_COUNT_ALGO, COUNT_WALK).search(pqs, pqe, what, order=ORDER_ASIS)
+        ix.set_option(OPT_COUNT_ALGO, COUNT_CELLS)
+        # below each run: the stab lists, the branch-array walk, and lists at a coarser checkpoint spacing
+        for lists, budget in ((1, 6), (0, 6), (1, 1)):
+            ix.set_option(OPT_STAB_LISTS, lists).set_option(OPT_STAB_BUDGET, budget)
+            off, lst = ix.search(pqs, pqe, what, order=ORDER_ASIS)
+            assert np.array_equal(off.cpu().numpy().astype(np.uint64), off_o), (case, what, lists, budget)
+            assert torch.equal(off, off_w) and torch.equal(lst, lst_w), (case, what, lists, budget)
+        if key:
+            assert np.array_equal(lst_w.cpu().numpy().astype(res[key].dtype).reshape(res[key].shape), res[key]), (case, key)
+    ix.set_option(OPT_STAB_LISTS, 1).set_option(OPT_STAB_BUDGET, 6)
+
+
+@pytest.mark.parametrize("shape,budget,want_state,min_shift", [("c2", 6, 1, 5), ("c2", 1, 1, 6), ("c3", 6, 1, 5),
+                                                               ("deep", 6, 2, 0), ("deep", 4096, 1, 5), ("tiny", 6, 2, 0)])
+def test_stab_lists_budget_and_fallback(shape, budget, want_state, min_shift):
+    """The stab lists behind the CSR fill: built on the first fill, checkpoint spacing doubled until the
+    lists fit the budget, an index nested too deeply (or too small) keeps the branch-array walk; every
+    variant returns the oracle's lists, and a rebuild drops the old lists."""
+    import torch
+    from superintervals_b200.device import (FILL_KEYS, OPT_STAB_BUDGET, ORDER_ASIS, DeviceIndex)
+    rng = np.random.default_rng(5)
+    if shape == "c2":
+        s, e, qs, qe = W.config2(60_000, 40_000, 3, axis=1_500_000)          # ~100 open intervals at every point
+    elif shape == "c3":
+        s, e, qs, qe = W.config3(80_000, 40_000, 9, axis=5_000_000)
+    elif shape == "deep":                                                    # every interval contains the next: depth = n
+        n = 40_000
+        s = np.arange(n, dtype=np.int32); e = (2 * n - s).astype(np.int32)
+        qs = rng.integers(-5, 2 * n + 5, 300).astype(np.int32); qe = (qs + rng.integers(0, 50, 300)).astype(np.int32)
+    else:
+        s = np.arange(40, dtype=np.int32); e = (s + 3).astype(np.int32)
+        qs = rng.integers(-2, 50, 500).astype(np.int32); qe = (qs + rng.integers(0, 9, 500)).astype(np.int32)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    ix = DeviceIndex().set_option(OPT_STAB_BUDGET, budget).build(dev(s), dev(e))
+    assert ix.stab_info()["state"] == 0
+    o = Oracle(s, e)
+    off_o, res = o.search_batch(qs, qe, want=("values", "keys"))
+    off, vals = ix.search_values(dev(qs), dev(qe), order=ORDER_ASIS)
+    info = ix.stab_info()
+    assert info["state"] == want_state, info
+    if want_state == 1:
+        assert info["shift"] >= min_shift and info["entries"] <= budget * s.size and info["lists"] == (s.size >> info["shift"]) + 1
+    assert np.array_equal(off.cpu().numpy().astype(np.uint64), off_o)
+    assert np.array_equal(vals.cpu().numpy(), res["values"])
+    _, keys = ix.search(dev(qs), dev(qe), FILL_KEYS, order=ORDER_ASIS)
+    assert np.array_equal(keys.cpu().numpy(), res["keys"])
+    # a rebuild forgets the lists; the next fill makes them for the new index
+    s2, e2 = (s[: s.size // 2] + 7).astype(np.int32), (e[: s.size // 2] + 9).astype(np.int32)
+    ix.build(dev(s2), dev(e2))
+    assert ix.stab_info()["state"] == 0
+    off2, vals2 = ix.search_values(dev(qs), dev(qe), order=ORDER_ASIS)
+    off_o2, res2 = Oracle(s2, e2).search_batch(qs, qe)
+    assert np.array_equal(off2.cpu().numpy().astype(np.uint64), off_o2) and np.array_equal(vals2.cpu().numpy(), res2["values"])
