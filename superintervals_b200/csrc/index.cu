@@ -513,19 +513,19 @@ int count_impl(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, 
 }
 
 // Stab lists for qk_fill_runs_kernel, made once per build by the first fill that can use them.
-// Checkpoint spacing: 32 positions, doubled (up to 1024) until the lists fit the budget of
+// Checkpoint spacing: 8 positions, doubled (up to 1024) until the lists fit the budget of
 // stab_budget entries per interval; an index nested deeper than that keeps the walk.
 int ensure_stab_lists(siIndex* ix, cudaStream_t s) {
     if (ix->stab_state != 0 || !ix->stab_enabled) return 0;
     ix->stab_state = 2;
     if (ix->n < 64) return 0;   // nothing to skip
     const uint32_t n = ix->n;
-    const uint32_t nl0 = (n >> 5) + 1;
+    const uint32_t nl0 = (n >> QK_STAB_SHIFT0) + 1;
     if (ix->stab_cnt.ensure(((size_t)nl0 + 4) * 4) || ensure_small(ix)) return last_error_code();
     unsigned long long* d_tot = reinterpret_cast<unsigned long long*>(ix->small.as<uint32_t>() + 16);
     SIB_CHECK(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long) * QK_STAB_SPACINGS, s));
     const IndexView v = view_of(ix);
-    SIB_LAUNCH((qk_stab_lists_kernel<false>), (nl0 + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, 5u, nl0,
+    SIB_LAUNCH((qk_stab_lists_kernel<false>), (nl0 + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, QK_STAB_SHIFT0, nl0,
                ix->stab_cnt.as<uint32_t>(), (const uint64_t*)nullptr, (int2*)nullptr);
     SIB_LAUNCH(qk_stab_totals_kernel, grid_for(nl0, QK_THREADS, ix->sm_count * 8), QK_THREADS, 0, s,
                ix->stab_cnt.as<uint32_t>(), nl0, d_tot);
@@ -536,7 +536,7 @@ int ensure_stab_lists(siIndex* ix, cudaStream_t s) {
     int k = 0;
     while (k < QK_STAB_SPACINGS && tot[k] > budget) ++k;
     if (k == QK_STAB_SPACINGS) return 0;   // too deep: stay with the walk
-    const uint32_t kshift = 5u + (uint32_t)k;
+    const uint32_t kshift = QK_STAB_SHIFT0 + (uint32_t)k;
     const uint32_t nl = (n >> kshift) + 1;
     if (k > 0)   // the kept checkpoints' counts, contiguous
         SIB_LAUNCH((qk_stab_lists_kernel<false>), (nl + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, kshift, nl,

@@ -724,8 +724,9 @@ qk_stab_lists_kernel(IndexView ix, uint32_t kshift, uint32_t nlists, uint32_t* _
     if (!FILL) counts[b] = c;
 }
 
-// totals[k] = sum of counts[b] over the checkpoints a spacing of 2^(kshift0 + k) keeps (b % 2^k == 0)
-constexpr int QK_STAB_SPACINGS = 6;
+// totals[k] = sum of counts[b] over the checkpoints a spacing of 2^(QK_STAB_SHIFT0 + k) keeps (b % 2^k == 0)
+constexpr uint32_t QK_STAB_SHIFT0 = 3;   // finest checkpoint spacing: 8 positions (two 128-bit loads of ends at most)
+constexpr int QK_STAB_SPACINGS = 8;      // coarsest: 1024
 __global__ void __launch_bounds__(QK_THREADS)
 qk_stab_totals_kernel(const uint32_t* __restrict__ counts, uint32_t nlists, unsigned long long* __restrict__ totals) {
     unsigned long long acc[QK_STAB_SPACINGS];

@@ -222,8 +222,8 @@ def test_rank_cells_edge_cases(case, fill):
     ix.set_option(OPT_STAB_LISTS, 1).set_option(OPT_STAB_BUDGET, 6)
 
 
-@pytest.mark.parametrize("shape,budget,want_state,min_shift", [("c2", 6, 1, 5), ("c2", 1, 1, 6), ("c3", 6, 1, 5),
-                                                               ("deep", 6, 2, 0), ("deep", 4096, 1, 5), ("tiny", 6, 2, 0)])
+@pytest.mark.parametrize("shape,budget,want_state,min_shift", [("c2", 6, 1, 4), ("c2", 1, 1, 6), ("c3", 6, 1, 3),
+                                                               ("deep", 6, 2, 0), ("deep", 4096, 1, 3), ("tiny", 6, 2, 0)])
 def test_stab_lists_budget_and_fallback(shape, budget, want_state, min_shift):
     """The stab lists behind the CSR fill: built on the first fill, checkpoint spacing doubled until the
     lists fit the budget, an index nested too deeply (or too small) keeps the branch-array walk; every
