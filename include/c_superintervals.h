@@ -93,6 +93,26 @@ void   searchPoint(cSuperIntervals* si, int32_t point, cIndexResult* found);
 void   coverage(cSuperIntervals* si, int32_t start, int32_t end, size_t* count_out, int32_t* coverage_out);
 void   findOverlaps(cSuperIntervals* si, int32_t start, int32_t end, int32_t* found, size_t* found_size);
 
+/* set operations -- ref:243-324 (definitions ref:823-1064). Each returns a NEW, NOT-yet-indexed
+ * set (owning pointer; free with destroySuperIntervals) in the reference's emission order.
+ * Intervals are end-inclusive; merging coalesces overlapping intervals only ([1,5],[6,10] stay
+ * apart). `combine` resolves the data when intervals fold together (NULL keeps the first/left).
+ * intersection / difference / symmetricDifference query `other` through its index: it must be
+ * indexed (symmetricDifference: both). Here: device sort + head flags + scan + scatter
+ * (merge / unique / gaps), A's stored intervals as one query batch against B's index
+ * (intersection / difference), elementwise count + scan + scatter (expand / flank). */
+typedef int32_t (*cCombineFn)(int32_t, int32_t);                                           /* ref:128 */
+cSuperIntervals* mergeOverlaps(const cSuperIntervals* si, cCombineFn combine);            /* ref:264 */
+cSuperIntervals* intervalGaps(const cSuperIntervals* si, int32_t lo, int32_t hi, int32_t fill);   /* ref:271 */
+cSuperIntervals* unionWith(const cSuperIntervals* si, const cSuperIntervals* other, cCombineFn combine);   /* ref:278 */
+cSuperIntervals* intersection(const cSuperIntervals* si, cSuperIntervals* other, cCombineFn combine);      /* ref:286 */
+cSuperIntervals* difference(const cSuperIntervals* si, cSuperIntervals* other);           /* ref:292 */
+cSuperIntervals* symmetricDifference(cSuperIntervals* si, cSuperIntervals* other);        /* ref:298 */
+bool intervalSpan(const cSuperIntervals* si, int32_t* lo_out, int32_t* hi_out);           /* ref:305 */
+cSuperIntervals* expandIntervals(const cSuperIntervals* si, int32_t left, int32_t right, int32_t lo, int32_t hi);   /* ref:314 */
+cSuperIntervals* flankIntervals(const cSuperIntervals* si, int32_t left, int32_t right, int32_t lo, int32_t hi);    /* ref:324 */
+cSuperIntervals* uniqueIntervals(const cSuperIntervals* si, cCombineFn combine);          /* ref:332 */
+
 /* result buffers -- ref:339-357 */
 cIndexResult createIndexResult(void);
 void clearIndexResult(cIndexResult* r);

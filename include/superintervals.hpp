@@ -14,8 +14,10 @@
 // Differences from the reference, all outside the accelerated path:
 //   * S must be a 32-bit integer type (the reference's AVX2 path has the same
 //     restriction, hpp:688; its C ABI is int32 only).
-//   * IntervalMapEytz, the set algebra (hpp:1037-1390) and the lazy iterator classes
-//     are not provided; search_idxs(s,e)/search_items(s,e) return eager ranges.
+//   * IntervalMapEytz and the lazy iterator classes are not provided;
+//     search_idxs(s,e)/search_items(s,e) return eager ranges.
+//   * The set algebra (hpp:1037-1390) is provided on top of the C ABI's device set
+//     operations; `other` arguments must have been built.
 //   * New: count_batch / search_values_batch / search_idxs_batch / search_keys_batch
 //     (CSR), the throughput path.
 #pragma once
@@ -23,6 +25,7 @@
 #include <algorithm>
 #include <cstddef>
 #include <cstdint>
+#include <limits>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -231,7 +234,182 @@ class IntervalMap {
 
     cSuperIntervals* handle() const { return h_; }   // for the device-resident API: siIndexOf(handle())
 
+    // ---- set algebra (hpp:1037-1390) ---------------------------------------------------------
+    // Each returns a NEW map that is NOT indexed (call build() before querying it), like the
+    // reference. The geometry -- the sort, the coalescing sweep, the batch of overlap queries
+    // against `other` -- runs on the device through the C ABI's set operations
+    // (c_superintervals.h "set operations"); payloads of type T are carried or folded on the
+    // host in the reference's visiting order (hpp:1363-1390: stored order when both
+    // sortedness flags hold, else (start, end) ascending).
+    template <typename Combine>
+    IntervalMap merge_overlaps(Combine combine) const {   // hpp:1057-1087
+        IntervalMap out;
+        if (starts.empty()) return out;
+        CHandle t;
+        to_handle(t, false);
+        CHandle m{mergeOverlaps(t.h, nullptr)};
+        const std::vector<size_t> order = visiting_order();
+        size_t c = 0;
+        bool open = false;
+        T acc{};
+        for (size_t idx : order) {
+            while (open && c < m.h->size && starts[idx] > (S)m.h->ends[c]) {   // past the open cluster: flush
+                out.add((S)m.h->starts[c], (S)m.h->ends[c], acc);
+                ++c;
+                open = false;
+            }
+            if (!open) { acc = data[idx]; open = true; }
+            else acc = combine(acc, data[idx]);
+        }
+        if (open && c < m.h->size) out.add((S)m.h->starts[c], (S)m.h->ends[c], acc);
+        return out;
+    }
+    IntervalMap merge_overlaps() const {
+        return merge_overlaps([](const T& a, const T&) { return a; });
+    }
+
+    IntervalMap gaps(S lo, S hi, const T& fill = T{}) const {   // hpp:1104-1127
+        IntervalMap out;
+        CHandle t;
+        to_handle(t, false);
+        CHandle g{intervalGaps(t.h, (int32_t)lo, (int32_t)hi, 0)};
+        for (size_t i = 0; i < g.h->size; ++i) out.add((S)g.h->starts[i], (S)g.h->ends[i], fill);
+        return out;
+    }
+
+    template <typename Combine>
+    IntervalMap union_with(const IntervalMap& other, Combine combine) const {   // hpp:1137-1147
+        IntervalMap combined;
+        combined.reserve(starts.size() + other.starts.size());
+        for (size_t k = 0; k < starts.size(); ++k) combined.add(starts[k], ends[k], data[k]);
+        for (size_t k = 0; k < other.starts.size(); ++k) combined.add(other.starts[k], other.ends[k], other.data[k]);
+        return combined.merge_overlaps(combine);
+    }
+    IntervalMap union_with(const IntervalMap& other) const {
+        return union_with(other, [](const T& a, const T&) { return a; });
+    }
+
+    // `other` must be built (it is queried through its index). Pieces are not coalesced.
+    template <typename Combine>
+    IntervalMap intersection(const IntervalMap& other, Combine combine) const {   // hpp:1164-1179
+        IntervalMap out;
+        if (starts.empty() || other.starts.empty()) return out;
+        CHandle a, b;
+        to_handle(a, false);
+        other.to_handle(b, true);
+        cIndexResult bd = createIndexResult();
+        CHandle r{intersectionPairs(a.h, b.h, &bd)};
+        for (size_t i = 0; i < r.h->size && i < bd.size; ++i)
+            out.add((S)r.h->starts[i], (S)r.h->ends[i], combine(data[(size_t)r.h->data[i]], other.data[(size_t)bd.data[i]]));
+        destroyIndexResult(&bd);
+        return out;
+    }
+    IntervalMap intersection(const IntervalMap& other) const {
+        return intersection(other, [](const T& a, const T&) { return a; });
+    }
+
+    IntervalMap difference(const IntervalMap& other) const {   // hpp:1189-1211
+        IntervalMap out;
+        if (starts.empty()) return out;
+        CHandle a, b;
+        to_handle(a, false);
+        other.to_handle(b, true);
+        CHandle r{::difference(a.h, b.h)};
+        for (size_t i = 0; i < r.h->size; ++i) out.add((S)r.h->starts[i], (S)r.h->ends[i], data[(size_t)r.h->data[i]]);
+        return out;
+    }
+
+    IntervalMap symmetric_difference(const IntervalMap& other) const {   // hpp:1219-1223
+        IntervalMap a_minus_b = difference(other);
+        IntervalMap b_minus_a = other.difference(*this);
+        return a_minus_b.union_with(b_minus_a);
+    }
+
+    bool span(std::pair<S, S>& result) const {   // hpp:1230-1243
+        if (starts.empty()) return false;
+        CHandle t;
+        to_handle(t, false);
+        int32_t lo = 0, hi = 0;
+        if (!intervalSpan(t.h, &lo, &hi)) return false;
+        result = {(S)lo, (S)hi};
+        return true;
+    }
+
+    IntervalMap expand(S left, S right, S lo = std::numeric_limits<S>::min(),
+                       S hi = std::numeric_limits<S>::max()) const {   // hpp:1258-1290
+        return resized(left, right, lo, hi, false);
+    }
+    IntervalMap flank(S left, S right, S lo = std::numeric_limits<S>::min(),
+                      S hi = std::numeric_limits<S>::max()) const {   // hpp:1305-1330
+        return resized(left, right, lo, hi, true);
+    }
+
+    template <typename Combine>
+    IntervalMap unique(Combine combine) const {   // hpp:1341-1360
+        IntervalMap out;
+        if (starts.empty()) return out;
+        CHandle t;
+        to_handle(t, false);
+        CHandle u{uniqueIntervals(t.h, nullptr)};   // how many distinct pairs: the fold below must agree
+        const std::vector<size_t> order = visiting_order();
+        size_t run = order[0];
+        T acc = data[run];
+        for (size_t k = 1; k < order.size(); ++k) {
+            const size_t idx = order[k];
+            if (starts[idx] == starts[run] && ends[idx] == ends[run]) acc = combine(acc, data[idx]);
+            else { out.add(starts[run], ends[run], acc); run = idx; acc = data[idx]; }
+        }
+        out.add(starts[run], ends[run], acc);
+        if (out.starts.size() != u.h->size) out.clear();   // device and host disagree: report nothing rather than guess
+        return out;
+    }
+    IntervalMap unique() const {
+        return unique([](const T& a, const T&) { return a; });
+    }
+
    private:
+    struct CHandle {   // owning wrapper of a C handle
+        cSuperIntervals* h = nullptr;
+        CHandle() = default;
+        explicit CHandle(cSuperIntervals* p) : h(p) {}
+        ~CHandle() { destroySuperIntervals(h); }
+        CHandle(const CHandle&) = delete;
+        CHandle& operator=(const CHandle&) = delete;
+    };
+    // the stored intervals as a C handle whose payload is the position in starts/ends/data
+    void to_handle(CHandle& c, bool index) const {
+        c.h = createSuperIntervals();
+        if (!starts.empty())
+            addIntervals(c.h, reinterpret_cast<const int32_t*>(starts.data()), reinterpret_cast<const int32_t*>(ends.data()),
+                         nullptr, starts.size());
+        if (index) indexSuperIntervals(c.h);
+    }
+    IntervalMap resized(S left, S right, S lo, S hi, bool flanks) const {
+        IntervalMap out;
+        if (starts.empty()) return out;
+        CHandle t;
+        to_handle(t, false);
+        CHandle r{flanks ? flankIntervals(t.h, (int32_t)left, (int32_t)right, (int32_t)lo, (int32_t)hi)
+                         : expandIntervals(t.h, (int32_t)left, (int32_t)right, (int32_t)lo, (int32_t)hi)};
+        for (size_t i = 0; i < r.h->size; ++i) out.add((S)r.h->starts[i], (S)r.h->ends[i], data[(size_t)r.h->data[i]]);
+        return out;
+    }
+    // hpp:1363-1390: stored order when add()/build() left both flags set, else (start, end) ascending
+    std::vector<size_t> visiting_order() const {
+        std::vector<size_t> order(starts.size());
+        for (size_t k = 0; k < order.size(); ++k) order[k] = k;
+        bool sorted = start_sorted && end_sorted;
+        if (!sorted) {
+            sorted = true;
+            for (size_t k = 1; k < starts.size() && sorted; ++k)
+                sorted = !(starts[k] < starts[k - 1] || (starts[k] == starts[k - 1] && ends[k] < ends[k - 1]));
+        }
+        if (!sorted)
+            std::sort(order.begin(), order.end(), [this](size_t x, size_t y) {
+                return starts[x] < starts[y] || (starts[x] == starts[y] && ends[x] < ends[y]);
+            });
+        return order;
+    }
     bool ready() const { return h_ != nullptr && !starts.empty() && siIndexOf(h_) != nullptr; }
     cSuperIntervals* h_;
     mutable cIndexResult scratch_ = {nullptr, 0, 0};

@@ -69,6 +69,11 @@ void searchItemsBatch(cSuperIntervals* si, const int32_t* starts, const int32_t*
 /* coverage (c_superintervals.h:758-792) per query. */
 void coverageBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n,
                    size_t* count_out, int32_t* coverage_out);
+/* intersection() (c_superintervals.h:286) without a callback: the pieces carry `si`'s data, and
+ * the `other` side's data of every piece is appended to other_data in the same order, so a
+ * host-language binding can pair or combine payloads itself (intervalmap.pyx:577-609 pairs
+ * them into tuples). */
+cSuperIntervals* intersectionPairs(const cSuperIntervals* si, cSuperIntervals* other, cIndexResult* other_data);
 
 /* ---- 3. device-resident core ------------------------------------------------------- */
 typedef struct siIndex siIndex;

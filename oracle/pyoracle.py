@@ -33,11 +33,12 @@ def build_oracle(force: bool = False) -> str:
     """Compile oracle/si_oracle.c (gcc) if the .so is missing or stale."""
     so = os.path.join(HERE, "libsi_oracle.so")
     src = os.path.join(HERE, "si_oracle.c")
+    src2 = os.path.join(HERE, "si_oracle_setops.c")
     hdr = os.path.join(HERE, "si_oracle.h")
     stale = (not os.path.exists(so)) or any(
-        os.path.getmtime(p) > os.path.getmtime(so) for p in (src, hdr))
+        os.path.getmtime(p) > os.path.getmtime(so) for p in (src, src2, hdr))
     if force or stale:
-        subprocess.check_call(["gcc", "-O2", "-std=c99", "-fPIC", "-shared", src, "-o", so])
+        subprocess.check_call(["gcc", "-O2", "-std=c99", "-fPIC", "-shared", src, src2, "-o", so])
     return so
 
 
@@ -334,3 +335,207 @@ class Reference:
     def time_build(self, starts, ends):
         s, e = _i32(starts), _i32(ends)
         return float(self.lib().si_ref_time_build(self._h, s, e, s.size))
+
+
+# ---------------------------------------------------------------------------------------
+# set algebra (oracle/si_oracle_setops.c) and the compiled reference C header beside it
+# ---------------------------------------------------------------------------------------
+class _SetStruct(C.Structure):
+    _fields_ = [("starts", C.POINTER(C.c_int32)), ("ends", C.POINTER(C.c_int32)), ("data", C.POINTER(C.c_int32)),
+                ("n", C.c_size_t), ("cap", C.c_size_t)]
+
+
+COMBINE_T = C.CFUNCTYPE(C.c_int32, C.c_int32, C.c_int32)
+COMBINERS = {None: None,
+             "sum": COMBINE_T(lambda a, b: C.c_int32(a + b).value),
+             "max": COMBINE_T(lambda a, b: max(a, b)),
+             "second": COMBINE_T(lambda a, b: b)}
+SETOPS = ("merge", "gaps", "union", "intersection", "difference", "symmetric_difference", "span", "expand", "flank", "unique")
+
+
+def _triple(s, e, d=None):
+    s, e = _i32(s), _i32(e)
+    d = np.arange(s.size, dtype=np.int32) if d is None else _i32(d)
+    return s, e, d
+
+
+class OracleSetOps:
+    """The set-algebra restatement over plain arrays. Every method returns (starts, ends, data) int32
+    arrays in the reference's emission order (span: (lo, hi) or None)."""
+
+    _bound = False
+
+    @classmethod
+    def lib(cls):
+        L = Oracle.lib()
+        if not cls._bound:
+            P, ip, sz, i32, vp = C.POINTER(_SetStruct), _i32p, C.c_size_t, C.c_int32, C.c_void_p
+            IX = C.POINTER(_IndexStruct)
+            L.si_oracle_set_free.argtypes = [P]
+            for name, args in (("merge", [ip, ip, ip, sz, vp]), ("gaps", [ip, ip, ip, sz, i32, i32, i32]),
+                               ("union", [ip, ip, ip, sz, ip, ip, ip, sz, vp]), ("intersection", [ip, ip, ip, sz, IX, vp]),
+                               ("difference", [ip, ip, ip, sz, IX]), ("symmetric_difference", [IX, IX]),
+                               ("expand", [ip, ip, ip, sz, i32, i32, i32, i32]), ("flank", [ip, ip, ip, sz, i32, i32, i32, i32]),
+                               ("unique", [ip, ip, ip, sz, vp])):
+                f = getattr(L, "si_oracle_" + name)
+                f.restype, f.argtypes = P, args
+            L.si_oracle_span.restype = C.c_int
+            L.si_oracle_span.argtypes = [ip, ip, sz, C.POINTER(i32), C.POINTER(i32)]
+            cls._bound = True
+        return L
+
+    @classmethod
+    def _take(cls, p):
+        n = int(p.contents.n)
+        out = tuple(np.ctypeslib.as_array(getattr(p.contents, f), shape=(n,)).copy() if n else np.zeros(0, np.int32)
+                    for f in ("starts", "ends", "data"))
+        cls.lib().si_oracle_set_free(p)
+        return out
+
+    @staticmethod
+    def _fn(combine):
+        f = COMBINERS[combine]
+        return None if f is None else C.cast(f, C.c_void_p)
+
+    @classmethod
+    def merge(cls, s, e, d=None, combine=None):
+        s, e, d = _triple(s, e, d)
+        return cls._take(cls.lib().si_oracle_merge(s, e, d, s.size, cls._fn(combine)))
+
+    @classmethod
+    def gaps(cls, s, e, d, lo, hi, fill):
+        s, e, d = _triple(s, e, d)
+        return cls._take(cls.lib().si_oracle_gaps(s, e, d, s.size, lo, hi, fill))
+
+    @classmethod
+    def union(cls, a, b, combine=None):
+        a, b = _triple(*a), _triple(*b)
+        return cls._take(cls.lib().si_oracle_union(a[0], a[1], a[2], a[0].size, b[0], b[1], b[2], b[0].size, cls._fn(combine)))
+
+    @classmethod
+    def intersection(cls, a, b, combine=None):
+        """a: stored order arrays; b: arrays of the OTHER set, indexed here (payload = its data)."""
+        a, b = _triple(*a), _triple(*b)
+        o = Oracle(b[0], b[1], b[2])
+        return cls._take(cls.lib().si_oracle_intersection(a[0], a[1], a[2], a[0].size, o._ix, cls._fn(combine)))
+
+    @classmethod
+    def difference(cls, a, b):
+        a, b = _triple(*a), _triple(*b)
+        o = Oracle(b[0], b[1], b[2])
+        return cls._take(cls.lib().si_oracle_difference(a[0], a[1], a[2], a[0].size, o._ix))
+
+    @classmethod
+    def symmetric_difference(cls, a, b):
+        a, b = _triple(*a), _triple(*b)
+        oa, ob = Oracle(a[0], a[1], a[2]), Oracle(b[0], b[1], b[2])
+        return cls._take(cls.lib().si_oracle_symmetric_difference(oa._ix, ob._ix))
+
+    @classmethod
+    def span(cls, s, e):
+        s, e = _i32(s), _i32(e)
+        lo, hi = C.c_int32(0), C.c_int32(0)
+        return (lo.value, hi.value) if cls.lib().si_oracle_span(s, e, s.size, C.byref(lo), C.byref(hi)) else None
+
+    @classmethod
+    def expand(cls, s, e, d, left, right, lo, hi):
+        s, e, d = _triple(s, e, d)
+        return cls._take(cls.lib().si_oracle_expand(s, e, d, s.size, left, right, lo, hi))
+
+    @classmethod
+    def flank(cls, s, e, d, left, right, lo, hi):
+        s, e, d = _triple(s, e, d)
+        return cls._take(cls.lib().si_oracle_flank(s, e, d, s.size, left, right, lo, hi))
+
+    @classmethod
+    def unique(cls, s, e, d=None, combine=None):
+        s, e, d = _triple(s, e, d)
+        return cls._take(cls.lib().si_oracle_unique(s, e, d, s.size, cls._fn(combine)))
+
+
+class CSetOps:
+    """The same operations through a library exporting the reference's C ABI: the compiled reference
+    header (oracle/_ref/libsi_cref.so, `CSetOps.reference()`) or libsuperintervals_b200.so
+    (`CSetOps(lib)`). Sets are created with addInterval x n in stored order; `other` sets are indexed."""
+
+    CREF = os.path.join(HERE, "_ref", "libsi_cref.so")
+
+    class _SI(C.Structure):
+        _fields_ = [("starts", C.POINTER(C.c_int32)), ("ends", C.POINTER(C.c_int32)), ("data", C.POINTER(C.c_int32)),
+                    ("branch", C.POINTER(C.c_size_t)), ("size", C.c_size_t), ("capacity", C.c_size_t), ("idx", C.c_size_t),
+                    ("startSorted", C.c_bool), ("endSorted", C.c_bool)]
+
+    @classmethod
+    def reference_available(cls):
+        return os.path.exists(cls.CREF)
+
+    @classmethod
+    def reference(cls):
+        return cls(C.CDLL(cls.CREF))
+
+    def __init__(self, L):
+        # a library already bound elsewhere (superintervals_b200._lib.bind) keeps its handle type
+        rt = L.createSuperIntervals.restype
+        SI = rt if isinstance(rt, type) and issubclass(rt, C._Pointer) else C.POINTER(self._SI)
+        self.SI = SI
+        i32, vp = C.c_int32, C.c_void_p
+        self.L = L
+        L.createSuperIntervals.restype = SI
+        L.destroySuperIntervals.argtypes = [SI]
+        L.addInterval.argtypes = [SI, i32, i32, i32]
+        L.indexSuperIntervals.argtypes = [SI]
+        for name, args in (("mergeOverlaps", [SI, vp]), ("intervalGaps", [SI, i32, i32, i32]), ("unionWith", [SI, SI, vp]),
+                           ("intersection", [SI, SI, vp]), ("difference", [SI, SI]), ("symmetricDifference", [SI, SI]),
+                           ("expandIntervals", [SI, i32, i32, i32, i32]), ("flankIntervals", [SI, i32, i32, i32, i32]),
+                           ("uniqueIntervals", [SI, vp])):
+            f = getattr(L, name)
+            f.restype, f.argtypes = SI, args
+        L.intervalSpan.restype = C.c_bool
+        L.intervalSpan.argtypes = [SI, C.POINTER(i32), C.POINTER(i32)]
+
+    def make(self, s, e, d=None, index=False):
+        s, e, d = _triple(s, e, d)
+        si = self.L.createSuperIntervals()
+        if hasattr(self.L, "addIntervals"):
+            self.L.addIntervals.argtypes = [self.SI, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+            self.L.addIntervals(si, s.ctypes.data, e.ctypes.data, d.ctypes.data, s.size)
+        else:
+            for k in range(s.size):
+                self.L.addInterval(si, int(s[k]), int(e[k]), int(d[k]))
+        if index:
+            self.L.indexSuperIntervals(si)
+        return si
+
+    def take(self, si, flags=False):
+        n = int(si.contents.size)
+        out = tuple(np.ctypeslib.as_array(getattr(si.contents, f), shape=(n,)).copy() if n else np.zeros(0, np.int32)
+                    for f in ("starts", "ends", "data"))
+        if flags:
+            out = out + ((bool(si.contents.startSorted), bool(si.contents.endSorted)),)
+        self.L.destroySuperIntervals(si)
+        return out
+
+    @staticmethod
+    def _fn(combine):
+        f = COMBINERS[combine]
+        return None if f is None else C.cast(f, C.c_void_p)
+
+    def run(self, op, a, b=None, combine=None, args=(), index_a=False, flags=False):
+        """op in SETOPS; a, b = (starts, ends[, data]) in stored order; returns arrays (span: (lo, hi) or None)."""
+        A = self.make(*a, index=index_a or op == "symmetric_difference")
+        B = self.make(*b, index=op in ("intersection", "difference", "symmetric_difference")) if b is not None else None
+        L = self.L
+        try:
+            if op == "span":
+                lo, hi = C.c_int32(0), C.c_int32(0)
+                return (lo.value, hi.value) if L.intervalSpan(A, C.byref(lo), C.byref(hi)) else None
+            r = {"merge": lambda: L.mergeOverlaps(A, self._fn(combine)), "gaps": lambda: L.intervalGaps(A, *args),
+                 "union": lambda: L.unionWith(A, B, self._fn(combine)), "intersection": lambda: L.intersection(A, B, self._fn(combine)),
+                 "difference": lambda: L.difference(A, B), "symmetric_difference": lambda: L.symmetricDifference(A, B),
+                 "expand": lambda: L.expandIntervals(A, *args), "flank": lambda: L.flankIntervals(A, *args),
+                 "unique": lambda: L.uniqueIntervals(A, self._fn(combine))}[op]()
+            return self.take(r, flags)
+        finally:
+            L.destroySuperIntervals(A)
+            if B is not None:
+                L.destroySuperIntervals(B)

@@ -84,12 +84,14 @@ C_ABI_SYMBOLS = [
     "searchKeys", "searchItems", "searchPoint", "coverage", "findOverlaps", "createIndexResult",
     "clearIndexResult", "destroyIndexResult", "createKeyResult", "clearKeyResult", "destroyKeyResult",
     "createItemResult", "clearItemResult", "destroyItemResult",
+    "mergeOverlaps", "intervalGaps", "unionWith", "intersection", "difference", "symmetricDifference",
+    "intervalSpan", "expandIntervals", "flankIntervals", "uniqueIntervals",
 ]
 B200_SYMBOLS = [
     "si_b200_last_error", "si_b200_last_error_string", "si_b200_clear_error", "si_b200_version",
     "si_b200_device_count", "si_b200_kernel_launches", "addIntervals", "siSetHostMirror",
     "countOverlapsBatch", "anyOverlapsBatch", "searchValuesBatch", "searchIdxsBatch", "searchKeysBatch",
-    "searchItemsBatch", "coverageBatch", "siIndexCreate", "siIndexDestroy", "siIndexOf", "siIndexSize",
+    "searchItemsBatch", "coverageBatch", "intersectionPairs", "siIndexCreate", "siIndexDestroy", "siIndexOf", "siIndexSize",
     "siIndexDeviceView", "siIndexBuildHost", "siIndexBuildDevice", "siIndexExport", "siCountDevice",
     "siCountDevice64", "siSortQueriesDevice", "siIndexSetOption", "siIndexCellsInfo", "siIndexStabInfo", "siIndexReadTimings", "siAnyDevice", "siScanDevice", "siFillDevice", "siCoverageDevice",
     "siIndexDeviceBytes",
@@ -131,6 +133,17 @@ def bind(L):
     L.searchPoint.argtypes = [SI, i32, C.POINTER(cIndexResult)]
     L.coverage.argtypes = [SI, i32, i32, C.POINTER(sz), C.POINTER(i32)]
     L.findOverlaps.argtypes = [SI, i32, i32, C.POINTER(i32), C.POINTER(sz)]
+    # set operations (c_superintervals.h:243-334): new un-indexed handles
+    for name, args in (("mergeOverlaps", [SI, vp]), ("intervalGaps", [SI, i32, i32, i32]), ("unionWith", [SI, SI, vp]),
+                       ("intersection", [SI, SI, vp]), ("difference", [SI, SI]), ("symmetricDifference", [SI, SI]),
+                       ("expandIntervals", [SI, i32, i32, i32, i32]), ("flankIntervals", [SI, i32, i32, i32, i32]),
+                       ("uniqueIntervals", [SI, vp])):
+        if hasattr(L, name):
+            getattr(L, name).restype = SI
+            getattr(L, name).argtypes = args
+    if hasattr(L, "intervalSpan"):
+        L.intervalSpan.restype = C.c_bool
+        L.intervalSpan.argtypes = [SI, C.POINTER(i32), C.POINTER(i32)]
     L.createIndexResult.restype = cIndexResult
     L.createKeyResult.restype = cKeyResult
     L.createItemResult.restype = cItemResult
@@ -175,6 +188,9 @@ def bind_b200(L):
     L.siSortQueriesDevice.argtypes = [vp, vp, vp, sz, vp]
     L.siIndexCellsInfo.argtypes = [vp, C.c_int, C.POINTER(siCellsInfo)]
     L.siIndexCellsInfo.restype = C.c_int
+    if hasattr(L, "intersectionPairs"):
+        L.intersectionPairs.restype = SI
+        L.intersectionPairs.argtypes = [SI, SI, C.POINTER(cIndexResult)]
     L.siIndexStabInfo.argtypes = [vp, C.POINTER(siStabInfo)]
     L.siIndexStabInfo.restype = C.c_int
     L.siIndexSetOption.argtypes = [vp, C.c_int, C.c_longlong]

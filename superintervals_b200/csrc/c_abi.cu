@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "index.cuh"
+#include "host_common.cuh"
 
 #include <condition_variable>
 #include <cstdio>
@@ -23,38 +24,14 @@
 extern "C" int si_b200_upper_bound_(siIndex* ix, int32_t value, size_t* out);
 extern "C" int si_b200_resolve_order_(siIndex* ix, const int32_t* d_qs, size_t n, void* stream);
 
-namespace {
+namespace sib {
 
-constexpr uint64_t HANDLE_MAGIC = 0x53495F4232303021ull;   // "SI_B200!"
-
-struct Handle {
-    cSuperIntervals pub;   // must stay first: &handle->pub is what callers hold
-    uint64_t magic;
-    siIndex* ix;
-    bool mirror;
-    bool indexed;
-};
-
-inline Handle* H(cSuperIntervals* si) { return reinterpret_cast<Handle*>(si); }
-
-bool ready(Handle* h, const char* who) {
+bool handle_ready(Handle* h, const char* who) {
     if (h && h->magic == HANDLE_MAGIC && h->indexed && h->ix) return true;
     char msg[160];
     snprintf(msg, sizeof(msg), "%s: handle not indexed (call indexSuperIntervals first)", who);
-    sib::set_error_msg(cudaErrorNotReady, msg);
+    set_error_msg(cudaErrorNotReady, msg);
     return false;
-}
-
-template <typename R>
-bool grow(R* r, size_t need_total, size_t elem) {
-    if (need_total <= r->capacity) return true;
-    size_t cap = r->capacity ? r->capacity : 16;   // reference growth: x2 from 16 (c.h:585-588)
-    while (cap < need_total) cap *= 2;
-    void* p = realloc(r->data, cap * elem);
-    if (!p) { sib::set_error_msg(cudaErrorMemoryAllocation, "realloc of result buffer failed"); return false; }
-    r->data = reinterpret_cast<decltype(r->data)>(p);
-    r->capacity = cap;
-    return true;
 }
 
 // ---- host side of the copies -------------------------------------------------------------
@@ -160,7 +137,7 @@ int copy_d2h(siIndex* ix, void* dst, const void* src_dev, size_t bytes, cudaStre
         SIB_CHECK(cudaStreamSynchronize(s));
         return 0;
     }
-    if (ensure_stage(ix)) return sib::last_error_code();
+    if (ensure_stage(ix)) return last_error_code();
     char* stage[2] = {(char*)ix->pinned, (char*)ix->pinned + STAGE_BYTES};
     const size_t chunks = (bytes + STAGE_BYTES - 1) / STAGE_BYTES;
     auto len = [&](size_t k) { return k + 1 < chunks ? STAGE_BYTES : bytes - k * STAGE_BYTES; };
@@ -186,7 +163,7 @@ int copy_h2d(siIndex* ix, void* dst_dev, const void* src, size_t bytes, cudaStre
         if (bytes > DIRECT_BYTES) return 0;       // pinned: truly asynchronous, the caller synchronises before returning
         return 0;                                  // small pageable: the runtime stages it before returning
     }
-    if (ensure_stage(ix)) return sib::last_error_code();
+    if (ensure_stage(ix)) return last_error_code();
     char* stage[2] = {(char*)ix->pinned, (char*)ix->pinned + STAGE_BYTES};
     const size_t chunks = (bytes + STAGE_BYTES - 1) / STAGE_BYTES;
     for (size_t k = 0; k < chunks; ++k) {
@@ -204,7 +181,7 @@ int copy_h2d(siIndex* ix, void* dst_dev, const void* src, size_t bytes, cudaStre
 
 // upload a query batch into the index's staging buffers
 int stage_queries(siIndex* ix, const int32_t* qs, const int32_t* qe, size_t n) {
-    if (ix->h_qs.ensure(n * 4) || ix->h_qe.ensure(n * 4)) return sib::last_error_code();
+    if (ix->h_qs.ensure(n * 4) || ix->h_qe.ensure(n * 4)) return last_error_code();
     int rc = copy_h2d(ix, ix->h_qs.p, qs, n * 4, ix->own_stream);
     if (rc) return rc;
     return copy_h2d(ix, ix->h_qe.p, qe, n * 4, ix->own_stream);
@@ -218,12 +195,12 @@ int search_batch(Handle* h, const int32_t* qs, const int32_t* qe, size_t n, size
     if (n == 0) { if (offsets_out) offsets_out[0] = 0; return 0; }
     int rc = stage_queries(ix, qs, qe, n);
     if (rc) return rc;
-    if (ix->h_counts.ensure(n * 4 + 64) || ix->h_offsets.ensure((n + 1) * 8 + 64)) return sib::last_error_code();
+    if (ix->h_counts.ensure(n * 4 + 64) || ix->h_offsets.ensure((n + 1) * 8 + 64)) return last_error_code();
     const int32_t* dqs = ix->h_qs.as<int32_t>();
     const int32_t* dqe = ix->h_qe.as<int32_t>();
     // resolve the query order once so that count and fill agree and share one sort
     const int order = si_b200_resolve_order_(ix, dqs, n, ix->own_stream);
-    if (order < 0) return sib::last_error_code();
+    if (order < 0) return last_error_code();
     rc = siCountDevice(ix, dqs, dqe, n, ix->h_counts.as<uint32_t>(), order, ix->own_stream);
     if (rc) return rc;
     rc = siScanDevice(ix, ix->h_counts.as<uint32_t>(), n, ix->h_offsets.as<uint64_t>(), ix->own_stream);
@@ -234,7 +211,7 @@ int search_batch(Handle* h, const int32_t* qs, const int32_t* qe, size_t n, size
     SIB_CHECK(cudaStreamSynchronize(ix->own_stream));
     if (total) {
         if (!grow(found, found->size + total, elem)) return cudaErrorMemoryAllocation;
-        if (ix->h_out.ensure(total * elem)) return sib::last_error_code();
+        if (ix->h_out.ensure(total * elem)) return last_error_code();
         // the fill runs while the offsets travel
         rc = siFillDevice(ix, dqs, dqe, n, ix->h_offsets.as<uint64_t>(), what, ix->h_out.p, order, ix->own_stream);
         if (rc) return rc;
@@ -255,7 +232,9 @@ int search_batch(Handle* h, const int32_t* qs, const int32_t* qe, size_t n, size
     return 0;
 }
 
-}  // namespace
+}  // namespace sib
+
+using namespace sib;
 
 extern "C" {
 
@@ -346,7 +325,7 @@ static int build_from_handle(Handle* h) {
     cSuperIntervals* si = &h->pub;
     if (!h->ix) {
         h->ix = siIndexCreate();
-        if (!h->ix) return sib::last_error_code();
+        if (!h->ix) return last_error_code();
     }
     return siIndexBuildHost(h->ix, si->starts, si->ends, si->data, si->size);
 }
@@ -368,7 +347,7 @@ void indexSuperIntervals(cSuperIntervals* si) {
     if (build_from_handle(h)) return;
     if (h->mirror) {
         size_t* b = (size_t*)realloc(si->branch, si->size * sizeof(size_t));
-        if (!b) { sib::set_error_msg(cudaErrorMemoryAllocation, "realloc(branch) failed"); return; }
+        if (!b) { set_error_msg(cudaErrorMemoryAllocation, "realloc(branch) failed"); return; }
         si->branch = b;
         if (siIndexExport(h->ix, si->starts, si->ends, si->data, si->branch, nullptr)) return;
         si->startSorted = true;
@@ -406,7 +385,7 @@ static int count_batch_pipelined(siIndex* ix, const int32_t* qs, const int32_t* 
         ix->pipe_ready = true;
     }
     if (ix->h_qs.ensure(2 * CHUNK * 4) || ix->h_qe.ensure(2 * CHUNK * 4) || ix->h_counts.ensure(2 * CHUNK * 8))
-        return sib::last_error_code();
+        return last_error_code();
     cudaStream_t s_in = ix->s_in, s_k = ix->own_stream, s_out = ix->s_out;
     int order = SI_ORDER_AUTO;
     size_t k = 0;
@@ -426,7 +405,7 @@ static int count_batch_pipelined(siIndex* ix, const int32_t* qs, const int32_t* 
             // one device check on the first chunk decides sort-or-not for the whole batch; any
             // order is answered correctly, the choice only affects locality
             order = si_b200_resolve_order_(ix, dqs, m, s_k);
-            if (order < 0) return sib::last_error_code();
+            if (order < 0) return last_error_code();
         }
         int rc = siCountDevice64(ix, dqs, dqe, m, dc, order, s_k);
         if (rc) return rc;
@@ -445,7 +424,7 @@ void countOverlapsBatch(cSuperIntervals* si, const int32_t* starts, const int32_
     Handle* h = H(si);
     if (n == 0) return;
     if (si->size == 0) { memset(counts_out, 0, n * sizeof(size_t)); return; }   // ref:730-732
-    if (!ready(h, "countOverlapsBatch")) { memset(counts_out, 0, n * sizeof(size_t)); return; }
+    if (!handle_ready(h, "countOverlapsBatch")) { memset(counts_out, 0, n * sizeof(size_t)); return; }
     siIndex* ix = h->ix;
     static_assert(sizeof(size_t) == 8, "LP64 only");
     if (n > ((size_t)12 << 20)) {
@@ -458,14 +437,14 @@ void countOverlapsBatch(cSuperIntervals* si, const int32_t* starts, const int32_
         return;
     if (cudaMemcpyAsync(counts_out, ix->h_counts.p, n * 8, cudaMemcpyDeviceToHost, ix->own_stream) != cudaSuccess ||
         cudaStreamSynchronize(ix->own_stream) != cudaSuccess)
-        sib::set_error(cudaGetLastError(), "countOverlapsBatch copy-back", __FILE__, __LINE__);
+        set_error(cudaGetLastError(), "countOverlapsBatch copy-back", __FILE__, __LINE__);
 }
 
 void anyOverlapsBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n, bool* out) {
     Handle* h = H(si);
     if (n == 0) return;
     if (si->size == 0) { memset(out, 0, n); return; }
-    if (!ready(h, "anyOverlapsBatch")) { memset(out, 0, n); return; }
+    if (!handle_ready(h, "anyOverlapsBatch")) { memset(out, 0, n); return; }
     siIndex* ix = h->ix;
     if (stage_queries(ix, starts, ends, n) || ix->h_counts.ensure(n)) return;
     if (siAnyDevice(ix, ix->h_qs.as<int32_t>(), ix->h_qe.as<int32_t>(), n, ix->h_counts.as<uint8_t>(), ix->own_stream))
@@ -473,14 +452,14 @@ void anyOverlapsBatch(cSuperIntervals* si, const int32_t* starts, const int32_t*
     static_assert(sizeof(bool) == 1, "bool must be one byte");
     if (cudaMemcpyAsync(out, ix->h_counts.p, n, cudaMemcpyDeviceToHost, ix->own_stream) != cudaSuccess ||
         cudaStreamSynchronize(ix->own_stream) != cudaSuccess)
-        sib::set_error(cudaGetLastError(), "anyOverlapsBatch copy-back", __FILE__, __LINE__);
+        set_error(cudaGetLastError(), "anyOverlapsBatch copy-back", __FILE__, __LINE__);
 }
 
 #define SIB_SEARCH_BATCH(NAME, RTYPE, WHAT, ELEM)                                                         \
     void NAME(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n, size_t* offsets_out, \
               RTYPE* found) {                                                                             \
         Handle* h = H(si);                                                                                \
-        if (si->size == 0 || !ready(h, #NAME)) {                                                          \
+        if (si->size == 0 || !handle_ready(h, #NAME)) {                                                          \
             if (offsets_out) memset(offsets_out, 0, (n + 1) * sizeof(size_t));                            \
             return;                                                                                       \
         }                                                                                                 \
@@ -496,7 +475,7 @@ void coverageBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* en
                    int32_t* coverage_out) {
     Handle* h = H(si);
     if (n == 0) return;
-    if (si->size == 0 || !ready(h, "coverageBatch")) {
+    if (si->size == 0 || !handle_ready(h, "coverageBatch")) {
         memset(count_out, 0, n * sizeof(size_t));
         memset(coverage_out, 0, n * sizeof(int32_t));
         return;
@@ -510,7 +489,7 @@ void coverageBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* en
     if (cudaMemcpyAsync(tmp, ix->h_counts.p, n * 4, cudaMemcpyDeviceToHost, ix->own_stream) != cudaSuccess ||
         cudaMemcpyAsync(coverage_out, ix->h_cov.p, n * 4, cudaMemcpyDeviceToHost, ix->own_stream) != cudaSuccess ||
         cudaStreamSynchronize(ix->own_stream) != cudaSuccess)
-        sib::set_error(cudaGetLastError(), "coverageBatch copy-back", __FILE__, __LINE__);
+        set_error(cudaGetLastError(), "coverageBatch copy-back", __FILE__, __LINE__);
     for (size_t i = 0; i < n; ++i) count_out[i] = tmp[i];
     free(tmp);
 }
@@ -519,7 +498,7 @@ void coverageBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* en
 size_t upperBound(cSuperIntervals* si, int32_t value) {
     Handle* h = H(si);
     size_t r = SI_NONE;
-    if (si->size != 0 && ready(h, "upperBound")) si_b200_upper_bound_(h->ix, value, &r);
+    if (si->size != 0 && handle_ready(h, "upperBound")) si_b200_upper_bound_(h->ix, value, &r);
     si->idx = r;   // ref:539,562,566
     return r;
 }

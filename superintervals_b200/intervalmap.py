@@ -14,8 +14,12 @@ Additions to the reference API (the CSR forms the GPU path produces natively):
 The ``*_batch`` methods of the reference return Python lists / list-of-lists
 (pyx:395-400, 436-446, 482-494); they are kept and built from the CSR forms.
 
-Not provided: the set-algebra methods (pyx:510-819) -- outside the accelerated
-path.
+Set algebra (pyx:510-819: merge_overlaps, union_with, intersection, difference,
+symmetric_difference, gaps, span, expand, flank, unique): the geometry comes from the
+library's device implementation of the reference's C functions
+(include/c_superintervals.h "set operations"); Python payload objects are folded on the
+host exactly as the reference does (tuples by default, or the caller's ``combine``). As
+in the reference every result is a new, BUILT map.
 """
 from __future__ import annotations
 
@@ -253,3 +257,132 @@ class IntervalMap:
         off, idx = self.search_values_batch_csr(starts, ends)
         vals = self._values
         return [[vals[i] for i in idx[int(off[q]):int(off[q + 1])]] for q in range(len(off) - 1)]
+
+    # ---- set algebra (pyx:510-819) ------------------------------------------------------------------
+    def _stored(self):
+        """Stored arrays (starts, ends, payload index) in the handle's current order."""
+        return self._mirror("starts", np.int32), self._mirror("ends", np.int32), self._mirror("data", np.int32)
+
+    @classmethod
+    def _wrap(cls, L, si, values):
+        """A map over a handle the library returned; `values[i]` is the payload of its i-th interval."""
+        m = cls.__new__(cls)
+        m._L, m._si, m._values, m._built = L, si, list(values), False
+        n = int(si.contents.size)
+        if n:
+            np.ctypeslib.as_array(si.contents.data, shape=(n,))[:] = np.arange(n, dtype=np.int32)
+        m.build()
+        return m
+
+    def _take(self, si):
+        n = int(si.contents.size)
+        if n == 0:
+            z = np.zeros(0, np.int32)
+            return z, z, z
+        return tuple(np.ctypeslib.as_array(getattr(si.contents, f), shape=(n,)).copy() for f in ("starts", "ends", "data"))
+
+    @staticmethod
+    def _fold(acc, d, combine):
+        if combine is not None:
+            return combine(acc, d)
+        return acc + (d,) if isinstance(acc, tuple) else (acc, d)          # pyx:549-550
+
+    def _merged(self, si, starts, ends, vals, combine):
+        """Fold payloads into the clusters of a merged handle: members in (start, end) order (pyx:522)."""
+        ms, _, _ = self._take(si)
+        out = [None] * ms.size
+        seen = np.zeros(ms.size, bool)
+        order = np.lexsort((ends, starts))
+        cl = np.searchsorted(ms, starts[order], "right") - 1
+        for k, c in zip(order, cl):
+            if seen[c]:
+                out[c] = self._fold(out[c], vals[k], combine)
+            else:
+                out[c], seen[c] = vals[k], True
+        return self._wrap(self._L, si, out)
+
+    def merge_overlaps(self, combine=None):
+        """Coalesce overlapping intervals into a disjoint set (pyx:525-556); merged payloads are
+        collected into a tuple unless `combine(a, b)` is given."""
+        s, e, d = self._stored()
+        si = self._L.mergeOverlaps(self._si, None)
+        _lib.check("merge_overlaps")
+        return self._merged(si, s, e, [self._values[i] for i in d], combine)
+
+    def union_with(self, other, combine=None):
+        """All covered regions of both maps, coalesced (pyx:558-575)."""
+        s1, e1, d1 = self._stored()
+        s2, e2, d2 = other._stored()
+        si = self._L.unionWith(self._si, other._si, None)
+        _lib.check("union_with")
+        vals = [self._values[i] for i in d1] + [other._values[i] for i in d2]
+        return self._merged(si, np.concatenate([s1, s2]), np.concatenate([e1, e2]), vals, combine)
+
+    def intersection(self, other, combine=None):
+        """Every overlapping sub-region of the two maps, not coalesced (pyx:577-609); payloads are
+        paired into (a, b) unless `combine(a, b)` is given. `other` must be built."""
+        b = self._L.createIndexResult()
+        si = self._L.intersectionPairs(self._si, other._si, C.byref(b))
+        _lib.check("intersection")
+        _, _, da = self._take(si)
+        db = [b.data[i] for i in range(int(b.size))]
+        self._L.destroyIndexResult(C.byref(b))
+        pair = combine if combine is not None else (lambda x, y: (x, y))
+        return self._wrap(self._L, si, [pair(self._values[i], other._values[j]) for i, j in zip(da, db)])
+
+    def difference(self, other):
+        """Regions of this map not covered by `other` (pyx:611-649); pieces inherit their source payload."""
+        si = self._L.difference(self._si, other._si)
+        _lib.check("difference")
+        _, _, d = self._take(si)
+        return self._wrap(self._L, si, [self._values[i] for i in d])
+
+    def symmetric_difference(self, other):
+        """Regions in exactly one of the two maps (pyx:651-664). Both must be built."""
+        return self.difference(other).union_with(other.difference(self))
+
+    def gaps(self, lo, hi, fill=None):
+        """The uncovered regions inside [lo, hi] (pyx:666-695)."""
+        si = self._L.intervalGaps(self._si, int(lo), int(hi), 0)
+        _lib.check("gaps")
+        return self._wrap(self._L, si, [fill] * int(si.contents.size))
+
+    def span(self):
+        """(min start, max end), or None when empty (pyx:697-715)."""
+        lo, hi = C.c_int32(0), C.c_int32(0)
+        ok = self._L.intervalSpan(self._si, C.byref(lo), C.byref(hi))
+        _lib.check("span")
+        return (lo.value, hi.value) if ok else None
+
+    _I32 = np.iinfo(np.int32)
+
+    def expand(self, left, right, lo=None, hi=None):
+        """Grow or shrink every interval, like `bedtools slop` (pyx:717-746)."""
+        si = self._L.expandIntervals(self._si, int(left), int(right), self._I32.min if lo is None else int(lo),
+                                     self._I32.max if hi is None else int(hi))
+        _lib.check("expand")
+        _, _, d = self._take(si)
+        return self._wrap(self._L, si, [self._values[i] for i in d])
+
+    def flank(self, left, right, lo=None, hi=None):
+        """The strips beside each interval, like `bedtools flank` (pyx:748-788); originals are not emitted."""
+        si = self._L.flankIntervals(self._si, int(left), int(right), self._I32.min if lo is None else int(lo),
+                                    self._I32.max if hi is None else int(hi))
+        _lib.check("flank")
+        _, _, d = self._take(si)
+        return self._wrap(self._L, si, [self._values[i] for i in d])
+
+    def unique(self, combine=None):
+        """One interval per distinct (start, end) pair (pyx:790-819); the first payload is kept
+        unless `combine(a, b)` folds the duplicates."""
+        s, e, d = self._stored()
+        si = self._L.uniqueIntervals(self._si, None)
+        _lib.check("unique")
+        us, ue, ud = self._take(si)
+        if combine is None:
+            return self._wrap(self._L, si, [self._values[i] for i in ud])
+        acc = {}
+        for k in np.lexsort((e, s)):
+            key = (int(s[k]), int(e[k]))
+            acc[key] = combine(acc[key], self._values[d[k]]) if key in acc else self._values[d[k]]
+        return self._wrap(self._L, si, [acc[(int(a), int(b))] for a, b in zip(us, ue)])

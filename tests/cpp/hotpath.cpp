@@ -159,6 +159,73 @@ static void test_batch_and_payload_types() {
     }
 }
 
+// ---- set operations: the reference's known answers (test/tests.cpp:259-378) ------------------
+static std::vector<std::pair<int, int>> geometry(Map& m) {
+    std::vector<std::pair<int, int>> v;
+    for (size_t i = 0; i < m.size(); ++i) v.emplace_back(m.starts[i], m.ends[i]);
+    return v;
+}
+
+static void test_set_operations() {
+    {   // tests.cpp:259-278
+        Map a; a.add(1, 5, 0); a.add(3, 8, 1); a.add(20, 30, 2); a.build();
+        Map merged = a.merge_overlaps();
+        auto v = geometry(merged);
+        CHECK(v.size() == 2 && v[0] == std::make_pair(1, 8) && v[1] == std::make_pair(20, 30));
+        Map summed = a.merge_overlaps([](const int& x, const int& y) { return x + y; });
+        CHECK(summed.at(0).data == 1);
+    }
+    {   // tests.cpp:280-293
+        Map a; a.add(10, 20, 0); a.add(30, 40, 1); a.build();
+        Map g = a.gaps(0, 50);
+        auto v = geometry(g);
+        CHECK(v.size() == 3 && v[0] == std::make_pair(0, 9) && v[1] == std::make_pair(21, 29) && v[2] == std::make_pair(41, 50));
+    }
+    {   // tests.cpp:295-306
+        Map a, b; a.add(1, 10, 0); b.add(5, 25, 1); a.build(); b.build();
+        Map u = a.union_with(b);
+        auto v = geometry(u);
+        CHECK(v.size() == 1 && v[0] == std::make_pair(1, 25));
+    }
+    {   // tests.cpp:308-329
+        Map a, b; a.add(1, 10, 0); a.add(20, 30, 1); b.add(5, 25, 2); a.build(); b.build();
+        Map inter = a.intersection(b);
+        auto v = geometry(inter);
+        CHECK(v.size() == 2 && v[0] == std::make_pair(5, 10) && v[1] == std::make_pair(20, 25));
+        inter.build();
+        CHECK(inter.has_overlaps(7, 7) && !inter.has_overlaps(15, 15));
+    }
+    {   // tests.cpp:331-343
+        Map a, b; a.add(1, 10, 0); b.add(4, 6, 1); a.build(); b.build();
+        Map d = a.difference(b);
+        auto v = geometry(d);
+        CHECK(v.size() == 2 && v[0] == std::make_pair(1, 3) && v[1] == std::make_pair(7, 10));
+    }
+    {   // tests.cpp:345-357
+        Map a, b; a.add(1, 10, 0); b.add(5, 15, 1); a.build(); b.build();
+        Map x = a.symmetric_difference(b);
+        auto v = geometry(x);
+        CHECK(v.size() == 2 && v[0] == std::make_pair(1, 4) && v[1] == std::make_pair(11, 15));
+    }
+    {   // tests.cpp:359-373
+        Map a; a.add(10, 20, 0); a.add(5, 8, 1); a.add(15, 50, 2); a.build();
+        std::pair<int, int> sp;
+        CHECK(a.span(sp) && sp.first == 5 && sp.second == 50);
+        Map empty;
+        CHECK(!empty.span(sp));
+    }
+    {   // expand / flank / unique (hpp:1258-1360; no reference unit test: checked against their definitions)
+        Map a; a.add(10, 20, 7); a.add(10, 20, 8); a.add(30, 31, 9); a.build();
+        Map e = a.expand(2, 3, 9, 33);
+        auto v = geometry(e);
+        CHECK(v.size() == 3 && v[0] == std::make_pair(9, 23) && v[2] == std::make_pair(28, 33));
+        Map f = a.flank(2, 2);
+        CHECK(f.size() == 6 && f.starts[0] == 8 && f.ends[0] == 9 && f.starts[1] == 21 && f.ends[1] == 22);
+        Map u = a.unique([](const int& x, const int& y) { return x + y; });
+        CHECK(u.size() == 2 && u.at(0).data == 15 && u.at(1).data == 9);
+    }
+}
+
 int main() {
     test_basics();
     test_iteration();
@@ -169,5 +236,8 @@ int main() {
     test_batch_and_payload_types();
     CHECK(si_b200_last_error() == 0);
     std::printf("All query tests passed\n");
+    test_set_operations();
+    CHECK(si_b200_last_error() == 0);
+    std::printf("All set operation tests passed\n");
     return 0;
 }

@@ -27,7 +27,7 @@ def test_library_is_built_and_loads():
 
 def test_every_declared_symbol_is_exported():
     L = _lib.lib()
-    declared = (_declared("c_superintervals.h") | _declared("superintervals_b200.h")) - {"size_t"}
+    declared = (_declared("c_superintervals.h") | _declared("superintervals_b200.h")) - {"size_t", "int32_t"}   # int32_t: return type of the cCombineFn function-pointer typedef
     missing = sorted(s for s in declared if not hasattr(L, s))
     assert not missing, f"declared in include/*.h but not exported: {missing}"
     # and the python binding lists them all

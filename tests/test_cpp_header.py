@@ -28,3 +28,4 @@ def test_cpp_hot_path_unit_tests_pass_on_gpu():
     out = subprocess.run([EXE], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "All query tests passed" in out.stdout
+    assert "All set operation tests passed" in out.stdout
