@@ -75,6 +75,29 @@ void coverageBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* en
  * them into tuples). */
 cSuperIntervals* intersectionPairs(const cSuperIntervals* si, cSuperIntervals* other, cIndexResult* other_data);
 
+/* ---- 2b. BED ingest: the step before the path ------------------------------------------
+ * Tokenises BED text on the device (csrc/bed.cu): one record per line, tab-separated
+ * chrom, start, end (further columns ignored), numbers read with std::stoi's rules -- what
+ * the reference's callers do one line at a time on the host (test/bench.cpp:67-102,
+ * examples/bed-intersect-si.rs:63-123). Lines without a chrom, a numeric start and a numeric
+ * end (headers, comments, blanks; the reference would throw) are skipped and counted.
+ * normalize != 0 swaps start/end when start > end (bench.cpp:89); end_shift is added to every
+ * end (-1 turns BED's half-open ends into the inclusive ends the index stores, bench.cpp:210).
+ * contig[i] indexes names[], which lists the distinct chroms in order of first appearance.
+ * All arrays are malloc'd by the library; release with siBedTableFree. Returns 0 or a CUDA error. */
+typedef struct {
+    int32_t* contig;
+    int32_t* starts;
+    int32_t* ends;
+    size_t n;          /* records parsed (line order) */
+    size_t lines;      /* lines seen */
+    size_t skipped;    /* lines - n */
+    char** names;
+    size_t n_contigs;
+} siBedTable;
+int siParseBed(const char* text, size_t bytes, int normalize, int end_shift, siBedTable* out);
+void siBedTableFree(siBedTable* t);
+
 /* ---- 3. device-resident core ------------------------------------------------------- */
 typedef struct siIndex siIndex;
 

@@ -61,6 +61,12 @@ class siCellsInfo(C.Structure):
                 ("overfull", C.c_ulonglong), ("direct", C.c_int)]
 
 
+class siBedTable(C.Structure):
+    _fields_ = [("contig", C.POINTER(C.c_int32)), ("starts", C.POINTER(C.c_int32)), ("ends", C.POINTER(C.c_int32)),
+                ("n", C.c_size_t), ("lines", C.c_size_t), ("skipped", C.c_size_t),
+                ("names", C.POINTER(C.c_char_p)), ("n_contigs", C.c_size_t)]
+
+
 class siStabInfo(C.Structure):
     _fields_ = [("state", C.c_int), ("shift", C.c_uint), ("lists", C.c_ulonglong), ("entries", C.c_ulonglong)]
 
@@ -91,7 +97,7 @@ B200_SYMBOLS = [
     "si_b200_last_error", "si_b200_last_error_string", "si_b200_clear_error", "si_b200_version",
     "si_b200_device_count", "si_b200_kernel_launches", "addIntervals", "siSetHostMirror",
     "countOverlapsBatch", "anyOverlapsBatch", "searchValuesBatch", "searchIdxsBatch", "searchKeysBatch",
-    "searchItemsBatch", "coverageBatch", "intersectionPairs", "siIndexCreate", "siIndexDestroy", "siIndexOf", "siIndexSize",
+    "searchItemsBatch", "coverageBatch", "intersectionPairs", "siParseBed", "siBedTableFree", "siIndexCreate", "siIndexDestroy", "siIndexOf", "siIndexSize",
     "siIndexDeviceView", "siIndexBuildHost", "siIndexBuildDevice", "siIndexExport", "siCountDevice",
     "siCountDevice64", "siSortQueriesDevice", "siIndexSetOption", "siIndexCellsInfo", "siIndexStabInfo", "siIndexReadTimings", "siAnyDevice", "siScanDevice", "siFillDevice", "siCoverageDevice",
     "siIndexDeviceBytes",
@@ -191,6 +197,9 @@ def bind_b200(L):
     if hasattr(L, "intersectionPairs"):
         L.intersectionPairs.restype = SI
         L.intersectionPairs.argtypes = [SI, SI, C.POINTER(cIndexResult)]
+    L.siParseBed.restype = C.c_int
+    L.siParseBed.argtypes = [C.c_char_p, sz, C.c_int, C.c_int, C.POINTER(siBedTable)]
+    L.siBedTableFree.argtypes = [C.POINTER(siBedTable)]
     L.siIndexStabInfo.argtypes = [vp, C.POINTER(siStabInfo)]
     L.siIndexStabInfo.restype = C.c_int
     L.siIndexSetOption.argtypes = [vp, C.c_int, C.c_longlong]

@@ -320,7 +320,10 @@ class IntervalMap:
 
     def intersection(self, other, combine=None):
         """Every overlapping sub-region of the two maps, not coalesced (pyx:577-609); payloads are
-        paired into (a, b) unless `combine(a, b)` is given. `other` must be built."""
+        paired into (a, b) unless `combine(a, b)` is given. `other` must be built. Every overlapping
+        pair is returned once, as the C++ and C implementations do (hpp:1164-1179, c.h:921-939); the
+        reference's Python method re-emits pairs because it never clears `other.found_indexes`
+        (pyx:597-599) -- its output is this one with duplicates."""
         b = self._L.createIndexResult()
         si = self._L.intersectionPairs(self._si, other._si, C.byref(b))
         _lib.check("intersection")

@@ -29,9 +29,9 @@ def cases(scale=1):
     big = (np.array([5, 10 * n, 3], np.int32), np.array([25 * n, 28 * n, 2 * n], np.int32), np.array([7, 8, 9], np.int32))
     out.append(("containers", tuple(np.concatenate([x, y]) for x, y in zip(a, big)), _rand(rng, n // 2, 30 * n, 400)))
     s = rng.integers(-2_000_000_000, 2_000_000_000, n, dtype=np.int64)
-    e = np.minimum(s + rng.integers(0, 60_000_000, n), I32.max - 1)
+    e = np.minimum(s + rng.integers(0, 60_000_000 // scale, n), I32.max - 1)
     out.append(("signed_wide", (s.astype(np.int32), e.astype(np.int32), rng.integers(-9, 9, n).astype(np.int32)),
-                _rand(rng, n, 1_000_000, 5_000)))
+                _rand(rng, n, 1_000_000 if scale == 1 else 20_000 * n, 5_000)))
     out.append(("empty_a", (np.zeros(0, np.int32),) * 3, _rand(rng, 20, 500, 30)))
     out.append(("empty_b", _rand(rng, 20, 500, 30), (np.zeros(0, np.int32),) * 3))
     out.append(("single", (np.array([7], np.int32), np.array([19], np.int32), np.array([1], np.int32)),

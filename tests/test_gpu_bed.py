@@ -1,0 +1,73 @@
+"""GPU: BED ingest (siParseBed / superintervals_b200.bed.parse_bed) against the CPU restatement of the
+reference's tokenising (oracle/bed_oracle.py <- reference test/bench.cpp:67-102)."""
+import numpy as np
+import pytest
+
+from oracle import bed_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _bed(rng, n, contigs, extras=True, crlf=False, final_newline=True):
+    rows = []
+    for i in range(n):
+        c = contigs[int(rng.integers(0, len(contigs)))]
+        s = int(rng.integers(0, 250_000_000))
+        e = s + int(rng.integers(-5 if i % 97 == 0 else 0, 10_000))
+        tail = f"\tname{i}\t{int(rng.integers(0, 1000))}\t+" if extras and i % 3 == 0 else ""
+        rows.append(f"{c}\t{s}\t{e}{tail}")
+    eol = "\r\n" if crlf else "\n"
+    txt = eol.join(rows) + (eol if final_newline else "")
+    return txt.encode()
+
+
+def _same(got, want):
+    names, contig, starts, ends, lines, skipped = want
+    assert got.names == names
+    assert got.lines == lines and got.skipped == skipped
+    assert np.array_equal(got.contig, contig) and np.array_equal(got.starts, starts) and np.array_equal(got.ends, ends)
+
+
+@pytest.mark.parametrize("n,crlf,final_newline", [(1, False, True), (1, False, False), (1000, False, True),
+                                                  (1000, True, False), (200_000, False, True)])
+@pytest.mark.parametrize("normalize,end_shift", [(False, 0), (True, -1)])
+def test_bed_text_parses_like_the_reference(n, crlf, final_newline, normalize, end_shift):
+    from superintervals_b200.bed import parse_bed
+    rng = np.random.default_rng(n + 7 * crlf)
+    text = _bed(rng, n, ["chr1", "chr2", "chrX", "chrUn_KI270742v1", "1"], crlf=crlf, final_newline=final_newline)
+    _same(parse_bed(text, normalize, end_shift), bed_oracle.parse_bed(text, normalize, end_shift))
+
+
+def test_headers_blanks_and_broken_lines_are_skipped_and_counted():
+    from superintervals_b200.bed import parse_bed
+    text = (b"track name=x description=\"y\"\n# comment\tstill\tcomment\nbrowser position chr1:1-100\n\n"
+            b"chr1\t10\t20\nchr1\t  +30\t40abc\textra\nchr2\t-5\t7\nchr1\tx\t9\nchr1\t5\n\t1\t2\nchr3\t1\t99999999999\n"
+            b"chr2\t2147483647\t2147483647\nchr1 10 20\nchr9\t3\t-4")
+    for norm, shift in ((False, 0), (True, 0), (False, -1), (False, 1)):
+        _same(parse_bed(text, norm, shift), bed_oracle.parse_bed(text, norm, shift))
+    t = parse_bed(text)
+    assert t.names == ["chr1", "chr2", "chr9"] and t.skipped == t.lines - len(t.starts) and len(t.starts) == 5
+
+
+def test_empty_and_newline_only_inputs():
+    from superintervals_b200.bed import parse_bed
+    for text in (b"", b"\n", b"\n\n\n", b"chr1"):
+        _same(parse_bed(text), bed_oracle.parse_bed(text))
+
+
+def test_bed_to_queries_end_to_end(tmp_path):
+    """File -> device parse -> per-contig index -> counts, equal to the oracle on the same records
+    (the reference's bench flow, bench.cpp:200-252, for every chrom instead of chr1 only)."""
+    from oracle.pyoracle import Oracle
+    from superintervals_b200 import IntervalMap
+    from superintervals_b200.bed import parse_bed, split_by_contig
+    rng = np.random.default_rng(5)
+    contigs = ["chr1", "chr2", "chr3"]
+    p_ref, p_q = tmp_path / "ref.bed", tmp_path / "q.bed"
+    p_ref.write_bytes(_bed(rng, 30_000, contigs))
+    p_q.write_bytes(_bed(rng, 20_000, contigs, extras=False))
+    ref, qry = split_by_contig(parse_bed(str(p_ref), True, -1)), split_by_contig(parse_bed(str(p_q), True, -1))
+    assert set(ref) == set(contigs)
+    for c in contigs:
+        m = IntervalMap.from_arrays(*ref[c])
+        assert np.array_equal(m.count_batch_np(*qry[c]), Oracle(*ref[c]).count_batch(*qry[c]))

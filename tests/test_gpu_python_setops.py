@@ -57,6 +57,14 @@ def test_python_set_algebra_matches_the_reference_module(name, A, B):
             continue
         rows = [[int(s), int(e), repr(v)] for s, e, v in (got.at(i) for i in range(len(got)))]
         first_kept = key in ("merge_first", "unique")
+        if key.startswith("intersection"):
+            # reference defect (pyx:597-599): intersection() clears self.found_indexes but appends to
+            # other.found_indexes, so stale hits of earlier intervals are re-tested and every true pair is
+            # emitted 1 + (earlier intervals sharing that partner) times. C++ (hpp:1167) and C (c.h:927)
+            # clear per interval. We return each pair once: equal as sets, never more than the reference.
+            assert set(canon(rows, False)) == set(canon(want, False)), (name, key)
+            assert len(rows) == len(set(canon(rows, False))) <= len(want), (name, key)
+            continue
         assert canon(rows, first_kept) == canon(want, first_kept), (name, key)
         if key == "unique":
             assert all(ast.literal_eval(r) in stored[(s, e)] for s, e, r in rows)
