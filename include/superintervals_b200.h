@@ -176,11 +176,12 @@ typedef struct {
 int siIndexCellsInfo(const siIndex* ix, int which, siCellsInfo* out);
 /* The stab lists of the CSR fill (made by the first siFillDevice after a build): state 0 = not
  * made yet, 1 = in use, 2 = over budget or too small (the fill walks); a checkpoint every
- * 2^shift positions, `lists` lists holding `entries` (position, end) pairs of 8 bytes. */
+ * 2^shift positions, `lists` lists holding `entries` records of `record_bytes` bytes. */
 typedef struct {
     int state;
     unsigned shift;
     unsigned long long lists, entries;
+    unsigned record_bytes;   /* 8: (position, end); 16: (position, end, value, -) on dense data */
 } siStabInfo;
 int siIndexStabInfo(const siIndex* ix, siStabInfo* out);
 /* With SI_OPT_TIMING = 1 every hot kernel launch is bracketed by a CUDA event pair on its

@@ -68,7 +68,8 @@ class siBedTable(C.Structure):
 
 
 class siStabInfo(C.Structure):
-    _fields_ = [("state", C.c_int), ("shift", C.c_uint), ("lists", C.c_ulonglong), ("entries", C.c_ulonglong)]
+    _fields_ = [("state", C.c_int), ("shift", C.c_uint), ("lists", C.c_ulonglong), ("entries", C.c_ulonglong),
+                ("record_bytes", C.c_uint)]
 
 
 def build_library(verbose: bool = False) -> str:

@@ -163,7 +163,7 @@ IndexView view_of(const siIndex* ix) {
     v.cells_s = RankCells{ix->cells_s.as<uint4>(), ix->cm_s.lo, ix->cm_s.span, ix->cm_s.shift, ix->cm_s.fmt};
     v.cells_e = RankCells{ix->cells_e.as<uint4>(), ix->cm_e.lo, ix->cm_e.span, ix->cm_e.shift, ix->cm_e.fmt};
     const bool stab = ix->stab_state == 1 && ix->stab_enabled;
-    v.stab = StabLists{ix->stab_off.as<uint64_t>(), stab ? ix->stab_ent.as<int2>() : nullptr, ix->stab_kshift, ix->stab_nlists};
+    v.stab = StabLists{ix->stab_off.as<uint64_t>(), stab ? ix->stab_ent.p : nullptr, ix->stab_rec16 ? 1u : 0u, ix->stab_kshift, ix->stab_nlists};
     v.n = ix->n;
     v.wellformed = ix->wellformed ? 1u : 0u;
     return v;
@@ -525,8 +525,8 @@ int ensure_stab_lists(siIndex* ix, cudaStream_t s) {
     unsigned long long* d_tot = reinterpret_cast<unsigned long long*>(ix->small.as<uint32_t>() + 16);
     SIB_CHECK(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long) * QK_STAB_SPACINGS, s));
     const IndexView v = view_of(ix);
-    SIB_LAUNCH((qk_stab_lists_kernel<false>), (nl0 + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, QK_STAB_SHIFT0, nl0,
-               ix->stab_cnt.as<uint32_t>(), (const uint64_t*)nullptr, (int2*)nullptr);
+    SIB_LAUNCH((qk_stab_lists_kernel<false, false>), (nl0 + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, QK_STAB_SHIFT0, nl0,
+               ix->stab_cnt.as<uint32_t>(), (const uint64_t*)nullptr, (void*)nullptr);
     SIB_LAUNCH(qk_stab_totals_kernel, grid_for(nl0, QK_THREADS, ix->sm_count * 8), QK_THREADS, 0, s,
                ix->stab_cnt.as<uint32_t>(), nl0, d_tot);
     unsigned long long tot[QK_STAB_SPACINGS];
@@ -539,13 +539,20 @@ int ensure_stab_lists(siIndex* ix, cudaStream_t s) {
     const uint32_t kshift = QK_STAB_SHIFT0 + (uint32_t)k;
     const uint32_t nl = (n >> kshift) + 1;
     if (k > 0)   // the kept checkpoints' counts, contiguous
-        SIB_LAUNCH((qk_stab_lists_kernel<false>), (nl + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, kshift, nl,
-                   ix->stab_cnt.as<uint32_t>(), (const uint64_t*)nullptr, (int2*)nullptr);
-    if (ix->stab_off.ensure(((size_t)nl + 1) * 8) || ix->stab_ent.ensure((size_t)(tot[k] ? tot[k] : 1) * 8)) return last_error_code();
+        SIB_LAUNCH((qk_stab_lists_kernel<false, false>), (nl + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, kshift, nl,
+                   ix->stab_cnt.as<uint32_t>(), (const uint64_t*)nullptr, (void*)nullptr);
+    // long lists (dense data): nearly every record read is a hit, so the value rides in the record
+    const bool rec16 = tot[k] >= 16ull * nl;
+    if (ix->stab_off.ensure(((size_t)nl + 1) * 8) || ix->stab_ent.ensure((size_t)(tot[k] ? tot[k] : 1) * (rec16 ? 16 : 8))) return last_error_code();
     int rc = siScanDevice(ix, ix->stab_cnt.as<uint32_t>(), nl, ix->stab_off.as<uint64_t>(), (void*)s);
     if (rc) return rc;
-    SIB_LAUNCH((qk_stab_lists_kernel<true>), (nl + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, kshift, nl,
-               (uint32_t*)nullptr, ix->stab_off.as<uint64_t>(), ix->stab_ent.as<int2>());
+    if (rec16)
+        SIB_LAUNCH((qk_stab_lists_kernel<true, true>), (nl + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, kshift, nl,
+                   (uint32_t*)nullptr, ix->stab_off.as<uint64_t>(), ix->stab_ent.p);
+    else
+        SIB_LAUNCH((qk_stab_lists_kernel<true, false>), (nl + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, kshift, nl,
+                   (uint32_t*)nullptr, ix->stab_off.as<uint64_t>(), ix->stab_ent.p);
+    ix->stab_rec16 = rec16;
     ix->stab_kshift = kshift;
     ix->stab_nlists = nl;
     ix->stab_entries = tot[k];
@@ -649,6 +656,7 @@ int siIndexStabInfo(const siIndex* ix, siStabInfo* out) {
     out->shift = ix->stab_state == 1 ? ix->stab_kshift : 0;
     out->lists = ix->stab_state == 1 ? ix->stab_nlists : 0;
     out->entries = ix->stab_state == 1 ? ix->stab_entries : 0;
+    out->record_bytes = ix->stab_state == 1 ? (ix->stab_rec16 ? 16u : 8u) : 0u;
     return 0;
 }
 

@@ -62,6 +62,7 @@ struct siIndex {
     // stab lists (StabLists in query_kernels.cuh), made by the first CSR fill that can use them
     sib::DevBuf stab_off, stab_ent, stab_cnt;
     uint32_t stab_kshift = 0, stab_nlists = 0;
+    bool stab_rec16 = false;                       // 16-byte (position, end, value) records instead of 8-byte (position, end)
     int stab_state = 0;                            // 0 = not tried yet, 1 = built, 2 = over budget (the fill walks)
     unsigned long long stab_entries = 0;
     bool stab_enabled = true;                      // SI_OPT_STAB_LISTS

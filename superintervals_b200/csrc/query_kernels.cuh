@@ -57,16 +57,26 @@ struct RankCells {
 // positions; list b holds every interval below position b << kshift that is still open just after
 // the start at position (b << kshift) - 1,
 //     L(b) = { j < b << kshift : ends[j] > starts[(b << kshift) - 1] },   L(0) empty,
-// as (position, end) pairs in descending position. Any query whose candidates end at
+// as records in descending position: 8-byte (position, end) on sparse data, where few records are
+// read per query and only the hits fetch their payload, or 16-byte (position, end, value, -) when
+// the lists are long (>= 16 records on average: nearly every record is a hit and a gather per hit
+// would cost more than carrying the value). Any query whose candidates end at
 // top = #{starts < qs} with top >> kshift == b has qs > starts[(b << kshift) - 1], so its hits
 // below the checkpoint are exactly the entries of L(b) with end >= qs: one sequential list read
 // instead of the branch-array walk's chain of dependent loads.
 struct StabLists {
     const uint64_t* off;   // nlists + 1 offsets into ent
-    const int2* ent;       // (position, end); nullptr = not built (too deep, or not asked for yet)
+    const void* ent;       // int2 (position, end) or int4 (position, end, value, 0) records; nullptr = not built
+    uint32_t rec16;        // 1: 16-byte records
     uint32_t kshift;
     uint32_t nlists;       // (n >> kshift) + 1
 };
+
+__device__ __forceinline__ int4 ld_stab_record(const StabLists& st, uint64_t p) {
+    if (st.rec16) return __ldg(reinterpret_cast<const int4*>(st.ent) + p);
+    const int2 r = __ldg(reinterpret_cast<const int2*>(st.ent) + p);
+    return make_int4(r.x, r.y, 0, 0);
+}
 
 struct IndexView {
     const int32_t* starts;
@@ -684,10 +694,10 @@ qk_fill_kernel(IndexView ix, QueryRecords rec, uint32_t nq, const uint64_t* __re
 // FILL = false counts |L(b)|, FILL = true writes the entries at off[b]. The walk is the
 // reference's (hpp:551-579) with the threshold x = starts[(b << kshift) - 1] + 1, started at the
 // checkpoint's last position; a miss jumps to the smallest branch target over the block's misses.
-template <bool FILL>
+template <bool FILL, bool REC16>
 __global__ void __launch_bounds__(QK_THREADS)
 qk_stab_lists_kernel(IndexView ix, uint32_t kshift, uint32_t nlists, uint32_t* __restrict__ counts,
-                     const uint64_t* __restrict__ off, int2* __restrict__ ent) {
+                     const uint64_t* __restrict__ off, void* __restrict__ ent_out) {
     const uint64_t t64 = (uint64_t)blockIdx.x * QK_THREADS + threadIdx.x;
     if (t64 >= nlists) return;
     const uint32_t b = (uint32_t)t64;
@@ -704,10 +714,16 @@ qk_stab_lists_kernel(IndexView ix, uint32_t kshift, uint32_t nlists, uint32_t* _
                 const uint32_t k = i - base;
                 const bool hx = e.x >= x, hy = k >= 1u && e.y >= x, hz = k >= 2u && e.z >= x, hw = k >= 3u && e.w >= x;
                 if (FILL) {
-                    if (hw) ent[o++] = make_int2((int)(base + 3u), e.w);
-                    if (hz) ent[o++] = make_int2((int)(base + 2u), e.z);
-                    if (hy) ent[o++] = make_int2((int)(base + 1u), e.y);
-                    if (hx) ent[o++] = make_int2((int)base, e.x);
+#define SIB_PUT(J, E)                                                                                     \
+                    do {                                                                                  \
+                        if (REC16) reinterpret_cast<int4*>(ent_out)[o++] = make_int4((int)(J), (E), ld_nc(ix.values + (J)), 0); \
+                        else reinterpret_cast<int2*>(ent_out)[o++] = make_int2((int)(J), (E));            \
+                    } while (0)
+                    if (hw) SIB_PUT(base + 3u, e.w);
+                    if (hz) SIB_PUT(base + 2u, e.z);
+                    if (hy) SIB_PUT(base + 1u, e.y);
+                    if (hx) SIB_PUT(base, e.x);
+#undef SIB_PUT
                 } else {
                     c += (hx ? 1u : 0u) + (hy ? 1u : 0u) + (hz ? 1u : 0u) + (hw ? 1u : 0u);
                 }
@@ -755,9 +771,12 @@ qk_stab_totals_kernel(const uint32_t* __restrict__ counts, uint32_t nlists, unsi
 //         reference's search_values_large locates by search, hpp:588-615). No ends are tested:
 //         the list's head is a reversed copy of values[top .. ub(qe)].
 //   stab  j < top with ends[j] >= qs: the intervals that begin before the query and reach into
-//         it. With stab lists (StabLists above): the ends of the partial checkpoint block
-//         [top & ~(2^kshift - 1), top) are tested with 128-bit loads, then the checkpoint's list is
-//         read front to back and filtered by end >= qs -- independent loads, no pointer chase.
+//         it. With stab lists (StabLists above) the candidates of a query are the positions of
+//         its partial checkpoint block [top & ~(2^kshift - 1), top), descending, followed by the
+//         checkpoint's list; the candidates of a warp's 32 queries are pooled like the runs, every
+//         lane tests one candidate per step (neighbouring lanes read neighbouring ends / list
+//         records), hits are ranked inside their query's lane segment with ballot/popc and stored
+//         next to each other -- independent coalesced loads, no pointer chase.
 //         Without them (an index nested too deeply for the lists' memory budget): the
 //         reference's own branch-array walk from top - 1. Either way it stops as soon as the CSR
 //         slot is full (the offsets say how many hits exist).
@@ -771,6 +790,7 @@ qk_stab_totals_kernel(const uint32_t* __restrict__ counts, uint32_t nlists, unsi
 constexpr int QF_THREADS = 256;
 constexpr int QF_WARPS = QF_THREADS / 32;
 constexpr uint32_t QF_LONG_RUN = 1024;
+constexpr uint32_t QF_POOL_MIN = 32 * 24;   // stab hits owed by a warp from which its candidates are pooled
 
 // one element of a run: position j is a hit for certain, only the payload is read
 template <int MODE>
@@ -789,8 +809,10 @@ template <int MODE>
 __global__ void __launch_bounds__(QF_THREADS)
 qk_fill_runs_kernel(IndexView ix, QueryRecords rec, uint32_t nq, const uint64_t* __restrict__ offsets,
                     typename FillOut<MODE>::T* __restrict__ out) {
-    __shared__ uint32_t s_pre[QF_WARPS][32];   // inclusive prefix sums of the warp's pooled run lengths
-    __shared__ uint32_t s_top[QF_WARPS][32];   // highest position of each run (= ub(qe))
+    // 4 KB per CTA: six resident CTAs stay inside the smallest shared-memory carve-out, the rest of the
+    // SM's 256 KB remains L1 for the scattered index reads (9 KB per CTA cost 20 % of the kernel)
+    __shared__ uint32_t s_pre[QF_WARPS][32];   // inclusive prefix sums of the warp's pooled run (then candidate) counts
+    __shared__ uint32_t s_top[QF_WARPS][32];   // highest position of each run (= ub(qe)); then hits written per query
     __shared__ uint64_t s_out[QF_WARPS][32];   // where each run's first element goes
     const uint64_t t64 = (uint64_t)blockIdx.x * QF_THREADS + threadIdx.x;
     const bool live = t64 < nq;
@@ -859,33 +881,143 @@ qk_fill_runs_kernel(IndexView ix, QueryRecords rec, uint32_t nq, const uint64_t*
     // ---- stab: below top, until the slot is full
     const bool more = any_hits && o < o_end;
     if (ix.stab.ent) {
+        // candidates of this query: plen positions top-1 .. cb (descending), then llen list records
+        uint32_t plen = 0, llen = 0;
+        uint64_t l0 = 0;
         if (more && top) {
-            const uint32_t cb = (top >> ix.stab.kshift) << ix.stab.kshift;   // checkpoint at or below top
-            const uint64_t* lp = ix.stab.off + (top >> ix.stab.kshift);
-            const uint64_t l0 = __ldg(lp), l1 = __ldg(lp + 1);               // requested before the block scan
-            if (top > cb) {
-                uint32_t base = (top - 1u) & ~3u;
-                uint32_t k = (top - 1u) - base;
-                while (true) {
-                    const int4 e = ld_nc4(ix.ends + base);
-                    if (k >= 3u && e.w >= qs) emit<MODE>(ix, out, o++, base + 3u, e.w);
-                    if (k >= 2u && e.z >= qs) emit<MODE>(ix, out, o++, base + 2u, e.z);
-                    if (k >= 1u && e.y >= qs) emit<MODE>(ix, out, o++, base + 1u, e.y);
-                    if (e.x >= qs) emit<MODE>(ix, out, o++, base, e.x);
-                    if (base == cb || o == o_end) break;
-                    base -= 4u;
-                    k = 3u;
+            const uint32_t b = top >> ix.stab.kshift;
+            plen = top - (b << ix.stab.kshift);
+            l0 = __ldg(ix.stab.off + b);
+            llen = (uint32_t)(__ldg(ix.stab.off + b + 1) - l0);   // a list holds fewer than n < 2^32 records
+        }
+        const uint32_t topm1 = top - 1u;
+        const bool rec16 = ix.stab.rec16 != 0;   // list records carry their value
+        // one candidate: c < plen -> position topm1 - c read from ends[], else list record c - plen
+#define SIB_STAB_CAND(C, PLEN, TOPM1, L0, POS, END, VAL, FROM_LIST)                                   \
+        if ((C) < (PLEN)) { POS = (TOPM1) - (C); END = ld_nc(ix.ends + POS); VAL = 0; FROM_LIST = false; } \
+        else { const int4 r_ = ld_stab_record(ix.stab, (L0) + ((C) - (PLEN))); POS = (uint32_t)r_.x; END = r_.y; VAL = r_.z; FROM_LIST = rec16; }
+#define SIB_STAB_EMIT(AT, POS, END, VAL, FROM_LIST)                                                   \
+        if (MODE == FILL_VALUES) reinterpret_cast<int32_t*>(out)[AT] = (FROM_LIST) ? (VAL) : ld_nc(ix.values + (POS)); /* FROM_LIST: VAL is valid */ \
+        else emit<MODE>(ix, out, (AT), (POS), (END));
+        // few stab hits in the whole warp (sparse data): pooling costs more instructions than the
+        // scattered accesses it saves, so each lane sweeps its own candidates. Decided from the hits
+        // still owed -- known from the offsets -- so that nothing waits for the list bounds here.
+        const uint32_t owed = more ? (uint32_t)min(o_end - o, (uint64_t)0x3FFFFFFu) : 0u;
+        const uint32_t wsum = __reduce_add_sync(FULL_MASK, owed);
+        if (wsum < QF_POOL_MIN) {
+            if (more && top) {
+                if (plen) {
+                    uint32_t base = topm1 & ~3u;
+                    uint32_t k = topm1 - base;
+                    const uint32_t cb = top - plen;
+                    while (true) {
+                        const int4 e = ld_nc4(ix.ends + base);
+                        if (k >= 3u && e.w >= qs) emit<MODE>(ix, out, o++, base + 3u, e.w);
+                        if (k >= 2u && e.z >= qs) emit<MODE>(ix, out, o++, base + 2u, e.z);
+                        if (k >= 1u && e.y >= qs) emit<MODE>(ix, out, o++, base + 1u, e.y);
+                        if (e.x >= qs) emit<MODE>(ix, out, o++, base, e.x);
+                        if (base == cb || o == o_end) break;
+                        base -= 4u;
+                        k = 3u;
+                    }
+                }
+                const uint64_t l1 = l0 + llen;
+                if (!rec16) {
+                    const int2* __restrict__ ent2 = reinterpret_cast<const int2*>(ix.stab.ent);
+                    for (uint64_t p = l0; p < l1 && o < o_end; p += 4) {   // four records in flight per step
+                        int2 v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) v[u] = (p + u < l1) ? __ldg(ent2 + p + u) : make_int2(0, INT_MIN);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (p + u < l1 && v[u].y >= qs) emit<MODE>(ix, out, o++, (uint32_t)v[u].x, v[u].y);
+                    }
+                } else {
+                    const int4* __restrict__ ent4 = reinterpret_cast<const int4*>(ix.stab.ent);
+                    for (uint64_t p = l0; p < l1 && o < o_end; p += 2) {
+                        const int4 r0 = __ldg(ent4 + p);
+                        const int4 r1 = (p + 1 < l1) ? __ldg(ent4 + p + 1) : make_int4(0, INT_MIN, 0, 0);
+                        if (r0.y >= qs) { SIB_STAB_EMIT(o, (uint32_t)r0.x, r0.y, r0.z, true) ++o; }
+                        if (p + 1 < l1 && r1.y >= qs) { SIB_STAB_EMIT(o, (uint32_t)r1.x, r1.y, r1.z, true) ++o; }
+                    }
                 }
             }
-            for (uint64_t p = l0; p < l1 && o < o_end; p += 4) {
-                int2 v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = (p + u < l1) ? __ldg(ix.stab.ent + p + u) : make_int2(0, INT_MIN);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (p + u < l1 && v[u].y >= qs) emit<MODE>(ix, out, o++, (uint32_t)v[u].x, v[u].y);
+            return;
+        }
+        const uint64_t clen64 = (uint64_t)plen + llen;
+        // queries with very many candidates: the whole warp sweeps one query at a time
+        uint32_t longm = __ballot_sync(FULL_MASK, clen64 > QF_LONG_RUN);
+        while (longm) {
+            const int src = __ffs(longm) - 1;
+            longm &= longm - 1;
+            const uint32_t bpl = __shfl_sync(FULL_MASK, plen, src), bll = __shfl_sync(FULL_MASK, llen, src);
+            const uint32_t btm = __shfl_sync(FULL_MASK, topm1, src);
+            const uint64_t bl0 = __shfl_sync(FULL_MASK, l0, src);
+            const int32_t bqs = __shfl_sync(FULL_MASK, qs, src);
+            uint64_t bo = __shfl_sync(FULL_MASK, o, src);
+            const uint64_t bo_end = __shfl_sync(FULL_MASK, o_end, src);
+            const uint64_t bn = (uint64_t)bpl + bll;
+            for (uint64_t cb = 0; cb < bn && bo < bo_end; cb += 32) {
+                const uint64_t c = cb + lane;
+                uint32_t pos = 0; int32_t end = INT_MIN, val = 0; bool fl = false;
+                if (c < bn) {
+                    if (c < bpl) { pos = btm - (uint32_t)c; end = ld_nc(ix.ends + pos); }
+                    else { const int4 r = ld_stab_record(ix.stab, bl0 + (c - bpl)); pos = (uint32_t)r.x; end = r.y; val = r.z; fl = rec16; }
+                }
+                const bool hit = c < bn && end >= bqs;
+                const uint32_t hm = __ballot_sync(FULL_MASK, hit);
+                if (hit) { SIB_STAB_EMIT(bo + __popc(hm & lanemask_lt()), pos, end, val, fl) }
+                bo += __popc(hm);
             }
         }
+        // everything else pooled over the warp
+        const uint32_t pooled_c = clen64 > QF_LONG_RUN ? 0u : (uint32_t)clen64;
+        uint32_t cincl = pooled_c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t x = __shfl_up_sync(FULL_MASK, cincl, d);
+            if ((int)lane >= d) cincl += x;
+        }
+        const uint32_t ctotal = __shfl_sync(FULL_MASK, cincl, 31);
+        if (ctotal) {
+            s_pre[w][lane] = cincl;
+            s_top[w][lane] = 0;               // hits of each query written so far
+            __syncwarp();
+            for (uint32_t kb = 0; kb < ctotal; kb += 32u) {
+                const uint32_t k = kb + lane;
+                const bool valid = k < ctotal;
+                uint32_t own = 0;
+                if (valid) {
+#pragma unroll
+                    for (uint32_t step = 16; step; step >>= 1) own += (s_pre[w][own + step - 1u] <= k) ? step : 0u;
+                }
+                const uint32_t excl = own ? s_pre[w][own - 1u] : 0u;
+                // the owner's query lives in lane `own`: read it from there
+                const uint32_t o_pl = __shfl_sync(FULL_MASK, plen, own), o_tm = __shfl_sync(FULL_MASK, topm1, own);
+                const uint64_t o_l0 = __shfl_sync(FULL_MASK, l0, own), o_at = __shfl_sync(FULL_MASK, o, own);
+                const int32_t o_qs = __shfl_sync(FULL_MASK, qs, own);
+                uint32_t pos = 0; int32_t end = INT_MIN, val = 0; bool fl = false;
+                bool hit = false;
+                if (valid) {
+                    const uint32_t c = k - excl;
+                    SIB_STAB_CAND(c, o_pl, o_tm, o_l0, pos, end, val, fl)
+                    hit = end >= o_qs;
+                }
+                const uint32_t hm = __ballot_sync(FULL_MASK, hit);
+                // lanes of one query are neighbours: its segment starts at lane seg0 of this step
+                const uint32_t seg0 = excl > kb ? excl - kb : 0u;
+                const uint32_t seg = hm & ~((1u << seg0) - 1u);
+                const uint32_t carry = valid ? s_top[w][own] : 0u;
+                if (hit) { SIB_STAB_EMIT(o_at + carry + __popc(seg & lanemask_lt()), pos, end, val, fl) }
+                __syncwarp();
+                const uint32_t next_own = __shfl_down_sync(FULL_MASK, own, 1);
+                const bool last = valid && (lane == 31u || k + 1u >= ctotal || next_own != own);
+                if (last) s_top[w][own] = carry + __popc(seg & (lanemask_lt() | (1u << lane)));
+                __syncwarp();
+            }
+        }
+#undef SIB_STAB_CAND
+#undef SIB_STAB_EMIT
         return;
     }
     uint32_t i = (more && top) ? top - 1u : NONE32;

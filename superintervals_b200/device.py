@@ -141,7 +141,8 @@ class DeviceIndex:
         if self._L.siIndexStabInfo(self._ix, C.byref(si)):
             raise RuntimeError("siIndexStabInfo: index not built")
         return {"state": int(si.state), "shift": int(si.shift), "lists": int(si.lists), "entries": int(si.entries),
-                "bytes": int(si.entries) * 8 + (int(si.lists) + 1) * 8 if si.state == 1 else 0}
+                "record_bytes": int(si.record_bytes),
+                "bytes": int(si.entries) * int(si.record_bytes) + (int(si.lists) + 1) * 8 if si.state == 1 else 0}
 
     def read_timings(self, max_records=4096):
         """[(kernel name, ms), ...] recorded since the last read (needs set_option(OPT_TIMING, 1))."""
