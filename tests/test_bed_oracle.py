@@ -1,0 +1,41 @@
+"""CPU: the two restatements of the reference's BED loader loop (reference test/bench.cpp:67-102) agree --
+oracle/bed_oracle.py (the checker of the device tokeniser) and oracle/bed_cpu.cpp (the timed CPU
+baseline of tools/bed_bench.py) -- and the library exports the ingest entry points."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from oracle import bed_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_python_and_cpp_restatements_agree_on_well_formed_bed():
+    so = os.path.join(ROOT, "oracle", "libsi_bedcpu.so")
+    if not os.path.exists(so):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "libsi_bedcpu.so"])
+    L = C.CDLL(so)
+    L.si_bed_parse_cpu.restype = C.c_size_t
+    L.si_bed_parse_cpu.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    rng = np.random.default_rng(3)
+    rows = []
+    for i in range(5000):
+        s = int(rng.integers(0, 1_000_000)); e = s + int(rng.integers(-50, 5000))
+        rows.append(f"chr{int(rng.integers(1, 6))}\t{s}\t{e}" + ("\tx\t0\t+" if i % 4 == 0 else ""))
+    text = ("\n".join(rows) + "\n").encode()
+    names, contig, starts, ends, lines, skipped = bed_oracle.parse_bed(text, normalize=True)
+    n = len(rows)
+    cs, ce, cc = (np.empty(n, np.int32) for _ in range(3))
+    m = L.si_bed_parse_cpu(text, len(text), cs.ctypes.data, ce.ctypes.data, cc.ctypes.data, n)
+    assert m == n == lines and skipped == 0
+    assert np.array_equal(cs, starts) and np.array_equal(ce, ends) and np.array_equal(cc, contig)
+
+
+def test_stoi_rules_of_the_oracle():
+    text = b"a\t 12\t13x\nb\t+7\t-2\nc\tz\t1\nd\t1\t\n\ne\t2147483648\t1\nf\t00012\t0013\textra\n"
+    names, contig, starts, ends, lines, skipped = bed_oracle.parse_bed(text)
+    assert names == ["a", "b", "f"] and starts.tolist() == [12, 7, 12] and ends.tolist() == [13, -2, 13]
+    assert lines == 7 and skipped == 4
+    assert bed_oracle.parse_bed(text, normalize=True, end_shift=-1)[2:4][1].tolist() == [12, 6, 12]
