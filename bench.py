@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--partition", action="store_true", help="cells kernel through the locality partition (SI_OPT_CELLS_DIRECT_BYTES=1)")
     ap.add_argument("--sv-intervals", type=int, default=4_000_000)
     ap.add_argument("--sv-queries", type=int, default=4_000_000)
+    ap.add_argument("--bed-lines", type=int, default=20_000_000, help="records of the secondary BED-ingest measurement (0 = skip)")
     return ap.parse_args()
 
 
@@ -139,6 +140,27 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
                 "sm_max_mhz": self.max_sm, "power_w_max": max(r[3] for r in rows) if rows else None,
                 "samples": len(rows), "reasons": reasons, "source": "NVML polled every ~2 ms inside the timed regions"}
+
+
+def bind_near_gpu(gpu_index):
+    """Multi-GPU runs: keep this rank's threads (and therefore its pinned host buffers, first touch) on
+    the CPUs NVML reports as local to its GPU, so that eight ranks do not pull their PCIe traffic
+    through one socket's memory. Returns the CPU list used, or None when nothing was changed."""
+    try:
+        import pynvml as nv
+        import torch
+        nv.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+        h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        words = nv.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        near = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        use = near & os.sched_getaffinity(0)
+        if use and use != os.sched_getaffinity(0):
+            os.sched_setaffinity(0, use)
+            return sorted(use)
+    except Exception:   # noqa: BLE001
+        pass
+    return None
 
 
 # ---------------------------------------------------------------------------------------
@@ -311,6 +333,33 @@ def bench_search_values(a, torch, L, _lib, rank):
     return out
 
 
+def bench_bed_ingest(a, rank):
+    """Secondary line: the step before the path -- BED text to columns (siParseBed) -- beside the
+    reference's loader loop (test/bench.cpp:67-102, restated in oracle/bed_cpu.cpp) on one host thread."""
+    from superintervals_b200 import workloads as W
+    from superintervals_b200.bed import parse_bed
+    n = a.bed_lines
+    text, cid, s, e = W.bed_text(n)
+    parse_bed(text[: 26 * 1000])
+    t0 = time.perf_counter(); t = parse_bed(text, True, -1); dt = time.perf_counter() - t0
+    ok = bool(len(t.starts) == n and np.array_equal(t.starts, s.astype(np.int32)) and np.array_equal(t.ends, (e - 1).astype(np.int32)))
+    out = {"workload": f"{n/1e6:g}M BED records ({text.size/1e6:.0f} MB of text, 24 contigs) -> contig/start/end columns",
+           "value": n / dt, "unit": "lines/s", "seconds": dt, "text_gb_per_s": text.size / dt / 1e9, "equals_generator": ok,
+           "note": "host text buffer in, host columns out: H2D of the text and D2H of the columns are inside"}
+    so = os.path.join(ROOT, "oracle", "libsi_bedcpu.so")
+    if rank == 0 and not a.no_cpu_baseline and os.path.exists(so):
+        L = C.CDLL(so)
+        L.si_bed_parse_cpu.restype = C.c_size_t
+        L.si_bed_parse_cpu.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        m = min(n, 4_000_000)
+        cs, ce, cc = (np.empty(m, np.int32) for _ in range(3))
+        t0 = time.perf_counter(); got = L.si_bed_parse_cpu(text.ctypes.data, 26 * m, cs.ctypes.data, ce.ctypes.data, cc.ctypes.data, m); dc = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": got / dc, "unit": "lines/s", "cores": 1, "kind": "port",
+                               "sample": f"first {m} lines; getline + istringstream + stoi loop of test/bench.cpp:67-102 (oracle/bed_cpu.cpp)",
+                               "matches_device": bool(np.array_equal(cs, t.starts[:m]) and np.array_equal(ce - 1, t.ends[:m]))}
+    return out
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -327,6 +376,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: superintervals_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    near_cpus = bind_near_gpu(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = _lib.lib()
@@ -440,6 +490,10 @@ def main():
     if world == 1 and not a.no_search_values:
         sv = bench_search_values(a, torch, L, _lib, rank)
 
+    bed = None
+    if world == 1 and not a.no_search_values and a.bed_lines > 0:
+        bed = bench_bed_ingest(a, rank)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -511,11 +565,12 @@ def main():
             "e2e": {"value": world * nq / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * nq,
                     "d2h_bytes_per_step": 8 * nq, "ms_per_step": e2e_s * 1e3,
                     "pcie_gbs_each_way": 8 * nq / e2e_s / 1e9,
-                    "call": "countOverlapsBatch(si, qs, qe, n, size_t* counts) with pinned host buffers"},
+                    "call": "countOverlapsBatch(si, qs, qe, n, size_t* counts) with pinned host buffers",
+                    "rank0_cpus_near_gpu": (len(near_cpus) if near_cpus else None)},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "cpu_baseline": cpu_baseline, "parity": parity, "build_ms": build_ms,
             "shard_hits": shard_hits, "shard_csr_base": shard_base, "device_bytes": ix.device_bytes,
-            "search_values": sv}
+            "search_values": sv, "bed_ingest": bed}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -100,7 +100,9 @@ void   findOverlaps(cSuperIntervals* si, int32_t start, int32_t end, int32_t* fo
  * intersection / difference / symmetricDifference query `other` through its index: it must be
  * indexed (symmetricDifference: both). Here: device sort + head flags + scan + scatter
  * (merge / unique / gaps), A's stored intervals as one query batch against B's index
- * (intersection / difference), elementwise count + scan + scatter (expand / flank). */
+ * (intersection / difference), elementwise count + scan + scatter (expand / flank).
+ * Like the queries, an operation that queries `other` uses that handle's device staging: do
+ * not run two of them on the same `other` concurrently. */
 typedef int32_t (*cCombineFn)(int32_t, int32_t);                                           /* ref:128 */
 cSuperIntervals* mergeOverlaps(const cSuperIntervals* si, cCombineFn combine);            /* ref:264 */
 cSuperIntervals* intervalGaps(const cSuperIntervals* si, int32_t lo, int32_t hi, int32_t fill);   /* ref:271 */

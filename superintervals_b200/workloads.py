@@ -140,3 +140,23 @@ def shard_range(n, rank, world):
     base, rem = divmod(n, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def bed_text(n, seed=1, contigs=24):
+    """n BED records 'chrNN\\tSSSSSSSSS\\tEEEEEEEEE\\n' as a uint8 array (26 bytes per line; the numbers are
+    zero-padded, which std::stoi reads the same), plus the generating columns (contig number, start, end)."""
+    rng = np.random.default_rng(seed)
+    cid = rng.integers(1, contigs + 1, n)
+    s = rng.integers(0, 249_000_000, n)
+    e = s + rng.integers(1, 10_000, n)
+    buf = np.empty((n, 26), np.uint8)
+    buf[:, 0:3] = np.frombuffer(b"chr", np.uint8)
+    buf[:, 3] = 48 + cid // 10
+    buf[:, 4] = 48 + cid % 10
+    buf[:, 5] = 9
+    for k in range(9):
+        buf[:, 6 + k] = 48 + (s // 10 ** (8 - k)) % 10
+        buf[:, 16 + k] = 48 + (e // 10 ** (8 - k)) % 10
+    buf[:, 15] = 9
+    buf[:, 25] = 10
+    return buf.reshape(-1), cid, s, e

@@ -1,6 +1,6 @@
 """CPU: the two restatements of the reference's BED loader loop (reference test/bench.cpp:67-102) agree --
 oracle/bed_oracle.py (the checker of the device tokeniser) and oracle/bed_cpu.cpp (the timed CPU
-baseline of tools/bed_bench.py) -- and the library exports the ingest entry points."""
+baseline of bench.py's bed_ingest line)."""
 import ctypes as C
 import os
 
