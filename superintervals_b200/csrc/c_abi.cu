@@ -99,12 +99,18 @@ private:
     bool stop_ = false;
 };
 
-void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+void copy_to_output(void* dst, const void* src, size_t n);   // host_copy.cpp: non-temporal stores
+
+// to_output: dst is a caller's result array (written once) -> stream the stores past the caches
+void parallel_memcpy(void* dst, const void* src, size_t bytes, bool to_output = false) {
     if (bytes < ((size_t)1 << 20)) { memcpy(dst, src, bytes); return; }
     HostPool::get().run([&](int t, int n) {
         const size_t per = ((bytes + n - 1) / n + 4095) & ~(size_t)4095;
         const size_t a = (size_t)t * per;
-        if (a < bytes) memcpy((char*)dst + a, (const char*)src + a, bytes - a < per ? bytes - a : per);
+        if (a >= bytes) return;
+        const size_t len = bytes - a < per ? bytes - a : per;
+        if (to_output) copy_to_output((char*)dst + a, (const char*)src + a, len);
+        else memcpy((char*)dst + a, (const char*)src + a, len);
     });
 }
 
@@ -150,7 +156,7 @@ int copy_d2h(siIndex* ix, void* dst, const void* src_dev, size_t bytes, cudaStre
             SIB_CHECK(cudaEventRecord(ix->e_stage[(k + 1) & 1], s));
         }
         SIB_CHECK(cudaEventSynchronize(ix->e_stage[k & 1]));
-        parallel_memcpy((char*)dst + k * STAGE_BYTES, stage[k & 1], len(k));
+        parallel_memcpy((char*)dst + k * STAGE_BYTES, stage[k & 1], len(k), true);
     }
     return 0;
 }
