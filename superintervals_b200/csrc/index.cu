@@ -121,7 +121,7 @@ using namespace sib;
     } while (0)
 
 size_t siIndex::device_bytes() const {
-    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &esort, &eall, &grid_tab, &cells_s, &cells_e, &stab_off, &stab_ent, &stab_cnt, &b_in_s, &b_in_e, &b_in_v,
+    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &esort, &eall, &grid_tab, &cells_s, &cells_e, &stab_off, &stab_hdr, &stab_ent, &stab_cnt, &b_in_s, &b_in_e, &b_in_v,
                            &b_kA, &b_kB, &b_vA, &b_vB, &b_ws, &small, &q_A, &q_B,
                            &q_ws, &scan_status, &h_qs, &h_qe, &h_counts, &h_offsets, &h_out, &h_cov};
     size_t s = 0;
@@ -163,7 +163,7 @@ IndexView view_of(const siIndex* ix) {
     v.cells_s = RankCells{ix->cells_s.as<uint4>(), ix->cm_s.lo, ix->cm_s.span, ix->cm_s.shift, ix->cm_s.fmt};
     v.cells_e = RankCells{ix->cells_e.as<uint4>(), ix->cm_e.lo, ix->cm_e.span, ix->cm_e.shift, ix->cm_e.fmt};
     const bool stab = ix->stab_state == 1 && ix->stab_enabled;
-    v.stab = StabLists{ix->stab_off.as<uint64_t>(), stab ? ix->stab_ent.p : nullptr, ix->stab_rec16 ? 1u : 0u, ix->stab_kshift, ix->stab_nlists};
+    v.stab = StabLists{ix->stab_hdr.as<uint4>(), stab ? ix->stab_ent.p : nullptr, ix->stab_rec16 ? 1u : 0u, ix->stab_kshift, ix->stab_nlists};
     v.n = ix->n;
     v.wellformed = ix->wellformed ? 1u : 0u;
     return v;
@@ -281,7 +281,7 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
     if (ensure_small(ix)) return last_error_code();
     const size_t pad_b = (size_t)ix->n_padded * 4;
     if (ix->starts.ensure(pad_b) || ix->ends.ensure(pad_b) || ix->branch.ensure(pad_b) ||
-        ix->values.ensure(n * 4) || ix->perm.ensure(n * 4))
+        ix->values.ensure(pad_b) || ix->perm.ensure(n * 4))   // values padded: the fill reads aligned 128-bit groups
         return last_error_code();
     uint32_t* d_flags = ix->small.as<uint32_t>();
     const int cap = ix->sm_count * 16;
@@ -526,7 +526,7 @@ int ensure_stab_lists(siIndex* ix, cudaStream_t s) {
     SIB_CHECK(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long) * QK_STAB_SPACINGS, s));
     const IndexView v = view_of(ix);
     SIB_LAUNCH((qk_stab_lists_kernel<false, false>), (nl0 + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, QK_STAB_SHIFT0, nl0,
-               ix->stab_cnt.as<uint32_t>(), (const uint64_t*)nullptr, (void*)nullptr);
+               ix->stab_cnt.as<uint32_t>(), (const uint64_t*)nullptr, (void*)nullptr, (uint4*)nullptr);
     SIB_LAUNCH(qk_stab_totals_kernel, grid_for(nl0, QK_THREADS, ix->sm_count * 8), QK_THREADS, 0, s,
                ix->stab_cnt.as<uint32_t>(), nl0, d_tot);
     unsigned long long tot[QK_STAB_SPACINGS];
@@ -540,18 +540,18 @@ int ensure_stab_lists(siIndex* ix, cudaStream_t s) {
     const uint32_t nl = (n >> kshift) + 1;
     if (k > 0)   // the kept checkpoints' counts, contiguous
         SIB_LAUNCH((qk_stab_lists_kernel<false, false>), (nl + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, kshift, nl,
-                   ix->stab_cnt.as<uint32_t>(), (const uint64_t*)nullptr, (void*)nullptr);
+                   ix->stab_cnt.as<uint32_t>(), (const uint64_t*)nullptr, (void*)nullptr, (uint4*)nullptr);
     // long lists (dense data): nearly every record read is a hit, so the value rides in the record
     const bool rec16 = tot[k] >= 16ull * nl;
-    if (ix->stab_off.ensure(((size_t)nl + 1) * 8) || ix->stab_ent.ensure((size_t)(tot[k] ? tot[k] : 1) * (rec16 ? 16 : 8))) return last_error_code();
+    if (ix->stab_hdr.ensure((size_t)nl * 16) || ix->stab_off.ensure(((size_t)nl + 1) * 8) || ix->stab_ent.ensure((size_t)(tot[k] ? tot[k] : 1) * (rec16 ? 16 : 8))) return last_error_code();
     int rc = siScanDevice(ix, ix->stab_cnt.as<uint32_t>(), nl, ix->stab_off.as<uint64_t>(), (void*)s);
     if (rc) return rc;
     if (rec16)
         SIB_LAUNCH((qk_stab_lists_kernel<true, true>), (nl + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, kshift, nl,
-                   (uint32_t*)nullptr, ix->stab_off.as<uint64_t>(), ix->stab_ent.p);
+                   (uint32_t*)nullptr, ix->stab_off.as<uint64_t>(), ix->stab_ent.p, ix->stab_hdr.as<uint4>());
     else
         SIB_LAUNCH((qk_stab_lists_kernel<true, false>), (nl + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, kshift, nl,
-                   (uint32_t*)nullptr, ix->stab_off.as<uint64_t>(), ix->stab_ent.p);
+                   (uint32_t*)nullptr, ix->stab_off.as<uint64_t>(), ix->stab_ent.p, ix->stab_hdr.as<uint4>());
     ix->stab_rec16 = rec16;
     ix->stab_kshift = kshift;
     ix->stab_nlists = nl;
@@ -617,7 +617,7 @@ void siIndexDestroy(siIndex* ix) {
     if (!ix) return;
     DeviceGuard g(ix->device);
     DevBuf* all[] = {&ix->starts, &ix->ends, &ix->values, &ix->branch, &ix->perm, &ix->tree, &ix->esort, &ix->eall, &ix->grid_tab,
-                     &ix->cells_s, &ix->cells_e, &ix->stab_off, &ix->stab_ent, &ix->stab_cnt,
+                     &ix->cells_s, &ix->cells_e, &ix->stab_off, &ix->stab_hdr, &ix->stab_ent, &ix->stab_cnt,
                      &ix->b_in_s, &ix->b_in_e, &ix->b_in_v, &ix->b_kA, &ix->b_kB, &ix->b_vA, &ix->b_vB, &ix->b_ws,
                      &ix->small, &ix->q_A, &ix->q_B, &ix->q_ws, &ix->scan_status, &ix->h_qs,
                      &ix->h_qe, &ix->h_counts, &ix->h_offsets, &ix->h_out, &ix->h_cov};

@@ -60,7 +60,7 @@ struct siIndex {
     size_t cells_direct_bytes = 0;                 // cells up to this size answer unpartitioned batches (0: 60 % of L2)
     size_t l2_bytes = 0;
     // stab lists (StabLists in query_kernels.cuh), made by the first CSR fill that can use them
-    sib::DevBuf stab_off, stab_ent, stab_cnt;
+    sib::DevBuf stab_off, stab_hdr, stab_ent, stab_cnt;   // scan offsets (build only), list headers, records, counts
     uint32_t stab_kshift = 0, stab_nlists = 0;
     bool stab_rec16 = false;                       // 16-byte (position, end, value) records instead of 8-byte (position, end)
     int stab_state = 0;                            // 0 = not tried yet, 1 = built, 2 = over budget (the fill walks)

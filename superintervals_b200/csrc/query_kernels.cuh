@@ -60,12 +60,14 @@ struct RankCells {
 // as records in descending position: 8-byte (position, end) on sparse data, where few records are
 // read per query and only the hits fetch their payload, or 16-byte (position, end, value, -) when
 // the lists are long (>= 16 records on average: nearly every record is a hit and a gather per hit
-// would cost more than carrying the value). Any query whose candidates end at
+// would cost more than carrying the value). Every list is padded to a multiple of four records
+// (pad: end = INT_MIN, never a hit), so it starts on a 32-byte boundary and four 8-byte records
+// travel in one 256-bit load; one 16-byte header per list holds its first record and its length. Any query whose candidates end at
 // top = #{starts < qs} with top >> kshift == b has qs > starts[(b << kshift) - 1], so its hits
 // below the checkpoint are exactly the entries of L(b) with end >= qs: one sequential list read
 // instead of the branch-array walk's chain of dependent loads.
 struct StabLists {
-    const uint64_t* off;   // nlists + 1 offsets into ent
+    const uint4* hdr;      // per list: first record (64 bits: x | y << 32), record count (z); lists start on 32-byte boundaries
     const void* ent;       // int2 (position, end) or int4 (position, end, value, 0) records; nullptr = not built
     uint32_t rec16;        // 1: 16-byte records
     uint32_t kshift;
@@ -697,12 +699,13 @@ qk_fill_kernel(IndexView ix, QueryRecords rec, uint32_t nq, const uint64_t* __re
 template <bool FILL, bool REC16>
 __global__ void __launch_bounds__(QK_THREADS)
 qk_stab_lists_kernel(IndexView ix, uint32_t kshift, uint32_t nlists, uint32_t* __restrict__ counts,
-                     const uint64_t* __restrict__ off, void* __restrict__ ent_out) {
+                     const uint64_t* __restrict__ off, void* __restrict__ ent_out, uint4* __restrict__ hdr) {
     const uint64_t t64 = (uint64_t)blockIdx.x * QK_THREADS + threadIdx.x;
     if (t64 >= nlists) return;
     const uint32_t b = (uint32_t)t64;
     uint32_t c = 0;
-    uint64_t o = FILL ? off[b] : 0;
+    const uint64_t o0 = FILL ? off[b] : 0;
+    uint64_t o = o0;
     if (b > 0) {
         uint32_t i = (b << kshift) - 1u;
         const int32_t sv = ld_nc(ix.starts + i);
@@ -737,7 +740,16 @@ qk_stab_lists_kernel(IndexView ix, uint32_t kshift, uint32_t nlists, uint32_t* _
             }
         }
     }
-    if (!FILL) counts[b] = c;
+    if (!FILL) {
+        counts[b] = (c + 3u) & ~3u;          // padded: every list starts on a 32-byte boundary
+    } else {
+        const uint32_t len = (uint32_t)(o - o0);
+        for (uint64_t pad = o; pad < o0 + ((len + 3u) & ~3u); ++pad) {
+            if (REC16) reinterpret_cast<int4*>(ent_out)[pad] = make_int4(0, INT_MIN, 0, 0);
+            else reinterpret_cast<int2*>(ent_out)[pad] = make_int2(0, INT_MIN);
+        }
+        hdr[b] = make_uint4((uint32_t)o0, (uint32_t)(o0 >> 32), len, 0u);
+    }
 }
 
 // totals[k] = sum of counts[b] over the checkpoints a spacing of 2^(QK_STAB_SHIFT0 + k) keeps (b % 2^k == 0)
@@ -887,8 +899,9 @@ qk_fill_runs_kernel(IndexView ix, QueryRecords rec, uint32_t nq, const uint64_t*
         if (more && top) {
             const uint32_t b = top >> ix.stab.kshift;
             plen = top - (b << ix.stab.kshift);
-            l0 = __ldg(ix.stab.off + b);
-            llen = (uint32_t)(__ldg(ix.stab.off + b + 1) - l0);   // a list holds fewer than n < 2^32 records
+            const uint4 h = __ldg(ix.stab.hdr + b);                // first record and length in one load
+            l0 = (uint64_t)h.x | ((uint64_t)h.y << 32);
+            llen = h.z;
         }
         const uint32_t topm1 = top - 1u;
         const bool rec16 = ix.stab.rec16 != 0;   // list records carry their value
@@ -912,10 +925,23 @@ qk_fill_runs_kernel(IndexView ix, QueryRecords rec, uint32_t nq, const uint64_t*
                     const uint32_t cb = top - plen;
                     while (true) {
                         const int4 e = ld_nc4(ix.ends + base);
-                        if (k >= 3u && e.w >= qs) emit<MODE>(ix, out, o++, base + 3u, e.w);
-                        if (k >= 2u && e.z >= qs) emit<MODE>(ix, out, o++, base + 2u, e.z);
-                        if (k >= 1u && e.y >= qs) emit<MODE>(ix, out, o++, base + 1u, e.y);
-                        if (e.x >= qs) emit<MODE>(ix, out, o++, base, e.x);
+                        const bool hw = k >= 3u && e.w >= qs, hz = k >= 2u && e.z >= qs, hy = k >= 1u && e.y >= qs, hx = e.x >= qs;
+                        if (MODE == FILL_VALUES) {
+                            // the four payloads are neighbours: one 128-bit load instead of a gather per hit
+                            if (hw || hz || hy || hx) {
+                                const int4 pv = ld_nc4(ix.values + base);   // values[] is padded like ends[]
+                                int32_t* o32 = reinterpret_cast<int32_t*>(out);
+                                if (hw) o32[o++] = pv.w;
+                                if (hz) o32[o++] = pv.z;
+                                if (hy) o32[o++] = pv.y;
+                                if (hx) o32[o++] = pv.x;
+                            }
+                        } else {
+                            if (hw) emit<MODE>(ix, out, o++, base + 3u, e.w);
+                            if (hz) emit<MODE>(ix, out, o++, base + 2u, e.z);
+                            if (hy) emit<MODE>(ix, out, o++, base + 1u, e.y);
+                            if (hx) emit<MODE>(ix, out, o++, base, e.x);
+                        }
                         if (base == cb || o == o_end) break;
                         base -= 4u;
                         k = 3u;
@@ -924,13 +950,27 @@ qk_fill_runs_kernel(IndexView ix, QueryRecords rec, uint32_t nq, const uint64_t*
                 const uint64_t l1 = l0 + llen;
                 if (!rec16) {
                     const int2* __restrict__ ent2 = reinterpret_cast<const int2*>(ix.stab.ent);
-                    for (uint64_t p = l0; p < l1 && o < o_end; p += 4) {   // four records in flight per step
+                    for (uint64_t p = l0; p < l1 && o < o_end; p += 4) {   // four records = one 32-byte sector per step
+                        const CellRec r = ld_cell(reinterpret_cast<const uint4*>(ent2 + p));   // lists are padded to 4
                         int2 v[4];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) v[u] = (p + u < l1) ? __ldg(ent2 + p + u) : make_int2(0, INT_MIN);
+                        for (int u = 0; u < 4; ++u) v[u] = make_int2((int)r.w[2 * u], (int)r.w[2 * u + 1]);
+                        bool h[4];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (p + u < l1 && v[u].y >= qs) emit<MODE>(ix, out, o++, (uint32_t)v[u].x, v[u].y);
+                        for (int u = 0; u < 4; ++u) h[u] = v[u].y >= qs;   // pad records end at INT_MIN
+                        if (MODE == FILL_VALUES) {
+                            int32_t pv[4];                       // the hits' payload gathers leave together
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) pv[u] = h[u] ? ld_nc(ix.values + (uint32_t)v[u].x) : 0;
+                            int32_t* o32 = reinterpret_cast<int32_t*>(out);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (h[u]) o32[o++] = pv[u];
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (h[u]) emit<MODE>(ix, out, o++, (uint32_t)v[u].x, v[u].y);
+                        }
                     }
                 } else {
                     const int4* __restrict__ ent4 = reinterpret_cast<const int4*>(ix.stab.ent);
