@@ -249,7 +249,8 @@ cSuperIntervals* intervalGaps(const cSuperIntervals* si, int32_t lo, int32_t hi,
         unsigned long long* d_count = reinterpret_cast<unsigned long long*>(ix->small.as<uint32_t>() + 32);
         so_gaps_seq_kernel<<<1, 32, 0, st>>>(c.set.s, c.set.e, (uint32_t)m, lo, hi, fill, os.as<int32_t>(), oe.as<int32_t>(),
                                             od.as<int32_t>(), d_count);
-        if (cudaGetLastError() != cudaSuccess) { set_error(cudaGetLastError(), "so_gaps_seq_kernel", __FILE__, __LINE__); return createSuperIntervals(); }
+        const cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) { set_error(le, "so_gaps_seq_kernel", __FILE__, __LINE__); return createSuperIntervals(); }
         note_launch();
         if (read_u64(reinterpret_cast<const uint64_t*>(d_count), &pieces, st)) return createSuperIntervals();
     } else {
@@ -395,6 +396,8 @@ bool intervalSpan(const cSuperIntervals* si, int32_t* lo_out, int32_t* hi_out) {
     if (cudaMemcpyAsync(d_res, res, 8, cudaMemcpyHostToDevice, st) != cudaSuccess) return false;
     const unsigned grid = (unsigned)((n + SO_THREADS - 1) / SO_THREADS < (size_t)ix->sm_count * 8 ? (n + SO_THREADS - 1) / SO_THREADS : (size_t)ix->sm_count * 8);
     so_span_kernel<<<grid, SO_THREADS, 0, st>>>(a.s, a.e, (uint32_t)n, d_res);
+    const cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) { set_error(le, "so_span_kernel", __FILE__, __LINE__); return false; }
     note_launch();
     if (cudaMemcpyAsync(res, d_res, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
         set_error(cudaGetLastError(), "intervalSpan", __FILE__, __LINE__);
