@@ -84,6 +84,9 @@ cSuperIntervals* intersectionPairs(const cSuperIntervals* si, cSuperIntervals* o
  * normalize != 0 swaps start/end when start > end (bench.cpp:89); end_shift is added to every
  * end (-1 turns BED's half-open ends into the inclusive ends the index stores, bench.cpp:210).
  * contig[i] indexes names[], which lists the distinct chroms in order of first appearance.
+ * group_by_contig != 0 reorders the records by contig (stable: line order inside a contig) and fills
+ * contig_offsets[0..n_contigs]: contig k owns records [contig_offsets[k], contig_offsets[k+1]) --
+ * the per-chrom containers of bed-intersect-si.rs:100-123, ready for one index each.
  * All arrays are malloc'd by the library; release with siBedTableFree. Returns 0 or a CUDA error. */
 typedef struct {
     int32_t* contig;
@@ -94,8 +97,9 @@ typedef struct {
     size_t skipped;    /* lines - n */
     char** names;
     size_t n_contigs;
+    size_t* contig_offsets;   /* n_contigs + 1 entries when grouped, else NULL */
 } siBedTable;
-int siParseBed(const char* text, size_t bytes, int normalize, int end_shift, siBedTable* out);
+int siParseBed(const char* text, size_t bytes, int normalize, int end_shift, int group_by_contig, siBedTable* out);
 void siBedTableFree(siBedTable* t);
 
 /* ---- 3. device-resident core ------------------------------------------------------- */

@@ -64,7 +64,7 @@ class siCellsInfo(C.Structure):
 class siBedTable(C.Structure):
     _fields_ = [("contig", C.POINTER(C.c_int32)), ("starts", C.POINTER(C.c_int32)), ("ends", C.POINTER(C.c_int32)),
                 ("n", C.c_size_t), ("lines", C.c_size_t), ("skipped", C.c_size_t),
-                ("names", C.POINTER(C.c_char_p)), ("n_contigs", C.c_size_t)]
+                ("names", C.POINTER(C.c_char_p)), ("n_contigs", C.c_size_t), ("contig_offsets", C.POINTER(C.c_size_t))]
 
 
 class siStabInfo(C.Structure):
@@ -199,7 +199,7 @@ def bind_b200(L):
         L.intersectionPairs.restype = SI
         L.intersectionPairs.argtypes = [SI, SI, C.POINTER(cIndexResult)]
     L.siParseBed.restype = C.c_int
-    L.siParseBed.argtypes = [C.c_char_p, sz, C.c_int, C.c_int, C.POINTER(siBedTable)]
+    L.siParseBed.argtypes = [C.c_char_p, sz, C.c_int, C.c_int, C.c_int, C.POINTER(siBedTable)]
     L.siBedTableFree.argtypes = [C.POINTER(siBedTable)]
     L.siIndexStabInfo.argtypes = [vp, C.POINTER(siStabInfo)]
     L.siIndexStabInfo.restype = C.c_int

@@ -27,11 +27,13 @@ class BedTable:
     ends: np.ndarray          # int32[n]
     lines: int                # lines seen
     skipped: int              # lines without chrom + numeric start + numeric end
+    contig_offsets: np.ndarray = None   # int64[len(names) + 1] when grouped by contig on the device
 
 
-def parse_bed(source, normalize: bool = False, end_shift: int = 0) -> BedTable:
+def parse_bed(source, normalize: bool = False, end_shift: int = 0, group_by_contig: bool = False) -> BedTable:
     """source: a path, bytes, or a uint8 array holding BED text. normalize swaps start/end where
-    start > end (bench.cpp:89); end_shift = -1 stores BED's half-open ends inclusively (bench.cpp:210)."""
+    start > end (bench.cpp:89); end_shift = -1 stores BED's half-open ends inclusively (bench.cpp:210);
+    group_by_contig reorders the records by contig on the device (stable) and fills contig_offsets."""
     if isinstance(source, (bytes, bytearray, memoryview)):
         buf = np.frombuffer(source, np.uint8)
     elif isinstance(source, np.ndarray):
@@ -40,7 +42,8 @@ def parse_bed(source, normalize: bool = False, end_shift: int = 0) -> BedTable:
         buf = np.fromfile(source, np.uint8)
     L = _lib.lib()
     t = _lib.siBedTable()
-    rc = L.siParseBed(C.cast(buf.ctypes.data, C.c_char_p), buf.size, int(bool(normalize)), int(end_shift), C.byref(t))
+    rc = L.siParseBed(C.cast(buf.ctypes.data, C.c_char_p), buf.size, int(bool(normalize)), int(end_shift),
+                      int(bool(group_by_contig)), C.byref(t))
     _lib.check("siParseBed")
     if rc:
         raise RuntimeError(f"siParseBed failed with CUDA error {rc}")
@@ -48,6 +51,8 @@ def parse_bed(source, normalize: bool = False, end_shift: int = 0) -> BedTable:
     take = lambda p: np.ctypeslib.as_array(p, shape=(n,)).copy() if n else np.zeros(0, np.int32)
     out = BedTable([t.names[k].decode() for k in range(int(t.n_contigs))], take(t.contig), take(t.starts), take(t.ends),
                    int(t.lines), int(t.skipped))
+    if group_by_contig and t.contig_offsets:
+        out.contig_offsets = np.ctypeslib.as_array(t.contig_offsets, shape=(int(t.n_contigs) + 1,)).astype(np.int64)
     L.siBedTableFree(C.byref(t))
     return out
 
@@ -55,6 +60,9 @@ def parse_bed(source, normalize: bool = False, end_shift: int = 0) -> BedTable:
 def split_by_contig(table: BedTable) -> Dict[str, Tuple[np.ndarray, np.ndarray]]:
     """{chrom: (starts, ends)} in line order inside each chrom -- the per-contig containers of
     bed-intersect-si.rs:100-123, ready for one index per contig (genome.GenomeIndex)."""
+    if table.contig_offsets is not None:          # grouped on the device: slices, no host sort
+        b = table.contig_offsets
+        return {name: (table.starts[b[k]:b[k + 1]], table.ends[b[k]:b[k + 1]]) for k, name in enumerate(table.names)}
     order = np.argsort(table.contig, kind="stable")
     bounds = np.searchsorted(table.contig[order], np.arange(len(table.names) + 1))
     return {name: (table.starts[order[bounds[k]:bounds[k + 1]]], table.ends[order[bounds[k]:bounds[k + 1]]])

@@ -15,6 +15,8 @@
 //                       in a small open-addressing table (atomicCAS / atomicMin)
 //   5. host             names the distinct chroms in order of first appearance (a handful)
 //   6. bd_finish        valid lines -> scan -> compact (contig id, start, end) in line order
+//   7. (optional)       group by contig: stable radix sort of the record numbers by contig id, gather,
+//                       per-contig offsets -- the per-chrom containers of the reference's callers
 #include "../../include/superintervals_b200.h"
 
 #include "common.cuh"
@@ -28,6 +30,8 @@
 #include <vector>
 
 using namespace sib;
+
+extern "C" int si_b200_stable_order_(siIndex* ix, const int32_t* d_key, size_t n, int key_bits, uint32_t* d_perm, void* stream);
 
 namespace {
 
@@ -186,8 +190,34 @@ bd_finish(const unsigned long long* __restrict__ hash, const int32_t* __restrict
     out_e[o] = ends[l];
 }
 
+// group == 1: records reordered by contig (stable), perm from the build's radix sort
+__global__ void __launch_bounds__(BD_THREADS)
+bd_group_kernel(const uint32_t* __restrict__ perm, const int32_t* __restrict__ c, const int32_t* __restrict__ s,
+                const int32_t* __restrict__ e, uint64_t n, int32_t* __restrict__ gc, int32_t* __restrict__ gs,
+                int32_t* __restrict__ ge) {
+    const uint64_t i = (uint64_t)blockIdx.x * BD_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = perm[i];
+    gc[i] = c[j];
+    gs[i] = s[j];
+    ge[i] = e[j];
+}
+
+// offsets[k] = first record of contig k in the grouped columns (k = 0..contigs; offsets[contigs] = n)
+__global__ void bd_contig_offsets_kernel(const int32_t* __restrict__ gc, uint64_t n, uint32_t contigs,
+                                         unsigned long long* __restrict__ offsets) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > contigs) return;
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (gc[mid] < (int32_t)k) lo = mid + 1; else hi = mid;
+    }
+    offsets[k] = lo;
+}
+
 struct Bufs {
-    DevBuf b[14];
+    DevBuf b[20];
     ~Bufs() { for (auto& x : b) x.release(); }
 };
 
@@ -207,7 +237,7 @@ int scan_u32(siIndex* ix, DevBuf& cnt, uint64_t n, DevBuf& off, uint64_t* total)
     return 0;
 }
 
-int parse_impl(siIndex* ix, const char* text, size_t bytes, int normalize, int end_shift, siBedTable* out) {
+int parse_impl(siIndex* ix, const char* text, size_t bytes, int normalize, int end_shift, int group, siBedTable* out) {
     cudaStream_t st = ix->own_stream;
     Bufs B;
     DevBuf &d_text = B.b[0], &cnt = B.b[1], &off = B.b[2], &line_at = B.b[3], &hash = B.b[4], &ds = B.b[5], &de = B.b[6],
@@ -273,11 +303,33 @@ int parse_impl(siIndex* ix, const char* text, size_t bytes, int normalize, int e
     SIB_CHECK(cudaMemcpyAsync(ids.p, h_ids.data(), (size_t)BD_TABLE * 4, cudaMemcpyHostToDevice, st));
     BD_LAUNCH(bd_finish, lines, st, hash.as<unsigned long long>(), ds.as<int32_t>(), de.as<int32_t>(), valid.as<uint32_t>(),
               voff.as<uint64_t>(), lines, table.as<ChromSlot>(), ids.as<int32_t>(), oc.as<int32_t>(), os.as<int32_t>(), oe.as<int32_t>());
+    const void *fc = oc.p, *fs = os.p, *fe = oe.p;
+    if (group) {
+        // per-contig containers (bed-intersect-si.rs:100-123): a stable sort of the record numbers by
+        // contig id, the columns gathered through it, and where each contig begins
+        DevBuf &perm = B.b[14], &gc = B.b[15], &gs = B.b[16], &ge = B.b[17], &coff = B.b[18];
+        if (perm.ensure(n * 4) || gc.ensure(n * 4) || gs.ensure(n * 4) || ge.ensure(n * 4) || coff.ensure((seen.size() + 1) * 8)) return last_error_code();
+        int bits = 1;
+        while (((size_t)1 << bits) < seen.size()) ++bits;
+        rc = si_b200_stable_order_(ix, oc.as<int32_t>(), n, bits, perm.as<uint32_t>(), st);
+        if (rc) return rc;
+        BD_LAUNCH(bd_group_kernel, n, st, perm.as<uint32_t>(), oc.as<int32_t>(), os.as<int32_t>(), oe.as<int32_t>(), (uint64_t)n,
+                  gc.as<int32_t>(), gs.as<int32_t>(), ge.as<int32_t>());
+        bd_contig_offsets_kernel<<<(unsigned)((seen.size() + 1 + 127) / 128), 128, 0, st>>>(gc.as<int32_t>(), (uint64_t)n, (uint32_t)seen.size(),
+                                                                                          coff.as<unsigned long long>());
+        SIB_CHECK_LAUNCH();
+        note_launch();
+        out->contig_offsets = (size_t*)malloc((seen.size() + 1) * sizeof(size_t));
+        if (!out->contig_offsets) { set_error_msg(cudaErrorMemoryAllocation, "siParseBed: out of host memory"); return cudaErrorMemoryAllocation; }
+        static_assert(sizeof(size_t) == 8, "LP64 only");
+        SIB_CHECK(cudaMemcpyAsync(out->contig_offsets, coff.p, (seen.size() + 1) * 8, cudaMemcpyDeviceToHost, st));
+        fc = gc.p; fs = gs.p; fe = ge.p;
+    }
     out->contig = (int32_t*)malloc(n * 4);
     out->starts = (int32_t*)malloc(n * 4);
     out->ends = (int32_t*)malloc(n * 4);
     if (!out->contig || !out->starts || !out->ends) { set_error_msg(cudaErrorMemoryAllocation, "siParseBed: out of host memory"); return cudaErrorMemoryAllocation; }
-    if (copy_d2h(ix, out->contig, oc.p, n * 4, st) || copy_d2h(ix, out->starts, os.p, n * 4, st) || copy_d2h(ix, out->ends, oe.p, n * 4, st))
+    if (copy_d2h(ix, out->contig, fc, n * 4, st) || copy_d2h(ix, out->starts, fs, n * 4, st) || copy_d2h(ix, out->ends, fe, n * 4, st))
         return last_error_code();
     return 0;
 }
@@ -286,13 +338,13 @@ int parse_impl(siIndex* ix, const char* text, size_t bytes, int normalize, int e
 
 extern "C" {
 
-int siParseBed(const char* text, size_t bytes, int normalize, int end_shift, siBedTable* out) {
+int siParseBed(const char* text, size_t bytes, int normalize, int end_shift, int group_by_contig, siBedTable* out) {
     if (!out) return cudaErrorInvalidValue;
     memset(out, 0, sizeof(*out));
     if (!text || bytes == 0) return 0;
     siIndex* ix = siIndexCreate();
     if (!ix) return last_error_code();
-    const int rc = parse_impl(ix, text, bytes, normalize, end_shift, out);
+    const int rc = parse_impl(ix, text, bytes, normalize, end_shift, group_by_contig, out);
     siIndexDestroy(ix);
     if (rc) siBedTableFree(out);
     return rc;
@@ -303,6 +355,7 @@ void siBedTableFree(siBedTable* t) {
     free(t->contig);
     free(t->starts);
     free(t->ends);
+    free(t->contig_offsets);
     if (t->names) {
         for (size_t k = 0; k < t->n_contigs; ++k) free(t->names[k]);
         free(t->names);

@@ -35,6 +35,23 @@ bk_check_sorted_kernel(const int32_t* __restrict__ s, const int32_t* __restrict_
     if (lane_id() == 0 && bad) atomicAnd(flags, ~bad);
 }
 
+// ---- stable grouping of records by a small non-negative key (BED ingest: contig id) -----
+__global__ void __launch_bounds__(BK_THREADS)
+bk_iota_key_kernel(const int32_t* __restrict__ key, uint32_t n, uint32_t* __restrict__ k, uint32_t* __restrict__ v) {
+    const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i < n; i += stride) {
+        k[i] = (uint32_t)key[i];
+        v[i] = (uint32_t)i;
+    }
+}
+__global__ void __launch_bounds__(BK_THREADS)
+bk_take_perm_kernel(const uint32_t* __restrict__ vA, const uint32_t* __restrict__ vB, const uint32_t* __restrict__ final_sel,
+                    uint32_t n, uint32_t* __restrict__ perm) {
+    const uint32_t* __restrict__ v = *final_sel ? vB : vA;
+    const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i < n; i += stride) perm[i] = v[i];
+}
+
 // ---- key packing: (start asc, end DESC, insertion idx) ------------------------------
 __global__ void __launch_bounds__(BK_THREADS)
 bk_make_keys_kernel(const int32_t* __restrict__ s, const int32_t* __restrict__ e, uint32_t n,

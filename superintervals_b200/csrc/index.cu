@@ -894,6 +894,28 @@ int siCoverageDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size
     return 0;
 }
 
+// used by bed.cu: d_perm[i] = index of the i-th record in stable order of d_key (0 <= key < 2^key_bits),
+// through the build's radix sort and its scratch buffers
+int si_b200_stable_order_(siIndex* ix, const int32_t* d_key, size_t n, int key_bits, uint32_t* d_perm, void* stream) {
+    if (!ix || n > 0xFFFFFFFFull) return cudaErrorInvalidValue;
+    if (n == 0) return 0;
+    DeviceGuard g(ix->device);
+    cudaStream_t s = pick_stream(ix, stream);
+    const uint32_t n32 = (uint32_t)n;
+    if (ix->b_kA.ensure(n * 4) || ix->b_kB.ensure(n * 4) || ix->b_vA.ensure(n * 4) || ix->b_vB.ensure(n * 4) ||
+        ix->b_ws.ensure(rs_workspace_bytes<uint32_t>(n32)))
+        return last_error_code();
+    const int cap = ix->sm_count * 16;
+    SIB_LAUNCH(bk_iota_key_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, d_key, n32, ix->b_kA.as<uint32_t>(), ix->b_vA.as<uint32_t>());
+    int rc = radix_sort_pairs<uint32_t>(ix->b_kA.as<uint32_t>(), ix->b_kB.as<uint32_t>(), ix->b_vA.as<uint32_t>(), ix->b_vB.as<uint32_t>(),
+                                        n32, key_bits, ix->b_ws.p, ix->sm_count, s);
+    if (rc) return rc;
+    RsWorkspace ws = rs_carve(ix->b_ws.p);
+    SIB_LAUNCH(bk_take_perm_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, ix->b_vA.as<uint32_t>(), ix->b_vB.as<uint32_t>(),
+               ws.final_sel, n32, d_perm);
+    return 0;
+}
+
 // used by c_abi.cu: resolve SI_ORDER_AUTO once for a count -> fill pair
 int si_b200_resolve_order_(siIndex* ix, const int32_t* d_qs, size_t n, void* stream) {
     DeviceGuard g(ix->device);

@@ -49,6 +49,23 @@ def test_headers_blanks_and_broken_lines_are_skipped_and_counted():
     assert t.names == ["chr1", "chr2", "chr9"] and t.skipped == t.lines - len(t.starts) and len(t.starts) == 5
 
 
+def test_grouping_by_contig_on_the_device_is_a_stable_partition():
+    from superintervals_b200.bed import parse_bed, split_by_contig
+    rng = np.random.default_rng(17)
+    text = _bed(rng, 120_000, ["chr7", "chr1", "chrM", "chr22", "scaffold_123", "chrX"])
+    flat = parse_bed(text, True, -1)
+    grp = parse_bed(text, True, -1, group_by_contig=True)
+    assert grp.names == flat.names and grp.contig_offsets is not None and grp.contig_offsets[0] == 0
+    assert grp.contig_offsets[-1] == len(flat.starts) and np.all(np.diff(grp.contig_offsets) >= 0)
+    order = np.argsort(flat.contig, kind="stable")
+    assert np.array_equal(grp.contig, flat.contig[order])
+    assert np.array_equal(grp.starts, flat.starts[order]) and np.array_equal(grp.ends, flat.ends[order])
+    a, b = split_by_contig(grp), split_by_contig(flat)
+    assert a.keys() == b.keys() and all(np.array_equal(a[k][0], b[k][0]) and np.array_equal(a[k][1], b[k][1]) for k in a)
+    one = parse_bed(b"chr5\t1\t2\nchr5\t3\t4\n", group_by_contig=True)
+    assert one.contig_offsets.tolist() == [0, 2] and one.starts.tolist() == [1, 3]
+
+
 def test_empty_and_newline_only_inputs():
     from superintervals_b200.bed import parse_bed
     for text in (b"", b"\n", b"\n\n\n", b"chr1"):
@@ -66,7 +83,8 @@ def test_bed_to_queries_end_to_end(tmp_path):
     p_ref, p_q = tmp_path / "ref.bed", tmp_path / "q.bed"
     p_ref.write_bytes(_bed(rng, 30_000, contigs))
     p_q.write_bytes(_bed(rng, 20_000, contigs, extras=False))
-    ref, qry = split_by_contig(parse_bed(str(p_ref), True, -1)), split_by_contig(parse_bed(str(p_q), True, -1))
+    ref = split_by_contig(parse_bed(str(p_ref), True, -1, group_by_contig=True))
+    qry = split_by_contig(parse_bed(str(p_q), True, -1))
     assert set(ref) == set(contigs)
     for c in contigs:
         m = IntervalMap.from_arrays(*ref[c])
