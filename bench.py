@@ -11,11 +11,14 @@ count over the whole 100M-query batch. Under N>1 every rank holds the same index
 and its own independent 100M-query shard (weak scaling, no data-path collective;
 only the per-rank hit totals are gathered over NCCL for the CSR base offsets).
 
-value   queries/s, whole job, queries resident in HBM (shuffled order: the step
-        includes the device radix sort of the batch by start + the count kernel).
+value   queries/s, whole job, queries resident in HBM, shuffled order: the step is one
+        launch of the rank-cells count kernel on the batch as it arrives (behind the
+        locality partition only when the rank cells outgrow L2).
 e2e     same metric through the C-ABI host-buffer call countOverlapsBatch()
         (pinned host buffers; H2D of the queries and D2H of the counts inside).
 roofline / cpu_baseline: see DESIGN.md section "Measurement".
+Secondary objects of the same line: search_values (C3: CSR on heavy-tailed nested
+intervals) and bed_ingest (BED text -> columns), each with its own CPU baseline.
 """
 from __future__ import annotations
 
