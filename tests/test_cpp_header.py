@@ -29,3 +29,16 @@ def test_cpp_hot_path_unit_tests_pass_on_gpu():
     assert out.returncode == 0, out.stdout + out.stderr
     assert "All query tests passed" in out.stdout
     assert "All set operation tests passed" in out.stdout
+
+
+REF_TESTS = os.path.join(ROOT, "oracle", "_ref", "run-tests-b200")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REF_TESTS), reason="oracle/_ref/run-tests-b200 not built (needs /root/reference at build time)")
+def test_the_references_own_test_program_passes_against_this_library():
+    """reference test/tests.cpp, UNMODIFIED, compiled by oracle/Makefile against include/superintervals.hpp and
+    libsuperintervals_b200.so: its asserts (query families, edge cases, set operations) run on the GPU."""
+    out = subprocess.run([REF_TESTS], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "All query tests passed" in out.stdout and "All set operation tests passed" in out.stdout
