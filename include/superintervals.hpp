@@ -14,8 +14,8 @@
 // Differences from the reference, all outside the accelerated path:
 //   * S must be a 32-bit integer type (the reference's AVX2 path has the same
 //     restriction, hpp:688; its C ABI is int32 only).
-//   * IntervalMapEytz and the lazy iterator classes are not provided;
-//     search_idxs(s,e)/search_items(s,e) return eager ranges.
+//   * The lazy iterator classes are not provided: search_idxs(s,e)/search_items(s,e) return eager
+//     ranges. IntervalMapEytz is the same implementation under the reference's name.
 //   * The set algebra (hpp:1037-1390) is provided on top of the C ABI's device set
 //     operations; `other` arguments must have been built.
 //   * New: count_batch / search_values_batch / search_idxs_batch / search_keys_batch
@@ -418,5 +418,11 @@ class IntervalMap {
     // scratch_ is malloc'd by the library; released with the object
     struct ScratchGuard { cIndexResult* r; ~ScratchGuard() { destroyIndexResult(r); } } guard_{&scratch_};
 };
+
+// hpp:1457-1535: IntervalMapEytz keeps the starts in Eytzinger order for a cache-friendlier CPU
+// upper_bound; its results are identical to IntervalMap's. On the device that layout question does
+// not arise, so the name is provided for source compatibility and is the same implementation.
+template <typename S, typename T>
+class IntervalMapEytz : public IntervalMap<S, T> {};
 
 }  // namespace si

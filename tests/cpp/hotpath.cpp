@@ -236,6 +236,12 @@ int main() {
     test_batch_and_payload_types();
     CHECK(si_b200_last_error() == 0);
     std::printf("All query tests passed\n");
+    {   // hpp:1457-1535: the Eytzinger variant answers exactly like the plain map
+        si::IntervalMapEytz<int, int> ez;
+        ez.add(10, 20, 0); ez.add(11, 12, 1); ez.add(25, 29, 2);
+        ez.build();
+        CHECK(ez.count(12, 26) == 3 && ez.has_overlaps(26, 40) && ez.upper_bound(24) == 1);
+    }
     test_set_operations();
     CHECK(si_b200_last_error() == 0);
     std::printf("All set operation tests passed\n");
