@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--intervals", type=int, default=10_000_000)
     ap.add_argument("--queries", type=int, default=100_000_000, help="queries per GPU per step")
     ap.add_argument("--order", default="shuffled", choices=["shuffled", "sorted"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c1"],
+                    help="c2: BASELINE configs[1] (the metric's workload); c1: configs[0], the reference's own "
+                         "generate_test_intervals.py pair (1M x 1M on chr1; sets --intervals/--queries)")
     ap.add_argument("--cpu-sample", type=int, default=16_000_000, help="queries timed on the host CPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -63,8 +66,24 @@ def parse():
 
 
 def workload_name(a):
+    if a.workload == "c1":
+        return (f"C1: reference test/generate_test_intervals.py pair, {a.intervals/1e6:g}M intervals x {a.queries/1e6:g}M queries "
+                f"(~2 kb each) on chr1, count, {a.order} queries")
     return (f"C2: {a.intervals/1e6:g}M read-length intervals (150bp-10kb) x {a.queries/1e6:g}M range queries "
             f"per GPU, 250Mb axis, count only, {a.order} queries")
+
+
+def make_workload(a, rank, nq):
+    """(starts, ends, qs, qe) of the chosen workload; rank selects the query shard under weak scaling."""
+    from superintervals_b200 import workloads as W
+    if a.workload == "c1":
+        s, e, qs, qe = W.config1(a.intervals, seed=rank)
+        if rank:   # one index for every rank: rank 0's intervals
+            s, e, _, _ = W.config1(a.intervals, seed=0)
+        return s, e, qs[:nq], qe[:nq]
+    s, e = W.config2_intervals(a.intervals, 2)
+    qs, qe = W.config2_queries(nq, 2, shard=rank)
+    return s, e, qs, qe
 
 
 def host_threads():
@@ -213,9 +232,7 @@ def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0   # N>1: rank 0 alone runs the CPU arm
-    from superintervals_b200 import workloads as W
-    starts, ends = W.config2_intervals(a.intervals, 2)
-    qs, qe = W.config2_queries(min(a.queries, a.cpu_sample), 2, shard=0)
+    starts, ends, qs, qe = make_workload(a, 0, min(a.queries, a.cpu_sample))
     threads = host_threads()
     r = cpu_reference(a, starts, ends, qs, qe, a.steps, a.warmup, threads)
     line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "impl": "reference", "n_gpus": a.gpus,
@@ -369,6 +386,8 @@ def bench_bed_ingest(a, rank):
 
 def main():
     a = parse()
+    if a.workload == "c1":
+        a.intervals = a.queries = min(a.intervals, 1_000_000) if a.intervals != 10_000_000 else 1_000_000
     if a.impl == "reference":
         return run_reference_arm(a)
 
@@ -389,8 +408,7 @@ def main():
     L = _lib.lib()
 
     # ---- synthetic inputs (seeded): same index on every rank, one query shard per rank
-    starts, ends = W.config2_intervals(a.intervals, 2)
-    qs, qe = W.config2_queries(a.queries, 2, shard=rank)
+    starts, ends, qs, qe = make_workload(a, rank, a.queries)
     if a.order == "sorted":
         o = np.argsort(qs, kind="stable")
         qs, qe = np.ascontiguousarray(qs[o]), np.ascontiguousarray(qe[o])
@@ -567,7 +585,9 @@ def main():
                        "count_kernel": next((k for k in ("count_cells", "count_rank", "count_walk") if k in kernels), None),
                        "rank_cells": cells_info,
                        "count_algo": a.algo,
-                       "l2": "inputs larger than L2: 800 MB of queries + 400 MB of counts per step vs 126 MB",
+                       "l2": (f"inputs larger than L2: {8 * nq / 1e6:.0f} MB of queries + {4 * nq / 1e6:.0f} MB of counts per step vs 126 MB"
+                              if 12 * nq > 2 * 126e6 else
+                              f"inputs ({12 * nq / 1e6:.0f} MB per step) FIT in L2: a parity/side configuration, not the metric's workload"),
                        "index": "replicated per GPU", "collective": "all_gather of per-rank hit totals (CSR bases)"},
             "e2e": {"value": world * nq / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * nq,
                     "d2h_bytes_per_step": 8 * nq, "ms_per_step": e2e_s * 1e3,
