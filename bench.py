@@ -361,15 +361,19 @@ def bench_bed_ingest(a, rank):
     n = a.bed_lines
     text, cid, s, e = W.bed_text(n)
     parse_bed(text[: 26 * 1000])
-    t0 = time.perf_counter(); t = parse_bed(text, True, -1); dt = time.perf_counter() - t0
+    dt = float("inf")
+    for _ in range(2):   # best of two: the first call also pays for first-touch of fresh host pages
+        t0 = time.perf_counter(); t = parse_bed(text, True, -1); dt = min(dt, time.perf_counter() - t0)
     ok = bool(len(t.starts) == n and np.array_equal(t.starts, s.astype(np.int32)) and np.array_equal(t.ends, (e - 1).astype(np.int32)))
-    t0 = time.perf_counter(); g = parse_bed(text, True, -1, group_by_contig=True); dg = time.perf_counter() - t0
+    dg = float("inf")
+    for _ in range(2):
+        t0 = time.perf_counter(); g = parse_bed(text, True, -1, group_by_contig=True); dg = min(dg, time.perf_counter() - t0)
     ok_g = bool(g.contig_offsets is not None and int(g.contig_offsets[-1]) == n and
                 np.array_equal(g.starts[:int(g.contig_offsets[1])], t.starts[t.contig == 0]))   # stable: line order inside a contig
     out = {"workload": f"{n/1e6:g}M BED records ({text.size/1e6:.0f} MB of text, 24 contigs) -> contig/start/end columns",
            "value": n / dt, "unit": "lines/s", "seconds": dt, "text_gb_per_s": text.size / dt / 1e9, "equals_generator": ok,
            "grouped_by_contig": {"seconds": dg, "value": n / dg, "unit": "lines/s", "first_contig_equals_line_order_filter": ok_g},
-           "note": "host text buffer in, host columns out: H2D of the text and D2H of the columns are inside"}
+           "note": "host text buffer in, host columns out: H2D of the text and D2H of the columns are inside; best of 2 calls"}
     so = os.path.join(ROOT, "oracle", "libsi_bedcpu.so")
     if rank == 0 and not a.no_cpu_baseline and os.path.exists(so):
         L = C.CDLL(so)
