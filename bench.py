@@ -18,7 +18,8 @@ e2e     same metric through the C-ABI host-buffer call countOverlapsBatch()
         (pinned host buffers; H2D of the queries and D2H of the counts inside).
 roofline / cpu_baseline: see DESIGN.md section "Measurement".
 Secondary objects of the same line: search_values (C3: CSR on heavy-tailed nested
-intervals) and bed_ingest (BED text -> columns), each with its own CPU baseline.
+intervals), bed_ingest (BED text -> columns) and set_algebra (mergeOverlaps /
+intersection / difference through the C ABI), each with its own CPU baseline.
 """
 from __future__ import annotations
 
@@ -62,6 +63,7 @@ def parse():
     ap.add_argument("--sv-intervals", type=int, default=4_000_000)
     ap.add_argument("--sv-queries", type=int, default=4_000_000)
     ap.add_argument("--bed-lines", type=int, default=20_000_000, help="records of the secondary BED-ingest measurement (0 = skip)")
+    ap.add_argument("--setop-intervals", type=int, default=1_000_000, help="intervals per set of the secondary set-algebra measurement (0 = skip)")
     return ap.parse_args()
 
 
@@ -388,6 +390,55 @@ def bench_bed_ingest(a, rank):
     return out
 
 
+def bench_set_algebra(a, L, _lib, rank):
+    """Secondary line: the set-algebra callers of the path through the C ABI (host arrays in, new host
+    set out) beside the reference's own sequential C functions (oracle/_ref/libsi_cref.so, one thread)."""
+    from superintervals_b200 import workloads as W
+    n = a.setop_intervals
+    A = W.config2_intervals(n, 11)
+    B = W.config2_intervals(n, 12)
+
+    def run(lib, timed):
+        def make(s, e, index):
+            si = lib.createSuperIntervals()
+            if hasattr(lib, "addIntervals"):
+                lib.addIntervals(si, s.ctypes.data, e.ctypes.data, None, s.size)
+            else:
+                for k in range(s.size):
+                    lib.addInterval(si, int(s[k]), int(e[k]), k)
+            if index:
+                lib.indexSuperIntervals(si)
+            return si
+        a_, b_ = make(*A, False), make(*B, True)
+        out = {}
+        for name, call in (("mergeOverlaps", lambda: lib.mergeOverlaps(a_, None)), ("intersection", lambda: lib.intersection(a_, b_, None)),
+                           ("difference", lambda: lib.difference(a_, b_))):
+            best, size, chk = float("inf"), 0, 0
+            for _ in range(timed):
+                t0 = time.perf_counter(); r = call(); dt = time.perf_counter() - t0
+                size = int(r.contents.size)
+                if size:
+                    st = np.ctypeslib.as_array(r.contents.starts, shape=(size,)); en = np.ctypeslib.as_array(r.contents.ends, shape=(size,))
+                    chk = int(st.astype(np.int64).sum() * 3 + en.astype(np.int64).sum())
+                lib.destroySuperIntervals(r)
+                best = min(best, dt)
+            out[name] = {"seconds": best, "pieces": size, "checksum": chk}
+        lib.destroySuperIntervals(a_); lib.destroySuperIntervals(b_)
+        return out
+
+    ours = run(L, 3)
+    _lib.check("set algebra")
+    res = {"workload": f"A, B = {n/1e6:g}M read-length intervals each on the 250 Mb axis (B indexed); host arrays in, new host set out",
+           "ops": {k: {"seconds": v["seconds"], "pieces": v["pieces"], "input_intervals_per_s": n / v["seconds"]} for k, v in ours.items()}}
+    cref = os.path.join(ROOT, "oracle", "_ref", "libsi_cref.so")
+    if rank == 0 and not a.no_cpu_baseline and os.path.exists(cref):
+        ref = run(_lib.bind(C.CDLL(cref)), 1)
+        res["cpu_baseline"] = {"kind": "reference", "cores": 1, "sample": "same sets, reference c_superintervals.h compiled -O3 (oracle/_ref/libsi_cref.so), one pass",
+                               "ops": {k: {"seconds": v["seconds"], "pieces": v["pieces"], "equal_to_device": v["pieces"] == ours[k]["pieces"] and v["checksum"] == ours[k]["checksum"]}
+                                       for k, v in ref.items()}}
+    return res
+
+
 def main():
     a = parse()
     if a.workload == "c1":
@@ -522,6 +573,9 @@ def main():
     bed = None
     if world == 1 and not a.no_search_values and a.bed_lines > 0:
         bed = bench_bed_ingest(a, rank)
+    setops = None
+    if world == 1 and not a.no_search_values and a.setop_intervals > 0:
+        setops = bench_set_algebra(a, L, _lib, rank)
 
     if rank != 0:
         if world > 1:
@@ -601,7 +655,7 @@ def main():
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "cpu_baseline": cpu_baseline, "parity": parity, "build_ms": build_ms,
             "shard_hits": shard_hits, "shard_csr_base": shard_base, "device_bytes": ix.device_bytes,
-            "search_values": sv, "bed_ingest": bed}
+            "search_values": sv, "bed_ingest": bed, "set_algebra": setops}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
