@@ -101,12 +101,13 @@ bk_identity_kernel(const int32_t* __restrict__ s, const int32_t* __restrict__ e,
 }
 
 // pad tail [n, n_padded) so 128-bit loads past the end read harmless data
-__global__ void bk_pad_kernel(int32_t* __restrict__ starts, int32_t* __restrict__ ends,
+__global__ void bk_pad_kernel(int32_t* __restrict__ starts, int32_t* __restrict__ ends, int32_t* __restrict__ values,
                               uint32_t* __restrict__ branch, uint32_t n, uint32_t n_padded) {
     uint32_t i = n + blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_padded) {
         starts[i] = INT_MAX;
         ends[i] = INT_MIN;
+        values[i] = 0;        // read (never used) by the fill's aligned 128-bit payload loads
         branch[i] = NONE32;
     }
 }

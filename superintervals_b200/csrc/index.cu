@@ -317,7 +317,7 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
                    ix->perm.as<uint32_t>());
     }
     if (ix->n_padded > ix->n) {
-        SIB_LAUNCH(bk_pad_kernel, 1, 128, 0, s, ix->starts.as<int32_t>(), ix->ends.as<int32_t>(),
+        SIB_LAUNCH(bk_pad_kernel, 1, 128, 0, s, ix->starts.as<int32_t>(), ix->ends.as<int32_t>(), ix->values.as<int32_t>(),
                    ix->branch.as<uint32_t>(), ix->n, ix->n_padded);
     }
     if (ix->esort.ensure(pad_b)) return last_error_code();
@@ -335,7 +335,9 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
             return last_error_code();
         SIB_LAUNCH(bk_end_keys_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, ix->ends.as<int32_t>(), ix->n,
                    ix->b_kA.as<uint32_t>());
-        // payload buffers ride along unused: the sort moves (key, uint32) pairs
+        // payload buffers ride along unused: the sort moves (key, uint32) pairs (zeroed so that no kernel
+        // ever reads uninitialised memory: compute-sanitizer initcheck stays clean)
+        SIB_CHECK(cudaMemsetAsync(ix->b_vA.p, 0, n * 4, s));
         rc = radix_sort_pairs<uint32_t>(ix->b_kA.as<uint32_t>(), ix->b_kB.as<uint32_t>(), ix->b_vA.as<uint32_t>(),
                                         ix->b_vB.as<uint32_t>(), ix->n, 32, ix->b_ws.p, ix->sm_count, s);
         if (rc) return rc;
