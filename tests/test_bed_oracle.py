@@ -39,3 +39,14 @@ def test_stoi_rules_of_the_oracle():
     assert names == ["a", "b", "f"] and starts.tolist() == [12, 7, 12] and ends.tolist() == [13, -2, 13]
     assert lines == 7 and skipped == 4
     assert bed_oracle.parse_bed(text, normalize=True, end_shift=-1)[2:4][1].tolist() == [12, 6, 12]
+
+
+def test_synthetic_bed_text_round_trips_through_the_oracle():
+    """workloads.bed_text (the generator bench.py and tools/bed_bench.py feed to the device tokeniser) writes what
+    it says: the oracle reads back the generating columns."""
+    from superintervals_b200 import workloads as W
+    text, cid, s, e = W.bed_text(3000, seed=9)
+    names, contig, starts, ends, lines, skipped = bed_oracle.parse_bed(bytes(text), normalize=True, end_shift=-1)
+    assert lines == 3000 and skipped == 0 and len(names) <= 24
+    assert np.array_equal(starts, s.astype(np.int32)) and np.array_equal(ends, (e - 1).astype(np.int32))
+    assert [names[c] for c in contig] == [f"chr{c:02d}" for c in cid]
