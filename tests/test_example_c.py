@@ -35,15 +35,15 @@ def test_c_example_totals_match_the_oracle(tmp_path):
         rows = []
         for _ in range(n):
             s = int(rng.integers(0, 3_000_000)); e = s + int(rng.integers(1, 6000))
-            rows.append(f"{contigs[int(rng.integers(0, len(contigs)))]}\\t{s}\\t{e}")
-        return ("\\n".join(rows) + "\\n").encode()
+            rows.append(f"{contigs[int(rng.integers(0, len(contigs)))]}\t{s}\t{e}")
+        return ("\n".join(rows) + "\n").encode()
 
     ta, tq = bed(40_000, ["chr1", "chr2", "chrX"]), bed(25_000, ["chr2", "chr1", "chrY"])
     pa, pq = tmp_path / "a.bed", tmp_path / "q.bed"
     pa.write_bytes(ta); pq.write_bytes(tq)
     out = subprocess.run([EXE, str(pa), str(pq)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
-    got = {l.split("\\t")[0]: l.split("\\t") for l in out.stdout.strip().splitlines()}
+    got = {l.split("\t")[0]: l.split("\t") for l in out.stdout.strip().splitlines()}
     an, ac, as_, ae, _, _ = bed_oracle.parse_bed(ta, True, -1)
     qn, qc, qs_, qe_, _, _ = bed_oracle.parse_bed(tq, True, -1)
     total = 0
