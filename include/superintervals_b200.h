@@ -165,7 +165,10 @@ enum { SI_OPT_COUNT_ALGO = 0, SI_OPT_BUCKET_INTERVALS = 1, SI_OPT_WINDOW_SHIFT =
        SI_OPT_CELLS_DIRECT_BYTES = 5, /* rank cells up to this many bytes answer batches unpartitioned (0 = 60 % of L2) */
        SI_OPT_CELLS_FILL = 6, /* mean values per rank cell (1..28); applies to the next build */
        SI_OPT_STAB_LISTS = 7, /* 1 (default): the CSR fill of a well-formed index reads its stab lists; 0: it walks the branch array */
-       SI_OPT_STAB_BUDGET = 8 /* stab-list entries per interval at most (default 6); deeper indexes double the checkpoint spacing, then walk */ };
+       SI_OPT_STAB_BUDGET = 8, /* stab-list entries per interval at most (default 6); deeper indexes double the checkpoint spacing, then walk */
+       SI_OPT_STREAM = 9, /* 1 (default): position-sorted batches are counted by the streaming kernel (TMA-staged rank bits) when the
+                             index carries them; 0: never; 2: every batch, whatever its order (a tile whose window does not fit reads the cells) */
+       SI_OPT_STREAM_BUDGET = 10 /* rank bits are built when they cost at most this many bytes per interval (default 64; 0 = never); next build */ };
 enum { SI_COUNT_AUTO = 0, SI_COUNT_WALK = 1, SI_COUNT_RANK = 2, SI_COUNT_CELLS = 3 };
 int siIndexSetOption(siIndex* ix, int option, long long value);
 /* The rank cells build() made (which = 0: over starts, 1: over ends). format 0 = none
@@ -178,6 +181,14 @@ typedef struct {
     int direct;
 } siCellsInfo;
 int siIndexCellsInfo(const siIndex* ix, int which, siCellsInfo* out);
+/* The rank bits build() made for the streaming count (csrc/stream_kernels.cuh): built = 1 when position-sorted
+ * batches stream; words / bytes over both tables; slow_words = words holding a coordinate with three or more
+ * values (answered from the rank cells). */
+typedef struct {
+    int built;
+    unsigned long long words, bytes, slow_words;
+} siBitsInfo;
+int siIndexBitsInfo(const siIndex* ix, siBitsInfo* out);
 /* The stab lists of the CSR fill (made by the first siFillDevice after a build): state 0 = not
  * made yet, 1 = in use, 2 = over budget or too small (the fill walks); a checkpoint every
  * 2^shift positions, `lists` lists holding `entries` records of `record_bytes` bytes. */
@@ -193,7 +204,7 @@ int siIndexStabInfo(const siIndex* ix, siStabInfo* out);
  * clears them; waits for the recorded work. Tags: 1 partition histogram + scan, 2 partition
  * pass, 3 count (walk), 4 count (rank), 5 CSR scan, 6 CSR fill (walk), 7 count (cells), 8 CSR fill (runs + stab lists). bench.py's roofline uses it. */
 enum { SI_TAG_PT_HIST = 1, SI_TAG_PT_PASS = 2, SI_TAG_COUNT_WALK = 3, SI_TAG_COUNT_RANK = 4, SI_TAG_SCAN = 5, SI_TAG_FILL = 6,
-       SI_TAG_COUNT_CELLS = 7, SI_TAG_FILL_RUNS = 8 };
+       SI_TAG_COUNT_CELLS = 7, SI_TAG_FILL_RUNS = 8, SI_TAG_COUNT_STREAM = 9 };
 int siIndexReadTimings(siIndex* ix, int* tags, float* ms, int max_out);
 
 int siAnyDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n,

@@ -19,7 +19,8 @@ FILL_VALUES, FILL_IDXS, FILL_KEYS, FILL_ITEMS = 0, 1, 2, 3
 OPT_COUNT_ALGO, OPT_BUCKET_INTERVALS, OPT_WINDOW_SHIFT, OPT_TIMING, OPT_GRID_INTERVALS = 0, 1, 2, 3, 4
 OPT_CELLS_DIRECT_BYTES, OPT_CELLS_FILL = 5, 6
 OPT_STAB_LISTS, OPT_STAB_BUDGET = 7, 8
-TAG_NAMES = {1: "pt_histogram", 2: "pt_onesweep", 3: "count_walk", 4: "count_rank", 5: "scan", 6: "fill", 7: "count_cells", 8: "fill_runs"}
+OPT_STREAM, OPT_STREAM_BUDGET = 9, 10
+TAG_NAMES = {1: "pt_histogram", 2: "pt_onesweep", 3: "count_walk", 4: "count_rank", 5: "scan", 6: "fill", 7: "count_cells", 8: "fill_runs", 9: "count_stream"}
 COUNT_AUTO, COUNT_WALK, COUNT_RANK, COUNT_CELLS = 0, 1, 2, 3
 
 
@@ -61,6 +62,10 @@ class siCellsInfo(C.Structure):
                 ("overfull", C.c_ulonglong), ("direct", C.c_int)]
 
 
+class siBitsInfo(C.Structure):
+    _fields_ = [("built", C.c_int), ("words", C.c_ulonglong), ("bytes", C.c_ulonglong), ("slow_words", C.c_ulonglong)]
+
+
 class siBedTable(C.Structure):
     _fields_ = [("contig", C.POINTER(C.c_int32)), ("starts", C.POINTER(C.c_int32)), ("ends", C.POINTER(C.c_int32)),
                 ("n", C.c_size_t), ("lines", C.c_size_t), ("skipped", C.c_size_t),
@@ -100,7 +105,7 @@ B200_SYMBOLS = [
     "countOverlapsBatch", "anyOverlapsBatch", "searchValuesBatch", "searchIdxsBatch", "searchKeysBatch",
     "searchItemsBatch", "coverageBatch", "intersectionPairs", "siParseBed", "siBedTableFree", "siIndexCreate", "siIndexDestroy", "siIndexOf", "siIndexSize",
     "siIndexDeviceView", "siIndexBuildHost", "siIndexBuildDevice", "siIndexExport", "siCountDevice",
-    "siCountDevice64", "siSortQueriesDevice", "siIndexSetOption", "siIndexCellsInfo", "siIndexStabInfo", "siIndexReadTimings", "siAnyDevice", "siScanDevice", "siFillDevice", "siCoverageDevice",
+    "siCountDevice64", "siSortQueriesDevice", "siIndexSetOption", "siIndexCellsInfo", "siIndexBitsInfo", "siIndexStabInfo", "siIndexReadTimings", "siAnyDevice", "siScanDevice", "siFillDevice", "siCoverageDevice",
     "siIndexDeviceBytes",
 ]
 
@@ -195,6 +200,8 @@ def bind_b200(L):
     L.siSortQueriesDevice.argtypes = [vp, vp, vp, sz, vp]
     L.siIndexCellsInfo.argtypes = [vp, C.c_int, C.POINTER(siCellsInfo)]
     L.siIndexCellsInfo.restype = C.c_int
+    L.siIndexBitsInfo.argtypes = [vp, C.POINTER(siBitsInfo)]
+    L.siIndexBitsInfo.restype = C.c_int
     if hasattr(L, "intersectionPairs"):
         L.intersectionPairs.restype = SI
         L.intersectionPairs.argtypes = [SI, SI, C.POINTER(cIndexResult)]

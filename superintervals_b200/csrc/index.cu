@@ -8,6 +8,7 @@
 #include "partition.cuh"
 #include "query_kernels.cuh"
 #include "radix_sort.cuh"
+#include "stream_kernels.cuh"
 
 #include <atomic>
 #include <cstdio>
@@ -121,7 +122,7 @@ using namespace sib;
     } while (0)
 
 size_t siIndex::device_bytes() const {
-    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &esort, &eall, &grid_tab, &cells_s, &cells_e, &stab_off, &stab_hdr, &stab_ent, &stab_cnt, &b_in_s, &b_in_e, &b_in_v,
+    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &esort, &eall, &grid_tab, &cells_s, &cells_e, &bits_s_t, &bits_s_d, &bits_e_t, &bits_e_d, &stream_ws, &stab_off, &stab_hdr, &stab_ent, &stab_cnt, &b_in_s, &b_in_e, &b_in_v,
                            &b_kA, &b_kB, &b_vA, &b_vB, &b_ws, &small, &q_A, &q_B,
                            &q_ws, &scan_status, &h_qs, &h_qe, &h_counts, &h_offsets, &h_out, &h_cov};
     size_t s = 0;
@@ -162,6 +163,9 @@ IndexView view_of(const siIndex* ix) {
     v.grid.cells = ix->grid_cells;
     v.cells_s = RankCells{ix->cells_s.as<uint4>(), ix->cm_s.lo, ix->cm_s.span, ix->cm_s.shift, ix->cm_s.fmt};
     v.cells_e = RankCells{ix->cells_e.as<uint4>(), ix->cm_e.lo, ix->cm_e.span, ix->cm_e.shift, ix->cm_e.fmt};
+    const bool bits = ix->bits_ok;
+    v.bits_s = RankBits{bits ? ix->bits_s_t.as<uint2>() : nullptr, ix->bits_s_d.as<uint32_t>(), ix->cm_s.lo, ix->cm_s.span, ix->bits_words_s};
+    v.bits_e = RankBits{bits ? ix->bits_e_t.as<uint2>() : nullptr, ix->bits_e_d.as<uint32_t>(), ix->cm_e.lo, ix->cm_e.span, ix->bits_words_e};
     const bool stab = ix->stab_state == 1 && ix->stab_enabled;
     v.stab = StabLists{ix->stab_hdr.as<uint4>(), stab ? ix->stab_ent.p : nullptr, ix->stab_rec16 ? 1u : 0u, ix->stab_kshift, ix->stab_nlists};
     v.n = ix->n;
@@ -264,11 +268,25 @@ int build_cells(siIndex* ix, const int32_t* A, int32_t first, int32_t last, DevB
     return 0;
 }
 
+// Rank bits over a sorted device array whose rank cells exist (stream_kernels.cuh).
+int build_bits(siIndex* ix, const int32_t* A, const DevBuf& cells, const siIndex::CellsMeta& m, DevBuf* t, DevBuf* d2,
+               uint32_t* nwords_out, unsigned long long* d_slow, cudaStream_t s) {
+    const uint32_t nwords = (uint32_t)(((uint64_t)m.span + 1) >> 5) + 1u;
+    const uint32_t padded = ((nwords + 3u) & ~3u) + 4u;
+    if (t->ensure((size_t)padded * 8) || d2->ensure((size_t)padded * 4)) return last_error_code();
+    const RankCells rc{cells.as<uint4>(), m.lo, m.span, m.shift, m.fmt};
+    SIB_LAUNCH(sk_rank_bits_kernel, grid_for(padded, 256, ix->sm_count * 16), 256, 0, s, rc, A, ix->n, nwords, padded,
+               t->as<uint2>(), d2->as<uint32_t>(), d_slow);
+    *nwords_out = nwords;
+    return 0;
+}
+
 int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const int32_t* d_v, size_t n,
                       cudaStream_t s) {
     ix->built = false;
     ix->plan_valid = false;
     ix->cm_s.fmt = ix->cm_e.fmt = 0;
+    ix->bits_ok = false;
     ix->stab_state = 0;
     ix->stab_entries = 0;
     if (n > MAX_N) {
@@ -363,6 +381,20 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
             SIB_CHECK(cudaStreamSynchronize(s));
             ix->cm_s.overfull = over[0];
             ix->cm_e.overfull = over[1];
+            // rank bits for the streaming count: only where they stay affordable next to the index
+            const uint64_t words = (((uint64_t)ix->cm_s.span + 1) >> 5) + (((uint64_t)ix->cm_e.span + 1) >> 5) + 16;
+            if (ix->stream_mode != 0 && n < 0x40000000ull && words * 12 <= (uint64_t)ix->bits_budget * n) {
+                SIB_CHECK(cudaMemsetAsync(d_over, 0, 16, s));
+                rc = build_bits(ix, ix->starts.as<int32_t>(), ix->cells_s, ix->cm_s, &ix->bits_s_t, &ix->bits_s_d, &ix->bits_words_s, d_over, s);
+                if (rc) return rc;
+                rc = build_bits(ix, ix->eall.as<int32_t>(), ix->cells_e, ix->cm_e, &ix->bits_e_t, &ix->bits_e_d, &ix->bits_words_e, d_over + 1, s);
+                if (rc) return rc;
+                SIB_CHECK(cudaMemcpyAsync(ix->bits_slow, d_over, 16, cudaMemcpyDeviceToHost, s));
+                SIB_CHECK(cudaStreamSynchronize(s));
+                // words with a triple coordinate are answered from the cells, one dependent global load each:
+                // beyond a few percent of the words the streaming kernel would not stream
+                ix->bits_ok = (ix->bits_slow[0] + ix->bits_slow[1]) * 32 <= words;
+            }
         }
         {
             const uint64_t range = (uint64_t)((int64_t)ix->hi - (int64_t)ix->lo) + 1;   // >= 1 on a well-formed index
@@ -474,6 +506,31 @@ int launch_count(siIndex* ix, const QueryRecords& rec, uint32_t nq, CountT* d_co
     return 0;
 }
 
+// The streaming kernel answers position-sorted batches of an index that carries rank bits.
+bool stream_ready(const siIndex* ix) {
+    return ix->bits_ok && ix->stream_mode != 0 && ix->count_algo == SI_COUNT_AUTO && count_algo_of(ix) == SI_COUNT_CELLS;
+}
+
+template <typename CountT>
+int launch_count_stream(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, uint32_t nq, CountT* d_counts, cudaStream_t s) {
+    static_assert(SK_TILE % QC_TILE == 0, "a streaming tile is a whole number of rank-cells tiles");
+    const int grid = (int)(((uint64_t)nq + SK_TILE - 1) / SK_TILE);
+    const uint32_t vec_ok = ((((uintptr_t)d_qs) | ((uintptr_t)d_qe) | ((uintptr_t)d_counts)) & 31u) == 0 ? 1u : 0u;
+    if (ix->stream_ws.ensure(((size_t)grid + 16) * 4)) return last_error_code();
+    uint32_t* fail_count = ix->stream_ws.as<uint32_t>();
+    uint32_t* fail_list = fail_count + 8;
+    SIB_CHECK(cudaMemsetAsync(fail_count, 0, 4, s));
+    ix->timer.begin(TAG_COUNT_STREAM, s);
+    sk_count_stream_kernel<CountT><<<grid, SK_THREADS, SK_SMEM, s>>>(view_of(ix), d_qs, d_qe, nq, d_counts, vec_ok, fail_list, fail_count);
+    SIB_CHECK_LAUNCH();
+    const int grid2 = grid < ix->sm_count * 4 ? grid : ix->sm_count * 4;
+    sk_count_failed_tiles_kernel<CountT><<<grid2, QC_THREADS, 0, s>>>(view_of(ix), d_qs, d_qe, nq, d_counts, fail_list, fail_count);
+    SIB_CHECK_LAUNCH();
+    ix->timer.end(s);
+    note_launch(2);
+    return 0;
+}
+
 template <typename CountT>
 int count_impl(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, CountT* d_counts, int order,
                void* stream) {
@@ -494,12 +551,27 @@ int count_impl(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, 
     }
     const bool armed = ix->plan_armed;
     ix->plan_armed = false;
-    if (cells_direct(ix) && !(armed && order == SI_ORDER_UNSORTED)) order = SI_ORDER_ASIS;   // order is irrelevant to the cells kernel
+    bool streaming = false;
+    if (stream_ready(ix)) {
+        // a position-sorted batch streams (stream_kernels.cuh); SI_ORDER_AUTO pays one pass over the starts to find out
+        if (order == SI_ORDER_AUTO && ix->stream_mode == 1) {
+            order = resolve_order(ix, d_qs, (uint32_t)n, order, s);
+            if (order < 0) { set_error(cudaGetLastError(), "resolve_order", __FILE__, __LINE__); return last_error_code(); }
+        }
+        streaming = ix->stream_mode == 2 || order == SI_ORDER_SORTED;
+    }
+    if (!streaming && cells_direct(ix) && !(armed && order == SI_ORDER_UNSORTED)) order = SI_ORDER_ASIS;   // order is irrelevant to the cells kernel
     order = resolve_order(ix, d_qs, (uint32_t)n, order, s);
     if (order < 0) { set_error(cudaGetLastError(), "resolve_order", __FILE__, __LINE__); return last_error_code(); }
     // batches beyond the partition's size are processed in slices (their scratch is bounded too)
     for (size_t at = 0; at < n; at += PT_MAX_BATCH) {
         const uint32_t m = (uint32_t)(n - at < PT_MAX_BATCH ? n - at : PT_MAX_BATCH);
+        if (streaming) {
+            ix->plan_valid = false;
+            int rc = launch_count_stream<CountT>(ix, d_qs + at, d_qe + at, m, d_counts + at, s);
+            if (rc) return rc;
+            continue;
+        }
         QueryRecords rec{d_qs + at, d_qe + at, nullptr};
         if (order == SI_ORDER_UNSORTED) {
             // an explicit siSortQueriesDevice() on this batch arms a one-shot reuse; otherwise partition now
@@ -619,7 +691,7 @@ void siIndexDestroy(siIndex* ix) {
     if (!ix) return;
     DeviceGuard g(ix->device);
     DevBuf* all[] = {&ix->starts, &ix->ends, &ix->values, &ix->branch, &ix->perm, &ix->tree, &ix->esort, &ix->eall, &ix->grid_tab,
-                     &ix->cells_s, &ix->cells_e, &ix->stab_off, &ix->stab_hdr, &ix->stab_ent, &ix->stab_cnt,
+                     &ix->cells_s, &ix->cells_e, &ix->bits_s_t, &ix->bits_s_d, &ix->bits_e_t, &ix->bits_e_d, &ix->stream_ws, &ix->stab_off, &ix->stab_hdr, &ix->stab_ent, &ix->stab_cnt,
                      &ix->b_in_s, &ix->b_in_e, &ix->b_in_v, &ix->b_kA, &ix->b_kB, &ix->b_vA, &ix->b_vB, &ix->b_ws,
                      &ix->small, &ix->q_A, &ix->q_B, &ix->q_ws, &ix->scan_status, &ix->h_qs,
                      &ix->h_qe, &ix->h_counts, &ix->h_offsets, &ix->h_out, &ix->h_cov};
@@ -649,6 +721,15 @@ int siIndexCellsInfo(const siIndex* ix, int which, siCellsInfo* out) {
     out->bytes = out->cells * 32;
     out->overfull = m.overfull;
     out->direct = cells_direct(ix) ? 1 : 0;
+    return 0;
+}
+
+int siIndexBitsInfo(const siIndex* ix, siBitsInfo* out) {
+    if (!ix || !out || !ix->built) return cudaErrorInvalidValue;
+    out->built = ix->bits_ok ? 1 : 0;
+    out->words = ix->bits_ok ? (unsigned long long)ix->bits_words_s + ix->bits_words_e : 0;
+    out->bytes = out->words * 12;
+    out->slow_words = ix->bits_slow[0] + ix->bits_slow[1];
     return 0;
 }
 
@@ -791,6 +872,14 @@ int siIndexSetOption(siIndex* ix, int option, long long value) {
             if (value < 0 || value > 4096) break;
             ix->stab_budget = (uint32_t)value;
             if (ix->stab_state == 2) ix->stab_state = 0;
+            return 0;
+        case SI_OPT_STREAM:                // 0: never; 1 (default): position-sorted batches stream; 2: every batch (tests)
+            if (value < 0 || value > 2) break;
+            ix->stream_mode = (int)value;
+            return 0;
+        case SI_OPT_STREAM_BUDGET:         // bytes of rank bits per interval at most; applies to the next build
+            if (value < 0 || value > 4096) break;
+            ix->bits_budget = (uint32_t)value;
             return 0;
         case SI_OPT_WINDOW_SHIFT:
             if (value < 10 || value > 31) break;

@@ -21,7 +21,8 @@ unsigned long long launches();
 
 // Optional per-launch device timing (siIndexSetOption SI_OPT_TIMING): a CUDA event pair on the
 // launching stream around each hot kernel, read back by siIndexReadTimings. Off by default.
-enum LaunchTag : int { TAG_PT_HIST = 1, TAG_PT_PASS = 2, TAG_COUNT_WALK = 3, TAG_COUNT_RANK = 4, TAG_SCAN = 5, TAG_FILL = 6, TAG_COUNT_CELLS = 7, TAG_FILL_RUNS = 8 };
+enum LaunchTag : int { TAG_PT_HIST = 1, TAG_PT_PASS = 2, TAG_COUNT_WALK = 3, TAG_COUNT_RANK = 4, TAG_SCAN = 5, TAG_FILL = 6, TAG_COUNT_CELLS = 7, TAG_FILL_RUNS = 8,
+                       TAG_COUNT_STREAM = 9 };
 struct LaunchTimer {
     bool on = false;
     cudaEvent_t* ev = nullptr;   // 2 * cap events
@@ -59,6 +60,15 @@ struct siIndex {
     uint32_t cells_fill8 = 16, cells_fill16 = 7;   // target mean values per cell (28 / 14 slots)
     size_t cells_direct_bytes = 0;                 // cells up to this size answer unpartitioned batches (0: 60 % of L2)
     size_t l2_bytes = 0;
+    // rank bits (RankBits in query_kernels.cuh): 12 B per 32 coordinates of the span, per table; the
+    // streaming count kernel's tables. Built only when they cost at most bits_budget bytes per interval.
+    sib::DevBuf bits_s_t, bits_s_d, bits_e_t, bits_e_d;
+    sib::DevBuf stream_ws;                         // tiles the streaming kernel hands to the rank-cells code (count + list)
+    uint32_t bits_words_s = 0, bits_words_e = 0;
+    bool bits_ok = false;
+    unsigned long long bits_slow[2] = {0, 0};      // words holding a coordinate with >= 3 values (answered from the cells)
+    uint32_t bits_budget = 64;                     // SI_OPT_STREAM_BUDGET: bytes per interval at most (0 = never build)
+    int stream_mode = 1;                           // SI_OPT_STREAM: 0 off, 1 position-sorted batches, 2 every batch
     // stab lists (StabLists in query_kernels.cuh), made by the first CSR fill that can use them
     sib::DevBuf stab_off, stab_hdr, stab_ent, stab_cnt;   // scan offsets (build only), list headers, records, counts
     uint32_t stab_kshift = 0, stab_nlists = 0;

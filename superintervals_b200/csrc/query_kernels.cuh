@@ -53,6 +53,18 @@ struct RankCells {
     uint32_t fmt;       // 0 = not built
 };
 
+// Rank bits (build(), dense well-formed indexes only; stream_kernels.cuh): the same sorted array A as
+// bit maps, one entry per 32 coordinates -- what the streaming count kernel stages in shared memory.
+//   t[k]  = { #{A < lo + 32k} | flags (bits 31, 30),  coordinates of word k holding >= 1 value }
+//   d2[k] = coordinates of word k holding >= 2 values
+struct RankBits {
+    const uint2* t;        // nullptr = not built
+    const uint32_t* d2;
+    int32_t lo;            // A[0]
+    uint32_t span;         // A[n-1] - A[0]
+    uint32_t nwords;       // ((span + 1) >> 5) + 1; both arrays are padded by >= 4 entries with prefix = n
+};
+
 // Stab lists (built on the first CSR fill of a well-formed index): a checkpoint every 2^kshift
 // positions; list b holds every interval below position b << kshift that is still open just after
 // the start at position (b << kshift) - 1,
@@ -92,6 +104,8 @@ struct IndexView {
     RankCells cells_s;       // rank cells over starts  } qk_count_cells_kernel; only on a well-formed
     RankCells cells_e;       // rank cells over eall    } index of fewer than 2^31 intervals
     StabLists stab;          // qk_fill_runs_kernel's lists; ent == nullptr -> it walks instead
+    RankBits bits_s;         // rank bits over starts  } sk_count_stream_kernel; only on a dense well-formed
+    RankBits bits_e;         // rank bits over eall    } index (t == nullptr otherwise)
     uint32_t n;
     uint32_t wellformed;     // 1 when every stored interval has start <= end (checked by build())
 };
@@ -501,11 +515,11 @@ __device__ __forceinline__ uint32_t cells_rank_lt(const RankCells& rc, const int
     return cell_rank(rc, A, r, cell, off, x);
 }
 
+// one tile of QC_TILE queries starting at `base` (whole CTA)
 template <typename CountT>
-__global__ void __launch_bounds__(QC_THREADS)
-qk_count_cells_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __restrict__ counts) {
+__device__ __forceinline__ void count_cells_tile(const IndexView& ix, const QueryRecords& rec, uint64_t base, uint32_t nq,
+                                                 CountT* __restrict__ counts) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    const uint64_t base = (uint64_t)blockIdx.x * QC_TILE;
     const RankCells cs = ix.cells_s, ce = ix.cells_e;
 
     int32_t qs[QC_PER_THREAD], qe[QC_PER_THREAD];
@@ -546,6 +560,12 @@ qk_count_cells_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __res
             else st_stream(counts + t, (CountT)c);
         }
     }
+}
+
+template <typename CountT>
+__global__ void __launch_bounds__(QC_THREADS)
+qk_count_cells_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __restrict__ counts) {
+    count_cells_tile<CountT>(ix, rec, (uint64_t)blockIdx.x * QC_TILE, nq, counts);
 }
 
 // ---- has_overlaps: tests ONLY the last candidate (hpp:865-871, quirk Q1) ----------------

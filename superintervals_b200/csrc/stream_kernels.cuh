@@ -1,0 +1,250 @@
+// stream_kernels.cuh -- count for POSITION-SORTED query batches at streaming speed (sm_100a).
+//
+// The reference answers a sorted batch faster than a shuffled one because consecutive
+// queries touch the same cache lines (superintervals.hpp:501-513 binary search + 651-825 walk;
+// test/generate_test_intervals.py:43-51 runs the sorted case). Here a CTA owns a contiguous
+// tile of the sorted batch, so everything its queries need from the index is ONE contiguous
+// window per table: the window is copied into shared memory by the TMA engine
+// (cp.async.bulk, completion on an mbarrier) and every rank is answered from shared memory.
+//
+// Closed form, as in qk_count_cells_kernel (well-formed index, qs <= qe):
+//     count = #{starts <= qe} - #{ends < qs}
+// Table: RankBits, one entry per 32 coordinates of a sorted array A,
+//     t[k]  = { #{A < lo + 32k} | flags,  b1 = coordinates of the word holding >= 1 value }
+//     d2[k] = coordinates of the word holding >= 2 values        (read only when RB_DUP is set)
+//     #{A < x} = prefix + popc(b1 & below(x)) + popc(d2 & below(x))
+// -- one 8-byte shared-memory load, a mask and a popc per rank. A word holding a coordinate
+// with three or more values (RB_SLOW) is answered from the rank cells in global memory.
+// 12 B per 32 coordinates: read once per pass over the batch, sequentially.
+//
+// Per tile of 2048 queries: 16 KB of queries in (256-bit loads), the two windows in (TMA),
+// 8 KB of counts out (256-bit stores). Nothing depends on the batch REALLY being sorted:
+// the window is [min, max] over the tile, and a tile whose window does not fit the staging
+// buffers (an unsorted or very sparse tile) answers each query from the rank cells instead.
+// Queries with qs > qe (quirk Q6) take the branch-array walk, as in every count kernel.
+#pragma once
+
+#include "query_kernels.cuh"
+
+namespace sib {
+
+constexpr uint32_t RB_DUP = 0x80000000u;    // d2[k] != 0
+constexpr uint32_t RB_SLOW = 0x40000000u;   // some coordinate of the word holds >= 3 values
+constexpr uint32_t RB_MASK = 0x3FFFFFFFu;
+
+// ---- build: one thread per word; ranks at the word borders come from the rank cells -------------
+__global__ void __launch_bounds__(256)
+sk_rank_bits_kernel(RankCells rc, const int32_t* __restrict__ A, uint32_t n, uint32_t nwords, uint32_t nwords_padded,
+                    uint2* __restrict__ t, uint32_t* __restrict__ d2, unsigned long long* __restrict__ slow_words) {
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t k = (uint64_t)blockIdx.x * 256 + threadIdx.x; k < nwords_padded; k += stride) {
+        if (k >= nwords) { t[k] = make_uint2(n, 0u); d2[k] = 0u; continue; }   // beyond A[n-1]: everything is below
+        const int64_t v0 = (int64_t)rc.lo + (int64_t)(k << 5);
+        const uint32_t p0 = k ? cells_rank_lt(rc, A, v0) : 0u;
+        const uint32_t p1 = cells_rank_lt(rc, A, v0 + 32);
+        uint32_t b1 = 0, b2 = 0, flags = 0;
+        int32_t prev = 0;
+        uint32_t run = 0;
+        for (uint32_t i = p0; i < p1; ++i) {
+            const int32_t a = ld_nc(A + i);
+            run = (i > p0 && a == prev) ? run + 1u : 1u;
+            prev = a;
+            const uint32_t bit = 1u << (uint32_t)((int64_t)a - v0);
+            if (run == 1u) b1 |= bit;
+            else if (run == 2u) b2 |= bit;
+            else flags |= RB_SLOW;
+        }
+        if (b2) flags |= RB_DUP;
+        if (flags & RB_SLOW) atomicAdd(slow_words, 1ull);
+        t[k] = make_uint2(p0 | flags, b1);
+        d2[k] = b2;
+    }
+}
+
+// ---- PTX: mbarrier + TMA bulk copy (SASS: SYNCS / UBLKCP) ------------------------------------------
+__device__ __forceinline__ uint32_t sk_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sk_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sk_smem(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void sk_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sk_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sk_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sk_smem(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(sk_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void sk_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(sk_smem(bar)), "r"(parity) : "memory");
+    }
+}
+
+struct __align__(32) Vec8 { uint32_t w[8]; };
+__device__ __forceinline__ Vec8 sk_ld8(const int32_t* p) {
+    Vec8 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void sk_st8(uint32_t* p, const uint32_t* c) {
+    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(c[5]), "r"(c[6]), "r"(c[7]) : "memory");
+}
+__device__ __forceinline__ void sk_st8(uint64_t* p, const uint32_t* c) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        __stcs(reinterpret_cast<ulonglong2*>(p) + k, make_ulonglong2((unsigned long long)c[2 * k], (unsigned long long)c[2 * k + 1]));
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------------
+constexpr int SK_THREADS = 256;
+constexpr int SK_PER_THREAD = 8;
+constexpr uint32_t SK_TILE = SK_THREADS * SK_PER_THREAD;   // 2048 queries: 16 KB in, 8 KB out
+#ifndef SIB_SK_SW
+#define SIB_SK_SW 1536
+#endif
+#ifndef SIB_SK_EW
+#define SIB_SK_EW 768
+#endif
+constexpr uint32_t SK_SW = SIB_SK_SW;   // staged words of the starts table (x 32 coordinates)
+constexpr uint32_t SK_EW = SIB_SK_EW;   // staged words of the ends table
+constexpr size_t SK_SMEM = (size_t)(SK_SW + SK_EW) * 12 + 64;
+
+// d = x - lo clamped to [0, span + 1]: everything below A ranks 0, everything above ranks n
+__device__ __forceinline__ uint32_t sk_clamp(int64_t x, int32_t lo, uint32_t span) {
+    int64_t d = x - (int64_t)lo;
+    d = d < 0 ? 0 : d;
+    const int64_t dmax = (int64_t)span + 1;
+    return (uint32_t)(d > dmax ? dmax : d);
+}
+
+#ifndef SIB_SK_MINBLOCKS
+#define SIB_SK_MINBLOCKS 4
+#endif
+// fail_list / fail_count: tiles this kernel does not answer -- their window does not fit the staging
+// buffers (an unsorted or very sparse tile) or they hold a query with qs > qe (quirk Q6: the closed
+// form does not apply) -- are appended here and answered by sk_count_failed_tiles_kernel right after.
+template <typename CountT>
+__global__ void __launch_bounds__(SK_THREADS, SIB_SK_MINBLOCKS)
+sk_count_stream_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* __restrict__ qe_in, uint32_t nq,
+                       CountT* __restrict__ counts, uint32_t vec_ok, uint32_t* __restrict__ fail_list,
+                       uint32_t* __restrict__ fail_count) {
+    extern __shared__ __align__(128) unsigned char sk_sh[];
+    uint2* Ts = reinterpret_cast<uint2*>(sk_sh);
+    uint2* Te = Ts + SK_SW;
+    uint32_t* Ds = reinterpret_cast<uint32_t*>(Te + SK_EW);
+    uint32_t* De = Ds + SK_SW;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(De + SK_EW);
+    __shared__ uint32_t s_red[SK_THREADS / 32][5];
+    __shared__ uint32_t s_win[4];   // first staged word of each table, staged?
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const RankBits bs = ix.bits_s, be = ix.bits_e;
+    const uint64_t base = (uint64_t)blockIdx.x * SK_TILE + (uint64_t)tid * SK_PER_THREAD;
+
+    if (tid == 0) sk_mbar_init(bar, 1);
+
+    int32_t qs[SK_PER_THREAD], qe[SK_PER_THREAD];
+    const bool full = base + SK_PER_THREAD <= nq;
+    if (full && vec_ok) {
+        const Vec8 a = sk_ld8(qs_in + base), b = sk_ld8(qe_in + base);
+#pragma unroll
+        for (int j = 0; j < SK_PER_THREAD; ++j) { qs[j] = (int32_t)a.w[j]; qe[j] = (int32_t)b.w[j]; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < SK_PER_THREAD; ++j) {
+            const bool live = base + j < nq;
+            qs[j] = live ? ld_stream(qs_in + base + j) : 0;
+            qe[j] = live ? ld_stream(qe_in + base + j) : 0;
+        }
+    }
+    // where each rank falls, and the tile's window of words in either table
+    uint32_t ds[SK_PER_THREAD], de[SK_PER_THREAD];
+    uint32_t smin = 0xFFFFFFFFu, smax = 0, emin = 0xFFFFFFFFu, emax = 0, inv = 0;
+#pragma unroll
+    for (int j = 0; j < SK_PER_THREAD; ++j) {
+        ds[j] = sk_clamp((int64_t)qe[j] + 1, bs.lo, bs.span);   // #{starts <= qe} = #{starts < qe + 1}
+        de[j] = sk_clamp((int64_t)qs[j], be.lo, be.span);       // #{ends < qs}
+        if (base + j < nq) {
+            smin = min(smin, ds[j]); smax = max(smax, ds[j]);
+            emin = min(emin, de[j]); emax = max(emax, de[j]);
+            inv |= qs[j] > qe[j] ? 1u : 0u;
+        }
+    }
+    smin = __reduce_min_sync(FULL_MASK, smin); smax = __reduce_max_sync(FULL_MASK, smax);
+    emin = __reduce_min_sync(FULL_MASK, emin); emax = __reduce_max_sync(FULL_MASK, emax);
+    inv = __reduce_or_sync(FULL_MASK, inv);
+    if (lane == 0) { s_red[warp][0] = smin; s_red[warp][1] = smax; s_red[warp][2] = emin; s_red[warp][3] = emax; s_red[warp][4] = inv; }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int w = 1; w < SK_THREADS / 32; ++w) {
+            smin = min(smin, s_red[w][0]); smax = max(smax, s_red[w][1]);
+            emin = min(emin, s_red[w][2]); emax = max(emax, s_red[w][3]);
+            inv |= s_red[w][4];
+        }
+        // windows in words, first word aligned to 4 (16-byte granules of both arrays), length a multiple of 4
+        const uint32_t ks0 = (smin >> 5) & ~3u, ke0 = (emin >> 5) & ~3u;
+        const uint32_t ls = (((smax >> 5) - ks0) | 3u) + 1u, le = (((emax >> 5) - ke0) | 3u) + 1u;
+        const bool ok = !inv && ls <= SK_SW && le <= SK_EW;
+        s_win[0] = ks0; s_win[1] = ke0; s_win[2] = ok ? 1u : 0u;
+        if (ok) {
+            sk_mbar_expect_tx(bar, (ls + le) * 12u);
+            sk_bulk_g2s(Ts, bs.t + ks0, ls * 8u, bar);
+            sk_bulk_g2s(Te, be.t + ke0, le * 8u, bar);
+            sk_bulk_g2s(Ds, bs.d2 + ks0, ls * 4u, bar);
+            sk_bulk_g2s(De, be.d2 + ke0, le * 4u, bar);
+        } else {
+            fail_list[atomicAdd(fail_count, 1u)] = blockIdx.x;
+        }
+    }
+    __syncthreads();
+    if (s_win[2] == 0) return;
+    const uint32_t ks0 = s_win[0], ke0 = s_win[1];
+    sk_mbar_wait(bar, 0);
+    uint32_t c[SK_PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < SK_PER_THREAD; ++j) {
+        const uint32_t k1 = (ds[j] >> 5) - ks0, k2 = (de[j] >> 5) - ke0;
+        const uint2 e1 = Ts[k1], e2 = Te[k2];
+        const uint32_t m1 = (1u << (ds[j] & 31u)) - 1u, m2 = (1u << (de[j] & 31u)) - 1u;
+        uint32_t ns = (e1.x & RB_MASK) + __popc(e1.y & m1);
+        uint32_t ne = (e2.x & RB_MASK) + __popc(e2.y & m2);
+        if (e1.x & RB_DUP) ns += __popc(Ds[k1] & m1);
+        if (e2.x & RB_DUP) ne += __popc(De[k2] & m2);
+        if ((e1.x | e2.x) & RB_SLOW) {   // a coordinate with >= 3 values in one of the words: rank cells (rare)
+            if (e1.x & RB_SLOW) ns = cells_rank_lt(ix.cells_s, ix.starts, (int64_t)qe[j] + 1);
+            if (e2.x & RB_SLOW) ne = cells_rank_lt(ix.cells_e, ix.eall, (int64_t)qs[j]);
+        }
+        c[j] = ns - ne;
+    }
+    if (full && vec_ok) {
+        sk_st8(counts + base, c);
+    } else {
+#pragma unroll
+        for (int j = 0; j < SK_PER_THREAD; ++j)
+            if (base + j < nq) counts[base + j] = (CountT)c[j];
+    }
+}
+
+// The tiles the streaming kernel handed back, by the rank-cells code (any order, inverted queries walk).
+// Persistent grid: a sorted batch leaves the list empty and the kernel returns at once.
+template <typename CountT>
+__global__ void __launch_bounds__(QC_THREADS)
+sk_count_failed_tiles_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* __restrict__ qe_in, uint32_t nq,
+                             CountT* __restrict__ counts, const uint32_t* __restrict__ fail_list,
+                             const uint32_t* __restrict__ fail_count) {
+    const uint32_t nfail = *fail_count;
+    const QueryRecords rec{qs_in, qe_in, nullptr};
+    constexpr uint32_t PARTS = SK_TILE / QC_TILE;
+    for (uint32_t w = blockIdx.x; w < nfail * PARTS; w += gridDim.x) {
+        const uint64_t base = (uint64_t)fail_list[w / PARTS] * SK_TILE + (uint64_t)(w % PARTS) * QC_TILE;
+        if (base < nq) count_cells_tile<CountT>(ix, rec, base, nq, counts);
+    }
+}
+
+}  // namespace sib

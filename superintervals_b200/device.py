@@ -13,12 +13,12 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (OPT_STAB_BUDGET, OPT_STAB_LISTS, COUNT_AUTO, COUNT_CELLS, COUNT_RANK, COUNT_WALK, OPT_CELLS_DIRECT_BYTES, OPT_CELLS_FILL, FILL_IDXS, FILL_ITEMS, FILL_KEYS, FILL_VALUES, OPT_BUCKET_INTERVALS,
+from ._lib import (OPT_STREAM, OPT_STREAM_BUDGET, OPT_STAB_BUDGET, OPT_STAB_LISTS, COUNT_AUTO, COUNT_CELLS, COUNT_RANK, COUNT_WALK, OPT_CELLS_DIRECT_BYTES, OPT_CELLS_FILL, FILL_IDXS, FILL_ITEMS, FILL_KEYS, FILL_VALUES, OPT_BUCKET_INTERVALS,
                    OPT_COUNT_ALGO, OPT_TIMING, OPT_WINDOW_SHIFT, ORDER_ASIS, ORDER_AUTO, ORDER_SORTED, ORDER_UNSORTED)
 
 __all__ = ["DeviceIndex", "ORDER_AUTO", "ORDER_SORTED", "ORDER_UNSORTED", "ORDER_ASIS", "OPT_COUNT_ALGO",
            "OPT_BUCKET_INTERVALS", "OPT_WINDOW_SHIFT", "OPT_TIMING", "COUNT_AUTO", "COUNT_WALK", "COUNT_RANK", "COUNT_CELLS",
-           "OPT_CELLS_DIRECT_BYTES", "OPT_CELLS_FILL", "OPT_STAB_LISTS", "OPT_STAB_BUDGET"]
+           "OPT_CELLS_DIRECT_BYTES", "OPT_CELLS_FILL", "OPT_STAB_LISTS", "OPT_STAB_BUDGET", "OPT_STREAM", "OPT_STREAM_BUDGET"]
 
 
 def _stream():
@@ -134,6 +134,13 @@ class DeviceIndex:
             out[name] = {"format": int(ci.format), "shift": int(ci.shift), "cells": int(ci.cells), "bytes": int(ci.bytes),
                          "overfull": int(ci.overfull), "direct": bool(ci.direct)}
         return out
+
+    def bits_info(self):
+        """Rank bits of the streaming count (siIndexBitsInfo): built, words, bytes, slow_words."""
+        bi = _lib.siBitsInfo()
+        if self._L.siIndexBitsInfo(self._ix, C.byref(bi)):
+            raise RuntimeError("siIndexBitsInfo: index not built")
+        return {"built": bool(bi.built), "words": int(bi.words), "bytes": int(bi.bytes), "slow_words": int(bi.slow_words)}
 
     def stab_info(self):
         """Stab lists of the CSR fill (siIndexStabInfo): state 0 not made yet / 1 in use / 2 the fill walks."""
