@@ -14,8 +14,12 @@
 // Differences from the reference, all outside the accelerated path:
 //   * S must be a 32-bit integer type (the reference's AVX2 path has the same
 //     restriction, hpp:688; its C ABI is int32 only).
-//   * The lazy iterator classes are not provided: search_idxs(s,e)/search_items(s,e) return eager
-//     ranges. IntervalMapEytz is the same implementation under the reference's name.
+//   * The range classes IndexRange / KeyRange / ValueRange / ItemRange (hpp:153-494) exist with the
+//     reference's names and iteration order; begin() runs the query on the device (one round trip
+//     for the whole hit list) and the iterators then step through it, reading the host mirrors.
+//     IntervalMapEytz is the same implementation under the reference's name.
+//   * const queries may be called from several threads at once, as in the reference: per-thread
+//     scratch here, and the library serialises the calls that reach one handle.
 //   * The set algebra (hpp:1037-1390) is provided on top of the C ABI's device set
 //     operations; `other` arguments must have been built.
 //   * New: count_batch / search_values_batch / search_idxs_batch / search_keys_batch
@@ -26,6 +30,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <limits>
+#include <memory>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -58,7 +63,11 @@ class IntervalMap {
     virtual ~IntervalMap() { destroySuperIntervals(h_); }
     IntervalMap(const IntervalMap&) = delete;
     IntervalMap& operator=(const IntervalMap&) = delete;
-    IntervalMap(IntervalMap&& o) noexcept { *this = std::move(o); }
+    IntervalMap(IntervalMap&& o) noexcept
+        : starts(std::move(o.starts)), ends(std::move(o.ends)), branch(std::move(o.branch)), data(std::move(o.data)),
+          start_sorted(o.start_sorted), end_sorted(o.end_sorted), h_(o.h_) {
+        o.h_ = nullptr;
+    }
     IntervalMap& operator=(IntervalMap&& o) noexcept {
         if (this != &o) {
             destroySuperIntervals(h_);
@@ -92,7 +101,9 @@ class IntervalMap {
         addIntervals(h_, reinterpret_cast<const int32_t*>(starts.data()),
                      reinterpret_cast<const int32_t*>(ends.data()), nullptr, starts.size());
         indexSuperIntervals(h_);
-        if (si_b200_last_error()) return;   // inspect si_b200_last_error_string()
+        // success is "this handle now carries a device index" -- not the process-wide sticky error flag,
+        // which an unrelated earlier failure may have left set
+        if (siIndexOf(h_) == nullptr) return;   // inspect si_b200_last_error_string(); the map stays not ready
         const size_t n = starts.size();
         std::vector<T> sorted;
         sorted.reserve(n);
@@ -118,9 +129,8 @@ class IntervalMap {
     // ---- single queries: appended to `found`, descending position order -------------------
     void search_values(const S start, const S end, std::vector<T>& found) const {   // hpp:551-579
         if (!ready()) return;
-        scratch_.size = 0;
-        searchIdxs(h_, (int32_t)start, (int32_t)end, &scratch_);
-        for (size_t k = 0; k < scratch_.size; ++k) found.push_back(data[(size_t)(uint32_t)scratch_.data[k]]);
+        const cIndexResult& r = hit_positions(start, end);
+        for (size_t k = 0; k < r.size; ++k) found.push_back(data[(size_t)(uint32_t)r.data[k]]);
     }
     void search_values_large(const S start, const S end, std::vector<T>& found) const {   // hpp:588: same output
         search_values(start, end, found);
@@ -141,11 +151,10 @@ class IntervalMap {
     // descending; reproduced here from the descending device result.
     void search_idxs(const S start, const S end, std::vector<size_t>& found) const {
         if (!ready()) return;
-        scratch_.size = 0;
-        searchIdxs(h_, (int32_t)start, (int32_t)end, &scratch_);
+        const cIndexResult& r = hit_positions(start, end);
         const size_t first = found.size();
-        for (size_t k = 0; k < scratch_.size; ++k) found.push_back((size_t)(uint32_t)scratch_.data[k]);
-        if (scratch_.size == 0) return;
+        for (size_t k = 0; k < r.size; ++k) found.push_back((size_t)(uint32_t)r.data[k]);
+        if (r.size == 0) return;
         const size_t ub = (size_t)(std::upper_bound(starts.begin(), starts.end(), end) - starts.begin()) - 1;
         if (found[first] != ub) return;
         size_t run = 1;
@@ -163,10 +172,9 @@ class IntervalMap {
 
     void search_items(const S start, const S end, std::vector<Interval<S, T>>& found) const {   // hpp:946-971
         if (!ready()) return;
-        scratch_.size = 0;
-        searchIdxs(h_, (int32_t)start, (int32_t)end, &scratch_);
-        for (size_t k = 0; k < scratch_.size; ++k) {
-            const size_t j = (size_t)(uint32_t)scratch_.data[k];
+        const cIndexResult& r = hit_positions(start, end);
+        for (size_t k = 0; k < r.size; ++k) {
+            const size_t j = (size_t)(uint32_t)r.data[k];
             found.emplace_back(starts[j], ends[j], data[j]);
         }
     }
@@ -180,20 +188,74 @@ class IntervalMap {
         cov_result.second += (S)v;
     }
 
-    // eager stand-ins for the reference's lazy ranges (hpp:153-494): usable in range-for
-    std::vector<size_t> search_idxs(const S start, const S end) const {
-        std::vector<size_t> v;
-        if (!ready()) return v;
-        scratch_.size = 0;
-        searchIdxs(h_, (int32_t)start, (int32_t)end, &scratch_);
-        for (size_t k = 0; k < scratch_.size; ++k) v.push_back((size_t)(uint32_t)scratch_.data[k]);
-        return v;   // all-descending, like the reference's IndexRange
-    }
-    std::vector<Interval<S, T>> search_items(const S start, const S end) const {
-        std::vector<Interval<S, T>> v;
-        search_items(start, end, v);
-        return v;
-    }
+    // ---- range objects (hpp:153-494): `for (auto x : map.search_idxs(s, e))` ------------------
+    // Same class names, same descending iteration order, same "end() compares by exhaustion"
+    // convention as the reference. The reference's iterators walk the branch array one hit at a
+    // time on the host; here begin() asks the device for the query's whole hit list once and the
+    // iterator steps through those positions, projecting each on the host mirrors.
+   private:
+    struct ProjIndex { using value_type = size_t;
+        static void get(const IntervalMap* m, size_t j, value_type& v) { (void)m; v = j; } };
+    struct ProjKey { using value_type = std::pair<S, S>;
+        static void get(const IntervalMap* m, size_t j, value_type& v) { v.first = m->starts[j]; v.second = m->ends[j]; } };
+    struct ProjValue { using value_type = T;
+        static void get(const IntervalMap* m, size_t j, value_type& v) { v = m->data[j]; } };
+    struct ProjItem { using value_type = Interval<S, T>;
+        static void get(const IntervalMap* m, size_t j, value_type& v) { v.start = m->starts[j]; v.end = m->ends[j]; v.data = m->data[j]; } };
+
+    template <typename Proj>
+    class HitIterator {
+       public:
+        using value_type = typename Proj::value_type;
+        HitIterator() = default;   // exhausted
+        HitIterator(const IntervalMap* parent, std::shared_ptr<const std::vector<uint32_t>> hits)
+            : parent_(parent), hits_(std::move(hits)) { load(); }
+        const value_type& operator*() const { return value_; }
+        HitIterator& operator++() { ++at_; load(); return *this; }
+        bool operator!=(const HitIterator& o) const { return has_value_ != o.has_value_; }
+        bool operator==(const HitIterator& o) const { return has_value_ == o.has_value_; }
+       private:
+        void load() {
+            has_value_ = hits_ && at_ < hits_->size();
+            if (has_value_) Proj::get(parent_, (size_t)(*hits_)[at_], value_);
+        }
+        const IntervalMap* parent_ = nullptr;
+        std::shared_ptr<const std::vector<uint32_t>> hits_;
+        size_t at_ = 0;
+        bool has_value_ = false;
+        value_type value_{};
+    };
+    template <typename Proj>
+    class HitRange {
+       public:
+        HitRange(const IntervalMap* parent, S start, S end) : parent_(parent), start_(start), end_(end) {}
+        HitIterator<Proj> begin() const {
+            auto hits = std::make_shared<std::vector<uint32_t>>();
+            if (parent_->ready()) {
+                const cIndexResult& r = parent_->hit_positions(start_, end_);
+                hits->assign(reinterpret_cast<const uint32_t*>(r.data), reinterpret_cast<const uint32_t*>(r.data) + r.size);
+            }
+            return HitIterator<Proj>(parent_, std::move(hits));
+        }
+        HitIterator<Proj> end() const { return HitIterator<Proj>(); }
+       private:
+        const IntervalMap* parent_;
+        S start_, end_;
+    };
+
+   public:
+    using IndexIterator = HitIterator<ProjIndex>;   // hpp:153
+    using IndexRange = HitRange<ProjIndex>;         // hpp:211
+    using KeyIterator = HitIterator<ProjKey>;       // hpp:237
+    using KeyRange = HitRange<ProjKey>;             // hpp:297
+    using ValueIterator = HitIterator<ProjValue>;   // hpp:324
+    using ValueRange = HitRange<ProjValue>;         // hpp:382
+    using ItemIterator = HitIterator<ProjItem>;     // hpp:408
+    using ItemRange = HitRange<ProjItem>;           // hpp:470
+    IndexRange search_idxs(S start, S end) const noexcept { return IndexRange(this, start, end); }     // hpp:233
+    KeyRange search_keys(S start, S end) const noexcept { return KeyRange(this, start, end); }         // hpp:319
+    ValueRange search_values(S start, S end) const noexcept { return ValueRange(this, start, end); }   // hpp:404
+    ItemRange search_items(S start, S end) const noexcept { return ItemRange(this, start, end); }      // hpp:492
 
     // ---- batch queries (the throughput path; shaped after intervalmap.pyx:363-494) --------
     void count_batch(const S* qs, const S* qe, size_t n, std::vector<size_t>& counts) const {
@@ -411,12 +473,20 @@ class IntervalMap {
         return order;
     }
     bool ready() const { return h_ != nullptr && !starts.empty() && siIndexOf(h_) != nullptr; }
-    cSuperIntervals* h_;
-    mutable cIndexResult scratch_ = {nullptr, 0, 0};
-
-   public:
-    // scratch_ is malloc'd by the library; released with the object
-    struct ScratchGuard { cIndexResult* r; ~ScratchGuard() { destroyIndexResult(r); } } guard_{&scratch_};
+    // positions of the hits of one query, descending: one scratch buffer per calling thread, so that const
+    // queries stay re-entrant like the reference's (hpp:551, 651)
+    static cIndexResult& scratch() {
+        struct Holder { cIndexResult r = {nullptr, 0, 0}; ~Holder() { destroyIndexResult(&r); } };
+        thread_local Holder h;
+        return h.r;
+    }
+    cIndexResult& hit_positions(const S start, const S end) const {
+        cIndexResult& r = scratch();
+        r.size = 0;
+        searchIdxs(h_, (int32_t)start, (int32_t)end, &r);
+        return r;
+    }
+    cSuperIntervals* h_ = nullptr;
 };
 
 // hpp:1457-1535: IntervalMapEytz keeps the starts in Eytzinger order for a cache-friendlier CPU

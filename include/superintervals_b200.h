@@ -189,6 +189,10 @@ typedef struct {
     unsigned long long words, bytes, slow_words;
 } siBitsInfo;
 int siIndexBitsInfo(const siIndex* ix, siBitsInfo* out);
+/* The last streaming count (its last slice of 2^27 queries): tiles of 2048 queries launched, and how many of them the
+ * streaming kernel handed back to the rank-cells code (window too wide for the staging buffers, or a query with
+ * start > end inside). Synchronises the device. */
+int siIndexStreamStats(siIndex* ix, unsigned long long* tiles, unsigned long long* handed_back);
 /* The stab lists of the CSR fill (made by the first siFillDevice after a build): state 0 = not
  * made yet, 1 = in use, 2 = over budget or too small (the fill walks); a checkpoint every
  * 2^shift positions, `lists` lists holding `entries` records of `record_bytes` bytes. */

@@ -105,7 +105,7 @@ B200_SYMBOLS = [
     "countOverlapsBatch", "anyOverlapsBatch", "searchValuesBatch", "searchIdxsBatch", "searchKeysBatch",
     "searchItemsBatch", "coverageBatch", "intersectionPairs", "siParseBed", "siBedTableFree", "siIndexCreate", "siIndexDestroy", "siIndexOf", "siIndexSize",
     "siIndexDeviceView", "siIndexBuildHost", "siIndexBuildDevice", "siIndexExport", "siCountDevice",
-    "siCountDevice64", "siSortQueriesDevice", "siIndexSetOption", "siIndexCellsInfo", "siIndexBitsInfo", "siIndexStabInfo", "siIndexReadTimings", "siAnyDevice", "siScanDevice", "siFillDevice", "siCoverageDevice",
+    "siCountDevice64", "siSortQueriesDevice", "siIndexSetOption", "siIndexCellsInfo", "siIndexBitsInfo", "siIndexStreamStats", "siIndexStabInfo", "siIndexReadTimings", "siAnyDevice", "siScanDevice", "siFillDevice", "siCoverageDevice",
     "siIndexDeviceBytes",
 ]
 
@@ -202,6 +202,8 @@ def bind_b200(L):
     L.siIndexCellsInfo.restype = C.c_int
     L.siIndexBitsInfo.argtypes = [vp, C.POINTER(siBitsInfo)]
     L.siIndexBitsInfo.restype = C.c_int
+    L.siIndexStreamStats.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    L.siIndexStreamStats.restype = C.c_int
     if hasattr(L, "intersectionPairs"):
         L.intersectionPairs.restype = SI
         L.intersectionPairs.argtypes = [SI, SI, C.POINTER(cIndexResult)]

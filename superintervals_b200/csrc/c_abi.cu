@@ -19,6 +19,7 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 extern "C" int si_b200_upper_bound_(siIndex* ix, int32_t value, size_t* out);
@@ -114,6 +115,56 @@ void parallel_memcpy(void* dst, const void* src, size_t bytes, bool to_output = 
     });
 }
 
+// ---- registered result buffers ------------------------------------------------------------------
+namespace {
+std::mutex g_reg_mu;
+std::unordered_map<void*, size_t> g_registered;   // base pointer -> registered bytes
+constexpr size_t REGISTER_MIN = (size_t)1 << 20;  // smaller buffers stay plain realloc memory
+
+bool unregister_if_ours(void* p) {
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    auto it = g_registered.find(p);
+    if (it == g_registered.end()) return false;
+    if (cudaHostUnregister(p) != cudaSuccess) (void)cudaGetLastError();
+    g_registered.erase(it);
+    return true;
+}
+}  // namespace
+
+void* result_realloc(void* old, size_t old_bytes, size_t new_bytes) {
+    if (new_bytes < REGISTER_MIN) {
+        if (old && unregister_if_ours(old)) {      // cannot happen (buffers only grow), kept for safety
+            void* q = malloc(new_bytes);
+            if (q) memcpy(q, old, old_bytes < new_bytes ? old_bytes : new_bytes);
+            free(old);
+            return q;
+        }
+        return realloc(old, new_bytes);
+    }
+    const size_t bytes = (new_bytes + 4095) & ~(size_t)4095;
+    void* q = aligned_alloc(4096, bytes);
+    if (!q) return nullptr;
+    if (old) {
+        if (old_bytes) memcpy(q, old, old_bytes);
+        unregister_if_ours(old);
+        free(old);
+    }
+    // pins (and so first-touches) the pages; on failure the buffer simply stays pageable
+    if (cudaHostRegister(q, bytes, cudaHostRegisterDefault) == cudaSuccess) {
+        std::lock_guard<std::mutex> lk(g_reg_mu);
+        g_registered[q] = bytes;
+    } else {
+        (void)cudaGetLastError();
+    }
+    return q;
+}
+
+void result_free(void* p) {
+    if (!p) return;
+    unregister_if_ours(p);
+    free(p);
+}
+
 bool is_pinned(const void* p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
@@ -199,6 +250,7 @@ int search_batch(Handle* h, const int32_t* qs, const int32_t* qe, size_t n, size
                  int what, size_t elem) {
     siIndex* ix = h->ix;
     if (n == 0) { if (offsets_out) offsets_out[0] = 0; return 0; }
+    std::lock_guard<std::mutex> lk(ix->api_mu);
     int rc = stage_queries(ix, qs, qe, n);
     if (rc) return rc;
     if (ix->h_counts.ensure(n * 4 + 64) || ix->h_offsets.ensure((n + 1) * 8 + 64)) return last_error_code();
@@ -433,6 +485,7 @@ void countOverlapsBatch(cSuperIntervals* si, const int32_t* starts, const int32_
     if (!handle_ready(h, "countOverlapsBatch")) { memset(counts_out, 0, n * sizeof(size_t)); return; }
     siIndex* ix = h->ix;
     static_assert(sizeof(size_t) == 8, "LP64 only");
+    std::lock_guard<std::mutex> lk(ix->api_mu);
     if (n > ((size_t)12 << 20)) {
         count_batch_pipelined(ix, starts, ends, n, counts_out);
         return;
@@ -452,6 +505,7 @@ void anyOverlapsBatch(cSuperIntervals* si, const int32_t* starts, const int32_t*
     if (si->size == 0) { memset(out, 0, n); return; }
     if (!handle_ready(h, "anyOverlapsBatch")) { memset(out, 0, n); return; }
     siIndex* ix = h->ix;
+    std::lock_guard<std::mutex> lk(ix->api_mu);
     if (stage_queries(ix, starts, ends, n) || ix->h_counts.ensure(n)) return;
     if (siAnyDevice(ix, ix->h_qs.as<int32_t>(), ix->h_qe.as<int32_t>(), n, ix->h_counts.as<uint8_t>(), ix->own_stream))
         return;
@@ -487,6 +541,7 @@ void coverageBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* en
         return;
     }
     siIndex* ix = h->ix;
+    std::lock_guard<std::mutex> lk(ix->api_mu);
     if (stage_queries(ix, starts, ends, n) || ix->h_counts.ensure(n * 4) || ix->h_cov.ensure(n * 4)) return;
     if (siCoverageDevice(ix, ix->h_qs.as<int32_t>(), ix->h_qe.as<int32_t>(), n, ix->h_counts.as<uint32_t>(),
                          ix->h_cov.as<int32_t>(), ix->own_stream))
@@ -504,7 +559,10 @@ void coverageBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* en
 size_t upperBound(cSuperIntervals* si, int32_t value) {
     Handle* h = H(si);
     size_t r = SI_NONE;
-    if (si->size != 0 && handle_ready(h, "upperBound")) si_b200_upper_bound_(h->ix, value, &r);
+    if (si->size != 0 && handle_ready(h, "upperBound")) {
+        std::lock_guard<std::mutex> lk(h->ix->api_mu);
+        si_b200_upper_bound_(h->ix, value, &r);
+    }
     si->idx = r;   // ref:539,562,566
     return r;
 }
@@ -547,18 +605,18 @@ void findOverlaps(cSuperIntervals* si, int32_t start, int32_t end, int32_t* foun
     searchValuesBatch(si, &start, &end, 1, nullptr, &tmp);
     if (tmp.size) memcpy(found, tmp.data, tmp.size * sizeof(int32_t));
     *found_size = tmp.size;
-    free(tmp.data);
+    result_free(tmp.data);
 }
 
 // ---- result buffers (ref:1066-1089) -----------------------------------------------------------
 cIndexResult createIndexResult(void) { cIndexResult r = {nullptr, 0, 0}; return r; }
 void clearIndexResult(cIndexResult* r) { r->size = 0; }
-void destroyIndexResult(cIndexResult* r) { free(r->data); r->data = nullptr; r->size = r->capacity = 0; }
+void destroyIndexResult(cIndexResult* r) { result_free(r->data); r->data = nullptr; r->size = r->capacity = 0; }
 cKeyResult createKeyResult(void) { cKeyResult r = {nullptr, 0, 0}; return r; }
 void clearKeyResult(cKeyResult* r) { r->size = 0; }
-void destroyKeyResult(cKeyResult* r) { free(r->data); r->data = nullptr; r->size = r->capacity = 0; }
+void destroyKeyResult(cKeyResult* r) { result_free(r->data); r->data = nullptr; r->size = r->capacity = 0; }
 cItemResult createItemResult(void) { cItemResult r = {nullptr, 0, 0}; return r; }
 void clearItemResult(cItemResult* r) { r->size = 0; }
-void destroyItemResult(cItemResult* r) { free(r->data); r->data = nullptr; r->size = r->capacity = 0; }
+void destroyItemResult(cItemResult* r) { result_free(r->data); r->data = nullptr; r->size = r->capacity = 0; }
 
 }  // extern "C"

@@ -28,12 +28,20 @@ inline const Handle* H(const cSuperIntervals* si) { return reinterpret_cast<cons
 // true when the handle carries a built device index; latches an error otherwise
 bool handle_ready(Handle* h, const char* who);
 
+// Result buffers (cIndexResult / cKeyResult / cItemResult .data) are library-owned memory that the
+// reference grows by realloc and frees in destroy*Result (c.h:585-588, 1066-1089). Large ones are
+// page-aligned malloc memory REGISTERED with the CUDA driver (cudaHostRegister), so that the device
+// copies results straight into them by DMA instead of through a pinned staging slot and a host memcpy.
+// They remain ordinary malloc memory to the caller; result_free() un-registers before freeing.
+void* result_realloc(void* old, size_t old_bytes, size_t new_bytes);
+void result_free(void* p);
+
 template <typename R>
 bool grow(R* r, size_t need_total, size_t elem) {
     if (need_total <= r->capacity) return true;
     size_t cap = r->capacity ? r->capacity : 16;   // reference growth: x2 from 16 (c.h:585-588)
     while (cap < need_total) cap *= 2;
-    void* p = realloc(r->data, cap * elem);
+    void* p = result_realloc(r->data, r->size * elem, cap * elem);
     if (!p) { set_error_msg(cudaErrorMemoryAllocation, "realloc of result buffer failed"); return false; }
     r->data = reinterpret_cast<decltype(r->data)>(p);
     r->capacity = cap;

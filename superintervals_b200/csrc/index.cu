@@ -520,6 +520,7 @@ int launch_count_stream(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, u
     uint32_t* fail_count = ix->stream_ws.as<uint32_t>();
     uint32_t* fail_list = fail_count + 8;
     SIB_CHECK(cudaMemsetAsync(fail_count, 0, 4, s));
+    ix->stream_tiles = (unsigned long long)grid;
     ix->timer.begin(TAG_COUNT_STREAM, s);
     sk_count_stream_kernel<CountT><<<grid, SK_THREADS, SK_SMEM, s>>>(view_of(ix), d_qs, d_qe, nq, d_counts, vec_ok, fail_list, fail_count);
     SIB_CHECK_LAUNCH();
@@ -730,6 +731,19 @@ int siIndexBitsInfo(const siIndex* ix, siBitsInfo* out) {
     out->words = ix->bits_ok ? (unsigned long long)ix->bits_words_s + ix->bits_words_e : 0;
     out->bytes = out->words * 12;
     out->slow_words = ix->bits_slow[0] + ix->bits_slow[1];
+    return 0;
+}
+
+int siIndexStreamStats(siIndex* ix, unsigned long long* tiles, unsigned long long* handed_back) {
+    if (!ix || !tiles || !handed_back) return cudaErrorInvalidValue;
+    *tiles = ix->stream_tiles;
+    *handed_back = 0;
+    if (!ix->stream_tiles || !ix->stream_ws.p) return 0;
+    DeviceGuard g(ix->device);
+    uint32_t f = 0;
+    SIB_CHECK(cudaDeviceSynchronize());
+    SIB_CHECK(cudaMemcpy(&f, ix->stream_ws.p, 4, cudaMemcpyDeviceToHost));
+    *handed_back = f;
     return 0;
 }
 

@@ -3,6 +3,8 @@
 
 #include "common.cuh"
 
+#include <mutex>
+
 struct siIndex;   // C-visible opaque name
 
 namespace sib {
@@ -63,6 +65,7 @@ struct siIndex {
     // rank bits (RankBits in query_kernels.cuh): 12 B per 32 coordinates of the span, per table; the
     // streaming count kernel's tables. Built only when they cost at most bits_budget bytes per interval.
     sib::DevBuf bits_s_t, bits_s_d, bits_e_t, bits_e_d;
+    unsigned long long stream_tiles = 0;           // tiles of the last streaming count (siIndexStreamStats)
     sib::DevBuf stream_ws;                         // tiles the streaming kernel hands to the rank-cells code (count + list)
     uint32_t bits_words_s = 0, bits_words_e = 0;
     bool bits_ok = false;
@@ -98,6 +101,11 @@ struct siIndex {
     bool plan_armed = false;                    // set by siSortQueriesDevice: next count may reuse
 
     sib::LaunchTimer timer;
+    // The host-buffer entry points of one handle (countOverlapsBatch ... upperBound) share its stream and
+    // staging buffers: they take this lock, so that concurrent const queries from several host threads
+    // are safe, as with the reference (SURVEY 8b "Threading"). The device API (siCountDevice ...) on caller
+    // streams is not locked: callers serialise their calls on one siIndex.
+    std::mutex api_mu;
 
     // ---- options (siIndexSetOption) ----------------------------------------------------
     int count_algo = 0;                         // SI_COUNT_AUTO / SI_COUNT_WALK / SI_COUNT_RANK / SI_COUNT_CELLS

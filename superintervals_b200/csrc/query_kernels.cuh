@@ -227,6 +227,18 @@ __device__ __forceinline__ void walk_tail(const IndexView& ix, uint32_t i, int32
     }
 }
 
+// The same, out of line: for kernels whose fast path never walks (inverted queries in the rank kernels are
+// rare), so that the walk's registers do not count against the fast path. Returns the hits found.
+__device__ __noinline__ uint32_t walk_tail_rare(const int32_t* __restrict__ ends, const uint32_t* __restrict__ branch,
+                                                uint32_t i, int32_t qs) {
+    IndexView v;
+    v.ends = ends;
+    v.branch = branch;
+    uint32_t c = 0;
+    walk_tail(v, i, qs, c, lane_id());
+    return c;
+}
+
 constexpr uint32_t QK_DENSE_SPAN = 256;      // max spread of upper bounds inside a tile for the sweep
 constexpr uint32_t QK_DENSE_MIN_HITS = 8;    // a 32-interval chunk must yield this many hits tile-wide
 constexpr int QK_DENSE_MAX_CHUNKS = 256;     // then the sparse tail goes to the branch walk
@@ -439,14 +451,41 @@ qk_count_rank_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __rest
 // the counts streamed out coalesced, the two sectors per query served by L2 (C2: 62 MB of cells).
 // Per query: 8 B in, 4 B out, 2 x 32 B sector reads. Queries with qs > qe (quirk Q6) take the
 // branch-array walk, as in qk_count_rank_kernel. Bit-exact with qk_count_kernel.
-constexpr int QC_THREADS = 256;
+#ifndef SIB_QC_THREADS
+#define SIB_QC_THREADS 256
+#endif
+constexpr int QC_THREADS = SIB_QC_THREADS;
 #ifndef SIB_QC_PER_THREAD
-#define SIB_QC_PER_THREAD 4
+#define SIB_QC_PER_THREAD 2
 #endif
 constexpr int QC_PER_THREAD = SIB_QC_PER_THREAD;
 constexpr uint32_t QC_TILE = QC_THREADS * QC_PER_THREAD;
 
 struct __align__(32) CellRec { uint32_t w[8]; };
+
+// L2 eviction policies (SIB_QC_HINTS): the rank cells should stay in L2 (evict_last) while the
+// query / count streams pass through (evict_first).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ int32_t ld_stream_hint(const int32_t* p, uint64_t pol) {
+    int32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_stream_hint(uint32_t* p, uint32_t v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_stream_hint(uint64_t* p, uint64_t v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
 
 __device__ __forceinline__ CellRec ld_cell(const uint4* p) {
     CellRec r;
@@ -457,6 +496,13 @@ __device__ __forceinline__ CellRec ld_cell(const uint4* p) {
 #endif
                  : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
                  : "l"(p));
+    return r;
+}
+__device__ __forceinline__ CellRec ld_cell_hint(const uint4* p, uint64_t pol) {
+    CellRec r;
+    asm volatile("ld.global.nc.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+                 : "l"(p), "l"(pol));
     return r;
 }
 
@@ -471,8 +517,15 @@ __device__ __forceinline__ void cell_of(const RankCells& rc, int64_t x, uint32_t
     off = (uint32_t)d & ((1u << rc.shift) - 1u);
 }
 
-// #{ offsets in the record < off }, SWAR over the 7 payload words
+// #{ offsets in the record < off }, SWAR over the 7 payload words. Per lane (byte or half-word) of a
+// word a and the replicated threshold t:  a < t  <=>  (~a & t) | (~(a ^ t) & ~d)  at the lane's top bit,
+// where d = (a | H) - (t & ~H) never borrows across lanes and has its top bit set iff low(a) >= low(t).
+// The seven words' top bits are shifted to distinct positions and counted by ONE popc.
 __device__ __forceinline__ uint32_t cell_below(const CellRec& r, uint32_t off, uint32_t fmt) {
+#ifdef SIB_QC_NOSWAR   // timing experiment only (wrong counts): what the kernel costs without the in-cell rank
+    return (r.w[1] ^ r.w[7]) & 1u;
+#endif
+#ifdef SIB_QC_SWAR_OLD
     uint32_t acc = 0;
     if (fmt == 1u) {
         const uint32_t t = off * 0x01010101u;
@@ -484,6 +537,20 @@ __device__ __forceinline__ uint32_t cell_below(const CellRec& r, uint32_t off, u
 #pragma unroll
     for (int k = 1; k < 8; ++k) acc += __vcmpltu2(r.w[k], t) & 0x00010001u;
     return (acc + (acc >> 16)) & 0xFFFFu;
+#else
+    const uint32_t H = fmt == 1u ? 0x80808080u : 0x80008000u;
+    const uint32_t t = off * (fmt == 1u ? 0x01010101u : 0x00010001u);
+    const uint32_t tl = t & ~H;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+        const uint32_t a = r.w[k];
+        const uint32_t d = (a | H) - tl;
+        const uint32_t lt = (~a & t) | (~(a ^ t) & ~d);
+        acc |= (lt & H) >> (k - 1);
+    }
+    return __popc(acc);
+#endif
 }
 
 // an over-full cell (bit 31 of word 0): #{ A < x } by halving search inside the cell's run of A
@@ -519,8 +586,11 @@ __device__ __forceinline__ uint32_t cells_rank_lt(const RankCells& rc, const int
 template <typename CountT>
 __device__ __forceinline__ void count_cells_tile(const IndexView& ix, const QueryRecords& rec, uint64_t base, uint32_t nq,
                                                  CountT* __restrict__ counts) {
-    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t tid = threadIdx.x;
     const RankCells cs = ix.cells_s, ce = ix.cells_e;
+#ifdef SIB_QC_HINTS
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_pass = l2_policy_evict_first();
+#endif
 
     int32_t qs[QC_PER_THREAD], qe[QC_PER_THREAD];
     bool live[QC_PER_THREAD];
@@ -528,8 +598,13 @@ __device__ __forceinline__ void count_cells_tile(const IndexView& ix, const Quer
     for (int j = 0; j < QC_PER_THREAD; ++j) {
         const uint64_t t = base + (uint64_t)j * QC_THREADS + tid;
         live[j] = t < nq;
+#ifdef SIB_QC_HINTS
+        qs[j] = live[j] ? ld_stream_hint(rec.qs + t, pol_pass) : 0;
+        qe[j] = live[j] ? ld_stream_hint(rec.qe + t, pol_pass) : 0;
+#else
         qs[j] = live[j] ? ld_stream(rec.qs + t) : 0;
         qe[j] = live[j] ? ld_stream(rec.qe + t) : 0;
+#endif
     }
     // all sector loads of the thread's queries in flight together
     uint32_t cell_s[QC_PER_THREAD], off_s[QC_PER_THREAD], cell_e[QC_PER_THREAD], off_e[QC_PER_THREAD];
@@ -538,8 +613,13 @@ __device__ __forceinline__ void count_cells_tile(const IndexView& ix, const Quer
     for (int j = 0; j < QC_PER_THREAD; ++j) {
         cell_of(cs, (int64_t)qe[j] + 1, cell_s[j], off_s[j]);   // #{starts <= qe} = #{starts < qe + 1}
         cell_of(ce, (int64_t)qs[j], cell_e[j], off_e[j]);       // #{ends < qs}
+#ifdef SIB_QC_HINTS
+        rs[j] = ld_cell_hint(cs.rec + 2 * (size_t)cell_s[j], pol_keep);
+        re[j] = ld_cell_hint(ce.rec + 2 * (size_t)cell_e[j], pol_keep);
+#else
         rs[j] = ld_cell(cs.rec + 2 * (size_t)cell_s[j]);
         re[j] = ld_cell(ce.rec + 2 * (size_t)cell_e[j]);
+#endif
     }
 #pragma unroll
     for (int j = 0; j < QC_PER_THREAD; ++j) {
@@ -549,21 +629,27 @@ __device__ __forceinline__ void count_cells_tile(const IndexView& ix, const Quer
         const bool inverted = live[j] && qs[j] > qe[j];
         if (__any_sync(FULL_MASK, inverted)) {
             // qs > qe: the walk's own definition, #{ j <= ub(qe) : ends[j] >= qs }
-            uint32_t cw = 0;
             const uint32_t i = inverted ? ns - 1u : NONE32;   // ns = #{starts <= qe}; 0 - 1 wraps to NONE32
-            walk_tail(ix, i, qs[j], cw, lane);
+            const uint32_t cw = walk_tail_rare(ix.ends, ix.branch, i, qs[j]);
             if (inverted) c = cw;
         }
         const uint64_t t = base + (uint64_t)j * QC_THREADS + tid;
         if (live[j]) {
             if (rec.idx) counts[ld_stream(rec.idx + t)] = (CountT)c;
+#ifdef SIB_QC_HINTS
+            else st_stream_hint(counts + t, (CountT)c, pol_pass);
+#else
             else st_stream(counts + t, (CountT)c);
+#endif
         }
     }
 }
 
+#ifndef SIB_QC_MINBLOCKS
+#define SIB_QC_MINBLOCKS 4
+#endif
 template <typename CountT>
-__global__ void __launch_bounds__(QC_THREADS)
+__global__ void __launch_bounds__(QC_THREADS, SIB_QC_MINBLOCKS)
 qk_count_cells_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __restrict__ counts) {
     count_cells_tile<CountT>(ix, rec, (uint64_t)blockIdx.x * QC_TILE, nq, counts);
 }

@@ -155,11 +155,12 @@ sk_count_stream_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const in
 #pragma unroll
         for (int j = 0; j < SK_PER_THREAD; ++j) { qs[j] = (int32_t)a.w[j]; qe[j] = (int32_t)b.w[j]; }
     } else {
+        // lanes past the end of the batch repeat its last query: they stay inside the tile's window
 #pragma unroll
         for (int j = 0; j < SK_PER_THREAD; ++j) {
-            const bool live = base + j < nq;
-            qs[j] = live ? ld_stream(qs_in + base + j) : 0;
-            qe[j] = live ? ld_stream(qe_in + base + j) : 0;
+            const uint64_t t = base + j < nq ? base + j : (uint64_t)nq - 1;
+            qs[j] = ld_stream(qs_in + t);
+            qe[j] = ld_stream(qe_in + t);
         }
     }
     // where each rank falls, and the tile's window of words in either table

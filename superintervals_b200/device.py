@@ -142,6 +142,13 @@ class DeviceIndex:
             raise RuntimeError("siIndexBitsInfo: index not built")
         return {"built": bool(bi.built), "words": int(bi.words), "bytes": int(bi.bytes), "slow_words": int(bi.slow_words)}
 
+    def stream_stats(self):
+        """(tiles, handed_back) of the last streaming count (siIndexStreamStats)."""
+        t, f = C.c_ulonglong(0), C.c_ulonglong(0)
+        self._L.siIndexStreamStats(self._ix, C.byref(t), C.byref(f))
+        _lib.check("siIndexStreamStats")
+        return int(t.value), int(f.value)
+
     def stab_info(self):
         """Stab lists of the CSR fill (siIndexStabInfo): state 0 not made yet / 1 in use / 2 the fill walks."""
         si = _lib.siStabInfo()

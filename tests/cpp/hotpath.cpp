@@ -6,6 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <numeric>
+#include <string>
+#include <thread>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -226,6 +229,106 @@ static void test_set_operations() {
     }
 }
 
+// ---- the four range classes of the reference (hpp:153-494) under their own names ---------------
+static void test_range_classes() {
+    Map m;
+    m.add(1, 10, 100); m.add(3, 4, 101); m.add(5, 20, 102); m.add(30, 40, 103);
+    m.build();
+    static_assert(std::is_same<decltype(m.search_idxs(5, 11)), Map::IndexRange>::value, "search_idxs(s, e) -> IndexRange");
+    static_assert(std::is_same<decltype(m.search_keys(5, 11)), Map::KeyRange>::value, "search_keys(s, e) -> KeyRange");
+    static_assert(std::is_same<decltype(m.search_values(5, 11)), Map::ValueRange>::value, "search_values(s, e) -> ValueRange");
+    static_assert(std::is_same<decltype(m.search_items(5, 11)), Map::ItemRange>::value, "search_items(s, e) -> ItemRange");
+    std::vector<size_t> idx;
+    for (size_t i : m.search_idxs(5, 11)) idx.push_back(i);                    // descending positions
+    CHECK(idx.size() == 2 && idx[0] == 2 && idx[1] == 0);
+    std::vector<int> vals;
+    for (const int& v : m.search_values(5, 11)) vals.push_back(v);
+    CHECK(vals.size() == 2 && vals[0] == 102 && vals[1] == 100);
+    std::vector<std::pair<int, int>> keys;
+    for (const auto& k : m.search_keys(4, 4)) keys.push_back(k);
+    CHECK(keys.size() == 2 && keys[0] == std::make_pair(3, 4) && keys[1] == std::make_pair(1, 10));
+    size_t items = 0;
+    for (const auto& it : m.search_items(35, 36)) { CHECK(it.start == 30 && it.end == 40 && it.data == 103); ++items; }
+    CHECK(items == 1);
+    Map::IndexRange none = m.search_idxs(21, 29);
+    CHECK(!(none.begin() != none.end()));
+    Map::IndexIterator it = m.search_idxs(0, 100).begin();                      // explicit iterator use, as hpp:153-209 allows
+    size_t seen = 0;
+    for (; it != m.search_idxs(0, 100).end(); ++it) ++seen;
+    CHECK(seen == 4);
+}
+
+// ---- ownership: a built map survives a real move (vector growth, std::move) ------------------------
+static void test_moves() {
+    std::vector<Map> maps;
+    for (int k = 0; k < 5; ++k) {   // push_back reallocates and move-constructs the earlier maps
+        Map m;
+        m.add(10 * k, 10 * k + 5, k); m.add(10 * k + 2, 10 * k + 3, 100 + k);
+        m.build();
+        maps.push_back(std::move(m));
+    }
+    for (int k = 0; k < 5; ++k) CHECK(maps[k].count(10 * k + 2, 10 * k + 2) == 2 && maps[k].count(10 * k + 7, 10 * k + 8) == 0);
+    Map b = std::move(maps[3]);
+    CHECK(b.count(32, 33) == 2);
+    Map c;
+    c = std::move(b);
+    std::vector<int> v;
+    c.search_values(30, 31, v);
+    CHECK(v.size() == 1 && v[0] == 3);
+}
+
+// ---- a stale process-wide error must not make build() skip its host-side reordering ------------------
+static void test_build_ignores_a_stale_error() {
+    Map broken;
+    CHECK(broken.count(1, 2) == 0);
+    cIndexResult r = createIndexResult();
+    cSuperIntervals* raw = createSuperIntervals();
+    addInterval(raw, 1, 2, 0);
+    searchValues(raw, 1, 2, &r);                       // not indexed: latches "handle not indexed"
+    CHECK(si_b200_last_error() != 0);
+    Map m;
+    m.add(50, 60, 7); m.add(10, 20, 8); m.add(30, 40, 9);
+    m.build();                                          // the sticky error is still set
+    CHECK(m.starts[0] == 10 && m.data[0] == 8 && m.data[2] == 7);
+    std::vector<int> v;
+    m.search_values(55, 56, v);
+    CHECK(v.size() == 1 && v[0] == 7);
+    si_b200_clear_error();
+    destroyIndexResult(&r);
+    destroySuperIntervals(raw);
+}
+
+// ---- const queries from several threads at once (reference: safe, hpp:551,651) -----------
+static void test_concurrent_const_queries() {
+    Map m;
+    unsigned x = 777;
+    auto rnd = [&x]() { x = x * 1664525u + 1013904223u; return (int)(x >> 8); };
+    for (int i = 0; i < 20000; ++i) { int s = rnd() % 200000; m.add(s, s + rnd() % 900, i); }
+    m.build();
+    std::vector<int> qs, qe;
+    for (int i = 0; i < 400; ++i) { int s = rnd() % 200000; qs.push_back(s); qe.push_back(s + rnd() % 1500); }
+    std::vector<size_t> want(qs.size());
+    std::vector<std::vector<int>> want_v(qs.size());
+    for (size_t q = 0; q < qs.size(); ++q) { want[q] = m.count(qs[q], qe[q]); m.search_values(qs[q], qe[q], want_v[q]); }
+    const Map& cm = m;
+    std::vector<int> bad(4, 0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < 4; ++t)
+        th.emplace_back([&, t]() {
+            for (int rep = 0; rep < 3; ++rep)
+                for (size_t q = t; q < qs.size(); q += 2) {      // threads overlap on the same queries
+                    std::vector<int> v;
+                    cm.search_values(qs[q], qe[q], v);
+                    size_t n_it = 0;
+                    for (size_t i : cm.search_idxs(qs[q], qe[q])) { (void)i; ++n_it; }
+                    if (cm.count(qs[q], qe[q]) != want[q] || v != want_v[q] || n_it != want[q]) ++bad[t];
+                    if (cm.has_overlaps(qs[q], qe[q]) && want[q] == 0) ++bad[t];
+                }
+        });
+    for (auto& t : th) t.join();
+    CHECK(bad[0] + bad[1] + bad[2] + bad[3] == 0);
+}
+
 int main() {
     test_basics();
     test_iteration();
@@ -234,6 +337,11 @@ int main() {
     test_edge_cases();
     test_quirks();
     test_batch_and_payload_types();
+    test_range_classes();
+    test_moves();
+    test_concurrent_const_queries();
+    CHECK(si_b200_last_error() == 0);
+    test_build_ignores_a_stale_error();
     CHECK(si_b200_last_error() == 0);
     std::printf("All query tests passed\n");
     {   // hpp:1457-1535: the Eytzinger variant answers exactly like the plain map

@@ -12,7 +12,7 @@ EXE = os.path.join(ROOT, "tests", "cpp", "hotpath")
 def _compile():
     cmd = ["g++", "-std=c++17", "-O1", "-Wall", os.path.join(ROOT, "tests", "cpp", "hotpath.cpp"),
            "-I" + os.path.join(ROOT, "include"), "-L" + os.path.join(ROOT, "superintervals_b200"),
-           "-lsuperintervals_b200", "-Wl,-rpath," + os.path.join(ROOT, "superintervals_b200"), "-o", EXE]
+           "-lsuperintervals_b200", "-pthread", "-Wl,-rpath," + os.path.join(ROOT, "superintervals_b200"), "-o", EXE]
     out = subprocess.run(cmd, capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
 

@@ -29,11 +29,11 @@ def dense():
     """C2-shaped: read-length intervals, one per ~25 coordinates."""
     from superintervals_b200.device import DeviceIndex
     rng = np.random.default_rng(7)
-    n, axis = 400_000, 10_000_000
+    n, axis = 200_000, 5_000_000
     ln = np.exp(rng.uniform(np.log(150), np.log(10_000), n)).astype(np.int64)
     s = rng.integers(0, axis - ln).astype(np.int32)
     e = (s + ln - 1).astype(np.int32)
-    nq = 300_001                                    # ragged: not a multiple of the 2048-query tile
+    nq = 600_001                                    # ragged: not a multiple of the 2048-query tile; ~0.12 queries per coordinate
     lq = np.exp(rng.uniform(0, np.log(10_000), nq)).astype(np.int64)
     qs = rng.integers(0, axis - lq).astype(np.int32)
     qe = (qs + lq - 1).astype(np.int32)
@@ -56,6 +56,8 @@ def test_sorted_batch_streams_and_matches_the_oracle(dense):
     got = _u32(ix.count(_dev(sq), _dev(se), order=ORDER_SORTED))
     assert _kernels(ix) == {"count_stream"}
     assert np.array_equal(got, want)
+    tiles, back = ix.stream_stats()
+    assert tiles == (sq.size + 2047) // 2048 and back == 0            # every tile answered from its TMA-staged window
     got = _u32(ix.count(_dev(sq), _dev(se), order=ORDER_AUTO))       # found sorted by the device check
     assert _kernels(ix) == {"count_stream"}
     ix.set_option(OPT_TIMING, 0)
@@ -75,6 +77,8 @@ def test_shuffled_batch_keeps_the_cells_kernel_unless_forced(dense):
     # the staging buffers go to the rank-cells code
     assert np.array_equal(_u32(ix.count(dqs, dqe, order=ORDER_SORTED)), want)
     assert _kernels(ix) == {"count_stream"}
+    tiles, back = ix.stream_stats()
+    assert back == tiles                                              # shuffled: no tile's window fits
     ix.set_option(OPT_STREAM, 2)
     assert np.array_equal(_u32(ix.count(dqs, dqe, order=ORDER_UNSORTED)), want)
     assert _kernels(ix) == {"count_stream"}
@@ -98,6 +102,8 @@ def test_inverted_and_out_of_span_queries_in_a_sorted_batch(dense):
     sq[-300:] = np.int32(2_000_000_000); se[-300:] = np.int32(2_100_000_000)   # far above
     sq[300] = np.iinfo(np.int32).min; se[300] = np.iinfo(np.int32).max         # everything
     assert np.array_equal(_u32(ix.count(_dev(sq), _dev(se), order=ORDER_SORTED)), orc.count_batch(sq, se))
+    tiles, back = ix.stream_stats()
+    assert 0 < back < tiles                                           # tiles holding an inverted query went to the walk
 
 
 def test_unaligned_pointers_and_tiny_batches(dense):
@@ -125,18 +131,18 @@ def test_duplicate_coordinates_take_the_second_bitmap_and_the_slow_words():
     (RB_SLOW words answered from the rank cells)."""
     from superintervals_b200.device import DeviceIndex, ORDER_SORTED
     rng = np.random.default_rng(11)
-    n, axis = 200_000, 600_000
-    s = (rng.integers(0, axis // 3, n) * 3).astype(np.int32)
+    n, axis = 200_000, 3_000_000
+    s = (rng.integers(0, axis // 3, n) * 3).astype(np.int32)          # ~0.2 values per lattice point: doubles common, triples ~1 %
     e = (s + rng.integers(0, 400, n) * 3).astype(np.int32)
     orc = Oracle(s, e)
     ix = DeviceIndex().build(_dev(s), _dev(e))
     info = ix.bits_info()
-    qs = np.sort(rng.integers(-100, axis + 1500, 150_000)).astype(np.int32)
+    qs = np.sort(rng.integers(-100, axis + 1500, 300_000)).astype(np.int32)
     qe = (qs + rng.integers(0, 900, qs.size)).astype(np.int32)
     got = _u32(ix.count(_dev(qs), _dev(qe), order=ORDER_SORTED))
     assert np.array_equal(got, orc.count_batch(qs, qe)), info
-    if info["built"]:
-        assert info["slow_words"] > 0
+    assert info["built"] and info["slow_words"] > 0
+    assert ix.stream_stats()[1] == 0
 
 
 def test_sparse_index_has_no_rank_bits_and_still_counts():
