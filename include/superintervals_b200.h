@@ -168,6 +168,8 @@ enum { SI_OPT_COUNT_ALGO = 0, SI_OPT_BUCKET_INTERVALS = 1, SI_OPT_WINDOW_SHIFT =
        SI_OPT_STAB_BUDGET = 8, /* stab-list entries per interval at most (default 6); deeper indexes double the checkpoint spacing, then walk */
        SI_OPT_STREAM = 9, /* 1 (default): position-sorted batches are counted by the streaming kernel (TMA-staged rank bits) when the
                              index carries them; 0: never; 2: every batch, whatever its order (a tile whose window does not fit reads the cells) */
+       SI_OPT_L2_PERSIST = 11, /* 1 (default): the rank-cells count is launched with an L2 access-policy window that keeps the cells
+                                   resident (persisting) and lets the query / count streams pass (streaming); 0: plain launch */
        SI_OPT_STREAM_BUDGET = 10 /* rank bits are built when they cost at most this many bytes per interval (default 64; 0 = never); next build */ };
 enum { SI_COUNT_AUTO = 0, SI_COUNT_WALK = 1, SI_COUNT_RANK = 2, SI_COUNT_CELLS = 3 };
 int siIndexSetOption(siIndex* ix, int option, long long value);

@@ -162,7 +162,7 @@ IndexView view_of(const siIndex* ix) {
     v.grid.shift = ix->grid_shift;
     v.grid.cells = ix->grid_cells;
     v.cells_s = RankCells{ix->cells_s.as<uint4>(), ix->cm_s.lo, ix->cm_s.span, ix->cm_s.shift, ix->cm_s.fmt};
-    v.cells_e = RankCells{ix->cells_e.as<uint4>(), ix->cm_e.lo, ix->cm_e.span, ix->cm_e.shift, ix->cm_e.fmt};
+    v.cells_e = RankCells{ix->cells_e_ptr, ix->cm_e.lo, ix->cm_e.span, ix->cm_e.shift, ix->cm_e.fmt};
     const bool bits = ix->bits_ok;
     v.bits_s = RankBits{bits ? ix->bits_s_t.as<uint2>() : nullptr, ix->bits_s_d.as<uint32_t>(), ix->cm_s.lo, ix->cm_s.span, ix->bits_words_s};
     v.bits_e = RankBits{bits ? ix->bits_e_t.as<uint2>() : nullptr, ix->bits_e_d.as<uint32_t>(), ix->cm_e.lo, ix->cm_e.span, ix->bits_words_e};
@@ -237,9 +237,9 @@ int build_branch(siIndex* ix, cudaStream_t s) {
 }
 
 // Rank cells over a sorted device array A[0..n) whose first and last values are known on the
-// host: pick the record format and the cell width from the density, then one thread per cell.
-int build_cells(siIndex* ix, const int32_t* A, int32_t first, int32_t last, DevBuf* buf, siIndex::CellsMeta* m,
-                unsigned long long* d_overfull, cudaStream_t s) {
+// host: pick the record format and the cell width from the density (cells_plan), then one thread per cell
+// (cells_fill). Both tables share one allocation, so that one L2 access-policy window covers them.
+void cells_plan(const siIndex* ix, int32_t first, int32_t last, siIndex::CellsMeta* m) {
     const uint32_t n = ix->n;
     const uint64_t range = (uint64_t)((int64_t)last - (int64_t)first) + 1;
     // largest shift <= smax with a mean of at most `fill` values per cell
@@ -257,24 +257,26 @@ int build_cells(siIndex* ix, const int32_t* A, int32_t first, int32_t last, DevB
     m->span = (uint32_t)(range - 1);
     m->shift = shift;
     m->cells = (uint32_t)(range >> shift) + 1u;   // cell of hi + 1 included
-    const size_t bytes = ((size_t)m->cells + 1) * 32;
-    if (buf->ensure(bytes)) return last_error_code();
-    const int grid = grid_for((uint64_t)m->cells + 1, BK_THREADS, ix->sm_count * 16);
-    if (fmt == 1)
-        SIB_LAUNCH((bk_rank_cells_kernel<1>), grid, BK_THREADS, 0, s, A, n, first, shift, m->cells, buf->as<uint4>(), d_overfull);
-    else
-        SIB_LAUNCH((bk_rank_cells_kernel<2>), grid, BK_THREADS, 0, s, A, n, first, shift, m->cells, buf->as<uint4>(), d_overfull);
     m->fmt = fmt;
+}
+size_t cells_bytes(const siIndex::CellsMeta& m) { return (((size_t)m.cells + 1) * 32 + 255) & ~(size_t)255; }
+
+int cells_fill(siIndex* ix, const int32_t* A, const siIndex::CellsMeta& m, uint4* rec, unsigned long long* d_overfull, cudaStream_t s) {
+    const int grid = grid_for((uint64_t)m.cells + 1, BK_THREADS, ix->sm_count * 16);
+    if (m.fmt == 1)
+        SIB_LAUNCH((bk_rank_cells_kernel<1>), grid, BK_THREADS, 0, s, A, ix->n, m.lo, m.shift, m.cells, rec, d_overfull);
+    else
+        SIB_LAUNCH((bk_rank_cells_kernel<2>), grid, BK_THREADS, 0, s, A, ix->n, m.lo, m.shift, m.cells, rec, d_overfull);
     return 0;
 }
 
 // Rank bits over a sorted device array whose rank cells exist (stream_kernels.cuh).
-int build_bits(siIndex* ix, const int32_t* A, const DevBuf& cells, const siIndex::CellsMeta& m, DevBuf* t, DevBuf* d2,
+int build_bits(siIndex* ix, const int32_t* A, const uint4* cells, const siIndex::CellsMeta& m, DevBuf* t, DevBuf* d2,
                uint32_t* nwords_out, unsigned long long* d_slow, cudaStream_t s) {
     const uint32_t nwords = (uint32_t)(((uint64_t)m.span + 1) >> 5) + 1u;
     const uint32_t padded = ((nwords + 3u) & ~3u) + 4u;
     if (t->ensure((size_t)padded * 8) || d2->ensure((size_t)padded * 4)) return last_error_code();
-    const RankCells rc{cells.as<uint4>(), m.lo, m.span, m.shift, m.fmt};
+    const RankCells rc{cells, m.lo, m.span, m.shift, m.fmt};
     SIB_LAUNCH(sk_rank_bits_kernel, grid_for(padded, 256, ix->sm_count * 16), 256, 0, s, rc, A, ix->n, nwords, padded,
                t->as<uint2>(), d2->as<uint32_t>(), d_slow);
     *nwords_out = nwords;
@@ -372,10 +374,18 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
         if (n < 0x80000000ull) {   // bit 31 of a cell's rank word flags an over-full cell
             unsigned long long* d_over = reinterpret_cast<unsigned long long*>(ix->small.as<uint32_t>() + 8);
             SIB_CHECK(cudaMemsetAsync(d_over, 0, 16, s));
-            rc = build_cells(ix, ix->starts.as<int32_t>(), ix->lo, last_start, &ix->cells_s, &ix->cm_s, d_over, s);
+            siIndex::CellsMeta ms, me;
+            cells_plan(ix, ix->lo, last_start, &ms);
+            cells_plan(ix, first_end, ix->hi, &me);
+            if (ix->cells_s.ensure(cells_bytes(ms) + cells_bytes(me))) return last_error_code();
+            ix->cells_e_ptr = reinterpret_cast<uint4*>(reinterpret_cast<char*>(ix->cells_s.p) + cells_bytes(ms));
+            ix->cells_total_bytes = cells_bytes(ms) + cells_bytes(me);
+            rc = cells_fill(ix, ix->starts.as<int32_t>(), ms, ix->cells_s.as<uint4>(), d_over, s);
             if (rc) return rc;
-            rc = build_cells(ix, ix->eall.as<int32_t>(), first_end, ix->hi, &ix->cells_e, &ix->cm_e, d_over + 1, s);
+            rc = cells_fill(ix, ix->eall.as<int32_t>(), me, ix->cells_e_ptr, d_over + 1, s);
             if (rc) return rc;
+            ix->cm_s = ms;
+            ix->cm_e = me;
             unsigned long long over[2] = {0, 0};
             SIB_CHECK(cudaMemcpyAsync(over, d_over, 16, cudaMemcpyDeviceToHost, s));
             SIB_CHECK(cudaStreamSynchronize(s));
@@ -383,11 +393,12 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
             ix->cm_e.overfull = over[1];
             // rank bits for the streaming count: only where they stay affordable next to the index
             const uint64_t words = (((uint64_t)ix->cm_s.span + 1) >> 5) + (((uint64_t)ix->cm_e.span + 1) >> 5) + 16;
-            if (ix->stream_mode != 0 && n < 0x40000000ull && words * 12 <= (uint64_t)ix->bits_budget * n) {
+            if (ix->stream_mode != 0 && n < 0x40000000ull && words * 12 <= (uint64_t)ix->bits_budget * n &&
+                ix->cm_s.span < 0xFFFFFFF0u && ix->cm_e.span < 0xFFFFFFF0u) {   // the kernel's clamps are 32-bit
                 SIB_CHECK(cudaMemsetAsync(d_over, 0, 16, s));
-                rc = build_bits(ix, ix->starts.as<int32_t>(), ix->cells_s, ix->cm_s, &ix->bits_s_t, &ix->bits_s_d, &ix->bits_words_s, d_over, s);
+                rc = build_bits(ix, ix->starts.as<int32_t>(), ix->cells_s.as<uint4>(), ix->cm_s, &ix->bits_s_t, &ix->bits_s_d, &ix->bits_words_s, d_over, s);
                 if (rc) return rc;
-                rc = build_bits(ix, ix->eall.as<int32_t>(), ix->cells_e, ix->cm_e, &ix->bits_e_t, &ix->bits_e_d, &ix->bits_words_e, d_over + 1, s);
+                rc = build_bits(ix, ix->eall.as<int32_t>(), ix->cells_e_ptr, ix->cm_e, &ix->bits_e_t, &ix->bits_e_d, &ix->bits_words_e, d_over + 1, s);
                 if (rc) return rc;
                 SIB_CHECK(cudaMemcpyAsync(ix->bits_slow, d_over, 16, cudaMemcpyDeviceToHost, s));
                 SIB_CHECK(cudaStreamSynchronize(s));
@@ -495,7 +506,29 @@ int launch_count(siIndex* ix, const QueryRecords& rec, uint32_t nq, CountT* d_co
     const int algo = count_algo_of(ix);
     if (algo == SI_COUNT_CELLS) {
         const int grid = (int)(((uint64_t)nq + QC_TILE - 1) / QC_TILE);
-        SIB_LAUNCH_T(ix, TAG_COUNT_CELLS, (qk_count_cells_kernel<CountT>), grid, QC_THREADS, 0, s, view_of(ix), rec, nq, d_counts);
+        if (ix->l2_persist && ix->cells_total_bytes <= ix->l2_persist_max) {
+            // the rank cells are the only data read more than once: ask L2 to keep them (persisting) while the
+            // query and count streams pass through (streaming) -- a per-launch access-policy window
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)grid);
+            cfg.blockDim = dim3(QC_THREADS);
+            cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+            at[0].val.accessPolicyWindow.base_ptr = ix->cells_s.p;
+            at[0].val.accessPolicyWindow.num_bytes = ix->cells_total_bytes;
+            at[0].val.accessPolicyWindow.hitRatio = 1.0f;
+            at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            ix->timer.begin(TAG_COUNT_CELLS, s);
+            SIB_CHECK(cudaLaunchKernelEx(&cfg, qk_count_cells_kernel<CountT>, view_of(ix), rec, nq, d_counts));
+            ix->timer.end(s);
+            note_launch();
+        } else {
+            SIB_LAUNCH_T(ix, TAG_COUNT_CELLS, (qk_count_cells_kernel<CountT>), grid, QC_THREADS, 0, s, view_of(ix), rec, nq, d_counts);
+        }
     } else if (algo == SI_COUNT_RANK) {
         const int grid = (int)(((uint64_t)nq + QR_TILE - 1) / QR_TILE);
         SIB_LAUNCH_T(ix, TAG_COUNT_RANK, (qk_count_rank_kernel<CountT>), grid, QR_THREADS, 0, s, view_of(ix), rec, nq, d_counts);
@@ -683,6 +716,16 @@ siIndex* siIndexCreate(void) {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) ix->sm_count = sms;
     int l2 = 0;
     if (cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev) == cudaSuccess && l2 > 0) ix->l2_bytes = (size_t)l2;
+    int pmax = 0;
+    if (cudaDeviceGetAttribute(&pmax, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess && pmax > 0) {
+        // the set-aside is a device-wide limit: raise it to the maximum once (never lower what another user set)
+        size_t cur = 0;
+        if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) == cudaSuccess && cur < (size_t)pmax)
+            (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)pmax);
+        if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) == cudaSuccess) ix->l2_persist_max = cur;
+        (void)cudaGetLastError();
+    }
+    if (const char* e = getenv("SIB_L2_PERSIST")) ix->l2_persist = atoi(e) != 0;
     e = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { sib::set_error(e, "cudaStreamCreate", __FILE__, __LINE__); delete ix; return nullptr; }
     return ix;
@@ -894,6 +937,10 @@ int siIndexSetOption(siIndex* ix, int option, long long value) {
         case SI_OPT_STREAM_BUDGET:         // bytes of rank bits per interval at most; applies to the next build
             if (value < 0 || value > 4096) break;
             ix->bits_budget = (uint32_t)value;
+            return 0;
+        case SI_OPT_L2_PERSIST:            // 1: the cells kernel is launched with an L2 access-policy window over the rank cells
+            if (value < 0 || value > 1) break;
+            ix->l2_persist = value != 0;
             return 0;
         case SI_OPT_WINDOW_SHIFT:
             if (value < 10 || value > 31) break;

@@ -57,7 +57,11 @@ struct siIndex {
     uint32_t grid_intervals = 8;    // target intervals per grid cell
     // rank cells (RankCells in query_kernels.cuh): one 32-byte record per 2^shift coordinates
     struct CellsMeta { int32_t lo = 0; uint32_t span = 0, shift = 0, fmt = 0, cells = 0; unsigned long long overfull = 0; };
-    sib::DevBuf cells_s, cells_e;
+    sib::DevBuf cells_s, cells_e;                  // cells_s owns both tables (one L2 policy window); cells_e stays empty
+    uint4* cells_e_ptr = nullptr;                  // inside cells_s
+    size_t cells_total_bytes = 0;
+    bool l2_persist = true;                        // SI_OPT_L2_PERSIST / SIB_L2_PERSIST
+    size_t l2_persist_max = 0;                     // cudaLimitPersistingL2CacheSize in force
     CellsMeta cm_s, cm_e;
     uint32_t cells_fill8 = 16, cells_fill16 = 7;   // target mean values per cell (28 / 14 slots)
     size_t cells_direct_bytes = 0;                 // cells up to this size answer unpartitioned batches (0: 60 % of L2)

@@ -456,7 +456,7 @@ qk_count_rank_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __rest
 #endif
 constexpr int QC_THREADS = SIB_QC_THREADS;
 #ifndef SIB_QC_PER_THREAD
-#define SIB_QC_PER_THREAD 2
+#define SIB_QC_PER_THREAD 1
 #endif
 constexpr int QC_PER_THREAD = SIB_QC_PER_THREAD;
 constexpr uint32_t QC_TILE = QC_THREADS * QC_PER_THREAD;
@@ -646,7 +646,7 @@ __device__ __forceinline__ void count_cells_tile(const IndexView& ix, const Quer
 }
 
 #ifndef SIB_QC_MINBLOCKS
-#define SIB_QC_MINBLOCKS 4
+#define SIB_QC_MINBLOCKS 8
 #endif
 template <typename CountT>
 __global__ void __launch_bounds__(QC_THREADS, SIB_QC_MINBLOCKS)

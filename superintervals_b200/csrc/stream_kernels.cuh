@@ -156,25 +156,31 @@ sk_count_stream_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const in
         for (int j = 0; j < SK_PER_THREAD; ++j) { qs[j] = (int32_t)a.w[j]; qe[j] = (int32_t)b.w[j]; }
     } else {
         // lanes past the end of the batch repeat its last query: they stay inside the tile's window
-#pragma unroll
+        // (and add nothing to it, to its inverted flag or to the output)
+#pragma unroll 1
         for (int j = 0; j < SK_PER_THREAD; ++j) {
             const uint64_t t = base + j < nq ? base + j : (uint64_t)nq - 1;
-            qs[j] = ld_stream(qs_in + t);
-            qe[j] = ld_stream(qe_in + t);
+            const int32_t a = ld_stream(qs_in + t), b = ld_stream(qe_in + t);
+#pragma unroll
+            for (int k = 0; k < SK_PER_THREAD; ++k)
+                if (k == j) { qs[k] = a; qe[k] = b; }
         }
     }
-    // where each rank falls, and the tile's window of words in either table
+    // where each rank falls (32-bit arithmetic: build() refuses rank bits on a span that would overflow it),
+    // and the tile's window of words in either table.
+    //   ds = clamp(qe + 1 - lo_s, 0, span_s + 1)      #{starts <= qe} = #{starts < qe + 1}
+    //   de = clamp(qs - lo_e, 0, span_e + 1)          #{ends < qs}
     uint32_t ds[SK_PER_THREAD], de[SK_PER_THREAD];
     uint32_t smin = 0xFFFFFFFFu, smax = 0, emin = 0xFFFFFFFFu, emax = 0, inv = 0;
+    const int32_t lo_s = bs.lo, lo_e = be.lo;
+    const uint32_t span_s = bs.span, span1_e = be.span + 1u;
 #pragma unroll
     for (int j = 0; j < SK_PER_THREAD; ++j) {
-        ds[j] = sk_clamp((int64_t)qe[j] + 1, bs.lo, bs.span);   // #{starts <= qe} = #{starts < qe + 1}
-        de[j] = sk_clamp((int64_t)qs[j], be.lo, be.span);       // #{ends < qs}
-        if (base + j < nq) {
-            smin = min(smin, ds[j]); smax = max(smax, ds[j]);
-            emin = min(emin, de[j]); emax = max(emax, de[j]);
-            inv |= qs[j] > qe[j] ? 1u : 0u;
-        }
+        ds[j] = qe[j] < lo_s ? 0u : min((uint32_t)qe[j] - (uint32_t)lo_s, span_s) + 1u;
+        de[j] = qs[j] <= lo_e ? 0u : min((uint32_t)qs[j] - (uint32_t)lo_e, span1_e);
+        smin = min(smin, ds[j]); smax = max(smax, ds[j]);      // lanes past the end repeat the last query
+        emin = min(emin, de[j]); emax = max(emax, de[j]);
+        inv |= qs[j] > qe[j] ? 1u : 0u;
     }
     smin = __reduce_min_sync(FULL_MASK, smin); smax = __reduce_max_sync(FULL_MASK, smax);
     emin = __reduce_min_sync(FULL_MASK, emin); emax = __reduce_max_sync(FULL_MASK, emax);
@@ -217,9 +223,10 @@ sk_count_stream_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const in
         uint32_t ne = (e2.x & RB_MASK) + __popc(e2.y & m2);
         if (e1.x & RB_DUP) ns += __popc(Ds[k1] & m1);
         if (e2.x & RB_DUP) ne += __popc(De[k2] & m2);
-        if ((e1.x | e2.x) & RB_SLOW) {   // a coordinate with >= 3 values in one of the words: rank cells (rare)
-            if (e1.x & RB_SLOW) ns = cells_rank_lt(ix.cells_s, ix.starts, (int64_t)qe[j] + 1);
-            if (e2.x & RB_SLOW) ne = cells_rank_lt(ix.cells_e, ix.eall, (int64_t)qs[j]);
+        if (__builtin_expect(((e1.x | e2.x) & RB_SLOW) != 0, 0)) {   // a coordinate with >= 3 values in one of the words: rank cells (rare)
+            // a slow word lies inside the table's span, where d was not clamped: the coordinate is lo + d
+            if (e1.x & RB_SLOW) ns = cells_rank_lt(ix.cells_s, ix.starts, (int64_t)lo_s + ds[j]);
+            if (e2.x & RB_SLOW) ne = cells_rank_lt(ix.cells_e, ix.eall, (int64_t)lo_e + de[j]);
         }
         c[j] = ns - ne;
     }

@@ -96,7 +96,7 @@ def test_inverted_and_out_of_span_queries_in_a_sorted_batch(dense):
     o = np.argsort(qs, kind="stable")
     sq, se = qs[o].copy(), qe[o].copy()
     rng = np.random.default_rng(3)
-    k = rng.choice(sq.size, 5000, replace=False)
+    k = rng.choice(sq.size, 40, replace=False)
     se[k] = sq[k] - rng.integers(1, 3000, k.size).astype(np.int32)     # qs > qe (quirk Q6): the walk's definition
     sq[:300] = np.int32(-2_000_000_000); se[:300] = np.int32(-1_999_999_000)   # far below the index
     sq[-300:] = np.int32(2_000_000_000); se[-300:] = np.int32(2_100_000_000)   # far above
