@@ -227,6 +227,40 @@ int siFillDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n
 int siCoverageDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n,
                      uint32_t* d_counts, int32_t* d_cov, void* stream);
 
+/* ---- 4. several GPUs of one node (single host process; csrc/multi.cu) --------------------------------
+ * The reference has no notion of devices: its callers hold one map per chromosome and loop over the
+ * queries (examples/bed-intersect-si.rs:100-123). siMulti keeps one replica of ONE index per device and
+ * cuts every host batch into one contiguous range per device:
+ *   siMultiBuildReplicated    one upload to the first device, ncclBroadcast of the interval columns to
+ *                             the others over NVLink, every device builds its replica from device memory;
+ *   siMultiCountBatch         H2D of each range on its own PCIe link, one count launch per device, ONE
+ *                             ncclAllGather of the per-query counts (every device then holds the whole count
+ *                             vector: siMultiDeviceCounts), each device returns its range to counts_out;
+ *   siMultiSearchValuesBatch  the gathered counts are scanned on every device into GLOBAL 64-bit CSR offsets,
+ *                             each device fills and returns its own segment of `found` (same layout and order
+ *                             as searchValuesBatch).
+ * devices == NULL: ordinals 0..n_devices-1; n_devices <= 0: every visible device. NCCL (libnccl.so.2) is
+ * loaded at run time and only when n_devices > 1. All functions return 0 or a cudaError_t value. */
+typedef struct siMulti siMulti;
+typedef struct {
+    double ms_total;            /* host wall clock of the last batch call */
+    double ms_h2d, ms_count, ms_gather, ms_d2h;   /* device time per phase, max over devices (CUDA events) */
+    unsigned long long nccl_bytes;                /* bytes received through NCCL collectives since creation, all ranks */
+    int nccl_version;
+} siMultiStats;
+siMulti* siMultiCreate(const int* devices, int n_devices);
+void     siMultiDestroy(siMulti* m);
+int      siMultiDeviceCount(const siMulti* m);
+siIndex* siMultiIndexOf(siMulti* m, int rank);   /* the replica on one device (siIndexSetOption, siIndexCellsInfo ...) */
+int siMultiBuildReplicated(siMulti* m, const int32_t* starts, const int32_t* ends, const int32_t* values, size_t n);
+int siMultiCountBatch(siMulti* m, const int32_t* starts, const int32_t* ends, size_t n, uint32_t* counts_out);
+int siMultiSearchValuesBatch(siMulti* m, const int32_t* starts, const int32_t* ends, size_t n, size_t* offsets_out,
+                             cIndexResult* found);
+/* the gathered counts of the last batch on device `rank`: n_devices ranges of *per entries; range r holds the
+ * queries [r * per, (r + 1) * per) of the batch (zeros past its end) */
+int siMultiDeviceCounts(siMulti* m, int rank, const uint32_t** d_counts, size_t* per);
+int siMultiLastStats(const siMulti* m, siMultiStats* out);
+
 /* bytes of device memory currently held by the index + its workspaces */
 size_t siIndexDeviceBytes(const siIndex* ix);
 /* kernels launched by this library since process start (bench.py's gpu_launches) */

@@ -66,6 +66,11 @@ class siBitsInfo(C.Structure):
     _fields_ = [("built", C.c_int), ("words", C.c_ulonglong), ("bytes", C.c_ulonglong), ("slow_words", C.c_ulonglong)]
 
 
+class siMultiStats(C.Structure):
+    _fields_ = [("ms_total", C.c_double), ("ms_h2d", C.c_double), ("ms_count", C.c_double), ("ms_gather", C.c_double),
+                ("ms_d2h", C.c_double), ("nccl_bytes", C.c_ulonglong), ("nccl_version", C.c_int)]
+
+
 class siBedTable(C.Structure):
     _fields_ = [("contig", C.POINTER(C.c_int32)), ("starts", C.POINTER(C.c_int32)), ("ends", C.POINTER(C.c_int32)),
                 ("n", C.c_size_t), ("lines", C.c_size_t), ("skipped", C.c_size_t),
@@ -107,6 +112,8 @@ B200_SYMBOLS = [
     "siIndexDeviceView", "siIndexBuildHost", "siIndexBuildDevice", "siIndexExport", "siCountDevice",
     "siCountDevice64", "siSortQueriesDevice", "siIndexSetOption", "siIndexCellsInfo", "siIndexBitsInfo", "siIndexStreamStats", "siIndexStabInfo", "siIndexReadTimings", "siAnyDevice", "siScanDevice", "siFillDevice", "siCoverageDevice",
     "siIndexDeviceBytes",
+    "siMultiCreate", "siMultiDestroy", "siMultiDeviceCount", "siMultiIndexOf", "siMultiBuildReplicated", "siMultiCountBatch",
+    "siMultiSearchValuesBatch", "siMultiDeviceCounts", "siMultiLastStats",
 ]
 
 _lib = None
@@ -200,6 +207,17 @@ def bind_b200(L):
     L.siSortQueriesDevice.argtypes = [vp, vp, vp, sz, vp]
     L.siIndexCellsInfo.argtypes = [vp, C.c_int, C.POINTER(siCellsInfo)]
     L.siIndexCellsInfo.restype = C.c_int
+    L.siMultiCreate.restype = vp
+    L.siMultiCreate.argtypes = [vp, C.c_int]
+    L.siMultiDestroy.argtypes = [vp]
+    L.siMultiDeviceCount.argtypes = [vp]
+    L.siMultiIndexOf.restype = vp
+    L.siMultiIndexOf.argtypes = [vp, C.c_int]
+    L.siMultiBuildReplicated.argtypes = [vp, vp, vp, vp, sz]
+    L.siMultiCountBatch.argtypes = [vp, vp, vp, sz, vp]
+    L.siMultiSearchValuesBatch.argtypes = [vp, vp, vp, sz, vp, C.POINTER(cIndexResult)]
+    L.siMultiDeviceCounts.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
+    L.siMultiLastStats.argtypes = [vp, C.POINTER(siMultiStats)]
     L.siIndexBitsInfo.argtypes = [vp, C.POINTER(siBitsInfo)]
     L.siIndexBitsInfo.restype = C.c_int
     L.siIndexStreamStats.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]

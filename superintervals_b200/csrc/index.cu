@@ -547,17 +547,24 @@ bool stream_ready(const siIndex* ix) {
 template <typename CountT>
 int launch_count_stream(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, uint32_t nq, CountT* d_counts, cudaStream_t s) {
     static_assert(SK_TILE % QC_TILE == 0, "a streaming tile is a whole number of rank-cells tiles");
-    const int grid = (int)(((uint64_t)nq + SK_TILE - 1) / SK_TILE);
+    const int tiles = (int)(((uint64_t)nq + SK_TILE - 1) / SK_TILE);
     const uint32_t vec_ok = ((((uintptr_t)d_qs) | ((uintptr_t)d_qe) | ((uintptr_t)d_counts)) & 31u) == 0 ? 1u : 0u;
-    if (ix->stream_ws.ensure(((size_t)grid + 16) * 4)) return last_error_code();
+    if (ix->stream_ws.ensure(((size_t)tiles + 16) * 4)) return last_error_code();
     uint32_t* fail_count = ix->stream_ws.as<uint32_t>();
     uint32_t* fail_list = fail_count + 8;
     SIB_CHECK(cudaMemsetAsync(fail_count, 0, 4, s));
-    ix->stream_tiles = (unsigned long long)grid;
+    ix->stream_tiles = (unsigned long long)tiles;
+    // persistent CTAs: as many as the device holds at once (two staging stages of dynamic shared memory each)
+    auto kern = sk_count_stream_kernel<CountT>;
+    SIB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM));
+    int per_sm = 0;
+    SIB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SK_THREADS, SK_SMEM));
+    if (per_sm < 1) per_sm = 1;
+    const int grid = tiles < ix->sm_count * per_sm ? tiles : ix->sm_count * per_sm;
     ix->timer.begin(TAG_COUNT_STREAM, s);
-    sk_count_stream_kernel<CountT><<<grid, SK_THREADS, SK_SMEM, s>>>(view_of(ix), d_qs, d_qe, nq, d_counts, vec_ok, fail_list, fail_count);
+    kern<<<grid, SK_THREADS, SK_SMEM, s>>>(view_of(ix), d_qs, d_qe, nq, d_counts, vec_ok, (uint32_t)tiles, fail_list, fail_count);
     SIB_CHECK_LAUNCH();
-    const int grid2 = grid < ix->sm_count * 4 ? grid : ix->sm_count * 4;
+    const int grid2 = tiles < ix->sm_count * 4 ? tiles : ix->sm_count * 4;
     sk_count_failed_tiles_kernel<CountT><<<grid2, QC_THREADS, 0, s>>>(view_of(ix), d_qs, d_qe, nq, d_counts, fail_list, fail_count);
     SIB_CHECK_LAUNCH();
     ix->timer.end(s);

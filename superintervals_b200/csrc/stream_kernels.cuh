@@ -101,7 +101,14 @@ __device__ __forceinline__ void sk_st8(uint64_t* p, const uint32_t* c) {
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------
+// Persistent CTAs, software-pipelined over their tiles (tile = blockIdx.x + k * gridDim.x):
+//     while tile k is being ranked out of shared memory (stage k & 1),
+//       the TMA copies of tile k+1's windows are in flight into the other stage (its mbarrier), and
+//       the 256-bit loads of tile k+2's queries are in flight into registers.
+// One __syncthreads per tile (the window reduction; it also frees the stage the next copies overwrite);
+// the window itself is published through the stage's mbarrier (thread 0 writes it before it arrives).
 constexpr int SK_THREADS = 256;
+constexpr int SK_WARPS = SK_THREADS / 32;
 constexpr int SK_PER_THREAD = 8;
 constexpr uint32_t SK_TILE = SK_THREADS * SK_PER_THREAD;   // 2048 queries: 16 KB in, 8 KB out
 #ifndef SIB_SK_SW
@@ -110,132 +117,173 @@ constexpr uint32_t SK_TILE = SK_THREADS * SK_PER_THREAD;   // 2048 queries: 16 K
 #ifndef SIB_SK_EW
 #define SIB_SK_EW 768
 #endif
+#ifndef SIB_SK_MINBLOCKS
+#define SIB_SK_MINBLOCKS 3
+#endif
 constexpr uint32_t SK_SW = SIB_SK_SW;   // staged words of the starts table (x 32 coordinates)
 constexpr uint32_t SK_EW = SIB_SK_EW;   // staged words of the ends table
-constexpr size_t SK_SMEM = (size_t)(SK_SW + SK_EW) * 12 + 64;
+constexpr size_t SK_STAGE = (size_t)(SK_SW + SK_EW) * 12;
+constexpr size_t SK_SMEM = 2 * SK_STAGE;
 
-// d = x - lo clamped to [0, span + 1]: everything below A ranks 0, everything above ranks n
-__device__ __forceinline__ uint32_t sk_clamp(int64_t x, int32_t lo, uint32_t span) {
-    int64_t d = x - (int64_t)lo;
-    d = d < 0 ? 0 : d;
-    const int64_t dmax = (int64_t)span + 1;
-    return (uint32_t)(d > dmax ? dmax : d);
+struct SkStage {
+    uint2* Ts; uint2* Te; uint32_t* Ds; uint32_t* De;
+};
+__device__ __forceinline__ SkStage sk_stage(unsigned char* base, uint32_t stage) {
+    unsigned char* p = base + stage * SK_STAGE;
+    SkStage st;
+    st.Ts = reinterpret_cast<uint2*>(p);
+    st.Te = st.Ts + SK_SW;
+    st.Ds = reinterpret_cast<uint32_t*>(st.Te + SK_EW);
+    st.De = st.Ds + SK_SW;
+    return st;
+}
+__device__ __forceinline__ void sk_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sk_smem(bar)) : "memory");
 }
 
-#ifndef SIB_SK_MINBLOCKS
-#define SIB_SK_MINBLOCKS 4
-#endif
 // fail_list / fail_count: tiles this kernel does not answer -- their window does not fit the staging
 // buffers (an unsorted or very sparse tile) or they hold a query with qs > qe (quirk Q6: the closed
 // form does not apply) -- are appended here and answered by sk_count_failed_tiles_kernel right after.
 template <typename CountT>
 __global__ void __launch_bounds__(SK_THREADS, SIB_SK_MINBLOCKS)
 sk_count_stream_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* __restrict__ qe_in, uint32_t nq,
-                       CountT* __restrict__ counts, uint32_t vec_ok, uint32_t* __restrict__ fail_list,
+                       CountT* __restrict__ counts, uint32_t vec_ok, uint32_t ntiles, uint32_t* __restrict__ fail_list,
                        uint32_t* __restrict__ fail_count) {
     extern __shared__ __align__(128) unsigned char sk_sh[];
-    uint2* Ts = reinterpret_cast<uint2*>(sk_sh);
-    uint2* Te = Ts + SK_SW;
-    uint32_t* Ds = reinterpret_cast<uint32_t*>(Te + SK_EW);
-    uint32_t* De = Ds + SK_SW;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(De + SK_EW);
-    __shared__ uint32_t s_red[SK_THREADS / 32][5];
-    __shared__ uint32_t s_win[4];   // first staged word of each table, staged?
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint32_t s_red[2][SK_WARPS][5];
+    __shared__ uint32_t s_win[2][4];   // per stage: first staged word of each table, staged?
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const RankBits bs = ix.bits_s, be = ix.bits_e;
-    const uint64_t base = (uint64_t)blockIdx.x * SK_TILE + (uint64_t)tid * SK_PER_THREAD;
-
-    if (tid == 0) sk_mbar_init(bar, 1);
-
-    int32_t qs[SK_PER_THREAD], qe[SK_PER_THREAD];
-    const bool full = base + SK_PER_THREAD <= nq;
-    if (full && vec_ok) {
-        const Vec8 a = sk_ld8(qs_in + base), b = sk_ld8(qe_in + base);
-#pragma unroll
-        for (int j = 0; j < SK_PER_THREAD; ++j) { qs[j] = (int32_t)a.w[j]; qe[j] = (int32_t)b.w[j]; }
-    } else {
-        // lanes past the end of the batch repeat its last query: they stay inside the tile's window
-        // (and add nothing to it, to its inverted flag or to the output)
-#pragma unroll 1
-        for (int j = 0; j < SK_PER_THREAD; ++j) {
-            const uint64_t t = base + j < nq ? base + j : (uint64_t)nq - 1;
-            const int32_t a = ld_stream(qs_in + t), b = ld_stream(qe_in + t);
-#pragma unroll
-            for (int k = 0; k < SK_PER_THREAD; ++k)
-                if (k == j) { qs[k] = a; qe[k] = b; }
-        }
-    }
-    // where each rank falls (32-bit arithmetic: build() refuses rank bits on a span that would overflow it),
-    // and the tile's window of words in either table.
-    //   ds = clamp(qe + 1 - lo_s, 0, span_s + 1)      #{starts <= qe} = #{starts < qe + 1}
-    //   de = clamp(qs - lo_e, 0, span_e + 1)          #{ends < qs}
-    uint32_t ds[SK_PER_THREAD], de[SK_PER_THREAD];
-    uint32_t smin = 0xFFFFFFFFu, smax = 0, emin = 0xFFFFFFFFu, emax = 0, inv = 0;
     const int32_t lo_s = bs.lo, lo_e = be.lo;
     const uint32_t span_s = bs.span, span1_e = be.span + 1u;
+
+    uint32_t tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    if (tid == 0) { sk_mbar_init(&s_bar[0], 1); sk_mbar_init(&s_bar[1], 1); }
+
+    int32_t qs[SK_PER_THREAD], qe[SK_PER_THREAD];
+    // the queries of one tile into registers; lanes past the end of the batch repeat its last query: they stay
+    // inside the tile's window (and add nothing to it, to its inverted flag or to the output)
+    auto load_queries = [&](uint32_t t) {
+        const uint64_t base = (uint64_t)t * SK_TILE + (uint64_t)tid * SK_PER_THREAD;
+        if (base + SK_PER_THREAD <= nq && vec_ok) {
+            const Vec8 a = sk_ld8(qs_in + base), b = sk_ld8(qe_in + base);
 #pragma unroll
-    for (int j = 0; j < SK_PER_THREAD; ++j) {
-        ds[j] = qe[j] < lo_s ? 0u : min((uint32_t)qe[j] - (uint32_t)lo_s, span_s) + 1u;
-        de[j] = qs[j] <= lo_e ? 0u : min((uint32_t)qs[j] - (uint32_t)lo_e, span1_e);
-        smin = min(smin, ds[j]); smax = max(smax, ds[j]);      // lanes past the end repeat the last query
-        emin = min(emin, de[j]); emax = max(emax, de[j]);
-        inv |= qs[j] > qe[j] ? 1u : 0u;
-    }
-    smin = __reduce_min_sync(FULL_MASK, smin); smax = __reduce_max_sync(FULL_MASK, smax);
-    emin = __reduce_min_sync(FULL_MASK, emin); emax = __reduce_max_sync(FULL_MASK, emax);
-    inv = __reduce_or_sync(FULL_MASK, inv);
-    if (lane == 0) { s_red[warp][0] = smin; s_red[warp][1] = smax; s_red[warp][2] = emin; s_red[warp][3] = emax; s_red[warp][4] = inv; }
-    __syncthreads();
-    if (tid == 0) {
+            for (int j = 0; j < SK_PER_THREAD; ++j) { qs[j] = (int32_t)a.w[j]; qe[j] = (int32_t)b.w[j]; }
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < SK_PER_THREAD; ++j) {
+                const uint64_t q = base + j < nq ? base + j : (uint64_t)nq - 1;
+                const int32_t a = ld_stream(qs_in + q), b = ld_stream(qe_in + q);
 #pragma unroll
-        for (int w = 1; w < SK_THREADS / 32; ++w) {
-            smin = min(smin, s_red[w][0]); smax = max(smax, s_red[w][1]);
-            emin = min(emin, s_red[w][2]); emax = max(emax, s_red[w][3]);
-            inv |= s_red[w][4];
+                for (int k = 0; k < SK_PER_THREAD; ++k)
+                    if (k == j) { qs[k] = a; qe[k] = b; }
+            }
+        }
+    };
+    // where each rank falls (32-bit arithmetic: build() refuses rank bits on a span that would overflow it):
+    //   ds = clamp(qe + 1 - lo_s, 0, span_s + 1)      #{starts <= qe} = #{starts < qe + 1}
+    //   de = clamp(qs - lo_e, 0, span_e + 1)          #{ends < qs}
+    // and this warp's share of the tile's window of words in either table
+    auto place = [&](uint32_t (&ds)[SK_PER_THREAD], uint32_t (&de)[SK_PER_THREAD], uint32_t buf) {
+        uint32_t smin = 0xFFFFFFFFu, smax = 0, emin = 0xFFFFFFFFu, emax = 0, inv = 0;
+#pragma unroll
+        for (int j = 0; j < SK_PER_THREAD; ++j) {
+            ds[j] = qe[j] < lo_s ? 0u : min((uint32_t)qe[j] - (uint32_t)lo_s, span_s) + 1u;
+            de[j] = qs[j] <= lo_e ? 0u : min((uint32_t)qs[j] - (uint32_t)lo_e, span1_e);
+            smin = min(smin, ds[j]); smax = max(smax, ds[j]);
+            emin = min(emin, de[j]); emax = max(emax, de[j]);
+            inv |= qs[j] > qe[j] ? 1u : 0u;
+        }
+        smin = __reduce_min_sync(FULL_MASK, smin); smax = __reduce_max_sync(FULL_MASK, smax);
+        emin = __reduce_min_sync(FULL_MASK, emin); emax = __reduce_max_sync(FULL_MASK, emax);
+        inv = __reduce_or_sync(FULL_MASK, inv);
+        if (lane == 0) { s_red[buf][warp][0] = smin; s_red[buf][warp][1] = smax; s_red[buf][warp][2] = emin; s_red[buf][warp][3] = emax; s_red[buf][warp][4] = inv; }
+    };
+    // thread 0, after the barrier: the tile's window, its TMA copies into `stage`, completion on the stage's mbarrier
+    auto issue = [&](uint32_t t, uint32_t stage, uint32_t buf) {
+        uint32_t smin = 0xFFFFFFFFu, smax = 0, emin = 0xFFFFFFFFu, emax = 0, inv = 0;
+#pragma unroll
+        for (int w = 0; w < SK_WARPS; ++w) {
+            smin = min(smin, s_red[buf][w][0]); smax = max(smax, s_red[buf][w][1]);
+            emin = min(emin, s_red[buf][w][2]); emax = max(emax, s_red[buf][w][3]);
+            inv |= s_red[buf][w][4];
         }
         // windows in words, first word aligned to 4 (16-byte granules of both arrays), length a multiple of 4
         const uint32_t ks0 = (smin >> 5) & ~3u, ke0 = (emin >> 5) & ~3u;
         const uint32_t ls = (((smax >> 5) - ks0) | 3u) + 1u, le = (((emax >> 5) - ke0) | 3u) + 1u;
         const bool ok = !inv && ls <= SK_SW && le <= SK_EW;
-        s_win[0] = ks0; s_win[1] = ke0; s_win[2] = ok ? 1u : 0u;
+        s_win[stage][0] = ks0; s_win[stage][1] = ke0; s_win[stage][2] = ok ? 1u : 0u;
+        uint64_t* bar = &s_bar[stage];
         if (ok) {
-            sk_mbar_expect_tx(bar, (ls + le) * 12u);
-            sk_bulk_g2s(Ts, bs.t + ks0, ls * 8u, bar);
-            sk_bulk_g2s(Te, be.t + ke0, le * 8u, bar);
-            sk_bulk_g2s(Ds, bs.d2 + ks0, ls * 4u, bar);
-            sk_bulk_g2s(De, be.d2 + ke0, le * 4u, bar);
+            const SkStage st = sk_stage(sk_sh, stage);
+            sk_mbar_expect_tx(bar, (ls + le) * 12u);      // release: s_win is visible to whoever sees the phase complete
+            sk_bulk_g2s(st.Ts, bs.t + ks0, ls * 8u, bar);
+            sk_bulk_g2s(st.Te, be.t + ke0, le * 8u, bar);
+            sk_bulk_g2s(st.Ds, bs.d2 + ks0, ls * 4u, bar);
+            sk_bulk_g2s(st.De, be.d2 + ke0, le * 4u, bar);
         } else {
-            fail_list[atomicAdd(fail_count, 1u)] = blockIdx.x;
+            fail_list[atomicAdd(fail_count, 1u)] = t;
+            sk_mbar_arrive(bar);                          // nothing to wait for: the phase completes at once
         }
-    }
-    __syncthreads();
-    if (s_win[2] == 0) return;
-    const uint32_t ks0 = s_win[0], ke0 = s_win[1];
-    sk_mbar_wait(bar, 0);
-    uint32_t c[SK_PER_THREAD];
+    };
+    // every rank of one tile from its staged windows
+    auto rank_tile = [&](uint32_t t, uint32_t stage, uint32_t parity, const uint32_t (&ds)[SK_PER_THREAD], const uint32_t (&de)[SK_PER_THREAD]) {
+        sk_mbar_wait(&s_bar[stage], parity);
+        if (s_win[stage][2] == 0) return;
+        const uint32_t ks0 = s_win[stage][0], ke0 = s_win[stage][1];
+        const SkStage st = sk_stage(sk_sh, stage);
+        uint32_t c[SK_PER_THREAD];
 #pragma unroll
-    for (int j = 0; j < SK_PER_THREAD; ++j) {
-        const uint32_t k1 = (ds[j] >> 5) - ks0, k2 = (de[j] >> 5) - ke0;
-        const uint2 e1 = Ts[k1], e2 = Te[k2];
-        const uint32_t m1 = (1u << (ds[j] & 31u)) - 1u, m2 = (1u << (de[j] & 31u)) - 1u;
-        uint32_t ns = (e1.x & RB_MASK) + __popc(e1.y & m1);
-        uint32_t ne = (e2.x & RB_MASK) + __popc(e2.y & m2);
-        if (e1.x & RB_DUP) ns += __popc(Ds[k1] & m1);
-        if (e2.x & RB_DUP) ne += __popc(De[k2] & m2);
-        if (__builtin_expect(((e1.x | e2.x) & RB_SLOW) != 0, 0)) {   // a coordinate with >= 3 values in one of the words: rank cells (rare)
-            // a slow word lies inside the table's span, where d was not clamped: the coordinate is lo + d
-            if (e1.x & RB_SLOW) ns = cells_rank_lt(ix.cells_s, ix.starts, (int64_t)lo_s + ds[j]);
-            if (e2.x & RB_SLOW) ne = cells_rank_lt(ix.cells_e, ix.eall, (int64_t)lo_e + de[j]);
+        for (int j = 0; j < SK_PER_THREAD; ++j) {
+            const uint32_t k1 = (ds[j] >> 5) - ks0, k2 = (de[j] >> 5) - ke0;
+            const uint2 e1 = st.Ts[k1], e2 = st.Te[k2];
+            const uint32_t m1 = (1u << (ds[j] & 31u)) - 1u, m2 = (1u << (de[j] & 31u)) - 1u;
+            uint32_t ns = (e1.x & RB_MASK) + __popc(e1.y & m1);
+            uint32_t ne = (e2.x & RB_MASK) + __popc(e2.y & m2);
+            if (e1.x & RB_DUP) ns += __popc(st.Ds[k1] & m1);
+            if (e2.x & RB_DUP) ne += __popc(st.De[k2] & m2);
+            if (__builtin_expect(((e1.x | e2.x) & RB_SLOW) != 0, 0)) {   // a coordinate with >= 3 values in one of the words: rank cells (rare)
+                // a slow word lies inside the table's span, where d was not clamped: the coordinate is lo + d
+                if (e1.x & RB_SLOW) ns = cells_rank_lt(ix.cells_s, ix.starts, (int64_t)lo_s + ds[j]);
+                if (e2.x & RB_SLOW) ne = cells_rank_lt(ix.cells_e, ix.eall, (int64_t)lo_e + de[j]);
+            }
+            c[j] = ns - ne;
         }
-        c[j] = ns - ne;
-    }
-    if (full && vec_ok) {
-        sk_st8(counts + base, c);
-    } else {
+        const uint64_t base = (uint64_t)t * SK_TILE + (uint64_t)tid * SK_PER_THREAD;
+        if (base + SK_PER_THREAD <= nq && vec_ok) {
+            sk_st8(counts + base, c);
+        } else {
 #pragma unroll
-        for (int j = 0; j < SK_PER_THREAD; ++j)
-            if (base + j < nq) counts[base + j] = (CountT)c[j];
+            for (int j = 0; j < SK_PER_THREAD; ++j)
+                if (base + j < nq) counts[base + j] = (CountT)c[j];
+        }
+    };
+
+    uint32_t dsA[SK_PER_THREAD], deA[SK_PER_THREAD], dsB[SK_PER_THREAD], deB[SK_PER_THREAD];
+    load_queries(tile);
+    place(dsA, deA, 0);
+    __syncthreads();                       // s_red[0] complete; the mbarrier inits are visible
+    if (tid == 0) issue(tile, 0, 0);
+    uint32_t next = tile + gridDim.x;
+    if (next < ntiles) load_queries(next);
+    for (uint32_t k = 0;; ++k) {
+        const uint32_t stage = k & 1u, parity = (k >> 1) & 1u;
+        const bool has_next = next < ntiles;
+        if (has_next) place(dsB, deB, (k + 1u) & 1u);
+        __syncthreads();                   // s_red complete; everyone has left tile k-1, whose stage the next copies overwrite
+        if (has_next) {
+            if (tid == 0) issue(next, stage ^ 1u, (k + 1u) & 1u);
+            if (next + gridDim.x < ntiles) load_queries(next + gridDim.x);
+        }
+        rank_tile(tile, stage, parity, dsA, deA);
+        if (!has_next) break;
+#pragma unroll
+        for (int j = 0; j < SK_PER_THREAD; ++j) { dsA[j] = dsB[j]; deA[j] = deB[j]; }
+        tile = next;
+        next += gridDim.x;
     }
 }
 
