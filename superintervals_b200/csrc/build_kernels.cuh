@@ -136,10 +136,46 @@ bk_sort_blocks_kernel(const int32_t* __restrict__ ends, uint32_t n_padded, int32
 }
 
 // ---- eall: every end, ascending (count by rank, query_kernels.cuh) ----------------------
+// Malformed intervals (start > end) take the largest key: they sort behind every well-formed end and are
+// cut off (the closed-form rank tables cover the well-formed intervals only; index.cu).
 __global__ void __launch_bounds__(BK_THREADS)
-bk_end_keys_kernel(const int32_t* __restrict__ ends, uint32_t n, uint32_t* __restrict__ keys) {
+bk_end_keys_kernel(const int32_t* __restrict__ starts, const int32_t* __restrict__ ends, uint32_t n, uint32_t* __restrict__ keys) {
     const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
-    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i < n; i += stride) keys[i] = flip_i32(ends[i]);
+    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i < n; i += stride)
+        keys[i] = starts[i] > ends[i] ? 0xFFFFFFFFu : flip_i32(ends[i]);
+}
+
+// ---- the (few) malformed intervals of a built index: positions, starts and ends, at most `cap` of them ----
+// out[0] = how many exist (may exceed cap); out[1 + 3k ..] = (position, start, end) of the first cap found
+// (in no particular order: the host sorts them by position).
+__global__ void __launch_bounds__(BK_THREADS)
+bk_find_malformed_kernel(const int32_t* __restrict__ starts, const int32_t* __restrict__ ends, uint32_t n, uint32_t cap,
+                         uint32_t* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i < n; i += stride) {
+        const int32_t s = starts[i], e = ends[i];
+        if (s > e) {
+            const uint32_t k = atomicAdd(out, 1u);
+            if (k < cap) { out[1 + 3 * k] = (uint32_t)i; out[2 + 3 * k] = (uint32_t)s; out[3 + 3 * k] = (uint32_t)e; }
+        }
+    }
+}
+
+constexpr int BK_MAX_MALFORMED = 8;
+struct MalformedList { uint32_t n; uint32_t pos[BK_MAX_MALFORMED]; };
+// starts of the well-formed intervals only, order kept: position i moves down by the malformed positions below it
+__global__ void __launch_bounds__(BK_THREADS)
+bk_compact_wellformed_kernel(const int32_t* __restrict__ starts, uint32_t n, MalformedList mal, uint32_t n_padded_out,
+                             int32_t* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i < n; i += stride) {
+        uint32_t below = 0;
+        bool is_mal = false;
+        for (uint32_t k = 0; k < mal.n; ++k) { below += mal.pos[k] < i ? 1u : 0u; is_mal |= mal.pos[k] == i; }
+        if (!is_mal) out[i - below] = starts[i];
+    }
+    // pad like the index arrays (128-bit loads never leave the array)
+    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x + (n - mal.n); i < n_padded_out; i += stride) out[i] = INT_MAX;
 }
 
 __global__ void __launch_bounds__(BK_THREADS)

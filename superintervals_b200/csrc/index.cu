@@ -122,7 +122,7 @@ using namespace sib;
     } while (0)
 
 size_t siIndex::device_bytes() const {
-    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &esort, &eall, &grid_tab, &cells_s, &cells_e, &bits_s_t, &bits_s_d, &bits_e_t, &bits_e_d, &stream_ws, &stab_off, &stab_hdr, &stab_ent, &stab_cnt, &b_in_s, &b_in_e, &b_in_v,
+    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &esort, &eall, &grid_tab, &cells_s, &cells_e, &bits_s_t, &bits_s_d, &bits_e_t, &bits_e_d, &stream_ws, &starts_wf, &stab_off, &stab_hdr, &stab_ent, &stab_cnt, &b_in_s, &b_in_e, &b_in_v,
                            &b_kA, &b_kB, &b_vA, &b_vB, &b_ws, &small, &q_A, &q_B,
                            &q_ws, &scan_status, &h_qs, &h_qe, &h_counts, &h_offsets, &h_out, &h_cov};
     size_t s = 0;
@@ -170,6 +170,9 @@ IndexView view_of(const siIndex* ix) {
     v.stab = StabLists{ix->stab_hdr.as<uint4>(), stab ? ix->stab_ent.p : nullptr, ix->stab_rec16 ? 1u : 0u, ix->stab_kshift, ix->stab_nlists};
     v.n = ix->n;
     v.wellformed = ix->wellformed ? 1u : 0u;
+    v.rstarts = ix->n_mal ? ix->starts_wf.as<int32_t>() : ix->starts.as<int32_t>();
+    v.n_mal = ix->rank_ok ? ix->n_mal : 0u;
+    for (int k = 0; k < 8; ++k) { v.mal_s[k] = ix->mal_s[k]; v.mal_e[k] = ix->mal_e[k]; }
     return v;
 }
 
@@ -239,8 +242,7 @@ int build_branch(siIndex* ix, cudaStream_t s) {
 // Rank cells over a sorted device array A[0..n) whose first and last values are known on the
 // host: pick the record format and the cell width from the density (cells_plan), then one thread per cell
 // (cells_fill). Both tables share one allocation, so that one L2 access-policy window covers them.
-void cells_plan(const siIndex* ix, int32_t first, int32_t last, siIndex::CellsMeta* m) {
-    const uint32_t n = ix->n;
+void cells_plan(const siIndex* ix, uint32_t n, int32_t first, int32_t last, siIndex::CellsMeta* m) {
     const uint64_t range = (uint64_t)((int64_t)last - (int64_t)first) + 1;
     // largest shift <= smax with a mean of at most `fill` values per cell
     auto pick = [&](uint32_t fill, uint32_t smax) {
@@ -261,12 +263,12 @@ void cells_plan(const siIndex* ix, int32_t first, int32_t last, siIndex::CellsMe
 }
 size_t cells_bytes(const siIndex::CellsMeta& m) { return (((size_t)m.cells + 1) * 32 + 255) & ~(size_t)255; }
 
-int cells_fill(siIndex* ix, const int32_t* A, const siIndex::CellsMeta& m, uint4* rec, unsigned long long* d_overfull, cudaStream_t s) {
+int cells_fill(siIndex* ix, const int32_t* A, uint32_t n, const siIndex::CellsMeta& m, uint4* rec, unsigned long long* d_overfull, cudaStream_t s) {
     const int grid = grid_for((uint64_t)m.cells + 1, BK_THREADS, ix->sm_count * 16);
     if (m.fmt == 1)
-        SIB_LAUNCH((bk_rank_cells_kernel<1>), grid, BK_THREADS, 0, s, A, ix->n, m.lo, m.shift, m.cells, rec, d_overfull);
+        SIB_LAUNCH((bk_rank_cells_kernel<1>), grid, BK_THREADS, 0, s, A, n, m.lo, m.shift, m.cells, rec, d_overfull);
     else
-        SIB_LAUNCH((bk_rank_cells_kernel<2>), grid, BK_THREADS, 0, s, A, ix->n, m.lo, m.shift, m.cells, rec, d_overfull);
+        SIB_LAUNCH((bk_rank_cells_kernel<2>), grid, BK_THREADS, 0, s, A, n, m.lo, m.shift, m.cells, rec, d_overfull);
     return 0;
 }
 
@@ -289,6 +291,8 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
     ix->plan_valid = false;
     ix->cm_s.fmt = ix->cm_e.fmt = 0;
     ix->bits_ok = false;
+    ix->rank_ok = false;
+    ix->n_mal = 0;
     ix->stab_state = 0;
     ix->stab_entries = 0;
     if (n > MAX_N) {
@@ -348,13 +352,48 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
 
     // span of the index on the host (the partition key buckets it); callers synchronise `s`
     SIB_CHECK(cudaMemcpyAsync(&ix->lo, ix->starts.p, 4, cudaMemcpyDeviceToHost, s));
-    if (ix->wellformed) {
-        // every end, ascending: the second array of the count-by-rank kernel
+    ix->rank_ok = ix->wellformed;
+    ix->n_mal = 0;
+    ix->n_rank = ix->n;
+    const int32_t* rstarts = ix->starts.as<int32_t>();
+    if (!ix->wellformed) {
+        // A few intervals with start > end (the reference stores them, quirk Q6) do not forfeit the closed-form
+        // count: list them; the rank tables then cover the well-formed intervals and every query tests the listed ones.
+        uint32_t* d_mal = ix->small.as<uint32_t>() + 32;   // count + 8 x (position, start, end)
+        SIB_CHECK(cudaMemsetAsync(d_mal, 0, 4 * (1 + 3 * BK_MAX_MALFORMED), s));
+        SIB_LAUNCH(bk_find_malformed_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, ix->starts.as<int32_t>(),
+                   ix->ends.as<int32_t>(), ix->n, (uint32_t)BK_MAX_MALFORMED, d_mal);
+        uint32_t h_mal[1 + 3 * BK_MAX_MALFORMED] = {0};
+        SIB_CHECK(cudaMemcpyAsync(h_mal, d_mal, sizeof(h_mal), cudaMemcpyDeviceToHost, s));
+        SIB_CHECK(cudaStreamSynchronize(s));
+        if (h_mal[0] <= (uint32_t)BK_MAX_MALFORMED && h_mal[0] < ix->n) {
+            ix->n_mal = h_mal[0];
+            // by position, ascending (insertion sort: at most 8 entries)
+            for (uint32_t a = 0; a < ix->n_mal; ++a) { ix->mal_pos[a] = h_mal[1 + 3 * a]; ix->mal_s[a] = (int32_t)h_mal[2 + 3 * a]; ix->mal_e[a] = (int32_t)h_mal[3 + 3 * a]; }
+            for (uint32_t a = 1; a < ix->n_mal; ++a)
+                for (uint32_t b = a; b > 0 && ix->mal_pos[b - 1] > ix->mal_pos[b]; --b) {
+                    std::swap(ix->mal_pos[b - 1], ix->mal_pos[b]); std::swap(ix->mal_s[b - 1], ix->mal_s[b]); std::swap(ix->mal_e[b - 1], ix->mal_e[b]);
+                }
+            ix->n_rank = ix->n - ix->n_mal;
+            const uint32_t wf_padded = (uint32_t)(((uint64_t)ix->n_rank + 127) & ~(uint64_t)127);
+            if (ix->starts_wf.ensure((size_t)wf_padded * 4)) return last_error_code();
+            MalformedList ml;
+            ml.n = ix->n_mal;
+            for (uint32_t a = 0; a < (uint32_t)BK_MAX_MALFORMED; ++a) ml.pos[a] = a < ix->n_mal ? ix->mal_pos[a] : 0u;
+            SIB_LAUNCH(bk_compact_wellformed_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, ix->starts.as<int32_t>(), ix->n, ml,
+                       wf_padded, ix->starts_wf.as<int32_t>());
+            rstarts = ix->starts_wf.as<int32_t>();
+            ix->rank_ok = true;
+        }
+    }
+    if (ix->rank_ok) {
+        const uint32_t nr = ix->n_rank;
+        // every (well-formed) end, ascending: the second array of the count-by-rank kernel
         if (ix->eall.ensure(pad_b) || ix->b_kA.ensure(n * 4) || ix->b_kB.ensure(n * 4) || ix->b_vA.ensure(n * 4) ||
             ix->b_vB.ensure(n * 4) || ix->b_ws.ensure(rs_workspace_bytes<uint32_t>(ix->n)))
             return last_error_code();
-        SIB_LAUNCH(bk_end_keys_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, ix->ends.as<int32_t>(), ix->n,
-                   ix->b_kA.as<uint32_t>());
+        SIB_LAUNCH(bk_end_keys_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, ix->starts.as<int32_t>(), ix->ends.as<int32_t>(),
+                   ix->n, ix->b_kA.as<uint32_t>());
         // payload buffers ride along unused: the sort moves (key, uint32) pairs (zeroed so that no kernel
         // ever reads uninitialised memory: compute-sanitizer initcheck stays clean)
         SIB_CHECK(cudaMemsetAsync(ix->b_vA.p, 0, n * 4, s));
@@ -363,26 +402,27 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
         if (rc) return rc;
         RsWorkspace ws = rs_carve(ix->b_ws.p);
         SIB_LAUNCH(bk_sorted_ends_kernel, grid_for(ix->n_padded, BK_THREADS, cap), BK_THREADS, 0, s,
-                   ix->b_kA.as<uint32_t>(), ix->b_kB.as<uint32_t>(), ws.final_sel, ix->n, ix->n_padded,
+                   ix->b_kA.as<uint32_t>(), ix->b_kB.as<uint32_t>(), ws.final_sel, nr, ix->n_padded,
                    ix->eall.as<int32_t>());
-        SIB_CHECK(cudaMemcpyAsync(&ix->hi, ix->eall.as<int32_t>() + (ix->n - 1), 4, cudaMemcpyDeviceToHost, s));
-        int32_t last_start = 0, first_end = 0;
-        SIB_CHECK(cudaMemcpyAsync(&last_start, ix->starts.as<int32_t>() + (ix->n - 1), 4, cudaMemcpyDeviceToHost, s));
+        SIB_CHECK(cudaMemcpyAsync(&ix->hi, ix->eall.as<int32_t>() + (nr - 1), 4, cudaMemcpyDeviceToHost, s));
+        int32_t last_start = 0, first_end = 0, first_start = 0;
+        SIB_CHECK(cudaMemcpyAsync(&first_start, rstarts, 4, cudaMemcpyDeviceToHost, s));
+        SIB_CHECK(cudaMemcpyAsync(&last_start, rstarts + (nr - 1), 4, cudaMemcpyDeviceToHost, s));
         SIB_CHECK(cudaMemcpyAsync(&first_end, ix->eall.as<int32_t>(), 4, cudaMemcpyDeviceToHost, s));
         // rank grid over [lo, hi]: the span has to be known on the host to size the tables
         SIB_CHECK(cudaStreamSynchronize(s));
-        if (n < 0x80000000ull) {   // bit 31 of a cell's rank word flags an over-full cell
+        if (nr < 0x80000000u) {   // bit 31 of a cell's rank word flags an over-full cell
             unsigned long long* d_over = reinterpret_cast<unsigned long long*>(ix->small.as<uint32_t>() + 8);
             SIB_CHECK(cudaMemsetAsync(d_over, 0, 16, s));
             siIndex::CellsMeta ms, me;
-            cells_plan(ix, ix->lo, last_start, &ms);
-            cells_plan(ix, first_end, ix->hi, &me);
+            cells_plan(ix, nr, first_start, last_start, &ms);
+            cells_plan(ix, nr, first_end, ix->hi, &me);
             if (ix->cells_s.ensure(cells_bytes(ms) + cells_bytes(me))) return last_error_code();
             ix->cells_e_ptr = reinterpret_cast<uint4*>(reinterpret_cast<char*>(ix->cells_s.p) + cells_bytes(ms));
             ix->cells_total_bytes = cells_bytes(ms) + cells_bytes(me);
-            rc = cells_fill(ix, ix->starts.as<int32_t>(), ms, ix->cells_s.as<uint4>(), d_over, s);
+            rc = cells_fill(ix, rstarts, nr, ms, ix->cells_s.as<uint4>(), d_over, s);
             if (rc) return rc;
-            rc = cells_fill(ix, ix->eall.as<int32_t>(), me, ix->cells_e_ptr, d_over + 1, s);
+            rc = cells_fill(ix, ix->eall.as<int32_t>(), nr, me, ix->cells_e_ptr, d_over + 1, s);
             if (rc) return rc;
             ix->cm_s = ms;
             ix->cm_e = me;
@@ -393,7 +433,7 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
             ix->cm_e.overfull = over[1];
             // rank bits for the streaming count: only where they stay affordable next to the index
             const uint64_t words = (((uint64_t)ix->cm_s.span + 1) >> 5) + (((uint64_t)ix->cm_e.span + 1) >> 5) + 16;
-            if (ix->stream_mode != 0 && n < 0x40000000ull && words * 12 <= (uint64_t)ix->bits_budget * n &&
+            if (ix->stream_mode != 0 && ix->n_mal == 0 && n < 0x40000000ull && words * 12 <= (uint64_t)ix->bits_budget * n &&
                 ix->cm_s.span < 0xFFFFFFF0u && ix->cm_e.span < 0xFFFFFFF0u) {   // the kernel's clamps are 32-bit
                 SIB_CHECK(cudaMemsetAsync(d_over, 0, 16, s));
                 rc = build_bits(ix, ix->starts.as<int32_t>(), ix->cells_s.as<uint4>(), ix->cm_s, &ix->bits_s_t, &ix->bits_s_d, &ix->bits_words_s, d_over, s);
@@ -407,7 +447,7 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
                 ix->bits_ok = (ix->bits_slow[0] + ix->bits_slow[1]) * 32 <= words;
             }
         }
-        {
+        if (ix->wellformed) {
             const uint64_t range = (uint64_t)((int64_t)ix->hi - (int64_t)ix->lo) + 1;   // >= 1 on a well-formed index
             int gbits = 0;
             while (gbits < 24 && ((uint64_t)ix->grid_intervals << gbits) < n) ++gbits;
@@ -438,7 +478,7 @@ void release_build_scratch(siIndex* ix) {
 
 // which count kernel answers this index (SI_OPT_COUNT_ALGO; results are identical)
 int count_algo_of(const siIndex* ix) {
-    const bool cells_ok = ix->wellformed && ix->cm_s.fmt && ix->cm_e.fmt;
+    const bool cells_ok = ix->rank_ok && ix->cm_s.fmt && ix->cm_e.fmt;
     switch (ix->count_algo) {
         case SI_COUNT_WALK: return SI_COUNT_WALK;
         case SI_COUNT_RANK: return ix->wellformed ? SI_COUNT_RANK : SI_COUNT_WALK;
@@ -455,7 +495,7 @@ bool cells_direct(const siIndex* ix) {
 
 // The CSR fill follows the count kernel: with rank cells it copies each query's certain run and
 // walks only below it (qk_fill_runs_kernel); otherwise the plain walk (qk_fill_kernel).
-bool fill_by_runs(const siIndex* ix) { return count_algo_of(ix) == SI_COUNT_CELLS; }
+bool fill_by_runs(const siIndex* ix) { return ix->wellformed && count_algo_of(ix) == SI_COUNT_CELLS; }
 
 // Partition a query batch for locality (partition.cuh): records grouped by (result window,
 // position bucket). *out describes the partitioned records; the partition of the same
@@ -742,7 +782,7 @@ void siIndexDestroy(siIndex* ix) {
     if (!ix) return;
     DeviceGuard g(ix->device);
     DevBuf* all[] = {&ix->starts, &ix->ends, &ix->values, &ix->branch, &ix->perm, &ix->tree, &ix->esort, &ix->eall, &ix->grid_tab,
-                     &ix->cells_s, &ix->cells_e, &ix->bits_s_t, &ix->bits_s_d, &ix->bits_e_t, &ix->bits_e_d, &ix->stream_ws, &ix->stab_off, &ix->stab_hdr, &ix->stab_ent, &ix->stab_cnt,
+                     &ix->cells_s, &ix->cells_e, &ix->bits_s_t, &ix->bits_s_d, &ix->bits_e_t, &ix->bits_e_d, &ix->stream_ws, &ix->starts_wf, &ix->stab_off, &ix->stab_hdr, &ix->stab_ent, &ix->stab_cnt,
                      &ix->b_in_s, &ix->b_in_e, &ix->b_in_v, &ix->b_kA, &ix->b_kB, &ix->b_vA, &ix->b_vB, &ix->b_ws,
                      &ix->small, &ix->q_A, &ix->q_B, &ix->q_ws, &ix->scan_status, &ix->h_qs,
                      &ix->h_qe, &ix->h_counts, &ix->h_offsets, &ix->h_out, &ix->h_cov};

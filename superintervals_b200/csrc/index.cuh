@@ -47,7 +47,15 @@ struct siIndex {
     // ---- the index, position order -------------------------------------------------
     uint32_t n = 0, n_padded = 0;
     bool built = false;
-    bool wellformed = false;   // every interval has start <= end (enables the count shortcut)
+    bool wellformed = false;   // every interval has start <= end
+    // The closed-form count needs start <= end. A FEW malformed intervals (the reference accepts them, quirk Q6)
+    // do not forfeit it: the rank tables are built over the well-formed intervals and the malformed ones are
+    // tested one by one per query (mal_*). rank_ok = closed form available; n_rank = intervals the tables cover.
+    bool rank_ok = false;
+    uint32_t n_rank = 0, n_mal = 0;
+    uint32_t mal_pos[8] = {0};
+    int32_t mal_s[8] = {0}, mal_e[8] = {0};
+    sib::DevBuf starts_wf;     // starts of the well-formed intervals (only when n_mal > 0)
     sib::DevBuf starts, ends, values, branch, perm;
     sib::DevBuf esort;         // ends, each aligned 32-block sorted ascending (count sweep)
     sib::DevBuf eall;          // all ends sorted ascending (count by rank); well-formed indexes only

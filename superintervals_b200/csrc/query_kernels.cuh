@@ -108,6 +108,11 @@ struct IndexView {
     RankBits bits_e;         // rank bits over eall    } index (t == nullptr otherwise)
     uint32_t n;
     uint32_t wellformed;     // 1 when every stored interval has start <= end (checked by build())
+    // closed-form count with a few malformed intervals: the rank tables (cells, eall) cover the well-formed
+    // intervals only -- rstarts are their starts (== starts when n_mal == 0) -- and the malformed ones are tested per query
+    const int32_t* rstarts;
+    uint32_t n_mal;
+    int32_t mal_s[8], mal_e[8];
 };
 
 // Number of starts <= v, by the reference's branch-free halving search (hpp:501-513).
@@ -623,13 +628,19 @@ __device__ __forceinline__ void count_cells_tile(const IndexView& ix, const Quer
     }
 #pragma unroll
     for (int j = 0; j < QC_PER_THREAD; ++j) {
-        const uint32_t ns = cell_rank(cs, ix.starts, rs[j], cell_s[j], off_s[j], (int64_t)qe[j] + 1);
+        const uint32_t ns = cell_rank(cs, ix.rstarts, rs[j], cell_s[j], off_s[j], (int64_t)qe[j] + 1);
         const uint32_t ne = cell_rank(ce, ix.eall, re[j], cell_e[j], off_e[j], (int64_t)qs[j]);
         uint32_t c = ns - ne;
+        uint32_t mal_before = 0;    // malformed intervals with start <= qe: they are candidates too
+        for (uint32_t k = 0; k < ix.n_mal; ++k) {           // warp-uniform trip count, usually zero
+            const bool cand = ix.mal_s[k] <= qe[j];
+            mal_before += cand ? 1u : 0u;
+            c += (cand && ix.mal_e[k] >= qs[j]) ? 1u : 0u;
+        }
         const bool inverted = live[j] && qs[j] > qe[j];
         if (__any_sync(FULL_MASK, inverted)) {
-            // qs > qe: the walk's own definition, #{ j <= ub(qe) : ends[j] >= qs }
-            const uint32_t i = inverted ? ns - 1u : NONE32;   // ns = #{starts <= qe}; 0 - 1 wraps to NONE32
+            // qs > qe: the walk's own definition, #{ j <= ub(qe) : ends[j] >= qs }, over ALL stored intervals
+            const uint32_t i = inverted ? ns + mal_before - 1u : NONE32;   // #{starts <= qe} - 1; 0 - 1 wraps to NONE32
             const uint32_t cw = walk_tail_rare(ix.ends, ix.branch, i, qs[j]);
             if (inverted) c = cw;
         }

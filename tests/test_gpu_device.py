@@ -96,6 +96,40 @@ def test_malformed_intervals_disable_the_shortcut_but_stay_exact():
     assert np.array_equal(off.cpu().numpy().astype(np.uint64), off_o) and np.array_equal(vals.cpu().numpy(), res["values"])
 
 
+@pytest.mark.parametrize("n_mal", [1, 8, 9])
+def test_a_few_malformed_intervals_keep_the_closed_form(n_mal):
+    """one start > end interval in 1 M must not flip the index to the walk kernels. Up to 8 are
+    listed beside the rank tables (count stays on the cells kernel); more than 8 fall back to the walk. Bit-exact either way,
+    inverted queries included (hpp:651-658, quirk Q6)."""
+    from superintervals_b200.device import DeviceIndex, OPT_TIMING, ORDER_UNSORTED
+    rng = np.random.default_rng(77 + n_mal)
+    n, nq = 1_000_000, 300_000
+    s = rng.integers(0, 50_000_000, n).astype(np.int32)
+    e = (s + rng.integers(0, 3000, n)).astype(np.int32)
+    bad = rng.choice(n, n_mal, replace=False)
+    e[bad] = s[bad] - rng.integers(1, 5000, n_mal).astype(np.int32)        # start > end
+    qs = rng.integers(0, 50_000_000, nq).astype(np.int32)
+    qe = (qs + rng.integers(-20, 4000, nq)).astype(np.int32)                # some queries inverted too
+    # queries that bracket the malformed intervals from every side
+    qs[:n_mal], qe[:n_mal] = e[bad], s[bad]
+    qs[n_mal:2 * n_mal], qe[n_mal:2 * n_mal] = s[bad], s[bad]
+    qs[2 * n_mal:3 * n_mal], qe[2 * n_mal:3 * n_mal] = e[bad] - 10, e[bad]
+    orc = Oracle(s, e)
+    ix = DeviceIndex().build(_dev(s), _dev(e))
+    ix.set_option(OPT_TIMING, 1)
+    got = _u32(ix.count(_dev(qs), _dev(qe), order=ORDER_UNSORTED))
+    names = {k for k, _ in ix.read_timings()}
+    ix.set_option(OPT_TIMING, 0)
+    assert np.array_equal(got, orc.count_batch(qs, qe))
+    assert ("count_cells" in names) == (n_mal <= 8), names
+    m = 50_000
+    off_o, res = orc.search_batch(qs[:m], qe[:m])
+    off, vals = ix.search_values(_dev(qs[:m]), _dev(qe[:m]))
+    assert np.array_equal(off.cpu().numpy().astype(np.uint64), off_o) and np.array_equal(vals.cpu().numpy(), res["values"])
+    s1, e1, _, b1, _ = ix.export()
+    assert np.array_equal(s1, orc.starts) and np.array_equal(e1, orc.ends) and np.array_equal(b1, orc.branch)
+
+
 def test_build_export_roundtrip_and_idempotence():
     from superintervals_b200.device import DeviceIndex
     s, e, _, _ = W.config2(200_000, 10, 3, axis=5_000_000)
