@@ -49,6 +49,10 @@ void siSetHostMirror(cSuperIntervals* si, bool enabled);
 /* count_batch (pyx:363-400): counts_out[i] = countOverlaps(si, starts[i], ends[i]). */
 void countOverlapsBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n,
                         size_t* counts_out);
+/* The same with 32-bit counts: a count never exceeds the number of stored intervals (< 2^32), and the
+ * copy back to the host is half as long -- the D2H half is what bounds the end-to-end rate of count. */
+void countOverlapsBatch32(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n,
+                          uint32_t* counts_out);
 /* out[i] = anyOverlaps(si, starts[i], ends[i]) -- same last-candidate-only test. */
 void anyOverlapsBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n,
                       bool* out);
@@ -226,6 +230,18 @@ int siFillDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n
 /* count + clipped-length sum per query (c_superintervals.h:758-792). */
 int siCoverageDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n,
                      uint32_t* d_counts, int32_t* d_cov, void* stream);
+
+/* ---- 3b. mode B routing: one index per contig (the reference's callers' convention, examples/bed-intersect-si.rs:100-123)
+ * A mixed batch (contig id, start, end per query) is grouped by contig ON THE DEVICE: d_perm[i] = original index of the i-th
+ * query in contig-major stable order, d_qs_out / d_qe_out = the queries in that order, offsets_out (HOST, n_contigs + 1
+ * entries) = where each contig's queries begin. Contig k's queries are then one contiguous device range for
+ * siCountDevice on contig k's index; siScatterCountsDevice puts the routed counts back in the caller's order
+ * (d_out[d_perm[i]] = d_counts[i]). `ix` lends its sort scratch (any index on the device; it is not modified).
+ * Ids must lie in [0, n_contigs). Synchronises `stream` once (the offsets). */
+int siRouteByContigDevice(siIndex* ix, const int32_t* d_contig, const int32_t* d_qs, const int32_t* d_qe, size_t n,
+                          int n_contigs, int32_t* d_qs_out, int32_t* d_qe_out, uint32_t* d_perm, size_t* offsets_out,
+                          void* stream);
+int siScatterCountsDevice(siIndex* ix, const uint32_t* d_counts, const uint32_t* d_perm, size_t n, uint32_t* d_out, void* stream);
 
 /* ---- 4. several GPUs of one node (single host process; csrc/multi.cu) --------------------------------
  * The reference has no notion of devices: its callers hold one map per chromosome and loop over the

@@ -107,11 +107,11 @@ C_ABI_SYMBOLS = [
 B200_SYMBOLS = [
     "si_b200_last_error", "si_b200_last_error_string", "si_b200_clear_error", "si_b200_version",
     "si_b200_device_count", "si_b200_kernel_launches", "addIntervals", "siSetHostMirror",
-    "countOverlapsBatch", "anyOverlapsBatch", "searchValuesBatch", "searchIdxsBatch", "searchKeysBatch",
+    "countOverlapsBatch", "countOverlapsBatch32", "anyOverlapsBatch", "searchValuesBatch", "searchIdxsBatch", "searchKeysBatch",
     "searchItemsBatch", "coverageBatch", "intersectionPairs", "siParseBed", "siBedTableFree", "siIndexCreate", "siIndexDestroy", "siIndexOf", "siIndexSize",
     "siIndexDeviceView", "siIndexBuildHost", "siIndexBuildDevice", "siIndexExport", "siCountDevice",
     "siCountDevice64", "siSortQueriesDevice", "siIndexSetOption", "siIndexCellsInfo", "siIndexBitsInfo", "siIndexStreamStats", "siIndexStabInfo", "siIndexReadTimings", "siAnyDevice", "siScanDevice", "siFillDevice", "siCoverageDevice",
-    "siIndexDeviceBytes",
+    "siIndexDeviceBytes", "siRouteByContigDevice", "siScatterCountsDevice",
     "siMultiCreate", "siMultiDestroy", "siMultiDeviceCount", "siMultiIndexOf", "siMultiBuildReplicated", "siMultiCountBatch",
     "siMultiSearchValuesBatch", "siMultiDeviceCounts", "siMultiLastStats",
 ]
@@ -184,6 +184,7 @@ def bind_b200(L):
     L.addIntervals.argtypes = [SI, vp, vp, vp, sz]
     L.siSetHostMirror.argtypes = [SI, C.c_bool]
     L.countOverlapsBatch.argtypes = [SI, vp, vp, sz, vp]
+    L.countOverlapsBatch32.argtypes = [SI, vp, vp, sz, vp]
     L.anyOverlapsBatch.argtypes = [SI, vp, vp, sz, vp]
     L.searchValuesBatch.argtypes = [SI, vp, vp, sz, vp, C.POINTER(cIndexResult)]
     L.searchIdxsBatch.argtypes = [SI, vp, vp, sz, vp, C.POINTER(cIndexResult)]
@@ -238,6 +239,8 @@ def bind_b200(L):
     L.siScanDevice.argtypes = [vp, vp, sz, vp, vp]
     L.siFillDevice.argtypes = [vp, vp, vp, sz, vp, C.c_int, vp, C.c_int, vp]
     L.siCoverageDevice.argtypes = [vp, vp, vp, sz, vp, vp, vp]
+    L.siRouteByContigDevice.argtypes = [vp, vp, vp, vp, sz, C.c_int, vp, vp, vp, vp, vp]
+    L.siScatterCountsDevice.argtypes = [vp, vp, vp, sz, vp, vp]
     return L
 
 

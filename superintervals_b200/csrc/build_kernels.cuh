@@ -52,6 +52,41 @@ bk_take_perm_kernel(const uint32_t* __restrict__ vA, const uint32_t* __restrict_
     for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i < n; i += stride) perm[i] = v[i];
 }
 
+// ---- mode B routing: a mixed query batch grouped by contig id -------------------------------
+// routed columns through the stable order of the contig ids; the routed ids stay for the offsets search
+__global__ void __launch_bounds__(BK_THREADS)
+bk_route_gather_kernel(const uint32_t* __restrict__ perm, const int32_t* __restrict__ c, const int32_t* __restrict__ qs,
+                       const int32_t* __restrict__ qe, uint32_t n, uint32_t contigs, int32_t* __restrict__ gc,
+                       int32_t* __restrict__ gs, int32_t* __restrict__ ge, unsigned long long* __restrict__ bad) {
+    const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i < n; i += stride) {
+        const uint32_t j = perm[i];
+        const int32_t cj = c[j];
+        if ((uint32_t)cj >= contigs) *bad = 1ull;     // id outside [0, contigs): the host reports it
+        gc[i] = cj;
+        gs[i] = qs[j];
+        ge[i] = qe[j];
+    }
+}
+// offsets[k] = first routed query of contig k (k = 0..contigs; offsets[contigs] = n)
+__global__ void bk_key_offsets_kernel(const int32_t* __restrict__ gc, uint32_t n, uint32_t contigs,
+                                      unsigned long long* __restrict__ offsets) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > contigs) return;
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if ((uint32_t)gc[mid] < k) lo = mid + 1; else hi = mid;
+    }
+    offsets[k] = lo;
+}
+// out[perm[i]] = v[i]: the routed counts back in the caller's order
+__global__ void __launch_bounds__(BK_THREADS)
+bk_scatter_u32_kernel(const uint32_t* __restrict__ v, const uint32_t* __restrict__ perm, uint32_t n, uint32_t* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i < n; i += stride) out[perm[i]] = v[i];
+}
+
 // ---- key packing: (start asc, end DESC, insertion idx) ------------------------------
 __global__ void __launch_bounds__(BK_THREADS)
 bk_make_keys_kernel(const int32_t* __restrict__ s, const int32_t* __restrict__ e, uint32_t n,

@@ -22,7 +22,8 @@
 #include <unordered_map>
 #include <vector>
 
-extern "C" int si_b200_upper_bound_(siIndex* ix, int32_t value, size_t* out);
+extern "C" int si_b200_upper_bound_(siIndex* ix, int32_t value, uint32_t* mailbox_word, size_t* out);
+extern "C" int si_b200_single_search_(siIndex* ix, int32_t qs, int32_t qe, int what, uint32_t cap, unsigned long long* found, void* out);
 extern "C" int si_b200_resolve_order_(siIndex* ix, const int32_t* d_qs, size_t n, void* stream);
 
 namespace sib {
@@ -244,6 +245,51 @@ int stage_queries(siIndex* ix, const int32_t* qs, const int32_t* qe, size_t n) {
     return copy_h2d(ix, ix->h_qe.p, qe, n * 4, ix->own_stream);
 }
 
+// ---- single-query mailbox ------------------------------------------------------------------------------
+// The reference's C ABI is one query per call (c.h:537-821) and its drivers loop over it (test/bench.cpp:219-222,
+// 240-242): such a call is pure latency. Its query and its answer therefore live in one block of MAPPED PINNED host
+// memory that the kernels address directly -- no cudaMemcpy in either direction, one launch and one stream
+// synchronise per call. The batch kernels serve it unchanged (n = 1, device pointers = mailbox addresses).
+struct Mailbox {
+    int32_t qs, qe;                       // the query, read by the kernels over PCIe
+    uint32_t ub, any;                     // upperBound / anyOverlaps answers
+    unsigned long long count;             // countOverlaps (64-bit count kernels), search: hits found
+    uint32_t cov_count; int32_t cov;      // coverage
+    alignas(32) unsigned char out[1];     // search results (MAILBOX_OUT_BYTES)
+};
+constexpr size_t MAILBOX_OUT_BYTES = (size_t)192 << 10;   // 16 K Interval records / 48 K values; longer lists take the batch path
+Mailbox* mailbox_of(siIndex* ix) {
+    if (!ix->mailbox) {
+        if (cudaHostAlloc(&ix->mailbox, sizeof(Mailbox) + MAILBOX_OUT_BYTES, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+            set_error(cudaGetLastError(), "cudaHostAlloc(mailbox)", __FILE__, __LINE__);
+            ix->mailbox = nullptr;
+            return nullptr;
+        }
+        memset(ix->mailbox, 0, sizeof(Mailbox));
+    }
+    return reinterpret_cast<Mailbox*>(ix->mailbox);
+}
+
+// one query through the single-search kernel; appended to `found` like the batch call. Returns -1 when the list is
+// longer than the mailbox (the caller then takes the batch path), 0 on success, else an error code.
+template <typename R>
+int search_single(Handle* h, int32_t qs, int32_t qe, R* found, int what, size_t elem) {
+    siIndex* ix = h->ix;
+    std::lock_guard<std::mutex> lk(ix->api_mu);
+    Mailbox* mb = mailbox_of(ix);
+    if (!mb) return last_error_code();
+    const uint32_t cap = (uint32_t)(MAILBOX_OUT_BYTES / elem);
+    int rc = si_b200_single_search_(ix, qs, qe, what, cap, &mb->count, mb->out);
+    if (rc) return rc;
+    const size_t total = (size_t)*reinterpret_cast<volatile unsigned long long*>(&mb->count);
+    if (total > cap) return -1;
+    if (total == 0) return 0;
+    if (!grow(found, found->size + total, elem)) return cudaErrorMemoryAllocation;
+    memcpy(reinterpret_cast<char*>(found->data) + found->size * elem, mb->out, total * elem);
+    found->size += total;
+    return 0;
+}
+
 // count -> scan -> (host learns total) -> grow -> fill -> copy back, appended to `found`
 template <typename R>
 int search_batch(Handle* h, const int32_t* qs, const int32_t* qe, size_t n, size_t* offsets_out, R* found,
@@ -427,10 +473,24 @@ int32_t startAt(const cSuperIntervals* si, size_t index) { return si->starts[ind
 int32_t endAt(const cSuperIntervals* si, size_t index) { return si->ends[index]; }
 int32_t dataAt(const cSuperIntervals* si, size_t index) { return si->data[index]; }
 
+}  // extern "C"
+
 // ---- batch queries over host buffers ---------------------------------------------------------
 // Large batches are pipelined in chunks over three streams so the PCIe copies of chunk
 // k+1 (H2D) and k-1 (D2H) overlap the kernels of chunk k; two buffer slots.
-static int count_batch_pipelined(siIndex* ix, const int32_t* qs, const int32_t* qe, size_t n, size_t* counts_out) {
+template <typename CountT>
+static int count_dev(siIndex* ix, const int32_t* dqs, const int32_t* dqe, size_t n, CountT* dc, int order, cudaStream_t s);
+template <>
+int count_dev<uint64_t>(siIndex* ix, const int32_t* dqs, const int32_t* dqe, size_t n, uint64_t* dc, int order, cudaStream_t s) {
+    return siCountDevice64(ix, dqs, dqe, n, dc, order, s);
+}
+template <>
+int count_dev<uint32_t>(siIndex* ix, const int32_t* dqs, const int32_t* dqe, size_t n, uint32_t* dc, int order, cudaStream_t s) {
+    return siCountDevice(ix, dqs, dqe, n, dc, order, s);
+}
+
+template <typename CountT>
+static int count_batch_pipelined(siIndex* ix, const int32_t* qs, const int32_t* qe, size_t n, CountT* counts_out) {
     constexpr size_t CHUNK = (size_t)8 << 20;   // queries per chunk: 64 MB in, 64 MB out
     if (!ix->pipe_ready) {
         SIB_CHECK(cudaStreamCreateWithFlags(&ix->s_in, cudaStreamNonBlocking));
@@ -442,7 +502,7 @@ static int count_batch_pipelined(siIndex* ix, const int32_t* qs, const int32_t* 
         }
         ix->pipe_ready = true;
     }
-    if (ix->h_qs.ensure(2 * CHUNK * 4) || ix->h_qe.ensure(2 * CHUNK * 4) || ix->h_counts.ensure(2 * CHUNK * 8))
+    if (ix->h_qs.ensure(2 * CHUNK * 4) || ix->h_qe.ensure(2 * CHUNK * 4) || ix->h_counts.ensure(2 * CHUNK * sizeof(CountT)))
         return last_error_code();
     cudaStream_t s_in = ix->s_in, s_k = ix->own_stream, s_out = ix->s_out;
     int order = SI_ORDER_AUTO;
@@ -452,7 +512,7 @@ static int count_batch_pipelined(siIndex* ix, const int32_t* qs, const int32_t* 
         const int slot = (int)(k & 1);
         int32_t* dqs = ix->h_qs.as<int32_t>() + slot * CHUNK;
         int32_t* dqe = ix->h_qe.as<int32_t>() + slot * CHUNK;
-        uint64_t* dc = ix->h_counts.as<uint64_t>() + slot * CHUNK;
+        CountT* dc = ix->h_counts.as<CountT>() + slot * CHUNK;
         if (k >= 2) SIB_CHECK(cudaStreamWaitEvent(s_in, ix->e_k[slot], 0));    // slot's inputs consumed (chunk k-2)
         SIB_CHECK(cudaMemcpyAsync(dqs, qs + at, m * 4, cudaMemcpyHostToDevice, s_in));
         SIB_CHECK(cudaMemcpyAsync(dqe, qe + at, m * 4, cudaMemcpyHostToDevice, s_in));
@@ -465,11 +525,11 @@ static int count_batch_pipelined(siIndex* ix, const int32_t* qs, const int32_t* 
             order = si_b200_resolve_order_(ix, dqs, m, s_k);
             if (order < 0) return last_error_code();
         }
-        int rc = siCountDevice64(ix, dqs, dqe, m, dc, order, s_k);
+        int rc = count_dev<CountT>(ix, dqs, dqe, m, dc, order, s_k);
         if (rc) return rc;
         SIB_CHECK(cudaEventRecord(ix->e_k[slot], s_k));
         SIB_CHECK(cudaStreamWaitEvent(s_out, ix->e_k[slot], 0));
-        SIB_CHECK(cudaMemcpyAsync(counts_out + at, dc, m * 8, cudaMemcpyDeviceToHost, s_out));
+        SIB_CHECK(cudaMemcpyAsync(counts_out + at, dc, m * sizeof(CountT), cudaMemcpyDeviceToHost, s_out));
         SIB_CHECK(cudaEventRecord(ix->e_out[slot], s_out));
     }
     SIB_CHECK(cudaStreamSynchronize(s_out));
@@ -477,26 +537,37 @@ static int count_batch_pipelined(siIndex* ix, const int32_t* qs, const int32_t* 
     return 0;
 }
 
-void countOverlapsBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n,
-                        size_t* counts_out) {
+template <typename CountT>
+static void count_batch_host(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n, CountT* counts_out, const char* who) {
     Handle* h = H(si);
     if (n == 0) return;
-    if (si->size == 0) { memset(counts_out, 0, n * sizeof(size_t)); return; }   // ref:730-732
-    if (!handle_ready(h, "countOverlapsBatch")) { memset(counts_out, 0, n * sizeof(size_t)); return; }
+    if (si->size == 0) { memset(counts_out, 0, n * sizeof(CountT)); return; }   // ref:730-732
+    if (!handle_ready(h, who)) { memset(counts_out, 0, n * sizeof(CountT)); return; }
     siIndex* ix = h->ix;
-    static_assert(sizeof(size_t) == 8, "LP64 only");
     std::lock_guard<std::mutex> lk(ix->api_mu);
     if (n > ((size_t)12 << 20)) {
-        count_batch_pipelined(ix, starts, ends, n, counts_out);
+        count_batch_pipelined<CountT>(ix, starts, ends, n, counts_out);
         return;
     }
-    if (stage_queries(ix, starts, ends, n) || ix->h_counts.ensure(n * 8)) return;
-    if (siCountDevice64(ix, ix->h_qs.as<int32_t>(), ix->h_qe.as<int32_t>(), n, ix->h_counts.as<uint64_t>(),
-                        SI_ORDER_AUTO, ix->own_stream))
+    if (stage_queries(ix, starts, ends, n) || ix->h_counts.ensure(n * sizeof(CountT))) return;
+    if (count_dev<CountT>(ix, ix->h_qs.as<int32_t>(), ix->h_qe.as<int32_t>(), n, ix->h_counts.as<CountT>(), SI_ORDER_AUTO, ix->own_stream))
         return;
-    if (cudaMemcpyAsync(counts_out, ix->h_counts.p, n * 8, cudaMemcpyDeviceToHost, ix->own_stream) != cudaSuccess ||
+    if (cudaMemcpyAsync(counts_out, ix->h_counts.p, n * sizeof(CountT), cudaMemcpyDeviceToHost, ix->own_stream) != cudaSuccess ||
         cudaStreamSynchronize(ix->own_stream) != cudaSuccess)
-        set_error(cudaGetLastError(), "countOverlapsBatch copy-back", __FILE__, __LINE__);
+        set_error(cudaGetLastError(), who, __FILE__, __LINE__);
+}
+
+extern "C" {
+
+void countOverlapsBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n,
+                        size_t* counts_out) {
+    static_assert(sizeof(size_t) == 8, "LP64 only");
+    count_batch_host<uint64_t>(si, starts, ends, n, reinterpret_cast<uint64_t*>(counts_out), "countOverlapsBatch");
+}
+// the same with 32-bit counts (a count never exceeds the number of stored intervals, < 2^32): half the D2H bytes
+void countOverlapsBatch32(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n,
+                          uint32_t* counts_out) {
+    count_batch_host<uint32_t>(si, starts, ends, n, counts_out, "countOverlapsBatch32");
 }
 
 void anyOverlapsBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* ends, size_t n, bool* out) {
@@ -555,54 +626,79 @@ void coverageBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* en
     free(tmp);
 }
 
-// ---- single queries (ref:537-821): the batch path with n = 1, no CPU fallback ---------------
+// ---- single queries (ref:537-821): one launch through the mapped mailbox, no CPU fallback ----------------
 size_t upperBound(cSuperIntervals* si, int32_t value) {
     Handle* h = H(si);
     size_t r = SI_NONE;
     if (si->size != 0 && handle_ready(h, "upperBound")) {
         std::lock_guard<std::mutex> lk(h->ix->api_mu);
-        si_b200_upper_bound_(h->ix, value, &r);
+        if (Mailbox* mb = mailbox_of(h->ix)) si_b200_upper_bound_(h->ix, value, &mb->ub, &r);
     }
     si->idx = r;   // ref:539,562,566
     return r;
 }
 
 bool anyOverlaps(cSuperIntervals* si, int32_t start, int32_t end) {
-    bool r = false;
-    anyOverlapsBatch(si, &start, &end, 1, &r);
-    return r;
+    Handle* h = H(si);
+    if (si->size == 0 || !handle_ready(h, "anyOverlaps")) return false;
+    siIndex* ix = h->ix;
+    std::lock_guard<std::mutex> lk(ix->api_mu);
+    Mailbox* mb = mailbox_of(ix);
+    if (!mb) return false;
+    mb->qs = start; mb->qe = end;
+    if (siAnyDevice(ix, &mb->qs, &mb->qe, 1, reinterpret_cast<uint8_t*>(&mb->any), ix->own_stream)) return false;
+    if (cudaStreamSynchronize(ix->own_stream) != cudaSuccess) { set_error(cudaGetLastError(), "anyOverlaps", __FILE__, __LINE__); return false; }
+    return *reinterpret_cast<volatile uint8_t*>(&mb->any) != 0;
 }
 
 size_t countOverlaps(cSuperIntervals* si, int32_t start, int32_t end) {
-    size_t c = 0;
-    countOverlapsBatch(si, &start, &end, 1, &c);
-    return c;
+    Handle* h = H(si);
+    if (si->size == 0 || !handle_ready(h, "countOverlaps")) return 0;   // ref:730-732
+    siIndex* ix = h->ix;
+    std::lock_guard<std::mutex> lk(ix->api_mu);
+    Mailbox* mb = mailbox_of(ix);
+    if (!mb) return 0;
+    mb->qs = start; mb->qe = end;
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "LP64 only");
+    if (siCountDevice64(ix, &mb->qs, &mb->qe, 1, reinterpret_cast<uint64_t*>(&mb->count), SI_ORDER_ASIS, ix->own_stream)) return 0;
+    if (cudaStreamSynchronize(ix->own_stream) != cudaSuccess) { set_error(cudaGetLastError(), "countOverlaps", __FILE__, __LINE__); return 0; }
+    return (size_t)*reinterpret_cast<volatile unsigned long long*>(&mb->count);
 }
 
-void searchValues(cSuperIntervals* si, int32_t start, int32_t end, cIndexResult* found) {
-    searchValuesBatch(si, &start, &end, 1, nullptr, found);
-}
-void searchIdxs(cSuperIntervals* si, int32_t start, int32_t end, cIndexResult* found) {
-    searchIdxsBatch(si, &start, &end, 1, nullptr, found);
-}
-void searchKeys(cSuperIntervals* si, int32_t start, int32_t end, cKeyResult* found) {
-    searchKeysBatch(si, &start, &end, 1, nullptr, found);
-}
-void searchItems(cSuperIntervals* si, int32_t start, int32_t end, cItemResult* found) {
-    searchItemsBatch(si, &start, &end, 1, nullptr, found);
-}
+#define SIB_SEARCH_SINGLE(NAME, BATCH, RTYPE, WHAT, ELEM)                                           \
+    void NAME(cSuperIntervals* si, int32_t start, int32_t end, RTYPE* found) {                      \
+        Handle* h = H(si);                                                                          \
+        if (si->size == 0 || !handle_ready(h, #NAME)) return;                                       \
+        if (search_single(h, start, end, found, WHAT, ELEM) == -1)                                  \
+            BATCH(si, &start, &end, 1, nullptr, found);   /* longer than the mailbox */             \
+    }
+SIB_SEARCH_SINGLE(searchValues, searchValuesBatch, cIndexResult, SI_FILL_VALUES, sizeof(int32_t))
+SIB_SEARCH_SINGLE(searchIdxs, searchIdxsBatch, cIndexResult, SI_FILL_IDXS, sizeof(int32_t))
+SIB_SEARCH_SINGLE(searchKeys, searchKeysBatch, cKeyResult, SI_FILL_KEYS, sizeof(KeyPair))
+SIB_SEARCH_SINGLE(searchItems, searchItemsBatch, cItemResult, SI_FILL_ITEMS, sizeof(Interval))
+#undef SIB_SEARCH_SINGLE
 void searchPoint(cSuperIntervals* si, int32_t point, cIndexResult* found) {   // ref:725-727
-    searchValuesBatch(si, &point, &point, 1, nullptr, found);
+    searchValues(si, point, point, found);
 }
 void coverage(cSuperIntervals* si, int32_t start, int32_t end, size_t* count_out, int32_t* coverage_out) {
     *count_out = 0;
     *coverage_out = 0;
-    coverageBatch(si, &start, &end, 1, count_out, coverage_out);
+    Handle* h = H(si);
+    if (si->size == 0 || !handle_ready(h, "coverage")) return;
+    siIndex* ix = h->ix;
+    std::lock_guard<std::mutex> lk(ix->api_mu);
+    Mailbox* mb = mailbox_of(ix);
+    if (!mb) return;
+    mb->qs = start; mb->qe = end;
+    if (siCoverageDevice(ix, &mb->qs, &mb->qe, 1, &mb->cov_count, &mb->cov, ix->own_stream)) return;
+    if (cudaStreamSynchronize(ix->own_stream) != cudaSuccess) { set_error(cudaGetLastError(), "coverage", __FILE__, __LINE__); return; }
+    *count_out = (size_t)*reinterpret_cast<volatile uint32_t*>(&mb->cov_count);
+    *coverage_out = *reinterpret_cast<volatile int32_t*>(&mb->cov);
 }
 void findOverlaps(cSuperIntervals* si, int32_t start, int32_t end, int32_t* found, size_t* found_size) {
     // legacy raw-buffer form (ref:794-821): the caller sized `found`
     cIndexResult tmp = {nullptr, 0, 0};
-    searchValuesBatch(si, &start, &end, 1, nullptr, &tmp);
+    searchValues(si, start, end, &tmp);
     if (tmp.size) memcpy(found, tmp.data, tmp.size * sizeof(int32_t));
     *found_size = tmp.size;
     result_free(tmp.data);

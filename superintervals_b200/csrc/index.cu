@@ -796,6 +796,7 @@ void siIndexDestroy(siIndex* ix) {
     if (ix->e_stage[0]) { cudaEventDestroy(ix->e_stage[0]); cudaEventDestroy(ix->e_stage[1]); }
     if (ix->pipe_ready_out) cudaStreamDestroy(ix->s_out2);
     if (ix->pinned) cudaFreeHost(ix->pinned);
+    if (ix->mailbox) cudaFreeHost(ix->mailbox);
     if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
     delete ix;
 }
@@ -1115,6 +1116,52 @@ int si_b200_stable_order_(siIndex* ix, const int32_t* d_key, size_t n, int key_b
     return 0;
 }
 
+// Mode B routing (superintervals_b200.h section 3b): the stable order of the contig ids through the build's radix sort,
+// the query columns gathered through it, and where each contig's queries begin (one small D2H, synchronises `stream`).
+int siRouteByContigDevice(siIndex* ix, const int32_t* d_contig, const int32_t* d_qs, const int32_t* d_qe, size_t n,
+                          int n_contigs, int32_t* d_qs_out, int32_t* d_qe_out, uint32_t* d_perm, size_t* offsets_out,
+                          void* stream) {
+    if (!ix || n > 0xFFFFFFFFull || n_contigs < 1 || n_contigs > (1 << 24)) {
+        set_error_msg(cudaErrorInvalidValue, "siRouteByContigDevice: bad arguments");
+        return cudaErrorInvalidValue;
+    }
+    for (int k = 0; k <= n_contigs; ++k) offsets_out[k] = 0;
+    if (n == 0) return 0;
+    DeviceGuard g(ix->device);
+    cudaStream_t s = pick_stream(ix, stream);
+    int bits = 1;
+    while ((1 << bits) < n_contigs) ++bits;
+    int rc = si_b200_stable_order_(ix, d_contig, n, bits, d_perm, stream);
+    if (rc) return rc;
+    if (ix->b_in_s.ensure(n * 4) || ix->b_in_e.ensure(((size_t)n_contigs + 2) * 8)) return last_error_code();
+    const int cap = ix->sm_count * 16;
+    unsigned long long* d_bad = ix->b_in_e.as<unsigned long long>() + n_contigs + 1;
+    SIB_CHECK(cudaMemsetAsync(d_bad, 0, 8, s));
+    SIB_LAUNCH(bk_route_gather_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, d_perm, d_contig, d_qs, d_qe, (uint32_t)n,
+               (uint32_t)n_contigs, ix->b_in_s.as<int32_t>(), d_qs_out, d_qe_out, d_bad);
+    SIB_LAUNCH(bk_key_offsets_kernel, (n_contigs + 1 + 127) / 128, 128, 0, s, ix->b_in_s.as<int32_t>(), (uint32_t)n, (uint32_t)n_contigs,
+               ix->b_in_e.as<unsigned long long>());
+    static_assert(sizeof(size_t) == 8, "LP64 only");
+    SIB_CHECK(cudaMemcpyAsync(offsets_out, ix->b_in_e.p, ((size_t)n_contigs + 1) * 8, cudaMemcpyDeviceToHost, s));
+    unsigned long long bad = 0;
+    SIB_CHECK(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, s));
+    SIB_CHECK(cudaStreamSynchronize(s));
+    if (bad) {
+        set_error_msg(cudaErrorInvalidValue, "siRouteByContigDevice: contig id out of range");
+        return cudaErrorInvalidValue;
+    }
+    return 0;
+}
+
+int siScatterCountsDevice(siIndex* ix, const uint32_t* d_counts, const uint32_t* d_perm, size_t n, uint32_t* d_out, void* stream) {
+    if (!ix || n > 0xFFFFFFFFull) return cudaErrorInvalidValue;
+    if (n == 0) return 0;
+    DeviceGuard g(ix->device);
+    cudaStream_t s = pick_stream(ix, stream);
+    SIB_LAUNCH(bk_scatter_u32_kernel, grid_for(n, BK_THREADS, ix->sm_count * 16), BK_THREADS, 0, s, d_counts, d_perm, (uint32_t)n, d_out);
+    return 0;
+}
+
 // used by c_abi.cu: resolve SI_ORDER_AUTO once for a count -> fill pair
 int si_b200_resolve_order_(siIndex* ix, const int32_t* d_qs, size_t n, void* stream) {
     DeviceGuard g(ix->device);
@@ -1123,8 +1170,28 @@ int si_b200_resolve_order_(siIndex* ix, const int32_t* d_qs, size_t n, void* str
     return o;
 }
 
+// used by c_abi.cu for the single-query search calls: one launch, the query as kernel parameters, hits written to
+// `out` (device-visible memory: the handle's mapped pinned mailbox), *found = all hits (cap bounds what was written)
+int si_b200_single_search_(siIndex* ix, int32_t qs, int32_t qe, int what, uint32_t cap, unsigned long long* found, void* out) {
+    if (!ix || !ix->built) {
+        set_error_msg(cudaErrorNotReady, "single-query search: index not built");
+        return cudaErrorNotReady;
+    }
+    DeviceGuard g(ix->device);
+    cudaStream_t s = ix->own_stream;
+    const IndexView v = view_of(ix);
+    switch (what) {
+        case SI_FILL_VALUES: SIB_LAUNCH((qk_single_search_kernel<FILL_VALUES>), 1, 32, 0, s, v, qs, qe, cap, found, reinterpret_cast<int32_t*>(out)); break;
+        case SI_FILL_IDXS: SIB_LAUNCH((qk_single_search_kernel<FILL_IDXS>), 1, 32, 0, s, v, qs, qe, cap, found, reinterpret_cast<uint32_t*>(out)); break;
+        case SI_FILL_KEYS: SIB_LAUNCH((qk_single_search_kernel<FILL_KEYS>), 1, 32, 0, s, v, qs, qe, cap, found, reinterpret_cast<int2*>(out)); break;
+        default: SIB_LAUNCH((qk_single_search_kernel<FILL_ITEMS>), 1, 32, 0, s, v, qs, qe, cap, found, reinterpret_cast<Item3*>(out)); break;
+    }
+    SIB_CHECK(cudaStreamSynchronize(s));
+    return 0;
+}
+
 // used by c_abi.cu for the single-query upperBound
-int si_b200_upper_bound_(siIndex* ix, int32_t value, size_t* out) {
+int si_b200_upper_bound_(siIndex* ix, int32_t value, uint32_t* mailbox_word, size_t* out) {
     if (!ix || !ix->built) {
         set_error_msg(cudaErrorNotReady, "upperBound: index not built");
         return cudaErrorNotReady;
@@ -1132,12 +1199,10 @@ int si_b200_upper_bound_(siIndex* ix, int32_t value, size_t* out) {
     *out = SI_NONE;
     if (ix->n == 0) return 0;
     DeviceGuard g(ix->device);
-    if (ensure_small(ix)) return last_error_code();
-    uint32_t* d = ix->small.as<uint32_t>() + 3;
-    SIB_LAUNCH(qk_upper_bound_kernel, 1, 32, 0, ix->own_stream, view_of(ix), value, d);
-    uint32_t r = NONE32;
-    SIB_CHECK(cudaMemcpyAsync(&r, d, 4, cudaMemcpyDeviceToHost, ix->own_stream));
+    // the kernel writes straight into the handle's mapped pinned mailbox: no copy back
+    SIB_LAUNCH(qk_upper_bound_kernel, 1, 32, 0, ix->own_stream, view_of(ix), value, mailbox_word);
     SIB_CHECK(cudaStreamSynchronize(ix->own_stream));
+    const uint32_t r = *reinterpret_cast<volatile uint32_t*>(mailbox_word);
     *out = r == NONE32 ? SI_NONE : (size_t)r;
     return 0;
 }

@@ -132,6 +132,9 @@ struct siIndex {
     void* pinned = nullptr;                     // two pinned staging slots for pageable caller buffers (c_abi.cu)
     size_t pinned_bytes = 0;
     cudaEvent_t e_stage[2] = {nullptr, nullptr};
+    // single-query calls (countOverlaps, searchValues ...): a mapped pinned mailbox the kernels read the query from and
+    // write the answer to, so that a call is one launch + one stream synchronise (c_abi.cu)
+    void* mailbox = nullptr;
     cudaStream_t s_out2 = nullptr;              // second copy-out stream (offsets travel while the fill runs)
     bool pipe_ready_out = false;
 

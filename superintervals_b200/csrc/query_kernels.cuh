@@ -680,9 +680,6 @@ qk_any_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* __
 }
 
 // ---- upperBound for the C ABI cursor (c_superintervals.h:537-568) ------------------------
-__global__ void qk_upper_bound_kernel(IndexView ix, int32_t value, uint32_t* __restrict__ out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) *out = ix.n ? count_le(ix.starts, ix.n, value) - 1u : NONE32;
-}
 
 // ---- coverage: hit count + sum of clipped lengths (hpp:979-1006, c.h:758-792) -----------
 // int32 arithmetic that wraps exactly like the reference's `S` accumulator.
@@ -807,6 +804,58 @@ qk_fill_kernel(IndexView ix, QueryRecords rec, uint32_t nq, const uint64_t* __re
             bi = (hm >> 31) ? low - 1u : ld_nc(ix.branch + low);
         }
     }
+}
+
+// ---- ONE query, one warp: the reference's single-query calls (hpp:551-579, 879-971; c.h:575-727) ----------
+// The C ABI is one query per call, and every reference driver loops over it (test/bench.cpp:219-222,240-242). A
+// call is then latency, not throughput: one launch of this kernel, whose query arrives as kernel parameters and
+// whose result goes straight into a mapped pinned mailbox on the host (no copy in, no copy out, one stream
+// synchronise). The warp finds upper_bound(qe) by a 32-ary search (5 dependent loads for 2^25 intervals instead
+// of 25) and walks the branch array 32 intervals at a time, hits emitted in the reference's descending order.
+// mailbox[0] = hits found (all of them, also those past `cap` that were not written: the host then takes the batch path).
+__device__ __forceinline__ uint32_t warp_count_le(const int32_t* __restrict__ starts, uint32_t n, int32_t v, uint32_t lane) {
+    uint32_t lo = 0, len = n;                       // every index < lo holds a start <= v; none at or past lo + len does
+    while (len) {
+        const uint32_t width = (len + 31u) >> 5;
+        const uint32_t p = lo + (lane + 1u) * width - 1u;
+        const bool le = p < lo + len && ld_nc(starts + p) <= v;
+        const uint32_t c = __popc(__ballot_sync(FULL_MASK, le));
+        const uint32_t nlo = lo + c * width;
+        const uint32_t rest = lo + len - nlo;       // c == 32 leaves nothing or the tail past the last probe
+        len = min(width - 1u, rest);
+        if (c == 32u) len = rest;
+        lo = nlo;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(32)
+qk_upper_bound_kernel(IndexView ix, int32_t value, uint32_t* __restrict__ out) {   // hpp:501-516, one warp
+    const uint32_t c = warp_count_le(ix.starts, ix.n, value, lane_id());
+    if (threadIdx.x == 0) *out = c - 1u;                                           // 0 - 1 wraps to NONE32
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(32)
+qk_single_search_kernel(IndexView ix, int32_t qs, int32_t qe, uint32_t cap, unsigned long long* __restrict__ found,
+                        typename FillOut<MODE>::T* __restrict__ out) {
+    const uint32_t lane = lane_id();
+    uint32_t bi = warp_count_le(ix.starts, ix.n, qe, lane) - 1u;      // 0 - 1 wraps to NONE32
+    uint32_t bo = 0;
+    while (bi != NONE32) {
+        const bool inb = lane <= bi;                                   // lane l looks at interval bi - l
+        const uint32_t j = bi - lane;
+        const int32_t e = inb ? ld_nc(ix.ends + j) : INT_MIN;
+        const bool hit = inb && e >= qs;
+        const uint32_t hm = __ballot_sync(FULL_MASK, hit);
+        const uint32_t pos = bo + __popc(hm & lanemask_lt());
+        if (hit && pos < cap) emit<MODE>(ix, out, pos, j, e);
+        bo += __popc(hm);
+        if (bi < 32u) break;
+        const uint32_t low = bi - 31u;
+        bi = (hm >> 31) ? low - 1u : ld_nc(ix.branch + low);
+    }
+    if (lane == 0) *found = bo;
 }
 
 // ---- stab lists: one branch-array walk per checkpoint, at build time ------------------------

@@ -118,7 +118,7 @@ constexpr uint32_t SK_TILE = SK_THREADS * SK_PER_THREAD;   // 2048 queries: 16 K
 #define SIB_SK_EW 768
 #endif
 #ifndef SIB_SK_MINBLOCKS
-#define SIB_SK_MINBLOCKS 3
+#define SIB_SK_MINBLOCKS 2
 #endif
 constexpr uint32_t SK_SW = SIB_SK_SW;   // staged words of the starts table (x 32 coordinates)
 constexpr uint32_t SK_EW = SIB_SK_EW;   // staged words of the ends table

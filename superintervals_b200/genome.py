@@ -5,14 +5,27 @@ chromosome and route every query to the map of its contig
 (reference examples/bed-intersect-si.rs:100-123; test/bench.cpp:67-102 handles one
 chromosome). ``GenomeIndex`` is that container for one process per GPU: contigs are
 assigned to ranks by longest-processing-time on (N_c + Q_c), a rank builds and queries
-only the contigs it owns, and the only exchange between ranks is the per-contig hit
-totals (one small all_gather over NCCL / gloo) from which every rank derives the base
-offset of each contig's segment in the global, contig-major CSR.
+only the contigs it owns.
 
-PyTorch is plumbing here (device memory, the routing sort, torch.distributed); every
-query kernel is the library's.
+A mixed batch (contig id, start, end per query) is answered in three device steps:
+
+  route     group the batch by contig ON THE DEVICE (siRouteByContigDevice: the build's
+            radix sort over the contig ids, the query columns gathered through it);
+  dispatch  with several ranks each rank holds a slice of the batch: every query travels to
+            the rank that owns its contig -- one all-to-all over NVLink (12 B per query:
+            contig, start, end), the counts travel back by the inverse all-to-all (4 B per
+            query). With one rank nothing moves;
+  count     contig c's queries are one contiguous device range for contig c's index.
+
+The per-contig hit totals are all-gathered into the base offsets of a global contig-major CSR.
+PyTorch is plumbing here (device memory, torch.distributed); routing, counting and the scatter
+back are the library's kernels. The route / count steps are injectable so that the exchange logic
+runs under gloo on CPU in the tests (tests/test_genome.py) -- the defaults are the CUDA library and
+there is no CPU fallback.
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 import torch
@@ -24,9 +37,9 @@ __all__ = ["GenomeIndex", "route_by_contig"]
 
 
 def route_by_contig(contig_ids, n_contigs):
-    """Stable grouping of a mixed query batch by contig id (host side, numpy).
-    Returns (order, bounds): queries order[bounds[c]:bounds[c+1]] belong to contig c, in
-    their original relative order."""
+    """Stable grouping of a mixed query batch by contig id (host side, numpy): the definition the device
+    routing is tested against. Returns (order, bounds): queries order[bounds[c]:bounds[c+1]] belong to
+    contig c, in their original relative order."""
     cid = np.ascontiguousarray(contig_ids)
     if cid.size and (cid.min() < 0 or cid.max() >= n_contigs):
         raise ValueError("contig id out of range")
@@ -36,10 +49,38 @@ def route_by_contig(contig_ids, n_contigs):
     return order, bounds
 
 
+class _CudaRouter:
+    """route / scatter through libsuperintervals_b200.so (siRouteByContigDevice, siScatterCountsDevice)."""
+
+    def __init__(self):
+        from . import _lib
+        from .device import DeviceIndex
+        self._lib = _lib
+        self._L = _lib.lib()
+        self._scratch = DeviceIndex()          # lends its sort scratch; never built
+
+    def route(self, key, qs, qe, n_keys):
+        n = key.numel()
+        gs, ge = torch.empty_like(qs), torch.empty_like(qe)
+        perm = torch.empty(n, dtype=torch.int32, device=key.device)
+        off = (C.c_size_t * (n_keys + 1))()
+        self._L.siRouteByContigDevice(self._scratch._ix, key.data_ptr(), qs.data_ptr(), qe.data_ptr(), n, n_keys,
+                                      gs.data_ptr(), ge.data_ptr(), perm.data_ptr(), off,
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        self._lib.check("siRouteByContigDevice")
+        return gs, ge, perm, np.frombuffer(off, dtype=np.uint64).astype(np.int64)
+
+    def scatter(self, counts, perm, out):
+        self._L.siScatterCountsDevice(self._scratch._ix, counts.data_ptr(), perm.data_ptr(), counts.numel(), out.data_ptr(),
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        self._lib.check("siScatterCountsDevice")
+        return out
+
+
 class GenomeIndex:
     """Per-contig indexes of the contigs this rank owns."""
 
-    def __init__(self, names, n_intervals, n_queries=None, rank=None, world=None):
+    def __init__(self, names, n_intervals, n_queries=None, rank=None, world=None, router=None, group=None):
         self.names = list(names)
         nc = len(self.names)
         if len(n_intervals) != nc:
@@ -49,10 +90,19 @@ class GenomeIndex:
         if world is None:
             world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank, self.world = int(rank), int(world)
+        self.group = group
         nq = n_queries if n_queries is not None else [0] * nc
-        self.owner = assign_contigs(n_intervals, nq, self.world)      # owner rank of every contig
+        self.owner = np.asarray(assign_contigs(n_intervals, nq, self.world), np.int64)   # owner rank of every contig
+        # slots: the contigs in (owner, contig) order -- routing by slot groups a batch by destination rank first
+        self.slot_contig = np.lexsort((np.arange(nc), self.owner)).astype(np.int64)
+        self.slot_of = np.empty(nc, np.int64)
+        self.slot_of[self.slot_contig] = np.arange(nc)
+        self.slot_bounds = np.searchsorted(self.owner[self.slot_contig], np.arange(self.world + 1))  # rank r owns slots [b[r], b[r+1])
         self._ix = {}                                                  # contig -> DeviceIndex (owned contigs only)
         self.hits = np.zeros(nc, np.int64)                             # hit totals of the last count per owned contig
+        self._router = router
+        self._lut = None
+        self.last_exchange = {"dispatch_bytes": 0, "combine_bytes": 0}
 
     def owns(self, c):
         return int(self.owner[c]) == self.rank
@@ -76,25 +126,105 @@ class GenomeIndex:
         """Counts for queries that all lie on contig c (device tensors)."""
         return self._ix[c].count(qs, qe, out=out, order=order)
 
+    # ---- mixed batches --------------------------------------------------------------------------------
+    def _route(self):
+        if self._router is None:
+            self._router = _CudaRouter()
+        return self._router
+
+    def _count_slots(self, gs, ge, off, slots, count_fn):
+        """counts of routed queries: slot k's queries are gs/ge[off[k]:off[k+1]] (k indexes `slots`)."""
+        counts = torch.zeros(gs.numel(), dtype=torch.int32, device=gs.device)
+        for k, slot in enumerate(slots):
+            lo, hi = int(off[k]), int(off[k + 1])
+            c = int(self.slot_contig[slot])
+            if hi == lo:
+                continue
+            if count_fn is not None:
+                count_fn(c, gs[lo:hi], ge[lo:hi], counts[lo:hi])
+            elif c in self._ix:
+                self._ix[c].count(gs[lo:hi], ge[lo:hi], out=counts[lo:hi])
+        return counts
+
+    def count_mixed(self, contig_ids, qs, qe, count_fn=None):
+        """Counts, in the caller's order, for THIS RANK'S slice of a mixed batch (int32 tensors on this rank's device:
+        contig id, start, end per query). Every query is answered by the rank that owns its contig: route by
+        destination, all-to-all dispatch, count, all-to-all combine. Collective: every rank of the group must call it."""
+        n = contig_ids.numel()
+        dev = contig_ids.device
+        nc = len(self.names)
+        R = self._route()
+        if self._lut is None or self._lut.device != dev:
+            self._lut = torch.from_numpy(self.slot_of.astype(np.int32)).to(dev)
+        if n and (int(contig_ids.min()) < 0 or int(contig_ids.max()) >= nc):
+            raise ValueError("contig id out of range")
+        if self.world == 1:                                            # one rank owns every contig: slots == contigs, nothing moves
+            gs, ge, perm, off = R.route(contig_ids, qs, qe, nc)
+            routed = self._count_slots(gs, ge, off, list(range(nc)), count_fn)
+            self._sum_hits(routed, off, list(range(nc)))
+            out = torch.empty(n, dtype=torch.int32, device=dev)
+            return R.scatter(routed, perm, out) if n else out
+        slot = self._lut[contig_ids.long()]
+        # ---- several ranks: dispatch by owner
+        gs, ge, perm, off = R.route(slot, qs, qe, nc)                 # slot-major = destination-major
+        gslot = slot[perm.long()] if n else slot                       # routed slot ids travel with the queries
+        send = np.array([off[self.slot_bounds[r + 1]] - off[self.slot_bounds[r]] for r in range(self.world)], np.int64)
+        t_send = torch.from_numpy(send).to(dev)
+        t_recv = torch.empty_like(t_send)
+        dist.all_to_all_single(t_recv, t_send, group=self.group)
+        recv = t_recv.cpu().numpy()
+        m = int(recv.sum())
+        rbuf = [torch.empty(m, dtype=torch.int32, device=dev) for _ in range(3)]
+        for dst, src in zip(rbuf, (gslot.to(torch.int32), gs, ge)):
+            dist.all_to_all_single(dst, src.contiguous(), output_split_sizes=recv.tolist(), input_split_sizes=send.tolist(),
+                                   group=self.group)
+        self.last_exchange = {"dispatch_bytes": 12 * int(send.sum() - send[self.rank]), "combine_bytes": 4 * int(send.sum() - send[self.rank])}
+        # what arrived is grouped by source rank: group it by my slots
+        my0, my1 = int(self.slot_bounds[self.rank]), int(self.slot_bounds[self.rank + 1])
+        local = rbuf[0] - my0
+        hs, he, hperm, hoff = R.route(local, rbuf[1], rbuf[2], max(1, my1 - my0))
+        hcounts = self._count_slots(hs, he, hoff, list(range(my0, my1)), count_fn)
+        self._sum_hits(hcounts, hoff, list(range(my0, my1)))
+        back = torch.empty(m, dtype=torch.int32, device=dev)
+        if m:
+            R.scatter(hcounts, hperm, back)                            # arrival order = source-major
+        routed = torch.empty(n, dtype=torch.int32, device=dev)
+        dist.all_to_all_single(routed, back, output_split_sizes=send.tolist(), input_split_sizes=recv.tolist(), group=self.group)
+        out = torch.empty(n, dtype=torch.int32, device=dev)
+        return R.scatter(routed, perm, out) if n else out
+
+    def _sum_hits(self, counts, off, slots):
+        self.hits[:] = 0
+        for k, slot in enumerate(slots):
+            lo, hi = int(off[k]), int(off[k + 1])
+            if hi > lo:
+                self.hits[int(self.slot_contig[slot])] = int(counts[lo:hi].to(torch.int64).sum().item())
+
     def count(self, contig_ids, qs, qe):
-        """Counts for a mixed host batch (numpy: contig id, start, end per query). Queries of
-        contigs this rank does not own get 0 here -- their owner answers them; summing the
-        vectors of all ranks (or indexing by owner) gives the full answer."""
-        order, bounds = route_by_contig(contig_ids, len(self.names))
-        qs = np.ascontiguousarray(qs, np.int32)
-        qe = np.ascontiguousarray(qe, np.int32)
-        out = np.zeros(qs.shape[0], np.uint32)
+        """Counts for a mixed HOST batch (numpy: contig id, start, end per query), routed on the device. Queries of
+        contigs this rank does not own get 0 here -- their owner answers them; summing the vectors of all
+        ranks gives the full answer. (No exchange: every rank sees the whole batch. count_mixed() is the
+        sharded form.)"""
+        cid = torch.from_numpy(np.ascontiguousarray(contig_ids, np.int32)).cuda()
+        dqs = torch.from_numpy(np.ascontiguousarray(qs, np.int32)).cuda()
+        dqe = torch.from_numpy(np.ascontiguousarray(qe, np.int32)).cuda()
+        n, nc = cid.numel(), len(self.names)
+        if n and (int(cid.min()) < 0 or int(cid.max()) >= nc):
+            raise ValueError("contig id out of range")
+        R = self._route()
+        gs, ge, perm, off = R.route(cid, dqs, dqe, nc)
+        routed = torch.zeros(n, dtype=torch.int32, device=cid.device)
         self.hits[:] = 0
         for c in self.owned:
-            lo, hi = int(bounds[c]), int(bounds[c + 1])
+            lo, hi = int(off[c]), int(off[c + 1])
             if hi == lo or c not in self._ix:
                 continue
-            sel = order[lo:hi]
-            d = self._ix[c].count(torch.from_numpy(qs[sel]).cuda(), torch.from_numpy(qe[sel]).cuda())
-            cnt = d.cpu().numpy().astype(np.uint32)
-            out[sel] = cnt
-            self.hits[c] = int(cnt.astype(np.int64).sum())
-        return out
+            self._ix[c].count(gs[lo:hi], ge[lo:hi], out=routed[lo:hi])
+            self.hits[c] = int(routed[lo:hi].to(torch.int64).sum().item())
+        out = torch.empty(n, dtype=torch.int32, device=cid.device)
+        if n:
+            R.scatter(routed, perm, out)
+        return out.cpu().numpy().astype(np.uint32)
 
     def csr_bases(self, hits=None, device=None, group=None):
         """All-gather the per-contig hit totals. Returns (bases, totals) int64[n_contigs]:

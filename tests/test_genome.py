@@ -67,6 +67,105 @@ def test_world_size_2_contig_csr_bases_gloo():
         assert dict(out) == {0: True, 1: True}
 
 
+class _HostRouter:
+    """The routing step restated with numpy (route_by_contig) for the gloo test of the exchange logic."""
+
+    def route(self, key, qs, qe, n_keys):
+        import torch
+        from superintervals_b200.genome import route_by_contig
+        order, bounds = route_by_contig(key.numpy().astype(np.int64), n_keys)
+        o = torch.from_numpy(order)
+        return qs[o].contiguous(), qe[o].contiguous(), o.to(torch.int32), bounds
+
+    def scatter(self, counts, perm, out):
+        out[perm.long()] = counts
+        return out
+
+
+def _mixed_case(n_contigs=6, seed=3):
+    rng = np.random.default_rng(seed)
+    data = []
+    for c in range(n_contigs):
+        n = int(rng.integers(50, 400))
+        s = rng.integers(0, 20_000, n).astype(np.int32)
+        e = (s + rng.integers(0, 900, n)).astype(np.int32)
+        data.append((s, e))
+    nq = 5000
+    cid = rng.integers(0, n_contigs, nq).astype(np.int32)
+    qs = rng.integers(0, 20_000, nq).astype(np.int32)
+    qe = (qs + rng.integers(0, 1500, nq)).astype(np.int32)
+    return data, cid, qs, qe
+
+
+def _mixed_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    from oracle.pyoracle import Oracle
+    from superintervals_b200.genome import GenomeIndex
+    from superintervals_b200.workloads import shard_range
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    data, cid, qs, qe = _mixed_case()
+    g = GenomeIndex([f"c{i}" for i in range(len(data))], [d[0].size for d in data], None, router=_HostRouter())
+    oracles = {c: Oracle(*data[c]) for c in g.owned}
+    asked = []
+
+    def count_fn(c, a, b, dst):                      # only the owner may be asked about a contig
+        asked.append(c)
+        dst.copy_(torch.from_numpy(oracles[c].count_batch(a.numpy(), b.numpy()).astype(np.int32)))
+
+    lo, hi = shard_range(cid.size, rank, world)       # this rank's slice of the mixed batch
+    got = g.count_mixed(torch.from_numpy(cid[lo:hi]), torch.from_numpy(qs[lo:hi]), torch.from_numpy(qe[lo:hi]), count_fn=count_fn)
+    want = np.zeros(hi - lo, np.int64)
+    for c in range(len(data)):
+        sel = cid[lo:hi] == c
+        want[sel] = Oracle(*data[c]).count_batch(qs[lo:hi][sel], qe[lo:hi][sel])
+    bases, totals = g.csr_bases()
+    full = np.array([int(Oracle(*data[c]).count_batch(qs[cid == c], qe[cid == c]).sum()) for c in range(len(data))])
+    ok = np.array_equal(got.numpy().astype(np.int64), want) and set(asked) <= set(g.owned) and np.array_equal(totals, full)
+    ok &= g.last_exchange["dispatch_bytes"] > 0
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_world_size_2_mixed_batch_dispatch_and_combine_gloo():
+    """Mode B with a sharded mixed batch: route by destination, all-to-all dispatch, count on the owner, all-to-all
+    combine -- the exchange logic on CPU (gloo) with the routing and counting steps injected (numpy / oracle)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        out = mgr.dict()
+        port = _free_port()
+        procs = [ctx.Process(target=_mixed_worker, args=(r, world, port, out)) for r in range(world)]
+        for p in procs: p.start()
+        for p in procs: p.join(180)
+        assert all(p.exitcode == 0 for p in procs)
+        assert dict(out) == {0: True, 1: True}
+
+
+@pytest.mark.gpu
+def test_device_routing_equals_the_host_definition_and_mixed_counts_match():
+    import torch
+    from oracle.pyoracle import Oracle
+    from superintervals_b200.genome import GenomeIndex, _CudaRouter, route_by_contig
+    data, cid, qs, qe = _mixed_case(24, 11)
+    R = _CudaRouter()
+    gs, ge, perm, off = R.route(torch.from_numpy(cid).cuda(), torch.from_numpy(qs).cuda(), torch.from_numpy(qe).cuda(), 24)
+    order, bounds = route_by_contig(cid, 24)
+    assert np.array_equal(perm.cpu().numpy().astype(np.int64), order) and np.array_equal(off, bounds)
+    assert np.array_equal(gs.cpu().numpy(), qs[order]) and np.array_equal(ge.cpu().numpy(), qe[order])
+    g = GenomeIndex([f"c{i}" for i in range(24)], [d[0].size for d in data], rank=0, world=1)
+    for c in range(24):
+        g.build_contig(c, torch.from_numpy(data[c][0]).cuda(), torch.from_numpy(data[c][1]).cuda())
+    got = g.count_mixed(torch.from_numpy(cid).cuda(), torch.from_numpy(qs).cuda(), torch.from_numpy(qe).cuda())
+    want = np.zeros(cid.size, np.int64)
+    for c in range(24):
+        want[cid == c] = Oracle(*data[c]).count_batch(qs[cid == c], qe[cid == c])
+    assert np.array_equal(got.cpu().numpy().astype(np.int64), want)
+    with pytest.raises(Exception):
+        R.route(torch.from_numpy(np.array([0, 99], np.int32)).cuda(), torch.zeros(2, dtype=torch.int32).cuda(),
+                torch.zeros(2, dtype=torch.int32).cuda(), 24)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [1, 3])
 def test_per_contig_counts_match_per_contig_oracles(world):

@@ -170,3 +170,67 @@ def test_rebuild_after_adding_and_clear():
     m.clear()
     m.build()
     assert m.count(0, 1000) == 0 and not m.has_overlaps(0, 1000)
+
+
+def test_single_query_calls_use_the_mailbox_and_long_lists_fall_back():
+    """The one-query-per-call C functions (c_superintervals.h:537-821) answer through the mapped pinned mailbox (one
+    launch, no copies); a result list longer than the mailbox takes the batch path. Same answers as the oracle either way."""
+    import ctypes as C
+    from superintervals_b200 import _lib
+    from oracle.pyoracle import Oracle
+    L = _lib.lib()
+    rng = np.random.default_rng(9)
+    n = 120_000
+    s = rng.integers(0, 1000, n).astype(np.int32)                 # everything overlaps everything: lists of ~n hits
+    e = (s + rng.integers(5000, 9000, n)).astype(np.int32)
+    orc = Oracle(s, e)
+    si = L.createSuperIntervals()
+    L.addIntervals(si, s.ctypes.data, e.ctypes.data, None, n)
+    L.indexSuperIntervals(si)
+    _lib.check("indexSuperIntervals")
+    for qs, qe in ((2000, 3000), (0, 10), (999, 999), (9500, 9999), (20000, 30000), (500, 400)):
+        a, b = np.array([qs], np.int32), np.array([qe], np.int32)
+        want = int(orc.count_batch(a, b)[0])
+        assert int(L.countOverlaps(si, qs, qe)) == want
+        _, res = orc.search_batch(a, b, want=("values", "keys", "idxs"))
+        r = L.createIndexResult()
+        L.searchValues(si, qs, qe, C.byref(r))
+        got = np.ctypeslib.as_array(r.data, shape=(int(r.size),)).copy() if r.size else np.zeros(0, np.int32)
+        assert np.array_equal(got, res["values"]), (qs, qe)
+        L.searchValues(si, qs, qe, C.byref(r))                    # appends (quirk Q4)
+        assert int(r.size) == 2 * want
+        L.destroyIndexResult(C.byref(r))
+        k = L.createKeyResult()
+        L.searchKeys(si, qs, qe, C.byref(k))
+        assert int(k.size) == want
+        if want:
+            kk = np.ctypeslib.as_array(C.cast(k.data, C.POINTER(C.c_int32)), shape=(want, 2))
+            assert np.array_equal(kk, res["keys"])
+        L.destroyKeyResult(C.byref(k))
+        cnt, cov = C.c_size_t(0), C.c_int32(0)
+        L.coverage(si, qs, qe, C.byref(cnt), C.byref(cov))
+        assert int(cnt.value) == want
+        assert bool(L.anyOverlaps(si, qs, qe)) == bool(orc.has_overlaps_batch(a, b)[0])
+    assert int(L.upperBound(si, 500)) == int(np.searchsorted(orc.starts, 500, "right")) - 1
+    assert int(L.upperBound(si, -5)) == 2**64 - 1
+    _lib.check("single queries")
+    L.destroySuperIntervals(si)
+
+
+def test_count_batch_32_bit_counts_equal_the_size_t_call():
+    from superintervals_b200 import _lib, workloads as W
+    L = _lib.lib()
+    s, e = W.config2_intervals(100_000, 5, axis=3_000_000)
+    qs, qe = W.config2_queries(14_000_000, 5, axis=3_000_000)      # above the 12 M pipeline threshold
+    si = L.createSuperIntervals()
+    L.addIntervals(si, s.ctypes.data, e.ctypes.data, None, s.size)
+    L.indexSuperIntervals(si)
+    for m in (1, 1000, qs.size):
+        c64, c32 = np.zeros(m, np.uint64), np.zeros(m, np.uint32)
+        L.countOverlapsBatch(si, qs.ctypes.data, qe.ctypes.data, m, c64.ctypes.data)
+        L.countOverlapsBatch32(si, qs.ctypes.data, qe.ctypes.data, m, c32.ctypes.data)
+        _lib.check("countOverlapsBatch32")
+        assert np.array_equal(c64, c32.astype(np.uint64))
+    ss, se = np.sort(s), np.sort(e)
+    assert np.array_equal(c32.astype(np.int64), np.searchsorted(ss, qe, "right") - np.searchsorted(se, qs, "left"))
+    L.destroySuperIntervals(si)
