@@ -468,6 +468,18 @@ def bench_bed_ingest(a, rank):
         out["cpu_baseline"] = {"value": got / dc, "unit": "lines/s", "cores": 1, "kind": "port",
                                "sample": f"first {m} lines; getline + istringstream + stoi loop of test/bench.cpp:67-102 (oracle/bed_cpu.cpp)",
                                "matches_device": bool(np.array_equal(cs, t.starts[:m]) and np.array_equal(ce - 1, t.ends[:m]))}
+        # the reference's OWN loader (Bench::load_intervals, test/bench.cpp:67-102, compiled in place: oracle/_ref/libsi_bedref.so)
+        # keeps "chr1" lines and reads from a file: a one-contig sample, file read (page cache) inside its time
+        from oracle import bed_oracle
+        if bed_oracle.reference_available():
+            rows = np.arange(2_000_000)
+            one = ("\n".join(f"chr1\t{int(x)}\t{int(y)}" for x, y in zip(s[rows], e[rows])) + "\n").encode()
+            (rs, re_), _, dr = bed_oracle.reference_load(one, return_seconds=True)
+            d1 = parse_bed(one, True, 0)
+            out["cpu_baseline"]["reference_loader"] = {
+                "value": rs.size / dr, "unit": "lines/s", "cores": 1, "kind": "reference",
+                "sample": f"{rs.size} one-contig lines through Bench::load_intervals (reads a temporary file from the page cache)",
+                "equals_device": bool(np.array_equal(rs, d1.starts) and np.array_equal(re_, d1.ends))}
     return out
 
 

@@ -9,11 +9,11 @@
  * (ref:363-1089); a caller switches implementation by including this header
  * instead and linking -lsuperintervals_b200. Nothing here mentions CUDA.
  *
- * Scope: build + overlap queries. The reference's set
- * algebra (ref:264-332: mergeOverlaps, intervalGaps, unionWith, intersection,
- * difference, symmetricDifference, intervalSpan, expandIntervals,
- * flankIntervals, uniqueIntervals) is host-side sequential code outside the
- * accelerated path and is NOT provided by this library.
+ * Scope: build + overlap queries, and the callers either
+ * side of them: the reference's set algebra (ref:264-332: mergeOverlaps,
+ * intervalGaps, unionWith, intersection, difference, symmetricDifference,
+ * intervalSpan, expandIntervals, flankIntervals, uniqueIntervals) is declared
+ * below and runs on the device as well.
  *
  * Semantics kept from the reference:
  *   - intervals and queries are END-INCLUSIVE;

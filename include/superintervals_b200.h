@@ -162,18 +162,21 @@ int siSortQueriesDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, s
  * start <= end; queries with qs > qe inside such a batch still take the walk);
  * SI_COUNT_CELLS is the same closed form answered from build()'s rank cells (one
  * 32-byte record per 2^k coordinates: one sector read per rank, no locality needed, so a
- * shuffled batch whose cells fit in L2 is answered without partitioning it);
+ * shuffled batch is answered without partitioning it, from L2 while the cells fit there, else from HBM);
  * SI_COUNT_AUTO picks CELLS, else RANK, whenever the index allows it. Results are identical. */
 enum { SI_OPT_COUNT_ALGO = 0, SI_OPT_BUCKET_INTERVALS = 1, SI_OPT_WINDOW_SHIFT = 2, SI_OPT_TIMING = 3,
        SI_OPT_GRID_INTERVALS = 4, /* intervals per cell of the rank grid; applies to the next build */
-       SI_OPT_CELLS_DIRECT_BYTES = 5, /* rank cells up to this many bytes answer batches unpartitioned (0 = 60 % of L2) */
+       SI_OPT_CELLS_DIRECT_BYTES = 5, /* rank cells up to this many bytes answer batches unpartitioned (0 = always, the default: the gather from
+                                         HBM beats partitioning first at every size measured; 1 = never) */
        SI_OPT_CELLS_FILL = 6, /* mean values per rank cell (1..28); applies to the next build */
        SI_OPT_STAB_LISTS = 7, /* 1 (default): the CSR fill of a well-formed index reads its stab lists; 0: it walks the branch array */
        SI_OPT_STAB_BUDGET = 8, /* stab-list entries per interval at most (default 6); deeper indexes double the checkpoint spacing, then walk */
        SI_OPT_STREAM = 9, /* 1 (default): position-sorted batches are counted by the streaming kernel (TMA-staged rank bits) when the
                              index carries them; 0: never; 2: every batch, whatever its order (a tile whose window does not fit reads the cells) */
-       SI_OPT_L2_PERSIST = 11, /* 1 (default): the rank-cells count is launched with an L2 access-policy window that keeps the cells
-                                   resident (persisting) and lets the query / count streams pass (streaming); 0: plain launch */
+       SI_OPT_L2_PERSIST = 11, /* 1: the rank-cells count is launched with an L2 access-policy window that keeps the cells resident
+                                   (persisting) and lets the query / count streams pass (streaming); raises the device-wide persisting
+                                   set-aside to its maximum. 0 (default): plain launch -- measured on C2: the window gains the count 1 %
+                                   and the set-aside costs every other kernel of the process 15-45 % (stream count, scan, fill) */
        SI_OPT_STREAM_BUDGET = 10 /* rank bits are built when they cost at most this many bytes per interval (default 64; 0 = never); next build */ };
 enum { SI_COUNT_AUTO = 0, SI_COUNT_WALK = 1, SI_COUNT_RANK = 2, SI_COUNT_CELLS = 3 };
 int siIndexSetOption(siIndex* ix, int option, long long value);
@@ -242,6 +245,13 @@ int siRouteByContigDevice(siIndex* ix, const int32_t* d_contig, const int32_t* d
                           int n_contigs, int32_t* d_qs_out, int32_t* d_qe_out, uint32_t* d_perm, size_t* offsets_out,
                           void* stream);
 int siScatterCountsDevice(siIndex* ix, const uint32_t* d_counts, const uint32_t* d_perm, size_t n, uint32_t* d_out, void* stream);
+/* The same batch WITHOUT routing: ixs[k] = the index of contig k (NULL or empty: its queries count 0; all on one device),
+ * d_counts[i] = count of query i on the index of contig d_contig[i] (ids outside [0, n_contigs) count 0), in the caller's
+ * order, one launch. Needs every index to answer from rank cells (any well-formed index, and one with a few start > end
+ * intervals); otherwise returns SI_MIXED_UNSUPPORTED without latching an error and the caller routes instead. */
+#define SI_MIXED_UNSUPPORTED (-2)
+int siCountMixedDevice(siIndex* const* ixs, int n_contigs, const int32_t* d_contig, const int32_t* d_qs, const int32_t* d_qe,
+                       size_t n, uint32_t* d_counts, void* stream);
 
 /* ---- 4. several GPUs of one node (single host process; csrc/multi.cu) --------------------------------
  * The reference has no notion of devices: its callers hold one map per chromosome and loop over the

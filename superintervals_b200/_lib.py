@@ -111,7 +111,7 @@ B200_SYMBOLS = [
     "searchItemsBatch", "coverageBatch", "intersectionPairs", "siParseBed", "siBedTableFree", "siIndexCreate", "siIndexDestroy", "siIndexOf", "siIndexSize",
     "siIndexDeviceView", "siIndexBuildHost", "siIndexBuildDevice", "siIndexExport", "siCountDevice",
     "siCountDevice64", "siSortQueriesDevice", "siIndexSetOption", "siIndexCellsInfo", "siIndexBitsInfo", "siIndexStreamStats", "siIndexStabInfo", "siIndexReadTimings", "siAnyDevice", "siScanDevice", "siFillDevice", "siCoverageDevice",
-    "siIndexDeviceBytes", "siRouteByContigDevice", "siScatterCountsDevice",
+    "siIndexDeviceBytes", "siRouteByContigDevice", "siScatterCountsDevice", "siCountMixedDevice",
     "siMultiCreate", "siMultiDestroy", "siMultiDeviceCount", "siMultiIndexOf", "siMultiBuildReplicated", "siMultiCountBatch",
     "siMultiSearchValuesBatch", "siMultiDeviceCounts", "siMultiLastStats",
 ]
@@ -241,6 +241,7 @@ def bind_b200(L):
     L.siCoverageDevice.argtypes = [vp, vp, vp, sz, vp, vp, vp]
     L.siRouteByContigDevice.argtypes = [vp, vp, vp, vp, sz, C.c_int, vp, vp, vp, vp, vp]
     L.siScatterCountsDevice.argtypes = [vp, vp, vp, sz, vp, vp]
+    L.siCountMixedDevice.argtypes = [vp, C.c_int, vp, vp, vp, sz, vp, vp]
     return L
 
 

@@ -6,10 +6,13 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#if defined(__x86_64__)
 #include <immintrin.h>
+#endif
 
 namespace sib {
 
+#if defined(__x86_64__)
 __attribute__((target("avx2"))) static void copy_stream_avx2(char* d, const char* s, size_t n) {
     size_t head = (32 - (reinterpret_cast<uintptr_t>(d) & 31)) & 31;
     if (head > n) head = n;
@@ -30,12 +33,15 @@ __attribute__((target("avx2"))) static void copy_stream_avx2(char* d, const char
     _mm_sfence();
     memcpy(d, s, n - blocks * 128);
 }
+#endif
 
 // dst is write-once output: stream it past the caches when that is possible and worth it
 void copy_to_output(void* dst, const void* src, size_t n) {
+#if defined(__x86_64__)
     static const bool avx2 = __builtin_cpu_supports("avx2");
-    if (avx2 && n >= 4096) copy_stream_avx2(static_cast<char*>(dst), static_cast<const char*>(src), n);
-    else memcpy(dst, src, n);
+    if (avx2 && n >= 4096) { copy_stream_avx2(static_cast<char*>(dst), static_cast<const char*>(src), n); return; }
+#endif
+    memcpy(dst, src, n);   // aarch64 hosts (Grace + B200): the libc copy
 }
 
 }  // namespace sib

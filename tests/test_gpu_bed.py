@@ -89,3 +89,22 @@ def test_bed_to_queries_end_to_end(tmp_path):
     for c in contigs:
         m = IntervalMap.from_arrays(*ref[c])
         assert np.array_equal(m.count_batch_np(*qry[c]), Oracle(*ref[c]).count_batch(*qry[c]))
+
+
+def test_device_parser_equals_the_reference_loaders_own_output():
+    """The device tokeniser against what Bench::load_intervals (reference test/bench.cpp:67-102, compiled in place by
+    oracle/Makefile) read from the same text: the committed golden pair, and -- where the compiled loader travelled --
+    a fresh text."""
+    import os
+    from superintervals_b200.bed import parse_bed
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = np.load(os.path.join(root, "tests", "golden", "bed_ref.npz"))
+    cases = [(g["intervals_text"].tobytes(), g["a_starts"], g["a_ends"]), (g["queries_text"].tobytes(), g["q_starts"], g["q_ends"])]
+    if bed_oracle.reference_available():
+        text = _bed(np.random.default_rng(5), 50_000, ["chr1", "chr2", "chr1_KI270706v1_random"])
+        (s, e), _ = bed_oracle.reference_load(text)
+        cases.append((text, s, e))
+    for text, s, e in cases:
+        t = parse_bed(text, normalize=True)
+        keep = t.contig == t.names.index("chr1")
+        assert t.skipped == 0 and np.array_equal(t.starts[keep], s) and np.array_equal(t.ends[keep], e)
