@@ -177,9 +177,16 @@ enum { SI_OPT_COUNT_ALGO = 0, SI_OPT_BUCKET_INTERVALS = 1, SI_OPT_WINDOW_SHIFT =
                                    (persisting) and lets the query / count streams pass (streaming); raises the device-wide persisting
                                    set-aside to its maximum. 0 (default): plain launch -- measured on C2: the window gains the count 1 %
                                    and the set-aside costs every other kernel of the process 15-45 % (stream count, scan, fill) */
+       SI_OPT_NARROW_SORT = 12, /* 1 (default): build() sorts an unsorted input by start only (32-bit keys: half the passes, two thirds of
+                                    the bytes per pass) and puts equal starts in end-descending order in place; a run of more than 16
+                                    equal starts falls back to the composite (start, end desc) 64-bit key. 0: always the composite key.
+                                    The built arrays are identical either way. */
        SI_OPT_STREAM_BUDGET = 10 /* rank bits are built when they cost at most this many bytes per interval (default 64; 0 = never); next build */ };
 enum { SI_COUNT_AUTO = 0, SI_COUNT_WALK = 1, SI_COUNT_RANK = 2, SI_COUNT_CELLS = 3 };
 int siIndexSetOption(siIndex* ix, int option, long long value);
+/* What the last build did with its input: 0 = already in (start asc, end desc) order, no sort (hpp:1416,1421);
+ * 1 = narrow sort + tie fix; 2 = composite 64-bit key; -1 = not built. */
+int siIndexLastSort(const siIndex* ix);
 /* The rank cells build() made (which = 0: over starts, 1: over ends). format 0 = none
  * (malformed index or >= 2^31 intervals), 1 = 28 one-byte offsets, 2 = 14 two-byte offsets per
  * 32-byte cell of 2^shift coordinates; overfull = cells answered from the sorted array instead;
@@ -247,11 +254,12 @@ int siRouteByContigDevice(siIndex* ix, const int32_t* d_contig, const int32_t* d
 int siScatterCountsDevice(siIndex* ix, const uint32_t* d_counts, const uint32_t* d_perm, size_t n, uint32_t* d_out, void* stream);
 /* The same batch WITHOUT routing: ixs[k] = the index of contig k (NULL or empty: its queries count 0; all on one device),
  * d_counts[i] = count of query i on the index of contig d_contig[i] (ids outside [0, n_contigs) count 0), in the caller's
- * order, one launch. Needs every index to answer from rank cells (any well-formed index, and one with a few start > end
+ * order, one launch; d_totals (device, n_contigs entries, may be NULL) receives the hit total of every contig -- what the
+ * CSR bases of a contig-major result are made of. Needs every index to answer from rank cells (any well-formed index, and one with a few start > end
  * intervals); otherwise returns SI_MIXED_UNSUPPORTED without latching an error and the caller routes instead. */
 #define SI_MIXED_UNSUPPORTED (-2)
 int siCountMixedDevice(siIndex* const* ixs, int n_contigs, const int32_t* d_contig, const int32_t* d_qs, const int32_t* d_qe,
-                       size_t n, uint32_t* d_counts, void* stream);
+                       size_t n, uint32_t* d_counts, unsigned long long* d_totals, void* stream);
 
 /* ---- 4. several GPUs of one node (single host process; csrc/multi.cu) --------------------------------
  * The reference has no notion of devices: its callers hold one map per chromosome and loop over the

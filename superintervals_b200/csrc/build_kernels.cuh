@@ -121,6 +121,63 @@ bk_gather_kernel(const uint64_t* __restrict__ kA, const uint64_t* __restrict__ k
     }
 }
 
+// ---- narrow sort: by START only (32-bit keys, half the passes of the composite key and 16 instead of 24 bytes per
+// record and pass), then the ties among equal starts put in end-DESCENDING order in place. Equal starts are rare on
+// genomic data and their runs short; a run longer than BK_TIE_MAX raises *overflow and the host redoes the build with
+// the 64-bit composite key. The order is the composite sort's exactly: the radix sort is stable (equal starts arrive in
+// insertion order) and the in-run insertion sort moves an element only past strictly smaller ends.
+constexpr uint32_t BK_TIE_MAX = 16;
+
+__global__ void __launch_bounds__(BK_THREADS)
+bk_make_start_keys_kernel(const int32_t* __restrict__ s, uint32_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+    const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i < n; i += stride) {
+        keys[i] = flip_i32(s[i]);
+        idx[i] = (uint32_t)i;
+    }
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+bk_gather_narrow_kernel(const uint32_t* __restrict__ kA, const uint32_t* __restrict__ kB, const uint32_t* __restrict__ vA,
+                        const uint32_t* __restrict__ vB, const uint32_t* __restrict__ sel, const int32_t* __restrict__ ends_in,
+                        const int32_t* __restrict__ values_in, uint32_t n, int32_t* __restrict__ starts, int32_t* __restrict__ ends,
+                        int32_t* __restrict__ values, uint32_t* __restrict__ perm) {
+    const bool useB = *sel != 0;
+    const uint32_t* __restrict__ keys = useB ? kB : kA;
+    const uint32_t* __restrict__ idx = useB ? vB : vA;
+    const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i < n; i += stride) {
+        const uint32_t j = idx[i];
+        starts[i] = unflip_i32(keys[i]);
+        ends[i] = ends_in[j];
+        values[i] = values_in ? values_in[j] : (int32_t)j;
+        perm[i] = j;
+    }
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+bk_fix_ties_kernel(const int32_t* __restrict__ starts, int32_t* __restrict__ ends, int32_t* __restrict__ values,
+                   uint32_t* __restrict__ perm, uint32_t n, uint32_t* __restrict__ overflow) {
+    const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i + 1 < n; i += stride) {
+        const int32_t s = starts[i];
+        if (starts[i + 1] != s || (i > 0 && starts[i - 1] == s)) continue;    // not the head of a run of >= 2
+        uint64_t r = i + 2;
+        while (r < n && r - i <= BK_TIE_MAX && starts[r] == s) ++r;
+        if (r - i > BK_TIE_MAX) { *overflow = 1u; continue; }
+        for (uint64_t a = i + 1; a < r; ++a) {                                  // stable insertion sort, end descending
+            const int32_t e = ends[a], v = values[a];
+            const uint32_t p = perm[a];
+            uint64_t b = a;
+            while (b > i && ends[b - 1] < e) {
+                ends[b] = ends[b - 1]; values[b] = values[b - 1]; perm[b] = perm[b - 1];
+                --b;
+            }
+            ends[b] = e; values[b] = v; perm[b] = p;
+        }
+    }
+}
+
 // already (start asc, end desc): the reference performs no sort (hpp:1416,1421)
 __global__ void __launch_bounds__(BK_THREADS)
 bk_identity_kernel(const int32_t* __restrict__ s, const int32_t* __restrict__ e,

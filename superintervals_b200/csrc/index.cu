@@ -10,6 +10,7 @@
 #include "radix_sort.cuh"
 #include "stream_kernels.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -381,10 +382,41 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
     ix->wellformed = (flags & 4u) != 0;
     if ((flags & 3u) == 3u) {
         // already (start asc, end desc): the reference does not sort (hpp:1416,1421)
+        ix->last_sort = 0;
         SIB_LAUNCH(bk_identity_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, d_s, d_e, d_v, ix->n,
                    ix->starts.as<int32_t>(), ix->ends.as<int32_t>(), ix->values.as<int32_t>(),
                    ix->perm.as<uint32_t>());
     } else {
+        // Narrow sort first (SI_OPT_NARROW_SORT, default on): 32-bit keys = the starts, four passes of 16 B per record instead of
+        // eight of 24 B, then equal starts put in end-descending order in place (bk_fix_ties_kernel). A run of more
+        // than BK_TIE_MAX equal starts sends the build to the composite 64-bit key below.
+        bool sorted_narrow = false;
+        if (ix->narrow_sort) {
+            if (ix->b_kA.ensure(n * 4) || ix->b_kB.ensure(n * 4) || ix->b_vA.ensure(n * 4) || ix->b_vB.ensure(n * 4) ||
+                ix->b_ws.ensure(rs_workspace_bytes<uint32_t>(ix->n)))
+                return last_error_code();
+            uint32_t* d_tie = ix->small.as<uint32_t>() + 3;
+            SIB_CHECK(cudaMemsetAsync(d_tie, 0, 4, s));
+            SIB_LAUNCH(bk_make_start_keys_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, d_s, ix->n,
+                       ix->b_kA.as<uint32_t>(), ix->b_vA.as<uint32_t>());
+            int rc = radix_sort_pairs<uint32_t>(ix->b_kA.as<uint32_t>(), ix->b_kB.as<uint32_t>(), ix->b_vA.as<uint32_t>(),
+                                                ix->b_vB.as<uint32_t>(), ix->n, 32, ix->b_ws.p, ix->sm_count, s);
+            if (rc) return rc;
+            RsWorkspace ws = rs_carve(ix->b_ws.p);
+            SIB_LAUNCH(bk_gather_narrow_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, ix->b_kA.as<uint32_t>(),
+                       ix->b_kB.as<uint32_t>(), ix->b_vA.as<uint32_t>(), ix->b_vB.as<uint32_t>(), ws.final_sel, d_e, d_v, ix->n,
+                       ix->starts.as<int32_t>(), ix->ends.as<int32_t>(), ix->values.as<int32_t>(), ix->perm.as<uint32_t>());
+            SIB_LAUNCH(bk_fix_ties_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, ix->starts.as<int32_t>(),
+                       ix->ends.as<int32_t>(), ix->values.as<int32_t>(), ix->perm.as<uint32_t>(), ix->n, d_tie);
+            uint32_t tie = 0;
+            SIB_CHECK(cudaMemcpyAsync(&tie, d_tie, 4, cudaMemcpyDeviceToHost, s));
+            SIB_CHECK(cudaStreamSynchronize(s));
+            sorted_narrow = tie == 0;
+            ix->last_sort = sorted_narrow ? 1 : 2;
+        } else {
+            ix->last_sort = 2;
+        }
+        if (!sorted_narrow) {
         if (ix->b_kA.ensure(n * 8) || ix->b_kB.ensure(n * 8) || ix->b_vA.ensure(n * 4) ||
             ix->b_vB.ensure(n * 4) || ix->b_ws.ensure(rs_workspace_bytes<uint64_t>(ix->n)))
             return last_error_code();
@@ -399,6 +431,7 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
                    ix->b_kB.as<uint64_t>(), ix->b_vA.as<uint32_t>(), ix->b_vB.as<uint32_t>(), ws.final_sel, d_v,
                    ix->n, ix->starts.as<int32_t>(), ix->ends.as<int32_t>(), ix->values.as<int32_t>(),
                    ix->perm.as<uint32_t>());
+        }
     }
     if (ix->n_padded > ix->n) {
         SIB_LAUNCH(bk_pad_kernel, 1, 128, 0, s, ix->starts.as<int32_t>(), ix->ends.as<int32_t>(), ix->values.as<int32_t>(),
@@ -917,6 +950,8 @@ int siIndexStreamStats(siIndex* ix, unsigned long long* tiles, unsigned long lon
     return 0;
 }
 
+int siIndexLastSort(const siIndex* ix) { return ix && ix->built ? ix->last_sort : -1; }
+
 int siIndexStabInfo(const siIndex* ix, siStabInfo* out) {
     if (!ix || !out || !ix->built) return cudaErrorInvalidValue;
     out->state = ix->stab_state;
@@ -1066,6 +1101,10 @@ int siIndexSetOption(siIndex* ix, int option, long long value) {
         case SI_OPT_STREAM_BUDGET:         // bytes of rank bits per interval at most; applies to the next build
             if (value < 0 || value > 4096) break;
             ix->bits_budget = (uint32_t)value;
+            return 0;
+        case SI_OPT_NARROW_SORT:           // 1 (default): build() sorts by start and fixes ties; 0: always the composite 64-bit key
+            if (value < 0 || value > 1) break;
+            ix->narrow_sort = value != 0;
             return 0;
         case SI_OPT_L2_PERSIST:            // 1: the cells kernel is launched with an L2 access-policy window over the rank cells
             if (value < 0 || value > 1) break;
@@ -1248,7 +1287,7 @@ int siScatterCountsDevice(siIndex* ix, const uint32_t* d_counts, const uint32_t*
 // qk_count_mixed_kernel. Returns SI_MIXED_UNSUPPORTED (no error latched) when one of the indexes cannot answer from
 // rank cells (malformed beyond the side list, >= 2^31 intervals): the caller then routes by contig instead.
 int siCountMixedDevice(siIndex* const* ixs, int n_contigs, const int32_t* d_contig, const int32_t* d_qs, const int32_t* d_qe,
-                       size_t n, uint32_t* d_counts, void* stream) {
+                       size_t n, uint32_t* d_counts, unsigned long long* d_totals, void* stream) {
     if (!ixs || n_contigs < 1 || n_contigs > (1 << 20) || n > 0xFFFFFFFFull) {
         set_error_msg(cudaErrorInvalidValue, "siCountMixedDevice: bad arguments");
         return cudaErrorInvalidValue;
@@ -1264,6 +1303,7 @@ int siCountMixedDevice(siIndex* const* ixs, int n_contigs, const int32_t* d_cont
             return cudaErrorInvalidValue;
         }
     }
+    if (d_totals) SIB_CHECK(cudaMemsetAsync(d_totals, 0, (size_t)n_contigs * 8, static_cast<cudaStream_t>(stream)));
     if (n == 0) return 0;
     if (!host) {   // no contig has an index: every count is 0
         SIB_CHECK(cudaMemsetAsync(d_counts, 0, n * 4, static_cast<cudaStream_t>(stream)));
@@ -1286,11 +1326,17 @@ int siCountMixedDevice(siIndex* const* ixs, int n_contigs, const int32_t* d_cont
     if (host->mixed_tab.ensure(bytes)) return last_error_code();
     // pageable source: the runtime stages it before returning, so the vector may go out of scope
     SIB_CHECK(cudaMemcpyAsync(host->mixed_tab.p, tab.data(), bytes, cudaMemcpyHostToDevice, s));
-    const size_t smem = n_contigs <= QM_SMEM_ENTRIES ? bytes : 0;
-    const int grid = (int)(((uint64_t)n + QC_THREADS - 1) / QC_THREADS);
+    const size_t smem = n_contigs <= QM_SMEM_ENTRIES ? ((bytes + 15) & ~(size_t)15) + (size_t)n_contigs * 8 : 0;
+    auto kern = qk_count_mixed_kernel<uint32_t>;
+    if (smem > ((size_t)48 << 10)) SIB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SIB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, QC_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    const uint64_t tiles = ((uint64_t)n + QC_THREADS - 1) / QC_THREADS;
+    const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)host->sm_count * per_sm);
     const MixedEntry* d_tab = reinterpret_cast<const MixedEntry*>(host->mixed_tab.p);
-    SIB_LAUNCH_T(host, TAG_COUNT_CELLS, (qk_count_mixed_kernel<uint32_t>), grid, QC_THREADS, smem, s, d_tab,
-                 (uint32_t)n_contigs, d_contig, d_qs, d_qe, (uint32_t)n, d_counts);
+    SIB_LAUNCH_T(host, TAG_COUNT_CELLS, kern, grid, QC_THREADS, smem, s, d_tab, (uint32_t)n_contigs, d_contig, d_qs, d_qe,
+                 (uint32_t)n, d_counts, d_totals);
     return 0;
 }
 

@@ -72,6 +72,8 @@ struct siIndex {
     sib::DevBuf cells_s, cells_e;                  // cells_s owns both tables (one L2 policy window); cells_e stays empty
     uint4* cells_e_ptr = nullptr;                  // inside cells_s
     size_t cells_total_bytes = 0;
+    bool narrow_sort = true;                       // SI_OPT_NARROW_SORT: build() sorts by start (32-bit keys) and fixes ties, before falling back to the 64-bit key
+    int last_sort = 0;                             // what the last build did: 0 input already sorted, 1 narrow sort, 2 composite 64-bit key
     bool l2_persist = false;                       // SI_OPT_L2_PERSIST / SIB_L2_PERSIST (off: the set-aside costs every other kernel more than it gives, r02g)
     size_t l2_persist_max = 0;                     // cudaLimitPersistingL2CacheSize in force
     CellsMeta cm_s, cm_e;

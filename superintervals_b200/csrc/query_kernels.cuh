@@ -694,45 +694,63 @@ __device__ __noinline__ uint32_t walk_scalar(const int32_t* __restrict__ ends, c
     return c;
 }
 
+// Persistent CTAs (grid = what the device holds): the table is staged once per CTA, tiles are taken grid-stride, and the
+// per-contig hit totals (for the CSR bases of mode B) are summed in shared memory and flushed once per CTA.
 template <typename CountT>
 __global__ void __launch_bounds__(QC_THREADS, SIB_QC_MINBLOCKS)
 qk_count_mixed_kernel(const MixedEntry* __restrict__ table, uint32_t n_contigs, const int32_t* __restrict__ contig,
-                      const int32_t* __restrict__ qs_in, const int32_t* __restrict__ qe_in, uint32_t nq, CountT* __restrict__ counts) {
+                      const int32_t* __restrict__ qs_in, const int32_t* __restrict__ qe_in, uint32_t nq, CountT* __restrict__ counts,
+                      unsigned long long* __restrict__ totals) {
     extern __shared__ __align__(16) unsigned char qm_smem[];
     const MixedEntry* tab = table;
+    unsigned long long* s_tot = nullptr;
     if (n_contigs <= (uint32_t)QM_SMEM_ENTRIES) {
         const uint32_t words = n_contigs * (uint32_t)(sizeof(MixedEntry) / 4);
         uint32_t* dst = reinterpret_cast<uint32_t*>(qm_smem);
         const uint32_t* src = reinterpret_cast<const uint32_t*>(table);
         for (uint32_t k = threadIdx.x; k < words; k += QC_THREADS) dst[k] = __ldg(src + k);
-        __syncthreads();
         tab = reinterpret_cast<const MixedEntry*>(qm_smem);
-    }
-    const uint64_t t = (uint64_t)blockIdx.x * QC_THREADS + threadIdx.x;
-    if (t >= nq) return;
-    const uint32_t cid = (uint32_t)ld_stream(contig + t);
-    const int32_t qs = ld_stream(qs_in + t), qe = ld_stream(qe_in + t);
-    uint32_t c = 0;
-    if (cid < n_contigs && tab[cid].n != 0u) {
-        const MixedEntry& e = tab[cid];
-        const RankCells cs = e.cs, ce = e.ce;
-        uint32_t cell_s, off_s, cell_e, off_e;
-        cell_of(cs, (int64_t)qe + 1, cell_s, off_s);
-        cell_of(ce, (int64_t)qs, cell_e, off_e);
-        const CellRec rs = ld_cell(cs.rec + 2 * (size_t)cell_s);
-        const CellRec re = ld_cell(ce.rec + 2 * (size_t)cell_e);
-        const uint32_t ns = cell_rank(cs, e.rstarts, rs, cell_s, off_s, (int64_t)qe + 1);
-        const uint32_t ne = cell_rank(ce, e.eall, re, cell_e, off_e, (int64_t)qs);
-        c = ns - ne;
-        uint32_t mal_before = 0;
-        for (uint32_t k = 0; k < e.n_mal; ++k) {
-            const bool cand = e.mal_s[k] <= qe;
-            mal_before += cand ? 1u : 0u;
-            c += (cand && e.mal_e[k] >= qs) ? 1u : 0u;
+        if (totals) {
+            s_tot = reinterpret_cast<unsigned long long*>(qm_smem + (((size_t)words * 4 + 15) & ~(size_t)15));
+            for (uint32_t k = threadIdx.x; k < n_contigs; k += QC_THREADS) s_tot[k] = 0ull;
         }
-        if (qs > qe) c = walk_scalar(e.ends, e.branch, ns + mal_before - 1u, qs);
+        __syncthreads();
     }
-    st_stream(counts + t, (CountT)c);
+    const uint64_t stride = (uint64_t)gridDim.x * QC_THREADS;
+    for (uint64_t t = (uint64_t)blockIdx.x * QC_THREADS + threadIdx.x; t < nq; t += stride) {
+        const uint32_t cid = (uint32_t)ld_stream(contig + t);
+        const int32_t qs = ld_stream(qs_in + t), qe = ld_stream(qe_in + t);
+        uint32_t c = 0;
+        if (cid < n_contigs && tab[cid].n != 0u) {
+            const MixedEntry& e = tab[cid];
+            const RankCells cs = e.cs, ce = e.ce;
+            uint32_t cell_s, off_s, cell_e, off_e;
+            cell_of(cs, (int64_t)qe + 1, cell_s, off_s);
+            cell_of(ce, (int64_t)qs, cell_e, off_e);
+            const CellRec rs = ld_cell(cs.rec + 2 * (size_t)cell_s);
+            const CellRec re = ld_cell(ce.rec + 2 * (size_t)cell_e);
+            const uint32_t ns = cell_rank(cs, e.rstarts, rs, cell_s, off_s, (int64_t)qe + 1);
+            const uint32_t ne = cell_rank(ce, e.eall, re, cell_e, off_e, (int64_t)qs);
+            c = ns - ne;
+            uint32_t mal_before = 0;
+            for (uint32_t k = 0; k < e.n_mal; ++k) {
+                const bool cand = e.mal_s[k] <= qe;
+                mal_before += cand ? 1u : 0u;
+                c += (cand && e.mal_e[k] >= qs) ? 1u : 0u;
+            }
+            if (qs > qe) c = walk_scalar(e.ends, e.branch, ns + mal_before - 1u, qs);
+            if (totals && c) {
+                if (s_tot) atomicAdd(s_tot + cid, (unsigned long long)c);
+                else atomicAdd(totals + cid, (unsigned long long)c);
+            }
+        }
+        st_stream(counts + t, (CountT)c);
+    }
+    if (s_tot) {
+        __syncthreads();
+        for (uint32_t k = threadIdx.x; k < n_contigs; k += QC_THREADS)
+            if (s_tot[k]) atomicAdd(totals + k, s_tot[k]);
+    }
 }
 
 // ---- has_overlaps: tests ONLY the last candidate (hpp:865-871, quirk Q1) ----------------

@@ -13,12 +13,12 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (OPT_STREAM, OPT_STREAM_BUDGET, OPT_STAB_BUDGET, OPT_STAB_LISTS, COUNT_AUTO, COUNT_CELLS, COUNT_RANK, COUNT_WALK, OPT_CELLS_DIRECT_BYTES, OPT_CELLS_FILL, FILL_IDXS, FILL_ITEMS, FILL_KEYS, FILL_VALUES, OPT_BUCKET_INTERVALS,
+from ._lib import (OPT_STREAM, OPT_STREAM_BUDGET, OPT_L2_PERSIST, OPT_NARROW_SORT, OPT_STAB_BUDGET, OPT_STAB_LISTS, COUNT_AUTO, COUNT_CELLS, COUNT_RANK, COUNT_WALK, OPT_CELLS_DIRECT_BYTES, OPT_CELLS_FILL, FILL_IDXS, FILL_ITEMS, FILL_KEYS, FILL_VALUES, OPT_BUCKET_INTERVALS,
                    OPT_COUNT_ALGO, OPT_TIMING, OPT_WINDOW_SHIFT, ORDER_ASIS, ORDER_AUTO, ORDER_SORTED, ORDER_UNSORTED)
 
 __all__ = ["DeviceIndex", "ORDER_AUTO", "ORDER_SORTED", "ORDER_UNSORTED", "ORDER_ASIS", "OPT_COUNT_ALGO",
            "OPT_BUCKET_INTERVALS", "OPT_WINDOW_SHIFT", "OPT_TIMING", "COUNT_AUTO", "COUNT_WALK", "COUNT_RANK", "COUNT_CELLS",
-           "OPT_CELLS_DIRECT_BYTES", "OPT_CELLS_FILL", "OPT_STAB_LISTS", "OPT_STAB_BUDGET", "OPT_STREAM", "OPT_STREAM_BUDGET"]
+           "OPT_CELLS_DIRECT_BYTES", "OPT_CELLS_FILL", "OPT_STAB_LISTS", "OPT_STAB_BUDGET", "OPT_STREAM", "OPT_STREAM_BUDGET", "OPT_L2_PERSIST", "OPT_NARROW_SORT"]
 
 
 def _stream():
@@ -123,6 +123,10 @@ class DeviceIndex:
         if rc:
             raise ValueError(f"siIndexSetOption({option}, {value}) failed")
         return self
+
+    def last_sort(self):
+        """0: the input was already sorted; 1: narrow sort + tie fix; 2: composite 64-bit key (siIndexLastSort)."""
+        return int(self._L.siIndexLastSort(self._ix))
 
     def cells_info(self):
         """Rank cells of the built index: {"starts": {...}, "ends": {...}} (siIndexCellsInfo)."""

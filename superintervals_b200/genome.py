@@ -72,15 +72,17 @@ class _CudaRouter:
 
     def count_mixed(self, indexes, contig, qs, qe, out):
         """out[i] = count of query i on indexes[contig[i]] (None: 0), caller's order, ONE launch, nothing routed
-        (siCountMixedDevice). False when an index cannot answer from rank cells: the caller routes by contig instead."""
+        (siCountMixedDevice). Returns the per-entry hit totals (int64 numpy), or None when an index cannot answer
+        from rank cells: the caller routes by contig instead."""
         n_c = len(indexes)
         arr = (C.c_void_p * n_c)(*[ix._ix if ix is not None else None for ix in indexes])
+        totals = torch.empty(n_c, dtype=torch.int64, device=contig.device)
         rc = self._L.siCountMixedDevice(arr, n_c, contig.data_ptr(), qs.data_ptr(), qe.data_ptr(), contig.numel(), out.data_ptr(),
-                                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                        totals.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
         if rc == -2:                                        # SI_MIXED_UNSUPPORTED
-            return False
+            return None
         self._lib.check("siCountMixedDevice")
-        return True
+        return totals.cpu().numpy()
 
     def scatter(self, counts, perm, out):
         self._L.siScatterCountsDevice(self._scratch._ix, counts.data_ptr(), perm.data_ptr(), counts.numel(), out.data_ptr(),
@@ -176,8 +178,9 @@ class GenomeIndex:
             self.last_exchange = {"dispatch_bytes": 0, "combine_bytes": 0}
             if direct:
                 out = torch.empty(n, dtype=torch.int32, device=dev)
-                if n == 0 or R.count_mixed(table, contig_ids, qs, qe, out):
-                    self._sum_hits_by_id(out, contig_ids)
+                tot = R.count_mixed(table, contig_ids, qs, qe, out)
+                if tot is not None:
+                    self.hits[:] = tot
                     return out
             gs, ge, perm, off = R.route(contig_ids, qs, qe, nc)
             routed = self._count_slots(gs, ge, off, list(range(nc)), count_fn)
@@ -207,9 +210,11 @@ class GenomeIndex:
             slot_table = [None] * nc
             for sl in range(my0, my1):
                 slot_table[sl] = self._ix.get(int(self.slot_contig[sl]))
-            answered = m == 0 or R.count_mixed(slot_table, rbuf[0], rbuf[1], rbuf[2], back)
+            tot = R.count_mixed(slot_table, rbuf[0], rbuf[1], rbuf[2], back)
+            answered = tot is not None
             if answered:
-                self._sum_hits_by_id(back, rbuf[0], slots=True)
+                self.hits[:] = 0
+                self.hits[self.slot_contig] = tot
         if not answered:
             # group what arrived by my slots, count per contig, back to arrival order
             local = rbuf[0] - my0
@@ -222,20 +227,6 @@ class GenomeIndex:
         dist.all_to_all_single(routed, back, output_split_sizes=send.tolist(), input_split_sizes=recv.tolist(), group=self.group)
         out = torch.empty(n, dtype=torch.int32, device=dev)
         return R.scatter(routed, perm, out) if n else out
-
-    def _sum_hits_by_id(self, counts, ids, slots=False):
-        """per-contig hit totals of one mixed launch (ids = contig ids, or slot ids when slots=True)"""
-        self.hits[:] = 0
-        if counts.numel() == 0:
-            return
-        nc = len(self.names)
-        tot = torch.zeros(nc, dtype=torch.int64, device=counts.device)
-        tot.index_add_(0, ids.long(), counts.to(torch.int64))
-        tot = tot.cpu().numpy()
-        if slots:
-            self.hits[self.slot_contig] = tot
-        else:
-            self.hits[:] = tot
 
     def _sum_hits(self, counts, off, slots):
         self.hits[:] = 0

@@ -222,8 +222,9 @@ def test_mixed_batch_in_one_launch_matches_per_contig_oracles_incl_malformed_emp
     L = _lib.lib()
     arr = (C.c_void_p * 6)(*[ix._ix if ix is not None else None for ix in idx])
     out = torch.full((cid.size,), -1, dtype=torch.int32, device="cuda")
-    rc = L.siCountMixedDevice(arr, 6, torch.from_numpy(cid).cuda().data_ptr(), torch.from_numpy(qs).cuda().data_ptr(),
-                              torch.from_numpy(qe).cuda().data_ptr(), cid.size, out.data_ptr(), None)
+    d_cid, d_qs, d_qe = torch.from_numpy(cid).cuda(), torch.from_numpy(qs).cuda(), torch.from_numpy(qe).cuda()
+    tot = torch.full((6,), -1, dtype=torch.int64, device="cuda")
+    rc = L.siCountMixedDevice(arr, 6, d_cid.data_ptr(), d_qs.data_ptr(), d_qe.data_ptr(), cid.size, out.data_ptr(), tot.data_ptr(), None)
     assert rc == 0
     _lib.check("siCountMixedDevice")
     torch.cuda.synchronize()
@@ -232,10 +233,9 @@ def test_mixed_batch_in_one_launch_matches_per_contig_oracles_incl_malformed_emp
         if c != 3:
             want[cid == c] = Oracle(*data[c]).count_batch(qs[cid == c], qe[cid == c])
     assert np.array_equal(out.cpu().numpy().astype(np.int64), want)
-    assert want[inv].sum() > 0 or True
+    assert tot.cpu().numpy().tolist() == [int(want[cid == c].sum()) for c in range(6)]
     # an index that cannot answer from rank cells (walk forced): the call declines without latching an error
     from superintervals_b200.device import OPT_COUNT_ALGO, COUNT_WALK
     idx[0].set_option(OPT_COUNT_ALGO, COUNT_WALK)
-    assert L.siCountMixedDevice(arr, 6, torch.from_numpy(cid).cuda().data_ptr(), torch.from_numpy(qs).cuda().data_ptr(),
-                                torch.from_numpy(qe).cuda().data_ptr(), cid.size, out.data_ptr(), None) == -2
+    assert L.siCountMixedDevice(arr, 6, d_cid.data_ptr(), d_qs.data_ptr(), d_qe.data_ptr(), cid.size, out.data_ptr(), None, None) == -2
     _lib.check("declined mixed count latches nothing")

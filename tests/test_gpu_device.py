@@ -190,3 +190,42 @@ def test_host_batch_pipeline_large_n():
     o = np.argsort(qs, kind="stable")                                              # position-sorted batch: no device sort
     got2 = m.count_batch_np(np.ascontiguousarray(qs[o]), np.ascontiguousarray(qe[o]))
     assert np.array_equal(got2, got[o])
+
+
+@pytest.mark.parametrize("case,expect", [("random", 1), ("short_runs", 1), ("equal_keys", 1), ("long_run", 2), ("option_off", 2),
+                                         ("presorted", 0)])
+def test_narrow_sort_with_tie_fix_builds_the_same_arrays_as_the_composite_key(case, expect):
+    """build() sorts by start alone (32-bit keys) and fixes equal starts in place; more than 16 equal starts fall back to
+    the composite 64-bit key. Whatever path ran (siIndexLastSort), starts / ends / payload order (stable among fully
+    equal keys, quirk Q3) / branch equal the oracle's."""
+    import torch
+    from oracle.pyoracle import Oracle
+    from superintervals_b200.device import DeviceIndex, OPT_NARROW_SORT
+    rng = np.random.default_rng(31)
+    n = 60_000
+    if case in ("random", "option_off", "presorted"):
+        s = rng.integers(0, 5_000_000, n).astype(np.int32)
+        e = (s + rng.integers(0, 4000, n)).astype(np.int32)
+    elif case == "short_runs":        # every start 1..16 times, ends all over the place, negative coordinates too
+        s = np.repeat(rng.integers(-2_000_000, 2_000_000, n // 8), rng.integers(1, 17, n // 8))[:n].astype(np.int32)
+        e = (s + rng.integers(0, 50_000, s.size)).astype(np.int32)
+        p = rng.permutation(s.size); s, e = s[p], e[p]
+    elif case == "equal_keys":        # runs whose ends repeat: insertion order must survive among equal (start, end)
+        s = np.repeat(rng.integers(0, 100_000, n // 6), 6).astype(np.int32)
+        e = (s + rng.integers(0, 3, s.size) * 100).astype(np.int32)
+        p = rng.permutation(s.size); s, e = s[p], e[p]
+    else:                              # one start 17 times among random data
+        s = rng.integers(0, 5_000_000, n).astype(np.int32)
+        s[rng.choice(n, 17, replace=False)] = 123_456
+        e = (s + rng.integers(0, 4000, n)).astype(np.int32)
+    if case == "presorted":
+        o = np.lexsort((-e.astype(np.int64), s)); s, e = s[o], e[o]
+    ix = DeviceIndex()
+    if case == "option_off":
+        ix.set_option(OPT_NARROW_SORT, 0)
+    ix.build(torch.from_numpy(s).cuda(), torch.from_numpy(e).cuda())
+    assert ix.last_sort() == expect
+    orc = Oracle(s, e)
+    gs, ge, gv, gb, gp = ix.export()
+    assert np.array_equal(gs, orc.starts) and np.array_equal(ge, orc.ends)
+    assert np.array_equal(gv, orc.data) and np.array_equal(gb, orc.branch)
