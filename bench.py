@@ -560,7 +560,10 @@ def bench_build(a, torch, ix, d_s, d_e, rank):
     out = {"intervals": n, "ms": best, "intervals_per_s": n / (best * 1e-3), "timing": "CUDA events around siIndexBuildDevice on its stream, best of 3, device-resident input",
            "algorithmic_bytes": a_build, "algorithmic_bytes_are": f"SURVEY 8d A_build with P = {P} live 8-bit digits: 12N in + P x 2 x 12N sort passes + 12N gather + 4N ends + 4N branch",
            "achieved_gbs": a_build / (best * 1e-3) / 1e9, "frac_hbm": a_build / (best * 1e-3) / 1e9 / peak,
-           "note": "the build also makes this implementation's own tables (all ends sorted, rank cells, rank bits, block-sorted ends, max tree): their bytes are not in A_build"}
+           "sort_path": {0: "input already sorted: no sort", 1: "narrow: 4 passes over (start, idx) 8-byte pairs + tie fix + 4 keys-only passes over the ends",
+                         2: "composite 64-bit key (start, ~end): 8 passes over 12-byte pairs"}.get(ix.last_sort(), "?"),
+           "note": "A_build is SURVEY 8d's figure for a composite-key sort; the narrow path moves fewer bytes than that. The build also makes this "
+                   "implementation's own tables (all ends sorted, rank cells, rank bits, block-sorted ends, max tree): their bytes are not in A_build"}
     exe = os.path.join(ROOT, "tools", "bin", "cub_sort")
     if rank == 0 and os.path.exists(exe):
         try:

@@ -482,16 +482,13 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
     if (ix->rank_ok) {
         const uint32_t nr = ix->n_rank;
         // every (well-formed) end, ascending: the second array of the count-by-rank kernel
-        if (ix->eall.ensure(pad_b) || ix->b_kA.ensure(n * 4) || ix->b_kB.ensure(n * 4) || ix->b_vA.ensure(n * 4) ||
-            ix->b_vB.ensure(n * 4) || ix->b_ws.ensure(rs_workspace_bytes<uint32_t>(ix->n)))
+        if (ix->eall.ensure(pad_b) || ix->b_kA.ensure(n * 4) || ix->b_kB.ensure(n * 4) || ix->b_ws.ensure(rs_workspace_bytes<uint32_t>(ix->n)))
             return last_error_code();
         SIB_LAUNCH(bk_end_keys_kernel, grid_for(n, BK_THREADS, cap), BK_THREADS, 0, s, ix->starts.as<int32_t>(), ix->ends.as<int32_t>(),
                    ix->n, ix->b_kA.as<uint32_t>());
-        // payload buffers ride along unused: the sort moves (key, uint32) pairs (zeroed so that no kernel
-        // ever reads uninitialised memory: compute-sanitizer initcheck stays clean)
-        SIB_CHECK(cudaMemsetAsync(ix->b_vA.p, 0, n * 4, s));
-        rc = radix_sort_pairs<uint32_t>(ix->b_kA.as<uint32_t>(), ix->b_kB.as<uint32_t>(), ix->b_vA.as<uint32_t>(),
-                                        ix->b_vB.as<uint32_t>(), ix->n, 32, ix->b_ws.p, ix->sm_count, s);
+        // keys only: no payload rides along (radix_sort.cuh, vA == nullptr)
+        rc = radix_sort_pairs<uint32_t>(ix->b_kA.as<uint32_t>(), ix->b_kB.as<uint32_t>(), nullptr, nullptr, ix->n, 32, ix->b_ws.p,
+                                        ix->sm_count, s);
         if (rc) return rc;
         RsWorkspace ws = rs_carve(ix->b_ws.p);
         SIB_LAUNCH(bk_sorted_ends_kernel, grid_for(ix->n_padded, BK_THREADS, cap), BK_THREADS, 0, s,

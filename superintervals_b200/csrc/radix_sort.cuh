@@ -131,7 +131,7 @@ rs_prepare_kernel(uint32_t* __restrict__ hist, RsPassInfo* __restrict__ info,
 }
 
 // ---- 3. onesweep pass --------------------------------------------------------------
-template <typename KeyT>
+template <typename KeyT, bool VALS>
 __global__ void __launch_bounds__(RS_THREADS)
 rs_onesweep_kernel(KeyT* __restrict__ kA, KeyT* __restrict__ kB,
                    uint32_t* __restrict__ vA, uint32_t* __restrict__ vB, uint32_t n, int pass,
@@ -254,10 +254,12 @@ rs_onesweep_kernel(KeyT* __restrict__ kA, KeyT* __restrict__ kB,
         slot[k] = s_dstart[d] + wh[d] + rank[k];
         s_keys[slot[k]] = key[k];
     }
+    if (VALS) {
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        uint64_t idx = wbase + (uint64_t)k * 32u + lane;
-        s_vals[slot[k]] = idx < n ? vin[idx] : 0u;
+        for (int k = 0; k < ITEMS; ++k) {
+            uint64_t idx = wbase + (uint64_t)k * 32u + lane;
+            s_vals[slot[k]] = idx < n ? vin[idx] : 0u;
+        }
     }
     __syncthreads();
 
@@ -271,7 +273,7 @@ rs_onesweep_kernel(KeyT* __restrict__ kA, KeyT* __restrict__ kB,
             uint32_t d = (uint32_t)((kk >> shift) & (RS_RADIX - 1));
             uint32_t dst = s_gofs[d] + li;
             kout[dst] = kk;
-            vout[dst] = s_vals[li];
+            if (VALS) vout[dst] = s_vals[li];
         }
     }
 }
@@ -314,12 +316,13 @@ __host__ inline int radix_sort_pairs(KeyT* kA, KeyT* kB, uint32_t* vA, uint32_t*
     SIB_CHECK_LAUNCH();
     note_launch();
 
+    // vA == nullptr: keys only (no payload read, staged or written: half the bytes of a 32-bit pass)
     const size_t smem = rs_onesweep_smem_bytes<KeyT>();
-    SIB_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = vA ? rs_onesweep_kernel<KeyT, true> : rs_onesweep_kernel<KeyT, false>;
+    SIB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int p = 0; p < run_passes; ++p) {
         SIB_CHECK(cudaMemsetAsync(ws.status, 0, sizeof(unsigned long long) * (size_t)tiles * RS_RADIX, s));
-        rs_onesweep_kernel<KeyT><<<tiles, RS_THREADS, smem, s>>>(kA, kB, vA, vB, n, p, ws.hist, ws.info,
-                                                                ws.status, ws.tickets + p);
+        kern<<<tiles, RS_THREADS, smem, s>>>(kA, kB, vA, vB, n, p, ws.hist, ws.info, ws.status, ws.tickets + p);
         SIB_CHECK_LAUNCH();
         note_launch();
     }

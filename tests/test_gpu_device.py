@@ -207,11 +207,11 @@ def test_narrow_sort_with_tie_fix_builds_the_same_arrays_as_the_composite_key(ca
         s = rng.integers(0, 5_000_000, n).astype(np.int32)
         e = (s + rng.integers(0, 4000, n)).astype(np.int32)
     elif case == "short_runs":        # every start 1..16 times, ends all over the place, negative coordinates too
-        s = np.repeat(rng.integers(-2_000_000, 2_000_000, n // 8), rng.integers(1, 17, n // 8))[:n].astype(np.int32)
+        s = np.repeat(rng.choice(4_000_000, n // 8, replace=False) - 2_000_000, rng.integers(1, 17, n // 8)).astype(np.int32)   # distinct starts: no run above 16
         e = (s + rng.integers(0, 50_000, s.size)).astype(np.int32)
         p = rng.permutation(s.size); s, e = s[p], e[p]
     elif case == "equal_keys":        # runs whose ends repeat: insertion order must survive among equal (start, end)
-        s = np.repeat(rng.integers(0, 100_000, n // 6), 6).astype(np.int32)
+        s = np.repeat(rng.choice(100_000, n // 6, replace=False), 6).astype(np.int32)
         e = (s + rng.integers(0, 3, s.size) * 100).astype(np.int32)
         p = rng.permutation(s.size); s, e = s[p], e[p]
     else:                              # one start 17 times among random data

@@ -14,6 +14,8 @@ WANT = [
     ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram % of peak"),
     ("lts__t_bytes.sum", "L2 bytes"), ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+    ("lts__t_sectors.sum", "L2 sectors"), ("lts__t_sectors_op_read.sum", "L2 sectors read"), ("lts__t_sectors_op_write.sum", "L2 sectors written"),
+    ("lts__t_sectors_srcunit_tex_op_read.sum", "L2 sectors read by SMs"),
     ("l1tex__t_bytes.sum", "L1 bytes"), ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
     ("l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "global ld requests"),
     ("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "global ld sectors"),
