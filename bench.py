@@ -789,12 +789,39 @@ def bench_c4(a, torch, dist, world, rank):
         got = out[sel].cpu().numpy().astype(np.uint32).astype(np.int64)
         par = {"checked": int(sel.numel()), "mismatches": int((got != want).sum()), "against": f"{kind} (oracle/_ref si::IntervalMap) on chr21's queries of rank 0's slice"}
     hits = int(out.to(torch.int64).sum().item())
+    # ---- the alternative at N > 1: every GPU holds ALL 24 indexes (3.8 GB for 100 M intervals) and counts its own slice in one
+    # launch -- no routing, no exchange. Moving a query to its owner costs 16 B over NVLink, as much time as counting it from
+    # HBM-resident rank cells, so partitioning the index pays only when it does not fit on one GPU.
+    repl = None
+    if world > 1:
+        full = GenomeIndex(names, [p[0] for p in parts], [p[1] for p in parts], rank=0, world=1)
+        rb = 0.0
+        for c in range(24):
+            n_c, q_c, Lc, seed = parts[c]
+            g = torch.Generator(device="cuda").manual_seed(seed)
+            s, e = gen_ranges_device(torch, g, n_c, int(Lc), 150, 10_000)
+            rb += timed_device(torch, lambda: full.build_contig(c, s, e), 1)
+            del s, e
+        out_r = full.count_mixed(cid, qs, qe)
+        torch.cuda.synchronize(); dist.barrier()
+        ms_r = timed_device(torch, lambda: full.count_mixed(cid, qs, qe), 3)
+        tr = torch.tensor([ms_r, rb], dtype=torch.float64, device="cuda")
+        same = torch.tensor([1.0 if torch.equal(out_r, out) else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        repl = {"index": "all 24 contig indexes on every GPU", "value": float(tot[0]) / (float(tr[0]) * 1e-3), "unit": UNIT,
+                "ms_per_step": float(tr[0]), "build_ms_max_over_ranks": float(tr[1]), "nccl_bytes_per_step": 0,
+                "step": "one launch of the mixed-batch count kernel on each GPU's slice, caller's order", "equals_partitioned_counts": bool(same[0] > 0)}
+        del full, out_r
+    step = ("device routing by owner (radix sort of the slot ids + gather), all-to-all dispatch, ONE mixed-batch count launch on each owner, "
+            "all-to-all combine, scatter back to the caller's order") if world > 1 else \
+           "ONE launch of the mixed-batch count kernel over the batch in the caller's order (per-contig rank-cell descriptors in shared memory): nothing routed"
     return {"workload": f"C4: 24 contigs (GRCh38 lengths), {int(tot[1])} intervals x {int(tot[0])} queries as one mixed batch, one index per contig, "
                         f"contigs owned by {world} GPU(s) (LPT)", "scaling": "strong",
             "value": float(tot[0]) / (float(t[0]) * 1e-3), "unit": UNIT, "ms_per_step": float(t[0]), "build_ms_max_over_ranks": float(t[1]),
-            "step": "device routing by contig (radix sort of the ids + gather)" + (", all-to-all dispatch, count on the owners, all-to-all combine" if world > 1 else ", 24 count launches") + ", scatter back to the caller's order",
+            "step": step, "index": "partitioned by contig (each GPU holds the contigs it owns)" if world > 1 else "all 24 contig indexes on the one GPU",
             "nccl_dispatch_bytes_per_step": int(tot[2]), "nccl_combine_bytes_per_step": int(tot[3]), "hits_rank0": hits, "parity": par,
-            "owner": [int(x) for x in gi.owner]}
+            "owner": [int(x) for x in gi.owner], "replicated": repl}
 
 
 def bench_configs(a, torch, dist, L, _lib, world, rank):

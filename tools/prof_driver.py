@@ -7,6 +7,23 @@ from superintervals_b200 import workloads as W
 from superintervals_b200.device import (DeviceIndex, ORDER_SORTED, ORDER_UNSORTED, OPT_COUNT_ALGO, COUNT_WALK,
                                         OPT_BUCKET_INTERVALS, OPT_WINDOW_SHIFT)
 
+if len(sys.argv) > 1 and sys.argv[1] == "mixed":
+    # mode B in one launch: 8 contigs of 2 M read-length intervals on 50 Mb each, 64 M mixed queries
+    import numpy as np
+    from superintervals_b200.genome import GenomeIndex
+    reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    gi = GenomeIndex([f"c{i}" for i in range(8)], [2_000_000] * 8, rank=0, world=1)
+    for c in range(8):
+        s, e = W.config2_intervals(2_000_000, 20 + c, axis=50_000_000)
+        gi.build_contig(c, torch.from_numpy(s).cuda(), torch.from_numpy(e).cuda())
+    qs, qe = W.config2_queries(64_000_000, 3, axis=50_000_000)
+    cid = torch.from_numpy(np.random.default_rng(1).integers(0, 8, qs.size).astype(np.int32)).cuda()
+    dqs, dqe = torch.from_numpy(qs).cuda(), torch.from_numpy(qe).cuda()
+    for _ in range(reps):
+        out = gi.count_mixed(cid, dqs, dqe)
+    torch.cuda.synchronize()
+    print("hits", int(out.long().sum().item()))
+    sys.exit(0)
 which = sys.argv[1] if len(sys.argv) > 1 else "c2s"
 mode = sys.argv[2] if len(sys.argv) > 2 else "count"
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
