@@ -638,6 +638,46 @@ def bench_strong(a, torch, dist, L, _lib, ix, world, rank, d_qs, d_qe, counts_ra
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         res[name] = float(t[0])
+    # ---- the same step with the collective FUSED into the count kernel: every count is stored into every GPU's copy of the
+    # gathered vector as it is produced (peer stores over NVLink, siCountFanoutDevice), then one one-warp kernel exchanges
+    # flags (siPeerBarrierDevice). No NCCL call in the step.
+    fused = None
+    try:
+        from superintervals_b200.sharding import PeerGathered
+        pg = PeerGathered(per, world, rank)
+
+        def fused_gather():
+            arr, sl, ptrs = pg.current()
+            if m:
+                ix.count_fanout(mqs, mqe, sl[:m], ptrs, order=ORDER_UNSORTED)
+            pg.barrier()
+            return arr
+
+        def fused_scan():
+            ix.scan(fused_gather(), out=offsets)
+
+        fr = {}
+        for name, fn in (("count_gather", fused_gather), ("count_gather_scan", fused_scan)):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize(); dist.barrier()
+            ms = timed_device(torch, fn, a.steps)
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            fr[name] = float(t[0])
+        arr = fused_gather()
+        torch.cuda.synchronize()
+        same = torch.tensor([1.0 if torch.equal(arr, gathered) and not pg.timed_out() else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        fused = {"ms_count_gather": fr["count_gather"], "ms_count_gather_scan": fr["count_gather_scan"],
+                 "value": nq / (fr["count_gather"] * 1e-3), "unit": UNIT,
+                 "equals_nccl_gather_on_every_gpu": bool(same[0] > 0),
+                 "nvlink_bytes_sent_per_gpu_per_step": 4 * per * (world - 1),
+                 "how": "count kernel stores each count into every GPU's gathered vector (CUDA IPC peer memory, double-buffered) + "
+                        "one-warp flag barrier kernel; no collective library call inside the step"}
+        pg.close()
+    except Exception as ex:   # noqa: BLE001
+        fused = {"unavailable": repr(ex)[:300]}
     ok = None
     if rank == 0:
         got = torch.cat([gathered[r * per: r * per + max(0, min(nq, (r + 1) * per) - r * per)] for r in range(world)])
@@ -649,7 +689,7 @@ def bench_strong(a, torch, dist, L, _lib, ix, world, rank, d_qs, d_qe, counts_ra
             "nccl_bytes_received_per_gpu_per_step": 4 * per * (world - 1),
             "nccl_bytes_per_step_all_gpus": 4 * per * (world - 1) * world,
             "gather_gbs_per_gpu": (4 * per * (world - 1)) / max(1e-9, (res["count_gather"] - res["count_only"]) * 1e-3) / 1e9,
-            "gathered_equals_single_gpu_counts": ok,
+            "gathered_equals_single_gpu_counts": ok, "fused": fused,
             "timing": "CUDA events on the launching stream (NCCL work joined by torch), max over ranks"}
 
 

@@ -261,15 +261,42 @@ int siScatterCountsDevice(siIndex* ix, const uint32_t* d_counts, const uint32_t*
 int siCountMixedDevice(siIndex* const* ixs, int n_contigs, const int32_t* d_contig, const int32_t* d_qs, const int32_t* d_qe,
                        size_t n, uint32_t* d_counts, unsigned long long* d_totals, void* stream);
 
+/* ---- 3c. count fused with the all-gather of the counts ---------------------------------------------
+ * siCountDevice that additionally stores every count at the same index of up to 15 further arrays. With the arrays
+ * being the OTHER GPUs' copies of a gathered count vector (peer memory: cudaDeviceEnablePeerAccess inside one process,
+ * or a CUDA IPC mapping of another process's buffer, below), "count, then ncclAllGather of the counts" becomes one
+ * kernel whose results travel over NVLink as peer stores while it is still ranking: d_counts = this GPU's slot of its
+ * own copy, peers[k] = the same slot in GPU k's copy. The caller orders the GPUs afterwards (event waits inside one
+ * process; any barrier across processes) before reading slots written by others. */
+int siCountFanoutDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, uint32_t* d_counts,
+                        uint32_t* const* peers, int n_peers, int order, void* stream);
+/* Device buffers shareable between the processes of one node (one process per GPU, torchrun): siIpcAlloc = cudaMalloc
+ * on the current device + its 64-byte CUDA IPC handle; siIpcOpen maps another process's buffer here (peer access over
+ * NVLink); siIpcClose / siIpcFree undo them. Exchange the handles by any means (an all_gather of 64 bytes per rank). */
+/* Barrier between GPUs through peer memory, stream-ordered (one 32-thread kernel, no collective library): stores `seq` to
+ * signal_ptrs[k] (a flag word in peer k's memory reserved for this rank), then waits until wait_ptrs[k] (this GPU's own
+ * flag word for peer k) shows seq or later. Use increasing seq values. *d_timed_out (device word, zeroed by the caller
+ * once) becomes 1 if a peer did not arrive within about 10 s. */
+int siPeerBarrierDevice(uint32_t* const* signal_ptrs, const uint32_t* const* wait_ptrs, int n_peers, uint32_t seq, uint32_t* d_timed_out,
+                        void* stream);
+int siIpcAlloc(size_t bytes, void** d_ptr, unsigned char handle_out[64]);
+int siIpcOpen(const unsigned char handle[64], void** d_ptr);
+int siIpcClose(void* d_ptr);
+int siIpcFree(void* d_ptr);
+
 /* ---- 4. several GPUs of one node (single host process; csrc/multi.cu) --------------------------------
  * The reference has no notion of devices: its callers hold one map per chromosome and loop over the
  * queries (examples/bed-intersect-si.rs:100-123). siMulti keeps one replica of ONE index per device and
  * cuts every host batch into one contiguous range per device:
  *   siMultiBuildReplicated    one upload to the first device, ncclBroadcast of the interval columns to
  *                             the others over NVLink, every device builds its replica from device memory;
- *   siMultiCountBatch         H2D of each range on its own PCIe link, one count launch per device, ONE
- *                             ncclAllGather of the per-query counts (every device then holds the whole count
- *                             vector: siMultiDeviceCounts), each device returns its range to counts_out;
+ *   siMultiCountBatch         H2D of each range on its own PCIe link, one count launch per device whose kernel stores
+ *                             every count into EVERY device's gathered vector as it is produced (peer stores over
+ *                             NVLink: the all-gather fused into the count, siCountFanoutDevice; the streams then wait
+ *                             for each other's kernels through events). Without peer access between the devices
+ *                             (or SIB_MULTI_P2P=0): count, then ONE ncclAllGather of the per-query counts. Either way
+ *                             every device then holds the whole count vector (siMultiDeviceCounts) and returns its
+ *                             own range to counts_out;
  *   siMultiSearchValuesBatch  the gathered counts are scanned on every device into GLOBAL 64-bit CSR offsets,
  *                             each device fills and returns its own segment of `found` (same layout and order
  *                             as searchValuesBatch).
@@ -281,6 +308,9 @@ typedef struct {
     double ms_h2d, ms_count, ms_gather, ms_d2h;   /* device time per phase, max over devices (CUDA events) */
     unsigned long long nccl_bytes;                /* bytes received through NCCL collectives since creation, all ranks */
     int nccl_version;
+    int peer_access;                              /* 1: every device can store into every other's memory (NVLink): the all-gather of
+                                                     the counts is fused into the count kernels (siCountFanoutDevice) */
+    unsigned long long peer_bytes;                /* bytes the count kernels stored into other devices' memory since creation */
 } siMultiStats;
 siMulti* siMultiCreate(const int* devices, int n_devices);
 void     siMultiDestroy(siMulti* m);

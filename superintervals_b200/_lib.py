@@ -68,7 +68,8 @@ class siBitsInfo(C.Structure):
 
 class siMultiStats(C.Structure):
     _fields_ = [("ms_total", C.c_double), ("ms_h2d", C.c_double), ("ms_count", C.c_double), ("ms_gather", C.c_double),
-                ("ms_d2h", C.c_double), ("nccl_bytes", C.c_ulonglong), ("nccl_version", C.c_int)]
+                ("ms_d2h", C.c_double), ("nccl_bytes", C.c_ulonglong), ("nccl_version", C.c_int),
+                ("peer_access", C.c_int), ("peer_bytes", C.c_ulonglong)]
 
 
 class siBedTable(C.Structure):
@@ -111,7 +112,7 @@ B200_SYMBOLS = [
     "searchItemsBatch", "coverageBatch", "intersectionPairs", "siParseBed", "siBedTableFree", "siIndexCreate", "siIndexDestroy", "siIndexOf", "siIndexSize",
     "siIndexDeviceView", "siIndexBuildHost", "siIndexBuildDevice", "siIndexExport", "siCountDevice",
     "siCountDevice64", "siSortQueriesDevice", "siIndexSetOption", "siIndexCellsInfo", "siIndexBitsInfo", "siIndexStreamStats", "siIndexStabInfo", "siIndexReadTimings", "siAnyDevice", "siScanDevice", "siFillDevice", "siCoverageDevice",
-    "siIndexDeviceBytes", "siRouteByContigDevice", "siScatterCountsDevice", "siCountMixedDevice", "siIndexLastSort",
+    "siIndexDeviceBytes", "siRouteByContigDevice", "siScatterCountsDevice", "siCountMixedDevice", "siIndexLastSort", "siCountFanoutDevice", "siPeerBarrierDevice", "siIpcAlloc", "siIpcOpen", "siIpcClose", "siIpcFree",
     "siMultiCreate", "siMultiDestroy", "siMultiDeviceCount", "siMultiIndexOf", "siMultiBuildReplicated", "siMultiCountBatch",
     "siMultiSearchValuesBatch", "siMultiDeviceCounts", "siMultiLastStats",
 ]
@@ -242,6 +243,12 @@ def bind_b200(L):
     L.siRouteByContigDevice.argtypes = [vp, vp, vp, vp, sz, C.c_int, vp, vp, vp, vp, vp]
     L.siScatterCountsDevice.argtypes = [vp, vp, vp, sz, vp, vp]
     L.siIndexLastSort.argtypes = [vp]
+    L.siCountFanoutDevice.argtypes = [vp, vp, vp, sz, vp, vp, C.c_int, C.c_int, vp]
+    L.siPeerBarrierDevice.argtypes = [vp, vp, C.c_int, C.c_uint32, vp, vp]
+    L.siIpcAlloc.argtypes = [sz, C.POINTER(vp), vp]
+    L.siIpcOpen.argtypes = [vp, C.POINTER(vp)]
+    L.siIpcClose.argtypes = [vp]
+    L.siIpcFree.argtypes = [vp]
     L.siCountMixedDevice.argtypes = [vp, C.c_int, vp, vp, vp, sz, vp, vp, vp]
     return L
 

@@ -646,7 +646,7 @@ int resolve_order(siIndex* ix, const int32_t* d_qs, uint32_t nq, int order, cuda
 }
 
 template <typename CountT>
-int launch_count(siIndex* ix, const QueryRecords& rec, uint32_t nq, CountT* d_counts, cudaStream_t s) {
+int launch_count(siIndex* ix, const QueryRecords& rec, uint32_t nq, CountT* d_counts, cudaStream_t s, const Fanout& fan) {
     const int algo = count_algo_of(ix);
     if (algo == SI_COUNT_CELLS) {
         const int grid = (int)(((uint64_t)nq + QC_TILE - 1) / QC_TILE);
@@ -667,11 +667,11 @@ int launch_count(siIndex* ix, const QueryRecords& rec, uint32_t nq, CountT* d_co
             cfg.attrs = at;
             cfg.numAttrs = 1;
             ix->timer.begin(TAG_COUNT_CELLS, s);
-            SIB_CHECK(cudaLaunchKernelEx(&cfg, qk_count_cells_kernel<CountT>, view_of(ix), rec, nq, d_counts));
+            SIB_CHECK(cudaLaunchKernelEx(&cfg, qk_count_cells_kernel<CountT>, view_of(ix), rec, nq, d_counts, fan));
             ix->timer.end(s);
             note_launch();
         } else {
-            SIB_LAUNCH_T(ix, TAG_COUNT_CELLS, (qk_count_cells_kernel<CountT>), grid, QC_THREADS, 0, s, view_of(ix), rec, nq, d_counts);
+            SIB_LAUNCH_T(ix, TAG_COUNT_CELLS, (qk_count_cells_kernel<CountT>), grid, QC_THREADS, 0, s, view_of(ix), rec, nq, d_counts, fan);
         }
     } else if (algo == SI_COUNT_RANK) {
         const int grid = (int)(((uint64_t)nq + QR_TILE - 1) / QR_TILE);
@@ -689,10 +689,12 @@ bool stream_ready(const siIndex* ix) {
 }
 
 template <typename CountT>
-int launch_count_stream(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, uint32_t nq, CountT* d_counts, cudaStream_t s) {
+int launch_count_stream(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, uint32_t nq, CountT* d_counts, cudaStream_t s, const Fanout& fan) {
     static_assert(SK_TILE % QC_TILE == 0, "a streaming tile is a whole number of rank-cells tiles");
     const int tiles = (int)(((uint64_t)nq + SK_TILE - 1) / SK_TILE);
-    const uint32_t vec_ok = ((((uintptr_t)d_qs) | ((uintptr_t)d_qe) | ((uintptr_t)d_counts)) & 31u) == 0 ? 1u : 0u;
+    uintptr_t align = ((uintptr_t)d_qs) | ((uintptr_t)d_qe) | ((uintptr_t)d_counts);
+    for (int f = 0; f < fan.n; ++f) align |= (uintptr_t)fan.p[f];
+    const uint32_t vec_ok = (align & 31u) == 0 ? 1u : 0u;
     if (ix->stream_ws.ensure(((size_t)tiles + 16) * 4)) return last_error_code();
     uint32_t* fail_count = ix->stream_ws.as<uint32_t>();
     uint32_t* fail_list = fail_count + 8;
@@ -706,10 +708,10 @@ int launch_count_stream(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, u
     if (per_sm < 1) per_sm = 1;
     const int grid = tiles < ix->sm_count * per_sm ? tiles : ix->sm_count * per_sm;
     ix->timer.begin(TAG_COUNT_STREAM, s);
-    kern<<<grid, SK_THREADS, SK_SMEM, s>>>(view_of(ix), d_qs, d_qe, nq, d_counts, vec_ok, (uint32_t)tiles, fail_list, fail_count);
+    kern<<<grid, SK_THREADS, SK_SMEM, s>>>(view_of(ix), d_qs, d_qe, nq, d_counts, vec_ok, (uint32_t)tiles, fail_list, fail_count, fan);
     SIB_CHECK_LAUNCH();
     const int grid2 = tiles < ix->sm_count * 4 ? tiles : ix->sm_count * 4;
-    sk_count_failed_tiles_kernel<CountT><<<grid2, QC_THREADS, 0, s>>>(view_of(ix), d_qs, d_qe, nq, d_counts, fail_list, fail_count);
+    sk_count_failed_tiles_kernel<CountT><<<grid2, QC_THREADS, 0, s>>>(view_of(ix), d_qs, d_qe, nq, d_counts, fail_list, fail_count, fan);
     SIB_CHECK_LAUNCH();
     ix->timer.end(s);
     note_launch(2);
@@ -718,7 +720,7 @@ int launch_count_stream(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, u
 
 template <typename CountT>
 int count_impl(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, CountT* d_counts, int order,
-               void* stream) {
+               void* stream, const Fanout* fanout = nullptr) {
     if (!ix || !ix->built) {
         set_error_msg(cudaErrorNotReady, "siCountDevice: index not built (call build/indexSuperIntervals first)");
         return cudaErrorNotReady;
@@ -732,8 +734,13 @@ int count_impl(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, 
     cudaStream_t s = pick_stream(ix, stream);
     if (ix->n == 0) {
         SIB_CHECK(cudaMemsetAsync(d_counts, 0, n * sizeof(CountT), s));
+        if (fanout)
+            for (int f = 0; f < fanout->n; ++f) SIB_CHECK(cudaMemsetAsync(fanout->p[f], 0, n * 4, s));
         return 0;
     }
+    // fan-out (fused all-gather): the cells and streaming kernels store into the peers' arrays themselves; the walk and
+    // rank-grid kernels (forced by option, or an index without rank cells) are followed by plain copies instead
+    const bool fan_in_kernel = fanout && fanout->n > 0 && count_algo_of(ix) == SI_COUNT_CELLS;
     const bool armed = ix->plan_armed;
     ix->plan_armed = false;
     bool streaming = false;
@@ -751,9 +758,15 @@ int count_impl(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, 
     // batches beyond the partition's size are processed in slices (their scratch is bounded too)
     for (size_t at = 0; at < n; at += PT_MAX_BATCH) {
         const uint32_t m = (uint32_t)(n - at < PT_MAX_BATCH ? n - at : PT_MAX_BATCH);
+        Fanout fan;
+        fan.n = 0;
+        if (fan_in_kernel) {
+            fan.n = fanout->n;
+            for (int f = 0; f < fanout->n; ++f) fan.p[f] = fanout->p[f] + at;
+        }
         if (streaming) {
             ix->plan_valid = false;
-            int rc = launch_count_stream<CountT>(ix, d_qs + at, d_qe + at, m, d_counts + at, s);
+            int rc = launch_count_stream<CountT>(ix, d_qs + at, d_qe + at, m, d_counts + at, s, fan);
             if (rc) return rc;
             continue;
         }
@@ -765,9 +778,11 @@ int count_impl(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, 
         } else {
             ix->plan_valid = false;
         }
-        int rc = launch_count<CountT>(ix, rec, m, d_counts + at, s);
+        int rc = launch_count<CountT>(ix, rec, m, d_counts + at, s, fan);
         if (rc) return rc;
     }
+    if (fanout && fanout->n > 0 && !fan_in_kernel && sizeof(CountT) == 4)
+        for (int f = 0; f < fanout->n; ++f) SIB_CHECK(cudaMemcpyAsync(fanout->p[f], d_counts, n * 4, cudaMemcpyDefault, s));
     return 0;
 }
 
@@ -1032,6 +1047,21 @@ int siCountDevice64(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_
                     void* stream) {
     return count_impl<uint64_t>(ix, d_qs, d_qe, n, d_counts, order, stream);
 }
+
+// count + fan-out of every count to further arrays (superintervals_b200.h section 3c): the fused form of
+// "count, then all-gather the counts" when the arrays are the other GPUs' copies of the gathered vector
+int siCountFanoutDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, uint32_t* d_counts,
+                        uint32_t* const* peers, int n_peers, int order, void* stream) {
+    if (n_peers < 0 || n_peers > SI_FANOUT_MAX || (n_peers && !peers)) {
+        set_error_msg(cudaErrorInvalidValue, "siCountFanoutDevice: 0..15 peer arrays");
+        return cudaErrorInvalidValue;
+    }
+    Fanout fan;
+    fan.n = n_peers;
+    for (int f = 0; f < n_peers; ++f) fan.p[f] = peers[f];
+    return count_impl<uint32_t>(ix, d_qs, d_qe, n, d_counts, order, stream, &fan);
+}
+
 
 int siSortQueriesDevice(siIndex* ix, const int32_t* d_qs, const int32_t* d_qe, size_t n, void* stream) {
     if (!ix || !ix->built) {
@@ -1336,6 +1366,61 @@ int siCountMixedDevice(siIndex* const* ixs, int n_contigs, const int32_t* d_cont
                  (uint32_t)n, d_counts, d_totals);
     return 0;
 }
+
+// ---- barrier between GPUs through peer memory --------------------------------------------------------------
+// After a fan-out count every GPU has to know that the others' stores have landed before it reads their slots. One warp:
+// lane k publishes `seq` in peer k's flag word for this rank (after a system-scope fence: the count kernel's peer stores
+// precede it in stream order), then spins on this GPU's own flag word for peer k until it shows `seq` (or later). A peer
+// that never arrives trips the timeout (about 10 s of %globaltimer) and sets *timed_out instead of hanging the GPU.
+struct PeerFlags { uint32_t* signal[SI_FANOUT_MAX]; const uint32_t* wait[SI_FANOUT_MAX]; int n; };
+__global__ void __launch_bounds__(32)
+pk_barrier_kernel(const __grid_constant__ PeerFlags f, uint32_t seq, uint32_t* __restrict__ timed_out) {
+    const int k = threadIdx.x;
+    if (k >= f.n) return;
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(f.signal[k]) = seq;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while ((int32_t)(*reinterpret_cast<const volatile uint32_t*>(f.wait[k]) - seq) < 0) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 10000000000ull) { *timed_out = 1u; break; }
+    }
+    __threadfence_system();
+}
+
+int siPeerBarrierDevice(uint32_t* const* signal_ptrs, const uint32_t* const* wait_ptrs, int n_peers, uint32_t seq, uint32_t* d_timed_out,
+                        void* stream) {
+    if (n_peers < 0 || n_peers > SI_FANOUT_MAX || (n_peers && (!signal_ptrs || !wait_ptrs)) || !d_timed_out) return cudaErrorInvalidValue;
+    if (n_peers == 0) return 0;
+    PeerFlags f;
+    f.n = n_peers;
+    for (int k = 0; k < n_peers; ++k) { f.signal[k] = signal_ptrs[k]; f.wait[k] = wait_ptrs[k]; }
+    pk_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(f, seq, d_timed_out);
+    SIB_CHECK_LAUNCH();
+    note_launch();
+    return 0;
+}
+
+// ---- buffers shared between the processes of one node (CUDA IPC) --------------------------------------
+int siIpcAlloc(size_t bytes, void** d_ptr, unsigned char handle_out[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    if (!d_ptr || !handle_out || bytes == 0) return cudaErrorInvalidValue;
+    SIB_CHECK(cudaMalloc(d_ptr, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *d_ptr);
+    if (e != cudaSuccess) { cudaFree(*d_ptr); *d_ptr = nullptr; set_error(e, "cudaIpcGetMemHandle", __FILE__, __LINE__); return (int)e; }
+    memcpy(handle_out, &h, 64);
+    return 0;
+}
+int siIpcOpen(const unsigned char handle[64], void** d_ptr) {
+    if (!d_ptr || !handle) return cudaErrorInvalidValue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    SIB_CHECK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int siIpcClose(void* d_ptr) { if (d_ptr) SIB_CHECK(cudaIpcCloseMemHandle(d_ptr)); return 0; }
+int siIpcFree(void* d_ptr) { if (d_ptr) SIB_CHECK(cudaFree(d_ptr)); return 0; }
 
 // used by c_abi.cu: resolve SI_ORDER_AUTO once for a count -> fill pair
 int si_b200_resolve_order_(siIndex* ix, const int32_t* d_qs, size_t n, void* stream) {

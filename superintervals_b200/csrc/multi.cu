@@ -5,9 +5,11 @@
 // and loop over queries. Here a host batch is cut into one contiguous range per device:
 //   build    the intervals go to the first device once (one H2D), ncclBroadcast carries them to the
 //            other devices over NVLink, every device builds its replica from device memory;
-//   count    H2D of each range on its own PCIe link, one count launch per device, then ONE
-//            ncclAllGather of the per-query counts (4 B x range per rank) so that every device holds the
-//            whole count vector; each device returns its own range to the host;
+//   count    H2D of each range on its own PCIe link, one count launch per device. With NVLink peer access the
+//            kernel itself stores each count into every device's gathered vector (fan-out: count and all-gather are
+//            one kernel, the streams then wait on each other's events); otherwise ONE ncclAllGather of the
+//            per-query counts (4 B x range per rank). Every device then holds the whole count vector and
+//            returns its own range to the host;
 //   search   the gathered counts are scanned on every device into the GLOBAL 64-bit CSR offsets
 //            (no host round trip for the bases), each device fills and returns its own segment.
 // NCCL is resolved at run time (dlopen of libnccl.so.2): a single-device process never needs it.
@@ -21,6 +23,7 @@
 
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -77,6 +80,8 @@ struct siMulti {
     std::vector<cudaEvent_t> ev;               // 5 per device: start, h2d done, count done, gather done, d2h done
     NcclApi nccl;
     std::vector<ncclComm_t> comm;
+    bool p2p = false;                          // every device can store into every other's memory (NVLink peer access enabled)
+    std::vector<cudaEvent_t> ev_done;          // per device: its fan-out count kernel has finished
     size_t per = 0;                            // queries per device of the last batch (padded range length)
     size_t n_intervals = 0;
     bool built = false;
@@ -132,33 +137,56 @@ float span_ms(siMulti* m, int a, int b) {   // max over devices of event b - eve
     return worst;
 }
 
-// count every range and gather: on return (stream-ordered) every device holds all counts in gather[i]
+// count every range and gather: on return (stream-ordered) every device holds all counts in gather[i].
+// With peer access between the devices (NVLink) the gather is FUSED into the count: device i's kernel stores each count into
+// its slot of every device's gathered vector as it is produced (siCountFanoutDevice), and the streams then wait for one
+// another's kernels through events -- no collective pass. Without peer access: count, then ncclAllGather in place.
 int count_ranges(siMulti* m, const int32_t* qs, const int32_t* qe, size_t nq) {
     const size_t per = (((nq + m->n - 1) / m->n) + 7) & ~(size_t)7;   // 32-byte aligned ranges
     m->per = per;
+    for (int i = 0; i < m->n; ++i) {   // every gathered vector exists before any kernel stores into it
+        SIB_CHECK(cudaSetDevice(m->dev[i]));
+        if (m->qs[i].ensure(per * 4) || m->qe[i].ensure(per * 4) || m->gather[i].ensure((size_t)m->n * per * 4)) return last_error_code();
+    }
+    const bool fused = m->p2p && m->n > 1;
     int rc = for_each_device(m, [&](int i) -> int {
         const size_t lo = (size_t)i * per < nq ? (size_t)i * per : nq;
         const size_t hi = lo + per < nq ? lo + per : nq;
         const size_t len = hi - lo;
         cudaStream_t s = m->st[i];
-        if (m->qs[i].ensure(per * 4) || m->qe[i].ensure(per * 4) || m->gather[i].ensure((size_t)m->n * per * 4)) return last_error_code();
         uint32_t* mine = m->gather[i].as<uint32_t>() + (size_t)i * per;
+        uint32_t* peers[16];
+        int np = 0;
+        if (fused)
+            for (int k = 0; k < m->n; ++k)
+                if (k != i) peers[np++] = m->gather[k].as<uint32_t>() + (size_t)i * per;
         SIB_CHECK(cudaEventRecord(m->ev[5 * i + 0], s));
         if (len) {
             SIB_CHECK(cudaMemcpyAsync(m->qs[i].p, qs + lo, len * 4, cudaMemcpyHostToDevice, s));
             SIB_CHECK(cudaMemcpyAsync(m->qe[i].p, qe + lo, len * 4, cudaMemcpyHostToDevice, s));
         }
         SIB_CHECK(cudaEventRecord(m->ev[5 * i + 1], s));
-        if (len < per) SIB_CHECK(cudaMemsetAsync(mine + len, 0, (per - len) * 4, s));   // padding counts as zero hits
+        if (len < per) {                                                             // padding counts as zero hits
+            SIB_CHECK(cudaMemsetAsync(mine + len, 0, (per - len) * 4, s));
+            for (int k = 0; k < np; ++k) SIB_CHECK(cudaMemsetAsync(peers[k] + len, 0, (per - len) * 4, s));
+        }
         if (len) {
-            int r = siCountDevice(m->ix[i], m->qs[i].as<int32_t>(), m->qe[i].as<int32_t>(), len, mine, SI_ORDER_AUTO, (void*)s);
+            int r = siCountFanoutDevice(m->ix[i], m->qs[i].as<int32_t>(), m->qe[i].as<int32_t>(), len, mine, peers, np, SI_ORDER_AUTO, (void*)s);
             if (r) return r;
         }
         SIB_CHECK(cudaEventRecord(m->ev[5 * i + 2], s));
+        if (fused) SIB_CHECK(cudaEventRecord(m->ev_done[i], s));
         return 0;
     });
     if (rc) return rc;
-    if (m->n > 1) {
+    if (fused) {
+        for (int i = 0; i < m->n; ++i) {   // device i may read the others' slots once their kernels are done
+            SIB_CHECK(cudaSetDevice(m->dev[i]));
+            for (int k = 0; k < m->n; ++k)
+                if (k != i) SIB_CHECK(cudaStreamWaitEvent(m->st[i], m->ev_done[k], 0));
+        }
+        m->stats.peer_bytes += (unsigned long long)per * 4 * (m->n - 1) * m->n;
+    } else if (m->n > 1) {
         SIB_NCCL(m, m->nccl.GroupStart());
         for (int i = 0; i < m->n; ++i) {
             uint32_t* all = m->gather[i].as<uint32_t>();
@@ -228,6 +256,32 @@ siMulti* siMultiCreate(const int* devices, int n_devices) {
             return nullptr;
         }
         if (m->nccl.GetVersion) m->nccl.GetVersion(&m->stats.nccl_version);
+        // peer access between every pair (NVLink / NVSwitch): the count kernels then store straight into the other devices'
+        // gathered vectors. SIB_MULTI_P2P=0 keeps the NCCL all-gather (also taken when a pair cannot reach each other).
+        const char* env = getenv("SIB_MULTI_P2P");
+        bool p2p = n_devices <= 16 && !(env && atoi(env) == 0);
+        for (int i = 0; i < n_devices && p2p; ++i)
+            for (int k = 0; k < n_devices && p2p; ++k) {
+                int can = 0;
+                if (i != k && (cudaDeviceCanAccessPeer(&can, m->dev[i], m->dev[k]) != cudaSuccess || !can)) p2p = false;
+            }
+        for (int i = 0; i < n_devices && p2p; ++i) {
+            cudaSetDevice(m->dev[i]);
+            for (int k = 0; k < n_devices; ++k) {
+                if (i == k) continue;
+                cudaError_t pe = cudaDeviceEnablePeerAccess(m->dev[k], 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) p2p = false;
+                (void)cudaGetLastError();
+            }
+        }
+        m->p2p = p2p;
+        m->stats.peer_access = p2p ? 1 : 0;
+        for (int i = 0; i < n_devices; ++i) {
+            cudaSetDevice(m->dev[i]);
+            cudaEvent_t ev = nullptr;
+            cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            m->ev_done.push_back(ev);
+        }
     }
     cudaSetDevice(prev);
     return m;
@@ -245,6 +299,7 @@ void siMultiDestroy(siMulti* m) {
             if (i < v->size()) (*v)[i].release();
         for (int k = 0; k < 5; ++k)
             if (5 * i + k < m->ev.size() && m->ev[5 * i + k]) cudaEventDestroy(m->ev[5 * i + k]);
+        if (i < m->ev_done.size() && m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
         if (m->st[i]) cudaStreamDestroy(m->st[i]);
         siIndexDestroy(m->ix[i]);
     }

@@ -468,6 +468,18 @@ constexpr uint32_t QC_TILE = QC_THREADS * QC_PER_THREAD;
 
 struct __align__(32) CellRec { uint32_t w[8]; };
 
+// Fused count + all-gather: besides its own output a count kernel stores every count into up to
+// SI_FANOUT_MAX further arrays at the same index -- the other GPUs' copies of the gathered count vector, written over
+// NVLink as peer stores while the kernel is still ranking (no separate collective pass). n == 0: plain kernel.
+constexpr int SI_FANOUT_MAX = 15;
+struct Fanout { uint32_t* p[SI_FANOUT_MAX]; int n; };
+template <typename CountT>
+__device__ __forceinline__ void fan_store(const Fanout& fan, uint64_t at, uint32_t c) {
+    if (sizeof(CountT) == 4) {
+        for (int k = 0; k < fan.n; ++k) st_stream(fan.p[k] + at, c);
+    }
+}
+
 // L2 eviction policies (SIB_QC_HINTS): the rank cells should stay in L2 (evict_last) while the
 // query / count streams pass through (evict_first).
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
@@ -590,7 +602,7 @@ __device__ __forceinline__ uint32_t cells_rank_lt(const RankCells& rc, const int
 // one tile of QC_TILE queries starting at `base` (whole CTA)
 template <typename CountT>
 __device__ __forceinline__ void count_cells_tile(const IndexView& ix, const QueryRecords& rec, uint64_t base, uint32_t nq,
-                                                 CountT* __restrict__ counts) {
+                                                 CountT* __restrict__ counts, const Fanout& fan) {
     const uint32_t tid = threadIdx.x;
     const RankCells cs = ix.cells_s, ce = ix.cells_e;
 #ifdef SIB_QC_HINTS
@@ -646,12 +658,18 @@ __device__ __forceinline__ void count_cells_tile(const IndexView& ix, const Quer
         }
         const uint64_t t = base + (uint64_t)j * QC_THREADS + tid;
         if (live[j]) {
-            if (rec.idx) counts[ld_stream(rec.idx + t)] = (CountT)c;
+            if (rec.idx) {
+                const uint32_t at = ld_stream(rec.idx + t);
+                counts[at] = (CountT)c;
+                fan_store<CountT>(fan, at, c);
+            } else {
 #ifdef SIB_QC_HINTS
-            else st_stream_hint(counts + t, (CountT)c, pol_pass);
+                st_stream_hint(counts + t, (CountT)c, pol_pass);
 #else
-            else st_stream(counts + t, (CountT)c);
+                st_stream(counts + t, (CountT)c);
 #endif
+                fan_store<CountT>(fan, t, c);
+            }
         }
     }
 }
@@ -661,8 +679,8 @@ __device__ __forceinline__ void count_cells_tile(const IndexView& ix, const Quer
 #endif
 template <typename CountT>
 __global__ void __launch_bounds__(QC_THREADS, SIB_QC_MINBLOCKS)
-qk_count_cells_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __restrict__ counts) {
-    count_cells_tile<CountT>(ix, rec, (uint64_t)blockIdx.x * QC_TILE, nq, counts);
+qk_count_cells_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __restrict__ counts, const __grid_constant__ Fanout fan) {
+    count_cells_tile<CountT>(ix, rec, (uint64_t)blockIdx.x * QC_TILE, nq, counts, fan);
 }
 
 // ---- count of a MIXED batch over several indexes (mode B: one index per contig) -----------------------
@@ -696,8 +714,11 @@ __device__ __noinline__ uint32_t walk_scalar(const int32_t* __restrict__ ends, c
 
 // Persistent CTAs (grid = what the device holds): the table is staged once per CTA, tiles are taken grid-stride, and the
 // per-contig hit totals (for the CSR bases of mode B) are summed in shared memory and flushed once per CTA.
+#ifndef SIB_QM_MINBLOCKS
+#define SIB_QM_MINBLOCKS 5
+#endif
 template <typename CountT>
-__global__ void __launch_bounds__(QC_THREADS, SIB_QC_MINBLOCKS)
+__global__ void __launch_bounds__(QC_THREADS, SIB_QM_MINBLOCKS)
 qk_count_mixed_kernel(const MixedEntry* __restrict__ table, uint32_t n_contigs, const int32_t* __restrict__ contig,
                       const int32_t* __restrict__ qs_in, const int32_t* __restrict__ qe_in, uint32_t nq, CountT* __restrict__ counts,
                       unsigned long long* __restrict__ totals) {

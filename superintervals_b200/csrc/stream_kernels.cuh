@@ -148,7 +148,7 @@ template <typename CountT>
 __global__ void __launch_bounds__(SK_THREADS, SIB_SK_MINBLOCKS)
 sk_count_stream_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* __restrict__ qe_in, uint32_t nq,
                        CountT* __restrict__ counts, uint32_t vec_ok, uint32_t ntiles, uint32_t* __restrict__ fail_list,
-                       uint32_t* __restrict__ fail_count) {
+                       uint32_t* __restrict__ fail_count, const __grid_constant__ Fanout fan) {
     extern __shared__ __align__(128) unsigned char sk_sh[];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ uint32_t s_red[2][SK_WARPS][5];
@@ -255,10 +255,12 @@ sk_count_stream_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const in
         const uint64_t base = (uint64_t)t * SK_TILE + (uint64_t)tid * SK_PER_THREAD;
         if (base + SK_PER_THREAD <= nq && vec_ok) {
             sk_st8(counts + base, c);
+            if (sizeof(CountT) == 4)
+                for (int f = 0; f < fan.n; ++f) sk_st8(fan.p[f] + base, c);      // peer copies of the gathered vector (vec_ok covers them)
         } else {
 #pragma unroll
             for (int j = 0; j < SK_PER_THREAD; ++j)
-                if (base + j < nq) counts[base + j] = (CountT)c[j];
+                if (base + j < nq) { counts[base + j] = (CountT)c[j]; fan_store<CountT>(fan, base + j, c[j]); }
         }
     };
 
@@ -293,13 +295,13 @@ template <typename CountT>
 __global__ void __launch_bounds__(QC_THREADS)
 sk_count_failed_tiles_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* __restrict__ qe_in, uint32_t nq,
                              CountT* __restrict__ counts, const uint32_t* __restrict__ fail_list,
-                             const uint32_t* __restrict__ fail_count) {
+                             const uint32_t* __restrict__ fail_count, const __grid_constant__ Fanout fan) {
     const uint32_t nfail = *fail_count;
     const QueryRecords rec{qs_in, qe_in, nullptr};
     constexpr uint32_t PARTS = SK_TILE / QC_TILE;
     for (uint32_t w = blockIdx.x; w < nfail * PARTS; w += gridDim.x) {
         const uint64_t base = (uint64_t)fail_list[w / PARTS] * SK_TILE + (uint64_t)(w % PARTS) * QC_TILE;
-        if (base < nq) count_cells_tile<CountT>(ix, rec, base, nq, counts);
+        if (base < nq) count_cells_tile<CountT>(ix, rec, base, nq, counts, fan);
     }
 }
 

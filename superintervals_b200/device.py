@@ -110,6 +110,16 @@ class DeviceIndex:
         _lib.check("siCountDevice")
         return out
 
+    def count_fanout(self, qs, qe, out, peer_ptrs, order=ORDER_AUTO):
+        """count() that also stores every count at the same index of the arrays at `peer_ptrs` (raw device addresses,
+        at most 15: other GPUs' copies of a gathered count vector -- siCountFanoutDevice, the fused count + all-gather)."""
+        _chk_i32(qs, "qs"); _chk_i32(qe, "qe")
+        n = qs.numel()
+        arr = (C.c_void_p * max(1, len(peer_ptrs)))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        self._L.siCountFanoutDevice(self._ix, qs.data_ptr(), qe.data_ptr(), n, out.data_ptr(), arr, len(peer_ptrs), order, _stream())
+        _lib.check("siCountFanoutDevice")
+        return out
+
     def sort_queries(self, qs, qe):
         """Explicit first half of an ORDER_UNSORTED count (see siSortQueriesDevice)."""
         _chk_i32(qs, "qs"); _chk_i32(qe, "qe")

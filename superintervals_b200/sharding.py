@@ -22,7 +22,7 @@ import torch.distributed as dist
 
 from .workloads import lpt_assign, shard_range
 
-__all__ = ["shard_range", "lpt_assign", "csr_shard_bases", "gather_counts", "assign_contigs"]
+__all__ = ["shard_range", "lpt_assign", "csr_shard_bases", "gather_counts", "assign_contigs", "PeerGathered"]
 
 
 def csr_shard_bases(local_total_hits: int, device=None, group=None):
@@ -60,3 +60,114 @@ def assign_contigs(n_intervals, n_queries, world):
     """Mode B: owner rank of every contig, LPT on (N_c + Q_c)."""
     cost = np.asarray(n_intervals, np.float64) + np.asarray(n_queries, np.float64)
     return lpt_assign(cost, world)
+
+
+class PeerGathered:
+    """Count vectors gathered WITHOUT a collective: two int32 arrays of `world * per` entries (double buffer) plus one
+    flag word per rank on every GPU, each GPU's block mapped into every other rank's address space (CUDA IPC over
+    NVLink peer access; siIpcAlloc / siIpcOpen). Rank r's count kernel stores its slot [r * per, (r + 1) * per) into
+    EVERY copy itself (siCountFanoutDevice), then a one-warp kernel signals and awaits the peers' flags
+    (siPeerBarrierDevice): "count, then all_gather of the counts" is one count kernel + one barrier kernel.
+    Steps alternate between the two arrays, so a fast rank's stores of step k+1 never land in an array a slower rank
+    is still reading for step k (it cannot pass step k+1's barrier, hence cannot start step k+2, before that rank has
+    finished step k). Collective: every rank of the group constructs it; close() before the process group goes away."""
+
+    def __init__(self, per, world, rank, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        if world - 1 > 15:
+            raise ValueError("at most 16 ranks")
+        self._L, self._lib, self._C = _lib.lib(), _lib, C
+        self.per, self.world, self.rank = int(per), int(world), int(rank)
+        self.n = self.per * self.world
+        self._flag_off = 2 * self.n * 4                     # bytes: [array 0][array 1][flags: world words][timed_out word]
+        total = self._flag_off + 4 * (world + 1)
+        total = (total + 255) & ~255
+        def agreed(ok, what):       # every rank learns whether every rank succeeded: a failure must not leave the others in a collective
+            t = torch.tensor([1.0 if ok else 0.0], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            if t.item() < 1.0:
+                _lib.lib().si_b200_clear_error()
+                raise RuntimeError(f"PeerGathered: {what} failed on at least one rank")
+
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        rc = self._L.siIpcAlloc(total, C.byref(ptr), handle)
+        self._own = ptr.value if rc == 0 else None
+        self._peers = {}
+        try:
+            agreed(rc == 0, "siIpcAlloc (cudaMalloc + cudaIpcGetMemHandle)")
+        except RuntimeError:
+            if self._own:
+                self._L.siIpcFree(self._own)
+            raise
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+        allh = torch.empty(world * 64, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        allh = allh.cpu().numpy()
+        opened = True
+        for r in range(world):
+            if r == rank:
+                continue
+            p = C.c_void_p()
+            hb = (C.c_ubyte * 64)(*allh[r * 64:(r + 1) * 64].tolist())
+            if self._L.siIpcOpen(hb, C.byref(p)) != 0:
+                opened = False
+                break
+            self._peers[r] = p.value
+        try:
+            agreed(opened, "siIpcOpen (cudaIpcOpenMemHandle: peer access between the GPUs)")
+        except RuntimeError:
+            for p in self._peers.values():
+                self._L.siIpcClose(p)
+            self._L.siIpcFree(self._own)
+            raise
+
+        class _Raw:   # __cuda_array_interface__ view of the cudaMalloc'ed block
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (total // 4,), "typestr": "<i4", "data": (self._own, False), "version": 3, "strides": None}
+        self._raw = raw
+        self._all = torch.as_tensor(raw, device="cuda")
+        self._all.zero_()
+        self.arrays = [self._all[:self.n], self._all[self.n:2 * self.n]]
+        self._timed_out = self._all[2 * self.n + world: 2 * self.n + world + 1]
+        order = sorted(self._peers)
+        self._signal = (C.c_void_p * max(1, len(order)))(*[C.c_void_p(self._peers[r] + self._flag_off + 4 * rank) for r in order])
+        self._wait = (C.c_void_p * max(1, len(order)))(*[C.c_void_p(self._own + self._flag_off + 4 * r) for r in order])
+        self._order = order
+        self.step = 0
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+
+    def current(self):
+        """(this step's gathered array, this rank's slot in it, addresses of this slot in the peers' copies)"""
+        b = self.step & 1
+        arr = self.arrays[b]
+        slot = arr[self.rank * self.per:(self.rank + 1) * self.per]
+        ptrs = [self._peers[r] + 4 * (b * self.n + self.rank * self.per) for r in self._order]
+        return arr, slot, ptrs
+
+    def barrier(self):
+        """Stream-ordered: returns (on the stream) once every peer's stores of this step have landed; advances the step."""
+        import torch
+        self.step += 1
+        self._L.siPeerBarrierDevice(self._signal, self._wait, len(self._order), self.step, self._timed_out.data_ptr(),
+                                    self._C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        self._lib.check("siPeerBarrierDevice")
+
+    def timed_out(self):
+        return bool(int(self._timed_out.item()))
+
+    def close(self):
+        import torch
+        torch.cuda.synchronize()
+        for p in self._peers.values():
+            self._L.siIpcClose(p)
+        self._peers = {}
+        self._all = self.arrays = self._timed_out = None
+        if self._own:
+            self._L.siIpcFree(self._own)
+            self._own = None

@@ -229,3 +229,50 @@ def test_narrow_sort_with_tie_fix_builds_the_same_arrays_as_the_composite_key(ca
     gs, ge, gv, gb, gp = ix.export()
     assert np.array_equal(gs, orc.starts) and np.array_equal(ge, orc.ends)
     assert np.array_equal(gv, orc.data) and np.array_equal(gb, orc.branch)
+
+
+@pytest.mark.parametrize("mode", ["cells_shuffled", "stream_sorted", "partitioned", "walk_fallback", "empty_index"])
+def test_count_fanout_stores_every_count_into_the_extra_arrays(mode):
+    """siCountFanoutDevice (the fused count + all-gather): besides its own output the count kernel stores every count at
+    the same index of the extra arrays -- here two more arrays on the same GPU, at an offset like a slot of a gathered vector."""
+    import torch
+    from oracle.pyoracle import Oracle
+    from superintervals_b200.device import (DeviceIndex, ORDER_SORTED, ORDER_UNSORTED, OPT_COUNT_ALGO, COUNT_WALK,
+                                            OPT_CELLS_DIRECT_BYTES)
+    s, e, qs, qe = W.config2(60_000, 70_001, 3, axis=3_000_000)
+    if mode == "empty_index":
+        s, e = s[:0], e[:0]
+    order = ORDER_UNSORTED
+    if mode == "stream_sorted":
+        o = np.argsort(qs, kind="stable"); qs, qe = qs[o], qe[o]
+        order = ORDER_SORTED
+    ix = DeviceIndex().build(torch.from_numpy(s).cuda(), torch.from_numpy(e).cuda())
+    if mode == "walk_fallback":
+        ix.set_option(OPT_COUNT_ALGO, COUNT_WALK)
+    if mode == "partitioned":
+        ix.set_option(OPT_CELLS_DIRECT_BYTES, 1)
+    n = qs.size
+    own = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    extra = torch.full((2, n + 64), -1, dtype=torch.int32, device="cuda")
+    ptrs = [extra[0, 8:].data_ptr(), extra[1, 40:].data_ptr()]
+    ix.count_fanout(torch.from_numpy(qs).cuda(), torch.from_numpy(qe).cuda(), own, ptrs, order=order)
+    torch.cuda.synchronize()
+    want = Oracle(s, e).count_batch(qs, qe).astype(np.int64) if s.size else np.zeros(n, np.int64)
+    assert np.array_equal(own.cpu().numpy().astype(np.int64), want)
+    assert np.array_equal(extra[0, 8:8 + n].cpu().numpy().astype(np.int64), want)
+    assert np.array_equal(extra[1, 40:40 + n].cpu().numpy().astype(np.int64), want)
+    assert (extra[0, :8] == -1).all() and (extra[0, 8 + n:] == -1).all() and (extra[1, :40] == -1).all() and (extra[1, 40 + n:] == -1).all()
+
+
+def test_peer_barrier_kernel_signals_waits_and_times_out_instead_of_hanging():
+    import ctypes as C
+    import torch
+    from superintervals_b200 import _lib
+    L = _lib.lib()
+    flags = torch.zeros(8, dtype=torch.int32, device="cuda")
+    # a "peer" on the same GPU: the word signalled is the word awaited
+    sig = (C.c_void_p * 2)(C.c_void_p(flags[0:].data_ptr()), C.c_void_p(flags[1:].data_ptr()))
+    for seq in (1, 2, 3):
+        assert L.siPeerBarrierDevice(sig, sig, 2, seq, flags[7:].data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    assert flags.cpu().tolist() == [3, 3, 0, 0, 0, 0, 0, 0]

@@ -49,3 +49,55 @@ def test_c_program_drives_the_multi_device_entry_points():
     out = subprocess.run([EXE, "0", "200000", "500003"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "mismatches 0" in out.stdout and "identical offsets and values" in out.stdout and "multi ok" in out.stdout
+
+
+def _fused_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    from oracle.pyoracle import Oracle
+    from superintervals_b200 import workloads as W
+    from superintervals_b200.device import DeviceIndex, ORDER_UNSORTED
+    from superintervals_b200.sharding import PeerGathered
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    s, e, qs, qe = W.config2(50_000, 200_003, 5, axis=2_000_000)
+    ix = DeviceIndex().build(torch.from_numpy(s).cuda(), torch.from_numpy(e).cuda())
+    nq = qs.size
+    per = (((nq + world - 1) // world) + 7) & ~7
+    lo = min(nq, rank * per); hi = min(nq, lo + per); m = hi - lo
+    mqs, mqe = torch.from_numpy(qs[lo:hi]).cuda(), torch.from_numpy(qe[lo:hi]).cuda()
+    pg = PeerGathered(per, world, rank)
+    ok = True
+    want = Oracle(s, e).count_batch(qs, qe).astype(np.int64)
+    for step in range(4):                      # both halves of the double buffer, twice
+        arr, slot, ptrs = pg.current()
+        ix.count_fanout(mqs, mqe, slot[:m], ptrs, order=ORDER_UNSORTED)
+        pg.barrier()
+        torch.cuda.synchronize()
+        got = torch.cat([arr[r * per: r * per + max(0, min(nq, (r + 1) * per) - r * per)] for r in range(world)]).cpu().numpy()
+        ok &= bool(np.array_equal(got.astype(np.int64), want))
+    ok &= not pg.timed_out()
+    pg.close()
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_fused_count_and_all_gather_over_peer_memory_two_processes():
+    """One process per GPU (torchrun's layout): each rank's count kernel stores its slot of the gathered count vector into
+    every GPU's copy (CUDA IPC peer memory over NVLink), a one-warp kernel exchanges flags; every rank then holds the
+    whole batch's counts -- equal to the oracle's. Needs two GPUs."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0)); port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        out = mgr.dict()
+        procs = [ctx.Process(target=_fused_worker, args=(r, 2, port, out)) for r in range(2)]
+        for p in procs: p.start()
+        for p in procs: p.join(240)
+        assert all(p.exitcode == 0 for p in procs)
+        assert dict(out) == {0: True, 1: True}
