@@ -35,8 +35,17 @@ struct RsPassInfo {
 };
 
 template <typename KeyT> struct RsTraits;
-template <> struct RsTraits<uint32_t> { static constexpr int ITEMS = 18; };
-template <> struct RsTraits<uint64_t> { static constexpr int ITEMS = 14; };
+#ifndef SIB_RS_ITEMS32
+#define SIB_RS_ITEMS32 18
+#endif
+#ifndef SIB_RS_ITEMS64
+#define SIB_RS_ITEMS64 14
+#endif
+#ifndef SIB_RS_MINBLOCKS
+#define SIB_RS_MINBLOCKS 1
+#endif
+template <> struct RsTraits<uint32_t> { static constexpr int ITEMS = SIB_RS_ITEMS32; };
+template <> struct RsTraits<uint64_t> { static constexpr int ITEMS = SIB_RS_ITEMS64; };
 
 struct RsWorkspace {
     uint32_t* hist;        // [RS_MAX_PASSES][256] counts, turned into exclusive scans in place
@@ -132,7 +141,7 @@ rs_prepare_kernel(uint32_t* __restrict__ hist, RsPassInfo* __restrict__ info,
 
 // ---- 3. onesweep pass --------------------------------------------------------------
 template <typename KeyT, bool VALS>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, SIB_RS_MINBLOCKS)
 rs_onesweep_kernel(KeyT* __restrict__ kA, KeyT* __restrict__ kB,
                    uint32_t* __restrict__ vA, uint32_t* __restrict__ vB, uint32_t n, int pass,
                    const uint32_t* __restrict__ gbase_all, const RsPassInfo* __restrict__ info,

@@ -92,6 +92,21 @@ elif what == "c5":
     res["sorted_ms"] = timed(lambda: ix.count(sq, sq, out=c_dir, order=ORDER_SORTED), 5)
     res["sorted_kernels"] = kernels(ix, 5)
     res["bits"] = ix.bits_info()
+elif what == "mixed":
+    import numpy as np
+    from superintervals_b200.genome import GenomeIndex
+    gi = GenomeIndex([f"c{i}" for i in range(8)], [2_000_000] * 8, rank=0, world=1)
+    for c in range(8):
+        s, e = W.config2_intervals(2_000_000, 20 + c, axis=50_000_000)
+        gi.build_contig(c, torch.from_numpy(s).cuda(), torch.from_numpy(e).cuda())
+    qs, qe = W.config2_queries(64_000_000, 3, axis=50_000_000)
+    cid = torch.from_numpy(np.random.default_rng(1).integers(0, 8, qs.size).astype(np.int32)).cuda()
+    dqs, dqe = torch.from_numpy(qs).cuda(), torch.from_numpy(qe).cuda()
+    for _ in range(3):
+        out = gi.count_mixed(cid, dqs, dqe)
+    res["mixed_ms"] = timed(lambda: gi.count_mixed(cid, dqs, dqe), 10)
+    res["hits"] = int(out.long().sum().item())
+    res["lib"] = os.environ.get("SIB_LIBRARY")
 else:
     s, e = W.config2_intervals(10_000_000, 2)
     ds, de = torch.from_numpy(s).cuda(), torch.from_numpy(e).cuda()
