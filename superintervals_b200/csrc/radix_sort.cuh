@@ -35,8 +35,13 @@ struct RsPassInfo {
 };
 
 template <typename KeyT> struct RsTraits;
+// 32-bit keys: 12 items per thread at 4 CTAs/SM (64 registers, no spills) measured best on the 10 M-interval build
+// (tools/gpu_r02l.sh: 1.95 ms against 2.07-2.20 ms for 18 items at 2 CTAs/SM); the pass is latency-bound, not bandwidth-bound
 #ifndef SIB_RS_ITEMS32
-#define SIB_RS_ITEMS32 18
+#define SIB_RS_ITEMS32 12
+#endif
+#ifndef SIB_RS_MINBLOCKS32
+#define SIB_RS_MINBLOCKS32 4
 #endif
 #ifndef SIB_RS_ITEMS64
 #define SIB_RS_ITEMS64 14
@@ -44,8 +49,8 @@ template <typename KeyT> struct RsTraits;
 #ifndef SIB_RS_MINBLOCKS
 #define SIB_RS_MINBLOCKS 1
 #endif
-template <> struct RsTraits<uint32_t> { static constexpr int ITEMS = SIB_RS_ITEMS32; };
-template <> struct RsTraits<uint64_t> { static constexpr int ITEMS = SIB_RS_ITEMS64; };
+template <> struct RsTraits<uint32_t> { static constexpr int ITEMS = SIB_RS_ITEMS32; static constexpr int MINB = SIB_RS_MINBLOCKS32; };
+template <> struct RsTraits<uint64_t> { static constexpr int ITEMS = SIB_RS_ITEMS64; static constexpr int MINB = SIB_RS_MINBLOCKS; };
 
 struct RsWorkspace {
     uint32_t* hist;        // [RS_MAX_PASSES][256] counts, turned into exclusive scans in place
@@ -141,7 +146,7 @@ rs_prepare_kernel(uint32_t* __restrict__ hist, RsPassInfo* __restrict__ info,
 
 // ---- 3. onesweep pass --------------------------------------------------------------
 template <typename KeyT, bool VALS>
-__global__ void __launch_bounds__(RS_THREADS, SIB_RS_MINBLOCKS)
+__global__ void __launch_bounds__(RS_THREADS, RsTraits<KeyT>::MINB)
 rs_onesweep_kernel(KeyT* __restrict__ kA, KeyT* __restrict__ kB,
                    uint32_t* __restrict__ vA, uint32_t* __restrict__ vB, uint32_t n, int pass,
                    const uint32_t* __restrict__ gbase_all, const RsPassInfo* __restrict__ info,
