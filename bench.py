@@ -698,9 +698,13 @@ def bench_strong(a, torch, dist, L, _lib, ix, world, rank, d_qs, d_qe, counts_ra
     if rank == 0:
         got = torch.cat([gathered[r * per: r * per + max(0, min(nq, (r + 1) * per) - r * per)] for r in range(world)])
         ok = bool(torch.equal(got, counts_rank0)) and int(offsets[world * per].item()) == int(counts_rank0.to(torch.int64).sum().item())
+    use_fused = bool(fused and fused.get("equals_nccl_gather_on_every_gpu"))
     return {"scaling": "strong", "queries": nq, "queries_per_gpu": per,
+            "value": fused["value"] if use_fused else nq / (res["count_gather"] * 1e-3), "unit": UNIT,
+            "value_is": ("count fused with the all-gather of the counts (peer stores over NVLink, see fused)" if use_fused
+                         else "count, then ncclAllGather of the counts"),
             "ms_count_only": res["count_only"], "ms_count_gather": res["count_gather"], "ms_count_gather_scan": res["count_gather_scan"],
-            "value_count_only": nq / (res["count_only"] * 1e-3), "value": nq / (res["count_gather"] * 1e-3), "unit": UNIT,
+            "value_count_only": nq / (res["count_only"] * 1e-3), "value_nccl": nq / (res["count_gather"] * 1e-3),
             "collective": "ncclAllGather of the per-query uint32 counts, in place (each GPU's count kernel writes its slot of the gathered vector)",
             "nccl_bytes_received_per_gpu_per_step": 4 * per * (world - 1),
             "nccl_bytes_per_step_all_gpus": 4 * per * (world - 1) * world,
