@@ -27,6 +27,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits.h>
+#include <string>
 #include <vector>
 
 using namespace sib;
@@ -175,17 +176,30 @@ bd_parse(const char* __restrict__ text, uint64_t bytes, const uint64_t* __restri
 
 // ids[slot] = contig id of the chrom in that table slot (host-assigned, order of first appearance)
 __global__ void __launch_bounds__(BD_THREADS)
+// A contig is identified by the 64-bit hash of its name; that the NAME is the same is verified here, byte for byte against
+// the name the host took from the contig's first line (names: name k at names + name_at[k], name_at[k + 1] - name_at[k]
+// bytes), so that two names sharing a hash are reported (*collision) instead of silently merged.
 bd_finish(const unsigned long long* __restrict__ hash, const int32_t* __restrict__ starts, const int32_t* __restrict__ ends,
           const uint32_t* __restrict__ valid, const uint64_t* __restrict__ off, uint64_t lines,
           const ChromSlot* __restrict__ table, const int32_t* __restrict__ ids, int32_t* __restrict__ out_c,
-          int32_t* __restrict__ out_s, int32_t* __restrict__ out_e) {
+          int32_t* __restrict__ out_s, int32_t* __restrict__ out_e, const char* __restrict__ text,
+          const uint64_t* __restrict__ line_at, const char* __restrict__ names, const uint32_t* __restrict__ name_at,
+          uint32_t* __restrict__ collision) {
     const uint64_t l = (uint64_t)blockIdx.x * BD_THREADS + threadIdx.x;
     if (l >= lines || !valid[l]) return;
     const unsigned long long h = hash[l];
     uint32_t slot = (uint32_t)(h ^ (h >> 32)) & (BD_TABLE - 1);
     while (table[slot].hash != h) slot = (slot + 1) & (BD_TABLE - 1);
     const uint64_t o = off[l];
-    out_c[o] = ids[slot];
+    const int32_t id = ids[slot];
+    {
+        const uint32_t a = name_at[id], len = name_at[id + 1] - a;
+        const char* t = text + line_at[l];
+        bool same = t[len] == '\t';                                    // a valid line has a tab after its chrom
+        for (uint32_t k = 0; k < len && same; ++k) same = t[k] == names[a + k];
+        if (!same) *collision = 1u;
+    }
+    out_c[o] = id;
     out_s[o] = starts[l];
     out_e[o] = ends[l];
 }
@@ -217,7 +231,7 @@ __global__ void bd_contig_offsets_kernel(const int32_t* __restrict__ gc, uint64_
 }
 
 struct Bufs {
-    DevBuf b[20];
+    DevBuf b[22];
     ~Bufs() { for (auto& x : b) x.release(); }
 };
 
@@ -301,8 +315,24 @@ int parse_impl(siIndex* ix, const char* text, size_t bytes, int normalize, int e
     if (n == 0) return 0;
     if (ids.ensure((size_t)BD_TABLE * 4) || oc.ensure(n * 4) || os.ensure(n * 4) || oe.ensure(n * 4)) return last_error_code();
     SIB_CHECK(cudaMemcpyAsync(ids.p, h_ids.data(), (size_t)BD_TABLE * 4, cudaMemcpyHostToDevice, st));
+    // the names on the device, for bd_finish's byte-for-byte check of every line's chrom against its contig's name
+    std::vector<uint32_t> h_name_at(seen.size() + 1, 0);
+    std::string blob;
+    for (size_t k = 0; k < seen.size(); ++k) { h_name_at[k] = (uint32_t)blob.size(); blob += out->names[k]; }
+    h_name_at[seen.size()] = (uint32_t)blob.size();
+    DevBuf &d_names = B.b[19], &d_name_at = B.b[20];
+    if (d_names.ensure(blob.size() + 16) || d_name_at.ensure(h_name_at.size() * 4)) return last_error_code();
+    SIB_CHECK(cudaMemcpyAsync(d_names.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
+    SIB_CHECK(cudaMemcpyAsync(d_name_at.p, h_name_at.data(), h_name_at.size() * 4, cudaMemcpyHostToDevice, st));
+    uint32_t* d_collision = d_full + 1;
+    SIB_CHECK(cudaMemsetAsync(d_collision, 0, 4, st));
     BD_LAUNCH(bd_finish, lines, st, hash.as<unsigned long long>(), ds.as<int32_t>(), de.as<int32_t>(), valid.as<uint32_t>(),
-              voff.as<uint64_t>(), lines, table.as<ChromSlot>(), ids.as<int32_t>(), oc.as<int32_t>(), os.as<int32_t>(), oe.as<int32_t>());
+              voff.as<uint64_t>(), lines, table.as<ChromSlot>(), ids.as<int32_t>(), oc.as<int32_t>(), os.as<int32_t>(), oe.as<int32_t>(),
+              dt, line_at.as<uint64_t>(), d_names.as<char>(), d_name_at.as<uint32_t>(), d_collision);
+    uint32_t collided = 0;
+    SIB_CHECK(cudaMemcpyAsync(&collided, d_collision, 4, cudaMemcpyDeviceToHost, st));
+    SIB_CHECK(cudaStreamSynchronize(st));
+    if (collided) { set_error_msg(cudaErrorInvalidValue, "siParseBed: two contig names share a 64-bit hash (not merged: rename one)"); return cudaErrorInvalidValue; }
     const void *fc = oc.p, *fs = os.p, *fe = oe.p;
     if (group) {
         // per-contig containers (bed-intersect-si.rs:100-123): a stable sort of the record numbers by

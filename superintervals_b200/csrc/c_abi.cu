@@ -22,8 +22,9 @@
 #include <unordered_map>
 #include <vector>
 
-extern "C" int si_b200_upper_bound_(siIndex* ix, int32_t value, uint32_t* mailbox_word, size_t* out);
-extern "C" int si_b200_single_search_(siIndex* ix, int32_t qs, int32_t qe, int what, uint32_t cap, unsigned long long* found, void* out);
+extern "C" int si_b200_single_scalar_(siIndex* ix, int op, int32_t a, int32_t b, uint32_t* out32, unsigned long long* out64, uint32_t* done);
+extern "C" int si_b200_single_search_(siIndex* ix, int32_t qs, int32_t qe, int what, uint32_t cap, unsigned long long* found, void* out,
+                                      uint32_t* done);
 extern "C" int si_b200_resolve_order_(siIndex* ix, const int32_t* d_qs, size_t n, void* stream);
 
 namespace sib {
@@ -255,6 +256,7 @@ struct Mailbox {
     uint32_t ub, any;                     // upperBound / anyOverlaps answers
     unsigned long long count;             // countOverlaps (64-bit count kernels), search: hits found
     uint32_t cov_count; int32_t cov;      // coverage
+    uint32_t done;                        // sequence number of the last call whose answer is complete (written last by its kernel)
     alignas(32) unsigned char out[1];     // search results (MAILBOX_OUT_BYTES)
 };
 constexpr size_t MAILBOX_OUT_BYTES = (size_t)192 << 10;   // 16 K Interval records / 48 K values; longer lists take the batch path
@@ -279,7 +281,7 @@ int search_single(Handle* h, int32_t qs, int32_t qe, R* found, int what, size_t 
     Mailbox* mb = mailbox_of(ix);
     if (!mb) return last_error_code();
     const uint32_t cap = (uint32_t)(MAILBOX_OUT_BYTES / elem);
-    int rc = si_b200_single_search_(ix, qs, qe, what, cap, &mb->count, mb->out);
+    int rc = si_b200_single_search_(ix, qs, qe, what, cap, &mb->count, mb->out, &mb->done);
     if (rc) return rc;
     const size_t total = (size_t)*reinterpret_cast<volatile unsigned long long*>(&mb->count);
     if (total > cap) return -1;
@@ -632,7 +634,12 @@ size_t upperBound(cSuperIntervals* si, int32_t value) {
     size_t r = SI_NONE;
     if (si->size != 0 && handle_ready(h, "upperBound")) {
         std::lock_guard<std::mutex> lk(h->ix->api_mu);
-        if (Mailbox* mb = mailbox_of(h->ix)) si_b200_upper_bound_(h->ix, value, &mb->ub, &r);
+        if (h->ix->n != 0)
+            if (Mailbox* mb = mailbox_of(h->ix))
+                if (si_b200_single_scalar_(h->ix, 0, value, 0, &mb->ub, &mb->count, &mb->done) == 0) {
+                    const uint32_t u = *reinterpret_cast<volatile uint32_t*>(&mb->ub);
+                    r = u == 0xFFFFFFFFu ? SI_NONE : (size_t)u;
+                }
     }
     si->idx = r;   // ref:539,562,566
     return r;
@@ -645,10 +652,8 @@ bool anyOverlaps(cSuperIntervals* si, int32_t start, int32_t end) {
     std::lock_guard<std::mutex> lk(ix->api_mu);
     Mailbox* mb = mailbox_of(ix);
     if (!mb) return false;
-    mb->qs = start; mb->qe = end;
-    if (siAnyDevice(ix, &mb->qs, &mb->qe, 1, reinterpret_cast<uint8_t*>(&mb->any), ix->own_stream)) return false;
-    if (cudaStreamSynchronize(ix->own_stream) != cudaSuccess) { set_error(cudaGetLastError(), "anyOverlaps", __FILE__, __LINE__); return false; }
-    return *reinterpret_cast<volatile uint8_t*>(&mb->any) != 0;
+    if (si_b200_single_scalar_(ix, 1, start, end, &mb->any, &mb->count, &mb->done)) return false;
+    return *reinterpret_cast<volatile uint32_t*>(&mb->any) != 0;
 }
 
 size_t countOverlaps(cSuperIntervals* si, int32_t start, int32_t end) {
@@ -658,10 +663,7 @@ size_t countOverlaps(cSuperIntervals* si, int32_t start, int32_t end) {
     std::lock_guard<std::mutex> lk(ix->api_mu);
     Mailbox* mb = mailbox_of(ix);
     if (!mb) return 0;
-    mb->qs = start; mb->qe = end;
-    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "LP64 only");
-    if (siCountDevice64(ix, &mb->qs, &mb->qe, 1, reinterpret_cast<uint64_t*>(&mb->count), SI_ORDER_ASIS, ix->own_stream)) return 0;
-    if (cudaStreamSynchronize(ix->own_stream) != cudaSuccess) { set_error(cudaGetLastError(), "countOverlaps", __FILE__, __LINE__); return 0; }
+    if (si_b200_single_scalar_(ix, 2, start, end, &mb->any, &mb->count, &mb->done)) return 0;
     return (size_t)*reinterpret_cast<volatile unsigned long long*>(&mb->count);
 }
 

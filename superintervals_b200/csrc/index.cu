@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1430,9 +1431,24 @@ int si_b200_resolve_order_(siIndex* ix, const int32_t* d_qs, size_t n, void* str
     return o;
 }
 
-// used by c_abi.cu for the single-query search calls: one launch, the query as kernel parameters, hits written to
-// `out` (device-visible memory: the handle's mapped pinned mailbox), *found = all hits (cap bounds what was written)
-int si_b200_single_search_(siIndex* ix, int32_t qs, int32_t qe, int what, uint32_t cap, unsigned long long* found, void* out) {
+// Single-query calls (c_abi.cu): one launch, the query as kernel parameters, the answer written into the handle's mapped
+// pinned mailbox followed by the call's sequence number; the host spins on that word (a few microseconds) instead of a
+// stream synchronise, and synchronises only if it does not show up (which also surfaces a launch or kernel error).
+static int single_wait(siIndex* ix, volatile uint32_t* done, uint32_t seq) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spins = 0; *done != seq; ++spins) {
+        if ((spins & 1023u) == 1023u &&
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() > 5.0) {
+            SIB_CHECK(cudaStreamSynchronize(ix->own_stream));
+            if (*done != seq) { set_error_msg(cudaErrorUnknown, "single-query kernel finished without publishing its answer"); return cudaErrorUnknown; }
+            break;
+        }
+    }
+    return 0;
+}
+
+int si_b200_single_search_(siIndex* ix, int32_t qs, int32_t qe, int what, uint32_t cap, unsigned long long* found, void* out,
+                           uint32_t* done) {
     if (!ix || !ix->built) {
         set_error_msg(cudaErrorNotReady, "single-query search: index not built");
         return cudaErrorNotReady;
@@ -1440,31 +1456,26 @@ int si_b200_single_search_(siIndex* ix, int32_t qs, int32_t qe, int what, uint32
     DeviceGuard g(ix->device);
     cudaStream_t s = ix->own_stream;
     const IndexView v = view_of(ix);
+    const uint32_t seq = ++ix->single_seq;
     switch (what) {
-        case SI_FILL_VALUES: SIB_LAUNCH((qk_single_search_kernel<FILL_VALUES>), 1, 32, 0, s, v, qs, qe, cap, found, reinterpret_cast<int32_t*>(out)); break;
-        case SI_FILL_IDXS: SIB_LAUNCH((qk_single_search_kernel<FILL_IDXS>), 1, 32, 0, s, v, qs, qe, cap, found, reinterpret_cast<uint32_t*>(out)); break;
-        case SI_FILL_KEYS: SIB_LAUNCH((qk_single_search_kernel<FILL_KEYS>), 1, 32, 0, s, v, qs, qe, cap, found, reinterpret_cast<int2*>(out)); break;
-        default: SIB_LAUNCH((qk_single_search_kernel<FILL_ITEMS>), 1, 32, 0, s, v, qs, qe, cap, found, reinterpret_cast<Item3*>(out)); break;
+        case SI_FILL_VALUES: SIB_LAUNCH((qk_single_search_kernel<FILL_VALUES>), 1, 32, 0, s, v, qs, qe, cap, found, reinterpret_cast<int32_t*>(out), done, seq); break;
+        case SI_FILL_IDXS: SIB_LAUNCH((qk_single_search_kernel<FILL_IDXS>), 1, 32, 0, s, v, qs, qe, cap, found, reinterpret_cast<uint32_t*>(out), done, seq); break;
+        case SI_FILL_KEYS: SIB_LAUNCH((qk_single_search_kernel<FILL_KEYS>), 1, 32, 0, s, v, qs, qe, cap, found, reinterpret_cast<int2*>(out), done, seq); break;
+        default: SIB_LAUNCH((qk_single_search_kernel<FILL_ITEMS>), 1, 32, 0, s, v, qs, qe, cap, found, reinterpret_cast<Item3*>(out), done, seq); break;
     }
-    SIB_CHECK(cudaStreamSynchronize(s));
-    return 0;
+    return single_wait(ix, done, seq);
 }
 
-// used by c_abi.cu for the single-query upperBound
-int si_b200_upper_bound_(siIndex* ix, int32_t value, uint32_t* mailbox_word, size_t* out) {
+// op 0: upper_bound(a) -> *out32; 1: has_overlaps(a, b) -> *out32; 2: count(a, b) -> *out64 (all mailbox words)
+int si_b200_single_scalar_(siIndex* ix, int op, int32_t a, int32_t b, uint32_t* out32, unsigned long long* out64, uint32_t* done) {
     if (!ix || !ix->built) {
-        set_error_msg(cudaErrorNotReady, "upperBound: index not built");
+        set_error_msg(cudaErrorNotReady, "single query: index not built");
         return cudaErrorNotReady;
     }
-    *out = SI_NONE;
-    if (ix->n == 0) return 0;
     DeviceGuard g(ix->device);
-    // the kernel writes straight into the handle's mapped pinned mailbox: no copy back
-    SIB_LAUNCH(qk_upper_bound_kernel, 1, 32, 0, ix->own_stream, view_of(ix), value, mailbox_word);
-    SIB_CHECK(cudaStreamSynchronize(ix->own_stream));
-    const uint32_t r = *reinterpret_cast<volatile uint32_t*>(mailbox_word);
-    *out = r == NONE32 ? SI_NONE : (size_t)r;
-    return 0;
+    const uint32_t seq = ++ix->single_seq;
+    SIB_LAUNCH(qk_single_scalar_kernel, 1, 32, 0, ix->own_stream, view_of(ix), op, a, b, out32, out64, done, seq);
+    return single_wait(ix, done, seq);
 }
 
 }  // extern "C"

@@ -145,6 +145,7 @@ struct siIndex {
     // single-query calls (countOverlaps, searchValues ...): a mapped pinned mailbox the kernels read the query from and
     // write the answer to, so that a call is one launch + one stream synchronise (c_abi.cu)
     void* mailbox = nullptr;
+    uint32_t single_seq = 0;                    // sequence number of the last single-query call (published by its kernel when done)
     cudaStream_t s_out2 = nullptr;              // second copy-out stream (offsets travel while the fill runs)
     bool pipe_ready_out = false;
 

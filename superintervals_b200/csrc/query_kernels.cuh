@@ -938,16 +938,52 @@ __device__ __forceinline__ uint32_t warp_count_le(const int32_t* __restrict__ st
     return lo;
 }
 
+// Every single-query kernel ends by publishing the call's sequence number in the mailbox (after a system-scope fence):
+// the host spins on that word in pinned memory instead of paying a stream synchronise.
+__device__ __forceinline__ void single_done(uint32_t* __restrict__ done, uint32_t seq) {
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(done) = seq;
+}
+
+// op 0: upper_bound(a) (hpp:501-516) -> out32; op 1: has_overlaps(a, b), the last candidate only (hpp:865-871, Q1) -> out32;
+// op 2: count(a, b) -> out64: the closed form from the rank cells where the index carries them and a <= b (two sector
+// loads by lane 0), else the reference's walk, 32 intervals per step.
 __global__ void __launch_bounds__(32)
-qk_upper_bound_kernel(IndexView ix, int32_t value, uint32_t* __restrict__ out) {   // hpp:501-516, one warp
-    const uint32_t c = warp_count_le(ix.starts, ix.n, value, lane_id());
-    if (threadIdx.x == 0) *out = c - 1u;                                           // 0 - 1 wraps to NONE32
+qk_single_scalar_kernel(IndexView ix, int op, int32_t a, int32_t b, uint32_t* __restrict__ out32,
+                        unsigned long long* __restrict__ out64, uint32_t* __restrict__ done, uint32_t seq) {
+    const uint32_t lane = lane_id();
+    if (op == 0) {
+        const uint32_t c = warp_count_le(ix.starts, ix.n, a, lane);
+        if (lane == 0) *out32 = c - 1u;                                            // 0 - 1 wraps to NONE32
+    } else if (op == 1) {
+        const uint32_t i = warp_count_le(ix.starts, ix.n, b, lane) - 1u;
+        if (lane == 0) *out32 = (i != NONE32 && a <= ld_nc(ix.ends + i)) ? 1u : 0u;
+    } else if (ix.cells_s.fmt && ix.cells_e.fmt && a <= b) {
+        if (lane == 0) {
+            uint32_t c = cells_rank_lt(ix.cells_s, ix.rstarts, (int64_t)b + 1) - cells_rank_lt(ix.cells_e, ix.eall, (int64_t)a);
+            for (uint32_t k = 0; k < ix.n_mal; ++k) c += (ix.mal_s[k] <= b && ix.mal_e[k] >= a) ? 1u : 0u;
+            *out64 = c;
+        }
+    } else {
+        uint32_t bi = warp_count_le(ix.starts, ix.n, b, lane) - 1u, bo = 0;
+        while (bi != NONE32) {
+            const bool inb = lane <= bi;
+            const bool hit = inb && ld_nc(ix.ends + (bi - lane)) >= a;
+            const uint32_t hm = __ballot_sync(FULL_MASK, hit);
+            bo += __popc(hm);
+            if (bi < 32u) break;
+            const uint32_t low = bi - 31u;
+            bi = (hm >> 31) ? low - 1u : ld_nc(ix.branch + low);
+        }
+        if (lane == 0) *out64 = bo;
+    }
+    if (lane == 0) single_done(done, seq);
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(32)
 qk_single_search_kernel(IndexView ix, int32_t qs, int32_t qe, uint32_t cap, unsigned long long* __restrict__ found,
-                        typename FillOut<MODE>::T* __restrict__ out) {
+                        typename FillOut<MODE>::T* __restrict__ out, uint32_t* __restrict__ done, uint32_t seq) {
     const uint32_t lane = lane_id();
     uint32_t bi = warp_count_le(ix.starts, ix.n, qe, lane) - 1u;      // 0 - 1 wraps to NONE32
     uint32_t bo = 0;
@@ -964,7 +1000,8 @@ qk_single_search_kernel(IndexView ix, int32_t qs, int32_t qe, uint32_t cap, unsi
         const uint32_t low = bi - 31u;
         bi = (hm >> 31) ? low - 1u : ld_nc(ix.branch + low);
     }
-    if (lane == 0) *found = bo;
+    __syncwarp();
+    if (lane == 0) { *found = bo; single_done(done, seq); }
 }
 
 // ---- stab lists: one branch-array walk per checkpoint, at build time ------------------------
