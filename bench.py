@@ -998,7 +998,7 @@ def bench_latency(a, L, _lib, starts, ends, qs, qe):
     t_ctypes = (time.perf_counter() - t0) / k
     out = {"calls": k, "countOverlaps_us": t_count * 1e6, "searchValues_us": t_search * 1e6, "ctypes_call_overhead_us": t_ctypes * 1e6,
            "hits_per_query": tot / k, "count_equals_search_sizes": tot == tot_v,
-           "path": "query as kernel parameters / mapped pinned mailbox, one launch + cudaStreamSynchronize per call (csrc/c_abi.cu)"}
+           "path": "query as kernel parameters / mapped pinned mailbox, one launch per call; the kernel publishes a sequence number after its answer and the host spins on that word (csrc/c_abi.cu)"}
     from oracle.pyoracle import Reference
     if Reference.available():
         ref = Reference(starts, ends)

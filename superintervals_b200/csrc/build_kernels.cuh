@@ -87,6 +87,13 @@ bk_scatter_u32_kernel(const uint32_t* __restrict__ v, const uint32_t* __restrict
     for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i < n; i += stride) out[perm[i]] = v[i];
 }
 
+// uint32 counts -> the size_t of the C ABI, on the device (the copy back then lands in the caller's array directly)
+__global__ void __launch_bounds__(BK_THREADS)
+bk_widen_kernel(const uint32_t* __restrict__ in, uint64_t n, unsigned long long* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * BK_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * BK_THREADS + threadIdx.x; i < n; i += stride) out[i] = in[i];
+}
+
 // ---- key packing: (start asc, end DESC, insertion idx) ------------------------------
 __global__ void __launch_bounds__(BK_THREADS)
 bk_make_keys_kernel(const int32_t* __restrict__ s, const int32_t* __restrict__ e, uint32_t n,

@@ -25,6 +25,7 @@
 extern "C" int si_b200_single_scalar_(siIndex* ix, int op, int32_t a, int32_t b, uint32_t* out32, unsigned long long* out64, uint32_t* done);
 extern "C" int si_b200_single_search_(siIndex* ix, int32_t qs, int32_t qe, int what, uint32_t cap, unsigned long long* found, void* out,
                                       uint32_t* done);
+extern "C" int si_b200_widen_(siIndex* ix, const uint32_t* d_in, size_t n, unsigned long long* d_out, void* stream);
 extern "C" int si_b200_resolve_order_(siIndex* ix, const int32_t* d_qs, size_t n, void* stream);
 
 namespace sib {
@@ -615,17 +616,17 @@ void coverageBatch(cSuperIntervals* si, const int32_t* starts, const int32_t* en
     }
     siIndex* ix = h->ix;
     std::lock_guard<std::mutex> lk(ix->api_mu);
-    if (stage_queries(ix, starts, ends, n) || ix->h_counts.ensure(n * 4) || ix->h_cov.ensure(n * 4)) return;
+    if (stage_queries(ix, starts, ends, n) || ix->h_counts.ensure(n * 4) || ix->h_cov.ensure(n * 4) || ix->h_out.ensure(n * 8)) return;
     if (siCoverageDevice(ix, ix->h_qs.as<int32_t>(), ix->h_qe.as<int32_t>(), n, ix->h_counts.as<uint32_t>(),
                          ix->h_cov.as<int32_t>(), ix->own_stream))
         return;
-    uint32_t* tmp = (uint32_t*)malloc(n * 4);
-    if (cudaMemcpyAsync(tmp, ix->h_counts.p, n * 4, cudaMemcpyDeviceToHost, ix->own_stream) != cudaSuccess ||
+    // the counts are widened to size_t on the device and land in the caller's array directly
+    static_assert(sizeof(size_t) == sizeof(unsigned long long), "LP64 only");
+    if (si_b200_widen_(ix, ix->h_counts.as<uint32_t>(), n, ix->h_out.as<unsigned long long>(), ix->own_stream)) return;
+    if (cudaMemcpyAsync(count_out, ix->h_out.p, n * 8, cudaMemcpyDeviceToHost, ix->own_stream) != cudaSuccess ||
         cudaMemcpyAsync(coverage_out, ix->h_cov.p, n * 4, cudaMemcpyDeviceToHost, ix->own_stream) != cudaSuccess ||
         cudaStreamSynchronize(ix->own_stream) != cudaSuccess)
         set_error(cudaGetLastError(), "coverageBatch copy-back", __FILE__, __LINE__);
-    for (size_t i = 0; i < n; ++i) count_out[i] = tmp[i];
-    free(tmp);
 }
 
 // ---- single queries (ref:537-821): one launch through the mapped mailbox, no CPU fallback ----------------

@@ -1368,6 +1368,14 @@ int siCountMixedDevice(siIndex* const* ixs, int n_contigs, const int32_t* d_cont
     return 0;
 }
 
+// used by c_abi.cu: 32-bit device counts widened to 64 bits on the device
+int si_b200_widen_(siIndex* ix, const uint32_t* d_in, size_t n, unsigned long long* d_out, void* stream) {
+    if (n == 0) return 0;
+    DeviceGuard g(ix->device);
+    SIB_LAUNCH(bk_widen_kernel, grid_for(n, BK_THREADS, ix->sm_count * 16), BK_THREADS, 0, static_cast<cudaStream_t>(stream), d_in, (uint64_t)n, d_out);
+    return 0;
+}
+
 // ---- barrier between GPUs through peer memory --------------------------------------------------------------
 // After a fan-out count every GPU has to know that the others' stores have landed before it reads their slots. One warp:
 // lane k publishes `seq` in peer k's flag word for this rank (after a system-scope fence: the count kernel's peer stores
