@@ -990,6 +990,28 @@ def bench_latency(a, L, _lib, starts, ends, qs, qe):
     t_search = (time.perf_counter() - t0) / k
     L.destroyIndexResult(C_.byref(r))
     _lib.check("single-query calls")
+    # the same loops with the resident polling warp (SI_OPT_RESIDENT_QUERIES): no launch per call
+    res_out = None
+    if L.siIndexSetOption(L.siIndexOf(si), _lib.OPT_RESIDENT_QUERIES, 1) == 0:
+        for s_, e_ in q[:50]:
+            L.countOverlaps(si, s_, e_)
+        t0 = time.perf_counter()
+        tot_r = 0
+        for s_, e_ in q:
+            tot_r += L.countOverlaps(si, s_, e_)
+        t_count_r = (time.perf_counter() - t0) / k
+        r = L.createIndexResult()
+        t0 = time.perf_counter()
+        tot_vr = 0
+        for s_, e_ in q:
+            L.clearIndexResult(C_.byref(r))
+            L.searchValues(si, s_, e_, C_.byref(r))
+            tot_vr += int(r.size)
+        t_search_r = (time.perf_counter() - t0) / k
+        L.destroyIndexResult(C_.byref(r))
+        res_out = {"countOverlaps_us": t_count_r * 1e6, "searchValues_us": t_search_r * 1e6, "same_answers": bool(tot_r == tot and tot_vr == tot_v),
+                   "path": "SI_OPT_RESIDENT_QUERIES = 1: one resident warp polls the mapped pinned mailbox (leaves after 0.2 ms idle / 2 ms at most, relaunched on demand)"}
+    _lib.check("resident single-query calls")
     L.destroySuperIntervals(si)
     # python/ctypes call overhead of the same loop shape (a function that returns at once)
     t0 = time.perf_counter()
@@ -997,7 +1019,7 @@ def bench_latency(a, L, _lib, starts, ends, qs, qe):
         L.si_b200_last_error()
     t_ctypes = (time.perf_counter() - t0) / k
     out = {"calls": k, "countOverlaps_us": t_count * 1e6, "searchValues_us": t_search * 1e6, "ctypes_call_overhead_us": t_ctypes * 1e6,
-           "hits_per_query": tot / k, "count_equals_search_sizes": tot == tot_v,
+           "hits_per_query": tot / k, "count_equals_search_sizes": tot == tot_v, "resident": res_out,
            "path": "query as kernel parameters / mapped pinned mailbox, one launch per call; the kernel publishes a sequence number after its answer and the host spins on that word (csrc/c_abi.cu)"}
     from oracle.pyoracle import Reference
     if Reference.available():

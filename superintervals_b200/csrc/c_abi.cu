@@ -22,9 +22,10 @@
 #include <unordered_map>
 #include <vector>
 
-extern "C" int si_b200_single_scalar_(siIndex* ix, int op, int32_t a, int32_t b, uint32_t* out32, unsigned long long* out64, uint32_t* done);
+extern "C" int si_b200_single_scalar_(siIndex* ix, int op, int32_t a, int32_t b, uint32_t* out32, unsigned long long* out64, uint32_t* done,
+                                      void* out, sib::SingleReq* req);
 extern "C" int si_b200_single_search_(siIndex* ix, int32_t qs, int32_t qe, int what, uint32_t cap, unsigned long long* found, void* out,
-                                      uint32_t* done);
+                                      uint32_t* done, uint32_t* out32, sib::SingleReq* req);
 extern "C" int si_b200_widen_(siIndex* ix, const uint32_t* d_in, size_t n, unsigned long long* d_out, void* stream);
 extern "C" int si_b200_resolve_order_(siIndex* ix, const int32_t* d_qs, size_t n, void* stream);
 
@@ -258,6 +259,7 @@ struct Mailbox {
     unsigned long long count;             // countOverlaps (64-bit count kernels), search: hits found
     uint32_t cov_count; int32_t cov;      // coverage
     uint32_t done;                        // sequence number of the last call whose answer is complete (written last by its kernel)
+    SingleReq req;                        // request block of the resident kernel (SI_OPT_RESIDENT_QUERIES)
     alignas(32) unsigned char out[1];     // search results (MAILBOX_OUT_BYTES)
 };
 constexpr size_t MAILBOX_OUT_BYTES = (size_t)192 << 10;   // 16 K Interval records / 48 K values; longer lists take the batch path
@@ -282,7 +284,7 @@ int search_single(Handle* h, int32_t qs, int32_t qe, R* found, int what, size_t 
     Mailbox* mb = mailbox_of(ix);
     if (!mb) return last_error_code();
     const uint32_t cap = (uint32_t)(MAILBOX_OUT_BYTES / elem);
-    int rc = si_b200_single_search_(ix, qs, qe, what, cap, &mb->count, mb->out, &mb->done);
+    int rc = si_b200_single_search_(ix, qs, qe, what, cap, &mb->count, mb->out, &mb->done, &mb->ub, &mb->req);
     if (rc) return rc;
     const size_t total = (size_t)*reinterpret_cast<volatile unsigned long long*>(&mb->count);
     if (total > cap) return -1;
@@ -637,7 +639,7 @@ size_t upperBound(cSuperIntervals* si, int32_t value) {
         std::lock_guard<std::mutex> lk(h->ix->api_mu);
         if (h->ix->n != 0)
             if (Mailbox* mb = mailbox_of(h->ix))
-                if (si_b200_single_scalar_(h->ix, 0, value, 0, &mb->ub, &mb->count, &mb->done) == 0) {
+                if (si_b200_single_scalar_(h->ix, 0, value, 0, &mb->ub, &mb->count, &mb->done, mb->out, &mb->req) == 0) {
                     const uint32_t u = *reinterpret_cast<volatile uint32_t*>(&mb->ub);
                     r = u == 0xFFFFFFFFu ? SI_NONE : (size_t)u;
                 }
@@ -653,8 +655,8 @@ bool anyOverlaps(cSuperIntervals* si, int32_t start, int32_t end) {
     std::lock_guard<std::mutex> lk(ix->api_mu);
     Mailbox* mb = mailbox_of(ix);
     if (!mb) return false;
-    if (si_b200_single_scalar_(ix, 1, start, end, &mb->any, &mb->count, &mb->done)) return false;
-    return *reinterpret_cast<volatile uint32_t*>(&mb->any) != 0;
+    if (si_b200_single_scalar_(ix, 1, start, end, &mb->ub, &mb->count, &mb->done, mb->out, &mb->req)) return false;
+    return *reinterpret_cast<volatile uint32_t*>(&mb->ub) != 0;
 }
 
 size_t countOverlaps(cSuperIntervals* si, int32_t start, int32_t end) {
@@ -664,7 +666,7 @@ size_t countOverlaps(cSuperIntervals* si, int32_t start, int32_t end) {
     std::lock_guard<std::mutex> lk(ix->api_mu);
     Mailbox* mb = mailbox_of(ix);
     if (!mb) return 0;
-    if (si_b200_single_scalar_(ix, 2, start, end, &mb->any, &mb->count, &mb->done)) return 0;
+    if (si_b200_single_scalar_(ix, 2, start, end, &mb->ub, &mb->count, &mb->done, mb->out, &mb->req)) return 0;
     return (size_t)*reinterpret_cast<volatile unsigned long long*>(&mb->count);
 }
 

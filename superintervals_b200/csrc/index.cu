@@ -346,8 +346,11 @@ int build_bits(siIndex* ix, const int32_t* A, const uint4* cells, const siIndex:
     return 0;
 }
 
+extern "C" int si_b200_server_stop_(siIndex* ix);
+
 int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const int32_t* d_v, size_t n,
                       cudaStream_t s) {
+    si_b200_server_stop_(ix);      // a resident single-query kernel reads the arrays that are about to change
     ix->built = false;
     ix->plan_valid = false;
     ix->cm_s.fmt = ix->cm_e.fmt = 0;
@@ -906,6 +909,8 @@ siIndex* siIndexCreate(void) {
 void siIndexDestroy(siIndex* ix) {
     if (!ix) return;
     DeviceGuard g(ix->device);
+    si_b200_server_stop_(ix);
+    if (ix->srv_stream) cudaStreamDestroy(ix->srv_stream);
     DevBuf* all[] = {&ix->starts, &ix->ends, &ix->values, &ix->branch, &ix->perm, &ix->tree, &ix->esort, &ix->eall, &ix->grid_tab,
                      &ix->cells_s, &ix->cells_e, &ix->bits_s_t, &ix->bits_s_d, &ix->bits_e_t, &ix->bits_e_d, &ix->stream_ws, &ix->mixed_tab, &ix->starts_wf, &ix->stab_off, &ix->stab_hdr, &ix->stab_ent, &ix->stab_cnt,
                      &ix->b_in_s, &ix->b_in_e, &ix->b_in_v, &ix->b_kA, &ix->b_kB, &ix->b_vA, &ix->b_vB, &ix->b_ws,
@@ -1129,6 +1134,11 @@ int siIndexSetOption(siIndex* ix, int option, long long value) {
         case SI_OPT_STREAM_BUDGET:         // bytes of rank bits per interval at most; applies to the next build
             if (value < 0 || value > 4096) break;
             ix->bits_budget = (uint32_t)value;
+            return 0;
+        case SI_OPT_RESIDENT_QUERIES:      // 1: single-query calls are answered by a resident polling warp; 0 (default): one launch per call
+            if (value < 0 || value > 1) break;
+            if (!value) si_b200_server_stop_(ix);
+            ix->resident = value != 0;
             return 0;
         case SI_OPT_NARROW_SORT:           // 1 (default): build() sorts by start and fixes ties; 0: always the composite 64-bit key
             if (value < 0 || value > 1) break;
@@ -1455,13 +1465,66 @@ static int single_wait(siIndex* ix, volatile uint32_t* done, uint32_t seq) {
     return 0;
 }
 
+// ---- resident single-query kernel (SI_OPT_RESIDENT_QUERIES; qk_single_server_kernel) ----------------------------------
+constexpr unsigned long long SRV_IDLE_NS = 200000ull;      // leaves after 0.2 ms without a request ...
+constexpr unsigned long long SRV_LIFE_NS = 2000000ull;     // ... and 2 ms after its launch at the latest (bounds what a device-wide synchronise waits)
+
+static int server_launch(siIndex* ix, SingleReq* req, uint32_t* out32, unsigned long long* out64, void* out, uint32_t* done) {
+    if (!ix->srv_stream) SIB_CHECK(cudaStreamCreateWithFlags(&ix->srv_stream, cudaStreamNonBlocking));
+    ix->srv_req = req;
+    *reinterpret_cast<volatile uint32_t*>(&req->stop) = 0u;
+    *reinterpret_cast<volatile uint32_t*>(&req->alive) = 1u;
+    const uint32_t last = *reinterpret_cast<volatile uint32_t*>(done);      // the last call that was answered
+    SIB_LAUNCH(qk_single_server_kernel, 1, 32, 0, ix->srv_stream, view_of(ix), req, out32, out64, out, done, last, SRV_IDLE_NS, SRV_LIFE_NS);
+    return 0;
+}
+
+// the resident kernel reads the index view it was launched with: it has to be gone before the index changes
+int si_b200_server_stop_(siIndex* ix) {
+    if (!ix || !ix->srv_stream || !ix->srv_req) return 0;
+    DeviceGuard g(ix->device);
+    *reinterpret_cast<volatile uint32_t*>(&ix->srv_req->stop) = 1u;
+    cudaError_t e = cudaStreamSynchronize(ix->srv_stream);
+    *reinterpret_cast<volatile uint32_t*>(&ix->srv_req->stop) = 0u;
+    *reinterpret_cast<volatile uint32_t*>(&ix->srv_req->alive) = 0u;
+    if (e != cudaSuccess) { set_error(e, "stopping the resident single-query kernel", __FILE__, __LINE__); return (int)e; }
+    return 0;
+}
+
+static int single_via_server(siIndex* ix, SingleReq* req, int op, int32_t a, int32_t b, uint32_t cap, uint32_t* out32,
+                             unsigned long long* out64, void* out, uint32_t* done) {
+    const uint32_t seq = ++ix->single_seq;
+    req->op = op; req->a = a; req->b = b; req->cap = cap;
+    std::atomic_thread_fence(std::memory_order_release);                     // the query before its sequence number
+    *reinterpret_cast<volatile uint32_t*>(&req->seq) = seq;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    volatile uint32_t* v_done = done;
+    volatile uint32_t* v_alive = &req->alive;
+    if (!*v_alive) { int rc = server_launch(ix, req, out32, out64, out, done); if (rc) return rc; }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spins = 1; *v_done != seq; ++spins) {
+        if ((spins & 255u) == 0u) {
+            if (!*v_alive && *v_done != seq) {                                // it left without seeing this request: start another
+                int rc = server_launch(ix, req, out32, out64, out, done);
+                if (rc) return rc;
+            }
+            if (std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() > 50.0) {
+                si_b200_server_stop_(ix);
+                if (*v_done != seq) { set_error_msg(cudaErrorUnknown, "resident single-query kernel did not answer"); return cudaErrorUnknown; }
+            }
+        }
+    }
+    return 0;
+}
+
 int si_b200_single_search_(siIndex* ix, int32_t qs, int32_t qe, int what, uint32_t cap, unsigned long long* found, void* out,
-                           uint32_t* done) {
+                           uint32_t* done, uint32_t* out32, SingleReq* req) {
     if (!ix || !ix->built) {
         set_error_msg(cudaErrorNotReady, "single-query search: index not built");
         return cudaErrorNotReady;
     }
     DeviceGuard g(ix->device);
+    if (ix->resident && req) return single_via_server(ix, req, 3 + what, qs, qe, cap, out32, found, out, done);
     cudaStream_t s = ix->own_stream;
     const IndexView v = view_of(ix);
     const uint32_t seq = ++ix->single_seq;
@@ -1475,12 +1538,14 @@ int si_b200_single_search_(siIndex* ix, int32_t qs, int32_t qe, int what, uint32
 }
 
 // op 0: upper_bound(a) -> *out32; 1: has_overlaps(a, b) -> *out32; 2: count(a, b) -> *out64 (all mailbox words)
-int si_b200_single_scalar_(siIndex* ix, int op, int32_t a, int32_t b, uint32_t* out32, unsigned long long* out64, uint32_t* done) {
+int si_b200_single_scalar_(siIndex* ix, int op, int32_t a, int32_t b, uint32_t* out32, unsigned long long* out64, uint32_t* done,
+                           void* out, SingleReq* req) {
     if (!ix || !ix->built) {
         set_error_msg(cudaErrorNotReady, "single query: index not built");
         return cudaErrorNotReady;
     }
     DeviceGuard g(ix->device);
+    if (ix->resident && req) return single_via_server(ix, req, op, a, b, 0u, out32, out64, out, done);
     const uint32_t seq = ++ix->single_seq;
     SIB_LAUNCH(qk_single_scalar_kernel, 1, 32, 0, ix->own_stream, view_of(ix), op, a, b, out32, out64, done, seq);
     return single_wait(ix, done, seq);

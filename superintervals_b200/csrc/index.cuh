@@ -10,6 +10,17 @@ struct siIndex;   // C-visible opaque name
 namespace sib {
 
 // cudaMalloc'd buffer that only ever grows (reallocation drops old contents)
+// request block of the resident single-query kernel, inside the mapped pinned mailbox (c_abi.cu)
+struct SingleReq {
+    uint32_t seq;      // host -> kernel: the call's sequence number, written LAST
+    int32_t op;        // 0 upper_bound, 1 has_overlaps, 2 count, 3 + SI_FILL_* search
+    int32_t a, b;      // the query
+    uint32_t cap;      // search: how many hits fit the mailbox
+    uint32_t stop;     // host -> kernel: leave now
+    uint32_t alive;    // kernel -> host: lowered when the kernel has left (or is leaving)
+    uint32_t pad;
+};
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -145,7 +156,10 @@ struct siIndex {
     // single-query calls (countOverlaps, searchValues ...): a mapped pinned mailbox the kernels read the query from and
     // write the answer to, so that a call is one launch + one stream synchronise (c_abi.cu)
     void* mailbox = nullptr;
-    uint32_t single_seq = 0;                    // sequence number of the last single-query call (published by its kernel when done)
+    uint32_t single_seq = 0;
+    bool resident = false;                      // SI_OPT_RESIDENT_QUERIES: single-query calls are answered by a resident polling warp
+    cudaStream_t srv_stream = nullptr;          // its stream
+    sib::SingleReq* srv_req = nullptr;          // its request block (to stop it before a rebuild / destroy)                    // sequence number of the last single-query call (published by its kernel when done)
     cudaStream_t s_out2 = nullptr;              // second copy-out stream (offsets travel while the fill runs)
     bool pipe_ready_out = false;
 

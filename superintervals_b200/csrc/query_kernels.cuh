@@ -948,10 +948,8 @@ __device__ __forceinline__ void single_done(uint32_t* __restrict__ done, uint32_
 // op 0: upper_bound(a) (hpp:501-516) -> out32; op 1: has_overlaps(a, b), the last candidate only (hpp:865-871, Q1) -> out32;
 // op 2: count(a, b) -> out64: the closed form from the rank cells where the index carries them and a <= b (two sector
 // loads by lane 0), else the reference's walk, 32 intervals per step.
-__global__ void __launch_bounds__(32)
-qk_single_scalar_kernel(IndexView ix, int op, int32_t a, int32_t b, uint32_t* __restrict__ out32,
-                        unsigned long long* __restrict__ out64, uint32_t* __restrict__ done, uint32_t seq) {
-    const uint32_t lane = lane_id();
+__device__ __forceinline__ void single_scalar_body(const IndexView& ix, int op, int32_t a, int32_t b, uint32_t* __restrict__ out32,
+                                                   unsigned long long* __restrict__ out64, uint32_t lane) {
     if (op == 0) {
         const uint32_t c = warp_count_le(ix.starts, ix.n, a, lane);
         if (lane == 0) *out32 = c - 1u;                                            // 0 - 1 wraps to NONE32
@@ -977,6 +975,13 @@ qk_single_scalar_kernel(IndexView ix, int op, int32_t a, int32_t b, uint32_t* __
         }
         if (lane == 0) *out64 = bo;
     }
+}
+
+__global__ void __launch_bounds__(32)
+qk_single_scalar_kernel(IndexView ix, int op, int32_t a, int32_t b, uint32_t* __restrict__ out32,
+                        unsigned long long* __restrict__ out64, uint32_t* __restrict__ done, uint32_t seq) {
+    const uint32_t lane = lane_id();
+    single_scalar_body(ix, op, a, b, out32, out64, lane);
     if (lane == 0) single_done(done, seq);
 }
 
@@ -985,10 +990,9 @@ qk_single_scalar_kernel(IndexView ix, int op, int32_t a, int32_t b, uint32_t* __
 // jumps of the element walk) take 4-6 steps instead of 25. Hits leave in the reference's descending order: a lane's
 // rank is the number of hits in the lanes above it (suffix sum by shuffles) plus those among its own higher slots.
 template <int MODE>
-__global__ void __launch_bounds__(32)
-qk_single_search_kernel(IndexView ix, int32_t qs, int32_t qe, uint32_t cap, unsigned long long* __restrict__ found,
-                        typename FillOut<MODE>::T* __restrict__ out, uint32_t* __restrict__ done, uint32_t seq) {
-    const uint32_t lane = lane_id();
+__device__ __forceinline__ void single_search_body(const IndexView& ix, int32_t qs, int32_t qe, uint32_t cap,
+                                                   unsigned long long* __restrict__ found, typename FillOut<MODE>::T* __restrict__ out,
+                                                   uint32_t lane) {
     uint32_t bi = warp_count_le(ix.starts, ix.n, qe, lane) - 1u;      // 0 - 1 wraps to NONE32
     uint32_t bo = 0;
     while (bi != NONE32) {
@@ -1027,8 +1031,86 @@ qk_single_search_kernel(IndexView ix, int32_t qs, int32_t qe, uint32_t cap, unsi
         }
     }
     __syncwarp();
-    if (lane == 0) { *found = bo; single_done(done, seq); }
+    if (lane == 0) *found = bo;
 }
+
+template <int MODE>
+__global__ void __launch_bounds__(32)
+qk_single_search_kernel(IndexView ix, int32_t qs, int32_t qe, uint32_t cap, unsigned long long* __restrict__ found,
+                        typename FillOut<MODE>::T* __restrict__ out, uint32_t* __restrict__ done, uint32_t seq) {
+    const uint32_t lane = lane_id();
+    single_search_body<MODE>(ix, qs, qe, cap, found, out, lane);
+    if (lane == 0) single_done(done, seq);
+}
+
+// ---- resident single-query kernel (SI_OPT_RESIDENT_QUERIES) --------------------------------------------------
+// A loop of single-query C calls pays a kernel launch per call (~11 us). With this option ONE warp stays resident and
+// polls the request block of the mapped pinned mailbox: the host writes the query and then its sequence number, the warp
+// answers with the same code as the per-call kernels and publishes the sequence number after the answer. The kernel
+// leaves by itself after `idle_ns` without a request and at the latest `life_ns` after its launch (so that a device-wide
+// synchronise elsewhere in the process -- cudaFree, cudaDeviceSynchronize -- is never held up for longer), or when the host
+// raises `stop`; the host relaunches it on demand. Before leaving it lowers `alive` and looks once more for a request.
+__device__ __forceinline__ uint32_t ld_sys_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(32)
+qk_single_server_kernel(IndexView ix, SingleReq* __restrict__ req, uint32_t* __restrict__ out32, unsigned long long* __restrict__ out64,
+                        void* __restrict__ out, uint32_t* __restrict__ done, uint32_t last, unsigned long long idle_ns,
+                        unsigned long long life_ns) {
+    const uint32_t lane = lane_id();
+    const unsigned long long t_start = global_ns();
+    unsigned long long t_idle = t_start;
+    while (true) {
+        uint32_t r = 0, stop = 0;
+        if (lane == 0) { r = ld_sys_u32(&req->seq); stop = ld_sys_u32(&req->stop); }
+        r = __shfl_sync(FULL_MASK, r, 0);
+        stop = __shfl_sync(FULL_MASK, stop, 0);
+        if (r != last && !stop) {
+            __threadfence_system();
+            int32_t op = 0, a = 0, b = 0;
+            uint32_t cap = 0;
+            if (lane == 0) {
+                op = (int32_t)ld_sys_u32(reinterpret_cast<const uint32_t*>(&req->op));
+                a = (int32_t)ld_sys_u32(reinterpret_cast<const uint32_t*>(&req->a));
+                b = (int32_t)ld_sys_u32(reinterpret_cast<const uint32_t*>(&req->b));
+                cap = ld_sys_u32(&req->cap);
+            }
+            op = __shfl_sync(FULL_MASK, op, 0); a = __shfl_sync(FULL_MASK, a, 0); b = __shfl_sync(FULL_MASK, b, 0);
+            cap = __shfl_sync(FULL_MASK, cap, 0);
+            switch (op) {
+                case 3 + FILL_VALUES: single_search_body<FILL_VALUES>(ix, a, b, cap, out64, reinterpret_cast<int32_t*>(out), lane); break;
+                case 3 + FILL_IDXS: single_search_body<FILL_IDXS>(ix, a, b, cap, out64, reinterpret_cast<uint32_t*>(out), lane); break;
+                case 3 + FILL_KEYS: single_search_body<FILL_KEYS>(ix, a, b, cap, out64, reinterpret_cast<int2*>(out), lane); break;
+                case 3 + FILL_ITEMS: single_search_body<FILL_ITEMS>(ix, a, b, cap, out64, reinterpret_cast<Item3*>(out), lane); break;
+                default: single_scalar_body(ix, op, a, b, out32, out64, lane); break;
+            }
+            __syncwarp();
+            if (lane == 0) single_done(done, r);
+            last = r;
+            t_idle = global_ns();
+            continue;
+        }
+        const unsigned long long now = global_ns();
+        const bool expired = now - t_start > life_ns;
+        if (stop || expired || now - t_idle > idle_ns) {
+            uint32_t again = 0;
+            if (lane == 0) {
+                *reinterpret_cast<volatile uint32_t*>(&req->alive) = 0u;
+                __threadfence_system();
+                again = (!stop && !expired && ld_sys_u32(&req->seq) != last) ? 1u : 0u;   // a request slipped in: stay
+                if (again) *reinterpret_cast<volatile uint32_t*>(&req->alive) = 1u;
+            }
+            again = __shfl_sync(FULL_MASK, again, 0);
+            if (!again) return;
+            t_idle = now;
+        }
+    }
+}
+
 
 // ---- stab lists: one branch-array walk per checkpoint, at build time ------------------------
 // FILL = false counts |L(b)|, FILL = true writes the entries at off[b]. The walk is the

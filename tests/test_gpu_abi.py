@@ -195,9 +195,11 @@ def test_rebuild_after_adding_and_clear():
     assert m.count(0, 1000) == 0 and not m.has_overlaps(0, 1000)
 
 
-def test_single_query_calls_use_the_mailbox_and_long_lists_fall_back():
+@pytest.mark.parametrize("resident", [False, True])
+def test_single_query_calls_use_the_mailbox_and_long_lists_fall_back(resident):
     """The one-query-per-call C functions (c_superintervals.h:537-821) answer through the mapped pinned mailbox (one
-    launch, no copies); a result list longer than the mailbox takes the batch path. Same answers as the oracle either way."""
+    launch per call, or -- SI_OPT_RESIDENT_QUERIES -- a resident polling warp; no copies); a result list longer than the
+    mailbox takes the batch path. Same answers as the oracle either way."""
     import ctypes as C
     from superintervals_b200 import _lib
     from oracle.pyoracle import Oracle
@@ -211,6 +213,8 @@ def test_single_query_calls_use_the_mailbox_and_long_lists_fall_back():
     L.addIntervals(si, s.ctypes.data, e.ctypes.data, None, n)
     L.indexSuperIntervals(si)
     _lib.check("indexSuperIntervals")
+    if resident:
+        assert L.siIndexSetOption(L.siIndexOf(si), _lib.OPT_RESIDENT_QUERIES, 1) == 0
     for qs, qe in ((2000, 3000), (0, 10), (999, 999), (9500, 9999), (20000, 30000), (500, 400)):
         a, b = np.array([qs], np.int32), np.array([qe], np.int32)
         want = int(orc.count_batch(a, b)[0])
@@ -238,6 +242,47 @@ def test_single_query_calls_use_the_mailbox_and_long_lists_fall_back():
     assert int(L.upperBound(si, -5)) == 2**64 - 1
     _lib.check("single queries")
     L.destroySuperIntervals(si)
+
+
+def test_resident_query_kernel_survives_idle_gaps_rebuilds_and_a_device_synchronise():
+    """SI_OPT_RESIDENT_QUERIES: the polling warp leaves after 0.2 ms without work (2 ms at most) and is relaunched on demand;
+    a rebuild stops it first (it reads the old arrays); a device-wide synchronise returns promptly while it is resident."""
+    import ctypes as C
+    import time
+    import torch
+    from superintervals_b200 import _lib, workloads as W
+    from oracle.pyoracle import Oracle
+    L = _lib.lib()
+    s, e, qs, qe = W.config3(30_000, 400, 5, axis=2_000_000)
+    orc = Oracle(s, e)
+    want = orc.count_batch(qs, qe)
+    si = L.createSuperIntervals()
+    L.addIntervals(si, s.ctypes.data, e.ctypes.data, None, s.size)
+    L.indexSuperIntervals(si)
+    L.siIndexSetOption(L.siIndexOf(si), _lib.OPT_RESIDENT_QUERIES, 1)
+    for k in range(qs.size):
+        assert int(L.countOverlaps(si, int(qs[k]), int(qe[k]))) == int(want[k])
+        if k % 97 == 0:
+            time.sleep(0.004)                                     # the kernel has left by now: the next call relaunches it
+        if k == 150:
+            t0 = time.perf_counter(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+            assert dt < 0.5                                       # bounded by the kernel's 2 ms lifetime, not by the caller's loop
+    _, res = orc.search_batch(qs[:50], qe[:50], want=("values",))
+    r = L.createIndexResult()
+    for k in range(50):
+        L.searchValues(si, int(qs[k]), int(qe[k]), C.byref(r))
+    got = np.ctypeslib.as_array(r.data, shape=(int(r.size),)).copy() if r.size else np.zeros(0, np.int32)
+    assert np.array_equal(got, res["values"])
+    L.destroyIndexResult(C.byref(r))
+    # add + rebuild while the resident kernel may still be polling
+    L.addInterval(si, 10, 1_999_999, 777)
+    L.indexSuperIntervals(si)
+    s2, e2 = np.append(s, np.int32(10)), np.append(e, np.int32(1_999_999))
+    want2 = Oracle(s2, e2).count_batch(qs[:100], qe[:100])
+    for k in range(100):
+        assert int(L.countOverlaps(si, int(qs[k]), int(qe[k]))) == int(want2[k])
+    _lib.check("resident single queries")
+    L.destroySuperIntervals(si)                                   # stops the kernel, frees the mailbox
 
 
 def test_count_batch_32_bit_counts_equal_the_size_t_call():
