@@ -1469,10 +1469,17 @@ static int single_wait(siIndex* ix, volatile uint32_t* done, uint32_t seq) {
 constexpr unsigned long long SRV_IDLE_NS = 200000ull;      // leaves after 0.2 ms without a request ...
 constexpr unsigned long long SRV_LIFE_NS = 2000000ull;     // ... and 2 ms after its launch at the latest (bounds what a device-wide synchronise waits)
 
+static void server_post(SingleReq* req, uint32_t seq, int op, int32_t a, int32_t b, uint32_t cap) {
+    req->a = a; req->b = b; req->opcap = ((uint32_t)op << 28) | (cap & 0x0FFFFFFFu);
+    std::atomic_thread_fence(std::memory_order_release);                     // the query before its sequence number
+    *reinterpret_cast<volatile uint32_t*>(&req->seq) = seq;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+}
+
 static int server_launch(siIndex* ix, SingleReq* req, uint32_t* out32, unsigned long long* out64, void* out, uint32_t* done) {
     if (!ix->srv_stream) SIB_CHECK(cudaStreamCreateWithFlags(&ix->srv_stream, cudaStreamNonBlocking));
     ix->srv_req = req;
-    *reinterpret_cast<volatile uint32_t*>(&req->stop) = 0u;
+    ix->srv_done = done;
     *reinterpret_cast<volatile uint32_t*>(&req->alive) = 1u;
     const uint32_t last = *reinterpret_cast<volatile uint32_t*>(done);      // the last call that was answered
     SIB_LAUNCH(qk_single_server_kernel, 1, 32, 0, ix->srv_stream, view_of(ix), req, out32, out64, out, done, last, SRV_IDLE_NS, SRV_LIFE_NS);
@@ -1483,9 +1490,10 @@ static int server_launch(siIndex* ix, SingleReq* req, uint32_t* out32, unsigned 
 int si_b200_server_stop_(siIndex* ix) {
     if (!ix || !ix->srv_stream || !ix->srv_req) return 0;
     DeviceGuard g(ix->device);
-    *reinterpret_cast<volatile uint32_t*>(&ix->srv_req->stop) = 1u;
+    const uint32_t seq = ++ix->single_seq;
+    server_post(ix->srv_req, seq, 15, 0, 0, 0);                              // "leave now" (a kernel that has left already never reads it)
     cudaError_t e = cudaStreamSynchronize(ix->srv_stream);
-    *reinterpret_cast<volatile uint32_t*>(&ix->srv_req->stop) = 0u;
+    *reinterpret_cast<volatile uint32_t*>(ix->srv_done) = seq;              // so that the next launch does not take it for a request
     *reinterpret_cast<volatile uint32_t*>(&ix->srv_req->alive) = 0u;
     if (e != cudaSuccess) { set_error(e, "stopping the resident single-query kernel", __FILE__, __LINE__); return (int)e; }
     return 0;
@@ -1494,13 +1502,13 @@ int si_b200_server_stop_(siIndex* ix) {
 static int single_via_server(siIndex* ix, SingleReq* req, int op, int32_t a, int32_t b, uint32_t cap, uint32_t* out32,
                              unsigned long long* out64, void* out, uint32_t* done) {
     const uint32_t seq = ++ix->single_seq;
-    req->op = op; req->a = a; req->b = b; req->cap = cap;
-    std::atomic_thread_fence(std::memory_order_release);                     // the query before its sequence number
-    *reinterpret_cast<volatile uint32_t*>(&req->seq) = seq;
-    std::atomic_thread_fence(std::memory_order_seq_cst);
     volatile uint32_t* v_done = done;
     volatile uint32_t* v_alive = &req->alive;
-    if (!*v_alive) { int rc = server_launch(ix, req, out32, out64, out, done); if (rc) return rc; }
+    if (!*v_alive) {                                                          // launch first: `last` must be the previous call
+        int rc = server_launch(ix, req, out32, out64, out, done);
+        if (rc) return rc;
+    }
+    server_post(req, seq, op, a, b, cap);
     const auto t0 = std::chrono::steady_clock::now();
     for (unsigned spins = 1; *v_done != seq; ++spins) {
         if ((spins & 255u) == 0u) {
@@ -1510,7 +1518,8 @@ static int single_via_server(siIndex* ix, SingleReq* req, int op, int32_t a, int
             }
             if (std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() > 50.0) {
                 si_b200_server_stop_(ix);
-                if (*v_done != seq) { set_error_msg(cudaErrorUnknown, "resident single-query kernel did not answer"); return cudaErrorUnknown; }
+                set_error_msg(cudaErrorUnknown, "resident single-query kernel did not answer");
+                return cudaErrorUnknown;
             }
         }
     }

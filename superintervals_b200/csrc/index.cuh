@@ -10,15 +10,16 @@ struct siIndex;   // C-visible opaque name
 namespace sib {
 
 // cudaMalloc'd buffer that only ever grows (reallocation drops old contents)
-// request block of the resident single-query kernel, inside the mapped pinned mailbox (c_abi.cu)
-struct SingleReq {
+// request block of the resident single-query kernel, inside the mapped pinned mailbox (c_abi.cu). The first 16 bytes are
+// ONE record the kernel fetches with a single 128-bit load per poll (a read of host memory costs the GPU a PCIe round
+// trip, ~2 us: one per poll, not one per field); the host writes a, b, opcap and then seq (x86 store order), and a 16-byte
+// aligned read never straddles a cache line, so a record showing the new seq shows the new query.
+struct alignas(16) SingleReq {
     uint32_t seq;      // host -> kernel: the call's sequence number, written LAST
-    int32_t op;        // 0 upper_bound, 1 has_overlaps, 2 count, 3 + SI_FILL_* search
     int32_t a, b;      // the query
-    uint32_t cap;      // search: how many hits fit the mailbox
-    uint32_t stop;     // host -> kernel: leave now
+    uint32_t opcap;    // op << 28 | cap. op: 0 upper_bound, 1 has_overlaps, 2 count, 3 + SI_FILL_* search, 15 leave now; cap: hits that fit the mailbox
     uint32_t alive;    // kernel -> host: lowered when the kernel has left (or is leaving)
-    uint32_t pad;
+    uint32_t pad[3];
 };
 
 struct DevBuf {
@@ -159,7 +160,8 @@ struct siIndex {
     uint32_t single_seq = 0;
     bool resident = false;                      // SI_OPT_RESIDENT_QUERIES: single-query calls are answered by a resident polling warp
     cudaStream_t srv_stream = nullptr;          // its stream
-    sib::SingleReq* srv_req = nullptr;          // its request block (to stop it before a rebuild / destroy)                    // sequence number of the last single-query call (published by its kernel when done)
+    sib::SingleReq* srv_req = nullptr;          // its request block (to stop it before a rebuild / destroy)
+    uint32_t* srv_done = nullptr;               // the mailbox word its answers' sequence numbers go to                    // sequence number of the last single-query call (published by its kernel when done)
     cudaStream_t s_out2 = nullptr;              // second copy-out stream (offsets travel while the fill runs)
     bool pipe_ready_out = false;
 

@@ -1057,6 +1057,12 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
+__device__ __forceinline__ uint4 ld_sys_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+
 __global__ void __launch_bounds__(32)
 qk_single_server_kernel(IndexView ix, SingleReq* __restrict__ req, uint32_t* __restrict__ out32, unsigned long long* __restrict__ out64,
                         void* __restrict__ out, uint32_t* __restrict__ done, uint32_t last, unsigned long long idle_ns,
@@ -1065,22 +1071,18 @@ qk_single_server_kernel(IndexView ix, SingleReq* __restrict__ req, uint32_t* __r
     const unsigned long long t_start = global_ns();
     unsigned long long t_idle = t_start;
     while (true) {
-        uint32_t r = 0, stop = 0;
-        if (lane == 0) { r = ld_sys_u32(&req->seq); stop = ld_sys_u32(&req->stop); }
-        r = __shfl_sync(FULL_MASK, r, 0);
-        stop = __shfl_sync(FULL_MASK, stop, 0);
-        if (r != last && !stop) {
-            __threadfence_system();
-            int32_t op = 0, a = 0, b = 0;
-            uint32_t cap = 0;
-            if (lane == 0) {
-                op = (int32_t)ld_sys_u32(reinterpret_cast<const uint32_t*>(&req->op));
-                a = (int32_t)ld_sys_u32(reinterpret_cast<const uint32_t*>(&req->a));
-                b = (int32_t)ld_sys_u32(reinterpret_cast<const uint32_t*>(&req->b));
-                cap = ld_sys_u32(&req->cap);
+        uint4 rec = make_uint4(0, 0, 0, 0);
+        if (lane == 0) rec = ld_sys_v4(req);                              // { seq, a, b, op << 28 | cap }: one PCIe read per poll
+        const uint32_t r = __shfl_sync(FULL_MASK, rec.x, 0);
+        if (r != last) {
+            const int32_t a = (int32_t)__shfl_sync(FULL_MASK, rec.y, 0), b = (int32_t)__shfl_sync(FULL_MASK, rec.z, 0);
+            const uint32_t opcap = __shfl_sync(FULL_MASK, rec.w, 0);
+            const int op = (int)(opcap >> 28);
+            const uint32_t cap = opcap & 0x0FFFFFFFu;
+            if (op == 15) {                                               // the host asks the kernel to leave
+                if (lane == 0) { *reinterpret_cast<volatile uint32_t*>(&req->alive) = 0u; __threadfence_system(); }
+                return;
             }
-            op = __shfl_sync(FULL_MASK, op, 0); a = __shfl_sync(FULL_MASK, a, 0); b = __shfl_sync(FULL_MASK, b, 0);
-            cap = __shfl_sync(FULL_MASK, cap, 0);
             switch (op) {
                 case 3 + FILL_VALUES: single_search_body<FILL_VALUES>(ix, a, b, cap, out64, reinterpret_cast<int32_t*>(out), lane); break;
                 case 3 + FILL_IDXS: single_search_body<FILL_IDXS>(ix, a, b, cap, out64, reinterpret_cast<uint32_t*>(out), lane); break;
@@ -1096,12 +1098,12 @@ qk_single_server_kernel(IndexView ix, SingleReq* __restrict__ req, uint32_t* __r
         }
         const unsigned long long now = global_ns();
         const bool expired = now - t_start > life_ns;
-        if (stop || expired || now - t_idle > idle_ns) {
+        if (expired || now - t_idle > idle_ns) {
             uint32_t again = 0;
             if (lane == 0) {
                 *reinterpret_cast<volatile uint32_t*>(&req->alive) = 0u;
                 __threadfence_system();
-                again = (!stop && !expired && ld_sys_u32(&req->seq) != last) ? 1u : 0u;   // a request slipped in: stay
+                again = (!expired && ld_sys_u32(&req->seq) != last) ? 1u : 0u;   // a request slipped in: stay
                 if (again) *reinterpret_cast<volatile uint32_t*>(&req->alive) = 1u;
             }
             again = __shfl_sync(FULL_MASK, again, 0);
@@ -1110,7 +1112,6 @@ qk_single_server_kernel(IndexView ix, SingleReq* __restrict__ req, uint32_t* __r
         }
     }
 }
-
 
 // ---- stab lists: one branch-array walk per checkpoint, at build time ------------------------
 // FILL = false counts |L(b)|, FILL = true writes the entries at off[b]. The walk is the
