@@ -973,6 +973,7 @@ def bench_latency(a, L, _lib, starts, ends, qs, qe):
     _lib.check("indexSuperIntervals")
     k = 2000
     q = [(int(qs[i]), int(qe[i])) for i in range(k)]
+    L.siIndexSetOption(L.siIndexOf(si), _lib.OPT_RESIDENT_QUERIES, 0)          # first: one kernel launch per call
     for s_, e_ in q[:50]:
         L.countOverlaps(si, s_, e_)
     t0 = time.perf_counter()
@@ -1010,7 +1011,7 @@ def bench_latency(a, L, _lib, starts, ends, qs, qe):
         t_search_r = (time.perf_counter() - t0) / k
         L.destroyIndexResult(C_.byref(r))
         res_out = {"countOverlaps_us": t_count_r * 1e6, "searchValues_us": t_search_r * 1e6, "same_answers": bool(tot_r == tot and tot_vr == tot_v),
-                   "path": "SI_OPT_RESIDENT_QUERIES = 1: one resident warp polls the mapped pinned mailbox (leaves after 0.2 ms idle / 2 ms at most, relaunched on demand)"}
+                   "path": "SI_OPT_RESIDENT_QUERIES = 1 (the default): one resident warp polls the mapped pinned mailbox (leaves after 0.2 ms idle / 2 ms at most, relaunched on demand)"}
     _lib.check("resident single-query calls")
     L.destroySuperIntervals(si)
     # python/ctypes call overhead of the same loop shape (a function that returns at once)
@@ -1020,7 +1021,7 @@ def bench_latency(a, L, _lib, starts, ends, qs, qe):
     t_ctypes = (time.perf_counter() - t0) / k
     out = {"calls": k, "countOverlaps_us": t_count * 1e6, "searchValues_us": t_search * 1e6, "ctypes_call_overhead_us": t_ctypes * 1e6,
            "hits_per_query": tot / k, "count_equals_search_sizes": tot == tot_v, "resident": res_out,
-           "path": "query as kernel parameters / mapped pinned mailbox, one launch per call; the kernel publishes a sequence number after its answer and the host spins on that word (csrc/c_abi.cu)"}
+           "path": "SI_OPT_RESIDENT_QUERIES = 0: query as kernel parameters / mapped pinned mailbox, one launch per call; the kernel publishes a sequence number after its answer and the host spins on that word (csrc/c_abi.cu)"}
     from oracle.pyoracle import Reference
     if Reference.available():
         ref = Reference(starts, ends)

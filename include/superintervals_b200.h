@@ -181,11 +181,12 @@ enum { SI_OPT_COUNT_ALGO = 0, SI_OPT_BUCKET_INTERVALS = 1, SI_OPT_WINDOW_SHIFT =
                                     the bytes per pass) and puts equal starts in end-descending order in place; a run of more than 16
                                     equal starts falls back to the composite (start, end desc) 64-bit key. 0: always the composite key.
                                     The built arrays are identical either way. */
-       SI_OPT_RESIDENT_QUERIES = 13, /* 1: the single-query C calls (countOverlaps, searchValues, upperBound ...) are answered by ONE resident
-                                    warp that polls the handle's mapped pinned mailbox, instead of a kernel launch per call (about 11 us):
-                                    for callers that loop over single queries, as every reference driver does. The kernel leaves by
-                                    itself after 0.2 ms without a request and at most 2 ms after its launch (a device-wide synchronise
-                                    elsewhere in the process never waits longer) and is relaunched on demand. 0 (default): per-call launch */
+       SI_OPT_RESIDENT_QUERIES = 13, /* 1 (default): the single-query C calls (countOverlaps, searchValues, upperBound ...) are answered by ONE
+                                    resident warp that polls the handle's mapped pinned mailbox (~5 us per call) instead of a kernel launch
+                                    per call (~11.5 us): for callers that loop over single queries, as every reference driver does. The
+                                    kernel leaves by itself after 0.2 ms without a request and at most 2 ms after its launch (a device-wide
+                                    synchronise elsewhere in the process never waits longer), is stopped before a rebuild, and is relaunched
+                                    on demand. 0 (or SIB_RESIDENT_QUERIES=0 in the environment): one launch per call */
        SI_OPT_STREAM_BUDGET = 10 /* rank bits are built when they cost at most this many bytes per interval (default 64; 0 = never); next build */ };
 enum { SI_COUNT_AUTO = 0, SI_COUNT_WALK = 1, SI_COUNT_RANK = 2, SI_COUNT_CELLS = 3 };
 int siIndexSetOption(siIndex* ix, int option, long long value);

@@ -900,6 +900,7 @@ siIndex* siIndexCreate(void) {
     if (cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev) == cudaSuccess && l2 > 0) ix->l2_bytes = (size_t)l2;
     if (const char* e = getenv("SIB_L2_PERSIST")) ix->l2_persist = atoi(e) != 0;
     if (const char* e = getenv("SIB_CELLS_DIRECT_BYTES")) ix->cells_direct_bytes = (size_t)atoll(e);
+    if (const char* e = getenv("SIB_RESIDENT_QUERIES")) ix->resident = atoi(e) != 0;
     if (ix->l2_persist) raise_persisting_set_aside(ix);
     e = cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { sib::set_error(e, "cudaStreamCreate", __FILE__, __LINE__); delete ix; return nullptr; }
@@ -1135,7 +1136,7 @@ int siIndexSetOption(siIndex* ix, int option, long long value) {
             if (value < 0 || value > 4096) break;
             ix->bits_budget = (uint32_t)value;
             return 0;
-        case SI_OPT_RESIDENT_QUERIES:      // 1: single-query calls are answered by a resident polling warp; 0 (default): one launch per call
+        case SI_OPT_RESIDENT_QUERIES:      // 1 (default): single-query calls are answered by a resident polling warp; 0: one launch per call
             if (value < 0 || value > 1) break;
             if (!value) si_b200_server_stop_(ix);
             ix->resident = value != 0;

@@ -158,7 +158,7 @@ struct siIndex {
     // write the answer to, so that a call is one launch + one stream synchronise (c_abi.cu)
     void* mailbox = nullptr;
     uint32_t single_seq = 0;
-    bool resident = false;                      // SI_OPT_RESIDENT_QUERIES: single-query calls are answered by a resident polling warp
+    bool resident = true;                       // SI_OPT_RESIDENT_QUERIES / SIB_RESIDENT_QUERIES: single-query calls are answered by a resident polling warp
     cudaStream_t srv_stream = nullptr;          // its stream
     sib::SingleReq* srv_req = nullptr;          // its request block (to stop it before a rebuild / destroy)
     uint32_t* srv_done = nullptr;               // the mailbox word its answers' sequence numbers go to                    // sequence number of the last single-query call (published by its kernel when done)

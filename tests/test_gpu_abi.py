@@ -213,8 +213,7 @@ def test_single_query_calls_use_the_mailbox_and_long_lists_fall_back(resident):
     L.addIntervals(si, s.ctypes.data, e.ctypes.data, None, n)
     L.indexSuperIntervals(si)
     _lib.check("indexSuperIntervals")
-    if resident:
-        assert L.siIndexSetOption(L.siIndexOf(si), _lib.OPT_RESIDENT_QUERIES, 1) == 0
+    assert L.siIndexSetOption(L.siIndexOf(si), _lib.OPT_RESIDENT_QUERIES, 1 if resident else 0) == 0
     for qs, qe in ((2000, 3000), (0, 10), (999, 999), (9500, 9999), (20000, 30000), (500, 400)):
         a, b = np.array([qs], np.int32), np.array([qe], np.int32)
         want = int(orc.count_batch(a, b)[0])
