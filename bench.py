@@ -68,6 +68,7 @@ def parse():
     ap.add_argument("--no-configs", action="store_true", help="skip the configs object (c1, c4, c5_lite)")
     ap.add_argument("--c4-scale", type=float, default=1.0, help="C4 size: 1.0 = 100M intervals x 1B queries over 24 contigs")
     ap.add_argument("--c5-intervals", type=int, default=32_000_000)
+    ap.add_argument("--c5-full-intervals", type=int, default=1_000_000_000, help="intervals (= stabbing queries) of the full-size C5 arm at N = 1 (0 = skip)")
     ap.add_argument("--algo", default="auto", choices=["auto", "walk", "rank", "cells"], help="count kernel (SI_OPT_COUNT_ALGO)")
     ap.add_argument("--partition", action="store_true", help="cells kernel through the locality partition (SI_OPT_CELLS_DIRECT_BYTES=1)")
     ap.add_argument("--sv-intervals", type=int, default=4_000_000)
@@ -959,6 +960,49 @@ def bench_configs(a, torch, dist, L, _lib, world, rank):
                       "parity": {"checked": m, "mismatches": int((got != want).sum()), "against": kind}}
     del ix, s5, e5, q5, c5
     torch.cuda.empty_cache()
+    # ---- C5 at FULL size (BASELINE configs[4]): 1 B intervals on a 2e9 axis, build() on device, 1 B stabbing queries. One GPU
+    # only (at N > 1 every rank would repeat it) and only where the memory is there (about 90 GB at the peak of the build).
+    n5f = a.c5_full_intervals
+    free_b = torch.cuda.mem_get_info()[0]
+    if world == 1 and n5f > 0 and free_b > 110 * (1 << 30) * (n5f / 1e9):
+        axis = 2_000_000_000
+        g = torch.Generator(device="cuda").manual_seed(5)
+        s5, e5 = gen_ranges_device(torch, g, n5f, axis, 150, 10_000)
+        ix = DeviceIndex()
+        bms = timed_device(torch, lambda: ix.build(s5, e5), 1)
+        # the parity sample first, while the inputs are still there: a 20 Mb window of the axis. Every interval that overlaps a
+        # point of the window starts within 10 kb before it, so the reference built on those intervals alone answers the
+        # window's stabbing queries exactly as one built on all 1 B would.
+        w0, w1 = 700_000_000, 720_000_000
+        keep = ((s5 >= w0 - 10_000) & (s5 <= w1)).nonzero().flatten()
+        hs, he = s5[keep].cpu().numpy(), e5[keep].cpu().numpy()
+        del s5, e5, keep
+        torch.cuda.empty_cache()
+        q5 = torch.empty(n5f, dtype=torch.int32, device="cuda")
+        CH = 1 << 27
+        for at in range(0, n5f, CH):
+            b = min(n5f, at + CH)
+            q5[at:b] = (torch.rand(b - at, generator=g, device="cuda", dtype=torch.float64) * axis).to(torch.int64).to(torch.int32)
+        c5 = torch.empty(n5f, dtype=torch.int32, device="cuda")
+        ix.count(q5, q5, out=c5, order=ORDER_UNSORTED)
+        ms5 = timed_device(torch, lambda: ix.count(q5, q5, out=c5, order=ORDER_UNSORTED), 3)
+        sel = ((q5 >= w0) & (q5 <= w1)).nonzero().flatten()[:200_000]
+        hq = q5[sel].cpu().numpy()
+        want, kind = reference_counts(hs, he, hq, hq)
+        got = c5[sel].cpu().numpy().astype(np.uint32).astype(np.int64)
+        ci = ix.cells_info()
+        res["c5"] = {"workload": f"C5 (BASELINE configs[4]): {n5f/1e9:g} B intervals (150bp-10kb) on a 2e9 axis, build() on device + {n5f/1e9:g} B stabbing queries",
+                     "build": {"ms": bms, "intervals_per_s": n5f / (bms * 1e-3), "sort_path": ix.last_sort()},
+                     "count": {"value": n5f / (ms5 * 1e-3), "unit": UNIT, "ms_per_step": ms5, "hits_per_query": float(c5[:10_000_000].to(torch.float64).mean().item()),
+                               "step": "one launch of the rank-cells kernel: both 32-byte sectors of a query gathered from HBM (the tables are far larger than L2)"},
+                     "rank_cells": ci, "device_bytes": ix.device_bytes(),
+                     "frac_hbm_compulsory": (12.0 * n5f + ci["starts"]["bytes"] + ci["ends"]["bytes"]) / (ms5 * 1e-3) / 1e9 / peak,
+                     "parity": {"checked": int(sel.numel()), "mismatches": int((got != want).sum()), "against": kind,
+                                "how": f"the stabbing queries that fall in [{w0}, {w1}] against the reference built on the {hs.size} intervals that can reach that window"}}
+        del ix, q5, c5
+        torch.cuda.empty_cache()
+    else:
+        res["c5"] = {"skipped": "full-size C5 runs on one GPU with enough free memory" if n5f > 0 else "--c5-full-intervals 0"}
     return res
 
 
