@@ -251,8 +251,10 @@ int stage_queries(siIndex* ix, const int32_t* qs, const int32_t* qe, size_t n) {
 // ---- single-query mailbox ------------------------------------------------------------------------------
 // The reference's C ABI is one query per call (c.h:537-821) and its drivers loop over it (test/bench.cpp:219-222,
 // 240-242): such a call is pure latency. Its query and its answer therefore live in one block of MAPPED PINNED host
-// memory that the kernels address directly -- no cudaMemcpy in either direction, one launch and one stream
-// synchronise per call. The batch kernels serve it unchanged (n = 1, device pointers = mailbox addresses).
+// memory that the kernels address directly -- no cudaMemcpy in either direction. By default one resident warp polls the
+// request record (SI_OPT_RESIDENT_QUERIES, index.cu / qk_single_server_kernel); with the option off every call is one
+// launch of a one-warp kernel. Either way the kernel publishes the call's sequence number after its answer and the
+// host spins on that word. coverage() still runs the batch kernel on the mailbox (n = 1).
 struct Mailbox {
     int32_t qs, qe;                       // the query, read by the kernels over PCIe
     uint32_t ub, any;                     // upperBound / anyOverlaps answers
