@@ -995,7 +995,7 @@ def bench_configs(a, torch, dist, L, _lib, world, rank):
                      "build": {"ms": bms, "intervals_per_s": n5f / (bms * 1e-3), "sort_path": ix.last_sort()},
                      "count": {"value": n5f / (ms5 * 1e-3), "unit": UNIT, "ms_per_step": ms5, "hits_per_query": float(c5[:10_000_000].to(torch.float64).mean().item()),
                                "step": "one launch of the rank-cells kernel: both 32-byte sectors of a query gathered from HBM (the tables are far larger than L2)"},
-                     "rank_cells": ci, "device_bytes": ix.device_bytes(),
+                     "rank_cells": ci, "device_bytes": ix.device_bytes,
                      "frac_hbm_compulsory": (12.0 * n5f + ci["starts"]["bytes"] + ci["ends"]["bytes"]) / (ms5 * 1e-3) / 1e9 / peak,
                      "parity": {"checked": int(sel.numel()), "mismatches": int((got != want).sum()), "against": kind,
                                 "how": f"the stabbing queries that fall in [{w0}, {w1}] against the reference built on the {hs.size} intervals that can reach that window"}}
@@ -1254,17 +1254,31 @@ def main():
     del h_out32
     wall["e2e"] = time.perf_counter() - t_start
 
+    def guarded(what, fn):
+        """A secondary measurement must not cost the line its headline: a failure is reported in place of the object."""
+        try:
+            return fn()
+        except Exception as ex:   # noqa: BLE001
+            import traceback
+            sys.stderr.write(f"[bench] {what} failed: {ex!r}\n{traceback.format_exc()}\n")
+            try:
+                L.si_b200_clear_error()
+                torch.cuda.empty_cache()
+            except Exception:   # noqa: BLE001
+                pass
+            return {"error": f"{what}: {ex!r}"[:400]}
+
     # ---- N > 1: one batch cut N ways, counts all-gathered over NCCL (mode A); search_values with global offsets
     strong = sv = None
     if world > 1:
         rank0_counts = counts.clone()
         dist.broadcast(rank0_counts, 0)
-        strong = bench_strong(a, torch, dist, L, _lib, ix, world, rank, d_qs, d_qe, rank0_counts)
+        strong = guarded("strong", lambda: bench_strong(a, torch, dist, L, _lib, ix, world, rank, d_qs, d_qe, rank0_counts))
         del rank0_counts
         if not a.no_search_values:
-            sv = bench_search_values_split(a, torch, dist, L, _lib, world, rank)
+            sv = guarded("search_values", lambda: bench_search_values_split(a, torch, dist, L, _lib, world, rank))
     elif not a.no_search_values:
-        sv = bench_search_values(a, torch, L, _lib, rank)
+        sv = guarded("search_values", lambda: bench_search_values(a, torch, L, _lib, rank))
     wall["search_values"] = time.perf_counter() - t_start
 
     # keep what the parity checks need, free the big device arrays before the other configs
@@ -1281,17 +1295,18 @@ def main():
     if not a.no_search_values and not a.no_configs:
         configs = {}
         if world == 1:
-            configs.update(bench_configs(a, torch, dist, L, _lib, world, rank))
-        configs["c4"] = bench_c4(a, torch, dist, world, rank)
+            r_ = guarded("configs", lambda: bench_configs(a, torch, dist, L, _lib, world, rank))
+            configs.update(r_ if "error" not in r_ else {"c1_c5": r_})
+        configs["c4"] = guarded("c4", lambda: bench_c4(a, torch, dist, world, rank))
     wall["configs"] = time.perf_counter() - t_start
 
     latency = bed = setops = None
     if world == 1 and not a.no_search_values:
-        latency = bench_latency(a, L, _lib, starts, ends, qs, qe)
+        latency = guarded("latency", lambda: bench_latency(a, L, _lib, starts, ends, qs, qe))
         if a.bed_lines > 0:
-            bed = bench_bed_ingest(a, rank)
+            bed = guarded("bed_ingest", lambda: bench_bed_ingest(a, rank))
         if a.setop_intervals > 0:
-            setops = bench_set_algebra(a, L, _lib, rank)
+            setops = guarded("set_algebra", lambda: bench_set_algebra(a, L, _lib, rank))
     wall["rows_either_side"] = time.perf_counter() - t_start
 
     if rank != 0:
