@@ -103,3 +103,32 @@ def test_world_size_2_csr_bookkeeping_gloo(n_total):
         for p in procs: p.join(120)
         assert all(p.exitcode == 0 for p in procs)
         assert dict(out) == {0: True, 1: True}
+
+
+def test_vector_overload_order_reproduces_the_reference_python_lists():
+    """intervalmap._vector_overload_order (host logic, no GPU): from the all-descending hit lists of the walk to the order
+    of the reference's C++ vector overload, which its Python class returns (pyx:299,440 -> hpp:879-905). Golden lists from
+    the unmodified Cython module (tests/golden/py_queries.json): search_values_batch there is the all-descending walk (payload =
+    insertion index, mapped to positions through the build's (start asc, end desc) order), search_idxs_batch the vector-overload order."""
+    import json
+    import os
+    from superintervals_b200.intervalmap import _vector_overload_order
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "py_queries.json")))
+    seen_reordered = 0
+    for name in ("nested", "reads", "readme"):
+        c = g[name]
+        starts, ends = np.array(c["starts"], np.int32), np.array(c["ends"], np.int32)
+        order = np.lexsort((-ends.astype(np.int64), starts))          # position -> insertion index
+        pos_of = np.empty(starts.size, np.int32)
+        pos_of[order] = np.arange(starts.size, dtype=np.int32)
+        desc = c["search_values_batch"]
+        off = np.concatenate([[0], np.cumsum([len(x) for x in desc])]).astype(np.uint64)
+        # the walk's positions are strictly descending; exact (start, end) duplicates may sit in either order in the reference's
+        # unstable sort (quirk Q3), so each list is put in descending position order after the mapping
+        flat = np.array([p for x in desc for p in sorted((int(pos_of[v]) for v in x), reverse=True)], np.int32)
+        ub = np.searchsorted(starts[order], np.array(c["qe"], np.int32), "right") - 1
+        got = _vector_overload_order(off, flat, ub)
+        want = np.array([v for x in c["search_idxs_batch"] for v in x], np.int32)
+        assert np.array_equal(got, want)
+        seen_reordered += int((flat != want).sum())
+    assert seen_reordered > 100          # the fixture does exercise the reordering
