@@ -17,6 +17,10 @@ A mixed batch (contig id, start, end per query) is answered in three device step
             query). With one rank nothing moves;
   count     contig c's queries are one contiguous device range for contig c's index.
 
+When this rank holds every contig (one rank, or the indexes replicated) nothing is routed at all: count_mixed() is ONE
+launch of the mixed-batch kernel over the batch in the caller's order (siCountMixedDevice: per-contig rank-cell descriptors
+in shared memory), and with the contigs partitioned the owner counts what arrived in one such launch.
+search_values_mixed() returns the contig-major CSR of a mixed batch (count -> scan -> per-contig fill).
 The per-contig hit totals are all-gathered into the base offsets of a global contig-major CSR.
 PyTorch is plumbing here (device memory, torch.distributed); routing, counting and the scatter
 back are the library's kernels. The route / count steps are injectable so that the exchange logic
@@ -260,6 +264,43 @@ class GenomeIndex:
         if n:
             R.scatter(routed, perm, out)
         return out.cpu().numpy().astype(np.uint32)
+
+    def search_values_mixed(self, contig_ids, qs, qe, what=None):
+        """search_values for a mixed batch on the contigs THIS rank holds (every contig when the indexes are replicated or
+        world == 1): the batch is grouped by contig on the device and each contig's queries are one count -> scan -> fill
+        on that contig's index. Returns (perm, offsets, values): routed query k is the caller's query perm[k] (contig-major,
+        stable), its hits are values[offsets[k]:offsets[k + 1]] in the reference's descending position order, and contig
+        c's segment starts at the base csr_bases() reports -- the global contig-major CSR of SURVEY 8e. Queries of contigs
+        without an index here get empty lists."""
+        from .device import FILL_VALUES
+        what = FILL_VALUES if what is None else what
+        n, nc, dev = contig_ids.numel(), len(self.names), contig_ids.device
+        if n and (int(contig_ids.min()) < 0 or int(contig_ids.max()) >= nc):
+            raise ValueError("contig id out of range")
+        R = self._route()
+        gs, ge, perm, off = R.route(contig_ids, qs, qe, nc)
+        counts = torch.zeros(n, dtype=torch.int32, device=dev)
+        for c in range(nc):
+            lo, hi = int(off[c]), int(off[c + 1])
+            if hi > lo and c in self._ix:
+                self._ix[c].count(gs[lo:hi], ge[lo:hi], out=counts[lo:hi])
+        any_ix = next(iter(self._ix.values()), None)
+        if any_ix is None or n == 0:
+            return perm, torch.zeros(n + 1, dtype=torch.int64, device=dev), torch.empty(0, dtype=torch.int32, device=dev)
+        offsets = any_ix.scan(counts)
+        bounds = offsets[torch.as_tensor(off, device=dev)].cpu().numpy()      # where each contig's values begin
+        values = torch.empty(int(bounds[-1]), dtype=torch.int32, device=dev)
+        self.hits[:] = 0
+        for c in range(nc):
+            lo, hi = int(off[c]), int(off[c + 1])
+            if hi == lo or c not in self._ix:
+                continue
+            self.hits[c] = int(bounds[c + 1] - bounds[c])
+            # the contig's own CSR: its slice of the offsets, re-based to its segment of `values`
+            seg_off = (offsets[lo:hi + 1] - offsets[lo]).contiguous()
+            self._ix[c].search(gs[lo:hi], ge[lo:hi], what=what, counts=counts[lo:hi].contiguous(), offsets=seg_off,
+                               out=values[int(bounds[c]):int(bounds[c + 1])])
+        return perm, offsets, values
 
     def csr_bases(self, hits=None, device=None, group=None):
         """All-gather the per-contig hit totals. Returns (bases, totals) int64[n_contigs]:

@@ -239,3 +239,33 @@ def test_mixed_batch_in_one_launch_matches_per_contig_oracles_incl_malformed_emp
     idx[0].set_option(OPT_COUNT_ALGO, COUNT_WALK)
     assert L.siCountMixedDevice(arr, 6, d_cid.data_ptr(), d_qs.data_ptr(), d_qe.data_ptr(), cid.size, out.data_ptr(), None, None) == -2
     _lib.check("declined mixed count latches nothing")
+
+
+@pytest.mark.gpu
+def test_search_values_of_a_mixed_batch_is_the_contig_major_csr_of_per_contig_oracles():
+    import torch
+    from oracle.pyoracle import Oracle
+    from superintervals_b200.genome import GenomeIndex, route_by_contig
+    data, cid, qs, qe = _mixed_case(7, 23)
+    g = GenomeIndex([f"c{i}" for i in range(7)], [d[0].size for d in data], rank=0, world=1)
+    for c in range(7):
+        if c != 4:                                        # contig 4 has no index here: empty lists
+            g.build_contig(c, torch.from_numpy(data[c][0]).cuda(), torch.from_numpy(data[c][1]).cuda())
+    perm, off, vals = g.search_values_mixed(torch.from_numpy(cid).cuda(), torch.from_numpy(qs).cuda(), torch.from_numpy(qe).cuda())
+    order, bounds = route_by_contig(cid, 7)
+    assert np.array_equal(perm.cpu().numpy().astype(np.int64), order)
+    off, vals = off.cpu().numpy(), vals.cpu().numpy()
+    want_vals, want_counts = [], []
+    for c in range(7):
+        sel = order[bounds[c]:bounds[c + 1]]
+        if c == 4 or sel.size == 0:
+            want_counts.append(np.zeros(sel.size, np.int64))
+            continue
+        o, res = Oracle(*data[c]).search_batch(qs[sel], qe[sel], want=("values",))
+        want_counts.append(np.diff(o.astype(np.int64)))
+        want_vals.append(res["values"])
+    want_off = np.concatenate([[0], np.cumsum(np.concatenate(want_counts))])
+    assert np.array_equal(off, want_off)
+    assert np.array_equal(vals, np.concatenate(want_vals))
+    bases, totals = g.csr_bases()
+    assert np.array_equal(totals, [int(c.sum()) for c in want_counts]) and np.array_equal(bases, want_off[bounds[:-1]])
