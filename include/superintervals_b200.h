@@ -187,6 +187,8 @@ enum { SI_OPT_COUNT_ALGO = 0, SI_OPT_BUCKET_INTERVALS = 1, SI_OPT_WINDOW_SHIFT =
                                     kernel leaves by itself after 0.2 ms without a request and at most 2 ms after its launch (a device-wide
                                     synchronise elsewhere in the process never waits longer), is stopped before a rebuild, and is relaunched
                                     on demand. 0 (or SIB_RESIDENT_QUERIES=0 in the environment): one launch per call */
+       SI_OPT_STAB_VALUE_LISTS = 14, /* 1 (default): short stab lists (8-byte records) are kept twice, as (position, end) and as (value, end),
+                                    so that search_values reads a hit's payload with its record instead of gathering it; 0: positions only */
        SI_OPT_STREAM_BUDGET = 10 /* rank bits are built when they cost at most this many bytes per interval (default 64; 0 = never); next build */ };
 enum { SI_COUNT_AUTO = 0, SI_COUNT_WALK = 1, SI_COUNT_RANK = 2, SI_COUNT_CELLS = 3 };
 int siIndexSetOption(siIndex* ix, int option, long long value);

@@ -183,7 +183,7 @@ using namespace sib;
     } while (0)
 
 size_t siIndex::device_bytes() const {
-    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &esort, &eall, &grid_tab, &cells_s, &cells_e, &bits_s_t, &bits_s_d, &bits_e_t, &bits_e_d, &stream_ws, &starts_wf, &stab_off, &stab_hdr, &stab_ent, &stab_cnt, &b_in_s, &b_in_e, &b_in_v,
+    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &esort, &eall, &grid_tab, &cells_s, &cells_e, &bits_s_t, &bits_s_d, &bits_e_t, &bits_e_d, &stream_ws, &starts_wf, &stab_off, &stab_hdr, &stab_ent, &stab_entv, &stab_cnt, &b_in_s, &b_in_e, &b_in_v,
                            &b_kA, &b_kB, &b_vA, &b_vB, &b_ws, &small, &q_A, &q_B,
                            &q_ws, &scan_status, &h_qs, &h_qe, &h_counts, &h_offsets, &h_out, &h_cov};
     size_t s = 0;
@@ -228,7 +228,8 @@ IndexView view_of(const siIndex* ix) {
     v.bits_s = RankBits{bits ? ix->bits_s_t.as<uint2>() : nullptr, ix->bits_s_d.as<uint32_t>(), ix->cm_s.lo, ix->cm_s.span, ix->bits_words_s};
     v.bits_e = RankBits{bits ? ix->bits_e_t.as<uint2>() : nullptr, ix->bits_e_d.as<uint32_t>(), ix->cm_e.lo, ix->cm_e.span, ix->bits_words_e};
     const bool stab = ix->stab_state == 1 && ix->stab_enabled;
-    v.stab = StabLists{ix->stab_hdr.as<uint4>(), stab ? ix->stab_ent.p : nullptr, ix->stab_rec16 ? 1u : 0u, ix->stab_kshift, ix->stab_nlists};
+    v.stab = StabLists{ix->stab_hdr.as<uint4>(), stab ? ix->stab_ent.p : nullptr, (stab && !ix->stab_rec16 && ix->stab_value_lists) ? ix->stab_entv.p : nullptr,
+                       ix->stab_rec16 ? 1u : 0u, ix->stab_kshift, ix->stab_nlists};
     v.n = ix->n;
     v.wellformed = ix->wellformed ? 1u : 0u;
     v.rstarts = ix->n_mal ? ix->starts_wf.as<int32_t>() : ix->starts.as<int32_t>();
@@ -804,7 +805,7 @@ int ensure_stab_lists(siIndex* ix, cudaStream_t s) {
     SIB_CHECK(cudaMemsetAsync(d_tot, 0, sizeof(unsigned long long) * QK_STAB_SPACINGS, s));
     const IndexView v = view_of(ix);
     SIB_LAUNCH((qk_stab_lists_kernel<false, false>), (nl0 + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, QK_STAB_SHIFT0, nl0,
-               ix->stab_cnt.as<uint32_t>(), (const uint64_t*)nullptr, (void*)nullptr, (uint4*)nullptr);
+               ix->stab_cnt.as<uint32_t>(), (const uint64_t*)nullptr, (void*)nullptr, (uint4*)nullptr, (int2*)nullptr);
     SIB_LAUNCH(qk_stab_totals_kernel, grid_for(nl0, QK_THREADS, ix->sm_count * 8), QK_THREADS, 0, s,
                ix->stab_cnt.as<uint32_t>(), nl0, d_tot);
     unsigned long long tot[QK_STAB_SPACINGS];
@@ -818,18 +819,23 @@ int ensure_stab_lists(siIndex* ix, cudaStream_t s) {
     const uint32_t nl = (n >> kshift) + 1;
     if (k > 0)   // the kept checkpoints' counts, contiguous
         SIB_LAUNCH((qk_stab_lists_kernel<false, false>), (nl + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, kshift, nl,
-                   ix->stab_cnt.as<uint32_t>(), (const uint64_t*)nullptr, (void*)nullptr, (uint4*)nullptr);
+                   ix->stab_cnt.as<uint32_t>(), (const uint64_t*)nullptr, (void*)nullptr, (uint4*)nullptr, (int2*)nullptr);
     // long lists (dense data): nearly every record read is a hit, so the value rides in the record
     const bool rec16 = tot[k] >= 16ull * nl;
     if (ix->stab_hdr.ensure((size_t)nl * 16) || ix->stab_off.ensure(((size_t)nl + 1) * 8) || ix->stab_ent.ensure((size_t)(tot[k] ? tot[k] : 1) * (rec16 ? 16 : 8))) return last_error_code();
     int rc = siScanDevice(ix, ix->stab_cnt.as<uint32_t>(), nl, ix->stab_off.as<uint64_t>(), (void*)s);
     if (rc) return rc;
+    // short lists (8-byte records): a second copy as (value, end), so that search_values reads a hit's payload with the record
+    // instead of gathering it -- one random sector less per stab hit for 8 B per list entry (SI_OPT_STAB_VALUE_LISTS)
+    const bool vlists = !rec16 && ix->stab_value_lists;
+    if (vlists && ix->stab_entv.ensure((size_t)(tot[k] ? tot[k] : 1) * 8)) return last_error_code();
     if (rec16)
         SIB_LAUNCH((qk_stab_lists_kernel<true, true>), (nl + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, kshift, nl,
-                   (uint32_t*)nullptr, ix->stab_off.as<uint64_t>(), ix->stab_ent.p, ix->stab_hdr.as<uint4>());
+                   (uint32_t*)nullptr, ix->stab_off.as<uint64_t>(), ix->stab_ent.p, ix->stab_hdr.as<uint4>(), (int2*)nullptr);
     else
         SIB_LAUNCH((qk_stab_lists_kernel<true, false>), (nl + QK_THREADS - 1) / QK_THREADS, QK_THREADS, 0, s, v, kshift, nl,
-                   (uint32_t*)nullptr, ix->stab_off.as<uint64_t>(), ix->stab_ent.p, ix->stab_hdr.as<uint4>());
+                   (uint32_t*)nullptr, ix->stab_off.as<uint64_t>(), ix->stab_ent.p, ix->stab_hdr.as<uint4>(),
+                   vlists ? ix->stab_entv.as<int2>() : (int2*)nullptr);
     ix->stab_rec16 = rec16;
     ix->stab_kshift = kshift;
     ix->stab_nlists = nl;
@@ -913,7 +919,7 @@ void siIndexDestroy(siIndex* ix) {
     si_b200_server_stop_(ix);
     if (ix->srv_stream) cudaStreamDestroy(ix->srv_stream);
     DevBuf* all[] = {&ix->starts, &ix->ends, &ix->values, &ix->branch, &ix->perm, &ix->tree, &ix->esort, &ix->eall, &ix->grid_tab,
-                     &ix->cells_s, &ix->cells_e, &ix->bits_s_t, &ix->bits_s_d, &ix->bits_e_t, &ix->bits_e_d, &ix->stream_ws, &ix->mixed_tab, &ix->starts_wf, &ix->stab_off, &ix->stab_hdr, &ix->stab_ent, &ix->stab_cnt,
+                     &ix->cells_s, &ix->cells_e, &ix->bits_s_t, &ix->bits_s_d, &ix->bits_e_t, &ix->bits_e_d, &ix->stream_ws, &ix->mixed_tab, &ix->starts_wf, &ix->stab_off, &ix->stab_hdr, &ix->stab_ent, &ix->stab_entv, &ix->stab_cnt,
                      &ix->b_in_s, &ix->b_in_e, &ix->b_in_v, &ix->b_kA, &ix->b_kB, &ix->b_vA, &ix->b_vB, &ix->b_ws,
                      &ix->small, &ix->q_A, &ix->q_B, &ix->q_ws, &ix->scan_status, &ix->h_qs,
                      &ix->h_qe, &ix->h_counts, &ix->h_offsets, &ix->h_out, &ix->h_cov};
@@ -1135,6 +1141,10 @@ int siIndexSetOption(siIndex* ix, int option, long long value) {
         case SI_OPT_STREAM_BUDGET:         // bytes of rank bits per interval at most; applies to the next build
             if (value < 0 || value > 4096) break;
             ix->bits_budget = (uint32_t)value;
+            return 0;
+        case SI_OPT_STAB_VALUE_LISTS:      // 1 (default): short stab lists also exist as (value, end) records; applies to lists not built yet
+            if (value < 0 || value > 1) break;
+            ix->stab_value_lists = value != 0;
             return 0;
         case SI_OPT_RESIDENT_QUERIES:      // 1 (default): single-query calls are answered by a resident polling warp; 0: one launch per call
             if (value < 0 || value > 1) break;
@@ -1369,12 +1379,12 @@ int siCountMixedDevice(siIndex* const* ixs, int n_contigs, const int32_t* d_cont
     auto kern = qk_count_mixed_kernel<uint32_t>;
     if (smem > ((size_t)48 << 10)) SIB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    SIB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, QC_THREADS, smem));
+    SIB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, QM_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
-    const uint64_t tiles = ((uint64_t)n + QC_THREADS - 1) / QC_THREADS;
+    const uint64_t tiles = ((uint64_t)n + QM_THREADS - 1) / QM_THREADS;
     const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)host->sm_count * per_sm);
     const MixedEntry* d_tab = reinterpret_cast<const MixedEntry*>(host->mixed_tab.p);
-    SIB_LAUNCH_T(host, TAG_COUNT_CELLS, kern, grid, QC_THREADS, smem, s, d_tab, (uint32_t)n_contigs, d_contig, d_qs, d_qe,
+    SIB_LAUNCH_T(host, TAG_COUNT_CELLS, kern, grid, QM_THREADS, smem, s, d_tab, (uint32_t)n_contigs, d_contig, d_qs, d_qe,
                  (uint32_t)n, d_counts, d_totals);
     return 0;
 }
@@ -1470,6 +1480,8 @@ static int single_wait(siIndex* ix, volatile uint32_t* done, uint32_t seq) {
 constexpr unsigned long long SRV_IDLE_NS = 200000ull;      // leaves after 0.2 ms without a request ...
 constexpr unsigned long long SRV_LIFE_NS = 2000000ull;     // ... and 2 ms after its launch at the latest (bounds what a device-wide synchronise waits)
 
+constexpr int SINGLE_RETRY_BY_LAUNCH = -3;
+
 static void server_post(SingleReq* req, uint32_t seq, int op, int32_t a, int32_t b, uint32_t cap) {
     req->a = a; req->b = b; req->opcap = ((uint32_t)op << 28) | (cap & 0x0FFFFFFFu);
     std::atomic_thread_fence(std::memory_order_release);                     // the query before its sequence number
@@ -1517,10 +1529,12 @@ static int single_via_server(siIndex* ix, SingleReq* req, int op, int32_t a, int
                 int rc = server_launch(ix, req, out32, out64, out, done);
                 if (rc) return rc;
             }
-            if (std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() > 50.0) {
-                si_b200_server_stop_(ix);
-                set_error_msg(cudaErrorUnknown, "resident single-query kernel did not answer");
-                return cudaErrorUnknown;
+            if (std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() > 2000.0) {
+                // no answer for two seconds (a saturated GPU may not have scheduled the warp yet): stop the kernel -- which waits for
+                // it -- and, if the request was not served on the way out, let the caller answer it with a launch of its own
+                int rc = si_b200_server_stop_(ix);
+                if (rc) return rc;
+                return SINGLE_RETRY_BY_LAUNCH;
             }
         }
     }
@@ -1534,7 +1548,10 @@ int si_b200_single_search_(siIndex* ix, int32_t qs, int32_t qe, int what, uint32
         return cudaErrorNotReady;
     }
     DeviceGuard g(ix->device);
-    if (ix->resident && req) return single_via_server(ix, req, 3 + what, qs, qe, cap, out32, found, out, done);
+    if (ix->resident && req) {
+        const int rc = single_via_server(ix, req, 3 + what, qs, qe, cap, out32, found, out, done);
+        if (rc != SINGLE_RETRY_BY_LAUNCH) return rc;
+    }
     cudaStream_t s = ix->own_stream;
     const IndexView v = view_of(ix);
     const uint32_t seq = ++ix->single_seq;
@@ -1555,7 +1572,10 @@ int si_b200_single_scalar_(siIndex* ix, int op, int32_t a, int32_t b, uint32_t* 
         return cudaErrorNotReady;
     }
     DeviceGuard g(ix->device);
-    if (ix->resident && req) return single_via_server(ix, req, op, a, b, 0u, out32, out64, out, done);
+    if (ix->resident && req) {
+        const int rc = single_via_server(ix, req, op, a, b, 0u, out32, out64, out, done);
+        if (rc != SINGLE_RETRY_BY_LAUNCH) return rc;
+    }
     const uint32_t seq = ++ix->single_seq;
     SIB_LAUNCH(qk_single_scalar_kernel, 1, 32, 0, ix->own_stream, view_of(ix), op, a, b, out32, out64, done, seq);
     return single_wait(ix, done, seq);

@@ -107,6 +107,8 @@ struct siIndex {
     int stream_mode = 1;                           // SI_OPT_STREAM: 0 off, 1 position-sorted batches, 2 every batch
     // stab lists (StabLists in query_kernels.cuh), made by the first CSR fill that can use them
     sib::DevBuf stab_off, stab_hdr, stab_ent, stab_cnt;   // scan offsets (build only), list headers, records, counts
+    sib::DevBuf stab_entv;                                // 8-byte lists again as (value, end): search_values' payload rides in the record
+    bool stab_value_lists = true;                         // SI_OPT_STAB_VALUE_LISTS
     uint32_t stab_kshift = 0, stab_nlists = 0;
     bool stab_rec16 = false;                       // 16-byte (position, end, value) records instead of 8-byte (position, end)
     int stab_state = 0;                            // 0 = not tried yet, 1 = built, 2 = over budget (the fill walks)

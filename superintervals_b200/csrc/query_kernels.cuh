@@ -81,6 +81,7 @@ struct RankBits {
 struct StabLists {
     const uint4* hdr;      // per list: first record (64 bits: x | y << 32), record count (z); lists start on 32-byte boundaries
     const void* ent;       // int2 (position, end) or int4 (position, end, value, 0) records; nullptr = not built
+    const void* entv;      // 8-byte lists only: the same records as (VALUE, end) -- search_values then needs no payload gather per hit
     uint32_t rec16;        // 1: 16-byte records
     uint32_t kshift;
     uint32_t nlists;       // (n >> kshift) + 1
@@ -456,8 +457,10 @@ qk_count_rank_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __rest
 // the counts streamed out coalesced, the two sectors per query served by L2 (C2: 62 MB of cells).
 // Per query: 8 B in, 4 B out, 2 x 32 B sector reads. Queries with qs > qe (quirk Q6) take the
 // branch-array walk, as in qk_count_rank_kernel. Bit-exact with qk_count_kernel.
+// 128 threads x 16 CTAs/SM measured 3.6 % faster than 256 x 8 on C2 (0.924 against 0.959 ms; 64 x 32 the same, 512 x 4 slower:
+// tools/gpu_r02v.sh): the same 2048 resident threads, a finer grain for the block scheduler
 #ifndef SIB_QC_THREADS
-#define SIB_QC_THREADS 256
+#define SIB_QC_THREADS 128
 #endif
 constexpr int QC_THREADS = SIB_QC_THREADS;
 #ifndef SIB_QC_PER_THREAD
@@ -675,7 +678,7 @@ __device__ __forceinline__ void count_cells_tile(const IndexView& ix, const Quer
 }
 
 #ifndef SIB_QC_MINBLOCKS
-#define SIB_QC_MINBLOCKS 8
+#define SIB_QC_MINBLOCKS 16
 #endif
 template <typename CountT>
 __global__ void __launch_bounds__(QC_THREADS, SIB_QC_MINBLOCKS)
@@ -701,6 +704,7 @@ struct MixedEntry {
     int32_t mal_s[8], mal_e[8];
 };
 constexpr int QM_SMEM_ENTRIES = 256;    // tables up to this many contigs are staged in shared memory
+constexpr int QM_THREADS = 256;
 
 // the reference's element walk (hpp:551-579) by one lane: only for inverted queries, which well-formed callers never send
 __device__ __noinline__ uint32_t walk_scalar(const int32_t* __restrict__ ends, const uint32_t* __restrict__ branch, uint32_t i, int32_t qs) {
@@ -718,7 +722,7 @@ __device__ __noinline__ uint32_t walk_scalar(const int32_t* __restrict__ ends, c
 #define SIB_QM_MINBLOCKS 5
 #endif
 template <typename CountT>
-__global__ void __launch_bounds__(QC_THREADS, SIB_QM_MINBLOCKS)
+__global__ void __launch_bounds__(QM_THREADS, SIB_QM_MINBLOCKS)
 qk_count_mixed_kernel(const MixedEntry* __restrict__ table, uint32_t n_contigs, const int32_t* __restrict__ contig,
                       const int32_t* __restrict__ qs_in, const int32_t* __restrict__ qe_in, uint32_t nq, CountT* __restrict__ counts,
                       unsigned long long* __restrict__ totals) {
@@ -729,16 +733,16 @@ qk_count_mixed_kernel(const MixedEntry* __restrict__ table, uint32_t n_contigs, 
         const uint32_t words = n_contigs * (uint32_t)(sizeof(MixedEntry) / 4);
         uint32_t* dst = reinterpret_cast<uint32_t*>(qm_smem);
         const uint32_t* src = reinterpret_cast<const uint32_t*>(table);
-        for (uint32_t k = threadIdx.x; k < words; k += QC_THREADS) dst[k] = __ldg(src + k);
+        for (uint32_t k = threadIdx.x; k < words; k += QM_THREADS) dst[k] = __ldg(src + k);
         tab = reinterpret_cast<const MixedEntry*>(qm_smem);
         if (totals) {
             s_tot = reinterpret_cast<unsigned long long*>(qm_smem + (((size_t)words * 4 + 15) & ~(size_t)15));
-            for (uint32_t k = threadIdx.x; k < n_contigs; k += QC_THREADS) s_tot[k] = 0ull;
+            for (uint32_t k = threadIdx.x; k < n_contigs; k += QM_THREADS) s_tot[k] = 0ull;
         }
         __syncthreads();
     }
-    const uint64_t stride = (uint64_t)gridDim.x * QC_THREADS;
-    for (uint64_t t = (uint64_t)blockIdx.x * QC_THREADS + threadIdx.x; t < nq; t += stride) {
+    const uint64_t stride = (uint64_t)gridDim.x * QM_THREADS;
+    for (uint64_t t = (uint64_t)blockIdx.x * QM_THREADS + threadIdx.x; t < nq; t += stride) {
         const uint32_t cid = (uint32_t)ld_stream(contig + t);
         const int32_t qs = ld_stream(qs_in + t), qe = ld_stream(qe_in + t);
         uint32_t c = 0;
@@ -769,7 +773,7 @@ qk_count_mixed_kernel(const MixedEntry* __restrict__ table, uint32_t n_contigs, 
     }
     if (s_tot) {
         __syncthreads();
-        for (uint32_t k = threadIdx.x; k < n_contigs; k += QC_THREADS)
+        for (uint32_t k = threadIdx.x; k < n_contigs; k += QM_THREADS)
             if (s_tot[k]) atomicAdd(totals + k, s_tot[k]);
     }
 }
@@ -1120,7 +1124,7 @@ qk_single_server_kernel(IndexView ix, SingleReq* __restrict__ req, uint32_t* __r
 template <bool FILL, bool REC16>
 __global__ void __launch_bounds__(QK_THREADS)
 qk_stab_lists_kernel(IndexView ix, uint32_t kshift, uint32_t nlists, uint32_t* __restrict__ counts,
-                     const uint64_t* __restrict__ off, void* __restrict__ ent_out, uint4* __restrict__ hdr) {
+                     const uint64_t* __restrict__ off, void* __restrict__ ent_out, uint4* __restrict__ hdr, int2* __restrict__ entv_out) {
     const uint64_t t64 = (uint64_t)blockIdx.x * QK_THREADS + threadIdx.x;
     if (t64 >= nlists) return;
     const uint32_t b = (uint32_t)t64;
@@ -1141,7 +1145,10 @@ qk_stab_lists_kernel(IndexView ix, uint32_t kshift, uint32_t nlists, uint32_t* _
 #define SIB_PUT(J, E)                                                                                     \
                     do {                                                                                  \
                         if (REC16) reinterpret_cast<int4*>(ent_out)[o++] = make_int4((int)(J), (E), ld_nc(ix.values + (J)), 0); \
-                        else reinterpret_cast<int2*>(ent_out)[o++] = make_int2((int)(J), (E));            \
+                        else {                                                                            \
+                            if (entv_out) entv_out[o] = make_int2(ld_nc(ix.values + (J)), (E));           \
+                            reinterpret_cast<int2*>(ent_out)[o++] = make_int2((int)(J), (E));             \
+                        }                                                                                 \
                     } while (0)
                     if (hw) SIB_PUT(base + 3u, e.w);
                     if (hz) SIB_PUT(base + 2u, e.z);
@@ -1167,7 +1174,10 @@ qk_stab_lists_kernel(IndexView ix, uint32_t kshift, uint32_t nlists, uint32_t* _
         const uint32_t len = (uint32_t)(o - o0);
         for (uint64_t pad = o; pad < o0 + ((len + 3u) & ~3u); ++pad) {
             if (REC16) reinterpret_cast<int4*>(ent_out)[pad] = make_int4(0, INT_MIN, 0, 0);
-            else reinterpret_cast<int2*>(ent_out)[pad] = make_int2(0, INT_MIN);
+            else {
+                reinterpret_cast<int2*>(ent_out)[pad] = make_int2(0, INT_MIN);
+                if (entv_out) entv_out[pad] = make_int2(0, INT_MIN);
+            }
         }
         hdr[b] = make_uint4((uint32_t)o0, (uint32_t)(o0 >> 32), len, 0u);
     }
@@ -1326,9 +1336,11 @@ qk_fill_runs_kernel(IndexView ix, QueryRecords rec, uint32_t nq, const uint64_t*
         }
         const uint32_t topm1 = top - 1u;
         const bool rec16 = ix.stab.rec16 != 0;   // list records carry their value
+        const bool vlist = MODE == FILL_VALUES && !rec16 && ix.stab.entv != nullptr;   // 8-byte (value, end) lists: no payload gather
         // one candidate: c < plen -> position topm1 - c read from ends[], else list record c - plen
 #define SIB_STAB_CAND(C, PLEN, TOPM1, L0, POS, END, VAL, FROM_LIST)                                   \
         if ((C) < (PLEN)) { POS = (TOPM1) - (C); END = ld_nc(ix.ends + POS); VAL = 0; FROM_LIST = false; } \
+        else if (vlist) { const int2 r_ = __ldg(reinterpret_cast<const int2*>(ix.stab.entv) + ((L0) + ((C) - (PLEN)))); POS = 0; END = r_.y; VAL = r_.x; FROM_LIST = true; } \
         else { const int4 r_ = ld_stab_record(ix.stab, (L0) + ((C) - (PLEN))); POS = (uint32_t)r_.x; END = r_.y; VAL = r_.z; FROM_LIST = rec16; }
 #define SIB_STAB_EMIT(AT, POS, END, VAL, FROM_LIST)                                                   \
         if (MODE == FILL_VALUES) reinterpret_cast<int32_t*>(out)[AT] = (FROM_LIST) ? (VAL) : ld_nc(ix.values + (POS)); /* FROM_LIST: VAL is valid */ \
@@ -1370,7 +1382,7 @@ qk_fill_runs_kernel(IndexView ix, QueryRecords rec, uint32_t nq, const uint64_t*
                 }
                 const uint64_t l1 = l0 + llen;
                 if (!rec16) {
-                    const int2* __restrict__ ent2 = reinterpret_cast<const int2*>(ix.stab.ent);
+                    const int2* __restrict__ ent2 = reinterpret_cast<const int2*>(vlist ? ix.stab.entv : ix.stab.ent);
                     for (uint64_t p = l0; p < l1 && o < o_end; p += 4) {   // four records = one 32-byte sector per step
                         const CellRec r = ld_cell(reinterpret_cast<const uint4*>(ent2 + p));   // lists are padded to 4
                         int2 v[4];
@@ -1382,7 +1394,7 @@ qk_fill_runs_kernel(IndexView ix, QueryRecords rec, uint32_t nq, const uint64_t*
                         if (MODE == FILL_VALUES) {
                             int32_t pv[4];                       // the hits' payload gathers leave together
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) pv[u] = h[u] ? ld_nc(ix.values + (uint32_t)v[u].x) : 0;
+                            for (int u = 0; u < 4; ++u) pv[u] = vlist ? v[u].x : (h[u] ? ld_nc(ix.values + (uint32_t)v[u].x) : 0);   // value lists: no gather
                             int32_t* o32 = reinterpret_cast<int32_t*>(out);
 #pragma unroll
                             for (int u = 0; u < 4; ++u)
@@ -1423,6 +1435,7 @@ qk_fill_runs_kernel(IndexView ix, QueryRecords rec, uint32_t nq, const uint64_t*
                 uint32_t pos = 0; int32_t end = INT_MIN, val = 0; bool fl = false;
                 if (c < bn) {
                     if (c < bpl) { pos = btm - (uint32_t)c; end = ld_nc(ix.ends + pos); }
+                    else if (vlist) { const int2 r = __ldg(reinterpret_cast<const int2*>(ix.stab.entv) + (bl0 + (c - bpl))); end = r.y; val = r.x; fl = true; }
                     else { const int4 r = ld_stab_record(ix.stab, bl0 + (c - bpl)); pos = (uint32_t)r.x; end = r.y; val = r.z; fl = rec16; }
                 }
                 const bool hit = c < bn && end >= bqs;

@@ -296,10 +296,9 @@ class GenomeIndex:
             if hi == lo or c not in self._ix:
                 continue
             self.hits[c] = int(bounds[c + 1] - bounds[c])
-            # the contig's own CSR: its slice of the offsets, re-based to its segment of `values`
-            seg_off = (offsets[lo:hi + 1] - offsets[lo]).contiguous()
-            self._ix[c].search(gs[lo:hi], ge[lo:hi], what=what, counts=counts[lo:hi].contiguous(), offsets=seg_off,
-                               out=values[int(bounds[c]):int(bounds[c + 1])])
+            # the contig's own count -> scan -> fill (fresh, aligned buffers), its values copied into its segment
+            _, v_c = self._ix[c].search(gs[lo:hi].contiguous(), ge[lo:hi].contiguous(), what=what)
+            values[int(bounds[c]):int(bounds[c + 1])] = v_c
         return perm, offsets, values
 
     def csr_bases(self, hits=None, device=None, group=None):

@@ -9,6 +9,7 @@ import pytest
 
 from oracle.pyoracle import Oracle
 from superintervals_b200 import workloads as W
+from superintervals_b200 import _lib
 
 pytestmark = pytest.mark.gpu
 
@@ -212,11 +213,13 @@ def test_rank_cells_edge_cases(case, fill):
         off_w, lst_w = ix.set_option(OPT_COUNT_ALGO, COUNT_WALK).search(pqs, pqe, what, order=ORDER_ASIS)
         ix.set_option(OPT_COUNT_ALGO, COUNT_CELLS)
         # below each run: the stab lists, the branch-array walk, and lists at a coarser checkpoint spacing
-        for lists, budget in ((1, 6), (0, 6), (1, 1)):
-            ix.set_option(OPT_STAB_LISTS, lists).set_option(OPT_STAB_BUDGET, budget)
+        # ... and the (value, end) copy of the short lists on and off (a view switch: the lists themselves stay)
+        for lists, budget, vlists in ((1, 6, 1), (1, 6, 0), (0, 6, 1), (1, 1, 1)):
+            ix.set_option(OPT_STAB_LISTS, lists).set_option(OPT_STAB_BUDGET, budget).set_option(_lib.OPT_STAB_VALUE_LISTS, vlists)
             off, lst = ix.search(pqs, pqe, what, order=ORDER_ASIS)
-            assert np.array_equal(off.cpu().numpy().astype(np.uint64), off_o), (case, what, lists, budget)
-            assert torch.equal(off, off_w) and torch.equal(lst, lst_w), (case, what, lists, budget)
+            assert np.array_equal(off.cpu().numpy().astype(np.uint64), off_o), (case, what, lists, budget, vlists)
+            assert torch.equal(off, off_w) and torch.equal(lst, lst_w), (case, what, lists, budget, vlists)
+        ix.set_option(_lib.OPT_STAB_VALUE_LISTS, 1)
         if key:
             assert np.array_equal(lst_w.cpu().numpy().astype(res[key].dtype).reshape(res[key].shape), res[key]), (case, key)
     ix.set_option(OPT_STAB_LISTS, 1).set_option(OPT_STAB_BUDGET, 6)

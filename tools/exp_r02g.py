@@ -92,6 +92,31 @@ elif what == "c5":
     res["sorted_ms"] = timed(lambda: ix.count(sq, sq, out=c_dir, order=ORDER_SORTED), 5)
     res["sorted_kernels"] = kernels(ix, 5)
     res["bits"] = ix.bits_info()
+elif what == "fill":
+    # C3 search_values with the (value, end) lists on and off: per-kernel times and equality of the results
+    from superintervals_b200._lib import OPT_STAB_VALUE_LISTS
+    s3, e3, qs3, qe3 = W.config3()
+    d3s, d3e = torch.from_numpy(qs3).cuda(), torch.from_numpy(qe3).cuda()
+    keep = {}
+    for vl in (1, 0):
+        ix3 = DeviceIndex()
+        ix3.set_option(OPT_STAB_VALUE_LISTS, vl)
+        ix3.build(torch.from_numpy(s3).cuda(), torch.from_numpy(e3).cuda())
+        off, vals = ix3.search_values(d3s, d3e, order=ORDER_UNSORTED)
+        cnt3 = torch.empty_like(d3s)
+
+        def sv():
+            ix3.count(d3s, d3e, out=cnt3, order=ORDER_UNSORTED)
+            ix3.search_values(d3s, d3e, order=ORDER_UNSORTED, counts=cnt3, offsets=off, out=vals)
+        for _ in range(3):
+            sv()
+        ix3.set_option(OPT_TIMING, 1)
+        res[f"vlists{vl}_ms"] = timed(sv, 10)
+        res[f"vlists{vl}_kernels"] = kernels(ix3, 10)
+        res[f"vlists{vl}_bytes"] = ix3.device_bytes
+        keep[vl] = (off.clone(), vals.clone())
+        del ix3
+    res["equal"] = bool(torch.equal(keep[0][0], keep[1][0]) and torch.equal(keep[0][1], keep[1][1]))
 elif what == "mixed":
     import numpy as np
     from superintervals_b200.genome import GenomeIndex
