@@ -753,8 +753,44 @@ def bench_search_values_split(a, torch, dist, L, _lib, world, rank):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ok = torch.tensor([1.0 if (total == 0 or torch.equal(seg[:total], vals1[base:base + total])) else 0.0], dtype=torch.float64, device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    # ---- the same step with the gather of the counts fused into the count kernel (peer stores + flag barrier, no NCCL call)
+    fused = None
+    try:
+        from superintervals_b200.sharding import PeerGathered
+        pg = PeerGathered(per, world, rank)
+        seg.zero_()
+
+        def fused_step():
+            arr, sl, ptrs = pg.current()
+            if m:
+                ix.count_fanout(mqs, mqe, sl[:m], ptrs, order=ORDER_UNSORTED)
+            pg.barrier()
+            ix.scan(arr, out=offsets)
+            if m:
+                L.siFillDevice(ix._ix, mqs.data_ptr(), mqe.data_ptr(), m, offsets.data_ptr() + 8 * rank * per, FILL_VALUES,
+                               seg.data_ptr() - 4 * base, ORDER_UNSORTED, stream)
+
+        for _ in range(3):
+            fused_step()
+        _lib.check("siFillDevice (split, fused)")
+        torch.cuda.synchronize(); dist.barrier()
+        ms_f = timed_device(torch, fused_step, a.steps)
+        tf = torch.tensor([ms_f], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        okf = torch.tensor([1.0 if ((total == 0 or torch.equal(seg[:total], vals1[base:base + total])) and not pg.timed_out()) else 0.0],
+                           dtype=torch.float64, device="cuda")
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        fused = {"value": nq / (float(tf[0]) * 1e-3), "unit": UNIT, "ms_per_step": float(tf[0]), "segments_equal_single_gpu_values": bool(okf[0] > 0.5),
+                 "how": "counts fanned out to every GPU's gathered vector by the count kernel (peer stores over NVLink) + flag barrier kernel, then scan and fill"}
+        pg.close()
+    except Exception as ex:   # noqa: BLE001
+        fused = {"unavailable": repr(ex)[:300]}
+    use_fused = bool(fused and fused.get("segments_equal_single_gpu_values"))
     return {"workload": f"C3: {n/1e6:g}M heavy-tailed nested intervals x {nq/1e6:g}M queries, search_values CSR, ONE batch cut into {world} ranges",
-            "scaling": "strong", "value": nq / (float(t[0]) * 1e-3), "unit": UNIT, "ms_per_step": float(t[0]),
+            "scaling": "strong", "value": fused["value"] if use_fused else nq / (float(t[0]) * 1e-3), "unit": UNIT,
+            "ms_per_step": fused["ms_per_step"] if use_fused else float(t[0]),
+            "value_is": "count fused with the gather of the counts" if use_fused else "count, ncclAllGather, scan, fill",
+            "value_nccl": nq / (float(t[0]) * 1e-3), "ms_per_step_nccl": float(t[0]), "fused": fused,
             "hits": int(off1[nq].item()), "collective": "ncclAllGather of per-query counts -> global 64-bit offsets on every GPU; value segments stay on their GPU",
             "nccl_bytes_received_per_gpu_per_step": 4 * per * (world - 1),
             "segments_equal_single_gpu_values": bool(ok[0] > 0.5)}
