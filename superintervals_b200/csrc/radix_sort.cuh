@@ -60,6 +60,27 @@ struct RsWorkspace {
     unsigned long long* status;   // [tiles][256] look-back words (re-zeroed per pass)
 };
 
+// Lanes of the warp holding the same 8-bit digit. MATCH.ANY is one instruction but a slow one (r02k: half of the
+// onesweep samples wait on it); eight ballots give the same mask from instructions that pipeline (SIB_RS_MATCH=1
+// restores the match instruction).
+#ifndef SIB_RS_MATCH
+#define SIB_RS_MATCH 0
+#endif
+__device__ __forceinline__ uint32_t rs_same_digit(uint32_t d) {
+#if SIB_RS_MATCH
+    return __match_any_sync(FULL_MASK, d);
+#else
+    uint32_t m = FULL_MASK;
+#pragma unroll
+    for (int b = 0; b < RS_RADIX_BITS; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t v = __ballot_sync(FULL_MASK, bit);
+        m &= bit ? v : ~v;
+    }
+    return m;
+#endif
+}
+
 template <typename KeyT>
 __host__ inline uint32_t rs_num_tiles(uint32_t n) {
     constexpr uint32_t TILE = RS_THREADS * RsTraits<KeyT>::ITEMS;
@@ -192,10 +213,13 @@ rs_onesweep_kernel(KeyT* __restrict__ kA, KeyT* __restrict__ kB,
     uint32_t rank[ITEMS];
     uint32_t* wh = s_whist + warp * RS_RADIX;
     const uint32_t lt = lanemask_lt();
+    uint32_t same[ITEMS];   // the masks first: they do not depend on the histogram chain below
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) same[k] = rs_same_digit((uint32_t)((key[k] >> shift) & (RS_RADIX - 1)));
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         uint32_t d = (uint32_t)((key[k] >> shift) & (RS_RADIX - 1));
-        uint32_t peers = __match_any_sync(FULL_MASK, d);
+        uint32_t peers = same[k];
         uint32_t leader = __ffs(peers) - 1;
         uint32_t pre = 0;
         if (lane == leader) {
