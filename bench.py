@@ -918,7 +918,32 @@ def bench_c4(a, torch, dist, world, rank):
             "value": float(tot[0]) / (float(t[0]) * 1e-3), "unit": UNIT, "ms_per_step": float(t[0]), "build_ms_max_over_ranks": float(t[1]),
             "step": step, "index": "partitioned by contig (each GPU holds the contigs it owns)" if world > 1 else "all 24 contig indexes on the one GPU",
             "nccl_dispatch_bytes_per_step": int(tot[2]), "nccl_combine_bytes_per_step": int(tot[3]), "hits_rank0": hits, "parity": par,
-            "owner": [int(x) for x in gi.owner], "replicated": repl}
+            "owner": [int(x) for x in gi.owner], "replicated": repl,
+            "pair_cells": (lambda own: gi.index(own[0]).cells_info()["pair"] if own else None)(gi.owned),
+            "pair_cells_are": "this rank's first contig: both ranks of a coordinate cell in one 32-byte record, one sector per query whose ends share a cell "
+                              "(GenomeIndex builds them when the owned contigs' rank cells cannot share L2)"}
+
+
+
+def cells_read_bytes(ci):
+    """bytes of rank tables a count reads: the pair cells when they answer, else both rank-cell tables"""
+    if ci.get("pair", {}).get("format"):
+        return ci["pair"]["bytes"]
+    return ci["starts"]["bytes"] + ci["ends"]["bytes"]
+
+
+# tools/hbm_gather.cu on B200 (profiles/hbm_gather_r02.json): random 32-byte sector reads from a table far larger than L2
+# are served at 37-43 G sectors/s, and an adjacent pair of sectors costs exactly two
+HBM_SECTORS_PER_S = {"peak": 37.05e9, "table_gb": 8.0, "source": "tools/hbm_gather.cu on B200 (profiles/hbm_gather_r02.json), 8 GB table"}
+
+
+def sector_gather(ci, nq, ms, stabs):
+    """the random-sector roofline of a count whose tables live in HBM: sectors gathered per second against the measured rate"""
+    per_query = 1.0 if (ci.get("pair", {}).get("format") and stabs) else 2.0
+    rate = per_query * nq / (ms * 1e-3)
+    return {"sectors_per_query": per_query, "achieved_sectors_per_s": rate, "peak_sectors_per_s": HBM_SECTORS_PER_S["peak"],
+            "frac": rate / HBM_SECTORS_PER_S["peak"], "peak_source": HBM_SECTORS_PER_S["source"],
+            "note": "the peak is the rate for an 8 GB table; smaller tables are served faster (43 G/s at 1 GB, 73 G/s at 256 MB), so frac can exceed 1"}
 
 
 def bench_configs(a, torch, dist, L, _lib, world, rank):
@@ -992,7 +1017,8 @@ def bench_configs(a, torch, dist, L, _lib, world, rank):
                       "count": {"value": 2 * n5 / (ms5 * 1e-3), "unit": UNIT, "ms_per_step": ms5, "kernels": k5,
                                 "hits_per_query": float(c5.to(torch.float64).mean().item())},
                       "rank_cells": ci,
-                      "frac_hbm_compulsory": (12.0 * 2 * n5 + ci["starts"]["bytes"] + ci["ends"]["bytes"]) / (ms5 * 1e-3) / 1e9 / peak,
+                      "frac_hbm_compulsory": (12.0 * 2 * n5 + cells_read_bytes(ci)) / (ms5 * 1e-3) / 1e9 / peak,
+                      "hbm_sector_gather": sector_gather(ci, 2 * n5, ms5, stabs=True),
                       "parity": {"checked": m, "mismatches": int((got != want).sum()), "against": kind}}
     del ix, s5, e5, q5, c5
     torch.cuda.empty_cache()
@@ -1030,9 +1056,12 @@ def bench_configs(a, torch, dist, L, _lib, world, rank):
         res["c5"] = {"workload": f"C5 (BASELINE configs[4]): {n5f/1e9:g} B intervals (150bp-10kb) on a 2e9 axis, build() on device + {n5f/1e9:g} B stabbing queries",
                      "build": {"ms": bms, "intervals_per_s": n5f / (bms * 1e-3), "sort_path": ix.last_sort()},
                      "count": {"value": n5f / (ms5 * 1e-3), "unit": UNIT, "ms_per_step": ms5, "hits_per_query": float(c5[:10_000_000].to(torch.float64).mean().item()),
-                               "step": "one launch of the rank-cells kernel: both 32-byte sectors of a query gathered from HBM (the tables are far larger than L2)"},
+                               "step": ("one launch of the rank-cells kernel on the pair cells: both ranks of a stabbing query in ONE 32-byte sector gathered from HBM"
+                                        if ci["pair"]["format"] else
+                                        "one launch of the rank-cells kernel: both 32-byte sectors of a query gathered from HBM (the tables are far larger than L2)")},
+                     "hbm_sector_gather": sector_gather(ci, n5f, ms5, stabs=True),
                      "rank_cells": ci, "device_bytes": ix.device_bytes,
-                     "frac_hbm_compulsory": (12.0 * n5f + ci["starts"]["bytes"] + ci["ends"]["bytes"]) / (ms5 * 1e-3) / 1e9 / peak,
+                     "frac_hbm_compulsory": (12.0 * n5f + cells_read_bytes(ci)) / (ms5 * 1e-3) / 1e9 / peak,
                      "parity": {"checked": int(sel.numel()), "mismatches": int((got != want).sum()), "against": kind,
                                 "how": f"the stabbing queries that fall in [{w0}, {w1}] against the reference built on the {hs.size} intervals that can reach that window"}}
         del ix, q5, c5

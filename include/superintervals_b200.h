@@ -189,6 +189,9 @@ enum { SI_OPT_COUNT_ALGO = 0, SI_OPT_BUCKET_INTERVALS = 1, SI_OPT_WINDOW_SHIFT =
                                     on demand. 0 (or SIB_RESIDENT_QUERIES=0 in the environment): one launch per call */
        SI_OPT_STAB_VALUE_LISTS = 14, /* 1 (default): short stab lists (8-byte records) are kept twice, as (position, end) and as (value, end),
                                     so that search_values reads a hit's payload with its record instead of gathering it; 0: positions only */
+       SI_OPT_PAIR_CELLS = 15, /* pair cells: both ranks of a coordinate cell in ONE 32-byte record, so that a stabbing or short query
+                                    gathers one sector instead of two. 1 (default): built when the rank cells exceed 3/4 of L2 (the gather
+                                    is then served by HBM, which charges per sector); 0: never; 2: always. Applies to the next build */
        SI_OPT_STREAM_BUDGET = 10 /* rank bits are built when they cost at most this many bytes per interval (default 64; 0 = never); next build */ };
 enum { SI_COUNT_AUTO = 0, SI_COUNT_WALK = 1, SI_COUNT_RANK = 2, SI_COUNT_CELLS = 3 };
 int siIndexSetOption(siIndex* ix, int option, long long value);
@@ -198,7 +201,9 @@ int siIndexLastSort(const siIndex* ix);
 /* The rank cells build() made (which = 0: over starts, 1: over ends). format 0 = none
  * (malformed index or >= 2^31 intervals), 1 = 28 one-byte offsets, 2 = 14 two-byte offsets per
  * 32-byte cell of 2^shift coordinates; overfull = cells answered from the sorted array instead;
- * direct = 1 when count answers unpartitioned batches straight from the cells. */
+ * direct = 1 when count answers unpartitioned batches straight from the cells.
+ * which = 2: the pair cells (SI_OPT_PAIR_CELLS); format 0 = not built, 4 = 24 four-bit offsets per side in cells of
+ * 16 coordinates, 8 = 12 one-byte offsets per side; overfull = sides answered from the sorted arrays. */
 typedef struct {
     unsigned format, shift;
     unsigned long long cells, bytes, overfull;

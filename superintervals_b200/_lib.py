@@ -20,6 +20,7 @@ OPT_COUNT_ALGO, OPT_BUCKET_INTERVALS, OPT_WINDOW_SHIFT, OPT_TIMING, OPT_GRID_INT
 OPT_CELLS_DIRECT_BYTES, OPT_CELLS_FILL = 5, 6
 OPT_STAB_LISTS, OPT_STAB_BUDGET = 7, 8
 OPT_STREAM, OPT_STREAM_BUDGET, OPT_L2_PERSIST, OPT_NARROW_SORT, OPT_RESIDENT_QUERIES, OPT_STAB_VALUE_LISTS = 9, 10, 11, 12, 13, 14
+OPT_PAIR_CELLS = 15
 TAG_NAMES = {1: "pt_histogram", 2: "pt_onesweep", 3: "count_walk", 4: "count_rank", 5: "scan", 6: "fill", 7: "count_cells", 8: "fill_runs", 9: "count_stream"}
 COUNT_AUTO, COUNT_WALK, COUNT_RANK, COUNT_CELLS = 0, 1, 2, 3
 

@@ -327,6 +327,11 @@ int search_batch(Handle* h, const int32_t* qs, const int32_t* qe, size_t n, size
         rc = siFillDevice(ix, dqs, dqe, n, ix->h_offsets.as<uint64_t>(), what, ix->h_out.p, order, ix->own_stream);
         if (rc) return rc;
     }
+    // a pinned result array (result_realloc registers the large ones) takes its DMA now: the values travel while the host
+    // stages the offsets below, instead of after it
+    char* vdst = total ? reinterpret_cast<char*>(found->data) + found->size * elem : nullptr;
+    const bool vals_async = total && total * elem > DIRECT_BYTES && is_pinned(vdst);
+    if (vals_async) SIB_CHECK(cudaMemcpyAsync(vdst, ix->h_out.p, total * elem, cudaMemcpyDeviceToHost, ix->own_stream));
     if (offsets_out) {
         if (!ix->pipe_ready_out) {
             SIB_CHECK(cudaStreamCreateWithFlags(&ix->s_out2, cudaStreamNonBlocking));
@@ -337,8 +342,11 @@ int search_batch(Handle* h, const int32_t* qs, const int32_t* qe, size_t n, size
         if (rc) return rc;
     }
     if (total == 0) return 0;
-    rc = copy_d2h(ix, reinterpret_cast<char*>(found->data) + found->size * elem, ix->h_out.p, total * elem, ix->own_stream);
-    if (rc) return rc;
+    if (vals_async) SIB_CHECK(cudaStreamSynchronize(ix->own_stream));
+    else {
+        rc = copy_d2h(ix, vdst, ix->h_out.p, total * elem, ix->own_stream);
+        if (rc) return rc;
+    }
     found->size += total;
     return 0;
 }

@@ -183,7 +183,7 @@ using namespace sib;
     } while (0)
 
 size_t siIndex::device_bytes() const {
-    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &esort, &eall, &grid_tab, &cells_s, &cells_e, &bits_s_t, &bits_s_d, &bits_e_t, &bits_e_d, &stream_ws, &starts_wf, &stab_off, &stab_hdr, &stab_ent, &stab_entv, &stab_cnt, &b_in_s, &b_in_e, &b_in_v,
+    const DevBuf* all[] = {&starts, &ends, &values, &branch, &perm, &tree, &esort, &eall, &grid_tab, &cells_s, &cells_e, &pair_cells, &bits_s_t, &bits_s_d, &bits_e_t, &bits_e_d, &stream_ws, &starts_wf, &stab_off, &stab_hdr, &stab_ent, &stab_entv, &stab_cnt, &b_in_s, &b_in_e, &b_in_v,
                            &b_kA, &b_kB, &b_vA, &b_vB, &b_ws, &small, &q_A, &q_B,
                            &q_ws, &scan_status, &h_qs, &h_qe, &h_counts, &h_offsets, &h_out, &h_cov};
     size_t s = 0;
@@ -224,6 +224,8 @@ IndexView view_of(const siIndex* ix) {
     v.grid.cells = ix->grid_cells;
     v.cells_s = RankCells{ix->cells_s.as<uint4>(), ix->cm_s.lo, ix->cm_s.span, ix->cm_s.shift, ix->cm_s.fmt};
     v.cells_e = RankCells{ix->cells_e_ptr, ix->cm_e.lo, ix->cm_e.span, ix->cm_e.shift, ix->cm_e.fmt};
+    v.pair = ix->pair_ok ? PairCells{ix->pair_cells.as<uint4>(), ix->cm_pair.lo, ix->cm_pair.span, ix->cm_pair.shift, ix->cm_pair.fmt}
+                         : PairCells{nullptr, 0, 0u, 0u, 0u};
     const bool bits = ix->bits_ok;
     v.bits_s = RankBits{bits ? ix->bits_s_t.as<uint2>() : nullptr, ix->bits_s_d.as<uint32_t>(), ix->cm_s.lo, ix->cm_s.span, ix->bits_words_s};
     v.bits_e = RankBits{bits ? ix->bits_e_t.as<uint2>() : nullptr, ix->bits_e_d.as<uint32_t>(), ix->cm_e.lo, ix->cm_e.span, ix->bits_words_e};
@@ -331,6 +333,42 @@ int cells_fill(siIndex* ix, const int32_t* A, uint32_t n, const siIndex::CellsMe
         SIB_LAUNCH((bk_rank_cells_kernel<1>), grid, BK_THREADS, 0, s, A, n, m.lo, m.shift, m.cells, rec, d_overfull);
     else
         SIB_LAUNCH((bk_rank_cells_kernel<2>), grid, BK_THREADS, 0, s, A, n, m.lo, m.shift, m.cells, rec, d_overfull);
+    return 0;
+}
+
+// Pair cells over both arrays (PairCells in query_kernels.cuh). Format by density: four-bit offsets in cells of 16
+// coordinates when a cell would hold 3-11 values per side on average, else one-byte offsets in the widest cell
+// (<= 256 coordinates) with a mean of at most 4 per side. Returns false when neither fits (denser than ~0.7 values per
+// coordinate) or the table would cost more than 16 B per interval... the caller then keeps the separate tables only.
+bool pair_plan(uint32_t n, int64_t first, int64_t last, siIndex::CellsMeta* m) {
+    if (first < (int64_t)INT32_MIN || last - first >= (int64_t)0xFFFFFFF0ll) return false;
+    const uint64_t range = (uint64_t)(last - first) + 1;
+    uint32_t fmt, shift;
+    if ((uint64_t)n * 16 >= 3 * range) {
+        if ((uint64_t)n * 16 > 11 * range) return false;
+        fmt = 4; shift = 4;
+    } else {
+        fmt = 8; shift = 0;
+        while (shift < 8 && ((uint64_t)n << (shift + 1)) <= 4 * range) ++shift;
+    }
+    const uint64_t cells = (range >> shift) + 1;          // the cell of last + 1 included
+    if (cells * 32 > (uint64_t)n * 24 + (1u << 20)) return false;   // too sparse to be worth its memory
+    m->lo = (int32_t)first;
+    m->span = (uint32_t)(range - 1);
+    m->shift = shift;
+    m->cells = (uint32_t)cells;
+    m->fmt = fmt;
+    m->overfull = 0;
+    return true;
+}
+int pair_fill(siIndex* ix, const int32_t* S, const int32_t* E, uint32_t n, const siIndex::CellsMeta& m, unsigned long long* d_overfull, cudaStream_t s) {
+    const RankCells cs{ix->cells_s.as<uint4>(), ix->cm_s.lo, ix->cm_s.span, ix->cm_s.shift, ix->cm_s.fmt};
+    const RankCells ce{ix->cells_e_ptr, ix->cm_e.lo, ix->cm_e.span, ix->cm_e.shift, ix->cm_e.fmt};
+    const int grid = grid_for((uint64_t)m.cells + 1, PC_BUILD_THREADS, ix->sm_count * 16);
+    if (m.fmt == 4)
+        SIB_LAUNCH((bk_pair_cells_kernel<4>), grid, PC_BUILD_THREADS, 0, s, cs, ce, S, E, n, m.lo, m.shift, m.cells, ix->pair_cells.as<uint4>(), d_overfull);
+    else
+        SIB_LAUNCH((bk_pair_cells_kernel<8>), grid, PC_BUILD_THREADS, 0, s, cs, ce, S, E, n, m.lo, m.shift, m.cells, ix->pair_cells.as<uint4>(), d_overfull);
     return 0;
 }
 
@@ -521,6 +559,26 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
             if (rc) return rc;
             ix->cm_s = ms;
             ix->cm_e = me;
+            // pair cells: only where the gather is served by HBM (rank cells beyond 3/4 of L2), or on request
+            ix->pair_ok = false;
+            ix->pair_counters_pending = false;
+            if (ix->pair_mode == 2 || (ix->pair_mode == 1 && ix->cells_total_bytes > (ix->l2_bytes / 4) * 3)) {
+                siIndex::CellsMeta mp;
+                const int64_t pfirst = std::min<int64_t>((int64_t)first_start - 1, (int64_t)first_end);
+                const int64_t plast = std::max<int64_t>((int64_t)last_start - 1, (int64_t)ix->hi);
+                if (pair_plan(nr, pfirst, plast, &mp)) {
+                    if (ix->pair_cells.ensure(((size_t)mp.cells + 1) * 32)) return last_error_code();
+                    unsigned long long* d_pover = reinterpret_cast<unsigned long long*>(ix->small.as<uint32_t>() + 58);
+                    SIB_CHECK(cudaMemsetAsync(d_pover, 0, 16, s));
+                    rc = pair_fill(ix, rstarts, ix->eall.as<int32_t>(), nr, mp, d_pover, s);
+                    if (rc) return rc;
+                    ix->cm_pair = mp;
+                    ix->pair_ok = true;
+                    SIB_CHECK(cudaMemcpyAsync(ix->pair_counters, d_pover, 16, cudaMemcpyDeviceToHost, s));
+                    ix->pair_counters_pending = true;
+                }
+            }
+            if (!ix->pair_ok) ix->pair_cells.release();
             // rank bits for the streaming count: only where they stay affordable next to the index
             const uint64_t words = (((uint64_t)ix->cm_s.span + 1) >> 5) + (((uint64_t)ix->cm_e.span + 1) >> 5) + 16;
             ix->bits_pending_words = 0;
@@ -559,6 +617,12 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
 
 // the counters the build's kernels left behind, once its stream has been synchronised
 void finish_build(siIndex* ix) {
+    if (ix->pair_counters_pending) {
+        ix->pair_counters_pending = false;
+        ix->cm_pair.overfull = ix->pair_counters[0] + ix->pair_counters[1];
+        // an over-full side costs a halving search in HBM: beyond one side in a thousand the separate tables answer
+        if (ix->cm_pair.overfull * 1000 > (unsigned long long)ix->cm_pair.cells * 2) ix->pair_ok = false;
+    }
     if (!ix->build_counters_pending) return;
     ix->build_counters_pending = false;
     ix->cm_s.overfull = ix->build_counters[0];
@@ -676,7 +740,10 @@ int launch_count(siIndex* ix, const QueryRecords& rec, uint32_t nq, CountT* d_co
             ix->timer.end(s);
             note_launch();
         } else {
-            SIB_LAUNCH_T(ix, TAG_COUNT_CELLS, (qk_count_cells_kernel<CountT>), grid, QC_THREADS, 0, s, view_of(ix), rec, nq, d_counts, fan);
+            if (ix->pair_ok)
+                SIB_LAUNCH_T(ix, TAG_COUNT_CELLS, (qk_count_cells_kernel<CountT, true>), grid, QC_THREADS, 0, s, view_of(ix), rec, nq, d_counts, fan);
+            else
+                SIB_LAUNCH_T(ix, TAG_COUNT_CELLS, (qk_count_cells_kernel<CountT>), grid, QC_THREADS, 0, s, view_of(ix), rec, nq, d_counts, fan);
         }
     } else if (algo == SI_COUNT_RANK) {
         const int grid = (int)(((uint64_t)nq + QR_TILE - 1) / QR_TILE);
@@ -919,7 +986,7 @@ void siIndexDestroy(siIndex* ix) {
     si_b200_server_stop_(ix);
     if (ix->srv_stream) cudaStreamDestroy(ix->srv_stream);
     DevBuf* all[] = {&ix->starts, &ix->ends, &ix->values, &ix->branch, &ix->perm, &ix->tree, &ix->esort, &ix->eall, &ix->grid_tab,
-                     &ix->cells_s, &ix->cells_e, &ix->bits_s_t, &ix->bits_s_d, &ix->bits_e_t, &ix->bits_e_d, &ix->stream_ws, &ix->mixed_tab, &ix->starts_wf, &ix->stab_off, &ix->stab_hdr, &ix->stab_ent, &ix->stab_entv, &ix->stab_cnt,
+                     &ix->cells_s, &ix->cells_e, &ix->pair_cells, &ix->bits_s_t, &ix->bits_s_d, &ix->bits_e_t, &ix->bits_e_d, &ix->stream_ws, &ix->mixed_tab, &ix->starts_wf, &ix->stab_off, &ix->stab_hdr, &ix->stab_ent, &ix->stab_entv, &ix->stab_cnt,
                      &ix->b_in_s, &ix->b_in_e, &ix->b_in_v, &ix->b_kA, &ix->b_kB, &ix->b_vA, &ix->b_vB, &ix->b_ws,
                      &ix->small, &ix->q_A, &ix->q_B, &ix->q_ws, &ix->scan_status, &ix->h_qs,
                      &ix->h_qe, &ix->h_counts, &ix->h_offsets, &ix->h_out, &ix->h_cov};
@@ -942,7 +1009,17 @@ size_t siIndexSize(const siIndex* ix) { return ix ? ix->n : 0; }
 size_t siIndexDeviceBytes(const siIndex* ix) { return ix ? ix->device_bytes() : 0; }
 
 int siIndexCellsInfo(const siIndex* ix, int which, siCellsInfo* out) {
-    if (!ix || !out || !ix->built || which < 0 || which > 1) return cudaErrorInvalidValue;
+    if (!ix || !out || !ix->built || which < 0 || which > 2) return cudaErrorInvalidValue;
+    if (which == 2) {   // the pair cells
+        const bool ok = ix->pair_ok;
+        out->format = ok ? ix->cm_pair.fmt : 0;
+        out->shift = ok ? ix->cm_pair.shift : 0;
+        out->cells = ok ? (unsigned long long)ix->cm_pair.cells + 1 : 0;
+        out->bytes = out->cells * 32;
+        out->overfull = ok ? ix->cm_pair.overfull : 0;
+        out->direct = ok ? 1 : 0;
+        return 0;
+    }
     const siIndex::CellsMeta& m = which ? ix->cm_e : ix->cm_s;
     out->format = m.fmt;
     out->shift = m.shift;
@@ -1160,6 +1237,10 @@ int siIndexSetOption(siIndex* ix, int option, long long value) {
             ix->l2_persist = value != 0;
             if (ix->l2_persist) raise_persisting_set_aside(ix);
             return 0;
+        case SI_OPT_PAIR_CELLS:            // 0: never; 1 (default): when the rank cells exceed 3/4 of L2; 2: always; applies to the next build
+            if (value < 0 || value > 2) break;
+            ix->pair_mode = (int)value;
+            return 0;
         case SI_OPT_WINDOW_SHIFT:
             if (value < 10 || value > 31) break;
             ix->window_shift = (uint32_t)value;
@@ -1367,7 +1448,7 @@ int siCountMixedDevice(siIndex* const* ixs, int n_contigs, const int32_t* d_cont
         if (!ix || !ix->built || ix->n == 0) continue;
         const IndexView v = view_of(ix);
         MixedEntry& e = tab[(size_t)k];
-        e.cs = v.cells_s; e.ce = v.cells_e; e.rstarts = v.rstarts; e.eall = v.eall; e.ends = v.ends; e.branch = v.branch;
+        e.cs = v.cells_s; e.ce = v.cells_e; e.pc = v.pair; e.rstarts = v.rstarts; e.eall = v.eall; e.ends = v.ends; e.branch = v.branch;
         e.n = v.n; e.n_mal = v.n_mal;
         for (int a = 0; a < 8; ++a) { e.mal_s[a] = v.mal_s[a]; e.mal_e[a] = v.mal_e[a]; }
     }

@@ -89,6 +89,14 @@ struct siIndex {
     bool l2_persist = false;                       // SI_OPT_L2_PERSIST / SIB_L2_PERSIST (off: the set-aside costs every other kernel more than it gives, r02g)
     size_t l2_persist_max = 0;                     // cudaLimitPersistingL2CacheSize in force
     CellsMeta cm_s, cm_e;
+    // pair cells (PairCells in query_kernels.cuh): both ranks of a coordinate cell in one record, for indexes whose
+    // rank cells do not fit L2 -- a stabbing or short query then gathers one sector from HBM instead of two
+    sib::DevBuf pair_cells;
+    CellsMeta cm_pair;                             // overfull = over-full sides
+    bool pair_ok = false;
+    int pair_mode = 1;                             // SI_OPT_PAIR_CELLS: 0 never, 1 when the rank cells exceed 3/4 of L2, 2 always; next build
+    unsigned long long pair_counters[2] = {0, 0};
+    bool pair_counters_pending = false;
     uint32_t cells_fill8 = 16, cells_fill16 = 7;   // target mean values per cell (28 / 14 slots)
     size_t cells_direct_bytes = 0;                 // cells up to this size answer unpartitioned batches (0: always)
     size_t l2_bytes = 0;

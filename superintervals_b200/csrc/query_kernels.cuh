@@ -53,6 +53,22 @@ struct RankCells {
     uint32_t fmt;       // 0 = not built
 };
 
+// Pair cells (build(), only when the rank cells outgrow L2): BOTH ranks of a coordinate cell in one 32-byte record,
+//   word 0 = #{ starts - 1 < cell_lo }, word 1 = #{ eall < cell_lo }   (bit 31: that side holds more values than fit)
+//   words 2-4 = the cell's (starts - 1) values, words 5-7 = its ends, as ascending offsets from cell_lo, padded with
+//   all-ones: 24 x 4 bits per side (fmt 4, cells of 16 coordinates) or 12 x 8 bits (fmt 8, cells of <= 256).
+// #{starts <= qe} = #{starts - 1 < qe} is read in the cell of qe, #{ends < qs} in the cell of qs: a stabbing or short
+// query finds both in ONE sector. A table in HBM is charged per 32-byte sector (tools/hbm_gather.cu: an adjacent
+// pair of sectors costs exactly two), so this halves the gather of such queries; range queries whose ends fall in
+// different cells read two records, as with the separate tables.
+struct PairCells {
+    const uint4* rec;   // 2 x uint4 per cell, cells + 1 records (the last is a sentinel with words 0, 1 = n)
+    int32_t lo;         // coordinate of cell 0
+    uint32_t span;      // largest covered value - lo
+    uint32_t shift;
+    uint32_t fmt;       // 0 = not built, 4, 8
+};
+
 // Rank bits (build(), dense well-formed indexes only; stream_kernels.cuh): the same sorted array A as
 // bit maps, one entry per 32 coordinates -- what the streaming count kernel stages in shared memory.
 //   t[k]  = { #{A < lo + 32k} | flags (bits 31, 30),  coordinates of word k holding >= 1 value }
@@ -104,6 +120,7 @@ struct IndexView {
     RankGrid grid;           // rank tables for qk_count_rank_kernel; only on a well-formed index
     RankCells cells_s;       // rank cells over starts  } qk_count_cells_kernel; only on a well-formed
     RankCells cells_e;       // rank cells over eall    } index of fewer than 2^31 intervals
+    PairCells pair;          // both ranks per record; built when the rank cells do not fit L2 (fmt == 0 otherwise)
     StabLists stab;          // qk_fill_runs_kernel's lists; ent == nullptr -> it walks instead
     RankBits bits_s;         // rank bits over starts  } sk_count_stream_kernel; only on a dense well-formed
     RankBits bits_e;         // rank bits over eall    } index (t == nullptr otherwise)
@@ -602,8 +619,103 @@ __device__ __forceinline__ uint32_t cells_rank_lt(const RankCells& rc, const int
     return cell_rank(rc, A, r, cell, off, x);
 }
 
+// ---- pair cells -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pair_cell_of(const PairCells& pc, int32_t x, uint32_t& cell, uint32_t& off) {
+    int64_t d = (int64_t)x - (int64_t)pc.lo;
+    d = d < 0 ? 0 : d;
+    const int64_t dmax = (int64_t)pc.span + 1;
+    d = d > dmax ? dmax : d;
+    cell = (uint32_t)((uint64_t)d >> pc.shift);
+    off = (uint32_t)d & ((1u << pc.shift) - 1u);
+}
+// #{ offsets of one side < off }: the SWAR compare of cell_below over three words, 4- or 8-bit lanes
+template <int FIRST>
+__device__ __forceinline__ uint32_t pair_below(const CellRec& r, uint32_t off, uint32_t fmt) {
+    const uint32_t H = fmt == 4u ? 0x88888888u : 0x80808080u;
+    const uint32_t t = off * (fmt == 4u ? 0x11111111u : 0x01010101u);
+    const uint32_t tl = t & ~H;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const uint32_t a = r.w[FIRST + k];
+        const uint32_t d = (a | H) - tl;
+        const uint32_t lt = (~a & t) | (~(a ^ t) & ~d);
+        acc |= (lt & H) >> k;
+    }
+    return __popc(acc);
+}
+// an over-full side: halving search inside the cell's run of A; SUB = 1 ranks A - 1 (the starts side)
+template <int SIDE>
+__device__ __noinline__ uint32_t pair_overflow_rank(const PairCells& pc, const int32_t* __restrict__ A, uint32_t cell, uint32_t base, int32_t x) {
+    const uint32_t next = __ldg(reinterpret_cast<const uint32_t*>(pc.rec + 2 * ((size_t)cell + 1)) + SIDE) & 0x7FFFFFFFu;
+    uint32_t lo = base, len = next - base;
+    while (len) {
+        const uint32_t half = len >> 1;
+        const bool below = SIDE == 0 ? (int64_t)ld_nc(A + lo + half) - 1 < (int64_t)x : (int64_t)ld_nc(A + lo + half) < (int64_t)x;
+        lo += below ? half + 1u : 0u;
+        len = below ? len - half - 1u : half;
+    }
+    return lo;
+}
+// SIDE 0: #{ starts <= x } from the record of x's cell; SIDE 1: #{ eall < x }
+template <int SIDE>
+__device__ __forceinline__ uint32_t pair_rank(const PairCells& pc, const int32_t* __restrict__ A, const CellRec& r, uint32_t cell, uint32_t off, int32_t x) {
+    const uint32_t b = r.w[SIDE];
+    if (b & 0x80000000u) return pair_overflow_rank<SIDE>(pc, A, cell, b & 0x7FFFFFFFu, x);
+    return b + pair_below<SIDE == 0 ? 2 : 5>(r, off, pc.fmt);
+}
+
+// ---- pair cells: both ranks of a coordinate cell in one record (layout: PairCells in query_kernels.cuh) ----
+// One thread per cell; the ranks at the cell borders come from the rank cells built just before (one sector each,
+// neighbouring threads share them). Side 0 stores starts - 1 (so that "< x" reads #{starts <= x}), side 1 the ends.
+// FMT 4: 24 four-bit offsets per side, FMT 8: 12 one-byte offsets. overfull[0,1] count the sides that did not fit.
+constexpr int PC_BUILD_THREADS = 256;
+template <int FMT>
+__global__ void __launch_bounds__(PC_BUILD_THREADS)
+bk_pair_cells_kernel(RankCells cs, RankCells ce, const int32_t* __restrict__ S, const int32_t* __restrict__ E, uint32_t n,
+                     int32_t lo, uint32_t shift, uint32_t cells, uint4* __restrict__ rec, unsigned long long* __restrict__ overfull) {
+    constexpr uint32_t SLOTS = FMT == 4 ? 24u : 12u;
+    constexpr uint32_t BITS = FMT == 4 ? 4u : 8u;
+    constexpr uint32_t PER_WORD = 32u / BITS;
+    constexpr uint32_t LANE = (1u << BITS) - 1u;
+    const uint64_t stride = (uint64_t)gridDim.x * PC_BUILD_THREADS;
+    for (uint64_t c = (uint64_t)blockIdx.x * PC_BUILD_THREADS + threadIdx.x; c <= cells; c += stride) {
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = 0xFFFFFFFFu;
+        if (c == cells) {                       // sentinel: the next-base words of the last cell
+            w[0] = n; w[1] = n;
+        } else {
+            const int64_t v0 = (int64_t)lo + (int64_t)(c << shift);
+            const int64_t v1 = v0 + ((int64_t)1 << shift);
+            // #{S - 1 < v} = #{S < v + 1};  #{E < v}
+            const uint32_t s0 = cells_rank_lt(cs, S, v0 + 1), s1 = cells_rank_lt(cs, S, v1 + 1);
+            const uint32_t e0 = cells_rank_lt(ce, E, v0), e1 = cells_rank_lt(ce, E, v1);
+            w[0] = s0; w[1] = e0;
+            if (s1 - s0 > SLOTS) { w[0] |= 0x80000000u; atomicAdd(overfull, 1ull); }
+            else
+                for (uint32_t k = 0; k < s1 - s0; ++k) {
+                    const uint32_t off = (uint32_t)((int64_t)S[s0 + k] - 1 - v0), sh = (k % PER_WORD) * BITS;
+                    const uint32_t word = 2u + k / PER_WORD;
+#pragma unroll
+                    for (uint32_t q = 2; q < 5; ++q) if (q == word) w[q] = (w[q] & ~(LANE << sh)) | (off << sh);
+                }
+            if (e1 - e0 > SLOTS) { w[1] |= 0x80000000u; atomicAdd(overfull + 1, 1ull); }
+            else
+                for (uint32_t k = 0; k < e1 - e0; ++k) {
+                    const uint32_t off = (uint32_t)((int64_t)E[e0 + k] - v0), sh = (k % PER_WORD) * BITS;
+                    const uint32_t word = 5u + k / PER_WORD;
+#pragma unroll
+                    for (uint32_t q = 5; q < 8; ++q) if (q == word) w[q] = (w[q] & ~(LANE << sh)) | (off << sh);
+                }
+        }
+        rec[2 * c] = make_uint4(w[0], w[1], w[2], w[3]);
+        rec[2 * c + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+
 // one tile of QC_TILE queries starting at `base` (whole CTA)
-template <typename CountT>
+template <typename CountT, bool PAIRED>
 __device__ __forceinline__ void count_cells_tile(const IndexView& ix, const QueryRecords& rec, uint64_t base, uint32_t nq,
                                                  CountT* __restrict__ counts, const Fanout& fan) {
     const uint32_t tid = threadIdx.x;
@@ -629,8 +741,18 @@ __device__ __forceinline__ void count_cells_tile(const IndexView& ix, const Quer
     // all sector loads of the thread's queries in flight together
     uint32_t cell_s[QC_PER_THREAD], off_s[QC_PER_THREAD], cell_e[QC_PER_THREAD], off_e[QC_PER_THREAD];
     CellRec rs[QC_PER_THREAD], re[QC_PER_THREAD];
+    const PairCells pc = ix.pair;
+    constexpr bool paired = PAIRED;        // the launch is compiled for one table kind
 #pragma unroll
     for (int j = 0; j < QC_PER_THREAD; ++j) {
+        if (paired) {     // both ranks from the pair table: one sector when qs and qe share a cell
+            pair_cell_of(pc, qe[j], cell_s[j], off_s[j]);
+            pair_cell_of(pc, qs[j], cell_e[j], off_e[j]);
+            rs[j] = ld_cell(pc.rec + 2 * (size_t)cell_s[j]);
+            re[j] = rs[j];
+            if (cell_e[j] != cell_s[j]) re[j] = ld_cell(pc.rec + 2 * (size_t)cell_e[j]);
+            continue;
+        }
         cell_of(cs, (int64_t)qe[j] + 1, cell_s[j], off_s[j]);   // #{starts <= qe} = #{starts < qe + 1}
         cell_of(ce, (int64_t)qs[j], cell_e[j], off_e[j]);       // #{ends < qs}
 #ifdef SIB_QC_HINTS
@@ -643,8 +765,10 @@ __device__ __forceinline__ void count_cells_tile(const IndexView& ix, const Quer
     }
 #pragma unroll
     for (int j = 0; j < QC_PER_THREAD; ++j) {
-        const uint32_t ns = cell_rank(cs, ix.rstarts, rs[j], cell_s[j], off_s[j], (int64_t)qe[j] + 1);
-        const uint32_t ne = cell_rank(ce, ix.eall, re[j], cell_e[j], off_e[j], (int64_t)qs[j]);
+        const uint32_t ns = paired ? pair_rank<0>(pc, ix.rstarts, rs[j], cell_s[j], off_s[j], qe[j])
+                                   : cell_rank(cs, ix.rstarts, rs[j], cell_s[j], off_s[j], (int64_t)qe[j] + 1);
+        const uint32_t ne = paired ? pair_rank<1>(pc, ix.eall, re[j], cell_e[j], off_e[j], qs[j])
+                                   : cell_rank(ce, ix.eall, re[j], cell_e[j], off_e[j], (int64_t)qs[j]);
         uint32_t c = ns - ne;
         uint32_t mal_before = 0;    // malformed intervals with start <= qe: they are candidates too
         for (uint32_t k = 0; k < ix.n_mal; ++k) {           // warp-uniform trip count, usually zero
@@ -680,10 +804,10 @@ __device__ __forceinline__ void count_cells_tile(const IndexView& ix, const Quer
 #ifndef SIB_QC_MINBLOCKS
 #define SIB_QC_MINBLOCKS 16
 #endif
-template <typename CountT>
+template <typename CountT, bool PAIRED = false>
 __global__ void __launch_bounds__(QC_THREADS, SIB_QC_MINBLOCKS)
 qk_count_cells_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __restrict__ counts, const __grid_constant__ Fanout fan) {
-    count_cells_tile<CountT>(ix, rec, (uint64_t)blockIdx.x * QC_TILE, nq, counts, fan);
+    count_cells_tile<CountT, PAIRED>(ix, rec, (uint64_t)blockIdx.x * QC_TILE, nq, counts, fan);
 }
 
 // ---- count of a MIXED batch over several indexes (mode B: one index per contig) -----------------------
@@ -695,6 +819,7 @@ qk_count_cells_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __res
 // Per query: 12 B in, 4 B out, 2 x 32 B sectors. Ids outside [0, n_contigs) and contigs without an index count 0.
 struct MixedEntry {
     RankCells cs, ce;
+    PairCells pc;             // fmt != 0: both ranks from the contig's pair table
     const int32_t* rstarts;   // sorted array under cs (starts of the well-formed intervals)
     const int32_t* eall;      // sorted array under ce
     const int32_t* ends;      // for the rare qs > qe walk (quirk Q6)
@@ -748,14 +873,25 @@ qk_count_mixed_kernel(const MixedEntry* __restrict__ table, uint32_t n_contigs, 
         uint32_t c = 0;
         if (cid < n_contigs && tab[cid].n != 0u) {
             const MixedEntry& e = tab[cid];
-            const RankCells cs = e.cs, ce = e.ce;
-            uint32_t cell_s, off_s, cell_e, off_e;
-            cell_of(cs, (int64_t)qe + 1, cell_s, off_s);
-            cell_of(ce, (int64_t)qs, cell_e, off_e);
-            const CellRec rs = ld_cell(cs.rec + 2 * (size_t)cell_s);
-            const CellRec re = ld_cell(ce.rec + 2 * (size_t)cell_e);
-            const uint32_t ns = cell_rank(cs, e.rstarts, rs, cell_s, off_s, (int64_t)qe + 1);
-            const uint32_t ne = cell_rank(ce, e.eall, re, cell_e, off_e, (int64_t)qs);
+            uint32_t cell_s, off_s, cell_e, off_e, ns, ne;
+            if (e.pc.fmt != 0u) {
+                const PairCells pc = e.pc;
+                pair_cell_of(pc, qe, cell_s, off_s);
+                pair_cell_of(pc, qs, cell_e, off_e);
+                const CellRec rs = ld_cell(pc.rec + 2 * (size_t)cell_s);
+                CellRec re = rs;
+                if (cell_e != cell_s) re = ld_cell(pc.rec + 2 * (size_t)cell_e);
+                ns = pair_rank<0>(pc, e.rstarts, rs, cell_s, off_s, qe);
+                ne = pair_rank<1>(pc, e.eall, re, cell_e, off_e, qs);
+            } else {
+                const RankCells cs = e.cs, ce = e.ce;
+                cell_of(cs, (int64_t)qe + 1, cell_s, off_s);
+                cell_of(ce, (int64_t)qs, cell_e, off_e);
+                const CellRec rs = ld_cell(cs.rec + 2 * (size_t)cell_s);
+                const CellRec re = ld_cell(ce.rec + 2 * (size_t)cell_e);
+                ns = cell_rank(cs, e.rstarts, rs, cell_s, off_s, (int64_t)qe + 1);
+                ne = cell_rank(ce, e.eall, re, cell_e, off_e, (int64_t)qs);
+            }
             c = ns - ne;
             uint32_t mal_before = 0;
             for (uint32_t k = 0; k < e.n_mal; ++k) {

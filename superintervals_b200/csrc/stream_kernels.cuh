@@ -301,7 +301,7 @@ sk_count_failed_tiles_kernel(IndexView ix, const int32_t* __restrict__ qs_in, co
     constexpr uint32_t PARTS = SK_TILE / QC_TILE;
     for (uint32_t w = blockIdx.x; w < nfail * PARTS; w += gridDim.x) {
         const uint64_t base = (uint64_t)fail_list[w / PARTS] * SK_TILE + (uint64_t)(w % PARTS) * QC_TILE;
-        if (base < nq) count_cells_tile<CountT>(ix, rec, base, nq, counts, fan);
+        if (base < nq) count_cells_tile<CountT, false>(ix, rec, base, nq, counts, fan);
     }
 }
 

@@ -139,9 +139,9 @@ class DeviceIndex:
         return int(self._L.siIndexLastSort(self._ix))
 
     def cells_info(self):
-        """Rank cells of the built index: {"starts": {...}, "ends": {...}} (siIndexCellsInfo)."""
+        """Rank cells of the built index: {"starts": {...}, "ends": {...}, "pair": {...}} (siIndexCellsInfo)."""
         out = {}
-        for which, name in ((0, "starts"), (1, "ends")):
+        for which, name in ((0, "starts"), (1, "ends"), (2, "pair")):
             ci = _lib.siCellsInfo()
             if self._L.siIndexCellsInfo(self._ix, which, C.byref(ci)):
                 raise RuntimeError("siIndexCellsInfo: index not built")

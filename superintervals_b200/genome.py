@@ -95,12 +95,19 @@ class _CudaRouter:
         return out
 
 
+def _lib_opt_pair_cells():
+    from ._lib import OPT_PAIR_CELLS
+    return OPT_PAIR_CELLS
+
+
 class GenomeIndex:
     """Per-contig indexes of the contigs this rank owns."""
 
-    def __init__(self, names, n_intervals, n_queries=None, rank=None, world=None, router=None, group=None):
+    def __init__(self, names, n_intervals, n_queries=None, rank=None, world=None, router=None, group=None, pair_cells=None):
         self.names = list(names)
         nc = len(self.names)
+        self._n_intervals = [int(x) for x in n_intervals]
+        self._pair_cells = pair_cells      # SI_OPT_PAIR_CELLS of every contig's index; None: decided from the genome's size
         if len(n_intervals) != nc:
             raise ValueError("one interval count per contig")
         if rank is None:
@@ -134,8 +141,19 @@ class GenomeIndex:
         from .device import DeviceIndex
         if not self.owns(c):
             raise ValueError(f"rank {self.rank} does not own contig {self.names[c]} (owner {int(self.owner[c])})")
-        self._ix[c] = DeviceIndex().build(starts, ends, values)
+        ix = DeviceIndex()
+        ix.set_option(_lib_opt_pair_cells(), self._pair_mode())
+        self._ix[c] = ix.build(starts, ends, values)
         return self._ix[c]
+
+    def _pair_mode(self):
+        """One index per contig: a mixed batch gathers from the rank cells of ALL owned contigs at once, so whether
+        they fit L2 is a property of the genome, not of one contig (~6 B of rank cells per interval against 3/4 of
+        the 126 MB L2). Beyond that every contig also gets pair cells: one sector per short query from HBM."""
+        if self._pair_cells is not None:
+            return int(self._pair_cells)
+        owned = sum(n for c, n in enumerate(self._n_intervals) if self.owns(c))
+        return 2 if owned * 6 > 96_000_000 else 1
 
     def index(self, c):
         return self._ix[c]

@@ -85,16 +85,26 @@ int main() {
     const double sizes_gb[] = {0.25, 1, 4, 8};
     bool first = true;
     const uint64_t target = 200000000ull;
-    for (double gb : sizes_gb) {
-        const size_t nrec = (size_t)(gb * 1073741824.0 / 32);
-        const double s1 = run<2, 1>(tab, nrec, sms, sink, target);
-        const double s1b = run<4, 1>(tab, nrec, sms, sink, target);
-        const double s2 = run<2, 2>(tab, nrec, sms, sink, target);
-        const double s2b = run<4, 2>(tab, nrec, sms, sink, target);
-        const double s4 = run<2, 4>(tab, nrec, sms, sink, target);
-        printf("%s\n {\"table_gb\": %.2f, \"single_per_s_k2\": %.4g, \"single_per_s_k4\": %.4g, \"pair_per_s_k2\": %.4g, \"pair_per_s_k4\": %.4g, \"line_per_s_k2\": %.4g}",
-               first ? "" : ",", gb, s1, s1b, s2, s2b, s4);
-        first = false;
+    // the L2 fetch granularity is a device-wide hint (cudaLimitMaxL2FetchGranularity, default 64): 0 = leave it alone
+    const size_t grans[] = {0, 32, 128};
+    for (size_t gran : grans) {
+        size_t got = 0;
+        if (gran) CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran));
+        CK(cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity));
+        for (double gb : sizes_gb) {
+            const size_t nrec = (size_t)(gb * 1073741824.0 / 32);
+            const double s0 = run<1, 1>(tab, nrec, sms, sink, target);
+            const double s1 = run<2, 1>(tab, nrec, sms, sink, target);
+            const double s1b = run<4, 1>(tab, nrec, sms, sink, target);
+            const double s1c = run<8, 1>(tab, nrec, sms, sink, target);
+            const double s2 = run<2, 2>(tab, nrec, sms, sink, target);
+            const double s2b = run<4, 2>(tab, nrec, sms, sink, target);
+            const double s4 = run<2, 4>(tab, nrec, sms, sink, target);
+            printf("%s\n {\"l2_fetch_granularity\": %zu, \"table_gb\": %.2f, \"single_per_s_k1\": %.4g, \"single_per_s_k2\": %.4g, \"single_per_s_k4\": %.4g, \"single_per_s_k8\": %.4g, "
+                   "\"pair_per_s_k2\": %.4g, \"pair_per_s_k4\": %.4g, \"line_per_s_k2\": %.4g}",
+                   first ? "" : ",", got, gb, s0, s1, s1b, s1c, s2, s2b, s4);
+            first = false;
+        }
     }
     printf("]}\n");
     return 0;
