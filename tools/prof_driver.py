@@ -24,6 +24,21 @@ if len(sys.argv) > 1 and sys.argv[1] == "mixed":
     torch.cuda.synchronize()
     print("hits", int(out.long().sum().item()))
     sys.exit(0)
+if len(sys.argv) > 1 and sys.argv[1] == "c5lite":
+    # C5's density at 1/32 of its size: 32 M intervals on a 64 Mb axis, 64 M stabbing queries (the pair cells answer them)
+    reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    n5 = 32_000_000
+    g = torch.Generator(device="cuda").manual_seed(5)
+    st = (torch.rand(n5, generator=g, device="cuda", dtype=torch.float64) * 2 * n5).to(torch.int64)
+    ln = (150 + torch.rand(n5, generator=g, device="cuda", dtype=torch.float64) * (10_000 - 150)).to(torch.int64)
+    ix = DeviceIndex().build(st.to(torch.int32), torch.clamp(st + ln, max=2**31 - 1).to(torch.int32))
+    q = (torch.rand(2 * n5, generator=g, device="cuda", dtype=torch.float64) * 2 * n5).to(torch.int64).to(torch.int32)
+    out = torch.empty_like(q)
+    for _ in range(reps):
+        ix.count(q, q, out=out, order=ORDER_UNSORTED)
+    torch.cuda.synchronize()
+    print("hits", int(out.long().sum().item()), ix.cells_info()["pair"])
+    sys.exit(0)
 which = sys.argv[1] if len(sys.argv) > 1 else "c2s"
 mode = sys.argv[2] if len(sys.argv) > 2 else "count"
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
