@@ -1463,10 +1463,16 @@ int siCountMixedDevice(siIndex* const* ixs, int n_contigs, const int32_t* d_cont
     SIB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, QM_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     const uint64_t tiles = ((uint64_t)n + QM_THREADS - 1) / QM_THREADS;
-    const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)host->sm_count * per_sm);
+    // tables beyond L2 (a whole genome): short-lived CTAs of `rounds` tiles each; tables that fit: persistent CTAs
+    size_t table_bytes = 0;
+    for (int k = 0; k < n_contigs; ++k)
+        if (ixs[k] && ixs[k]->built && ixs[k]->n) table_bytes += ixs[k]->pair_ok ? ((size_t)ixs[k]->cm_pair.cells + 1) * 32 : ixs[k]->cells_total_bytes;
+    uint32_t rounds = table_bytes > (host->l2_bytes / 4) * 3 ? 8u : 0u;
+    if (const char* e = getenv("SIB_QM_ROUNDS")) rounds = (uint32_t)atoi(e);
+    const int grid = rounds ? (int)((tiles + rounds - 1) / rounds) : (int)std::min<uint64_t>(tiles, (uint64_t)host->sm_count * per_sm);
     const MixedEntry* d_tab = reinterpret_cast<const MixedEntry*>(host->mixed_tab.p);
     SIB_LAUNCH_T(host, TAG_COUNT_CELLS, kern, grid, QM_THREADS, smem, s, d_tab, (uint32_t)n_contigs, d_contig, d_qs, d_qe,
-                 (uint32_t)n, d_counts, d_totals);
+                 (uint32_t)n, d_counts, d_totals, rounds);
     return 0;
 }
 
