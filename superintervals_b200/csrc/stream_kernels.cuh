@@ -117,8 +117,10 @@ constexpr uint32_t SK_TILE = SK_THREADS * SK_PER_THREAD;   // 2048 queries: 16 K
 #ifndef SIB_SK_EW
 #define SIB_SK_EW 768
 #endif
+// 3 CTAs/SM (80 registers, 24 bytes of spills, 3 x 55 KB of staging): 0.347 -> 0.312 ms on C2 sorted against 2 CTAs/SM at 114
+// registers; 4 CTAs/SM with 36 KB stages 0.308 ms, 3 with 36 KB stages 0.305 ms (tools/gpu_r02zi.sh) -- the wider windows are kept
 #ifndef SIB_SK_MINBLOCKS
-#define SIB_SK_MINBLOCKS 2
+#define SIB_SK_MINBLOCKS 3
 #endif
 constexpr uint32_t SK_SW = SIB_SK_SW;   // staged words of the starts table (x 32 coordinates)
 constexpr uint32_t SK_EW = SIB_SK_EW;   // staged words of the ends table
