@@ -296,7 +296,7 @@ def l2_gather_peak(table_bytes):
     best = {}
     for r in rows:
         mb = r["table_mb"]
-        best[mb] = max(best.get(mb, 0.0), r["sectors_per_s_k8"], r["sectors_per_s_k4"])
+        best[mb] = max(best.get(mb, 0.0), r["sectors_per_s_k8"], r["sectors_per_s_k4"], r.get("sectors_per_s_flat", 0.0))
     for mb in sorted(best):
         if mb * 1e6 >= table_bytes * 0.999:
             return best[mb], f"tools/l2_peak.cu on B200 (profiles/l2_peak_r02.json): random 32-byte sector reads from a {mb:g} MB table"

@@ -506,34 +506,56 @@ int count_dev<uint32_t>(siIndex* ix, const int32_t* dqs, const int32_t* dqe, siz
 
 template <typename CountT>
 static int count_batch_pipelined(siIndex* ix, const int32_t* qs, const int32_t* qe, size_t n, CountT* counts_out) {
-    constexpr size_t CHUNK = (size_t)8 << 20;   // queries per chunk: 64 MB in, 64 MB out
+    // 2 M queries per chunk (16 MB in, 8-16 MB out), SI_PIPE_SLOTS device slots: the copies of both directions run back to back
+    // and what is NOT overlapped -- the first chunk's upload and the last chunk's download -- is 0.3 ms each (8 M-query chunks
+    // on two slots left 1.3 ms each: 18.0 ms per 100 M queries against a bare-copy ceiling of 16.2 ms).
+    static const size_t CHUNK = [] {
+        size_t c = (size_t)2 << 20;
+        if (const char* e = getenv("SIB_PIPE_CHUNK")) { const long long v = atoll(e); if (v >= 65536) c = (size_t)v; }
+        return c;
+    }();
+    static const int SLOTS = [] {
+        int k = SI_PIPE_SLOTS;
+        if (const char* e = getenv("SIB_PIPE_SLOTS")) { const int v = atoi(e); if (v >= 2 && v <= SI_PIPE_SLOTS) k = v; }
+        return k;
+    }();
     if (!ix->pipe_ready) {
         SIB_CHECK(cudaStreamCreateWithFlags(&ix->s_in, cudaStreamNonBlocking));
         SIB_CHECK(cudaStreamCreateWithFlags(&ix->s_out, cudaStreamNonBlocking));
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < SI_PIPE_SLOTS; ++k) {
             SIB_CHECK(cudaEventCreateWithFlags(&ix->e_in[k], cudaEventDisableTiming));
             SIB_CHECK(cudaEventCreateWithFlags(&ix->e_k[k], cudaEventDisableTiming));
             SIB_CHECK(cudaEventCreateWithFlags(&ix->e_out[k], cudaEventDisableTiming));
         }
         ix->pipe_ready = true;
     }
-    if (ix->h_qs.ensure(2 * CHUNK * 4) || ix->h_qe.ensure(2 * CHUNK * 4) || ix->h_counts.ensure(2 * CHUNK * sizeof(CountT)))
+    if (ix->h_qs.ensure(SLOTS * CHUNK * 4) || ix->h_qe.ensure(SLOTS * CHUNK * 4) || ix->h_counts.ensure(SLOTS * CHUNK * sizeof(CountT)))
         return last_error_code();
     cudaStream_t s_in = ix->s_in, s_k = ix->own_stream, s_out = ix->s_out;
+    const size_t nchunks = (n + CHUNK - 1) / CHUNK;
+    auto len = [&](size_t j) { return n - j * CHUNK < CHUNK ? n - j * CHUNK : CHUNK; };
+    // upload of chunk j into its slot, once the count that last read the slot (chunk j - SLOTS) is done
+    auto upload = [&](size_t j) -> int {
+        const int slot = (int)(j % SLOTS);
+        if (j >= (size_t)SLOTS) SIB_CHECK(cudaStreamWaitEvent(s_in, ix->e_k[slot], 0));
+        SIB_CHECK(cudaMemcpyAsync(ix->h_qs.as<int32_t>() + slot * CHUNK, qs + j * CHUNK, len(j) * 4, cudaMemcpyHostToDevice, s_in));
+        SIB_CHECK(cudaMemcpyAsync(ix->h_qe.as<int32_t>() + slot * CHUNK, qe + j * CHUNK, len(j) * 4, cudaMemcpyHostToDevice, s_in));
+        SIB_CHECK(cudaEventRecord(ix->e_in[slot], s_in));
+        return 0;
+    };
     int order = SI_ORDER_AUTO;
-    size_t k = 0;
-    for (size_t at = 0; at < n; at += CHUNK, ++k) {
-        const size_t m = n - at < CHUNK ? n - at : CHUNK;
-        const int slot = (int)(k & 1);
+    size_t uploaded = 0;
+    for (size_t k = 0; k < nchunks; ++k) {
+        // uploads run ahead of the counts by up to SLOTS chunks (chunk j - SLOTS < k has had its count enqueued)
+        while (uploaded < nchunks && uploaded < k + SLOTS)
+            if (upload(uploaded++)) return last_error_code();
+        const int slot = (int)(k % SLOTS);
+        const size_t m = len(k);
         int32_t* dqs = ix->h_qs.as<int32_t>() + slot * CHUNK;
         int32_t* dqe = ix->h_qe.as<int32_t>() + slot * CHUNK;
         CountT* dc = ix->h_counts.as<CountT>() + slot * CHUNK;
-        if (k >= 2) SIB_CHECK(cudaStreamWaitEvent(s_in, ix->e_k[slot], 0));    // slot's inputs consumed (chunk k-2)
-        SIB_CHECK(cudaMemcpyAsync(dqs, qs + at, m * 4, cudaMemcpyHostToDevice, s_in));
-        SIB_CHECK(cudaMemcpyAsync(dqe, qe + at, m * 4, cudaMemcpyHostToDevice, s_in));
-        SIB_CHECK(cudaEventRecord(ix->e_in[slot], s_in));
         SIB_CHECK(cudaStreamWaitEvent(s_k, ix->e_in[slot], 0));
-        if (k >= 2) SIB_CHECK(cudaStreamWaitEvent(s_k, ix->e_out[slot], 0));   // slot's counts drained (chunk k-2)
+        if (k >= (size_t)SLOTS) SIB_CHECK(cudaStreamWaitEvent(s_k, ix->e_out[slot], 0));   // slot's counts drained (chunk k - SLOTS)
         if (k == 0) {
             // one device check on the first chunk decides sort-or-not for the whole batch; any
             // order is answered correctly, the choice only affects locality
@@ -544,7 +566,7 @@ static int count_batch_pipelined(siIndex* ix, const int32_t* qs, const int32_t* 
         if (rc) return rc;
         SIB_CHECK(cudaEventRecord(ix->e_k[slot], s_k));
         SIB_CHECK(cudaStreamWaitEvent(s_out, ix->e_k[slot], 0));
-        SIB_CHECK(cudaMemcpyAsync(counts_out + at, dc, m * sizeof(CountT), cudaMemcpyDeviceToHost, s_out));
+        SIB_CHECK(cudaMemcpyAsync(counts_out + k * CHUNK, dc, m * sizeof(CountT), cudaMemcpyDeviceToHost, s_out));
         SIB_CHECK(cudaEventRecord(ix->e_out[slot], s_out));
     }
     SIB_CHECK(cudaStreamSynchronize(s_out));
@@ -560,7 +582,9 @@ static void count_batch_host(cSuperIntervals* si, const int32_t* starts, const i
     if (!handle_ready(h, who)) { memset(counts_out, 0, n * sizeof(CountT)); return; }
     siIndex* ix = h->ix;
     std::lock_guard<std::mutex> lk(ix->api_mu);
-    if (n > ((size_t)12 << 20)) {
+    // chunked pipeline: always for large batches; from 4 M queries when the caller's buffers are pinned (pageable ones are
+    // staged faster by stage_queries' own threads than by the runtime)
+    if (n > ((size_t)12 << 20) || (n > ((size_t)4 << 20) && is_pinned(starts) && is_pinned(ends) && is_pinned(counts_out))) {
         count_batch_pipelined<CountT>(ix, starts, ends, n, counts_out);
         return;
     }

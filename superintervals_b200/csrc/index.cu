@@ -718,7 +718,11 @@ template <typename CountT>
 int launch_count(siIndex* ix, const QueryRecords& rec, uint32_t nq, CountT* d_counts, cudaStream_t s, const Fanout& fan) {
     const int algo = count_algo_of(ix);
     if (algo == SI_COUNT_CELLS) {
-        const int grid = (int)(((uint64_t)nq + QC_TILE - 1) / QC_TILE);
+        const int tiles = (int)(((uint64_t)nq + QC_TILE - 1) / QC_TILE);
+        // tables that fit L2: persistent CTAs (16 per SM); tables in HBM: one tile per CTA
+        bool persistent = !ix->pair_ok && ix->cells_total_bytes <= (ix->l2_bytes / 4) * 3;
+        if (const char* e = getenv("SIB_QC_PERSIST")) persistent = atoi(e) != 0;
+        const int grid = persistent ? std::min(tiles, ix->sm_count * SIB_QC_MINBLOCKS) : tiles;
         if (ix->l2_persist && ix->cells_total_bytes <= ix->l2_persist_max) {
             // the rank cells are the only data read more than once: ask L2 to keep them (persisting) while the
             // query and count streams pass through (streaming) -- a per-launch access-policy window
@@ -994,7 +998,7 @@ void siIndexDestroy(siIndex* ix) {
     if (ix->pipe_ready) {
         cudaStreamDestroy(ix->s_in);
         cudaStreamDestroy(ix->s_out);
-        for (int k = 0; k < 2; ++k) { cudaEventDestroy(ix->e_in[k]); cudaEventDestroy(ix->e_k[k]); cudaEventDestroy(ix->e_out[k]); }
+        for (int k = 0; k < SI_PIPE_SLOTS; ++k) { cudaEventDestroy(ix->e_in[k]); cudaEventDestroy(ix->e_k[k]); cudaEventDestroy(ix->e_out[k]); }
     }
     ix->timer.release();
     if (ix->e_stage[0]) { cudaEventDestroy(ix->e_stage[0]); cudaEventDestroy(ix->e_stage[1]); }

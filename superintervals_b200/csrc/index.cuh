@@ -5,6 +5,7 @@
 
 #include <mutex>
 
+constexpr int SI_PIPE_SLOTS = 4;   // device slots of the chunked host-batch pipeline (c_abi.cu)
 struct siIndex;   // C-visible opaque name
 
 namespace sib {
@@ -159,7 +160,7 @@ struct siIndex {
     sib::DevBuf h_qs, h_qe, h_counts, h_offsets, h_out, h_cov;
     bool pipe_ready = false;                    // chunked host-batch pipeline (c_abi.cu)
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t e_in[2] = {nullptr, nullptr}, e_k[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};
+    cudaEvent_t e_in[SI_PIPE_SLOTS] = {}, e_k[SI_PIPE_SLOTS] = {}, e_out[SI_PIPE_SLOTS] = {};
     void* pinned = nullptr;                     // two pinned staging slots for pageable caller buffers (c_abi.cu)
     size_t pinned_bytes = 0;
     cudaEvent_t e_stage[2] = {nullptr, nullptr};

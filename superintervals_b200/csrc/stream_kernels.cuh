@@ -107,7 +107,10 @@ __device__ __forceinline__ void sk_st8(uint64_t* p, const uint32_t* c) {
 //       the 256-bit loads of tile k+2's queries are in flight into registers.
 // One __syncthreads per tile (the window reduction; it also frees the stage the next copies overwrite);
 // the window itself is published through the stage's mbarrier (thread 0 writes it before it arrives).
-constexpr int SK_THREADS = 256;
+#ifndef SIB_SK_THREADS
+#define SIB_SK_THREADS 256
+#endif
+constexpr int SK_THREADS = SIB_SK_THREADS;
 constexpr int SK_WARPS = SK_THREADS / 32;
 constexpr int SK_PER_THREAD = 8;
 constexpr uint32_t SK_TILE = SK_THREADS * SK_PER_THREAD;   // 2048 queries: 16 KB in, 8 KB out

@@ -64,6 +64,30 @@ __global__ void __launch_bounds__(256) stream_kernel(const uint4* __restrict__ a
     }
 }
 
+// the count kernels' own shape: one sector per thread, one CTA of 128 threads per 128 requests, no loop
+__global__ void __launch_bounds__(128) flat_kernel(const Rec* __restrict__ tab, uint32_t nrec, uint32_t salt, uint32_t* __restrict__ sink) {
+    const uint32_t gid = blockIdx.x * 128 + threadIdx.x;
+    const Rec v = ld_sector(tab + (uint32_t)(((uint64_t)mix(gid * 977u + salt) * nrec) >> 32));
+    if ((v.w[0] ^ v.w[7]) == 0x12345u) sink[0] = v.w[0];
+}
+static double run_flat(const Rec* tab, uint32_t nrec, uint32_t* sink, uint64_t requests) {
+    const uint32_t grid = (uint32_t)(requests / 128);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    flat_kernel<<<grid / 4, 128>>>(tab, nrec, 1u, sink);
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int it = 0; it < 3; ++it) {
+        CK(cudaEventRecord(e0));
+        flat_kernel<<<grid, 128>>>(tab, nrec, 7u + it, sink);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    return (double)grid * 128 / (best * 1e-3);
+}
+
 template <int K, int BYTES>
 static double run_gather(const Rec* tab, uint32_t nrec, int ctas_per_sm, int sms, uint32_t* sink, uint64_t target_loads) {
     const int grid = sms * ctas_per_sm;
@@ -104,8 +128,9 @@ int main() {
             const double r4 = run_gather<4, 32>(tab, nrec, occ, sms, sink, target);
             const double r8 = run_gather<8, 32>(tab, nrec, occ, sms, sink, target);
             const double w8 = run_gather<8, 4>(tab, nrec, occ, sms, sink, target);
-            printf("%s\n {\"table_mb\": %.1f, \"ctas_per_sm\": %d, \"sectors_per_s_k4\": %.4g, \"sectors_per_s_k8\": %.4g, \"gbs_k8\": %.1f, \"words_per_s_k8\": %.4g}",
-                   first ? "" : ",", mb, occ, r4, r8, r8 * 32 / 1e9, w8);
+            const double fl = occ == 2 ? run_flat(tab, nrec, sink, target) : 0.0;
+            printf("%s\n {\"table_mb\": %.1f, \"ctas_per_sm\": %d, \"sectors_per_s_flat\": %.4g, \"sectors_per_s_k4\": %.4g, \"sectors_per_s_k8\": %.4g, \"gbs_k8\": %.1f, \"words_per_s_k8\": %.4g}",
+                   first ? "" : ",", mb, occ, fl, r4, r8, r8 * 32 / 1e9, w8);
             first = false;
         }
     }
