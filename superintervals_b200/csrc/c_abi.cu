@@ -506,16 +506,16 @@ int count_dev<uint32_t>(siIndex* ix, const int32_t* dqs, const int32_t* dqe, siz
 
 template <typename CountT>
 static int count_batch_pipelined(siIndex* ix, const int32_t* qs, const int32_t* qe, size_t n, CountT* counts_out) {
-    // 2 M queries per chunk (16 MB in, 8-16 MB out), SI_PIPE_SLOTS device slots: the copies of both directions run back to back
-    // and what is NOT overlapped -- the first chunk's upload and the last chunk's download -- is 0.3 ms each (8 M-query chunks
-    // on two slots left 1.3 ms each: 18.0 ms per 100 M queries against a bare-copy ceiling of 16.2 ms).
+    // 8 M queries per chunk (64 MB in, 32-64 MB out) on two device slots. Measured on C2 (100 M queries, bare-copy ceiling 16.2-16.6 ms,
+    // tools/gpu_r02zl.sh): 8 M x 2 slots 18.3 ms, 8 M x 4 slots 18.5 ms, 4 M x 4 18.3 ms, 2 M x 4 19.3 ms, 16 M x 3 19.4 ms -- smaller
+    // chunks and uploads running further ahead buy nothing (SIB_PIPE_CHUNK / SIB_PIPE_SLOTS override).
     static const size_t CHUNK = [] {
-        size_t c = (size_t)2 << 20;
+        size_t c = (size_t)8 << 20;
         if (const char* e = getenv("SIB_PIPE_CHUNK")) { const long long v = atoll(e); if (v >= 65536) c = (size_t)v; }
         return c;
     }();
     static const int SLOTS = [] {
-        int k = SI_PIPE_SLOTS;
+        int k = 2;
         if (const char* e = getenv("SIB_PIPE_SLOTS")) { const int v = atoi(e); if (v >= 2 && v <= SI_PIPE_SLOTS) k = v; }
         return k;
     }();

@@ -719,8 +719,9 @@ int launch_count(siIndex* ix, const QueryRecords& rec, uint32_t nq, CountT* d_co
     const int algo = count_algo_of(ix);
     if (algo == SI_COUNT_CELLS) {
         const int tiles = (int)(((uint64_t)nq + QC_TILE - 1) / QC_TILE);
-        // tables that fit L2: persistent CTAs (16 per SM); tables in HBM: one tile per CTA
-        bool persistent = !ix->pair_ok && ix->cells_total_bytes <= (ix->l2_bytes / 4) * 3;
+        // one tile per CTA. Persistent CTAs (SIB_QC_PERSIST=1: 16 per SM, tiles taken grid-stride) measured slower on C2 shuffled:
+        // 1.016 against 0.953 ms (tools/gpu_r02zl.sh), although the bare L2 gather prefers them (tools/l2_peak.cu)
+        bool persistent = false;
         if (const char* e = getenv("SIB_QC_PERSIST")) persistent = atoi(e) != 0;
         const int grid = persistent ? std::min(tiles, ix->sm_count * SIB_QC_MINBLOCKS) : tiles;
         if (ix->l2_persist && ix->cells_total_bytes <= ix->l2_persist_max) {
