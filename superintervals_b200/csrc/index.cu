@@ -719,11 +719,7 @@ int launch_count(siIndex* ix, const QueryRecords& rec, uint32_t nq, CountT* d_co
     const int algo = count_algo_of(ix);
     if (algo == SI_COUNT_CELLS) {
         const int tiles = (int)(((uint64_t)nq + QC_TILE - 1) / QC_TILE);
-        // one tile per CTA. Persistent CTAs (SIB_QC_PERSIST=1: 16 per SM, tiles taken grid-stride) measured slower on C2 shuffled:
-        // 1.016 against 0.953 ms (tools/gpu_r02zl.sh), although the bare L2 gather prefers them (tools/l2_peak.cu)
-        bool persistent = false;
-        if (const char* e = getenv("SIB_QC_PERSIST")) persistent = atoi(e) != 0;
-        const int grid = persistent ? std::min(tiles, ix->sm_count * SIB_QC_MINBLOCKS) : tiles;
+        const int grid = tiles;
         if (ix->l2_persist && ix->cells_total_bytes <= ix->l2_persist_max) {
             // the rank cells are the only data read more than once: ask L2 to keep them (persisting) while the
             // query and count streams pass through (streaming) -- a per-launch access-policy window

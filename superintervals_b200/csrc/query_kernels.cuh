@@ -807,11 +807,9 @@ __device__ __forceinline__ void count_cells_tile(const IndexView& ix, const Quer
 template <typename CountT, bool PAIRED = false>
 __global__ void __launch_bounds__(QC_THREADS, SIB_QC_MINBLOCKS)
 qk_count_cells_kernel(IndexView ix, QueryRecords rec, uint32_t nq, CountT* __restrict__ counts, const __grid_constant__ Fanout fan) {
-    // grid == tiles: one tile per CTA (tables in HBM: short-lived CTAs are served random sectors faster, tools/hbm_gather.cu);
-    // grid < tiles: persistent CTAs taking tiles grid-stride (tables in L2: no CTA turnover, tools/l2_peak.cu)
-    const uint32_t tiles = (uint32_t)(((uint64_t)nq + QC_TILE - 1) / QC_TILE);
-    for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x)
-        count_cells_tile<CountT, PAIRED>(ix, rec, (uint64_t)tile * QC_TILE, nq, counts, fan);
+    // one tile per CTA. Persistent CTAs taking tiles grid-stride (16 per SM) measured slower on C2 shuffled, 1.016 against 0.953 ms
+    // (tools/gpu_r02zl.sh), and short-lived CTAs are also what HBM serves random sectors to fastest (tools/hbm_gather.cu)
+    count_cells_tile<CountT, PAIRED>(ix, rec, (uint64_t)blockIdx.x * QC_TILE, nq, counts, fan);
 }
 
 // ---- count of a MIXED batch over several indexes (mode B: one index per contig) -----------------------
