@@ -886,6 +886,41 @@ def bench_c4(a, torch, dist, world, rank):
         got = out[sel].cpu().numpy().astype(np.uint32).astype(np.int64)
         par = {"checked": int(sel.numel()), "mismatches": int((got != want).sum()), "against": f"{kind} (oracle/_ref si::IntervalMap) on chr21's queries of rank 0's slice"}
     hits = int(out.to(torch.int64).sum().item())
+    # ---- mode B without the dispatch: the slices stay in peer-mapped memory, every GPU walks all of them in place over NVLink and
+    # answers the queries of its own contigs (siCountMixedPeerDevice); two flag barriers through peer memory, no collective
+    peer = None
+    if world > 1:
+        from superintervals_b200.sharding import PeerBatch
+        pb = None
+        try:
+            cap = torch.tensor([float(m)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(cap, op=dist.ReduceOp.MAX)
+            pb = PeerBatch(int(cap.item()), world, rank)
+            pb.contig[:m].copy_(cid); pb.qs[:m].copy_(qs); pb.qe[:m].copy_(qe)
+            pb.set_length(m)
+            got = gi.count_mixed_peer(pb)
+            flag = torch.tensor([1.0 if (got is not None and torch.equal(got, out)) else 0.0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if got is not None:
+                torch.cuda.synchronize(); dist.barrier()
+                ms_p = timed_device(torch, lambda: gi.count_mixed_peer(pb), 3)
+                tp = torch.tensor([ms_p], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+                away = torch.tensor([float(sum(n for r, n in enumerate(pb.lengths) if r != rank))], dtype=torch.float64, device="cuda")
+                dist.all_reduce(away, op=dist.ReduceOp.SUM)
+                peer = {"value": float(tot[0]) / (float(tp[0]) * 1e-3), "unit": UNIT, "ms_per_step": float(tp[0]),
+                        "equals_dispatched_counts": bool(flag[0] > 0), "timed_out": pb.timed_out(),
+                        "nvlink_contig_id_bytes_per_step": int(4 * away.item()),
+                        "nvlink_note": "every GPU reads the 4-byte contig id of every remote query; the owner also reads 8 B and stores 4 B per remote query of its contigs",
+                        "how": "slices stay in CUDA-IPC peer memory; each GPU walks all slices in place over NVLink, answers its own contigs' queries and "
+                               "stores the counts into the slice they belong to (siCountMixedPeerDevice + 2 flag barriers): no all-to-all, no routing sort, no scatter"}
+            else:
+                peer = {"unsupported": "a rank holds no rank-cell index"}
+        except Exception as ex:   # noqa: BLE001
+            peer = {"error": repr(ex)}
+        finally:
+            if pb is not None:
+                pb.close()
     # ---- the alternative at N > 1: every GPU holds ALL 24 indexes (3.8 GB for 100 M intervals) and counts its own slice in one
     # launch -- no routing, no exchange. Moving a query to its owner costs 16 B over NVLink, as much time as counting it from
     # HBM-resident rank cells, so partitioning the index pays only when it does not fit on one GPU.
@@ -913,10 +948,16 @@ def bench_c4(a, torch, dist, world, rank):
     step = ("device routing by owner (radix sort of the slot ids + gather), all-to-all dispatch, ONE mixed-batch count launch on each owner, "
             "all-to-all combine, scatter back to the caller's order") if world > 1 else \
            "ONE launch of the mixed-batch count kernel over the batch in the caller's order (per-contig rank-cell descriptors in shared memory): nothing routed"
+    dispatched = {"value": float(tot[0]) / (float(t[0]) * 1e-3), "unit": UNIT, "ms_per_step": float(t[0]), "step": step}
+    use_peer = bool(peer and peer.get("equals_dispatched_counts") and not peer.get("timed_out"))
     return {"workload": f"C4: 24 contigs (GRCh38 lengths), {int(tot[1])} intervals x {int(tot[0])} queries as one mixed batch, one index per contig, "
                         f"contigs owned by {world} GPU(s) (LPT)", "scaling": "strong",
-            "value": float(tot[0]) / (float(t[0]) * 1e-3), "unit": UNIT, "ms_per_step": float(t[0]), "build_ms_max_over_ranks": float(t[1]),
-            "step": step, "index": "partitioned by contig (each GPU holds the contigs it owns)" if world > 1 else "all 24 contig indexes on the one GPU",
+            "value": peer["value"] if use_peer else dispatched["value"], "unit": UNIT,
+            "ms_per_step": peer["ms_per_step"] if use_peer else dispatched["ms_per_step"], "build_ms_max_over_ranks": float(t[1]),
+            "value_is": ("queries read in place over NVLink peer memory, counts stored in place (see peer); equal to the dispatched counts" if use_peer
+                         else "routed + all-to-all dispatch / combine" if world > 1 else "one launch"),
+            "step": peer["how"] if use_peer else step, "peer": peer, "dispatched": dispatched if world > 1 else None,
+            "index": "partitioned by contig (each GPU holds the contigs it owns)" if world > 1 else "all 24 contig indexes on the one GPU",
             "nccl_dispatch_bytes_per_step": int(tot[2]), "nccl_combine_bytes_per_step": int(tot[3]), "hits_rank0": hits, "parity": par,
             "owner": [int(x) for x in gi.owner], "replicated": repl,
             "pair_cells": (lambda own: gi.index(own[0]).cells_info()["pair"] if own else None)(gi.owned),

@@ -273,6 +273,21 @@ int siScatterCountsDevice(siIndex* ix, const uint32_t* d_counts, const uint32_t*
 #define SI_MIXED_UNSUPPORTED (-2)
 int siCountMixedDevice(siIndex* const* ixs, int n_contigs, const int32_t* d_contig, const int32_t* d_qs, const int32_t* d_qe,
                        size_t n, uint32_t* d_counts, unsigned long long* d_totals, void* stream);
+/* Mode B across GPUs WITHOUT a dispatch (the reference keeps one map per contig, examples/bed-intersect-si.rs:100-123).
+ * The contigs are partitioned over the GPUs and every GPU's slice of the mixed batch stays where it is, in buffers its peers have
+ * mapped (cudaDeviceEnablePeerAccess inside one process, or siIpcAlloc / siIpcOpen between processes). Each GPU calls this with
+ * the same n_src slices (slice k lives on GPU k; home = this GPU's own position) and ITS table: ixs[c] = its index of contig c or
+ * NULL, foreign[c] != 0 where another GPU holds contig c's index. The GPU walks all slices -- the remote ones are read in place
+ * over NVLink -- answers exactly the queries of the contigs it indexes, and stores every count into the slice's own counts array
+ * (a peer store for a remote slice). Queries of a contig nobody indexes, or with an id outside [0, n_contigs), get their 0 from
+ * the slice's home GPU. No all-to-all, no routing sort, no scatter back: per query that crosses GPUs 4 B of contig id are read by
+ * every GPU, 8 B of coordinates are read and 4 B of count written by the owner. d_totals (n_contigs entries, may be NULL) receives
+ * the hit totals of this GPU's contigs over the whole batch. The caller puts a barrier between the GPUs on both sides
+ * (siPeerBarrierDevice): slices complete before peers read them, all stores landed before counts are used. Returns
+ * SI_MIXED_UNSUPPORTED as siCountMixedDevice does, and for a GPU that holds no index at all while other GPUs do. */
+int siCountMixedPeerDevice(siIndex* const* ixs, int n_contigs, const unsigned char* foreign, int n_src, int home,
+                           const int32_t* const* d_contig, const int32_t* const* d_qs, const int32_t* const* d_qe, const size_t* n,
+                           uint32_t* const* d_counts, unsigned long long* d_totals, void* stream);
 
 /* ---- 3c. count fused with the all-gather of the counts ---------------------------------------------
  * siCountDevice that additionally stores every count at the same index of up to 15 further arrays. With the arrays

@@ -113,7 +113,7 @@ B200_SYMBOLS = [
     "searchItemsBatch", "coverageBatch", "intersectionPairs", "siParseBed", "siBedTableFree", "siIndexCreate", "siIndexDestroy", "siIndexOf", "siIndexSize",
     "siIndexDeviceView", "siIndexBuildHost", "siIndexBuildDevice", "siIndexExport", "siCountDevice",
     "siCountDevice64", "siSortQueriesDevice", "siIndexSetOption", "siIndexCellsInfo", "siIndexBitsInfo", "siIndexStreamStats", "siIndexStabInfo", "siIndexReadTimings", "siAnyDevice", "siScanDevice", "siFillDevice", "siCoverageDevice",
-    "siIndexDeviceBytes", "siRouteByContigDevice", "siScatterCountsDevice", "siCountMixedDevice", "siIndexLastSort", "siCountFanoutDevice", "siPeerBarrierDevice", "siIpcAlloc", "siIpcOpen", "siIpcClose", "siIpcFree",
+    "siIndexDeviceBytes", "siRouteByContigDevice", "siScatterCountsDevice", "siCountMixedDevice", "siCountMixedPeerDevice", "siIndexLastSort", "siCountFanoutDevice", "siPeerBarrierDevice", "siIpcAlloc", "siIpcOpen", "siIpcClose", "siIpcFree",
     "siMultiCreate", "siMultiDestroy", "siMultiDeviceCount", "siMultiIndexOf", "siMultiBuildReplicated", "siMultiCountBatch",
     "siMultiSearchValuesBatch", "siMultiDeviceCounts", "siMultiLastStats",
 ]
@@ -251,6 +251,7 @@ def bind_b200(L):
     L.siIpcClose.argtypes = [vp]
     L.siIpcFree.argtypes = [vp]
     L.siCountMixedDevice.argtypes = [vp, C.c_int, vp, vp, vp, sz, vp, vp, vp]
+    L.siCountMixedPeerDevice.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     return L
 
 

@@ -393,6 +393,8 @@ int build_device_impl(siIndex* ix, const int32_t* d_s, const int32_t* d_e, const
     ix->built = false;
     ix->plan_valid = false;
     ix->cm_s.fmt = ix->cm_e.fmt = 0;
+    ix->pair_ok = false;
+    ix->pair_counters_pending = false;
     ix->bits_ok = false;
     ix->build_counters_pending = false;
     ix->rank_ok = false;
@@ -1417,46 +1419,11 @@ int siScatterCountsDevice(siIndex* ix, const uint32_t* d_counts, const uint32_t*
 // Mode B in one launch (superintervals_b200.h section 3b): the mixed batch answered in the caller's order by
 // qk_count_mixed_kernel. Returns SI_MIXED_UNSUPPORTED (no error latched) when one of the indexes cannot answer from
 // rank cells (malformed beyond the side list, >= 2^31 intervals): the caller then routes by contig instead.
-int siCountMixedDevice(siIndex* const* ixs, int n_contigs, const int32_t* d_contig, const int32_t* d_qs, const int32_t* d_qe,
-                       size_t n, uint32_t* d_counts, unsigned long long* d_totals, void* stream) {
-    if (!ixs || n_contigs < 1 || n_contigs > (1 << 20) || n > 0xFFFFFFFFull) {
-        set_error_msg(cudaErrorInvalidValue, "siCountMixedDevice: bad arguments");
-        return cudaErrorInvalidValue;
-    }
-    siIndex* host = nullptr;   // lends its stream, its device and the table's allocation
-    for (int k = 0; k < n_contigs; ++k) {
-        siIndex* ix = ixs[k];
-        if (!ix || !ix->built || ix->n == 0) continue;
-        if (count_algo_of(ix) != SI_COUNT_CELLS) return SI_MIXED_UNSUPPORTED;
-        if (!host) host = ix;
-        if (ix->device != host->device) {
-            set_error_msg(cudaErrorInvalidValue, "siCountMixedDevice: the indexes live on different devices");
-            return cudaErrorInvalidValue;
-        }
-    }
-    if (d_totals) SIB_CHECK(cudaMemsetAsync(d_totals, 0, (size_t)n_contigs * 8, static_cast<cudaStream_t>(stream)));
-    if (n == 0) return 0;
-    if (!host) {   // no contig has an index: every count is 0
-        SIB_CHECK(cudaMemsetAsync(d_counts, 0, n * 4, static_cast<cudaStream_t>(stream)));
-        return 0;
-    }
-    DeviceGuard g(host->device);
-    cudaStream_t s = pick_stream(host, stream);
-    std::vector<MixedEntry> tab((size_t)n_contigs);
-    memset(tab.data(), 0, tab.size() * sizeof(MixedEntry));
-    for (int k = 0; k < n_contigs; ++k) {
-        siIndex* ix = ixs[k];
-        if (!ix || !ix->built || ix->n == 0) continue;
-        const IndexView v = view_of(ix);
-        MixedEntry& e = tab[(size_t)k];
-        e.cs = v.cells_s; e.ce = v.cells_e; e.pc = v.pair; e.rstarts = v.rstarts; e.eall = v.eall; e.ends = v.ends; e.branch = v.branch;
-        e.n = v.n; e.n_mal = v.n_mal;
-        for (int a = 0; a < 8; ++a) { e.mal_s[a] = v.mal_s[a]; e.mal_e[a] = v.mal_e[a]; }
-    }
-    const size_t bytes = tab.size() * sizeof(MixedEntry);
-    if (host->mixed_tab.ensure(bytes)) return last_error_code();
-    // pageable source: the runtime stages it before returning, so the vector may go out of scope
-    SIB_CHECK(cudaMemcpyAsync(host->mixed_tab.p, tab.data(), bytes, cudaMemcpyHostToDevice, s));
+// one launch of the mixed-batch kernel over one slice; the descriptor table is already on the device
+static int mixed_launch(siIndex* host, siIndex* const* ixs, int n_contigs, size_t table_bytes_on_device, const int32_t* d_contig,
+                        const int32_t* d_qs, const int32_t* d_qe, size_t n, uint32_t* d_counts, unsigned long long* d_totals,
+                        uint32_t peer_mode, cudaStream_t s) {
+    const size_t bytes = table_bytes_on_device;
     const size_t smem = n_contigs <= QM_SMEM_ENTRIES ? ((bytes + 15) & ~(size_t)15) + (size_t)n_contigs * 8 : 0;
     auto kern = qk_count_mixed_kernel<uint32_t>;
     if (smem > ((size_t)48 << 10)) SIB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1473,7 +1440,120 @@ int siCountMixedDevice(siIndex* const* ixs, int n_contigs, const int32_t* d_cont
     const int grid = rounds ? (int)((tiles + rounds - 1) / rounds) : (int)std::min<uint64_t>(tiles, (uint64_t)host->sm_count * per_sm);
     const MixedEntry* d_tab = reinterpret_cast<const MixedEntry*>(host->mixed_tab.p);
     SIB_LAUNCH_T(host, TAG_COUNT_CELLS, kern, grid, QM_THREADS, smem, s, d_tab, (uint32_t)n_contigs, d_contig, d_qs, d_qe,
-                 (uint32_t)n, d_counts, d_totals, rounds);
+                 (uint32_t)n, d_counts, d_totals, rounds, peer_mode);
+    return 0;
+}
+
+// the per-contig descriptor table of a mixed launch, uploaded into host->mixed_tab; foreign[k] != 0 marks a contig without an
+// index here that another GPU answers (siCountMixedPeerDevice)
+static int mixed_table(siIndex* host, siIndex* const* ixs, int n_contigs, const unsigned char* foreign, cudaStream_t s, size_t* bytes_out) {
+    std::vector<MixedEntry> tab((size_t)n_contigs);
+    memset(tab.data(), 0, tab.size() * sizeof(MixedEntry));
+    for (int k = 0; k < n_contigs; ++k) {
+        siIndex* ix = ixs[k];
+        MixedEntry& e = tab[(size_t)k];
+        if (!ix || !ix->built || ix->n == 0) {
+            if (foreign && foreign[k]) e.n_mal = QM_FOREIGN;
+            continue;
+        }
+        const IndexView v = view_of(ix);
+        e.cs = v.cells_s; e.ce = v.cells_e; e.pc = v.pair; e.rstarts = v.rstarts; e.eall = v.eall; e.ends = v.ends; e.branch = v.branch;
+        e.n = v.n; e.n_mal = v.n_mal;
+        for (int a = 0; a < 8; ++a) { e.mal_s[a] = v.mal_s[a]; e.mal_e[a] = v.mal_e[a]; }
+    }
+    const size_t bytes = tab.size() * sizeof(MixedEntry);
+    if (host->mixed_tab.ensure(bytes)) return last_error_code();
+    // pageable source: the runtime stages it before returning, so the vector may go out of scope
+    SIB_CHECK(cudaMemcpyAsync(host->mixed_tab.p, tab.data(), bytes, cudaMemcpyHostToDevice, s));
+    *bytes_out = bytes;
+    return 0;
+}
+
+// the index that lends its stream, device and table allocation; SI_MIXED_UNSUPPORTED when an index cannot answer from rank cells
+static int mixed_host(siIndex* const* ixs, int n_contigs, siIndex** host_out, const char* who) {
+    siIndex* host = nullptr;
+    for (int k = 0; k < n_contigs; ++k) {
+        siIndex* ix = ixs[k];
+        if (!ix || !ix->built || ix->n == 0) continue;
+        if (count_algo_of(ix) != SI_COUNT_CELLS) return SI_MIXED_UNSUPPORTED;
+        if (!host) host = ix;
+        if (ix->device != host->device) {
+            set_error_msg(cudaErrorInvalidValue, who);
+            return cudaErrorInvalidValue;
+        }
+    }
+    *host_out = host;
+    return 0;
+}
+
+int siCountMixedDevice(siIndex* const* ixs, int n_contigs, const int32_t* d_contig, const int32_t* d_qs, const int32_t* d_qe,
+                       size_t n, uint32_t* d_counts, unsigned long long* d_totals, void* stream) {
+    if (!ixs || n_contigs < 1 || n_contigs > (1 << 20) || n > 0xFFFFFFFFull) {
+        set_error_msg(cudaErrorInvalidValue, "siCountMixedDevice: bad arguments");
+        return cudaErrorInvalidValue;
+    }
+    siIndex* host = nullptr;   // lends its stream, its device and the table's allocation
+    int rc = mixed_host(ixs, n_contigs, &host, "siCountMixedDevice: the indexes live on different devices");
+    if (rc) return rc;
+    if (d_totals) SIB_CHECK(cudaMemsetAsync(d_totals, 0, (size_t)n_contigs * 8, static_cast<cudaStream_t>(stream)));
+    if (n == 0) return 0;
+    if (!host) {   // no contig has an index: every count is 0
+        SIB_CHECK(cudaMemsetAsync(d_counts, 0, n * 4, static_cast<cudaStream_t>(stream)));
+        return 0;
+    }
+    DeviceGuard g(host->device);
+    cudaStream_t s = pick_stream(host, stream);
+    size_t bytes = 0;
+    rc = mixed_table(host, ixs, n_contigs, nullptr, s, &bytes);
+    if (rc) return rc;
+    return mixed_launch(host, ixs, n_contigs, bytes, d_contig, d_qs, d_qe, n, d_counts, d_totals, QM_PLAIN, s);
+}
+
+// Mode B (one index per contig, contigs partitioned over the GPUs) WITHOUT a dispatch: every GPU's slice of the mixed batch
+// stays where it is, in memory its peers have mapped (NVLink peer access / CUDA IPC). This GPU walks all n_src slices -- its
+// own first, the others read in place over NVLink -- and answers exactly the queries whose contig it holds an index for,
+// storing each count into the slice's own counts array (a peer store for a remote slice). foreign[k] != 0 marks a contig
+// that another GPU answers; a query of a contig nobody indexes, or with an id outside [0, n_contigs), gets its 0 from
+// the GPU the slice lives on (home = that slice's position in the arrays). Per query that crosses: 4 B of contig id read
+// by every GPU, 8 B of coordinates read and 4 B of count written by the owner -- no all-to-all, no routing sort, no scatter.
+// The caller brackets the call with a barrier between the GPUs on both sides (siPeerBarrierDevice): the slices must be
+// complete before peers read them, and every GPU's stores must have landed before a slice's counts are used.
+int siCountMixedPeerDevice(siIndex* const* ixs, int n_contigs, const unsigned char* foreign, int n_src, int home,
+                           const int32_t* const* d_contig, const int32_t* const* d_qs, const int32_t* const* d_qe, const size_t* n,
+                           uint32_t* const* d_counts, unsigned long long* d_totals, void* stream) {
+    if (!ixs || n_contigs < 1 || n_contigs > (1 << 20) || n_src < 1 || n_src > 64 || home < 0 || home >= n_src || !d_contig || !d_qs ||
+        !d_qe || !n || !d_counts) {
+        set_error_msg(cudaErrorInvalidValue, "siCountMixedPeerDevice: bad arguments");
+        return cudaErrorInvalidValue;
+    }
+    for (int k = 0; k < n_src; ++k)
+        if (n[k] > 0xFFFFFFFFull) return cudaErrorInvalidValue;
+    siIndex* host = nullptr;
+    int rc = mixed_host(ixs, n_contigs, &host, "siCountMixedPeerDevice: the indexes live on different devices");
+    if (rc) return rc;
+    if (d_totals) SIB_CHECK(cudaMemsetAsync(d_totals, 0, (size_t)n_contigs * 8, static_cast<cudaStream_t>(stream)));
+    if (!host) {
+        // nothing indexed here: only the zeros of the home slice are this GPU's to write -- an id outside the table or a contig
+        // nobody indexes; a foreign contig's count comes from its owner. One pass of the kernel over the home slice does that
+        // with an empty table, but it needs an index to lend its stream: fall back to a memset when no contig is foreign.
+        bool any_foreign = false;
+        for (int k = 0; foreign && k < n_contigs; ++k) any_foreign = any_foreign || foreign[k];
+        if (!any_foreign && n[home]) SIB_CHECK(cudaMemsetAsync(d_counts[home], 0, n[home] * 4, static_cast<cudaStream_t>(stream)));
+        if (any_foreign) return SI_MIXED_UNSUPPORTED;   // a GPU that owns no contig: the caller keeps it out of the partition
+        return 0;
+    }
+    DeviceGuard g(host->device);
+    cudaStream_t s = pick_stream(host, stream);
+    size_t bytes = 0;
+    rc = mixed_table(host, ixs, n_contigs, foreign, s, &bytes);
+    if (rc) return rc;
+    for (int k = 0; k < n_src; ++k) {
+        const int src = (home + k) % n_src;      // own slice first; the remote ones start at different peers on every GPU
+        if (n[src] == 0) continue;
+        rc = mixed_launch(host, ixs, n_contigs, bytes, d_contig[src], d_qs[src], d_qe[src], n[src], d_counts[src], d_totals,
+                          src == home ? QM_PEER_HOME : QM_PEER_AWAY, s);
+        if (rc) return rc;
+    }
     return 0;
 }
 

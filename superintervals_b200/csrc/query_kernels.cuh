@@ -831,6 +831,10 @@ struct MixedEntry {
     int32_t mal_s[8], mal_e[8];
 };
 constexpr int QM_SMEM_ENTRIES = 256;    // tables up to this many contigs are staged in shared memory
+constexpr uint32_t QM_PLAIN = 0u;       // every query of the batch is answered here (0 when its contig has no index)
+constexpr uint32_t QM_PEER_HOME = 1u;   // this GPU's own slice of a contig-partitioned batch: foreign contigs are skipped
+constexpr uint32_t QM_PEER_AWAY = 2u;   // another GPU's slice (peer memory): only the contigs indexed here are answered
+constexpr uint32_t QM_FOREIGN = 0xFFFFFFFFu;   // MixedEntry.n_mal of a contig (n == 0) that another GPU answers
 constexpr int QM_THREADS = 256;
 
 // the reference's element walk (hpp:551-579) by one lane: only for inverted queries, which well-formed callers never send
@@ -852,7 +856,7 @@ template <typename CountT>
 __global__ void __launch_bounds__(QM_THREADS, SIB_QM_MINBLOCKS)
 qk_count_mixed_kernel(const MixedEntry* __restrict__ table, uint32_t n_contigs, const int32_t* __restrict__ contig,
                       const int32_t* __restrict__ qs_in, const int32_t* __restrict__ qe_in, uint32_t nq, CountT* __restrict__ counts,
-                      unsigned long long* __restrict__ totals, uint32_t rounds) {
+                      unsigned long long* __restrict__ totals, uint32_t rounds, uint32_t peer_mode) {
     extern __shared__ __align__(16) unsigned char qm_smem[];
     const MixedEntry* tab = table;
     unsigned long long* s_tot = nullptr;
@@ -877,6 +881,13 @@ qk_count_mixed_kernel(const MixedEntry* __restrict__ table, uint32_t n_contigs, 
         const uint32_t cid = (uint32_t)ld_stream(contig + t);
         const int32_t qs = ld_stream(qs_in + t), qe = ld_stream(qe_in + t);
         uint32_t c = 0;
+        // contig-partitioned batches read in place (siCountMixedPeerDevice): a query whose contig another GPU owns is that
+        // GPU's to answer (it stores the count here itself); a query nobody answers gets its 0 from the slice's home GPU only
+        if (peer_mode != QM_PLAIN) {
+            const bool mine = cid < n_contigs && tab[cid].n != 0u;
+            const bool foreign = cid < n_contigs && tab[cid].n == 0u && tab[cid].n_mal == QM_FOREIGN;
+            if (!mine && (foreign || peer_mode == QM_PEER_AWAY)) continue;
+        }
         if (cid < n_contigs && tab[cid].n != 0u) {
             const MixedEntry& e = tab[cid];
             uint32_t cell_s, off_s, cell_e, off_e, ns, ne;
@@ -928,7 +939,10 @@ qk_any_kernel(IndexView ix, const int32_t* __restrict__ qs_in, const int32_t* __
     if (t >= nq) return;
     uint8_t r = 0;
     if (ix.n) {
-        const uint32_t i = count_le(ix.starts, ix.n, qe_in[t]) - 1u;
+        // ub(qe) = #{starts <= qe} - 1: one rank-cell sector where the cells cover every stored interval, else the halving search
+        const int32_t qe = qe_in[t];
+        const uint32_t i = (ix.cells_s.fmt != 0u && ix.n_mal == 0u ? cells_rank_lt(ix.cells_s, ix.starts, (int64_t)qe + 1)
+                                                                    : count_le(ix.starts, ix.n, qe)) - 1u;
         r = (i != NONE32 && qs_in[t] <= ld_nc(ix.ends + i)) ? 1 : 0;
     }
     out[t] = r;

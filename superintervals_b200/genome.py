@@ -250,6 +250,37 @@ class GenomeIndex:
         out = torch.empty(n, dtype=torch.int32, device=dev)
         return R.scatter(routed, perm, out) if n else out
 
+    def count_mixed_peer(self, batch):
+        """Mode B without a dispatch: `batch` is a sharding.PeerBatch whose slices the ranks have filled (set_length done).
+        Every rank walks all slices in place -- the remote ones over NVLink -- answers the queries of the contigs it holds
+        an index for and stores each count into the slice it belongs to (siCountMixedPeerDevice); two flag barriers through
+        peer memory bracket the walk. Returns this rank's counts (a view of batch.counts, the caller's order), or None when
+        the kernel cannot run here (an index without rank cells, or a rank that owns no indexed contig): route instead.
+        Collective. self.hits receives the totals of the owned contigs over the WHOLE batch; last_exchange the NVLink bytes."""
+        import ctypes as C
+        from . import _lib
+        L = _lib.lib()
+        nc, W = len(self.names), self.world
+        arr = (C.c_void_p * nc)(*[(self._ix[c]._ix if c in self._ix else None) for c in range(nc)])
+        foreign = (C.c_ubyte * nc)(*[1 if (not self.owns(c) and self._n_intervals[c] > 0) else 0 for c in range(nc)])
+        cap = batch.cap
+
+        def ptrs(k):
+            return (C.c_void_p * W)(*[C.c_void_p(batch.base(r) + 4 * k * cap) for r in range(W)])
+        lens = (C.c_size_t * W)(*batch.lengths)
+        totals = torch.zeros(nc, dtype=torch.int64, device=batch.counts.device)
+        batch.barrier()                       # every slice is complete before a peer reads it
+        rc = L.siCountMixedPeerDevice(arr, nc, foreign, W, self.rank, ptrs(0), ptrs(1), ptrs(2), lens, ptrs(3), totals.data_ptr(),
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        batch.barrier()                       # every rank's stores have landed before the counts are read
+        if rc == -2:                          # SI_MIXED_UNSUPPORTED
+            return None
+        _lib.check("siCountMixedPeerDevice")
+        self.hits[:] = totals.cpu().numpy()
+        away = sum(n for r, n in enumerate(batch.lengths) if r != self.rank)
+        self.last_exchange = {"contig_id_bytes_read_remote": 4 * away, "note": "plus 8 B read and 4 B written per remote query of an owned contig"}
+        return batch.counts[:batch.lengths[self.rank]]
+
     def _sum_hits(self, counts, off, slots):
         self.hits[:] = 0
         for k, slot in enumerate(slots):

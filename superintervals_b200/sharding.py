@@ -22,7 +22,7 @@ import torch.distributed as dist
 
 from .workloads import lpt_assign, shard_range
 
-__all__ = ["shard_range", "lpt_assign", "csr_shard_bases", "gather_counts", "assign_contigs", "PeerGathered"]
+__all__ = ["shard_range", "lpt_assign", "csr_shard_bases", "gather_counts", "assign_contigs", "PeerGathered", "PeerBatch"]
 
 
 def csr_shard_bases(local_total_hits: int, device=None, group=None):
@@ -168,6 +168,124 @@ class PeerGathered:
             self._L.siIpcClose(p)
         self._peers = {}
         self._all = self.arrays = self._timed_out = None
+        if self._own:
+            self._L.siIpcFree(self._own)
+            self._own = None
+
+
+class PeerBatch:
+    """A mixed query batch that stays where it was produced: every rank owns one slice (contig id, start, end per query, and
+    the counts that come back) in a device block every other rank has mapped (CUDA IPC over NVLink peer access; siIpcAlloc /
+    siIpcOpen). GenomeIndex.count_mixed_peer() lets each rank walk ALL slices in place and answer the queries of the contigs
+    it indexes, storing the counts straight into the slice they belong to -- mode B of SURVEY 8e without the all-to-all
+    dispatch and combine. Layout of a block (int32 words): [contig cap][qs cap][qe cap][counts cap][flags: world][timed_out].
+    Collective: every rank of the group constructs it with the same `cap` (queries per slice at most); close() before the
+    process group goes away."""
+
+    def __init__(self, cap, world, rank, group=None):
+        import ctypes as C
+        from . import _lib
+        if world - 1 > 15:
+            raise ValueError("at most 16 ranks")
+        self._L, self._lib, self._C = _lib.lib(), _lib, C
+        self.cap = (int(cap) + 63) & ~63
+        self.world, self.rank, self.group = int(world), int(rank), group
+        caps = torch.tensor([float(self.cap), -float(self.cap)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(caps, op=dist.ReduceOp.MAX, group=group)
+        if int(caps[0].item()) != -int(caps[1].item()):   # the peers' blocks are addressed with this rank's cap
+            raise ValueError("PeerBatch: every rank must pass the same capacity")
+        self._flag_off = 4 * self.cap * 4
+        total = (self._flag_off + 4 * (world + 1) + 255) & ~255
+
+        def agreed(ok, what):
+            t = torch.tensor([1.0 if ok else 0.0], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            if t.item() < 1.0:
+                _lib.lib().si_b200_clear_error()
+                raise RuntimeError(f"PeerBatch: {what} failed on at least one rank")
+
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        rc = self._L.siIpcAlloc(total, C.byref(ptr), handle)
+        self._own = ptr.value if rc == 0 else None
+        self._peers = {}
+        try:
+            agreed(rc == 0, "siIpcAlloc (cudaMalloc + cudaIpcGetMemHandle)")
+        except RuntimeError:
+            if self._own:
+                self._L.siIpcFree(self._own)
+            raise
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+        allh = torch.empty(world * 64, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        allh = allh.cpu().numpy()
+        opened = True
+        for r in range(world):
+            if r == rank:
+                continue
+            p = C.c_void_p()
+            hb = (C.c_ubyte * 64)(*allh[r * 64:(r + 1) * 64].tolist())
+            if self._L.siIpcOpen(hb, C.byref(p)) != 0:
+                opened = False
+                break
+            self._peers[r] = p.value
+        try:
+            agreed(opened, "siIpcOpen (cudaIpcOpenMemHandle: peer access between the GPUs)")
+        except RuntimeError:
+            for p in self._peers.values():
+                self._L.siIpcClose(p)
+            self._L.siIpcFree(self._own)
+            raise
+
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (total // 4,), "typestr": "<i4", "data": (self._own, False), "version": 3, "strides": None}
+        self._raw = raw
+        self._all = torch.as_tensor(raw, device="cuda")
+        self._all.zero_()
+        c = self.cap
+        self.contig, self.qs, self.qe, self.counts = (self._all[k * c:(k + 1) * c] for k in range(4))
+        self._timed_out = self._all[4 * c + world: 4 * c + world + 1]
+        order = sorted(self._peers)
+        self._signal = (C.c_void_p * max(1, len(order)))(*[C.c_void_p(self._peers[r] + self._flag_off + 4 * rank) for r in order])
+        self._wait = (C.c_void_p * max(1, len(order)))(*[C.c_void_p(self._own + self._flag_off + 4 * r) for r in order])
+        self._order = order
+        self.step = 0
+        self.lengths = [0] * world
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+
+    def base(self, r):
+        """device address of rank r's block in THIS process's address space"""
+        return self._own if r == self.rank else self._peers[r]
+
+    def set_length(self, n):
+        """this rank's slice holds n queries (contig[:n], qs[:n], qe[:n]); collective: every rank learns every length"""
+        if n > self.cap:
+            raise ValueError("slice longer than the batch's capacity")
+        t = torch.tensor([int(n)], dtype=torch.int64, device="cuda")
+        out = torch.empty(self.world, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(out, t, group=self.group)
+        self.lengths = [int(x) for x in out.cpu().tolist()]
+        return self.lengths
+
+    def barrier(self):
+        """Stream-ordered barrier between the ranks (siPeerBarrierDevice): flags through peer memory, no collective call."""
+        self.step += 1
+        self._L.siPeerBarrierDevice(self._signal, self._wait, len(self._order), self.step, self._timed_out.data_ptr(),
+                                    self._C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        self._lib.check("siPeerBarrierDevice")
+
+    def timed_out(self):
+        return bool(int(self._timed_out.item()))
+
+    def close(self):
+        torch.cuda.synchronize()
+        for p in self._peers.values():
+            self._L.siIpcClose(p)
+        self._peers = {}
+        self._all = self.contig = self.qs = self.qe = self.counts = self._timed_out = None
         if self._own:
             self._L.siIpcFree(self._own)
             self._own = None

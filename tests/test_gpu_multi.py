@@ -98,6 +98,82 @@ def test_fused_count_and_all_gather_over_peer_memory_two_processes():
         out = mgr.dict()
         procs = [ctx.Process(target=_fused_worker, args=(r, 2, port, out)) for r in range(2)]
         for p in procs: p.start()
-        for p in procs: p.join(240)
+        for p in procs: p.join(180)
+        for p in procs:
+            if p.is_alive(): p.kill()       # a rank that died leaves its peer in a collective: do not wait for it
+        assert all(p.exitcode == 0 for p in procs)
+        assert dict(out) == {0: True, 1: True}
+
+
+def _peer_mixed_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    from oracle.pyoracle import Oracle
+    from superintervals_b200 import workloads as W
+    from superintervals_b200.genome import GenomeIndex
+    from superintervals_b200.sharding import PeerBatch
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    axes = [3_000_000, 1_500_000, 800_000, 2_000_000, 500_000]
+    ns = [60_000, 40_000, 0, 50_000, 20_000]                      # contig 2 has no intervals: nobody indexes it
+    g = GenomeIndex([f"c{i}" for i in range(5)], ns, rank=rank, world=world, pair_cells=2 if rank == 0 else 0)
+    orcs = {}
+    for c, (n, axis) in enumerate(zip(ns, axes)):
+        if n == 0:
+            continue
+        s, e = W.config2_intervals(n, 30 + c, axis=axis)
+        orcs[c] = Oracle(s, e)
+        if g.owns(c):
+            g.build_contig(c, torch.from_numpy(s).cuda(), torch.from_numpy(e).cuda())
+    ok = len(g.owned) > 0
+    per = 150_000 + 1000 * rank                                    # slices of different lengths
+    batch = PeerBatch(150_000 + 1000 * (world - 1), world, rank)   # one capacity for every rank: the longest slice
+    for step in range(3):
+        rng = np.random.default_rng([step, rank])
+        cid = rng.integers(0, 6, per).astype(np.int32)             # id 5 lies outside the table
+        qs, qe = W.config2_queries(per, 40 + step, axis=3_000_000, shard=rank)
+        inv = rng.random(per) < 0.001                              # a few inverted queries (quirk Q6)
+        qs, qe = np.where(inv, qe, qs).astype(np.int32), np.where(inv, qs, qe).astype(np.int32)
+        batch.contig[:per].copy_(torch.from_numpy(cid)); batch.qs[:per].copy_(torch.from_numpy(qs)); batch.qe[:per].copy_(torch.from_numpy(qe))
+        batch.counts.fill_(-1)
+        batch.set_length(per)
+        got = g.count_mixed_peer(batch)
+        ok &= got is not None
+        if got is None:
+            break
+        want = np.zeros(per, np.int64)
+        for c, orc in orcs.items():
+            m = cid == c
+            want[m] = orc.count_batch(qs[m], qe[m]).astype(np.int64)
+        ok &= bool(np.array_equal(got.cpu().numpy().astype(np.uint32).astype(np.int64), want))
+        # the owned contigs' totals cover the WHOLE batch: compare their sum over the ranks with the batch's hits
+        tot = torch.tensor([int(g.hits.sum()), int(want.sum())], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tot)
+        ok &= int(tot[0]) == int(tot[1])
+    ok &= not batch.timed_out()
+    batch.close()
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_contig_partitioned_mixed_batch_read_in_place_over_peer_memory_two_processes():
+    """Mode B without a dispatch (siCountMixedPeerDevice): contigs partitioned over two GPUs, each rank's slice of the
+    mixed batch stays in its own (IPC-shared) memory, every rank answers the queries of its contigs in place and stores
+    the counts into the slice they belong to. Equal to one oracle per contig, empty / unknown contigs count 0. Needs two GPUs."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0)); port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        out = mgr.dict()
+        procs = [ctx.Process(target=_peer_mixed_worker, args=(r, 2, port, out)) for r in range(2)]
+        for p in procs: p.start()
+        for p in procs: p.join(180)
+        for p in procs:
+            if p.is_alive(): p.kill()
         assert all(p.exitcode == 0 for p in procs)
         assert dict(out) == {0: True, 1: True}
