@@ -1426,7 +1426,8 @@ static int mixed_launch(siIndex* host, siIndex* const* ixs, int n_contigs, size_
     const size_t bytes = table_bytes_on_device;
     const size_t smem = n_contigs <= QM_SMEM_ENTRIES ? ((bytes + 15) & ~(size_t)15) + (size_t)n_contigs * 8 : 0;
     auto kern = qk_count_mixed_kernel<uint32_t>;
-    if (smem > ((size_t)48 << 10)) SIB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the kernel also holds 8.2 KB of static shared memory (the compaction list of the peer modes): opt in beyond 48 KB in total
+    if (smem + ((size_t)9 << 10) > ((size_t)48 << 10)) SIB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SIB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, QM_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
@@ -1437,6 +1438,7 @@ static int mixed_launch(siIndex* host, siIndex* const* ixs, int n_contigs, size_
         if (ixs[k] && ixs[k]->built && ixs[k]->n) table_bytes += ixs[k]->pair_ok ? ((size_t)ixs[k]->cm_pair.cells + 1) * 32 : ixs[k]->cells_total_bytes;
     uint32_t rounds = table_bytes > (host->l2_bytes / 4) * 3 ? 8u : 0u;
     if (const char* e = getenv("SIB_QM_ROUNDS")) rounds = (uint32_t)atoi(e);
+    if (peer_mode != QM_PLAIN && rounds > QM_MAX_ROUNDS) rounds = QM_MAX_ROUNDS;   // the kernel's compaction list holds 8 tiles
     const int grid = rounds ? (int)((tiles + rounds - 1) / rounds) : (int)std::min<uint64_t>(tiles, (uint64_t)host->sm_count * per_sm);
     const MixedEntry* d_tab = reinterpret_cast<const MixedEntry*>(host->mixed_tab.p);
     SIB_LAUNCH_T(host, TAG_COUNT_CELLS, kern, grid, QM_THREADS, smem, s, d_tab, (uint32_t)n_contigs, d_contig, d_qs, d_qe,

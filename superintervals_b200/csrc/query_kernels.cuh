@@ -847,11 +847,46 @@ __device__ __noinline__ uint32_t walk_scalar(const int32_t* __restrict__ ends, c
     return c;
 }
 
-// Persistent CTAs (grid = what the device holds): the table is staged once per CTA, tiles are taken grid-stride, and the
-// per-contig hit totals (for the CSR bases of mode B) are summed in shared memory and flushed once per CTA.
+// count of one query on the index of its contig (e.n != 0): the two rank gathers of qk_count_cells_kernel in that contig's tables
+__device__ __forceinline__ uint32_t mixed_answer(const MixedEntry& e, int32_t qs, int32_t qe) {
+    uint32_t cell_s, off_s, cell_e, off_e, ns, ne;
+    if (e.pc.fmt != 0u) {
+        const PairCells pc = e.pc;
+        pair_cell_of(pc, qe, cell_s, off_s);
+        pair_cell_of(pc, qs, cell_e, off_e);
+        const CellRec rs = ld_cell(pc.rec + 2 * (size_t)cell_s);
+        CellRec re = rs;
+        if (cell_e != cell_s) re = ld_cell(pc.rec + 2 * (size_t)cell_e);
+        ns = pair_rank<0>(pc, e.rstarts, rs, cell_s, off_s, qe);
+        ne = pair_rank<1>(pc, e.eall, re, cell_e, off_e, qs);
+    } else {
+        const RankCells cs = e.cs, ce = e.ce;
+        cell_of(cs, (int64_t)qe + 1, cell_s, off_s);
+        cell_of(ce, (int64_t)qs, cell_e, off_e);
+        const CellRec rs = ld_cell(cs.rec + 2 * (size_t)cell_s);
+        const CellRec re = ld_cell(ce.rec + 2 * (size_t)cell_e);
+        ns = cell_rank(cs, e.rstarts, rs, cell_s, off_s, (int64_t)qe + 1);
+        ne = cell_rank(ce, e.eall, re, cell_e, off_e, (int64_t)qs);
+    }
+    uint32_t c = ns - ne;
+    uint32_t mal_before = 0;
+    for (uint32_t k = 0; k < e.n_mal; ++k) {
+        const bool cand = e.mal_s[k] <= qe;
+        mal_before += cand ? 1u : 0u;
+        c += (cand && e.mal_e[k] >= qs) ? 1u : 0u;
+    }
+    if (qs > qe) c = walk_scalar(e.ends, e.branch, ns + mal_before - 1u, qs);
+    return c;
+}
+
+// The descriptor table is staged in shared memory once per CTA; per-contig hit totals (the CSR bases of mode B) are summed in
+// shared memory and flushed once per CTA. rounds == 0: persistent CTAs (grid = what the device holds), tiles taken grid-stride;
+// rounds > 0: a CTA owns `rounds` consecutive tiles and leaves -- gathers that miss L2 are served faster to short-lived CTAs
+// (tools/hbm_gather.cu: 47 G against 37 G sectors/s).
 #ifndef SIB_QM_MINBLOCKS
 #define SIB_QM_MINBLOCKS 5
 #endif
+constexpr uint32_t QM_MAX_ROUNDS = 8;    // tiles per short-lived CTA at most (the compaction list of the peer modes holds them)
 template <typename CountT>
 __global__ void __launch_bounds__(QM_THREADS, SIB_QM_MINBLOCKS)
 qk_count_mixed_kernel(const MixedEntry* __restrict__ table, uint32_t n_contigs, const int32_t* __restrict__ contig,
@@ -872,57 +907,70 @@ qk_count_mixed_kernel(const MixedEntry* __restrict__ table, uint32_t n_contigs, 
         }
         __syncthreads();
     }
-    // rounds == 0: persistent CTAs, tiles taken grid-stride. rounds > 0: a CTA owns `rounds` consecutive tiles and leaves --
-    // gathers that miss L2 are served faster to short-lived CTAs (tools/hbm_gather.cu: 47 G against 37 G sectors/s)
-    const uint64_t stride = rounds ? (uint64_t)QM_THREADS : (uint64_t)gridDim.x * QM_THREADS;
-    const uint64_t first = rounds ? (uint64_t)blockIdx.x * rounds * QM_THREADS + threadIdx.x : (uint64_t)blockIdx.x * QM_THREADS + threadIdx.x;
-    const uint64_t last = rounds ? min((uint64_t)nq, ((uint64_t)blockIdx.x + 1) * rounds * QM_THREADS) : (uint64_t)nq;
-    for (uint64_t t = first; t < last; t += stride) {
-        const uint32_t cid = (uint32_t)ld_stream(contig + t);
-        const int32_t qs = ld_stream(qs_in + t), qe = ld_stream(qe_in + t);
-        uint32_t c = 0;
-        // contig-partitioned batches read in place (siCountMixedPeerDevice): a query whose contig another GPU owns is that
-        // GPU's to answer (it stores the count here itself); a query nobody answers gets its 0 from the slice's home GPU only
-        if (peer_mode != QM_PLAIN) {
-            const bool mine = cid < n_contigs && tab[cid].n != 0u;
-            const bool foreign = cid < n_contigs && tab[cid].n == 0u && tab[cid].n_mal == QM_FOREIGN;
-            if (!mine && (foreign || peer_mode == QM_PEER_AWAY)) continue;
+    auto add_total = [&](uint32_t cid, uint32_t c) {
+        if (totals && c) {
+            if (s_tot) atomicAdd(s_tot + cid, (unsigned long long)c);
+            else atomicAdd(totals + cid, (unsigned long long)c);
         }
-        if (cid < n_contigs && tab[cid].n != 0u) {
-            const MixedEntry& e = tab[cid];
-            uint32_t cell_s, off_s, cell_e, off_e, ns, ne;
-            if (e.pc.fmt != 0u) {
-                const PairCells pc = e.pc;
-                pair_cell_of(pc, qe, cell_s, off_s);
-                pair_cell_of(pc, qs, cell_e, off_e);
-                const CellRec rs = ld_cell(pc.rec + 2 * (size_t)cell_s);
-                CellRec re = rs;
-                if (cell_e != cell_s) re = ld_cell(pc.rec + 2 * (size_t)cell_e);
-                ns = pair_rank<0>(pc, e.rstarts, rs, cell_s, off_s, qe);
-                ne = pair_rank<1>(pc, e.eall, re, cell_e, off_e, qs);
-            } else {
-                const RankCells cs = e.cs, ce = e.ce;
-                cell_of(cs, (int64_t)qe + 1, cell_s, off_s);
-                cell_of(ce, (int64_t)qs, cell_e, off_e);
-                const CellRec rs = ld_cell(cs.rec + 2 * (size_t)cell_s);
-                const CellRec re = ld_cell(ce.rec + 2 * (size_t)cell_e);
-                ns = cell_rank(cs, e.rstarts, rs, cell_s, off_s, (int64_t)qe + 1);
-                ne = cell_rank(ce, e.eall, re, cell_e, off_e, (int64_t)qs);
+    };
+    if (peer_mode != QM_PLAIN && rounds != 0u) {
+        // Contig-partitioned batch read in place (siCountMixedPeerDevice): of this slice only the queries whose contig is indexed
+        // HERE are answered -- one in N on N GPUs. A thread per query would leave most lanes idle during the gathers, so the CTA
+        // first reads the contig ids of its tiles (4 B per query: all that crosses NVLink for the queries of other GPUs' contigs),
+        // packs the positions of its own queries into a shared list, and then answers the list with every lane busy. A query of
+        // a contig nobody indexes (or with an id outside the table) gets its 0 from the slice's home GPU.
+        __shared__ uint32_t s_list[QM_MAX_ROUNDS * QM_THREADS];     // (contig id << 11) | position inside the CTA's tiles
+        __shared__ uint32_t s_n;
+        if (threadIdx.x == 0) s_n = 0u;
+        __syncthreads();
+        const uint64_t base = (uint64_t)blockIdx.x * rounds * QM_THREADS;
+        const uint32_t lane = threadIdx.x & 31u;
+        for (uint32_t r = 0; r < rounds; ++r) {
+            const uint32_t i = r * QM_THREADS + threadIdx.x;
+            const uint64_t t = base + i;
+            const bool live = t < nq;
+            const uint32_t cid = live ? (uint32_t)ld_stream(contig + t) : 0xFFFFFFFFu;
+            const bool known = cid < n_contigs;
+            const bool mine = live && known && tab[known ? cid : 0u].n != 0u;
+            const bool foreign = live && known && tab[known ? cid : 0u].n == 0u && tab[known ? cid : 0u].n_mal == QM_FOREIGN;
+            const uint32_t m = __ballot_sync(FULL_MASK, mine);
+            if (m) {
+                uint32_t at = 0;
+                if (lane == (uint32_t)(__ffs(m) - 1)) at = atomicAdd(&s_n, (uint32_t)__popc(m));
+                at = __shfl_sync(FULL_MASK, at, __ffs(m) - 1);
+                if (mine) s_list[at + __popc(m & lanemask_lt())] = (cid << 11) | i;
             }
-            c = ns - ne;
-            uint32_t mal_before = 0;
-            for (uint32_t k = 0; k < e.n_mal; ++k) {
-                const bool cand = e.mal_s[k] <= qe;
-                mal_before += cand ? 1u : 0u;
-                c += (cand && e.mal_e[k] >= qs) ? 1u : 0u;
-            }
-            if (qs > qe) c = walk_scalar(e.ends, e.branch, ns + mal_before - 1u, qs);
-            if (totals && c) {
-                if (s_tot) atomicAdd(s_tot + cid, (unsigned long long)c);
-                else atomicAdd(totals + cid, (unsigned long long)c);
-            }
+            if (live && !mine && !foreign && peer_mode == QM_PEER_HOME) st_stream(counts + t, (CountT)0);
         }
-        st_stream(counts + t, (CountT)c);
+        __syncthreads();
+        const uint32_t n_mine = s_n;
+        for (uint32_t k = threadIdx.x; k < n_mine; k += QM_THREADS) {
+            const uint32_t rec = s_list[k], cid = rec >> 11;
+            const uint64_t t = base + (rec & 2047u);
+            const int32_t qs = ld_stream(qs_in + t), qe = ld_stream(qe_in + t);
+            const uint32_t c = mixed_answer(tab[cid], qs, qe);
+            add_total(cid, c);
+            st_stream(counts + t, (CountT)c);
+        }
+    } else {
+        const uint64_t stride = rounds ? (uint64_t)QM_THREADS : (uint64_t)gridDim.x * QM_THREADS;
+        const uint64_t first = rounds ? (uint64_t)blockIdx.x * rounds * QM_THREADS + threadIdx.x : (uint64_t)blockIdx.x * QM_THREADS + threadIdx.x;
+        const uint64_t last = rounds ? min((uint64_t)nq, ((uint64_t)blockIdx.x + 1) * rounds * QM_THREADS) : (uint64_t)nq;
+        for (uint64_t t = first; t < last; t += stride) {
+            const uint32_t cid = (uint32_t)ld_stream(contig + t);
+            const bool mine = cid < n_contigs && tab[cid < n_contigs ? cid : 0u].n != 0u;
+            if (peer_mode != QM_PLAIN) {   // tables that fit L2 (persistent CTAs): a thread per query, the others' queries skipped
+                const bool foreign = cid < n_contigs && tab[cid].n == 0u && tab[cid].n_mal == QM_FOREIGN;
+                if (!mine && (foreign || peer_mode == QM_PEER_AWAY)) continue;
+            }
+            uint32_t c = 0;
+            if (mine) {
+                const int32_t qs = ld_stream(qs_in + t), qe = ld_stream(qe_in + t);
+                c = mixed_answer(tab[cid], qs, qe);
+                add_total(cid, c);
+            }
+            st_stream(counts + t, (CountT)c);
+        }
     }
     if (s_tot) {
         __syncthreads();

@@ -137,6 +137,11 @@ def _peer_mixed_worker(rank, world, port, out):
         batch.contig[:per].copy_(torch.from_numpy(cid)); batch.qs[:per].copy_(torch.from_numpy(qs)); batch.qe[:per].copy_(torch.from_numpy(qe))
         batch.counts.fill_(-1)
         batch.set_length(per)
+        # step 0: persistent CTAs, a thread per query (tables in L2); steps 1, 2: short-lived CTAs of 8 / 3 tiles that pack their
+        # own queries into a shared list first (what a whole genome's tables get)
+        os.environ.pop("SIB_QM_ROUNDS", None)
+        if step:
+            os.environ["SIB_QM_ROUNDS"] = "8" if step == 1 else "3"
         got = g.count_mixed_peer(batch)
         ok &= got is not None
         if got is None:
