@@ -1002,6 +1002,8 @@ void siIndexDestroy(siIndex* ix) {
     ix->timer.release();
     if (ix->e_stage[0]) { cudaEventDestroy(ix->e_stage[0]); cudaEventDestroy(ix->e_stage[1]); }
     if (ix->pipe_ready_out) cudaStreamDestroy(ix->s_out2);
+    for (int k = 0; k < ix->peer_side_ready; ++k) { cudaStreamDestroy(ix->peer_side[k]); cudaEventDestroy(ix->peer_join[k]); }
+    if (ix->peer_fork) cudaEventDestroy(ix->peer_fork);
     if (ix->pinned) cudaFreeHost(ix->pinned);
     if (ix->mailbox) cudaFreeHost(ix->mailbox);
     if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
@@ -1549,12 +1551,35 @@ int siCountMixedPeerDevice(siIndex* const* ixs, int n_contigs, const unsigned ch
     size_t bytes = 0;
     rc = mixed_table(host, ixs, n_contigs, foreign, s, &bytes);
     if (rc) return rc;
+    // the home slice on the caller's stream, every remote slice on a side stream beside it: a remote walk waits on NVLink round
+    // trips, the home walk on HBM gathers, so they overlap instead of queueing (SIB_PEER_SERIAL=1: one after the other)
+    const bool serial = getenv("SIB_PEER_SERIAL") && atoi(getenv("SIB_PEER_SERIAL")) != 0;
+    const int want_side = serial ? 0 : std::min(n_src - 1, (int)siIndex::SI_PEER_SIDE);
+    while (host->peer_side_ready < want_side) {
+        const int k = host->peer_side_ready;
+        SIB_CHECK(cudaStreamCreateWithFlags(&host->peer_side[k], cudaStreamNonBlocking));
+        SIB_CHECK(cudaEventCreateWithFlags(&host->peer_join[k], cudaEventDisableTiming));
+        ++host->peer_side_ready;
+    }
+    if (want_side && !host->peer_fork) SIB_CHECK(cudaEventCreateWithFlags(&host->peer_fork, cudaEventDisableTiming));
+    if (want_side) SIB_CHECK(cudaEventRecord(host->peer_fork, s));      // after the table upload and the zeroing of the totals
+    int used = 0;
     for (int k = 0; k < n_src; ++k) {
         const int src = (home + k) % n_src;      // own slice first; the remote ones start at different peers on every GPU
         if (n[src] == 0) continue;
+        cudaStream_t sk = s;
+        if (k > 0 && want_side) {
+            sk = host->peer_side[(k - 1) % want_side];
+            if ((k - 1) < want_side) SIB_CHECK(cudaStreamWaitEvent(sk, host->peer_fork, 0));
+            used = std::max(used, std::min(k, want_side));
+        }
         rc = mixed_launch(host, ixs, n_contigs, bytes, d_contig[src], d_qs[src], d_qe[src], n[src], d_counts[src], d_totals,
-                          src == home ? QM_PEER_HOME : QM_PEER_AWAY, s);
+                          src == home ? QM_PEER_HOME : QM_PEER_AWAY, sk);
         if (rc) return rc;
+    }
+    for (int k = 0; k < used; ++k) {
+        SIB_CHECK(cudaEventRecord(host->peer_join[k], host->peer_side[k]));
+        SIB_CHECK(cudaStreamWaitEvent(s, host->peer_join[k], 0));
     }
     return 0;
 }

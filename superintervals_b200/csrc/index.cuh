@@ -173,6 +173,13 @@ struct siIndex {
     cudaStream_t srv_stream = nullptr;          // its stream
     sib::SingleReq* srv_req = nullptr;          // its request block (to stop it before a rebuild / destroy)
     uint32_t* srv_done = nullptr;               // the mailbox word its answers' sequence numbers go to                    // sequence number of the last single-query call (published by its kernel when done)
+    // siCountMixedPeerDevice: the walks over the other GPUs' slices run beside the walk over the home slice (NVLink-bound
+    // scans overlap HBM-bound gathers): up to SI_PEER_SIDE side streams, forked from and joined to the caller's stream
+    static constexpr int SI_PEER_SIDE = 15;
+    cudaStream_t peer_side[SI_PEER_SIDE] = {};
+    cudaEvent_t peer_join[SI_PEER_SIDE] = {};
+    cudaEvent_t peer_fork = nullptr;
+    int peer_side_ready = 0;
     cudaStream_t s_out2 = nullptr;              // second copy-out stream (offsets travel while the fill runs)
     bool pipe_ready_out = false;
 

@@ -925,11 +925,20 @@ qk_count_mixed_kernel(const MixedEntry* __restrict__ table, uint32_t n_contigs, 
         __syncthreads();
         const uint64_t base = (uint64_t)blockIdx.x * rounds * QM_THREADS;
         const uint32_t lane = threadIdx.x & 31u;
-        for (uint32_t r = 0; r < rounds; ++r) {
+        // all contig ids of the thread first: up to eight independent loads in flight (a remote slice answers after an NVLink round trip)
+        uint32_t cidv[QM_MAX_ROUNDS];
+#pragma unroll
+        for (uint32_t r = 0; r < QM_MAX_ROUNDS; ++r) {
+            const uint64_t t = base + r * QM_THREADS + threadIdx.x;
+            cidv[r] = (r < rounds && t < nq) ? (uint32_t)ld_stream(contig + t) : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (uint32_t r = 0; r < QM_MAX_ROUNDS; ++r) {
+            if (r >= rounds) break;
             const uint32_t i = r * QM_THREADS + threadIdx.x;
             const uint64_t t = base + i;
             const bool live = t < nq;
-            const uint32_t cid = live ? (uint32_t)ld_stream(contig + t) : 0xFFFFFFFFu;
+            const uint32_t cid = cidv[r];
             const bool known = cid < n_contigs;
             const bool mine = live && known && tab[known ? cid : 0u].n != 0u;
             const bool foreign = live && known && tab[known ? cid : 0u].n == 0u && tab[known ? cid : 0u].n_mal == QM_FOREIGN;
@@ -944,13 +953,21 @@ qk_count_mixed_kernel(const MixedEntry* __restrict__ table, uint32_t n_contigs, 
         }
         __syncthreads();
         const uint32_t n_mine = s_n;
-        for (uint32_t k = threadIdx.x; k < n_mine; k += QM_THREADS) {
-            const uint32_t rec = s_list[k], cid = rec >> 11;
-            const uint64_t t = base + (rec & 2047u);
-            const int32_t qs = ld_stream(qs_in + t), qe = ld_stream(qe_in + t);
-            const uint32_t c = mixed_answer(tab[cid], qs, qe);
-            add_total(cid, c);
-            st_stream(counts + t, (CountT)c);
+        // two list entries per thread and step: the coordinates of both (remote for another GPU's slice) are requested before either is used
+        for (uint32_t k = threadIdx.x; k < n_mine; k += 2 * QM_THREADS) {
+            const bool two = k + QM_THREADS < n_mine;
+            const uint32_t rec0 = s_list[k], rec1 = two ? s_list[k + QM_THREADS] : rec0;
+            const uint64_t t0 = base + (rec0 & 2047u), t1 = base + (rec1 & 2047u);
+            const int32_t qs0 = ld_stream(qs_in + t0), qe0 = ld_stream(qe_in + t0);
+            const int32_t qs1 = ld_stream(qs_in + t1), qe1 = ld_stream(qe_in + t1);
+            const uint32_t c0 = mixed_answer(tab[rec0 >> 11], qs0, qe0);
+            add_total(rec0 >> 11, c0);
+            st_stream(counts + t0, (CountT)c0);
+            if (two) {
+                const uint32_t c1 = mixed_answer(tab[rec1 >> 11], qs1, qe1);
+                add_total(rec1 >> 11, c1);
+                st_stream(counts + t1, (CountT)c1);
+            }
         }
     } else {
         const uint64_t stride = rounds ? (uint64_t)QM_THREADS : (uint64_t)gridDim.x * QM_THREADS;
