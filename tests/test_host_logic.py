@@ -132,3 +132,26 @@ def test_vector_overload_order_reproduces_the_reference_python_lists():
         assert np.array_equal(got, want)
         seen_reordered += int((flat != want).sum())
     assert seen_reordered > 100          # the fixture does exercise the reordering
+
+
+def test_genome_index_decides_pair_cells_from_the_genome_not_the_contig():
+    """One index per contig: whether the rank cells a mixed batch gathers from fit L2 is a property of all owned contigs
+    together (genome.py _pair_mode -> SI_OPT_PAIR_CELLS). No GPU needed: the decision is host arithmetic."""
+    from superintervals_b200.genome import GenomeIndex
+    names = [f"chr{i}" for i in range(24)]
+    small = GenomeIndex(names, [100_000] * 24, rank=0, world=1)
+    assert small._pair_mode() == 1                         # 2.4 M intervals: ~14 MB of rank cells, each index decides for itself
+    whole = GenomeIndex(names, [4_000_000] * 24, rank=0, world=1)
+    assert whole._pair_mode() == 2                         # 96 M intervals: ~580 MB of rank cells, every contig gets pair cells
+    split = GenomeIndex(names, [4_000_000] * 24, rank=3, world=8)
+    assert len(split.owned) == 3 and split._pair_mode() == 1   # 12 M intervals on this rank: they fit again
+    assert GenomeIndex(names, [4_000_000] * 24, rank=0, world=1, pair_cells=0)._pair_mode() == 0
+
+
+def test_c_abi_declares_the_peer_entry_points():
+    """siCountMixedPeerDevice / SI_OPT_PAIR_CELLS are declared in the public header and exported by the library."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "superintervals_b200.h")).read()
+    assert "siCountMixedPeerDevice" in hdr and "SI_OPT_PAIR_CELLS = 15" in hdr
+    from superintervals_b200 import _lib
+    assert hasattr(_lib.lib(), "siCountMixedPeerDevice") and _lib.OPT_PAIR_CELLS == 15
