@@ -899,9 +899,11 @@ def bench_c4(a, torch, dist, world, rank):
             pb.contig[:m].copy_(cid); pb.qs[:m].copy_(qs); pb.qe[:m].copy_(qe)
             pb.set_length(m)
             got = gi.count_mixed_peer(pb)
-            flag = torch.tensor([1.0 if (got is not None and torch.equal(got, out)) else 0.0], dtype=torch.float64, device="cuda")
+            # [answers equal the dispatched ones, the kernel could run] on EVERY rank: the ranks take the timed branch together or not at all
+            flag = torch.tensor([1.0 if (got is not None and torch.equal(got, out)) else 0.0, 1.0 if got is not None else 0.0],
+                                dtype=torch.float64, device="cuda")
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if got is not None:
+            if flag[1] > 0:
                 torch.cuda.synchronize(); dist.barrier()
                 ms_p = timed_device(torch, lambda: gi.count_mixed_peer(pb), 3)
                 tp = torch.tensor([ms_p], dtype=torch.float64, device="cuda")
