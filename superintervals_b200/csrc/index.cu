@@ -339,7 +339,8 @@ int cells_fill(siIndex* ix, const int32_t* A, uint32_t n, const siIndex::CellsMe
 // Pair cells over both arrays (PairCells in query_kernels.cuh). Format by density: four-bit offsets in cells of 16
 // coordinates when a cell would hold 3-11 values per side on average, else one-byte offsets in the widest cell
 // (<= 256 coordinates) with a mean of at most 4 per side. Returns false when neither fits (denser than ~0.7 values per
-// coordinate) or the table would cost more than 16 B per interval... the caller then keeps the separate tables only.
+// coordinate) or the table would cost more than 24 B per interval (a sparse index: most cells would be empty): the caller
+// then keeps the separate tables only.
 bool pair_plan(uint32_t n, int64_t first, int64_t last, siIndex::CellsMeta* m) {
     if (first < (int64_t)INT32_MIN || last - first >= (int64_t)0xFFFFFFF0ll) return false;
     const uint64_t range = (uint64_t)(last - first) + 1;
